@@ -1,0 +1,258 @@
+// hode_api.cu — the extern "C" surface of libhode.so (see include/hode.h).
+//
+// Argument validation, workspace carving and kernel selection.  No torch types, no
+// allocation (except in the *_host convenience entry, which uses the stream-ordered
+// allocator for its staging buffers), no CPU fallback: a configuration the CUDA kernels do
+// not cover returns HODE_E_UNSUPPORTED.
+#include <stdio.h>
+#include <string.h>
+
+#include "hode_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "ok";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof g_err, fmt, detail);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(e));
+  return (int)e;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+  size_t off_n, off_t, off_h, off_y, total;
+  int max_saved;
+};
+
+int max_saved_steps(const hode_cfg* c) {
+  if (c->solver == HODE_SOLVER_RK4) {
+    const int nsub = c->n_substeps > 0 ? c->n_substeps : 1;
+    return (c->n_obs - 1) * nsub;
+  }
+  return c->max_saved_steps > 0 ? c->max_saved_steps : 256;
+}
+
+Workspace fwd_workspace(const hode_cfg* c) {
+  Workspace w{};
+  const size_t units = (size_t)(c->n_samples > 0 ? c->n_samples : 1) * (size_t)c->n_traj;
+  w.max_saved = max_saved_steps(c);
+  if (!c->save_steps) return w;
+  size_t off = 0;
+  w.off_n = off; off = align_up(off + units * sizeof(int32_t), 256);
+  w.off_t = off; off = align_up(off + units * w.max_saved * sizeof(double), 256);
+  w.off_h = off; off = align_up(off + units * w.max_saved * sizeof(float), 256);
+  w.off_y = off; off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
+  w.total = off;
+  return w;
+}
+
+int validate(const hode_cfg* c) {
+  if (!c) return fail(HODE_E_NULL, "cfg is NULL");
+  if (c->struct_bytes != (int32_t)sizeof(hode_cfg))
+    return fail(HODE_E_SIZE, "cfg.struct_bytes != sizeof(hode_cfg): header/library mismatch");
+  if (c->n_traj < 0 || c->n_obs < 1) return fail(HODE_E_SIZE, "n_traj < 0 or n_obs < 1");
+  if (c->n_samples < 1) return fail(HODE_E_SIZE, "n_samples < 1");
+  for (int ch = 0; ch < 3; ++ch)
+    if (c->in_mode[ch] < HODE_IN_ABSENT || c->in_mode[ch] > HODE_IN_SERIES)
+      return fail(HODE_E_SHAPE, "in_mode out of range");
+  if (c->solver != HODE_SOLVER_RK4 && c->solver != HODE_SOLVER_DOPRI5)
+    return fail(HODE_E_UNSUPPORTED, "unknown solver");
+  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_TF32)
+    return fail(HODE_E_UNSUPPORTED, "unknown mlp arithmetic");
+  if (c->mlp != HODE_MLP_NONE) {
+    if (c->nn_hidden < 1 || c->nn_hidden > HODE_MAX_HIDDEN || c->nn_layers < 1 ||
+        c->nn_layers > HODE_MAX_LAYERS)
+      return fail(HODE_E_UNSUPPORTED, "nn_hidden must be in [1,128] and nn_layers in [1,8]");
+    if ((c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32) &&
+        (c->nn_hidden != 64 || c->nn_layers < 2))
+      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64, nn_layers >= 2");
+  }
+  if (c->solver == HODE_SOLVER_DOPRI5 && (!(c->rtol > 0) || !(c->atol >= 0)))
+    return fail(HODE_E_SIZE, "rtol must be > 0 and atol >= 0");
+  if (c->kink_mode != HODE_KINK_SCIPY && c->kink_mode != HODE_KINK_CLIP)
+    return fail(HODE_E_UNSUPPORTED, "unknown kink_mode");
+  return 0;
+}
+
+hode::RolloutArgs make_args(const hode_cfg* c, const float* y0, const float* t_obs,
+                            const float* u_meal, const float* u_tvns, const float* u_gd,
+                            const float* theta, const float* W) {
+  hode::RolloutArgs A{};
+  A.y0 = y0; A.t_obs = t_obs;
+  A.u[0] = u_meal; A.u[1] = u_tvns; A.u[2] = u_gd;
+  A.theta = theta; A.W = W;
+  A.B = c->n_traj; A.T = c->n_obs; A.S = c->n_samples;
+  A.t_per_traj = c->t_per_traj;
+  for (int ch = 0; ch < 3; ++ch) A.in_mode[ch] = c->in_mode[ch];
+  A.H = c->nn_hidden; A.L = c->nn_layers;
+  A.P = c->mlp != HODE_MLP_NONE ? (int)hode_mlp_param_count(c->nn_hidden, c->nn_layers) : 0;
+  A.solver = c->solver; A.n_substeps = c->n_substeps; A.max_steps = c->max_steps;
+  A.kink_mode = c->kink_mode;
+  A.rhs_part = c->rhs_part;
+  A.rtol = (float)c->rtol; A.atol = (float)c->atol;
+  return A;
+}
+
+int check_inputs(const hode_cfg* c, const float* u_meal, const float* u_tvns, const float* u_gd,
+                 const float* W) {
+  const float* u[3] = {u_meal, u_tvns, u_gd};
+  for (int ch = 0; ch < 3; ++ch)
+    if (c->in_mode[ch] != HODE_IN_ABSENT && !u[ch])
+      return fail(HODE_E_NULL, "input channel declared present but its pointer is NULL");
+  if (c->mlp != HODE_MLP_NONE && !W) return fail(HODE_E_NULL, "W is NULL but cfg.mlp != NONE");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hode_version(void) { return HODE_ABI_VERSION; }
+
+const char* hode_last_error_string(void) { return g_err; }
+
+int64_t hode_mlp_param_count(int32_t H, int32_t L) {
+  if (H < 1 || L < 1) return 0;
+  int64_t n = (int64_t)HODE_NN_IN * H + H;
+  for (int l = 1; l < L; ++l) n += (int64_t)H * H + H;
+  n += (int64_t)H * HODE_N_STATE + HODE_N_STATE;
+  return n;
+}
+
+int hode_workspace_bytes(const hode_cfg* cfg, size_t* fwd_bytes, size_t* bwd_bytes) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  const Workspace w = fwd_workspace(cfg);
+  if (fwd_bytes) *fwd_bytes = w.total;
+  if (bwd_bytes) *bwd_bytes = 0;
+  return 0;
+}
+
+int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
+                     const float* u_meal, const float* u_tvns, const float* u_gd,
+                     const float* theta, const float* W, float* traj, int32_t* status,
+                     int32_t* counters, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!y0 || !t_obs || !theta || !traj) return fail(HODE_E_NULL, "y0/t_obs/theta/traj is NULL");
+  rc = check_inputs(cfg, u_meal, u_tvns, u_gd, W);
+  if (rc) return rc;
+  if (cfg->n_traj == 0) return 0;
+  hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
+  A.traj = traj; A.status = status; A.counters = counters;
+  if (cfg->save_steps) {
+    const Workspace w = fwd_workspace(cfg);
+    if (!workspace || workspace_bytes < w.total)
+      return fail(HODE_E_WORKSPACE, "workspace missing or smaller than hode_workspace_bytes()");
+    char* base = (char*)workspace;
+    A.save_n = (int32_t*)(base + w.off_n);
+    A.save_t = (double*)(base + w.off_t);
+    A.save_h = (float*)(base + w.off_h);
+    A.save_y = (float*)(base + w.off_y);
+    A.max_saved = w.max_saved;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (cfg->mlp == HODE_MLP_NONE || cfg->mlp == HODE_MLP_FP32) {
+    e = hode::launch_rollout_simt(A, cfg->mlp, st);
+  } else {
+    return fail(HODE_E_UNSUPPORTED, "tensor-core MLP path is not built into this library");
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_fwd launch");
+  return 0;
+}
+
+int hode_rollout_bwd(const hode_cfg*, const float*, const float*, const float*, const float*,
+                     const float*, const float*, const float*, const float*, float*, float*,
+                     float*, void*, size_t, void*) {
+  return fail(HODE_E_UNSUPPORTED, "hode_rollout_bwd: not built yet");
+}
+
+int hode_vi_predictive(const hode_cfg*, const float*, const float*, const float*, const float*,
+                       const float*, const float*, const float*, float*, float*, int32_t*,
+                       int32_t*, void*) {
+  return fail(HODE_E_UNSUPPORTED, "hode_vi_predictive: not built yet");
+}
+
+int hode_rhs(const hode_cfg* cfg, const float* t, const float* state, const float* u_meal,
+             const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+             float* out, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!t || !state || !theta || !out) return fail(HODE_E_NULL, "t/state/theta/out is NULL");
+  rc = check_inputs(cfg, u_meal, u_tvns, u_gd, W);
+  if (rc) return rc;
+  if (cfg->n_traj == 0) return 0;
+  hode::RolloutArgs A = make_args(cfg, state, t, u_meal, u_tvns, u_gd, theta, W);
+  const int mode = cfg->mlp == HODE_MLP_NONE ? HODE_MLP_NONE : HODE_MLP_FP32;
+  cudaError_t e = hode::launch_rhs(A, mode, t, state, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "hode_rhs launch");
+  return 0;
+}
+
+int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t_obs_h,
+                          const float* u_meal_h, const float* u_tvns_h, const float* u_gd_h,
+                          const float* theta_h, const float* W_h, float* traj_h,
+                          int32_t* status_h, int32_t* counters_h, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!y0_h || !t_obs_h || !theta_h || !traj_h)
+    return fail(HODE_E_NULL, "y0/t_obs/theta/traj host pointer is NULL");
+  rc = check_inputs(cfg, u_meal_h, u_tvns_h, u_gd_h, W_h);
+  if (rc) return rc;
+  if (cfg->save_steps) return fail(HODE_E_UNSUPPORTED, "save_steps is not available on the host entry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = cfg->n_traj, T = cfg->n_obs, S = cfg->n_samples;
+  const size_t P = cfg->mlp != HODE_MLP_NONE ? hode_mlp_param_count(cfg->nn_hidden, cfg->nn_layers) : 0;
+  const float* uh[3] = {u_meal_h, u_tvns_h, u_gd_h};
+  size_t ub[3];
+  for (int ch = 0; ch < 3; ++ch)
+    ub[ch] = cfg->in_mode[ch] == HODE_IN_SERIES ? B * T * 4 : cfg->in_mode[ch] == HODE_IN_CONST ? B * 4 : 0;
+  const size_t sz_y0 = B * 6 * 4, sz_t = (cfg->t_per_traj ? B * T : T) * 4, sz_th = S * 17 * 4,
+               sz_W = S * P * 4, sz_traj = S * B * T * 6 * 4, sz_st = S * B * 4, sz_cn = 2 * S * B * 4;
+  size_t off = 0, o_y0, o_t, o_u[3], o_th, o_W, o_traj, o_st, o_cn;
+  o_y0 = off; off = align_up(off + sz_y0, 256);
+  o_t = off; off = align_up(off + sz_t, 256);
+  for (int ch = 0; ch < 3; ++ch) { o_u[ch] = off; off = align_up(off + ub[ch], 256); }
+  o_th = off; off = align_up(off + sz_th, 256);
+  o_W = off; off = align_up(off + sz_W, 256);
+  o_traj = off; off = align_up(off + sz_traj, 256);
+  o_st = off; off = align_up(off + sz_st, 256);
+  o_cn = off; off = align_up(off + sz_cn, 256);
+  char* d = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&d, off ? off : 256, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+#define H2D(dst, src, n) \
+  if ((n) && (e = cudaMemcpyAsync(d + (dst), (src), (n), cudaMemcpyHostToDevice, st)) != cudaSuccess) goto done
+  H2D(o_y0, y0_h, sz_y0);
+  H2D(o_t, t_obs_h, sz_t);
+  for (int ch = 0; ch < 3; ++ch) H2D(o_u[ch], uh[ch], ub[ch]);
+  H2D(o_th, theta_h, sz_th);
+  H2D(o_W, W_h, sz_W);
+#undef H2D
+  rc = hode_rollout_fwd(cfg, (float*)(d + o_y0), (float*)(d + o_t),
+                        ub[0] ? (float*)(d + o_u[0]) : nullptr, ub[1] ? (float*)(d + o_u[1]) : nullptr,
+                        ub[2] ? (float*)(d + o_u[2]) : nullptr, (float*)(d + o_th),
+                        sz_W ? (float*)(d + o_W) : nullptr, (float*)(d + o_traj),
+                        (int32_t*)(d + o_st), (int32_t*)(d + o_cn), nullptr, 0, stream);
+  if (rc) { cudaFreeAsync(d, st); cudaStreamSynchronize(st); return rc; }
+  if (sz_traj && (e = cudaMemcpyAsync(traj_h, d + o_traj, sz_traj, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
+  if (status_h && sz_st && (e = cudaMemcpyAsync(status_h, d + o_st, sz_st, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
+  if (counters_h && sz_cn && (e = cudaMemcpyAsync(counters_h, d + o_cn, sz_cn, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
+done:
+  cudaFreeAsync(d, st);
+  {
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_fwd_host");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// hode_common.cuh — device-side building blocks shared by every libhode kernel (sm_100a).
+//
+// Replaces, per trajectory and per RK stage, what the reference does in Python:
+//   mechanistic RHS ........ reference models/ode_core.py:122-161
+//   input interpolation .... reference models/hybrid_ode_nn.py:217-231
+//   Dormand-Prince tableau . scipy/integrate/_ivp/rk.py:538-565 (third-party; published tableau)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hode.h"
+
+namespace hode {
+
+constexpr int NS = HODE_N_STATE;
+
+// ---- launch-constant description of one rollout (passed by value to kernels) -----------
+struct RolloutArgs {
+  const float* y0;      // [B,6]
+  const float* t_obs;   // [T] or [B,T]
+  const float* u[3];    // per in_mode
+  const float* theta;   // [S,17]
+  const float* W;       // [S,P] or nullptr
+  float* traj;          // [S,B,T,6] (or nullptr in fused-statistics mode)
+  int32_t* status;      // [S,B] or nullptr
+  int32_t* counters;    // [2,S,B] or nullptr
+  // saved accepted steps (discrete adjoint): step-major [max_saved][S*B] so that the
+  // lanes of a warp write/read consecutive addresses
+  double* save_t;       // start time of accepted step n
+  float* save_h;        // step size
+  float* save_y;        // [max_saved][6][S*B] state at step start
+  int32_t* save_n;      // [S*B] number of saved steps
+  int32_t max_saved;
+  int32_t B, T, S;
+  int32_t t_per_traj;
+  int32_t in_mode[3];
+  int32_t H, L;         // MLP hidden width, hidden layer count
+  int32_t P;            // floats per packed MLP parameter set
+  int32_t solver, n_substeps, max_steps, kink_mode, rhs_part;
+  float rtol, atol;
+};
+
+// ---- Dormand-Prince 5(4) coefficients (float) --------------------------------------------
+namespace dp {
+constexpr float c2 = 1.f / 5, c3 = 3.f / 10, c4 = 4.f / 5, c5 = 8.f / 9;
+constexpr float a21 = 1.f / 5;
+constexpr float a31 = 3.f / 40, a32 = 9.f / 40;
+constexpr float a41 = 44.f / 45, a42 = -56.f / 15, a43 = 32.f / 9;
+constexpr float a51 = 19372.f / 6561, a52 = -25360.f / 2187, a53 = 64448.f / 6561,
+                a54 = -212.f / 729;
+constexpr float a61 = 9017.f / 3168, a62 = -355.f / 33, a63 = 46732.f / 5247, a64 = 49.f / 176,
+                a65 = -5103.f / 18656;
+constexpr float b1 = 35.f / 384, b3 = 500.f / 1113, b4 = 125.f / 192, b5 = -2187.f / 6784,
+                b6 = 11.f / 84;
+constexpr float e1 = -71.f / 57600, e3 = 71.f / 16695, e4 = -71.f / 1920, e5 = 17253.f / 339200,
+                e6 = -22.f / 525, e7 = 1.f / 40;
+// dense-output matrix P (7x4), rk.py:554-565; row index 1 is zero.  pJK = P[J-1][K-1].
+constexpr float p11 = 1.f;
+constexpr float p12 = (float)(-8048581381.0 / 2820520608), p13 = (float)(8663915743.0 / 2820520608),
+                p14 = (float)(-12715105075.0 / 11282082432);
+constexpr float p32 = (float)(131558114200.0 / 32700410799), p33 = (float)(-68118460800.0 / 10900136933),
+                p34 = (float)(87487479700.0 / 32700410799);
+constexpr float p42 = (float)(-1754552775.0 / 470086768), p43 = (float)(14199869525.0 / 1410260304),
+                p44 = (float)(-10690763975.0 / 1880347072);
+constexpr float p52 = (float)(127303824393.0 / 49829197408), p53 = (float)(-318862633887.0 / 49829197408),
+                p54 = (float)(701980252875.0 / 199316789632);
+constexpr float p62 = (float)(-282668133.0 / 205662961), p63 = (float)(2019193451.0 / 616988883),
+                p64 = (float)(-1453857185.0 / 822651844);
+constexpr float p72 = (float)(40617522.0 / 29380423), p73 = (float)(-110615467.0 / 29380423),
+                p74 = (float)(69997945.0 / 29380423);
+
+// Q = K^T P for one state component (rk.py:178-180); k1..k7 are that component's stages.
+__device__ __forceinline__ void dense_q(float k1, float k3, float k4, float k5, float k6, float k7,
+                                        float* q) {
+  q[0] = p11 * k1;
+  q[1] = fmaf(p72, k7, fmaf(p62, k6, fmaf(p52, k5, fmaf(p42, k4, fmaf(p32, k3, p12 * k1)))));
+  q[2] = fmaf(p73, k7, fmaf(p63, k6, fmaf(p53, k5, fmaf(p43, k4, fmaf(p33, k3, p13 * k1)))));
+  q[3] = fmaf(p74, k7, fmaf(p64, k6, fmaf(p54, k5, fmaf(p44, k4, fmaf(p34, k3, p14 * k1)))));
+}
+}  // namespace dp
+
+// ---- per-thread view of one trajectory's time grid and inputs ------------------------------
+struct TrajInputs {
+  const float* t_obs;  // this trajectory's grid (global, or the shared copy)
+  const float* u[3];   // series: this trajectory's [T] row; const: pointer to its value
+  int mode[3];
+  int T;
+  int cur;             // monotone cursor: count of grid points known to be < the step start
+};
+
+// np.searchsorted(t_eval, t, side='left') restricted to a forward walk from the cursor.
+__device__ __forceinline__ int grid_index_from(const TrajInputs& in, float t32, int start) {
+  int i = start;
+  while (i < in.T && in.t_obs[i] < t32) ++i;
+  return i;
+}
+
+// Reference models/hybrid_ode_nn.py:217-231 for one channel, float32 arithmetic.
+__device__ __forceinline__ float input_channel(const TrajInputs& in, int ch, float t32, int idx) {
+  if (in.mode[ch] == HODE_IN_ABSENT) return 0.f;
+  if (in.mode[ch] == HODE_IN_CONST) return in.u[ch][0];
+  const float* v = in.u[ch];
+  if (idx == 0) return v[0];
+  if (idx >= in.T) return v[in.T - 1];
+  const float t1 = in.t_obs[idx - 1], t2 = in.t_obs[idx];
+  const float alpha = __fdiv_rn(t32 - t1, t2 - t1);
+  const float v1 = v[idx - 1];
+  return __fadd_rn(v1, __fmul_rn(alpha, v[idx] - v1));
+}
+
+__device__ __forceinline__ bool any_series(const TrajInputs& in) {
+  return in.mode[0] == HODE_IN_SERIES || in.mode[1] == HODE_IN_SERIES ||
+         in.mode[2] == HODE_IN_SERIES;
+}
+
+// Grid point i is a kink when some series input is not flat across (i-1, i, i+1).
+__device__ __forceinline__ bool is_kink(const TrajInputs& in, int i) {
+  if (i <= 0 || i >= in.T - 1) return false;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    if (in.mode[ch] != HODE_IN_SERIES) continue;
+    const float a = in.u[ch][i - 1], b = in.u[ch][i], c = in.u[ch][i + 1];
+    if (a != b || b != c) return true;
+  }
+  return false;
+}
+
+// ---- mechanistic parameters held in registers -------------------------------------------------
+struct Theta {
+  float a_GI, k_I, rho, G_b, I_b, E_max, EC_50, Glu_b, V_max, K_m, k_L, k_GE0, IGD_50, g, p_7,
+      p_8, p_9;
+  float igd_pow;  // IGD_50^g (theta-only; hoisted out of the stage loop)
+};
+
+__device__ __forceinline__ Theta load_theta(const float* __restrict__ th) {
+  Theta p;
+  p.a_GI = th[0]; p.k_I = th[1]; p.rho = th[2]; p.G_b = th[3]; p.I_b = th[4];
+  p.E_max = th[5]; p.EC_50 = th[6]; p.Glu_b = th[7]; p.V_max = th[8]; p.K_m = th[9];
+  p.k_L = th[10]; p.k_GE0 = th[11]; p.IGD_50 = th[12]; p.g = th[13];
+  p.p_7 = th[14]; p.p_8 = th[15]; p.p_9 = th[16];
+  p.igd_pow = powf(p.IGD_50, p.g);
+  return p;
+}
+
+// f_physio: reference models/ode_core.py:122-161, same operation order, float32, IEEE division.
+// (FMA contraction is disabled inside so the result matches an unfused CPU evaluation bit for
+// bit wherever powf agrees.)
+__device__ __forceinline__ void rhs_mech(const Theta& p, const float* y, float meal, float GD,
+                                         bool gd_present, float* d) {
+  const float G = y[0], I = y[1], Glu = y[2], GLP1 = y[3], FFA = y[5];
+  const float Pi = __fadd_rn(1.0f, __fmul_rn(p.rho, GLP1));
+  d[1] = __fsub_rn(__fmul_rn(__fmul_rn(Pi, p.a_GI), G - p.G_b), __fmul_rn(p.k_I, I - p.I_b));
+  const float glp1_effect = __fmul_rn(p.E_max, __fdiv_rn(GLP1, p.EC_50 + GLP1));
+  d[2] = __fmul_rn(-glp1_effect, Glu - p.Glu_b);
+  d[3] = __fsub_rn(__fmul_rn(p.V_max, __fdiv_rn(G, p.K_m + G)), __fmul_rn(p.k_L, GLP1));
+  const float gdg = gd_present ? powf(GD, p.g) : powf(0.0f, p.g);
+  const float GD_effect = __fdiv_rn(gdg, p.igd_pow + gdg);
+  const float k_GE = __fmul_rn(p.k_GE0, 1.0f - GD_effect);
+  d[5] = __fadd_rn(__fsub_rn(__fmul_rn(-p.p_7, FFA), __fmul_rn(__fmul_rn(p.p_8, I), FFA)),
+                   __fmul_rn(__fmul_rn(p.p_9, G), FFA));
+  const float insulin_effect = __fmul_rn(0.01f, I - p.I_b);
+  const float glucagon_effect = __fmul_rn(0.005f, Glu - p.Glu_b);
+  d[0] = __fsub_rn(__fadd_rn(__fsub_rn(meal, insulin_effect), glucagon_effect),
+                   __fmul_rn(k_GE, G));
+  d[4] = 0.0f;
+}
+
+// float offset of layer l's transposed weight block inside the shared-memory MLP image.
+// Image layout per layer: Wt[n_in][ldo] (ldo = n_out rounded up to 8) then bias[ldo].
+__host__ __device__ inline int mlp_ldo(int n_out) { return (n_out + 7) & ~7; }
+__host__ __device__ inline int mlp_image_floats(int H, int L) {
+  int n = HODE_NN_IN * mlp_ldo(H) + mlp_ldo(H);
+  for (int l = 1; l < L; ++l) n += H * mlp_ldo(H) + mlp_ldo(H);
+  n += H * mlp_ldo(NS) + mlp_ldo(NS);
+  return n;
+}
+
+}  // namespace hode

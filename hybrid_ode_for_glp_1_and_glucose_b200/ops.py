@@ -1,0 +1,188 @@
+"""Tensor-level entry points over the C ABI (include/hode.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every number is computed
+by libhode.so.  All compute functions require CUDA tensors and raise otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HodeError
+
+CHANNELS = ("meal", "tVNS", "GD")
+SOLVERS = {
+    # the reference maps 'dopri5' -> SciPy DOP853 (models/hybrid_ode_nn.py:174-181); here, as
+    # BASELINE.json's north_star specifies, 'dopri5' is Dormand-Prince 5(4) (= SciPy 'RK45').
+    "dopri5": _lib.SOLVER_DOPRI5, "rk45": _lib.SOLVER_DOPRI5, "rk4": _lib.SOLVER_RK4,
+}
+PRECISIONS = {"fp32": _lib.MLP_FP32, "tf32x3": _lib.MLP_TF32X3, "tf32": _lib.MLP_TF32}
+KINKS = {"scipy": _lib.KINK_SCIPY, "clip": _lib.KINK_CLIP}
+
+
+@dataclass
+class RolloutInfo:
+    status: torch.Tensor      # int32 [B] or [S,B]
+    n_accept: torch.Tensor    # int32, accepted steps
+    n_reject: torch.Tensor    # int32, rejected attempts
+
+    @property
+    def n_attempts(self) -> torch.Tensor:
+        return self.n_accept + self.n_reject
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise HodeError("libhode kernels run on CUDA devices only (no CPU fallback); got device "
+                        f"'{device}'")
+
+
+def prepare(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
+            theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int, layers: int,
+            device: torch.device):
+    """Normalise shapes/dtypes, fill a hode_cfg.  Pure host logic (testable without a GPU)."""
+    if y0.dim() != 2 or y0.shape[1] != _lib.N_STATE:
+        raise ValueError(f"initial_state must be [B,6], got {tuple(y0.shape)}")
+    B = y0.shape[0]
+    if t_obs.dim() == 2:
+        if t_obs.shape[0] != B:
+            # reference models/hybrid_ode_nn.py:192-196: a leading dim != B is squeezed away
+            t_obs = t_obs.squeeze()
+            if t_obs.dim() != 1:
+                t_obs = t_obs.flatten()
+    elif t_obs.dim() != 1:
+        raise ValueError(f"t_span must be [T] or [B,T], got {tuple(t_obs.shape)}")
+    T = t_obs.shape[-1]
+    cfg = _lib.new_cfg()
+    cfg.n_traj, cfg.n_obs = B, T
+    cfg.t_per_traj = 1 if t_obs.dim() == 2 else 0
+    bufs = {"y0": _f32c(y0, device), "t_obs": _f32c(t_obs, device)}
+    for ch, name in enumerate(CHANNELS):
+        v = None if not inputs else inputs.get(name)
+        if v is None:
+            cfg.in_mode[ch] = _lib.IN_ABSENT
+            bufs[name] = None
+            continue
+        if not torch.is_tensor(v):
+            v = torch.as_tensor(v, dtype=torch.float32)
+        if v.dim() == 2:
+            if tuple(v.shape) != (B, T):
+                raise ValueError(f"input '{name}' must be [B,T]=({B},{T}), got {tuple(v.shape)}")
+            cfg.in_mode[ch] = _lib.IN_SERIES
+        else:
+            # reference models/hybrid_ode_nn.py:230-231: anything not 2-D is per-trajectory
+            v = v.reshape(-1)
+            if v.numel() == 1:
+                v = v.expand(B)
+            if v.numel() != B:
+                raise ValueError(f"input '{name}' must have B={B} entries, got {v.numel()}")
+            cfg.in_mode[ch] = _lib.IN_CONST
+        bufs[name] = _f32c(v, device)
+    theta2 = theta if theta.dim() == 2 else theta.unsqueeze(0)
+    if theta2.shape[1] != _lib.N_THETA:
+        raise ValueError(f"theta must have 17 entries per set, got {tuple(theta.shape)}")
+    S = theta2.shape[0]
+    cfg.n_samples = S
+    bufs["theta"] = _f32c(theta2, device)
+    if W is None:
+        cfg.mlp = _lib.MLP_NONE
+        bufs["W"] = None
+    else:
+        P = _expected_param_count(hidden, layers)
+        W2 = W if W.dim() == 2 else W.unsqueeze(0)
+        if tuple(W2.shape) != (S, P):
+            raise ValueError(f"W must be [{S},{P}] for hidden={hidden}, layers={layers}; got "
+                             f"{tuple(W2.shape)}")
+        cfg.mlp = _lib.MLP_FP32
+        cfg.nn_hidden, cfg.nn_layers = hidden, layers
+        bufs["W"] = _f32c(W2, device)
+    return cfg, bufs
+
+
+def _expected_param_count(hidden: int, layers: int) -> int:
+    return 9 * hidden + hidden + (layers - 1) * (hidden * hidden + hidden) + hidden * 6 + 6
+
+
+def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
+            theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
+            solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
+            kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
+            device: Optional[torch.device] = None) -> Tuple[torch.Tensor, RolloutInfo]:
+    """Batched IVP solve on the GPU (hode_rollout_fwd).
+
+    Returns traj [B,T,6] (or [S,B,T,6] when theta is [S,17]) and a RolloutInfo.
+    """
+    device = torch.device(device) if device is not None else y0.device
+    _require_cuda(device)
+    if solver.lower() not in SOLVERS:
+        raise HodeError(f"solver '{solver}' is not implemented on the GPU path; available: "
+                        f"{sorted(SOLVERS)}")
+    squeeze_s = theta.dim() == 1
+    cfg, bufs = prepare(y0, t_obs, inputs, theta, W, hidden, layers, device)
+    cfg.solver = SOLVERS[solver.lower()]
+    cfg.rtol, cfg.atol = float(rtol), float(atol)
+    cfg.n_substeps = int(n_substeps)
+    cfg.max_steps = int(max_steps)
+    cfg.kink_mode = KINKS[kinks]
+    if cfg.mlp != _lib.MLP_NONE:
+        cfg.mlp = PRECISIONS[precision]
+    B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
+    with torch.cuda.device(device):
+        traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
+        status = torch.empty((S, B), dtype=torch.int32, device=device)
+        counters = torch.empty((2, S, B), dtype=torch.int32, device=device)
+        rc = _lib.lib().hode_rollout_fwd(
+            ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
+            _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
+            _ptr(traj), _ptr(status), _ptr(counters), None, 0, _stream(device))
+    _lib.check(rc, "hode_rollout_fwd")
+    if squeeze_s:
+        return traj[0], RolloutInfo(status[0], counters[0, 0], counters[1, 0])
+    return traj, RolloutInfo(status, counters[0], counters[1])
+
+
+def rhs(t: torch.Tensor, state: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
+        theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
+        device: Optional[torch.device] = None, part: int = 0) -> torch.Tensor:
+    """One batched evaluation of f_physio + g_NN on the GPU (hode_rhs). state [B,6] -> [B,6]."""
+    device = torch.device(device) if device is not None else state.device
+    _require_cuda(device)
+    B = state.shape[0]
+    t = torch.as_tensor(t, dtype=torch.float32)
+    t = t.reshape(-1)
+    if t.numel() == 1:
+        t = t.expand(B)
+    cfg, bufs = prepare(state, t, inputs, theta, W, hidden, layers, device)
+    if cfg.n_samples != 1:
+        raise ValueError("rhs() takes one parameter set")
+    cfg.n_obs, cfg.t_per_traj = 1, 1  # `t` is one evaluation time per row, not a grid
+    cfg.rhs_part = part
+    with torch.cuda.device(device):
+        out = torch.empty((B, 6), dtype=torch.float32, device=device)
+        rc = _lib.lib().hode_rhs(
+            ctypes.byref(cfg), _ptr(bufs["t_obs"]), _ptr(bufs["y0"]), _ptr(bufs["meal"]),
+            _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
+            _ptr(out), _stream(device))
+    _lib.check(rc, "hode_rhs")
+    return out
+
+
+def rhs_vjp(t, state, inputs, theta, W, grad_out, hidden=64, layers=4, device=None, part=0):
+    """Vector-Jacobian product of rhs(): returns (grad_state [B,6], grad_theta [17], grad_W [P])."""
+    raise _lib.HodeError("hode_rhs_vjp is not built yet")

@@ -1,0 +1,198 @@
+/*
+ * hode.h — C ABI of libhode.so, the B200-native batched hybrid ODE-NN integrator.
+ *
+ * This is the drop-in boundary for the trajectory-rollout and gradient path of
+ * OliverDOU776/Hybrid-ODE-for-GLP-1-and-Glucose.  The reference has no FFI of
+ * its own (it is pure Python); each entry point below names the reference
+ * interface it replaces (file:line into the reference tree).
+ *
+ * Conventions
+ *   - every function is extern "C", returns int: 0 = ok, <0 = argument error
+ *     (HODE_E_*), >0 = a cudaError_t raised by a launch.  Nothing throws.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - all launches are asynchronous on the caller's stream (a cudaStream_t
+ *     passed as void*; 0 = the legacy default stream).
+ *   - the library allocates nothing behind the caller's back: workspace sizes
+ *     come from hode_workspace_bytes().
+ *   - there is no CPU fallback anywhere in this library.
+ *
+ * State layout (reference models/ode_core.py:103-108): 6 floats per trajectory,
+ *   [G, I, Glu, GLP1, GE, FFA], row-major [B,6].
+ * theta layout (reference models/ode_core.py:44-71, buffer registration order):
+ *   [a_GI, k_I, rho, G_b, I_b, E_max, EC_50, Glu_b, V_max, K_m, k_L,
+ *    k_GE0, IGD_50, g, p_7, p_8, p_9]                      -> 17 floats / set.
+ * W layout (reference models/nn_residual.py:60-78, named_parameters() order):
+ *   for l in 0..L: weight_l [out_l, in_l] row-major, then bias_l [out_l];
+ *   in_0 = 9, out_L = 6, all other widths = nn_hidden.  (13 510 floats at 64x4.)
+ */
+#ifndef HODE_H_
+#define HODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HODE_ABI_VERSION 1
+#define HODE_N_STATE 6
+#define HODE_N_THETA 17
+#define HODE_NN_IN 9
+#define HODE_MAX_HIDDEN 128
+#define HODE_MAX_LAYERS 8
+
+/* solver keyword (reference models/hybrid_ode_nn.py:137,174-181) */
+enum {
+  HODE_SOLVER_RK4 = 0,    /* classical fixed-step RK4, n_substeps per observation interval */
+  HODE_SOLVER_DOPRI5 = 1  /* Dormand-Prince 5(4), SciPy RK45 controller + dense output     */
+};
+
+/* how one external input channel is supplied (reference models/hybrid_ode_nn.py:217-231) */
+enum {
+  HODE_IN_ABSENT = 0, /* channel is identically zero (models/ode_core.py:115-117)        */
+  HODE_IN_CONST = 1,  /* one value per trajectory, [B]   (values.dim()==1 branch, :230)  */
+  HODE_IN_SERIES = 2  /* one value per observation time, [B,T], linearly interpolated    */
+};
+#define HODE_CH_MEAL 0
+#define HODE_CH_TVNS 1
+#define HODE_CH_GD 2
+
+/* arithmetic used for the residual MLP inside each RK stage */
+enum {
+  HODE_MLP_NONE = 0,   /* no residual network (ablation no_nn, train/train_hybrid.py:423-427) */
+  HODE_MLP_FP32 = 1,   /* FP32 FMA on CUDA cores: parity mode                                */
+  HODE_MLP_TF32X3 = 2, /* tcgen05 tensor cores, 3xTF32 split (fp32-equivalent accuracy)      */
+  HODE_MLP_TF32 = 3    /* tcgen05 tensor cores, single TF32 pass (fast, ~1e-3 on residual)   */
+};
+
+/*
+ * Treatment of the kinks of the piece-wise-linear inputs by the adaptive solver.
+ * SCIPY reproduces the reference: steps ignore the observation grid and the controller
+ * finds (or steps over!) each kink by rejection (scipy ivp.py:701-728 never clips to t_eval).
+ * CLIP ends a step at every grid point where a series input changes slope, so every step
+ * integrates a smooth RHS and the result converges to the exact solution.
+ */
+enum { HODE_KINK_SCIPY = 0, HODE_KINK_CLIP = 1 };
+
+/* which terms hode_rhs returns */
+enum { HODE_RHS_FULL = 0, HODE_RHS_NN_ONLY = 1 };
+
+/* per-trajectory status codes written by the rollout */
+enum {
+  HODE_ST_OK = 0,
+  HODE_ST_STEP_TOO_SMALL = 1, /* SciPy: "Required step size is less than spacing between numbers." */
+  HODE_ST_MAX_STEPS = 2,      /* attempt budget (cfg.max_steps) exhausted                        */
+  HODE_ST_NONFINITE = 3       /* state became NaN/Inf                                            */
+};
+
+/* argument errors */
+enum {
+  HODE_E_NULL = -1,
+  HODE_E_SIZE = -2,
+  HODE_E_SHAPE = -3,
+  HODE_E_UNSUPPORTED = -4,
+  HODE_E_WORKSPACE = -5,
+  HODE_E_NO_DEVICE = -6
+};
+
+typedef struct hode_cfg {
+  int32_t struct_bytes;  /* = sizeof(hode_cfg); checked                                        */
+  int32_t n_traj;        /* B: trajectories (rows of y0)                                       */
+  int32_t n_obs;         /* T: observation times per trajectory (>= 1)                         */
+  int32_t t_per_traj;    /* 0: t_obs is [T] shared; 1: t_obs is [B,T]                          */
+  int32_t in_mode[3];    /* HODE_IN_* for meal, tVNS, GD                                       */
+  int32_t nn_hidden;     /* H (ignored when mlp == HODE_MLP_NONE)                              */
+  int32_t nn_layers;     /* L hidden layers (reference n_layers); Linear count = L+1           */
+  int32_t mlp;           /* HODE_MLP_*                                                         */
+  int32_t n_samples;     /* S >= 1 parameter sets (VI sweep); unit (s,b) uses theta[s], W[s]   */
+  int32_t solver;        /* HODE_SOLVER_*                                                      */
+  int32_t n_substeps;    /* RK4: steps per observation interval (>= 1)                         */
+  int32_t max_steps;     /* DOPRI5: attempted-step budget per trajectory (0 -> 100000)         */
+  double rtol;           /* DOPRI5 (reference default 1e-6, models/hybrid_ode_nn.py:138)       */
+  double atol;           /* DOPRI5 (reference default 1e-8); both at byte offset 56/64         */
+  int32_t save_steps;    /* 1: record accepted steps in the workspace for hode_rollout_bwd     */
+  int32_t kink_mode;     /* DOPRI5: HODE_KINK_* (how input-slope discontinuities are handled)  */
+  int32_t max_saved_steps; /* DOPRI5 + save_steps: accepted-step capacity per trajectory (0 -> 256) */
+  int32_t rhs_part;      /* hode_rhs only: HODE_RHS_FULL or HODE_RHS_NN_ONLY                    */
+} hode_cfg;
+
+/* ABI version of the loaded library. */
+int hode_version(void);
+
+/* Human-readable text for the last non-zero return on this host thread. */
+const char* hode_last_error_string(void);
+
+/* Number of floats in one packed MLP parameter set (13 510 for hidden=64, layers=4). */
+int64_t hode_mlp_param_count(int32_t nn_hidden, int32_t nn_layers);
+
+/* Bytes of device workspace hode_rollout_fwd (save_steps=1) / hode_rollout_bwd need. */
+int hode_workspace_bytes(const hode_cfg* cfg, size_t* fwd_bytes, size_t* bwd_bytes);
+
+/*
+ * Batched IVP solve: replaces the per-trajectory loop + scipy.integrate.solve_ivp
+ * call of HybridODENN.forward (reference models/hybrid_ode_nn.py:184-256) and, with
+ * n_samples > 1, the forward_with_params loop of the VI sweeps
+ * (reference inference/vi.py:294-304, models/bayes.py:199-206).
+ *
+ *   y0     [B,6]                 t_obs [T] or [B,T] (strictly increasing per row)
+ *   u[c]   NULL | [B] | [B,T]    per cfg.in_mode[c]
+ *   theta  [S,17]                W [S, hode_mlp_param_count] (NULL when mlp == NONE)
+ *   traj   [S,B,T,6]  out        (rows after a solver failure are zero, as the
+ *                                 reference zero-pads, models/hybrid_ode_nn.py:252-254)
+ *   status [S,B] out             counters [2,S,B] out (accepted, rejected attempts); may be NULL
+ */
+int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
+                     const float* u_meal, const float* u_tvns, const float* u_gd,
+                     const float* theta, const float* W, float* traj, int32_t* status,
+                     int32_t* counters, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Discrete adjoint of hode_rollout_fwd over the recorded accepted steps (step sizes
+ * frozen).  The reference has no through-solver gradient (models/hybrid_ode_nn.py:248);
+ * this is the gradient path BASELINE.json's north_star item (3) asks for.
+ *   grad_traj [S,B,T,6] in;  grad_y0 [S,B,6] out (may be NULL);
+ *   grad_theta [S,17] out;   grad_W [S,P] out.
+ */
+int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
+                     const float* u_meal, const float* u_tvns, const float* u_gd,
+                     const float* theta, const float* W, const float* grad_traj,
+                     float* grad_y0, float* grad_theta, float* grad_W, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/*
+ * Posterior-predictive sweep with the mean / unbiased std over the S parameter sets
+ * reduced on the fly (reference inference/vi.py:291-310, models/bayes.py:196-212):
+ * the [S,B,T,6] stack is never materialised.
+ *   mean [B,T,6] out, std [B,T,6] out, status [S,B] out (may be NULL).
+ */
+int hode_vi_predictive(const hode_cfg* cfg, const float* y0, const float* t_obs,
+                       const float* u_meal, const float* u_tvns, const float* u_gd,
+                       const float* theta, const float* W, float* mean, float* std_out,
+                       int32_t* status, int32_t* counters, void* stream);
+
+/*
+ * One batched evaluation of f_physio + g_NN: replaces HybridODENN.ode_residual
+ * (reference models/hybrid_ode_nn.py:108-134) for the physics-residual loss term
+ * (:327).  t [B], state [B,6], u[c] NULL|[B], out [B,6].
+ */
+int hode_rhs(const hode_cfg* cfg, const float* t, const float* state, const float* u_meal,
+             const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+             float* out, void* stream);
+
+/*
+ * Host-buffer convenience entry (the e2e path timed by bench.py): same contract as
+ * hode_rollout_fwd but every pointer is HOST memory (pinned or pageable); the call
+ * stages H2D copies, runs the rollout and copies traj/status/counters back, all on
+ * `stream`, and synchronises that stream before returning.
+ */
+int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_host, const float* t_obs_host,
+                          const float* u_meal_host, const float* u_tvns_host,
+                          const float* u_gd_host, const float* theta_host, const float* W_host,
+                          float* traj_host, int32_t* status_host, int32_t* counters_host,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HODE_H_ */

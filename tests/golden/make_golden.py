@@ -1,0 +1,201 @@
+"""Generate the golden fixtures in tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):  python tests/golden/make_golden.py
+The .npz files it writes are committed; tests never import the reference.
+
+Every case stores the exact inputs handed to the reference and the outputs it returned:
+  rhs_*      HybridODENN.ode_residual / ODECore.forward   (models/hybrid_ode_nn.py:108,
+             models/ode_core.py:81), inputs from tests/test_ode_jacobians.py:68-75,143-150,183-185
+  rollout_*  HybridODENN.forward                            (models/hybrid_ode_nn.py:136)
+             with solver='rk45' (SciPy RK45 = DP5(4)) and 'dopri5' (SciPy DOP853)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("HODE_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.modules.setdefault("arviz", types.ModuleType("arviz"))  # inference/mcmc.py:11 imports it
+
+from models.hybrid_ode_nn import HybridODENN  # noqa: E402
+from train.train_hybrid import GlucoseDataset  # noqa: E402
+
+torch.set_num_threads(1)
+CPU = torch.device("cpu")
+
+
+def pack_W(model):
+    return np.concatenate([p.detach().cpu().numpy().reshape(-1).astype(np.float32)
+                           for _, p in model.nn_residual.named_parameters()])
+
+
+def theta_of(model):
+    return np.array([float(b) for _, b in model.ode_core.named_buffers()], dtype=np.float32)
+
+
+def make_model(hidden=64, layers=4, seed=0, out_std=0.0, ode_params=None):
+    torch.manual_seed(seed)
+    m = HybridODENN(ode_params=ode_params, nn_hidden=hidden, nn_layers=layers, device=CPU)
+    if out_std > 0:
+        with torch.no_grad():
+            last = m.nn_residual.network[-1]
+            last.weight.normal_(0.0, out_std)
+            last.bias.normal_(0.0, out_std)
+            # give hidden biases some life too so ReLU patterns are non-trivial
+            for layer in m.nn_residual.network[:-1]:
+                if isinstance(layer, torch.nn.Linear):
+                    layer.bias.normal_(0.0, 0.05)
+                    layer.weight.mul_(10.0)  # undo the gain-0.1 init: O(1) activations
+    return m
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: getattr(v, "shape", None) for k, v in arrays.items()})
+
+
+def rhs_cases():
+    states = np.array([
+        [5.0, 100.0, 50.0, 20.0, 0.0, 1.0],          # tests/test_ode_jacobians.py:68-75
+        [8.0, 150.0, 40.0, 30.0, 0.5, 1.2],          # :143-150
+        [0.1, 1.0, 1.0, 0.1, 0.0, 0.1],              # :183-185 (extreme low)
+        [30.0, 1000.0, 200.0, 100.0, 1.0, 5.0],      # extreme high
+        [5.0, 60.0, 80.0, 0.0, 0.0, 1.0],            # steady state
+    ], dtype=np.float32)
+    t = np.array([0.0, 1.0, 0.5, 2.0, 3.0], dtype=np.float32)
+    meal = np.array([0.0, 10.0, 0.0, 5.0, 0.0], dtype=np.float32)
+    tvns = np.array([0.0, 0.0, 1.0, 1.0, 0.0], dtype=np.float32)
+    gd = np.array([0.0, 0.0, 0.0, 500.0, 1500.0], dtype=np.float32)
+    for tag, hidden, layers, std in (("mech", 64, 4, 0.0), ("nn64x4", 64, 4, 0.05),
+                                     ("nn16x2", 16, 2, 0.05), ("nn32x3", 32, 3, 0.1)):
+        m = make_model(hidden, layers, seed=1, out_std=std)
+        ext = {"meal": torch.tensor(meal), "tVNS": torch.tensor(tvns), "GD": torch.tensor(gd)}
+        with torch.no_grad():
+            out_b = m.ode_residual(torch.tensor(t), torch.tensor(states), ext).numpy()
+            out_1 = np.stack([
+                m.ode_residual(torch.tensor(t[i]), torch.tensor(states[i]),
+                               {k: v[i] for k, v in ext.items()}).numpy()
+                for i in range(len(t))])
+        save(f"rhs_{tag}", t=t, state=states, meal=meal, tvns=tvns, gd=gd, theta=theta_of(m),
+             W=pack_W(m), hidden=hidden, layers=layers, out_batched=out_b, out_single=out_1)
+
+
+class StepLog:
+    """Records (t_n, h_n) of every accepted step SciPy's RK45 takes inside the reference's
+    forward(), by wrapping RungeKutta._step_impl (scipy/integrate/_ivp/rk.py:111)."""
+
+    def __enter__(self):
+        import scipy.integrate._ivp.rk as rk
+        self.rk, self.orig, self.log = rk, rk.RungeKutta._step_impl, []
+        outer = self
+
+        def patched(solver):
+            t0 = solver.t
+            ok = outer.orig(solver)
+            outer.log.append((t0, solver.t - t0, solver.nfev))
+            return ok
+        rk.RungeKutta._step_impl = patched
+        return self
+
+    def __exit__(self, *a):
+        self.rk.RungeKutta._step_impl = self.orig
+
+
+def run_forward(m, y0, t, ext, solver, rtol=1e-6, atol=1e-8):
+    ext_t = {k: torch.tensor(v) for k, v in ext.items()} if ext else None
+    with torch.no_grad():
+        return m.forward(torch.tensor(y0), torch.tensor(t), ext_t, solver=solver, rtol=rtol,
+                         atol=atol).numpy()
+
+
+def rollout_fig2():
+    # plots/plot_all.py:164-187 scenario
+    y0 = np.array([[5.0, 60.0, 80.0, 0.0, 0.0, 1.0]], dtype=np.float32)
+    t = np.linspace(0, 5, 61).astype(np.float32)
+    meal = np.zeros((1, 61), dtype=np.float32)
+    meal[0, 6] = 75.0
+    tv = np.zeros((1, 61), dtype=np.float32)
+    m = make_model()
+    with StepLog() as sl:
+        o45 = run_forward(m, y0, t, {"meal": meal, "tVNS": tv}, "rk45")
+    steps = np.array(sl.log, dtype=np.float64)
+    o853 = run_forward(m, y0, t, {"meal": meal, "tVNS": tv}, "dopri5")
+    save("rollout_fig2", y0=y0, t=t, meal=meal, tvns=tv, theta=theta_of(m), W=pack_W(m),
+         hidden=64, layers=4, out_rk45=o45, out_dopri5=o853, steps_rk45=steps)
+
+
+def windows_4gi():
+    ds = GlucoseDataset(os.path.join(REF, "data/4gi_dataset.csv"), 61, 30, True)
+    items = [ds[i] for i in range(len(ds))]
+    y0 = np.stack([it["initial_state"].numpy() for it in items])
+    obs = np.stack([it["observations"].numpy() for it in items])
+    t = np.stack([it["time_points"].numpy() for it in items])
+    meal = np.stack([it["external_inputs"]["meal"].numpy() for it in items])
+    tv = np.stack([it["external_inputs"]["tVNS"].numpy() for it in items])
+    return y0, obs, t, meal, tv, ds
+
+
+def rollout_4gi():
+    y0, obs, t, meal, tv, ds = windows_4gi()
+    for tag, std in (("mech", 0.0), ("nn", 0.05)):
+        m = make_model(seed=2, out_std=std)
+        out = {s: run_forward(m, y0, t, {"meal": meal, "tVNS": tv}, s) for s in ("rk45", "dopri5")}
+        save(f"rollout_4gi_{tag}", y0=y0, t=t, meal=meal, tvns=tv, obs=obs, theta=theta_of(m),
+             W=pack_W(m), hidden=64, layers=4, state_mean=ds.state_mean, state_std=ds.state_std,
+             out_rk45=out["rk45"], out_dopri5=out["dopri5"])
+
+
+def rollout_physio():
+    """Physiological-unit cohort (SURVEY §8d config 2/3 statistics), shared t, hybrid net,
+    small nets, constant inputs (the physics re-solve pattern, models/hybrid_ode_nn.py:320)."""
+    rng = np.random.default_rng(3)
+    B = 6
+    y0 = np.stack([7.0 * rng.normal(1, 0.1, B), 50.0 * rng.normal(1, 0.15, B),
+                   25.0 * rng.normal(1, 0.15, B), 10.0 * rng.normal(1, 0.15, B),
+                   np.zeros(B), np.ones(B)], axis=1).astype(np.float32)
+    t = np.linspace(0, 5, 61).astype(np.float32)
+    meal = np.zeros((B, 61), dtype=np.float32)
+    meal[:, 6] = 1.0
+    meal[:, 30] = rng.uniform(0.5, 1.5, B)
+    tv = np.zeros((B, 61), dtype=np.float32)
+    tv[::2, 20:40] = 1.0
+    for tag, hidden, layers in (("nn64x4", 64, 4), ("nn16x2", 16, 2)):
+        m = make_model(hidden, layers, seed=4, out_std=0.02)
+        out = run_forward(m, y0, t, {"meal": meal, "tVNS": tv}, "rk45")
+        save(f"rollout_physio_{tag}", y0=y0, t=t, meal=meal, tvns=tv, theta=theta_of(m),
+             W=pack_W(m), hidden=hidden, layers=layers, out_rk45=out)
+    # constant inputs, T=2 local-time window
+    m = make_model(seed=5, out_std=0.02)
+    t2 = np.array([0.0, 0.1], dtype=np.float32)
+    mc = rng.uniform(0, 2, B).astype(np.float32)
+    tc = (rng.uniform(0, 1, B) > 0.5).astype(np.float32)
+    with StepLog() as sl:
+        out = run_forward(m, y0[:1], t2, {"meal": mc[:1], "tVNS": tc[:1]}, "rk45")
+    steps = np.array(sl.log, dtype=np.float64)
+    out = run_forward(m, y0, t2, {"meal": mc, "tVNS": tc}, "rk45")
+    out8 = run_forward(m, y0, t2, {"meal": mc, "tVNS": tc}, "dopri5")
+    save("rollout_const_T2", y0=y0, t=t2, meal=mc, tvns=tc, theta=theta_of(m), W=pack_W(m),
+         hidden=64, layers=4, out_rk45=out, out_dopri5=out8, steps_rk45_traj0=steps)
+    # per-row time grids with jitter + non-default ODE parameters
+    m = make_model(seed=6, out_std=0.02, ode_params={"k_L": 0.05, "V_max": 7.0, "rho": 0.01})
+    T = 25
+    tj = np.sort(np.linspace(0, 2, T)[None, :] + rng.uniform(-0.02, 0.02, (B, T)), axis=1)
+    tj = tj.astype(np.float32)
+    mj = (rng.uniform(0, 1, (B, T)) > 0.85).astype(np.float32) * rng.lognormal(0, 0.5, (B, T)).astype(np.float32)
+    out = run_forward(m, y0, tj, {"meal": mj}, "rk45")
+    save("rollout_perrow_t", y0=y0, t=tj, meal=mj, theta=theta_of(m), W=pack_W(m), hidden=64,
+         layers=4, out_rk45=out)
+
+
+if __name__ == "__main__":
+    rhs_cases()
+    rollout_fig2()
+    rollout_4gi()
+    rollout_physio()

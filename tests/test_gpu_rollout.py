@@ -1,0 +1,277 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes -> libhode.so) and is checked
+against the CPU oracle and the reference-generated golden fixtures."""
+import ctypes
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import cohort, golden, golden_inputs, random_mlp, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def gpu_rollout(dev, y0, t, ins, theta, W, hidden=64, layers=4, **kw):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    tin = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in (ins or {}).items()}
+    traj, info = ops.rollout(torch.from_numpy(y0), torch.from_numpy(t), tin,
+                             torch.from_numpy(theta), None if W is None else torch.from_numpy(W),
+                             hidden=hidden, layers=layers, device=dev, **kw)
+    torch.cuda.synchronize()
+    return (traj.cpu().numpy(), info.status.cpu().numpy(), info.n_accept.cpu().numpy(),
+            info.n_reject.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------- RHS
+@pytest.mark.parametrize("tag", ["mech", "nn64x4", "nn16x2", "nn32x3"])
+def test_rhs_matches_reference_golden(dev, oracle, tag):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    d = golden(f"rhs_{tag}")
+    W = None if tag == "mech" else torch.from_numpy(d["W"])
+    ins = {k: torch.from_numpy(v) for k, v in golden_inputs(d).items()}
+    out = ops.rhs(torch.from_numpy(d["t"]), torch.from_numpy(d["state"]), ins,
+                  torch.from_numpy(d["theta"]), W, int(d["hidden"]), int(d["layers"]),
+                  device=dev).cpu().numpy().astype(np.float64)
+    ref = d["out_batched"].astype(np.float64)
+    if tag == "mech":
+        # same operation order, IEEE division: identical except for powf (rows with GD != 0)
+        assert np.array_equal(out[:3].astype(np.float32), d["out_batched"][:3])
+        np.testing.assert_allclose(out, ref, rtol=3e-7, atol=1e-9)
+    else:
+        tol = 4e-6 * np.maximum(np.abs(ref), np.abs(d["state"]).max(axis=1, keepdims=True) * 1e-2 + 1)
+        assert np.all(np.abs(out - ref) <= tol)
+    orc = oracle.rhs_eval(d["t"], d["state"], golden_inputs(d), d["theta"],
+                          None if tag == "mech" else d["W"], int(d["hidden"]), int(d["layers"]))
+    np.testing.assert_allclose(out, orc, rtol=1e-5, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------- fixed-step RK4
+def test_rk4_mechanistic_parity(dev, oracle):
+    """BASELINE config 2 shape at a size the oracle finishes in seconds: <= 1e-5 relative."""
+    y0, t, ins = cohort(4096, seed=1)
+    theta = oracle.THETA_DEFAULT
+    tr, st, na, _ = gpu_rollout(dev, y0, t, ins, theta, None, solver="rk4", n_substeps=4)
+    ref, _, cn, _ = oracle.rollout(y0, t, ins, theta, None, solver="rk4", n_substeps=4, n_threads=8)
+    assert (st == 0).all() and (na == 240).all() and (cn[0] == 240).all()
+    assert rel_err(tr, ref) < 1e-5
+    assert np.array_equal(tr[:, 0], y0)
+
+
+@pytest.mark.parametrize("hidden,layers", [(64, 4), (16, 2), (32, 3), (64, 1), (128, 2), (24, 5)])
+def test_rk4_hybrid_parity(dev, oracle, hidden, layers):
+    y0, t, ins = cohort(300, seed=2)
+    W = random_mlp(hidden, layers, seed=3)
+    theta = oracle.THETA_DEFAULT
+    tr, st, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, hidden, layers, solver="rk4", n_substeps=2)
+    ref, _, _, _ = oracle.rollout(y0, t, ins, theta, W, hidden, layers, solver="rk4", n_substeps=2,
+                                  n_threads=8)
+    assert (st == 0).all()
+    assert rel_err(tr, ref) < 1e-5
+
+
+def test_rk4_input_layouts(dev, oracle):
+    """per-row time grids, constant inputs, a GD series, ragged batch size."""
+    rng = np.random.default_rng(5)
+    B, T = 77, 25
+    y0, _, _ = cohort(B, T, seed=5)
+    t = np.sort(np.linspace(0, 2, T)[None] + rng.uniform(-0.02, 0.02, (B, T)), axis=1).astype(np.float32)
+    ins = {"meal": (rng.uniform(0, 1, (B, T)) > 0.8).astype(np.float32),
+           "tVNS": (rng.uniform(0, 1, B) > 0.5).astype(np.float32),
+           "GD": rng.uniform(0, 1500, (B, T)).astype(np.float32)}
+    W = random_mlp(seed=6)
+    theta = oracle.THETA_DEFAULT.copy()
+    theta[13] = 1.7                                        # non-integer Hill coefficient
+    tr, st, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, solver="rk4", n_substeps=3)
+    ref, _, _, _ = oracle.rollout(y0, t, ins, theta, W, solver="rk4", n_substeps=3)
+    assert (st == 0).all()
+    assert rel_err(tr, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------- adaptive DP5(4)
+def test_dopri5_mechanistic_clip_within_tolerance_of_truth(dev, oracle):
+    y0, t, ins = cohort(512, seed=7)
+    theta = oracle.THETA_DEFAULT
+    truth, _, _, _ = oracle.rollout(y0, t, ins, theta, None, rhs="f64", rtol=1e-11, atol=1e-13,
+                                    kinks="clip", n_threads=8)
+    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, None, solver="dopri5", kinks="clip")
+    assert (st == 0).all()
+    # global error after ~15 steps: tens of local-tolerance units (the reference's own error on
+    # its Fig-2 scenario is 18-99 units)
+    assert scaled_err(tr, truth.astype(np.float64)) < 150
+    orc, _, cn, _ = oracle.rollout(y0, t, ins, theta, None, kinks="clip", n_threads=8)
+    att_gpu, att_cpu = (na + nr).mean(), (cn[0] + cn[1]).mean()
+    assert abs(att_gpu - att_cpu) / att_cpu < 0.15
+    assert scaled_err(tr, orc.astype(np.float64)) < 150
+
+
+@pytest.mark.parametrize("kinks", ["clip", "scipy"])
+def test_dopri5_hybrid_as_accurate_as_the_oracle(dev, oracle, kinks):
+    y0, t, ins = cohort(256, seed=8)
+    W = random_mlp(seed=9, out_std=0.02)
+    theta = oracle.THETA_DEFAULT
+    truth, _, _, _ = oracle.rollout(y0, t, ins, theta, W, rhs="f64", rtol=1e-11, atol=1e-13,
+                                    kinks="clip", n_threads=8)
+    truth = truth.astype(np.float64)
+    orc, _, cn, _ = oracle.rollout(y0, t, ins, theta, W, kinks=kinks, n_threads=8)
+    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks=kinks)
+    assert (st == 0).all()
+    sc = 1e-8 + 1e-6 * np.abs(truth)
+    e_gpu = (np.abs(tr - truth) / sc).max(axis=(1, 2))
+    e_cpu = (np.abs(orc - truth) / sc).max(axis=(1, 2))
+    assert np.median(e_gpu) < 2 * np.median(e_cpu) + 50
+    assert np.percentile(e_gpu, 90) < 3 * np.percentile(e_cpu, 90) + 100
+    att_gpu, att_cpu = (na + nr).mean(), (cn[0] + cn[1]).mean()
+    assert abs(att_gpu - att_cpu) / att_cpu < 0.2
+
+
+def test_dopri5_against_reference_golden(dev, oracle):
+    # constant inputs (physics re-solve pattern): smooth, so kernel ~ reference directly
+    d = golden("rollout_const_T2")
+    tr, st, _, _ = gpu_rollout(dev, d["y0"], d["t"], golden_inputs(d), d["theta"], d["W"],
+                               solver="rk45", kinks="scipy")
+    assert (st == 0).all()
+    assert scaled_err(tr, d["out_rk45"]) < 100
+    assert scaled_err(tr, d["out_dopri5"]) < 100
+    # Fig-2 scenario: the reference caught the meal spike here; clip mode must agree with it
+    d = golden("rollout_fig2")
+    tr, st, _, _ = gpu_rollout(dev, d["y0"], d["t"], golden_inputs(d), d["theta"], None,
+                               solver="dopri5", kinks="clip")
+    assert st[0] == 0
+    assert scaled_err(tr, d["out_rk45"]) < 300
+    assert scaled_err(tr, d["out_dopri5"]) < 300
+    # real 4GI windows: reference steps over the pulses (see tests/test_oracle.py); the kernel
+    # in clip mode converges to the truth
+    d = golden("rollout_4gi_mech")
+    truth, _, _, _ = oracle.rollout(d["y0"], d["t"], golden_inputs(d), d["theta"], None, rhs="f64",
+                                    rtol=1e-11, atol=1e-13, kinks="clip")
+    tr, st, _, _ = gpu_rollout(dev, d["y0"], d["t"], golden_inputs(d), d["theta"], None,
+                               solver="dopri5", kinks="clip")
+    assert (st == 0).all()
+    assert scaled_err(tr, truth.astype(np.float64)) < 150
+
+
+def test_failure_status_and_zero_padding(dev, oracle):
+    y0, t, _ = cohort(40, 11, seed=10, meals=False, tvns=False)
+    theta = oracle.THETA_DEFAULT.copy()
+    theta[16] = 1e6
+    tr, st, _, _ = gpu_rollout(dev, y0, t, None, theta, None, solver="dopri5", max_steps=5000)
+    ref, st_ref, _, _ = oracle.rollout(y0, t, None, theta, None, max_steps=5000)
+    assert (st != 0).all() and (st_ref != 0).all()
+    assert (tr[:, -1] == 0).all() and np.array_equal(tr[:, 0], y0)
+    assert np.isfinite(tr).all()
+
+
+def test_edge_shapes(dev, oracle):
+    theta = oracle.THETA_DEFAULT
+    y0, t, ins = cohort(3, 61, seed=11)
+    for solver in ("rk4", "dopri5"):
+        tr, st, na, _ = gpu_rollout(dev, y0, t[:1], None, theta, None, solver=solver)   # T = 1
+        assert tr.shape == (3, 1, 6) and np.array_equal(tr[:, 0], y0) and (na == 0).all()
+        tr, st, _, _ = gpu_rollout(dev, y0[:1], t[:2], None, theta, None, solver=solver)  # B=1,T=2
+        assert tr.shape == (1, 2, 6) and (st == 0).all()
+    tr, st, _, _ = gpu_rollout(dev, y0[:0], t, None, theta, None)                        # B = 0
+    assert tr.shape == (0, 61, 6)
+
+
+def test_parameter_sets_sweep_equals_separate_launches(dev, oracle):
+    """n_samples > 1 (the VI sweep layout): sample s of the [S,B] launch is bit-identical to a
+    launch with that parameter set alone."""
+    y0, t, ins = cohort(130, seed=12)
+    S = 3
+    thetas = np.stack([oracle.THETA_DEFAULT * (1 + 0.05 * s) for s in range(S)]).astype(np.float32)
+    Ws = np.stack([random_mlp(seed=20 + s) for s in range(S)])
+    tr, st, _, _ = gpu_rollout(dev, y0, t, ins, thetas, Ws, solver="dopri5")
+    assert tr.shape == (S, 130, 61, 6)
+    for s in range(S):
+        one, _, _, _ = gpu_rollout(dev, y0, t, ins, thetas[s], Ws[s], solver="dopri5")
+        assert np.array_equal(one, tr[s])
+
+
+def test_host_entry_matches_device_entry(dev, oracle):
+    """hode_rollout_fwd_host (the e2e path bench.py times) == device-pointer path."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, ops
+    y0, t, ins = cohort(200, seed=13)
+    W = random_mlp(seed=14)
+    theta = oracle.THETA_DEFAULT
+    ref, st_ref, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5")
+    cfg, _ = ops.prepare(torch.from_numpy(y0), torch.from_numpy(t),
+                         {k: torch.from_numpy(v) for k, v in ins.items()},
+                         torch.from_numpy(theta), torch.from_numpy(W), 64, 4, torch.device("cpu"))
+    cfg.solver, cfg.kink_mode = _lib.SOLVER_DOPRI5, _lib.KINK_CLIP
+    traj = np.empty((200, 61, 6), np.float32)
+    status = np.empty(200, np.int32)
+    counters = np.empty((2, 200), np.int32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = _lib.lib().hode_rollout_fwd_host(ctypes.byref(cfg), p(y0), p(t), p(ins["meal"]),
+                                          p(ins["tVNS"]), None, p(theta), p(W), p(traj), p(status),
+                                          p(counters), None)
+    _lib.check(rc, "hode_rollout_fwd_host")
+    assert np.array_equal(traj, ref) and np.array_equal(status, st_ref)
+    assert np.array_equal(counters[0], na) and np.array_equal(counters[1], nr)
+
+
+def test_full_size_properties_config2(dev, oracle):
+    """BASELINE config 2 at full size (1 048 576 trajectories, RK4): size-independent
+    properties + an oracle check on a strided subsample."""
+    B = 1 << 20
+    y0, t, ins = cohort(B, seed=15, tvns=False)
+    theta = oracle.THETA_DEFAULT
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    dy0, dt = torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev)
+    dins = {k: torch.from_numpy(v).to(dev) for k, v in ins.items()}
+    th = torch.from_numpy(theta).to(dev)
+    traj, info = ops.rollout(dy0, dt, dins, th, None, solver="rk4", n_substeps=4)
+    assert bool((info.status == 0).all()) and bool((info.n_accept == 240).all())
+    assert bool(torch.isfinite(traj).all())
+    assert bool((traj[:, 0] == dy0).all())
+    assert bool((traj[:, :, 4] == 0).all())               # GE never moves without a network
+    # permutation equivariance: trajectories are independent and deterministic
+    perm = torch.randperm(B, device=dev, generator=torch.Generator(dev).manual_seed(0))
+    traj_p, _ = ops.rollout(dy0[perm], dt, {k: v[perm] for k, v in dins.items()}, th, None,
+                            solver="rk4", n_substeps=4)
+    assert bool((traj_p == traj[perm]).all())
+    idx = np.arange(0, B, B // 2048)
+    ref, _, _, _ = oracle.rollout(y0[idx], t, {k: v[idx] for k, v in ins.items()}, theta, None,
+                                  solver="rk4", n_substeps=4, n_threads=8)
+    assert rel_err(traj[torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------- module surface
+def test_module_forward_contract(dev, caplog):
+    """The reference's call pattern (models/hybrid_ode_nn.py:136-261) on the drop-in class."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    torch.manual_seed(0)
+    m = HybridODENN(nn_hidden=32, nn_layers=3, device=dev)
+    y0, t, ins = cohort(5, seed=16)
+    tin = {k: torch.from_numpy(v) for k, v in ins.items()}
+    out = m(torch.from_numpy(y0), torch.from_numpy(t), tin)           # CPU tensors in
+    assert out.shape == (5, 61, 6) and out.device.type == "cuda" and not out.requires_grad
+    out1 = m(torch.from_numpy(y0[0]), torch.from_numpy(t), {k: v[:1] for k, v in tin.items()})
+    assert out1.shape == (61, 6)
+    assert torch.equal(out1, out[0])
+    # fresh model == pure mechanistic ODE (zero output layer, reference nn_residual.py:83-98)
+    m.skip_zero_nn = False
+    out_nn = m(torch.from_numpy(y0), torch.from_numpy(t), tin)
+    assert torch.allclose(out_nn, out, rtol=1e-6, atol=1e-7)
+    # forward_with_params overrides without touching the module
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    smp = {"ode_k_L": torch.tensor(0.05), "nn_network_6_bias": torch.full((6,), 0.01)}
+    out_p = m.forward_with_params(smp, torch.from_numpy(y0), torch.from_numpy(t), tin)
+    assert not torch.allclose(out_p, out)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])
+    # solver failure -> warning + zero padding, no exception (reference :243-256)
+    m.ode_core.p_9.fill_(1e6)
+    with caplog.at_level(logging.WARNING):
+        bad = m(torch.from_numpy(y0), torch.from_numpy(t), tin, max_steps=2000)
+    assert "ODE solver failed for batch" in caplog.text
+    assert bool((bad[:, -1] == 0).all())
+    with pytest.raises(Exception):
+        m(torch.from_numpy(y0), torch.from_numpy(t), tin, solver="radau")

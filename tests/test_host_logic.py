@@ -1,0 +1,124 @@
+"""Host-side logic that needs no GPU: the drop-in surface (constructor, attribute names,
+state_dict keys, parameter packing order), input normalisation, and the loud failure when
+no CUDA device is available."""
+import numpy as np
+import pytest
+import torch
+
+import hybrid_ode_for_glp_1_and_glucose_b200 as hode
+from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, ops
+from helpers import golden
+
+CPU = torch.device("cpu")
+
+
+def test_state_dict_keys_match_the_reference():
+    # 63 keys with VI
+    m = hode.HybridODENN(use_variational=True, device=CPU)
+    keys = list(m.state_dict())
+    assert len(keys) == 63
+    ode = ["a_GI", "k_I", "rho", "G_b", "I_b", "E_max", "EC_50", "Glu_b", "V_max", "K_m", "k_L",
+           "k_GE0", "IGD_50", "g", "p_7", "p_8", "p_9"]
+    assert keys[:17] == [f"ode_core.{n}" for n in ode]
+    assert keys[17:27] == [f"nn_residual.network.{i}.{p}" for i in (0, 2, 4, 6, 8)
+                           for p in ("weight", "bias")]
+    assert "variational_params.means.ode_a_GI" in keys
+    assert "variational_params.log_stds.nn_network_8_bias" in keys
+    assert m.n_states == 6 and m.state_names[3] == "GLP1" and m.use_variational
+    assert hode.HybridODENN(device=CPU).variational_params is None
+
+
+def test_fresh_model_reproduces_reference_defaults():
+    d = golden("rhs_mech")
+    m = hode.HybridODENN(device=CPU)
+    assert np.array_equal(m.ode_core.theta().numpy(), d["theta"])
+    m2 = hode.HybridODENN(ode_params={"k_L": 0.05, "V_max": 7.0}, device=CPU)
+    th = m2.ode_core.theta().numpy()
+    assert th[10] == np.float32(0.05) and th[8] == np.float32(7.0) and th[0] == np.float32(0.0104)
+    # zero-initialised head, Xavier body with gain 0.1 (reference nn_residual.py:83-98)
+    lin = m.nn_residual.linears()
+    assert len(lin) == 5 and lin[0].weight.shape == (64, 9) and lin[-1].weight.shape == (6, 64)
+    assert float(lin[-1].weight.detach().abs().max()) == 0 and float(lin[-1].bias.detach().abs().max()) == 0
+    assert 0 < float(lin[1].weight.std()) < 0.03
+    assert m.nn_residual.is_identically_zero()
+    assert m.packed_parameters()[1] is None
+
+
+def test_packing_order_is_named_parameters_order():
+    m = hode.HybridODENN(nn_hidden=16, nn_layers=2, device=CPU)
+    with torch.no_grad():
+        for i, (_, p) in enumerate(m.nn_residual.named_parameters()):
+            p.fill_(float(i + 1))
+    W = m.nn_residual.packed().detach().numpy()
+    sizes = [16 * 9, 16, 16 * 16, 16, 6 * 16, 6]
+    assert W.shape == (sum(sizes),) == (_lib.mlp_param_count(16, 2),)
+    off = 0
+    for i, n in enumerate(sizes):
+        assert (W[off:off + n] == i + 1).all()
+        off += n
+    # overrides by the reference's 'nn_<clean name>' / 'ode_<name>' keys
+    th, W2 = m.packed_parameters({"ode_rho": torch.tensor(0.5),
+                                  "nn_network_2_bias": torch.zeros(16)})
+    assert float(th[2]) == 0.5 and (W2.detach()[16 * 9 + 16 + 256:16 * 9 + 16 + 256 + 16] == 0).all()
+    # packed() is differentiable w.r.t. the module parameters
+    m.nn_residual.packed().sum().backward()
+    assert all(p.grad is not None for p in m.nn_residual.parameters())
+
+
+def test_prepare_normalises_inputs_like_the_reference():
+    y0 = torch.zeros(4, 6)
+    t = torch.linspace(0, 1, 5)
+    th = torch.zeros(17)
+    cfg, bufs = ops.prepare(y0, t, {"meal": torch.ones(4, 5), "tVNS": torch.ones(4)}, th, None,
+                            64, 4, CPU)
+    assert (cfg.n_traj, cfg.n_obs, cfg.t_per_traj, cfg.n_samples) == (4, 5, 0, 1)
+    assert list(cfg.in_mode) == [_lib.IN_SERIES, _lib.IN_CONST, _lib.IN_ABSENT]
+    assert cfg.mlp == _lib.MLP_NONE
+    cfg, _ = ops.prepare(y0, t.repeat(4, 1), None, th.repeat(3, 1), torch.zeros(3, 13510), 64, 4, CPU)
+    assert cfg.t_per_traj == 1 and cfg.n_samples == 3 and cfg.mlp == _lib.MLP_FP32
+    # a [1,T] grid for B != 1 is squeezed (reference models/hybrid_ode_nn.py:192-196)
+    cfg, bufs = ops.prepare(y0, t.unsqueeze(0), None, th, None, 64, 4, CPU)
+    assert cfg.t_per_traj == 0 and bufs["t_obs"].shape == (5,)
+    with pytest.raises(ValueError):
+        ops.prepare(y0, t, {"meal": torch.ones(3, 5)}, th, None, 64, 4, CPU)
+    with pytest.raises(ValueError):
+        ops.prepare(y0, t, None, th, torch.zeros(100), 64, 4, CPU)
+    with pytest.raises(ValueError):
+        ops.prepare(torch.zeros(4, 5), t, None, th, None, 64, 4, CPU)
+
+
+def test_no_cpu_fallback():
+    m = hode.HybridODENN(device=CPU)
+    with pytest.raises(hode.HodeError):
+        m(torch.zeros(2, 6), torch.linspace(0, 1, 5))
+    with pytest.raises(hode.HodeError):
+        m.ode_residual(torch.tensor(0.0), torch.zeros(2, 6))
+    with pytest.raises(hode.HodeError):
+        ops.rollout(torch.zeros(2, 6), torch.linspace(0, 1, 5), None, torch.zeros(17), None)
+    with pytest.raises(NotImplementedError):
+        hode.NNResidual(activation="tanh")
+
+
+def test_variational_parameters_follow_the_reference_formulas():
+    torch.manual_seed(0)
+    shapes = {"ode_a": torch.Size([]), "nn_w": torch.Size([3, 2])}
+    vp = hode.VariationalParameters(shapes, {"ode_a": 0.5}, {"ode_a": 2.0})
+    assert float(vp.means["ode_a"]) == 0.5
+    assert abs(float(vp.log_stds["ode_a"]) - np.log(0.2)) < 1e-7      # 10 % of the prior std
+    assert abs(float(vp.log_stds["nn_w"][0, 0]) - np.log(0.1)) < 1e-7
+    # KL of N(mu, s) from N(mu_p, s_p), reference models/bayes.py:146-153
+    kl = float(vp.kl_divergence())
+    k_a = np.log(2.0) - np.log(0.2) + (0.2 ** 2) / (2 * 4.0) - 0.5
+    k_w = 6 * (0.0 - np.log(0.1) + (0.1 ** 2) / 2 - 0.5)
+    assert abs(kl - (k_a + k_w)) < 1e-5
+    # sampling consumes randn_like per tensor in insertion order (reference :117-123)
+    torch.manual_seed(1)
+    s = vp.sample(1)[0]
+    torch.manual_seed(1)
+    e_a = torch.randn(())
+    e_w = torch.randn(3, 2)
+    assert torch.allclose(s["ode_a"], 0.5 + e_a * 0.2) and torch.allclose(s["nn_w"], e_w * 0.1)
+    mu, ls = vp.get_flattened_params()
+    assert mu.shape == (7,) and ls.shape == (7,)
+    with pytest.raises(TypeError):
+        hode.bayes_loss(None, torch.zeros(1))
