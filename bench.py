@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — trajectory-steps/s of the hybrid ODE-NN rollout on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hybrid_fwd|mech_rk4]
+    python bench.py --impl reference ...      # the CPU restatement of the reference path
+
+A "step" is one pass of the hot path (one libhode rollout launch) over one batch of
+synthetic 4GI-shaped trajectories.  One JSON line is printed by rank 0.  Definitions of
+every reported quantity are in DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per unit (BASELINE.md §4 / SURVEY.md §8d)
+FLOP_MLP_EVAL = 26496.0          # 13 248 MAC
+FLOP_ATTEMPT_HYBRID = 6 * FLOP_MLP_EVAL + 700.0   # DP5(4) attempt, FSAL: 158 976 + ~700
+FLOP_STEP_RK4_MECH = 310.0
+BYTES_PER_TRAJ = lambda T, n_in, per_row_t: 24 + 4 * T * n_in + (4 * T if per_row_t else 0) + 24 * T
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hybrid_fwd", choices=["hybrid_fwd", "mech_rk4"])
+    ap.add_argument("--traj-per-gpu", type=int, default=0)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # configs/default.yaml-shaped: hybrid 64x4 net with a non-zero head, dopri5 1e-6/1e-8,
+    # 262 144 trajectories (the config's whole cohort on ONE GPU; weak scaling over N)
+    "hybrid_fwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip",
+                       nn=True, name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd, 262144 traj/GPU, T=61"),
+    # configs/ablation_no_nn.yaml-shaped: mechanistic only, RK4, 4 substeps per 5-min interval
+    "mech_rk4": dict(B=1048576, T=61, solver="rk4", n_substeps=4, nn=False,
+                     name="ablation_no_nn mechanistic rk4 4 substeps, 1048576 traj/GPU, T=61"),
+}
+
+
+def make_workload(kind: str, B: int, seed: int):
+    from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import THETA_DEFAULT, cohort, random_mlp
+    w = dict(WORKLOADS[kind])
+    if B:
+        w["B"] = B
+    y0, t, ins = cohort(w["B"], w["T"], seed=seed, tvns=(kind == "hybrid_fwd"))
+    W = random_mlp(64, 4, seed=1234, out_std=0.05) if w["nn"] else None
+    w.update(y0=y0, t=t, ins=ins, theta=THETA_DEFAULT.copy(), W=W)
+    return w
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "power_w_max": float(np.max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(w, n_traj: int, threads: int):
+    """Time the C restatement of the reference path on `n_traj` trajectories of workload w."""
+    from oracle import cpu_oracle as o
+    sl = slice(0, n_traj)
+    ins = {k: v[sl] for k, v in w["ins"].items()}
+    t0 = time.perf_counter()
+    if w["solver"] == "rk4":
+        _, st, cn, nfev = o.rollout(w["y0"][sl], w["t"], ins, w["theta"], w["W"], solver="rk4",
+                                    n_substeps=w["n_substeps"], n_threads=threads)
+    else:
+        _, st, cn, nfev = o.rollout(w["y0"][sl], w["t"], ins, w["theta"], w["W"], solver="dopri5",
+                                    rtol=w["rtol"], atol=w["atol"], kinks=w["kinks"], n_threads=threads)
+    dt = time.perf_counter() - t0
+    return float(cn[0].sum() + cn[1].sum()), dt
+
+
+def cpu_sample_size(w, threads: int, target_s: float) -> int:
+    probe = min(w["B"], 32 * threads)
+    cpu_oracle_run(w, min(probe, 2 * threads), threads)      # load/compile, warm caches
+    _, dt = cpu_oracle_run(w, probe, threads)
+    n = int(probe * target_s / max(dt, 1e-3))
+    return max(probe, min(w["B"], (n // 64) * 64 or 64))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    w = make_workload(args.workload, args.traj_per_gpu, seed=1000)
+    from oracle import cpu_oracle as o
+    o.build()
+    n = cpu_sample_size(w, threads, target_s=6.0)
+    for _ in range(args.warmup):
+        cpu_oracle_run(w, min(n, 8 * threads), threads)
+    steps_total, t_total = 0.0, 0.0
+    for _ in range(args.steps):
+        s, dt = cpu_oracle_run(w, n, threads)
+        steps_total += s
+        t_total += dt
+    value = steps_total / t_total
+    sample = (f"{n} of {w['B']} trajectories per step, C restatement of the reference path "
+              f"(oracle/hode_oracle.c: float32 RHS, float64 SciPy-RK45 stepping), {threads} pthreads")
+    line = {
+        "impl": "reference", "metric": "trajectory_steps_per_sec", "value": value,
+        "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": w["name"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": threads,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, build, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libhode has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+    L = _lib.lib()
+
+    w = make_workload(args.workload, args.traj_per_gpu, seed=1000 + rank)
+    B, T = w["B"], w["T"]
+    # host copies in pinned memory (the e2e path starts from these)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_y0, h_t, h_theta = pin(w["y0"]), pin(w["t"]), pin(w["theta"])
+    h_ins = {k: pin(v) for k, v in w["ins"].items()}
+    h_W = pin(w["W"]) if w["W"] is not None else None
+    d_y0, d_t, d_theta = h_y0.to(dev), h_t.to(dev), h_theta.to(dev)
+    d_ins = {k: v.to(dev) for k, v in h_ins.items()}
+    d_W = h_W.to(dev) if h_W is not None else None
+    kw = dict(solver=w["solver"], device=dev)
+    if w["solver"] == "rk4":
+        kw.update(n_substeps=w["n_substeps"])
+    else:
+        kw.update(rtol=w["rtol"], atol=w["atol"], kinks=w["kinks"], precision=args.precision)
+
+    def step():
+        return ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        traj, info = step()
+    barrier()
+    attempts_per_step = float((info.n_accept.sum() + info.n_reject.sum()).item())
+    assert bool((info.status == 0).all()), "synthetic workload must integrate without failures"
+
+    # ---- kernel-resident timing: inputs already in HBM, K launches, CUDA events ------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        traj, info = step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = args.steps
+
+    # ---- e2e: host buffers in, host result out, through the C ABI host entry --------------
+    cfg, _ = ops.prepare(h_y0, h_t, h_ins, h_theta, h_W, 64, 4, torch.device("cpu"))
+    cfg.solver = ops.SOLVERS[w["solver"]]
+    cfg.n_substeps = w.get("n_substeps", 1)
+    cfg.rtol, cfg.atol = w.get("rtol", 1e-6), w.get("atol", 1e-8)
+    cfg.kink_mode = ops.KINKS[w.get("kinks", "clip")]
+    if cfg.mlp != _lib.MLP_NONE:
+        cfg.mlp = ops.PRECISIONS[args.precision]
+    h_traj = torch.empty((B, T, 6), dtype=torch.float32).pin_memory()
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_cnt = torch.empty((2, B), dtype=torch.int32).pin_memory()
+    vp = lambda x: None if x is None else ctypes.c_void_p(x.data_ptr())
+    stream = torch.cuda.current_stream(dev)
+
+    def e2e_step():
+        rc = L.hode_rollout_fwd_host(ctypes.byref(cfg), vp(h_y0), vp(h_t), vp(h_ins.get("meal")),
+                                     vp(h_ins.get("tVNS")), vp(h_ins.get("GD")), vp(h_theta), vp(h_W),
+                                     vp(h_traj), vp(h_status), vp(h_cnt),
+                                     ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "hode_rollout_fwd_host")
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()          # synchronises its stream before returning
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    launches += e2e_steps + 1
+    e2e_attempts = float(h_cnt.sum().item())
+    h2d = sum(x.numel() * 4 for x in [h_y0, h_t, h_theta] + list(h_ins.values()) + ([h_W] if h_W is not None else []))
+    d2h = h_traj.numel() * 4 + h_status.numel() * 4 + h_cnt.numel() * 4
+
+    # ---- reduce over ranks: MAX time, SUM work ----------------------------------------------
+    stats = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    work = torch.tensor([attempts_per_step, e2e_attempts], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms_total, e2e_s = stats.tolist()
+    attempts_all, e2e_attempts_all = work.tolist()
+    value = attempts_all * args.steps / (ms_total * 1e-3)
+    e2e_value = e2e_attempts_all * e2e_steps / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        ms_kernel = ms_total / args.steps          # one launch per step, nothing else on the stream
+        if w["nn"]:
+            flops = attempts_per_step * FLOP_ATTEMPT_HYBRID
+            achieved = flops / (ms_kernel * 1e-3) / 1e12
+            if args.precision == "fp32":
+                peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
+                peak_src = (f"FP32 FMA pipe: {sm_count} SM x 128 lanes x 2 flop x {sm_max:.0f} MHz "
+                            "(derived; MEASURED_PEAKS.json has no FP32 CUDA-core figure)")
+                bound = "fp32"
+            else:
+                peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+                peak_src = "TF32 dense = measured sustained bf16 / 2 (MEASURED_PEAKS.json)"
+                bound = "tensor"
+            roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "kernel": "rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel",
+                    "kernel_ms": ms_kernel,
+                    "algorithmic_flop_per_launch": flops}
+        else:
+            nbytes = B * BYTES_PER_TRAJ(T, len(w["ins"]), False)
+            achieved = nbytes / (ms_kernel * 1e-3) / 1e9
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            flops = attempts_per_step * FLOP_STEP_RK4_MECH
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "kernel": "rollout_simt_kernel<0>", "kernel_ms": ms_kernel,
+                    "algorithmic_bytes_per_launch": nbytes,
+                    "fp32_tflops": flops / (ms_kernel * 1e-3) / 1e12}
+        line = {
+            "metric": "trajectory_steps_per_sec", "value": value, "unit": "trajectory-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "mlp_arithmetic": args.precision if w["nn"] else "none",
+                       "trajectories_total": B * world, "attempts_per_trajectory": attempts_per_step / B,
+                       "l2_policy": "inputs+outputs per step exceed L2 (no flush needed): "
+                                    f"{(B * BYTES_PER_TRAJ(T, len(w['ins']), False)) / 2**20:.0f} MiB"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "hode_rollout_fwd_host (pinned host buffers in, host trajectories out)"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "trajectories_per_sec": B * world * args.steps / (ms_total * 1e-3),
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = cpu_sample_size(w, threads, target_s=12.0)
+            s, dt = cpu_oracle_run(w, n, threads)
+            line["cpu_baseline"] = {
+                "value": s / dt, "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
+                "sample": f"{n} of {B} trajectories of the same workload, oracle/hode_oracle.c "
+                          f"(float32 RHS + float64 SciPy-RK45 stepping), {threads} pthreads, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

@@ -35,41 +35,4 @@ def rel_err(a, ref, floor=1e-3):
     return float((np.abs(a - ref) / denom).max())
 
 
-def cohort(B, T=61, seed=0, horizon=5.0, meals=True, tvns=True):
-    """4GI-shaped synthetic cohort: physiological-unit baselines,
-    meal pulses at 0.5 h and 2.5 h, optional tVNS windows."""
-    rng = np.random.default_rng(seed)
-    y0 = np.stack([7.0 * rng.normal(1, 0.1, B), 50.0 * rng.normal(1, 0.15, B),
-                   25.0 * rng.normal(1, 0.15, B), 10.0 * rng.normal(1, 0.15, B),
-                   np.zeros(B), np.ones(B)], axis=1).astype(np.float32)
-    t = np.linspace(0, horizon, T).astype(np.float32)
-    ins = {}
-    if meals:
-        meal = np.zeros((B, T), dtype=np.float32)
-        meal[:, T // 10] = rng.uniform(0.5, 1.5, B)
-        meal[:, T // 2] = rng.uniform(0.3, 1.0, B)
-        ins["meal"] = meal
-    if tvns:
-        tv = np.zeros((B, T), dtype=np.float32)
-        on = rng.uniform(0, 1, B) > 0.5
-        tv[on, T // 3: 2 * T // 3] = 1.0
-        ins["tVNS"] = tv
-    return y0, t, ins
-
-
-def random_mlp(hidden=64, layers=4, seed=0, out_std=0.02, w_gain=1.0):
-    """Packed MLP parameters (include/hode.h W layout) with a non-zero output layer."""
-    rng = np.random.default_rng(seed)
-    parts = []
-    n_in = 9
-    for l in range(layers + 1):
-        n_out = 6 if l == layers else hidden
-        if l == layers:
-            w = rng.normal(0, out_std, (n_out, n_in))
-            b = rng.normal(0, out_std, n_out)
-        else:
-            w = rng.normal(0, w_gain * np.sqrt(2.0 / (n_in + n_out)), (n_out, n_in))
-            b = rng.normal(0, 0.05, n_out)
-        parts += [w.reshape(-1), b]
-        n_in = n_out
-    return np.concatenate(parts).astype(np.float32)
+from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import cohort, random_mlp  # noqa: E402,F401
