@@ -130,6 +130,7 @@ struct Theta {
   float a_GI, k_I, rho, G_b, I_b, E_max, EC_50, Glu_b, V_max, K_m, k_L, k_GE0, IGD_50, g, p_7,
       p_8, p_9;
   float igd_pow;  // IGD_50^g (theta-only; hoisted out of the stage loop)
+  float kge0;     // k_GE when GD == 0 (no GD channel): k_GE0 * (1 - 0^g / (IGD_50^g + 0^g))
 };
 
 __device__ __forceinline__ Theta load_theta(const float* __restrict__ th) {
@@ -139,6 +140,8 @@ __device__ __forceinline__ Theta load_theta(const float* __restrict__ th) {
   p.k_L = th[10]; p.k_GE0 = th[11]; p.IGD_50 = th[12]; p.g = th[13];
   p.p_7 = th[14]; p.p_8 = th[15]; p.p_9 = th[16];
   p.igd_pow = powf(p.IGD_50, p.g);
+  const float z = powf(0.0f, p.g);
+  p.kge0 = __fmul_rn(p.k_GE0, 1.0f - __fdiv_rn(z, p.igd_pow + z));
   return p;
 }
 
@@ -153,9 +156,11 @@ __device__ __forceinline__ void rhs_mech(const Theta& p, const float* y, float m
   const float glp1_effect = __fmul_rn(p.E_max, __fdiv_rn(GLP1, p.EC_50 + GLP1));
   d[2] = __fmul_rn(-glp1_effect, Glu - p.Glu_b);
   d[3] = __fsub_rn(__fmul_rn(p.V_max, __fdiv_rn(G, p.K_m + G)), __fmul_rn(p.k_L, GLP1));
-  const float gdg = gd_present ? powf(GD, p.g) : powf(0.0f, p.g);
-  const float GD_effect = __fdiv_rn(gdg, p.igd_pow + gdg);
-  const float k_GE = __fmul_rn(p.k_GE0, 1.0f - GD_effect);
+  float k_GE = p.kge0;
+  if (gd_present) {
+    const float gdg = powf(GD, p.g);
+    k_GE = __fmul_rn(p.k_GE0, 1.0f - __fdiv_rn(gdg, p.igd_pow + gdg));
+  }
   d[5] = __fadd_rn(__fsub_rn(__fmul_rn(-p.p_7, FFA), __fmul_rn(__fmul_rn(p.p_8, I), FFA)),
                    __fmul_rn(__fmul_rn(p.p_9, G), FFA));
   const float insulin_effect = __fmul_rn(0.01f, I - p.I_b);

@@ -1,0 +1,322 @@
+// tc_probe.cu — standalone hardware probe for the tensor-core MLP path (not part of libhode.so).
+//
+// Validates, on a real B200, the exact tcgen05 recipe the rollout kernel relies on:
+//   * kind::tf32 MMA, M=128, N=64, A operand from TMEM (row r = lane r, K along columns),
+//     B operand from shared memory, K-major, no swizzle (8x16B core matrices), with
+//     LBO = stride between 16-byte K chunks and SBO = stride between 8-row groups;
+//   * tcgen05.st / tcgen05.ld 32x32b shapes, commit -> mbarrier, fences;
+//   * 3xTF32 split accuracy (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi) against float64;
+//   * throughput of the dependent chain  ld -> relu/split -> st -> mma  for 1..4 tiles per CTA.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/tc_probe tc_probe.cu
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, kind::tf32
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD_X32(taddr, r)                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                            \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22," \
+               "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                       \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), \
+                 "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),          \
+                 "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),       \
+                 "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),       \
+                 "=r"(r[31])                                                                        \
+               : "r"(taddr) : "memory")
+
+#define TMEM_ST_X32(taddr, r)                                                                        \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                       \
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23," \
+               "%24,%25,%26,%27,%28,%29,%30,%31,%32};"                                               \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),       \
+                 "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),     \
+                 "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), \
+                 "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), \
+                 "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int M = 128, N = 64, K = 64;
+// B image: float4 img[K/4][N]  (chunk-major) -> LBO = N*16 bytes, SBO = 128 bytes
+constexpr uint32_t LBO = N * 16, SBO = 128;
+
+// ---------------------------------------------------------------------------------------------
+// Test 1: D = A * B^T  (A [128,64] row-major fp32, B [64,64] = weight[out,in] row-major), with
+// `mode`: 0 = single TF32 pass, 1 = 3xTF32.  One CTA of 128 threads.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gemm_probe(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int mode) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* Bhi = reinterpret_cast<float*>(smem);            // 64*64 floats
+  float* Blo = Bhi + N * K;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // stage B: element (n,k) -> img[(k/4)*N + n][k%4]
+  for (int i = tid; i < N * K; i += blockDim.x) {
+    const int n = i / K, k = i % K;
+    const float w = B[i];
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const int o = ((k >> 2) * N + n) * 4 + (k & 3);
+    Bhi[o] = hi;
+    Blo[o] = w - hi;
+  }
+  if (tid == 0) mbar_init(&bar, 1);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = tmem_base_s;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t tD = tb, tAhi = tb + 64, tAlo = tb + 128;
+  // A row `tid` -> TMEM (hi and lo parts)
+  uint32_t hi[32], lo[32];
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = A[tid * K + half * 32 + j];
+      const uint32_t h = __float_as_uint(a) & 0xFFFFE000u;
+      hi[j] = h;
+      lo[j] = __float_as_uint(a - __uint_as_float(h));
+    }
+    TMEM_ST_X32(tAhi + lane_base + half * 32, hi);
+    TMEM_ST_X32(tAlo + lane_base + half * 32, lo);
+  }
+  tmem_wait_st();
+  fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after();
+    const uint32_t idesc = make_idesc_tf32(M, N);
+    const uint32_t bhi = smem_u32(Bhi), blo = smem_u32(Blo);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 8; ++ks) {
+      mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc);
+      acc = 1;
+    }
+    if (mode == 1) {
+      for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAhi + ks * 8, make_desc(blo + ks * 2 * LBO, LBO, SBO), idesc, 1);
+      for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, 1);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after();
+  uint32_t r[32];
+  for (int half = 0; half < 2; ++half) {
+    TMEM_LD_X32(tD + lane_base + half * 32, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[tid * N + half * 32 + j] = __uint_as_float(r[j]);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Test 2: throughput of the dependent layer chain for TILES tiles per CTA (each tile = 128 threads,
+// its own named barrier, mbarrier and 192 TMEM columns), persistent over `iters` layers.
+// ---------------------------------------------------------------------------------------------
+template <int TILES, int PRODUCTS>
+__global__ void __launch_bounds__(128 * TILES) chain_probe(const float* __restrict__ B, float* __restrict__ out, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* Bhi = reinterpret_cast<float*>(smem);
+  float* Blo = Bhi + N * K;
+  __shared__ uint64_t bars[TILES];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, tile = tid >> 7, ttid = tid & 127;
+  for (int i = tid; i < N * K; i += blockDim.x) {
+    const int n = i / K, k = i % K;
+    const float w = B[i];
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const int o = ((k >> 2) * N + n) * 4 + (k & 3);
+    Bhi[o] = hi;
+    Blo[o] = w - hi;
+  }
+  if (ttid == 0) mbar_init(&bars[tile], 1);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = tmem_base_s + tile * (TILES <= 2 ? 256 : 128);
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  // with > 2 tiles only the hi part fits (128 columns per tile): single-pass only
+  const uint32_t tD = tb, tAhi = tb + 64, tAlo = (TILES <= 2) ? tb + 128 : tb + 64;
+  uint32_t v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(0.01f * (float)((ttid + j) % 17));
+  TMEM_ST_X32(tAhi + lane_base, v);
+  TMEM_ST_X32(tAhi + lane_base + 32, v);
+  if (TILES <= 2) { TMEM_ST_X32(tAlo + lane_base, v); TMEM_ST_X32(tAlo + lane_base + 32, v); }
+  tmem_wait_st();
+  const uint32_t idesc = make_idesc_tf32(M, N);
+  const uint32_t bhi = smem_u32(Bhi), blo = smem_u32(Blo);
+  uint32_t parity = 0;
+  float sum = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(tile + 1) : "memory");
+    if (ttid == 0) {
+      fence_after();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ks = 0; ks < K / 8; ++ks) { mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc); acc = 1; }
+      if (PRODUCTS == 3) {
+#pragma unroll
+        for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAhi + ks * 8, make_desc(blo + ks * 2 * LBO, LBO, SBO), idesc, 1);
+#pragma unroll
+        for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, 1);
+      }
+      mma_commit(&bars[tile]);
+    }
+    mbar_wait(&bars[tile], parity);
+    parity ^= 1;
+    fence_after();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32], hi[32], lo[32];
+      TMEM_LD_X32(tD + lane_base + half * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = fmaxf(__uint_as_float(r[j]) * 0.05f + 0.01f, 0.f);   // bias + relu stand-in (keeps values bounded)
+        const uint32_t h = __float_as_uint(x) & 0xFFFFE000u;
+        hi[j] = h;
+        lo[j] = __float_as_uint(x - __uint_as_float(h));
+        sum += x;
+      }
+      TMEM_ST_X32(tAhi + lane_base + half * 32, hi);
+      if (TILES <= 2) TMEM_ST_X32(tAlo + lane_base + half * 32, lo);
+    }
+    tmem_wait_st();
+  }
+  out[blockIdx.x * blockDim.x + tid] = sum;
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+template <int TILES, int PRODUCTS>
+void run_chain(const float* dB, float* dout, int iters, const char* name) {
+  const size_t smem = 2 * N * K * sizeof(float);
+  CK(cudaFuncSetAttribute(chain_probe<TILES, PRODUCTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  chain_probe<TILES, PRODUCTS><<<148, 128 * TILES, smem>>>(dB, dout, 64);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  chain_probe<TILES, PRODUCTS><<<148, 128 * TILES, smem>>>(dB, dout, iters);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double layers = 148.0 * TILES * iters;
+  const double flops = layers * 2.0 * M * N * K;
+  printf("%-28s tiles/CTA %d products %d: %.3f ms, %.1f ns/layer/tile, %.1f cycles/layer-round @1.965GHz, %.1f TFLOP/s algorithmic (x%d tensor)\n",
+         name, TILES, PRODUCTS, ms, ms * 1e6 / iters, ms * 1e-3 / iters * 1.965e9, flops / (ms * 1e-3) / 1e12, PRODUCTS);
+}
+
+int main() {
+  std::vector<float> hA(M * K), hB(N * K), hD(M * N);
+  srand(1);
+  for (auto& x : hA) x = (float)rand() / RAND_MAX * 200.f - 50.f;   // like raw states: up to O(100)
+  for (auto& x : hB) x = ((float)rand() / RAND_MAX - 0.5f) * 0.5f;
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, hA.size() * 4)); CK(cudaMalloc(&dB, hB.size() * 4)); CK(cudaMalloc(&dD, hD.size() * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
+  const size_t smem = 2 * N * K * sizeof(float);
+  CK(cudaFuncSetAttribute(gemm_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int mode = 0; mode < 2; ++mode) {
+    CK(cudaMemset(dD, 0, hD.size() * 4));
+    gemm_probe<<<1, 128, smem>>>(dA, dB, dD, mode);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    double max_rel = 0, max_abs = 0, max_rel_f32 = 0;
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        double ref = 0, mag = 0;
+        float ref32 = 0.f;
+        for (int k = 0; k < K; ++k) {
+          ref += (double)hA[m * K + k] * hB[n * K + k];
+          mag += fabs((double)hA[m * K + k] * hB[n * K + k]);
+          ref32 = fmaf(hA[m * K + k], hB[n * K + k], ref32);
+        }
+        const double err = fabs(hD[m * N + n] - ref);
+        max_abs = fmax(max_abs, err);
+        max_rel = fmax(max_rel, err / mag);
+        max_rel_f32 = fmax(max_rel_f32, fabs(ref32 - ref) / mag);
+      }
+    printf("gemm mode %d (%s): max |err| %.3e, max err/sum|a*b| %.3e  (plain fp32 fma chain: %.3e)  D[0][0]=%f D[127][63]=%f\n",
+           mode, mode ? "3xTF32" : "1xTF32", max_abs, max_rel, max_rel_f32, hD[0], hD[M * N - 1]);
+  }
+  float* dout;
+  CK(cudaMalloc(&dout, 148 * 512 * 4));
+  const int iters = 20000;
+  run_chain<1, 1>(dB, dout, iters, "chain 1xTF32");
+  run_chain<2, 1>(dB, dout, iters, "chain 1xTF32");
+  run_chain<4, 1>(dB, dout, iters, "chain 1xTF32 (hi only)");
+  run_chain<1, 3>(dB, dout, iters, "chain 3xTF32");
+  run_chain<2, 3>(dB, dout, iters, "chain 3xTF32");
+  printf("probe done\n");
+  return 0;
+}

@@ -147,7 +147,7 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
         traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
         status = torch.empty((S, B), dtype=torch.int32, device=device)
         counters = torch.empty((2, S, B), dtype=torch.int32, device=device)
-        rc = _lib.lib().hode_rollout_fwd(
+        rc = 0 if B == 0 else _lib.lib().hode_rollout_fwd(
             ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
             _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
             _ptr(traj), _ptr(status), _ptr(counters), None, 0, _stream(device))

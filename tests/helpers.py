@@ -26,13 +26,25 @@ def scaled_err(a, ref, rtol=1e-6, atol=1e-8):
     return float((np.abs(np.asarray(a, np.float64) - ref) / (atol + rtol * np.abs(ref))).max())
 
 
-def rel_err(a, ref, floor=1e-3):
-    """max |a-ref| / max(|ref|, floor*scale_of_column)."""
+def rel_err(a, ref, floor=0.05):
+    """Relative error of trajectories [..., T, 6]: max |a-ref| / max(|ref|, floor * S) where
+    S is the size of that state component over its own trajectory (max over T).  A pure
+    element-wise ratio is meaningless where a component crosses zero."""
     a = np.asarray(a, np.float64)
     ref = np.asarray(ref, np.float64)
-    denom = np.maximum(np.abs(ref), floor * np.abs(ref).max(axis=tuple(range(ref.ndim - 1)),
-                                                           keepdims=True) + 1e-30)
+    scale = np.abs(ref).max(axis=-2, keepdims=True)
+    denom = np.maximum(np.abs(ref), floor * scale + 1e-30)
     return float((np.abs(a - ref) / denom).max())
+
+
+def rel_err_report(a, ref):
+    """Where the worst element is (for assertion messages)."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    scale = np.abs(ref).max(axis=-2, keepdims=True)
+    r = np.abs(a - ref) / np.maximum(np.abs(ref), 0.05 * scale + 1e-30)
+    idx = np.unravel_index(np.argmax(r), r.shape)
+    return f"worst {r[idx]:.3e} at {idx}: got {a[idx]!r} ref {ref[idx]!r} scale {scale[idx[:-2] + (0, idx[-1])]!r}"
 
 
 from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import cohort, random_mlp  # noqa: E402,F401
