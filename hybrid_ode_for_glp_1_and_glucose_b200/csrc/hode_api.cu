@@ -26,9 +26,13 @@ int cuda_fail(cudaError_t e, const char* where) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_n, off_t, off_h, off_y, total;
+  size_t off_n, off_t, off_h, off_y, off_tc, total;
   int max_saved;
 };
+
+bool uses_tensor_cores(const hode_cfg* c) {
+  return c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32;
+}
 
 int max_saved_steps(const hode_cfg* c) {
   if (c->solver == HODE_SOLVER_RK4) {
@@ -42,12 +46,18 @@ Workspace fwd_workspace(const hode_cfg* c) {
   Workspace w{};
   const size_t units = (size_t)(c->n_samples > 0 ? c->n_samples : 1) * (size_t)c->n_traj;
   w.max_saved = max_saved_steps(c);
-  if (!c->save_steps) return w;
   size_t off = 0;
-  w.off_n = off; off = align_up(off + units * sizeof(int32_t), 256);
-  w.off_t = off; off = align_up(off + units * w.max_saved * sizeof(double), 256);
-  w.off_h = off; off = align_up(off + units * w.max_saved * sizeof(float), 256);
-  w.off_y = off; off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
+  if (c->save_steps) {
+    w.off_n = off; off = align_up(off + units * sizeof(int32_t), 256);
+    w.off_t = off; off = align_up(off + units * w.max_saved * sizeof(double), 256);
+    w.off_h = off; off = align_up(off + units * w.max_saved * sizeof(float), 256);
+    w.off_y = off; off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
+  }
+  if (uses_tensor_cores(c)) {
+    // pre-split weight images (one per parameter set) + the per-set trajectory queue counters
+    w.off_tc = off;
+    off = align_up(off + hode::tc_workspace_bytes(c->n_samples, c->nn_layers), 256);
+  }
   w.total = off;
   return w;
 }
@@ -70,8 +80,8 @@ int validate(const hode_cfg* c) {
         c->nn_layers > HODE_MAX_LAYERS)
       return fail(HODE_E_UNSUPPORTED, "nn_hidden must be in [1,128] and nn_layers in [1,8]");
     if ((c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32) &&
-        (c->nn_hidden != 64 || c->nn_layers < 2))
-      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64, nn_layers >= 2");
+        (c->nn_hidden != 64 || c->nn_layers > 7))
+      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 7");
   }
   if (c->solver == HODE_SOLVER_DOPRI5 && (!(c->rtol > 0) || !(c->atol >= 0)))
     return fail(HODE_E_SIZE, "rtol must be > 0 and atol >= 0");
@@ -146,10 +156,10 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
   if (cfg->n_traj == 0) return 0;
   hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
   A.traj = traj; A.status = status; A.counters = counters;
+  const Workspace w = fwd_workspace(cfg);
+  if (w.total > 0 && (!workspace || workspace_bytes < w.total))
+    return fail(HODE_E_WORKSPACE, "workspace missing or smaller than hode_workspace_bytes()");
   if (cfg->save_steps) {
-    const Workspace w = fwd_workspace(cfg);
-    if (!workspace || workspace_bytes < w.total)
-      return fail(HODE_E_WORKSPACE, "workspace missing or smaller than hode_workspace_bytes()");
     char* base = (char*)workspace;
     A.save_n = (int32_t*)(base + w.off_n);
     A.save_t = (double*)(base + w.off_t);
@@ -162,7 +172,7 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
   if (cfg->mlp == HODE_MLP_NONE || cfg->mlp == HODE_MLP_FP32) {
     e = hode::launch_rollout_simt(A, cfg->mlp, st);
   } else {
-    return fail(HODE_E_UNSUPPORTED, "tensor-core MLP path is not built into this library");
+    e = hode::launch_rollout_tc(A, cfg->mlp, (char*)workspace + w.off_tc, st);
   }
   if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_fwd launch");
   return 0;
@@ -207,6 +217,7 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   rc = check_inputs(cfg, u_meal_h, u_tvns_h, u_gd_h, W_h);
   if (rc) return rc;
   if (cfg->save_steps) return fail(HODE_E_UNSUPPORTED, "save_steps is not available on the host entry");
+  const Workspace wsp = fwd_workspace(cfg);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t B = cfg->n_traj, T = cfg->n_obs, S = cfg->n_samples;
   const size_t P = cfg->mlp != HODE_MLP_NONE ? hode_mlp_param_count(cfg->nn_hidden, cfg->nn_layers) : 0;
@@ -225,6 +236,7 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   o_traj = off; off = align_up(off + sz_traj, 256);
   o_st = off; off = align_up(off + sz_st, 256);
   o_cn = off; off = align_up(off + sz_cn, 256);
+  const size_t o_ws = off; off = align_up(off + wsp.total, 256);
   char* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, off ? off : 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
@@ -240,7 +252,8 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
                         ub[0] ? (float*)(d + o_u[0]) : nullptr, ub[1] ? (float*)(d + o_u[1]) : nullptr,
                         ub[2] ? (float*)(d + o_u[2]) : nullptr, (float*)(d + o_th),
                         sz_W ? (float*)(d + o_W) : nullptr, (float*)(d + o_traj),
-                        (int32_t*)(d + o_st), (int32_t*)(d + o_cn), nullptr, 0, stream);
+                        (int32_t*)(d + o_st), (int32_t*)(d + o_cn), wsp.total ? d + o_ws : nullptr,
+                        wsp.total, stream);
   if (rc) { cudaFreeAsync(d, st); cudaStreamSynchronize(st); return rc; }
   if (sz_traj && (e = cudaMemcpyAsync(traj_h, d + o_traj, sz_traj, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
   if (status_h && sz_st && (e = cudaMemcpyAsync(status_h, d + o_st, sz_st, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;

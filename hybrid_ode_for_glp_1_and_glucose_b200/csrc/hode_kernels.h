@@ -15,4 +15,8 @@ cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t
 cudaError_t launch_rhs(const RolloutArgs& A, int mlp_mode, const float* t, const float* state,
                        float* out, cudaStream_t stream);
 
+// 128-trajectory tiles, MLP on tcgen05 tensor cores (hode_rollout_tc.cu)
+size_t tc_workspace_bytes(int S, int L);
+cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspace, cudaStream_t stream);
+
 }  // namespace hode

@@ -1,0 +1,777 @@
+// hode_rollout_tc.cu — the tensor-core rollout: RK stages of 128 trajectories in lock-step,
+// residual MLP as a chain of tcgen05 TF32 MMAs with activations and accumulators in TMEM.
+//
+// BASELINE.json north_star items (1)+(2): the Dormand-Prince / RK4 stepper state (6-state
+// mechanistic RHS, stage vectors, error norm, per-trajectory step control) lives in registers,
+// one trajectory per thread; the 9->64->..->64->6 MLP of every RK stage is evaluated for a
+// TILE of 128 trajectories as dense [128 x K] x [K x N] contractions on the 5th-gen tensor
+// cores.  Replaces reference models/hybrid_ode_nn.py:184-256 + models/nn_residual.py:136-146.
+//
+// CTA = 2 tiles x 128 threads (persistent, one CTA per SM).  Per tile, TMEM columns:
+//   [0,64) accumulator D0 | [64,128) A_hi | [128,192) A_lo | [192,256) accumulator D1
+// Per layer:  epilogue threads read D (tcgen05.ld), add bias, ReLU, split into TF32 hi/lo
+// (round-to-nearest) and write the next layer's A operand straight back to TMEM
+// (tcgen05.st); one elected thread issues  D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32,
+// fp32-equivalent accuracy; single pass in HODE_MLP_TF32 mode) with B = pre-split weights in
+// shared memory (K-major, no swizzle), then tcgen05.commit -> mbarrier.  The two tiles of a
+// CTA run out of phase, so one tile's epilogue overlaps the other tile's MMAs.
+// Weights are staged once per (CTA, parameter set) with one bulk async copy (TMA engine) of a
+// pre-split image built by prep_tc_image_kernel.
+// Trajectories are pulled lane by lane from a global queue, so a lane that finishes early
+// (adaptive steps diverge 5x between trajectories) is refilled instead of idling.
+#include <math.h>
+
+#include "hode_common.cuh"
+#include "hode_kernels.h"
+#include "hode_tcgen05.cuh"
+
+namespace hode {
+
+namespace {
+constexpr int TILE = 128;
+constexpr int TILES_PER_CTA = 2;
+constexpr int H = 64;
+constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_D1 = 192, TM_TILE_STRIDE = 256;
+}  // namespace
+
+// ---- weight image ----------------------------------------------------------------------------------
+// floats: [L0: Bhi 4x64x4, Blo][hidden l=1..L-1: Bhi 16x64x4, Blo][out: Bhi 16x16x4, Blo]
+//         [bias: L x 64][bias_out: 16]
+// B chunk-major: element (n, k) of an [N, K] weight at float ((k/4)*N + n)*4 + k%4.
+int tc_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024 + L * 64 + 16; }
+
+__global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
+                                     int img_floats) {
+  const float* w = W + (size_t)blockIdx.x * P;
+  float* out = img + (size_t)blockIdx.x * img_floats;
+  for (int i = threadIdx.x; i < img_floats; i += blockDim.x) out[i] = 0.f;
+  __syncthreads();
+  int n_in = HODE_NN_IN;
+  float* dst = out;
+  float* bias_dst = out + 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024;
+  for (int l = 0; l <= L; ++l) {
+    const int n_out = (l == L) ? NS : H;
+    const int Npad = (l == L) ? 16 : H;
+    const int Kpad = (l == 0) ? 16 : H;
+    const int part = (Kpad / 4) * Npad * 4;
+    for (int i = threadIdx.x; i < n_out * n_in; i += blockDim.x) {
+      const int n = i / n_in, k = i - n * n_in;
+      uint32_t hi, lo;
+      tc::split_tf32(w[i], hi, lo);
+      const int o = ((k >> 2) * Npad + n) * 4 + (k & 3);
+      dst[o] = __uint_as_float(hi);
+      dst[part + o] = __uint_as_float(lo);
+    }
+    for (int j = threadIdx.x; j < n_out; j += blockDim.x) bias_dst[j] = w[n_out * n_in + j];
+    w += n_out * n_in + n_out;
+    dst += 2 * part;
+    bias_dst += (l == L) ? 16 : H;
+    n_in = n_out;
+  }
+}
+
+// ---- per-tile context -------------------------------------------------------------------------------
+struct TileCtx {
+  const float* img;     // shared-memory weight image
+  uint64_t* mma_bar;    // this tile's MMA-complete mbarrier
+  uint32_t tmem;        // this tile's TMEM column base (lane field 0)
+  uint32_t lane_base;   // (warp%4)*32 << 16
+  uint32_t parity;      // mbarrier phase to wait for next
+  int bar_id;           // named barrier id of the tile
+  int ttid;             // thread index inside the tile
+  int L;                // hidden layer count
+};
+
+__device__ __forceinline__ void tile_sync(const TileCtx& c) {
+  asm volatile("bar.sync %0, 128;" ::"r"(c.bar_id) : "memory");
+}
+
+// Issue the MMAs of one layer (one elected thread): D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// The two correction products are accumulated FIRST, into a still-small accumulator: the tensor
+// core truncates when it adds into D, and measured on B200 (csrc/probe/tc_probe.cu) this order
+// gives max err/sum|a*b| = 1.7e-7 (a plain fp32 FMA chain gives 2.2e-7), against 4.5e-7 when the
+// products are interleaved per k-step and 6.9e-7 when the large product goes first.
+template <bool X3, int N, int KSTEPS>
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t b_hi,
+                                            uint32_t b_lo) {
+  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
+  constexpr uint32_t lbo16 = (uint32_t)N;                 // (N*16 bytes) >> 4
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+  const uint32_t lo_hi = ((b_hi >> 4) & 0x3FFFu) | (lbo16 << 16);
+  const uint32_t lo_lo = ((b_lo >> 4) & 0x3FFFu) | (lbo16 << 16);
+  if (X3) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      tc::mma_tf32_ts(d, alo + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
+                      idesc, ks == 0 ? 0u : 1u);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lo + (uint32_t)ks * 2u * lbo16),
+                      idesc, 1u);
+  }
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
+                    idesc, (!X3 && ks == 0) ? 0u : 1u);
+}
+
+// bias + ReLU + TF32 split of 32 accumulator columns, in place: v -> hi bits, lo -> lo bits.
+// Both parts are rounded to nearest TF32 (the tensor core would truncate), so a ~= hi + lo to 2^-22.
+template <bool X3>
+__device__ __forceinline__ void epilogue32(uint32_t* v, uint32_t* lo, const float* bias) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j4 * 4 + q;
+      const float a = fmaxf(__uint_as_float(v[j]) + bb[q], 0.f);
+      const uint32_t h = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
+      v[j] = h;
+      if (X3) lo[j] = (__float_as_uint(a - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
+    }
+  }
+}
+
+// The residual MLP for the 128 trajectories of a tile (reference models/nn_residual.py:136-146).
+// Every thread of the tile must call this converged.  x: the 9 input features of this thread's
+// trajectory; r: the 6 residuals.
+template <bool X3>
+__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r) {
+  const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
+  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
+  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
+  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+  const float* img = c.img;
+  const uint32_t img_s = tc::smem_u32(img);
+  const float* bias = img + 2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024;
+  // ---- layer 0 operand: 9 features zero-padded to K = 16 ----------------------------------------
+  {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < HODE_NN_IN) tc::split_tf32(x[k], hi[k], lo[k]);
+      else { hi[k] = 0u; lo[k] = 0u; }
+    }
+    HODE_TMEM_ST_X16(t_ahi, hi);
+    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
+  }
+  tc::wait_st();
+  tc::fence_before_sync();
+  tile_sync(c);
+  if (c.ttid == 0) {
+    tc::fence_after_sync();
+    issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, img_s, img_s + 1024 * 4);
+    tc::mma_commit(c.mma_bar);
+  }
+  uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
+  // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
+#pragma unroll 1
+  for (int l = 0; l < c.L; ++l) {
+    const bool last = (l + 1 == c.L);
+    const uint32_t b_hi = img_s + w_off * 4;
+    const uint32_t b_lo = b_hi + (last ? 1024u : 4096u) * 4u;
+    tc::mbar_wait(c.mma_bar, c.parity);
+    c.parity ^= 1u;
+    tc::fence_after_sync();
+    uint32_t v0[32], v1[32], lo[32];
+    HODE_TMEM_LD_X32(t_d, v0);
+    HODE_TMEM_LD_X32(t_d + 32, v1);
+    tc::wait_ld();
+    epilogue32<X3>(v0, lo, bias + l * H);
+    HODE_TMEM_ST_X32(t_ahi, v0);
+    if (X3) HODE_TMEM_ST_X32(t_alo, lo);
+    epilogue32<X3>(v1, lo, bias + l * H + 32);
+    HODE_TMEM_ST_X32(t_ahi + 32, v1);
+    if (X3) HODE_TMEM_ST_X32(t_alo + 32, lo);
+    tc::wait_st();
+    tc::fence_before_sync();
+    tile_sync(c);
+    if (c.ttid == 0) {
+      tc::fence_after_sync();
+      if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
+      else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
+      tc::mma_commit(c.mma_bar);
+    }
+    w_off += 2 * 4096;
+  }
+  // ---- output layer epilogue: 6 of the 16 accumulator columns ------------------------------------
+  tc::mbar_wait(c.mma_bar, c.parity);
+  c.parity ^= 1u;
+  tc::fence_after_sync();
+  {
+    uint32_t v[8];
+    HODE_TMEM_LD_X8(t_d, v);
+    tc::wait_ld();
+    const float* bo = bias + c.L * H;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) r[i] = __uint_as_float(v[i]) + bo[i];
+  }
+  // The next call overwrites A (tcgen05.st: every MMA has completed) and its layer-0 MMAs write
+  // D only after a tile barrier that every thread reaches after its wait::ld above.
+}
+
+// ---- per-lane trajectory state ---------------------------------------------------------------------
+struct Lane {
+  TrajInputs in;
+  float y[NS], cmp[NS];
+  double t;
+  long unit;          // flat (sample, trajectory) index, -1 = idle
+  float* out;         // this trajectory's [T,6] output rows (or nullptr)
+  int ei;             // next observation index to emit
+  int status, n_acc, n_rej, n_saved;
+  bool has;
+};
+
+__device__ __forceinline__ void store_row6(float* p, const float* y) {
+  float2* q = reinterpret_cast<float2*>(p);
+  q[0] = make_float2(y[0], y[1]);
+  q[1] = make_float2(y[2], y[3]);
+  q[2] = make_float2(y[4], y[5]);
+}
+
+__device__ __forceinline__ float rms6v(const float* v) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) s = fmaf(v[i], v[i], s);
+  return sqrtf(s * (1.0f / NS));
+}
+
+// One evaluation of f_physio + g_NN for this lane (tile-collective).
+template <bool X3>
+__device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln, double te,
+                                          const float* ys, float* d) {
+  const float t32 = (float)te;
+  float meal = 0.f, tvns = 0.f, gd = 0.f;
+  if (ln.has) {
+    int idx = 0;
+    if (any_series(ln.in)) idx = grid_index_from(ln.in, t32, ln.in.cur);
+    meal = input_channel(ln.in, HODE_CH_MEAL, t32, idx);
+    tvns = input_channel(ln.in, HODE_CH_TVNS, t32, idx);
+    gd = input_channel(ln.in, HODE_CH_GD, t32, idx);
+  }
+  float x[HODE_NN_IN], r[NS];
+  x[0] = t32;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[1 + i] = ys[i];
+  x[7] = ys[3];
+  x[8] = tvns;
+  __syncwarp();
+  mlp_tile<X3>(c, x, r);
+  rhs_mech(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) d[i] = __fadd_rn(d[i], r[i]);
+}
+
+__device__ __forceinline__ void lane_bind(Lane& ln, const RolloutArgs& A, const float* t_shared,
+                                          int s, long b) {
+  const long unit = (long)s * A.B + b;
+  ln.unit = unit;
+  ln.has = true;
+  ln.in.T = A.T;
+  ln.in.cur = 0;
+  ln.in.t_obs = A.t_per_traj ? A.t_obs + b * A.T : (t_shared ? t_shared : A.t_obs);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    ln.in.mode[ch] = A.in_mode[ch];
+    ln.in.u[ch] = A.in_mode[ch] == HODE_IN_SERIES ? A.u[ch] + b * A.T
+                : A.in_mode[ch] == HODE_IN_CONST ? A.u[ch] + b : nullptr;
+  }
+  ln.out = A.traj ? A.traj + (size_t)unit * A.T * NS : nullptr;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) { ln.y[i] = A.y0[b * NS + i]; ln.cmp[i] = 0.f; }
+  ln.ei = 0;
+  ln.status = HODE_ST_OK;
+  ln.n_acc = ln.n_rej = ln.n_saved = 0;
+}
+
+__device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A) {
+  const long n_units = (long)A.S * A.B;
+  if (ln.out) {
+    const float z[NS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (; ln.ei < A.T; ++ln.ei) store_row6(ln.out + (size_t)ln.ei * NS, z);
+  }
+  if (A.status) A.status[ln.unit] = ln.status;
+  if (A.counters) {
+    A.counters[ln.unit] = ln.n_acc;
+    A.counters[n_units + ln.unit] = ln.n_rej;
+  }
+  if (A.save_n) A.save_n[ln.unit] = ln.n_saved;
+  ln.has = false;
+  ln.unit = -1;
+}
+
+__device__ __forceinline__ void lane_save_step(Lane& ln, const RolloutArgs& A, double t, float hf) {
+  const long n_units = (long)A.S * A.B;
+  const size_t o = (size_t)ln.n_saved * n_units + ln.unit;
+  A.save_t[o] = t;
+  A.save_h[o] = hf;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) A.save_y[((size_t)ln.n_saved * NS + i) * n_units + ln.unit] = ln.y[i];
+  ++ln.n_saved;
+}
+
+// Bit i set <=> grid point i is a kink of some series input (T <= 64).  Built once per
+// trajectory with independent loads, so the first-touch latency of the input rows is paid with
+// memory-level parallelism instead of one dependent miss per grid point during stepping.
+__device__ __forceinline__ unsigned long long build_kink_mask(const TrajInputs& in) {
+  unsigned long long diff = 0ull;   // bit i: v[i] != v[i+1] in some series channel
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    if (in.mode[ch] != HODE_IN_SERIES) continue;
+    const float* v = in.u[ch];
+#pragma unroll 8
+    for (int i = 0; i + 1 < in.T; ++i)
+      if (v[i] != v[i + 1]) diff |= 1ull << i;
+  }
+  unsigned long long m = (diff | (diff << 1));          // kink(i) = diff(i-1) | diff(i)
+  m &= ~1ull;                                             // i = 0 is never a kink
+  if (in.T >= 1) m &= ~(1ull << (in.T - 1));             // nor is the last point
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The kernel.  grid = number of SMs (persistent), block = 256 threads = 2 tiles.
+// queue[s]: next unclaimed trajectory of parameter set s (zeroed before launch).
+// One "round" = one RK4 step (4 evaluations) or one DP5(4) attempt (6 evaluations) for every lane
+// of the tile; the evaluations of a round go through ONE call site of the tile MLP (slot loop),
+// which keeps the kernel small enough for the instruction cache.
+// ---------------------------------------------------------------------------------------------------
+template <bool X3, int SOLVER>
+__global__ void __launch_bounds__(TILE* TILES_PER_CTA, 1)
+rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_floats, int* queue) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* img = reinterpret_cast<float*>(smem_raw);
+  float* t_sh_buf = img + ((img_floats + 3) & ~3);
+  __shared__ __align__(8) uint64_t mma_bar[TILES_PER_CTA];
+  __shared__ __align__(8) uint64_t load_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int tile_active[TILES_PER_CTA][4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane_id = tid & 31;
+  const int tile = tid >> 7, ttid = tid & 127, wq = warp & 3;
+
+  if (tid == 0) {
+    tc::mbar_init(&mma_bar[0], 1);
+    tc::mbar_init(&mma_bar[1], 1);
+    tc::mbar_init(&load_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  const float* t_shared = nullptr;
+  if (!A.t_per_traj && A.T <= HODE_SIMT_MAX_SHARED_T) {
+    for (int i = tid; i < A.T; i += blockDim.x) t_sh_buf[i] = A.t_obs[i];
+    t_shared = t_sh_buf;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  TileCtx c;
+  c.img = img;
+  c.mma_bar = &mma_bar[tile];
+  c.tmem = tmem_base_s + (uint32_t)tile * TM_TILE_STRIDE;
+  c.lane_base = (uint32_t)(wq * 32) << 16;
+  c.parity = 0;
+  c.bar_id = 1 + tile;
+  c.ttid = ttid;
+  c.L = A.L;
+
+  constexpr int NSLOT = (SOLVER == HODE_SOLVER_RK4) ? 4 : 6;
+  const int T = A.T;
+  const float rtol = A.rtol, atol = A.atol;
+  const int max_steps = A.max_steps > 0 ? A.max_steps : 100000;
+  const int nsub = A.n_substeps > 0 ? A.n_substeps : 1;
+  const bool clip = (A.kink_mode == HODE_KINK_CLIP);
+  uint32_t load_parity = 0;
+
+  for (int si = 0; si < A.S; ++si) {
+    const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
+    // ---- stage this parameter set's weight image (one bulk copy) ------------------------------
+    __syncthreads();  // both tiles are done with the previous image
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)img_floats * 4u;
+      tc::mbar_expect_tx(&load_bar, bytes);
+      tc::bulk_g2s(img, img_g + (size_t)s * img_floats, bytes, &load_bar);
+    }
+    tc::mbar_wait(&load_bar, load_parity);
+    load_parity ^= 1u;
+    const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
+
+    Lane ln;
+    ln.has = false;
+    ln.unit = -1;
+    ln.out = nullptr;
+    ln.ei = 0;
+    ln.status = 0; ln.n_acc = 0; ln.n_rej = 0; ln.n_saved = 0;
+    ln.t = 0.0;
+    ln.in.T = T; ln.in.cur = 0; ln.in.t_obs = A.t_obs;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) { ln.in.mode[ch] = HODE_IN_ABSENT; ln.in.u[ch] = nullptr; }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { ln.y[i] = 0.f; ln.cmp[i] = 0.f; }
+    bool queue_dry = false;
+    // stage vectors: k[0] = k1 (FSAL) ... k[6] = k7;  RK4 uses k[0..3]
+    float k[7][NS];
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+      for (int i = 0; i < NS; ++i) k[j][i] = 0.f;
+    double h_abs = 0.0, t_stop = 0.0, t_bound = 0.0;
+    unsigned long long kink_mask = 0ull;
+    int attempts = 0, kink_cur = 1;
+    bool need_init = false, prev_rejected = false, need_stop = true;
+    int rk_n = 0, rk_ss = 0;
+
+    for (;;) {
+      // ---- refill idle lanes from the global queue (warp-aggregated) --------------------------
+      {
+        const bool want = !ln.has && !queue_dry;
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane_id == leader) base = atomicAdd(&queue[s], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          const long b = (long)base + __popc(m & ((1u << lane_id) - 1u));
+          if (want) {
+            if (b < A.B) {
+              lane_bind(ln, A, t_shared, s, b);
+              ln.t = (double)ln.in.t_obs[0];
+              t_bound = (double)ln.in.t_obs[T - 1];
+              need_init = true; prev_rejected = false; need_stop = true;
+              attempts = 0; kink_cur = 1; h_abs = 0.0;
+              rk_n = 0; rk_ss = 0;
+              if (SOLVER == HODE_SOLVER_RK4) {
+                if (ln.out) store_row6(ln.out, ln.y);
+                ln.ei = 1;
+                if (T < 2) lane_finish(ln, A);
+              } else if (clip && T <= 64 && any_series(ln.in)) {
+                kink_mask = build_kink_mask(ln.in);
+              }
+            } else {
+              queue_dry = true;
+            }
+          }
+        }
+      }
+      // ---- does this tile still have work? ------------------------------------------------------
+      {
+        const bool any = __any_sync(0xffffffffu, ln.has);
+        if (lane_id == 0) tile_active[tile][wq] = any ? 1 : 0;
+        tile_sync(c);
+        const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
+                        tile_active[tile][3];
+        tile_sync(c);
+        if (!go) break;
+      }
+
+      // ---- round set-up ---------------------------------------------------------------------------
+      const bool init = (SOLVER == HODE_SOLVER_DOPRI5) && ln.has && need_init;
+      bool run = ln.has && !init;   // lane performs a real step / attempt this round
+      double t = ln.t, h = 0.0, t_new = ln.t, h0 = 0.0;
+      float hf = 0.f, h0f = 0.f, d1 = 0.f;
+      float sc[NS], ynew[NS], incr[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { sc[i] = 1.f; ynew[i] = ln.y[i]; incr[i] = 0.f; }
+      if (SOLVER == HODE_SOLVER_RK4) {
+        if (run) {
+          const double ta = (double)ln.in.t_obs[rk_n];
+          h = ((double)ln.in.t_obs[rk_n + 1] - ta) / nsub;
+          t = ta + rk_ss * h;
+          t_new = t + h;
+          hf = (float)h;
+          ln.in.cur = rk_n;
+          if (A.save_n && ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
+        }
+      } else if (run) {
+        if (need_stop) {
+          t_stop = t_bound;
+          if (clip && any_series(ln.in)) {
+            if (T <= 64) {
+              unsigned long long m = kink_mask & ~((1ull << kink_cur) - 1ull);
+              while (m) {
+                const int i = __ffsll((long long)m) - 1;
+                if ((double)ln.in.t_obs[i] > t) { t_stop = (double)ln.in.t_obs[i]; kink_cur = i; break; }
+                m &= m - 1ull;
+                kink_cur = i + 1;
+              }
+            } else {
+              while (kink_cur < T - 1 && !((double)ln.in.t_obs[kink_cur] > t && is_kink(ln.in, kink_cur)))
+                ++kink_cur;
+              if (kink_cur < T - 1) t_stop = (double)ln.in.t_obs[kink_cur];
+            }
+          }
+          ln.in.cur = grid_index_from(ln.in, (float)t, ln.in.cur);
+          if (ln.in.cur > 0) --ln.in.cur;
+          need_stop = false;
+        }
+        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+        if (!prev_rejected && h_abs < min_step) h_abs = min_step;
+        if (h_abs < min_step) { ln.status = HODE_ST_STEP_TOO_SMALL; run = false; }
+        else if (attempts >= max_steps) { ln.status = HODE_ST_MAX_STEPS; run = false; }
+        else {
+          ++attempts;
+          t_new = t + h_abs;
+          if (t_new - t_stop > 0) t_new = t_stop;
+          h = t_new - t;
+          h_abs = h;
+          hf = (float)h;
+        }
+      }
+
+      // ---- the evaluations of this round: ONE call site of the tile MLP ------------------------
+#pragma unroll 1
+      for (int slot = 0; slot < NSLOT; ++slot) {
+        float ys[NS], d[NS];
+        double te;
+        if (SOLVER == HODE_SOLVER_RK4) {
+          const float a = (slot == 0) ? 0.f : (slot == 3 ? hf : 0.5f * hf);
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            const float kv = (slot == 1) ? k[0][i] : (slot == 2 ? k[1][i] : k[2][i]);
+            ys[i] = (slot == 0) ? ln.y[i] : fmaf(a, kv, ln.y[i]);
+          }
+          te = (slot == 0) ? t : (slot == 3 ? t + h : t + 0.5 * h);
+        } else {
+          if (slot == 0) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ys[i] = init ? ln.y[i] : fmaf(hf, dp::a21 * k[0][i], ln.y[i]);
+            te = init ? t : t + (double)dp::c2 * h;
+          } else if (slot == 1) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+              ys[i] = init ? fmaf(h0f, k[0][i], ln.y[i])
+                           : fmaf(hf, fmaf(dp::a32, k[1][i], dp::a31 * k[0][i]), ln.y[i]);
+            te = init ? t + h0 : t + (double)dp::c3 * h;
+          } else if (slot == 2) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+              ys[i] = fmaf(hf, fmaf(dp::a43, k[2][i], fmaf(dp::a42, k[1][i], dp::a41 * k[0][i])), ln.y[i]);
+            te = t + (double)dp::c4 * h;
+          } else if (slot == 3) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+              ys[i] = fmaf(hf, fmaf(dp::a54, k[3][i], fmaf(dp::a53, k[2][i], fmaf(dp::a52, k[1][i], dp::a51 * k[0][i]))), ln.y[i]);
+            te = t + (double)dp::c5 * h;
+          } else if (slot == 4) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+              ys[i] = fmaf(hf, fmaf(dp::a65, k[4][i], fmaf(dp::a64, k[3][i], fmaf(dp::a63, k[2][i], fmaf(dp::a62, k[1][i], dp::a61 * k[0][i])))), ln.y[i]);
+            te = t_new;
+          } else {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              incr[i] = hf * fmaf(dp::b6, k[5][i], fmaf(dp::b5, k[4][i], fmaf(dp::b4, k[3][i], fmaf(dp::b3, k[2][i], dp::b1 * k[0][i]))));
+              ynew[i] = ln.y[i] + (incr[i] - ln.cmp[i]);
+              ys[i] = ynew[i];
+            }
+            te = t_new;
+          }
+        }
+        lane_eval<X3>(c, th, ln, te, ys, d);
+        if (SOLVER == HODE_SOLVER_RK4) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            if (slot == 0) k[0][i] = d[i];
+            else if (slot == 1) k[1][i] = d[i];
+            else if (slot == 2) k[2][i] = d[i];
+            else k[3][i] = d[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            if (slot == 0) k[1][i] = d[i];
+            else if (slot == 1) k[2][i] = d[i];
+            else if (slot == 2) k[3][i] = d[i];
+            else if (slot == 3) k[4][i] = d[i];
+            else if (slot == 4) k[5][i] = d[i];
+            else k[6][i] = d[i];
+          }
+          if (init && slot == 0) {
+            // f(t0, y0) -> k1; outputs at t_eval <= t0; first part of select_initial_step
+#pragma unroll
+            for (int i = 0; i < NS; ++i) k[0][i] = d[i];
+            while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t) {
+              if (ln.out) store_row6(ln.out + (size_t)ln.ei * NS, ln.y);
+              ++ln.ei;
+            }
+            float v0[NS], v1[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              sc[i] = atol + fabsf(ln.y[i]) * rtol;
+              v0[i] = ln.y[i] / sc[i];
+              v1[i] = d[i] / sc[i];
+            }
+            const float d0 = rms6v(v0);
+            d1 = rms6v(v1);
+            h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
+            const double interval = t_bound - t;
+            if (h0 > interval) h0 = interval;
+            h0f = (float)h0;
+          } else if (init && slot == 1) {
+            const double interval = t_bound - t;
+            if (interval > 0) {
+              float v0[NS];
+#pragma unroll
+              for (int i = 0; i < NS; ++i) v0[i] = (d[i] - k[0][i]) / sc[i];
+              const float d2 = rms6v(v0) / h0f;
+              double h1;
+              if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmax(1e-6, h0 * 1e-3);
+              else h1 = (double)powf(0.01f / fmaxf(d1, d2), 0.2f);
+              h_abs = fmin(fmin(100.0 * h0, h1), interval);
+            }
+            need_init = false;
+          }
+        }
+      }
+
+      // ---- close the round ----------------------------------------------------------------------------
+      if (SOLVER == HODE_SOLVER_RK4) {
+        if (run) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            const float inc = (hf * (1.0f / 6.0f)) * (k[0][i] + 2.0f * k[1][i] + 2.0f * k[2][i] + k[3][i]);
+            const float yk = inc - ln.cmp[i];
+            const float tn = ln.y[i] + yk;
+            ln.cmp[i] = (tn - ln.y[i]) - yk;
+            ln.y[i] = tn;
+          }
+          ++ln.n_acc;
+          if (++rk_ss == nsub) {
+            rk_ss = 0;
+            ++rk_n;
+            if (ln.out) store_row6(ln.out + (size_t)rk_n * NS, ln.y);
+            ln.ei = rk_n + 1;
+            if (rk_n + 1 >= T) lane_finish(ln, A);
+          }
+        }
+        continue;
+      }
+      if (init) {
+        if (!(t < t_bound)) lane_finish(ln, A);   // T == 1 or zero-length span
+      } else if (ln.has && !run) {
+        lane_finish(ln, A);                         // step too small / budget exhausted
+      } else if (run) {
+        float e2 = 0.f;
+        bool finite = true;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          const float scale = fmaf(fmaxf(fabsf(ln.y[i]), fabsf(ynew[i])), rtol, atol);
+          const float ee = hf * fmaf(dp::e7, k[6][i], fmaf(dp::e6, k[5][i], fmaf(dp::e5, k[4][i], fmaf(dp::e4, k[3][i], fmaf(dp::e3, k[2][i], dp::e1 * k[0][i])))));
+          const float q = ee / scale;
+          e2 = fmaf(q, q, e2);
+          finite = finite && isfinite(ynew[i]);
+        }
+        const float err = sqrtf(e2 * (1.0f / NS));
+        if (err < 1.0f) {
+          float factor = (err == 0.f) ? 10.f : fminf(10.f, 0.9f * powf(err, -0.2f));
+          if (prev_rejected) factor = fminf(1.f, factor);
+          prev_rejected = false;
+          ++ln.n_acc;
+          bool ok = true;
+          if (A.save_n) {
+            if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
+            else { ln.status = HODE_ST_MAX_STEPS; ok = false; }
+          }
+          if (ok) {
+            if (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
+              float Q[NS][4];
+#pragma unroll
+              for (int i = 0; i < NS; ++i) dp::dense_q(k[0][i], k[2][i], k[3][i], k[4][i], k[5][i], k[6][i], Q[i]);
+              while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
+                const double te = (double)ln.in.t_obs[ln.ei];
+                float yo[NS];
+                if (te == t_new) {
+#pragma unroll
+                  for (int i = 0; i < NS; ++i) yo[i] = ynew[i];
+                } else {
+                  const float xq = (float)((te - t) / h);
+#pragma unroll
+                  for (int i = 0; i < NS; ++i) {
+                    const float poly = xq * fmaf(xq, fmaf(xq, fmaf(xq, Q[i][3], Q[i][2]), Q[i][1]), Q[i][0]);
+                    yo[i] = fmaf(hf, poly, ln.y[i]);
+                  }
+                }
+                if (ln.out) store_row6(ln.out + (size_t)ln.ei * NS, yo);
+                ++ln.ei;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              const float yk = incr[i] - ln.cmp[i];
+              ln.cmp[i] = (ynew[i] - ln.y[i]) - yk;
+              ln.y[i] = ynew[i];
+              k[0][i] = k[6][i];
+            }
+            ln.t = t_new;
+            h_abs *= (double)factor;
+            need_stop = true;
+            if (t_new - t_bound >= 0) lane_finish(ln, A);
+          } else {
+            lane_finish(ln, A);
+          }
+        } else {
+          ++ln.n_rej;
+          if (!finite || !(err == err)) {
+            ln.status = HODE_ST_STEP_TOO_SMALL;
+            lane_finish(ln, A);
+          } else {
+            h_abs *= (double)fmaxf(0.2f, 0.9f * powf(err, -0.2f));
+            prev_rejected = true;
+          }
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+size_t tc_workspace_bytes(int S, int L) {
+  return (size_t)S * tc_image_floats(L) * sizeof(float) + 256 + (size_t)S * sizeof(int);
+}
+
+cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspace, cudaStream_t stream) {
+  const int img_floats = tc_image_floats(A.L);
+  float* img = reinterpret_cast<float*>(workspace);
+  int* queue = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
+                                      (((size_t)A.S * img_floats * sizeof(float) + 255) / 256) * 256);
+  cudaError_t e = cudaMemsetAsync(queue, 0, (size_t)A.S * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  prep_tc_image_kernel<<<A.S, 256, 0, stream>>>(A.W, img, A.L, A.P, img_floats);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t smem = (size_t)((img_floats + 3) & ~3) * sizeof(float);
+  if (!A.t_per_traj && A.T <= HODE_SIMT_MAX_SHARED_T) smem += (size_t)A.T * sizeof(float);
+  smem = (smem + 1023) & ~(size_t)1023;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  const long units = (long)A.B;
+  int grid = sms;
+  const long need = (units + TILE * TILES_PER_CTA - 1) / (TILE * TILES_PER_CTA);
+  if (need < grid) grid = (int)(need > 0 ? need : 1);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<grid, TILE * TILES_PER_CTA, smem, stream>>>(A, img, img_floats, queue);
+    return cudaSuccess;
+  };
+  const bool x3 = (mlp_mode == HODE_MLP_TF32X3);
+  if (A.solver == HODE_SOLVER_RK4)
+    e = x3 ? launch(rollout_tc_kernel<true, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<false, HODE_SOLVER_RK4>);
+  else
+    e = x3 ? launch(rollout_tc_kernel<true, HODE_SOLVER_DOPRI5>) : launch(rollout_tc_kernel<false, HODE_SOLVER_DOPRI5>);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+}  // namespace hode

@@ -112,10 +112,15 @@ __global__ void __launch_bounds__(128) gemm_probe(const float* __restrict__ A, c
   for (int i = tid; i < N * K; i += blockDim.x) {
     const int n = i / K, k = i % K;
     const float w = B[i];
-    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    float lo = w - hi;
+    if (mode >= 2) {
+      hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+      lo = __uint_as_float((__float_as_uint(w - hi) + 0x1000u) & 0xFFFFE000u);
+    }
     const int o = ((k >> 2) * N + n) * 4 + (k & 3);
     Bhi[o] = hi;
-    Blo[o] = w - hi;
+    Blo[o] = lo;
   }
   if (tid == 0) mbar_init(&bar, 1);
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
@@ -132,9 +137,14 @@ __global__ void __launch_bounds__(128) gemm_probe(const float* __restrict__ A, c
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float a = A[tid * K + half * 32 + j];
-      const uint32_t h = __float_as_uint(a) & 0xFFFFE000u;
+      uint32_t h = __float_as_uint(a) & 0xFFFFE000u;
+      uint32_t l = __float_as_uint(a - __uint_as_float(h));
+      if (mode >= 2) {
+        h = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
+        l = (__float_as_uint(a - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
+      }
       hi[j] = h;
-      lo[j] = __float_as_uint(a - __uint_as_float(h));
+      lo[j] = l;
     }
     TMEM_ST_X32(tAhi + lane_base + half * 32, hi);
     TMEM_ST_X32(tAlo + lane_base + half * 32, lo);
@@ -147,13 +157,27 @@ __global__ void __launch_bounds__(128) gemm_probe(const float* __restrict__ A, c
     const uint32_t idesc = make_idesc_tf32(M, N);
     const uint32_t bhi = smem_u32(Bhi), blo = smem_u32(Blo);
     uint32_t acc = 0;
-    for (int ks = 0; ks < K / 8; ++ks) {
-      mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc);
-      acc = 1;
-    }
-    if (mode == 1) {
+    if (mode <= 2) {          // hi*hi first, then the corrections
+      for (int ks = 0; ks < K / 8; ++ks) { mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc); acc = 1; }
+      if (mode >= 1) {
+        for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAhi + ks * 8, make_desc(blo + ks * 2 * LBO, LBO, SBO), idesc, 1);
+        for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, 1);
+      }
+    } else if (mode == 3) {   // corrections first (blocks), hi*hi last
+      for (int ks = 0; ks < K / 8; ++ks) { mma_tf32_ts(tD, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc); acc = 1; }
       for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAhi + ks * 8, make_desc(blo + ks * 2 * LBO, LBO, SBO), idesc, 1);
-      for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, 1);
+      for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, 1);
+    } else if (mode == 4) {   // interleaved per k-step
+      for (int ks = 0; ks < K / 8; ++ks) {
+        mma_tf32_ts(tD, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc); acc = 1;
+        mma_tf32_ts(tD, tAhi + ks * 8, make_desc(blo + ks * 2 * LBO, LBO, SBO), idesc, 1);
+        mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, 1);
+      }
+    } else {                  // mode 5: corrections into their own accumulator columns, summed in fp32 afterwards
+      for (int ks = 0; ks < K / 8; ++ks) { mma_tf32_ts(tD, tAhi + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc); acc = 1; }
+      acc = 0;
+      for (int ks = 0; ks < K / 8; ++ks) { mma_tf32_ts(tD + 192, tAlo + ks * 8, make_desc(bhi + ks * 2 * LBO, LBO, SBO), idesc, acc); acc = 1; }
+      for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(tD + 192, tAhi + ks * 8, make_desc(blo + ks * 2 * LBO, LBO, SBO), idesc, 1);
     }
     mma_commit(&bar);
   }
@@ -163,6 +187,13 @@ __global__ void __launch_bounds__(128) gemm_probe(const float* __restrict__ A, c
   for (int half = 0; half < 2; ++half) {
     TMEM_LD_X32(tD + lane_base + half * 32, r);
     tmem_wait_ld();
+    if (mode == 5) {
+      uint32_t r2[32];
+      TMEM_LD_X32(tD + 192 + lane_base + half * 32, r2);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) D[tid * N + half * 32 + j] = __uint_as_float(r[j]);
   }
@@ -282,16 +313,17 @@ int main() {
   for (auto& x : hB) x = ((float)rand() / RAND_MAX - 0.5f) * 0.5f;
   float *dA, *dB, *dD;
   CK(cudaMalloc(&dA, hA.size() * 4)); CK(cudaMalloc(&dB, hB.size() * 4)); CK(cudaMalloc(&dD, hD.size() * 4));
+  for (auto& x : hA) x = fabsf(x) * 0.01f;
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
   const size_t smem = 2 * N * K * sizeof(float);
   CK(cudaFuncSetAttribute(gemm_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  for (int mode = 0; mode < 2; ++mode) {
+  for (int mode = 0; mode < 6; ++mode) {
     CK(cudaMemset(dD, 0, hD.size() * 4));
     gemm_probe<<<1, 128, smem>>>(dA, dB, dD, mode);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
-    double max_rel = 0, max_abs = 0, max_rel_f32 = 0;
+    double max_rel = 0, max_abs = 0, max_rel_f32 = 0, sum_signed = 0, sum_abs = 0;
     for (int m = 0; m < M; ++m)
       for (int n = 0; n < N; ++n) {
         double ref = 0, mag = 0;
@@ -305,17 +337,16 @@ int main() {
         max_abs = fmax(max_abs, err);
         max_rel = fmax(max_rel, err / mag);
         max_rel_f32 = fmax(max_rel_f32, fabs(ref32 - ref) / mag);
+        sum_signed += (hD[m * N + n] - ref) / mag;
+        sum_abs += err / mag;
       }
-    printf("gemm mode %d (%s): max |err| %.3e, max err/sum|a*b| %.3e  (plain fp32 fma chain: %.3e)  D[0][0]=%f D[127][63]=%f\n",
-           mode, mode ? "3xTF32" : "1xTF32", max_abs, max_rel, max_rel_f32, hD[0], hD[M * N - 1]);
+    const char* names[6] = {"1xTF32 trunc", "3x trunc, hi first", "3x RN, hi first", "3x RN, lo blocks first", "3x RN, interleaved/k", "3x RN, separate acc"};
+    printf("gemm mode %d (%-24s): max err/sum|a*b| %.3e  mean |err| %.3e  mean signed %.3e  (fp32 fma chain max: %.3e)\n",
+           mode, names[mode], max_rel, sum_abs / (M * N), sum_signed / (M * N), max_rel_f32);
   }
   float* dout;
   CK(cudaMalloc(&dout, 148 * 512 * 4));
   const int iters = 20000;
-  run_chain<1, 1>(dB, dout, iters, "chain 1xTF32");
-  run_chain<2, 1>(dB, dout, iters, "chain 1xTF32");
-  run_chain<4, 1>(dB, dout, iters, "chain 1xTF32 (hi only)");
-  run_chain<1, 3>(dB, dout, iters, "chain 3xTF32");
   run_chain<2, 3>(dB, dout, iters, "chain 3xTF32");
   printf("probe done\n");
   return 0;

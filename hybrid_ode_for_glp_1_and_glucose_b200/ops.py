@@ -119,6 +119,13 @@ def _expected_param_count(hidden: int, layers: int) -> int:
     return 9 * hidden + hidden + (layers - 1) * (hidden * hidden + hidden) + hidden * 6 + 6
 
 
+def workspace_bytes(cfg) -> Tuple[int, int]:
+    fwd, bwd = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.check(_lib.lib().hode_workspace_bytes(ctypes.byref(cfg), ctypes.byref(fwd),
+                                               ctypes.byref(bwd)), "hode_workspace_bytes")
+    return int(fwd.value), int(bwd.value)
+
+
 def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
             theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
             solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
@@ -147,10 +154,12 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
         traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
         status = torch.empty((S, B), dtype=torch.int32, device=device)
         counters = torch.empty((2, S, B), dtype=torch.int32, device=device)
+        ws_bytes = workspace_bytes(cfg)[0]
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
         rc = 0 if B == 0 else _lib.lib().hode_rollout_fwd(
             ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
             _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
-            _ptr(traj), _ptr(status), _ptr(counters), None, 0, _stream(device))
+            _ptr(traj), _ptr(status), _ptr(counters), _ptr(ws), ws_bytes, _stream(device))
     _lib.check(rc, "hode_rollout_fwd")
     if squeeze_s:
         return traj[0], RolloutInfo(status[0], counters[0, 0], counters[1, 0])

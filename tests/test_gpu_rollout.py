@@ -283,3 +283,80 @@ def test_module_forward_contract(dev, caplog):
     assert bool((bad[:, -1] == 0).all())
     with pytest.raises(Exception):
         m(torch.from_numpy(y0), torch.from_numpy(t), tin, solver="radau")
+
+
+# ---------------------------------------------------------------------------- tensor-core MLP path
+@pytest.mark.parametrize("layers", [4, 2, 1])
+def test_tc_rk4_parity(dev, oracle, layers):
+    """tcgen05 3xTF32 path: same <= 1e-5 relative bar as the FP32 CUDA-core path."""
+    y0, t, ins = cohort(700, seed=21)                      # not a multiple of the 128-row tile
+    W = random_mlp(64, layers, seed=22)
+    theta = oracle.THETA_DEFAULT
+    ref, _, _, _ = oracle.rollout(y0, t, ins, theta, W, 64, layers, solver="rk4", n_substeps=2,
+                                  n_threads=8)
+    tr, st, na, _ = gpu_rollout(dev, y0, t, ins, theta, W, 64, layers, solver="rk4", n_substeps=2,
+                                precision="tf32x3")
+    assert (st == 0).all() and (na == 120).all()
+    assert rel_err(tr, ref) < 1e-5, rel_err_report(tr, ref)
+    # and it agrees with the FP32 CUDA-core kernel to the same level
+    tr32, _, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, 64, layers, solver="rk4", n_substeps=2)
+    assert rel_err(tr, tr32) < 2e-5, rel_err_report(tr, tr32)   # two kernels, each <= 1e-5 from the oracle
+    # single-pass TF32 is the documented fast/approximate mode
+    trf, st, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, 64, layers, solver="rk4", n_substeps=2,
+                                precision="tf32")
+    assert (st == 0).all()
+    e = rel_err(trf, ref)
+    assert 1e-7 < e < 2e-2, e
+
+
+def test_tc_dopri5_accuracy_and_refill(dev, oracle):
+    y0, t, ins = cohort(1500, seed=23)
+    W = random_mlp(seed=24, out_std=0.02)
+    theta = oracle.THETA_DEFAULT
+    truth, _, _, _ = oracle.rollout(y0, t, ins, theta, W, rhs="f64", rtol=1e-11, atol=1e-13,
+                                    kinks="clip", n_threads=8)
+    truth = truth.astype(np.float64)
+    orc, _, cn, _ = oracle.rollout(y0, t, ins, theta, W, kinks="clip", n_threads=8)
+    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip",
+                                 precision="tf32x3")
+    assert (st == 0).all()
+    sc = 1e-8 + 1e-6 * np.abs(truth)
+    e_gpu = (np.abs(tr - truth) / sc).max(axis=(1, 2))
+    e_cpu = (np.abs(orc - truth) / sc).max(axis=(1, 2))
+    assert np.median(e_gpu) < 2 * np.median(e_cpu) + 50
+    assert np.percentile(e_gpu, 90) < 3 * np.percentile(e_cpu, 90) + 100
+    att_gpu, att_cpu = (na + nr).mean(), (cn[0] + cn[1]).mean()
+    assert abs(att_gpu - att_cpu) / att_cpu < 0.2
+    assert np.array_equal(tr[:, 0], y0)
+    # lanes are refilled in arbitrary order, yet every trajectory is deterministic
+    tr2, _, na2, nr2 = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip",
+                                   precision="tf32x3")
+    assert np.array_equal(tr, tr2) and np.array_equal(na, na2) and np.array_equal(nr, nr2)
+
+
+def test_tc_layouts_failure_and_sweep(dev, oracle):
+    rng = np.random.default_rng(25)
+    B, T = 333, 25
+    y0, _, _ = cohort(B, T, seed=25)
+    t = np.sort(np.linspace(0, 2, T)[None] + rng.uniform(-0.02, 0.02, (B, T)), axis=1).astype(np.float32)
+    ins = {"meal": (rng.uniform(0, 1, (B, T)) > 0.8).astype(np.float32),
+           "tVNS": (rng.uniform(0, 1, B) > 0.5).astype(np.float32)}
+    S = 3
+    thetas = np.stack([oracle.THETA_DEFAULT * (1 + 0.05 * s) for s in range(S)]).astype(np.float32)
+    Ws = np.stack([random_mlp(seed=30 + s) for s in range(S)])
+    tr, st, _, _ = gpu_rollout(dev, y0, t, ins, thetas, Ws, solver="rk4", n_substeps=3,
+                               precision="tf32x3")
+    assert tr.shape == (S, B, T, 6) and (st == 0).all()
+    for s in range(S):
+        ref, _, _, _ = oracle.rollout(y0, t, ins, thetas[s], Ws[s], solver="rk4", n_substeps=3,
+                                      n_threads=8)
+        assert rel_err(tr[s], ref) < 1e-5, rel_err_report(tr[s], ref)
+    # failure path: status + zero padding, T == 1
+    theta = oracle.THETA_DEFAULT.copy()
+    theta[16] = 1e6
+    trf, stf, _, _ = gpu_rollout(dev, y0[:50], t[0], None, theta, Ws[0], solver="dopri5",
+                                 max_steps=3000, precision="tf32x3")
+    assert (stf != 0).all() and (trf[:, -1] == 0).all() and np.array_equal(trf[:, 0], y0[:50])
+    tr1, st1, _, _ = gpu_rollout(dev, y0[:5], t[0, :1], None, oracle.THETA_DEFAULT, Ws[0],
+                                 solver="dopri5", precision="tf32x3")
+    assert tr1.shape == (5, 1, 6) and np.array_equal(tr1[:, 0], y0[:5]) and (st1 == 0).all()
