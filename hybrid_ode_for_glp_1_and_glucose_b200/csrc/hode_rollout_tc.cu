@@ -78,7 +78,7 @@ struct TileCtx {
   uint32_t lane_base;   // (warp%4)*32 << 16
   uint32_t parity;      // mbarrier phase to wait for next
   int bar_id;           // named barrier id of the tile
-  int ttid;             // thread index inside the tile
+  int wq;               // warp index inside the tile (warp-uniform)
   int L;                // hidden layer count
 };
 
@@ -160,10 +160,13 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r) {
   tc::wait_st();
   tc::fence_before_sync();
   tile_sync(c);
-  if (c.ttid == 0) {
-    tc::fence_after_sync();
-    issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, img_s, img_s + 1024 * 4);
-    tc::mma_commit(c.mma_bar);
+  if (c.wq == 0) {
+    if (tc::elect_one()) {
+      tc::fence_after_sync();
+      issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, img_s, img_s + 1024 * 4);
+      tc::mma_commit(c.mma_bar);
+    }
+    __syncwarp();
   }
   uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
   // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
@@ -188,11 +191,14 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r) {
     tc::wait_st();
     tc::fence_before_sync();
     tile_sync(c);
-    if (c.ttid == 0) {
-      tc::fence_after_sync();
-      if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
-      else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
-      tc::mma_commit(c.mma_bar);
+    if (c.wq == 0) {
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
+        else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
+        tc::mma_commit(c.mma_bar);
+      }
+      __syncwarp();
     }
     w_off += 2 * 4096;
   }
@@ -349,8 +355,11 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   __shared__ uint32_t tmem_base_s;
   __shared__ int tile_active[TILES_PER_CTA][4];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane_id = tid & 31;
-  const int tile = tid >> 7, ttid = tid & 127, wq = warp & 3;
+  const int tid = threadIdx.x, lane_id = tid & 31;
+  // warp-uniform by construction; the shuffle lets ptxas keep everything derived from it
+  // (tile, TMEM base, barrier ids) in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int tile = warp >> 2, wq = warp & 3;
 
   if (tid == 0) {
     tc::mbar_init(&mma_bar[0], 1);
@@ -375,7 +384,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   c.lane_base = (uint32_t)(wq * 32) << 16;
   c.parity = 0;
   c.bar_id = 1 + tile;
-  c.ttid = ttid;
+  c.wq = wq;
   c.L = A.L;
 
   constexpr int NSLOT = (SOLVER == HODE_SOLVER_RK4) ? 4 : 6;

@@ -13,6 +13,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// Warp-uniform election of one lane (PTX elect.sync).  tcgen05.mma must be issued from
+// warp-uniform control flow with warp-uniform operands: from a per-thread branch such as
+// `if (threadIdx.x == 0)` ptxas wraps EVERY UTCHMMA in an ELECT / R2UR.BROADCAST loop, which
+// was measured (ncu, profiles/) to cost ~100 cycles per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
