@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hybrid_fwd", choices=["hybrid_fwd", "mech_rk4"])
     ap.add_argument("--traj-per-gpu", type=int, default=0)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     return ap.parse_args()
@@ -304,11 +304,16 @@ def run_ours(args):
                 bound = "fp32"
             else:
                 peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
-                peak_src = "TF32 dense = measured sustained bf16 / 2 (MEASURED_PEAKS.json)"
+                peak_src = ("TF32 dense = measured sustained cuBLAS bf16 / 2 (MEASURED_PEAKS.json "
+                            "bf16_tflops_sustained; the kernel is timed inside a long step). achieved "
+                            "counts ALGORITHMIC flops (158 976 + 700 per attempt); the 3xTF32 "
+                            "emulation issues 3 tensor passes per algorithmic pass"
+                            if peaks else "fallback 1400/2 TFLOP/s")
                 bound = "tensor"
             roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "kernel": "rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel",
+                    "kernel": "rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel<x3,dopri5>",
+                    "tensor_passes_per_algorithmic_pass": 3 if args.precision == "tf32x3" else 1,
                     "kernel_ms": ms_kernel,
                     "algorithmic_flop_per_launch": flops}
         else:
