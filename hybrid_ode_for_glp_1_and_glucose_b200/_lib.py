@@ -12,7 +12,7 @@ from typing import Optional
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libhode.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 N_STATE, N_THETA, NN_IN = 6, 17, 9
 SOLVER_RK4, SOLVER_DOPRI5 = 0, 1
 IN_ABSENT, IN_CONST, IN_SERIES = 0, 1, 2
@@ -29,7 +29,7 @@ STATUS_TEXT = {
 
 EXPORTS = [
     "hode_version", "hode_last_error_string", "hode_mlp_param_count", "hode_workspace_bytes",
-    "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs",
+    "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs", "hode_rhs_vjp",
     "hode_rollout_fwd_host",
 ]
 
@@ -79,7 +79,10 @@ def lib() -> ctypes.CDLL:
     L.hode_rollout_fwd.restype = ctypes.c_int
     L.hode_rollout_fwd.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 11 + [ctypes.c_size_t, _P]
     L.hode_rollout_bwd.restype = ctypes.c_int
-    L.hode_rollout_bwd.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12 + [ctypes.c_size_t, _P]
+    L.hode_rollout_bwd.argtypes = ([ctypes.POINTER(HodeCfg)] + [_P] * 11
+                                   + [_P, ctypes.c_size_t, _P, ctypes.c_size_t, _P])
+    L.hode_rhs_vjp.restype = ctypes.c_int
+    L.hode_rhs_vjp.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12 + [ctypes.c_size_t, _P]
     L.hode_vi_predictive.restype = ctypes.c_int
     L.hode_vi_predictive.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12
     L.hode_rhs.restype = ctypes.c_int

@@ -55,3 +55,38 @@ def rhs(t, state, inputs: Optional[Dict[str, torch.Tensor]], theta, W, hidden, l
 def nn_only(t, state, tvns, W, hidden, layers):
     dummy_theta = torch.zeros(_lib.N_THETA, dtype=torch.float32, device=_dev(state, W))
     return _Rhs.apply(t, state, dummy_theta, W, None, tvns, None, hidden, layers, 1)
+
+
+class _Rollout(torch.autograd.Function):
+    """Batched IVP solve with a through-solver gradient: forward = hode_rollout_fwd with the
+    accepted steps recorded, backward = hode_rollout_bwd (discrete adjoint, step sizes frozen).
+    The reference's forward returns a graph-free tensor (models/hybrid_ode_nn.py:248); this is
+    the gradient path BASELINE.json's north_star item (3) adds."""
+
+    @staticmethod
+    def forward(ctx, y0, theta, W, t_obs, meal, tvns, gd, opts):
+        device = _dev(y0, theta, W, t_obs)
+        inputs = {"meal": meal, "tVNS": tvns, "GD": gd}
+        traj, info, tape = ops.rollout(y0, t_obs, inputs, theta, W, device=device, save_steps=True,
+                                       **{k: v for k, v in opts.items() if k != "info"})
+        opts["info"] = info
+        ctx.tape = tape
+        ctx.has_W = W is not None
+        return traj
+
+    @staticmethod
+    def backward(ctx, grad_traj):
+        g_y0, g_theta, g_W = ops.rollout_bwd(ctx.tape, grad_traj, need_y0=ctx.needs_input_grad[0])
+        return (g_y0 if ctx.needs_input_grad[0] else None,
+                g_theta if ctx.needs_input_grad[1] else None,
+                g_W if (ctx.has_W and ctx.needs_input_grad[2]) else None,
+                None, None, None, None, None)
+
+
+def rollout(y0, t_obs, inputs: Optional[Dict[str, torch.Tensor]], theta, W, **opts):
+    """Differentiable rollout; returns (traj, RolloutInfo).  opts: hidden, layers, solver, rtol,
+    atol, n_substeps, kinks, precision, max_steps, max_saved_steps."""
+    inputs = inputs or {}
+    traj = _Rollout.apply(y0, theta, W, t_obs, inputs.get("meal"), inputs.get("tVNS"),
+                          inputs.get("GD"), opts)
+    return traj, opts.get("info")

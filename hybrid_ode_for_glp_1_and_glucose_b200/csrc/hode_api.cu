@@ -135,12 +135,20 @@ int64_t hode_mlp_param_count(int32_t H, int32_t L) {
   return n;
 }
 
+static hode::AdjPlan bwd_plan(const hode_cfg* c) {
+  const bool has_nn = c->mlp != HODE_MLP_NONE;
+  const int P = has_nn ? (int)hode_mlp_param_count(c->nn_hidden, c->nn_layers) : 0;
+  return hode::adj_plan(c->n_traj, c->n_samples, has_nn ? c->nn_hidden : 0, has_nn ? c->nn_layers : 0,
+                        P, has_nn, c->n_obs, c->t_per_traj, 7);
+}
+
 int hode_workspace_bytes(const hode_cfg* cfg, size_t* fwd_bytes, size_t* bwd_bytes) {
   int rc = validate(cfg);
   if (rc) return rc;
   const Workspace w = fwd_workspace(cfg);
   if (fwd_bytes) *fwd_bytes = w.total;
-  if (bwd_bytes) *bwd_bytes = 0;
+  // gradient scratch (per-CTA partial gradients + activation stash); also covers hode_rhs_vjp
+  if (bwd_bytes) *bwd_bytes = hode::adj_workspace_bytes(bwd_plan(cfg));
   return 0;
 }
 
@@ -178,10 +186,68 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
   return 0;
 }
 
-int hode_rollout_bwd(const hode_cfg*, const float*, const float*, const float*, const float*,
-                     const float*, const float*, const float*, const float*, float*, float*,
-                     float*, void*, size_t, void*) {
-  return fail(HODE_E_UNSUPPORTED, "hode_rollout_bwd: not built yet");
+int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, const float* u_meal,
+                     const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+                     const float* grad_traj, float* grad_y0, float* grad_theta, float* grad_W,
+                     const void* fwd_workspace_ptr, size_t fwd_workspace_bytes, void* bwd_workspace,
+                     size_t bwd_workspace_bytes, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!t_obs || !theta || !grad_traj) return fail(HODE_E_NULL, "t_obs/theta/grad_traj is NULL");
+  (void)y0;
+  rc = check_inputs(cfg, u_meal, u_tvns, u_gd, W);
+  if (rc) return rc;
+  if (!cfg->save_steps)
+    return fail(HODE_E_UNSUPPORTED, "hode_rollout_bwd needs the forward pass to run with save_steps = 1");
+  const Workspace w = fwd_workspace(cfg);
+  if (!fwd_workspace_ptr || fwd_workspace_bytes < w.total)
+    return fail(HODE_E_WORKSPACE, "forward workspace missing or smaller than hode_workspace_bytes()");
+  const hode::AdjPlan plan = bwd_plan(cfg);
+  if (plan.smem > 227 * 1024)
+    return fail(HODE_E_UNSUPPORTED, "network too large for the shared-memory gradient accumulators");
+  if (!bwd_workspace || bwd_workspace_bytes < hode::adj_workspace_bytes(plan))
+    return fail(HODE_E_WORKSPACE, "backward workspace missing or smaller than hode_workspace_bytes()");
+  if (cfg->n_traj == 0) return 0;
+  hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
+  char* base = (char*)fwd_workspace_ptr;
+  A.save_n = (int32_t*)(base + w.off_n);
+  A.save_t = (double*)(base + w.off_t);
+  A.save_h = (float*)(base + w.off_h);
+  A.save_y = (float*)(base + w.off_y);
+  A.max_saved = w.max_saved;
+  cudaError_t e = hode::launch_rollout_bwd(A, cfg->mlp != HODE_MLP_NONE, grad_traj, grad_y0, grad_theta,
+                                           grad_W, bwd_workspace, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_bwd launch");
+  return 0;
+}
+
+int hode_rhs_vjp(const hode_cfg* cfg, const float* t, const float* state, const float* u_meal,
+                 const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+                 const float* grad_out, float* grad_state, float* grad_theta, float* grad_W,
+                 void* bwd_workspace, size_t bwd_workspace_bytes, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!t || !state || !theta || !grad_out) return fail(HODE_E_NULL, "t/state/theta/grad_out is NULL");
+  rc = check_inputs(cfg, u_meal, u_tvns, u_gd, W);
+  if (rc) return rc;
+  if (cfg->n_samples != 1) return fail(HODE_E_UNSUPPORTED, "hode_rhs_vjp takes one parameter set");
+  const hode::AdjPlan plan = bwd_plan(cfg);
+  if (plan.smem > 227 * 1024)
+    return fail(HODE_E_UNSUPPORTED, "network too large for the shared-memory gradient accumulators");
+  if (!bwd_workspace || bwd_workspace_bytes < hode::adj_workspace_bytes(plan))
+    return fail(HODE_E_WORKSPACE, "backward workspace missing or smaller than hode_workspace_bytes()");
+  hode::RolloutArgs A = make_args(cfg, state, t, u_meal, u_tvns, u_gd, theta, W);
+  if (cfg->n_traj == 0) {
+    // no rows: the gradients are zero
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_theta) cudaMemsetAsync(grad_theta, 0, HODE_N_THETA * sizeof(float), st);
+    if (grad_W && A.P) cudaMemsetAsync(grad_W, 0, (size_t)A.P * sizeof(float), st);
+    return 0;
+  }
+  cudaError_t e = hode::launch_rhs_vjp(A, cfg->mlp != HODE_MLP_NONE, t, state, grad_out, grad_state,
+                                       grad_theta, grad_W, bwd_workspace, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "hode_rhs_vjp launch");
+  return 0;
 }
 
 int hode_vi_predictive(const hode_cfg*, const float*, const float*, const float*, const float*,

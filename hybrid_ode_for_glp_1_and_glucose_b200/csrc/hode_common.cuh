@@ -180,4 +180,25 @@ __host__ __device__ inline int mlp_image_floats(int H, int L) {
   return n;
 }
 
+// Stage the packed reference-layout parameters (weight [out,in] row-major, bias) of one
+// parameter set into the transposed shared-memory image.
+__device__ inline void stage_mlp_image(float* img, const float* __restrict__ Wg, int H, int L) {
+  int n_in = HODE_NN_IN;
+  const float* src = Wg;
+  float* dst = img;
+  for (int l = 0; l <= L; ++l) {
+    const int n_out = (l == L) ? NS : H;
+    const int ldo = mlp_ldo(n_out);
+    for (int i = threadIdx.x; i < n_in * ldo; i += blockDim.x) {
+      const int k = i / ldo, j = i - k * ldo;
+      dst[i] = (j < n_out) ? src[j * n_in + k] : 0.f;
+    }
+    for (int j = threadIdx.x; j < ldo; j += blockDim.x)
+      dst[n_in * ldo + j] = (j < n_out) ? src[n_out * n_in + j] : 0.f;
+    src += n_out * n_in + n_out;
+    dst += n_in * ldo + ldo;
+    n_in = n_out;
+  }
+}
+
 }  // namespace hode

@@ -19,4 +19,19 @@ cudaError_t launch_rhs(const RolloutArgs& A, int mlp_mode, const float* t, const
 size_t tc_workspace_bytes(int S, int L);
 cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspace, cudaStream_t stream);
 
+// FP32 CUDA-core gradients (hode_adjoint_simt.cu)
+struct AdjPlan {
+  int grid_x, grid_y;
+  size_t smem;            // dynamic shared memory per CTA
+  size_t partial_floats;  // per-CTA partial gradients
+  size_t scratch_floats;  // activation stash
+};
+AdjPlan adj_plan(int B, int S, int H, int L, int P, bool has_nn, int T, int t_per_traj, int n_stages);
+size_t adj_workspace_bytes(const AdjPlan& p);
+cudaError_t launch_rollout_bwd(const RolloutArgs& A, bool has_nn, const float* grad_traj, float* grad_y0,
+                               float* grad_theta, float* grad_W, void* workspace, cudaStream_t stream);
+cudaError_t launch_rhs_vjp(const RolloutArgs& A, bool has_nn, const float* t, const float* state,
+                           const float* grad_out, float* grad_state, float* grad_theta, float* grad_W,
+                           void* workspace, cudaStream_t stream);
+
 }  // namespace hode

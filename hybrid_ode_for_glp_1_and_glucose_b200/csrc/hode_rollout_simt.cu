@@ -165,27 +165,6 @@ __device__ __noinline__ Vec6 mlp_eval_h64(const MlpSmem m, const Vec9 xin) {
   return res;
 }
 
-// Stage the packed reference-layout parameters (weight [out,in] row-major, bias) of one
-// parameter set into the transposed shared-memory image.
-__device__ void stage_mlp_image(float* img, const float* __restrict__ Wg, int H, int L) {
-  int n_in = HODE_NN_IN;
-  const float* src = Wg;
-  float* dst = img;
-  for (int l = 0; l <= L; ++l) {
-    const int n_out = (l == L) ? NS : H;
-    const int ldo = mlp_ldo(n_out);
-    for (int i = threadIdx.x; i < n_in * ldo; i += blockDim.x) {
-      const int k = i / ldo, j = i - k * ldo;
-      dst[i] = (j < n_out) ? src[j * n_in + k] : 0.f;
-    }
-    for (int j = threadIdx.x; j < ldo; j += blockDim.x)
-      dst[n_in * ldo + j] = (j < n_out) ? src[n_out * n_in + j] : 0.f;
-    src += n_out * n_in + n_out;
-    dst += n_in * ldo + ldo;
-    n_in = n_out;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // f_physio + g_NN for one trajectory (reference models/hybrid_ode_nn.py:108-134).
 // MLP_KIND: 0 none, 1 generic, 2 width-64 register path.
@@ -516,7 +495,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
     A.counters[unit] = n_acc;
     A.counters[n_units + unit] = n_rej;
   }
-  if (A.save_n) A.save_n[unit] = n_saved;
+  if (A.save_n) A.save_n[unit] = status == HODE_ST_OK ? n_saved : -1 - n_saved;  // < 0: no gradient
 }
 
 

@@ -303,7 +303,7 @@ __device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A) {
     A.counters[ln.unit] = ln.n_acc;
     A.counters[n_units + ln.unit] = ln.n_rej;
   }
-  if (A.save_n) A.save_n[ln.unit] = ln.n_saved;
+  if (A.save_n) A.save_n[ln.unit] = ln.status == HODE_ST_OK ? ln.n_saved : -1 - ln.n_saved;  // < 0: no gradient
   ln.has = false;
   ln.unit = -1;
 }

@@ -56,6 +56,10 @@ class HybridODENN(nn.Module):
         self.rk4_substeps = 4
         self.check_status = True
         self.skip_zero_nn = True
+        # False: forward() returns a graph-free tensor exactly like the reference
+        # (models/hybrid_ode_nn.py:248).  True: gradients flow through the solver (discrete
+        # adjoint, hode_rollout_bwd) to initial_state, the ODE parameters and the network.
+        self.differentiable = False
         self.last_info: Optional[ops.RolloutInfo] = None
         if use_variational:
             self._setup_variational_inference(prior_params)
@@ -98,7 +102,8 @@ class HybridODENN(nn.Module):
         models/nn_residual.py:83-98) is then integrated by the mechanistic-only kernel."""
         ode_over, nn_over = self._split_overrides(params)
         theta = self.ode_core.theta(ode_over)
-        if self.skip_zero_nn and not nn_over and self.nn_residual.is_identically_zero():
+        if (self.skip_zero_nn and not nn_over and not (self.differentiable and torch.is_grad_enabled())
+                and self.nn_residual.is_identically_zero()):
             return theta, None
         return theta, self.nn_residual.packed(nn_over)
 
@@ -136,14 +141,19 @@ class HybridODENN(nn.Module):
         squeeze = initial_state.dim() == 1
         y0 = initial_state.unsqueeze(0) if squeeze else initial_state
         theta, W = self.packed_parameters(params)
-        traj, info = ops.rollout(
-            y0, t_span, external_inputs, theta.to(dev), None if W is None else W.to(dev),
-            hidden=self.nn_residual.hidden_dim, layers=self.nn_residual.n_layers, solver=solver,
-            rtol=rtol, atol=atol,
-            n_substeps=kernel_opts.get("n_substeps", self.rk4_substeps),
-            kinks=kernel_opts.get("kinks", self.kinks),
-            precision=kernel_opts.get("precision", self.precision),
-            max_steps=kernel_opts.get("max_steps", 0), device=dev)
+        opts = dict(hidden=self.nn_residual.hidden_dim, layers=self.nn_residual.n_layers,
+                    solver=solver, rtol=rtol, atol=atol,
+                    n_substeps=kernel_opts.get("n_substeps", self.rk4_substeps),
+                    kinks=kernel_opts.get("kinks", self.kinks),
+                    precision=kernel_opts.get("precision", self.precision),
+                    max_steps=kernel_opts.get("max_steps", 0))
+        if kernel_opts.get("differentiable", self.differentiable) and torch.is_grad_enabled():
+            opts["max_saved_steps"] = kernel_opts.get("max_saved_steps", 0)
+            traj, info = autograd_ops.rollout(y0.to(dev), t_span, external_inputs, theta.to(dev),
+                                              None if W is None else W.to(dev), **opts)
+        else:
+            traj, info = ops.rollout(y0, t_span, external_inputs, theta.to(dev),
+                                     None if W is None else W.to(dev), device=dev, **opts)
         self.last_info = info
         if kernel_opts.get("check_status", self.check_status):
             self._warn_failures(info)
@@ -240,8 +250,10 @@ class HybridODENN(nn.Module):
             else:
                 reg_loss = self.nn_residual.regularization_loss(l2_weight=lambda2)
         total = data_loss + lambda1 * physics_loss + lambda2 * reg_loss
-        logger.debug(f"Loss components - Data: {float(data_loss):.4f}, "
-                     f"Physics: {float(physics_loss):.4f}, Reg: {float(reg_loss):.4f}")
+        if logger.isEnabledFor(logging.DEBUG):
+            logger.debug(f"Loss components - Data: {float(data_loss.detach()):.4f}, "
+                         f"Physics: {float(physics_loss.detach()):.4f}, "
+                         f"Reg: {float(torch.as_tensor(reg_loss).detach()):.4f}")
         return total
 
     # ------------------------------------------------------------------ Bayesian helpers

@@ -126,14 +126,25 @@ def workspace_bytes(cfg) -> Tuple[int, int]:
     return int(fwd.value), int(bwd.value)
 
 
+@dataclass
+class RolloutTape:
+    """What hode_rollout_bwd needs from a forward pass run with save_steps=1."""
+    cfg: object
+    bufs: Dict[str, Optional[torch.Tensor]]
+    workspace: torch.Tensor
+    squeeze_s: bool
+
+
 def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
             theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
             solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
             kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
-            device: Optional[torch.device] = None) -> Tuple[torch.Tensor, RolloutInfo]:
+            device: Optional[torch.device] = None, save_steps: bool = False,
+            max_saved_steps: int = 0):
     """Batched IVP solve on the GPU (hode_rollout_fwd).
 
-    Returns traj [B,T,6] (or [S,B,T,6] when theta is [S,17]) and a RolloutInfo.
+    Returns traj [B,T,6] (or [S,B,T,6] when theta is [S,17]) and a RolloutInfo; with
+    save_steps=True also a RolloutTape for rollout_bwd().
     """
     device = torch.device(device) if device is not None else y0.device
     _require_cuda(device)
@@ -147,6 +158,8 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
     cfg.n_substeps = int(n_substeps)
     cfg.max_steps = int(max_steps)
     cfg.kink_mode = KINKS[kinks]
+    cfg.save_steps = 1 if save_steps else 0
+    cfg.max_saved_steps = int(max_saved_steps)
     if cfg.mlp != _lib.MLP_NONE:
         cfg.mlp = PRECISIONS[precision]
     B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
@@ -162,8 +175,62 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
             _ptr(traj), _ptr(status), _ptr(counters), _ptr(ws), ws_bytes, _stream(device))
     _lib.check(rc, "hode_rollout_fwd")
     if squeeze_s:
-        return traj[0], RolloutInfo(status[0], counters[0, 0], counters[1, 0])
-    return traj, RolloutInfo(status, counters[0], counters[1])
+        out = traj[0], RolloutInfo(status[0], counters[0, 0], counters[1, 0])
+    else:
+        out = traj, RolloutInfo(status, counters[0], counters[1])
+    if save_steps:
+        return out + (RolloutTape(cfg, bufs, ws, squeeze_s),)
+    return out
+
+
+def rollout_bwd(tape: RolloutTape, grad_traj: torch.Tensor, need_y0: bool = True
+                ) -> Tuple[Optional[torch.Tensor], torch.Tensor, Optional[torch.Tensor]]:
+    """Discrete adjoint of a rollout (hode_rollout_bwd): (grad_y0 [S,B,6], grad_theta [S,17],
+    grad_W [S,P] or None); the S axis is dropped when the forward's theta was 1-D."""
+    cfg, bufs = tape.cfg, tape.bufs
+    device = bufs["y0"].device
+    _require_cuda(device)
+    B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
+    P = 0 if bufs["W"] is None else bufs["W"].shape[1]
+    g = _f32c(grad_traj.reshape(S, B, T, 6), device)
+    with torch.cuda.device(device):
+        g_y0 = torch.empty((S, B, 6), dtype=torch.float32, device=device) if need_y0 else None
+        g_theta = torch.empty((S, _lib.N_THETA), dtype=torch.float32, device=device)
+        g_W = torch.empty((S, P), dtype=torch.float32, device=device) if P else None
+        fwd_bytes, bwd_bytes = workspace_bytes(cfg)
+        bws = torch.empty(max(bwd_bytes, 16), dtype=torch.uint8, device=device)
+        if B == 0:
+            g_theta.zero_()
+            if g_W is not None:
+                g_W.zero_()
+            rc = 0
+        else:
+            rc = _lib.lib().hode_rollout_bwd(
+                ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
+                _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]), _ptr(g),
+                _ptr(g_y0), _ptr(g_theta), _ptr(g_W), _ptr(tape.workspace), fwd_bytes, _ptr(bws),
+                bwd_bytes, _stream(device))
+    _lib.check(rc, "hode_rollout_bwd")
+    if tape.squeeze_s:
+        return (None if g_y0 is None else g_y0[0], g_theta[0], None if g_W is None else g_W[0])
+    return g_y0, g_theta, g_W
+
+
+def saved_steps(tape: RolloutTape):
+    """(n [S*B] int32, t [max_saved, S*B] float64) views of the recorded accepted steps
+    (diagnostics / tests: the step sequence the adjoint differentiates)."""
+    cfg = tape.cfg
+    units = cfg.n_samples * cfg.n_traj
+    if cfg.solver == _lib.SOLVER_RK4:
+        max_saved = (cfg.n_obs - 1) * max(cfg.n_substeps, 1)
+    else:
+        max_saved = cfg.max_saved_steps if cfg.max_saved_steps > 0 else 256
+    al = lambda x: (x + 255) // 256 * 256
+    ws = tape.workspace
+    n = ws[: units * 4].view(torch.int32)
+    off_t = al(units * 4)
+    t = ws[off_t: off_t + units * max_saved * 8].view(torch.float64).reshape(max_saved, units)
+    return n, t
 
 
 def rhs(t: torch.Tensor, state: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
@@ -193,5 +260,30 @@ def rhs(t: torch.Tensor, state: torch.Tensor, inputs: Optional[Dict[str, torch.T
 
 
 def rhs_vjp(t, state, inputs, theta, W, grad_out, hidden=64, layers=4, device=None, part=0):
-    """Vector-Jacobian product of rhs(): returns (grad_state [B,6], grad_theta [17], grad_W [P])."""
-    raise _lib.HodeError("hode_rhs_vjp is not built yet")
+    """Vector-Jacobian product of rhs() (hode_rhs_vjp): returns (grad_state [B,6],
+    grad_theta [17], grad_W [P] or None)."""
+    device = torch.device(device) if device is not None else state.device
+    _require_cuda(device)
+    B = state.shape[0]
+    t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+    if t.numel() == 1:
+        t = t.expand(B)
+    cfg, bufs = prepare(state, t, inputs, theta, W, hidden, layers, device)
+    if cfg.n_samples != 1:
+        raise ValueError("rhs_vjp() takes one parameter set")
+    cfg.n_obs, cfg.t_per_traj = 1, 1
+    cfg.rhs_part = part
+    P = 0 if bufs["W"] is None else bufs["W"].shape[1]
+    g = _f32c(grad_out.reshape(B, 6), device)
+    with torch.cuda.device(device):
+        g_state = torch.empty((B, 6), dtype=torch.float32, device=device)
+        g_theta = torch.empty(_lib.N_THETA, dtype=torch.float32, device=device)
+        g_W = torch.empty(P, dtype=torch.float32, device=device) if P else None
+        bwd_bytes = workspace_bytes(cfg)[1]
+        bws = torch.empty(max(bwd_bytes, 16), dtype=torch.uint8, device=device)
+        rc = _lib.lib().hode_rhs_vjp(
+            ctypes.byref(cfg), _ptr(bufs["t_obs"]), _ptr(bufs["y0"]), _ptr(bufs["meal"]),
+            _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]), _ptr(g),
+            _ptr(g_state), _ptr(g_theta), _ptr(g_W), _ptr(bws), bwd_bytes, _stream(device))
+    _lib.check(rc, "hode_rhs_vjp")
+    return g_state, g_theta, g_W

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HODE_ABI_VERSION 1
+#define HODE_ABI_VERSION 2
 #define HODE_N_STATE 6
 #define HODE_N_THETA 17
 #define HODE_NN_IN 9
@@ -126,7 +126,8 @@ const char* hode_last_error_string(void);
 /* Number of floats in one packed MLP parameter set (13 510 for hidden=64, layers=4). */
 int64_t hode_mlp_param_count(int32_t nn_hidden, int32_t nn_layers);
 
-/* Bytes of device workspace hode_rollout_fwd (save_steps=1) / hode_rollout_bwd need. */
+/* Bytes of device workspace hode_rollout_fwd needs (saved steps when save_steps = 1, tensor-core
+ * weight images) and of gradient scratch hode_rollout_bwd / hode_rhs_vjp need. */
 int hode_workspace_bytes(const hode_cfg* cfg, size_t* fwd_bytes, size_t* bwd_bytes);
 
 /*
@@ -149,16 +150,34 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
 
 /*
  * Discrete adjoint of hode_rollout_fwd over the recorded accepted steps (step sizes
- * frozen).  The reference has no through-solver gradient (models/hybrid_ode_nn.py:248);
+ * frozen): the gradient autograd would give through the unrolled RK steps.  The reference
+ * has no through-solver gradient (models/hybrid_ode_nn.py:248 returns a graph-free tensor);
  * this is the gradient path BASELINE.json's north_star item (3) asks for.
+ *   cfg must be the forward's cfg (save_steps = 1); fwd_workspace is the buffer that
+ *   forward call filled; bwd_workspace has hode_workspace_bytes().bwd_bytes bytes.
  *   grad_traj [S,B,T,6] in;  grad_y0 [S,B,6] out (may be NULL);
- *   grad_theta [S,17] out;   grad_W [S,P] out.
+ *   grad_theta [S,17] out (may be NULL);  grad_W [S,P] out (may be NULL).
+ * Trajectories whose forward status is not HODE_ST_OK contribute zero gradient.
+ * The summation order is fixed: results are bit-reproducible run to run.
  */
 int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
                      const float* u_meal, const float* u_tvns, const float* u_gd,
                      const float* theta, const float* W, const float* grad_traj,
-                     float* grad_y0, float* grad_theta, float* grad_W, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     float* grad_y0, float* grad_theta, float* grad_W,
+                     const void* fwd_workspace, size_t fwd_workspace_bytes,
+                     void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
+
+/*
+ * Vector-Jacobian product of hode_rhs: the backward of HybridODENN.ode_residual, the only
+ * differentiable model call of the reference's loss (models/hybrid_ode_nn.py:327 -> :330,
+ * loss.backward() at train/train_hybrid.py:252).
+ *   grad_out [B,6] in;  grad_state [B,6] out (may be NULL);  grad_theta [17] out (may be
+ *   NULL);  grad_W [P] out (may be NULL).  cfg.rhs_part selects FULL or NN_ONLY as in hode_rhs.
+ */
+int hode_rhs_vjp(const hode_cfg* cfg, const float* t, const float* state, const float* u_meal,
+                 const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+                 const float* grad_out, float* grad_state, float* grad_theta, float* grad_W,
+                 void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
 
 /*
  * Posterior-predictive sweep with the mean / unbiased std over the S parameter sets

@@ -194,8 +194,68 @@ def rollout_physio():
          layers=4, out_rk45=out)
 
 
+def rhs_vjp_cases():
+    """Autograd of the reference's own ode_residual (the backward of the physics-residual loss
+    term, models/hybrid_ode_nn.py:327-330).  ODE parameters are buffers in the reference
+    (models/ode_core.py:78-79); to obtain their cotangents they are swapped for leaf tensors,
+    exactly what forward_with_params does with sampled values (models/hybrid_ode_nn.py:407-411)."""
+    d0 = np.load(os.path.join(HERE, "rhs_mech.npz"))
+    rng = np.random.default_rng(11)
+    g_out = rng.normal(0, 1, (5, 6)).astype(np.float32)
+    for tag, hidden, layers, std in (("mech", 64, 4, 0.0), ("nn64x4", 64, 4, 0.05),
+                                     ("nn16x2", 16, 2, 0.05), ("nn32x3", 32, 3, 0.1)):
+        m = make_model(hidden, layers, seed=1, out_std=std)
+        names = [n for n, _ in m.ode_core.named_buffers()]
+        for n in names:
+            m.ode_core._buffers[n] = m.ode_core._buffers[n].clone().requires_grad_(True)
+        state = torch.tensor(d0["state"], requires_grad=True)
+        ext = {"meal": torch.tensor(d0["meal"]), "tVNS": torch.tensor(d0["tvns"]),
+               "GD": torch.tensor(d0["gd"])}
+        out = m.ode_residual(torch.tensor(d0["t"]), state, ext)
+        out.backward(torch.tensor(g_out))
+        g_theta = np.array([float(m.ode_core._buffers[n].grad) for n in names], dtype=np.float32)
+        g_W = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().reshape(-1)
+                              for _, p in m.nn_residual.named_parameters()]).astype(np.float32)
+        save(f"rhs_vjp_{tag}", t=d0["t"], state=d0["state"], meal=d0["meal"], tvns=d0["tvns"],
+             gd=d0["gd"], theta=theta_of(m), W=pack_W(m), hidden=hidden, layers=layers,
+             grad_out=g_out, out=out.detach().numpy(), grad_state=state.grad.numpy(),
+             grad_theta=g_theta, grad_W=g_W)
+
+
+def loss_cases():
+    """HybridODENN.loss + backward of the reference on a collated batch (train/train_hybrid.py:247-252):
+    loss value and the gradient of every network parameter, with the torch seed that fixes the
+    physics-index draw (models/hybrid_ode_nn.py:301)."""
+    y0, obs, t, meal, tv, ds = windows_4gi()
+    B = 4
+    # physiological-unit cohort instead of the z-scored windows: keeps every solve well-conditioned
+    rng = np.random.default_rng(21)
+    y0 = np.stack([7.0 * rng.normal(1, 0.1, B), 50.0 * rng.normal(1, 0.15, B),
+                   25.0 * rng.normal(1, 0.15, B), 10.0 * rng.normal(1, 0.15, B),
+                   np.zeros(B), np.ones(B)], axis=1).astype(np.float32)
+    T = 13
+    tt = np.tile(np.linspace(0, 1, T).astype(np.float32), (B, 1))
+    ml = np.zeros((B, T), dtype=np.float32)
+    ml[:, 3] = rng.uniform(0.5, 1.5, B)
+    tvn = np.zeros((B, T), dtype=np.float32)
+    tvn[::2, 5:9] = 1.0
+    obs = (y0[:, None, :] * (1 + 0.1 * rng.normal(0, 1, (B, T, 6)))).astype(np.float32)
+    for tag, hidden, layers in (("nn64x4", 64, 4), ("nn16x2", 16, 2)):
+        m = make_model(hidden, layers, seed=7, out_std=0.02)
+        batch = {"initial_state": torch.tensor(y0), "observations": torch.tensor(obs),
+                 "time_points": torch.tensor(tt),
+                 "external_inputs": {"meal": torch.tensor(ml), "tVNS": torch.tensor(tvn)}}
+        torch.manual_seed(123)
+        loss = m.loss(batch, lambda1=1.0, lambda2=0.5)
+        loss.backward()
+        g_W = np.concatenate([p.grad.numpy().reshape(-1) for _, p in m.nn_residual.named_parameters()])
+        save(f"loss_{tag}", y0=y0, obs=obs, t=tt, meal=ml, tvns=tvn, theta=theta_of(m), W=pack_W(m),
+             hidden=hidden, layers=layers, seed=123, lambda1=1.0, lambda2=0.5,
+             loss=np.float64(loss.item()), grad_W=g_W.astype(np.float32))
+
+
 if __name__ == "__main__":
-    rhs_cases()
-    rollout_fig2()
-    rollout_4gi()
-    rollout_physio()
+    only = sys.argv[1:]
+    for fn in (rhs_cases, rollout_fig2, rollout_4gi, rollout_physio, rhs_vjp_cases, loss_cases):
+        if not only or fn.__name__ in only:
+            fn()

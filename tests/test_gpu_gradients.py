@@ -1,0 +1,239 @@
+"""GPU gradient parity: hode_rhs_vjp against autograd of the reference's own ode_residual
+(golden fixtures), hode_rollout_bwd against autograd through the float64 restatement over the
+kernel's own accepted steps, and HybridODENN.loss().backward() against the reference's.
+Tolerance: 1e-4 relative (BASELINE.json north_star), in the max norm per gradient tensor."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cohort, golden, golden_inputs, random_mlp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def relmax(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(a - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+# ---------------------------------------------------------------------------- RHS VJP
+@pytest.mark.parametrize("tag", ["mech", "nn64x4", "nn16x2", "nn32x3"])
+def test_rhs_vjp_matches_reference_autograd(dev, tag):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    d = golden(f"rhs_vjp_{tag}")
+    W = None if tag == "mech" else torch.from_numpy(d["W"])
+    ins = {k: torch.from_numpy(v) for k, v in golden_inputs(d).items()}
+    gs, gt, gW = ops.rhs_vjp(torch.from_numpy(d["t"]), torch.from_numpy(d["state"]), ins,
+                             torch.from_numpy(d["theta"]), W, torch.from_numpy(d["grad_out"]),
+                             int(d["hidden"]), int(d["layers"]), device=dev)
+    assert relmax(gs.cpu().numpy(), d["grad_state"]) < TOL
+    assert relmax(gt.cpu().numpy(), d["grad_theta"]) < TOL
+    if W is not None:
+        assert relmax(gW.cpu().numpy(), d["grad_W"]) < TOL
+
+
+@pytest.mark.parametrize("hidden,layers,B", [(64, 4, 1000), (24, 3, 300), (128, 1, 130)])
+def test_rhs_vjp_many_rows_vs_restatement_and_deterministic(dev, hidden, layers, B):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    from oracle import torch_restate as R
+    y0, _, _ = cohort(B, 2, seed=5, meals=False, tvns=False)
+    rng = np.random.default_rng(6)
+    state = (y0 * rng.uniform(0.5, 1.5, y0.shape)).astype(np.float32)
+    t = rng.uniform(0, 5, B).astype(np.float32)
+    meal = rng.uniform(0, 2, B).astype(np.float32)
+    tv = (rng.uniform(0, 1, B) > 0.5).astype(np.float32)
+    gd = rng.uniform(0, 1500, B).astype(np.float32)
+    g = rng.normal(0, 1, (B, 6)).astype(np.float32)
+    W = random_mlp(hidden, layers, seed=7, out_std=0.05)
+    theta = golden("rhs_mech")["theta"]
+    tt = lambda a: torch.from_numpy(a)
+    ins = {"meal": tt(meal), "tVNS": tt(tv), "GD": tt(gd)}
+    out1 = ops.rhs_vjp(tt(t), tt(state), ins, tt(theta), tt(W), tt(g), hidden, layers, device=dev)
+    out2 = ops.rhs_vjp(tt(t), tt(state), ins, tt(theta), tt(W), tt(g), hidden, layers, device=dev)
+    for a, b in zip(out1, out2):
+        assert torch.equal(a, b), "gradient reduction must be bit-reproducible"
+    f64 = lambda a, rg=False: torch.tensor(np.asarray(a, np.float64), requires_grad=rg)
+    s64, th64, W64 = f64(state, True), f64(theta, True), f64(W, True)
+    out = R.rhs(f64(t), s64, f64(meal), f64(tv), f64(gd), th64, W64, hidden, layers)
+    out.backward(f64(g))
+    assert relmax(out1[0].cpu().numpy(), s64.grad.numpy()) < TOL
+    assert relmax(out1[1].cpu().numpy(), th64.grad.numpy()) < TOL
+    assert relmax(out1[2].cpu().numpy(), W64.grad.numpy()) < TOL
+
+
+def test_ode_residual_autograd_through_module(dev):
+    """The call site of the reference's loss: ode_residual(...).backward() fills .grad of every
+    network parameter (tests/test_gradient_correctness.py:65 contract)."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    d = golden("rhs_vjp_nn16x2")
+    m = HybridODENN(nn_hidden=16, nn_layers=2, device=dev)
+    with torch.no_grad():
+        off = 0
+        for _, p in m.nn_residual.named_parameters():
+            p.copy_(torch.from_numpy(d["W"][off: off + p.numel()]).reshape(p.shape))
+            off += p.numel()
+    state = torch.from_numpy(d["state"]).to(dev).requires_grad_(True)
+    ext = {"meal": torch.from_numpy(d["meal"]).to(dev), "tVNS": torch.from_numpy(d["tvns"]).to(dev),
+           "GD": torch.from_numpy(d["gd"]).to(dev)}
+    out = m.ode_residual(torch.from_numpy(d["t"]).to(dev), state, ext)
+    out.backward(torch.from_numpy(d["grad_out"]).to(dev))
+    gW = torch.cat([p.grad.reshape(-1) for _, p in m.nn_residual.named_parameters()]).cpu().numpy()
+    assert relmax(gW, d["grad_W"]) < TOL
+    assert relmax(state.grad.cpu().numpy(), d["grad_state"]) < TOL
+
+
+# ---------------------------------------------------------------------------- discrete adjoint
+def _adjoint_case(dev, B, T, hidden, layers, solver, kinks="clip", const_inputs=False, seed=0,
+                  precision="fp32", **kw):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    from oracle import torch_restate as R
+    y0, t, ins = cohort(B, T, seed=seed, horizon=2.0)
+    if const_inputs:
+        ins = {"meal": ins["meal"][:, T // 10].copy(), "GD": np.full(B, 300.0, np.float32)}
+    W = random_mlp(hidden, layers, seed=seed + 1, out_std=0.05)
+    theta = golden("rhs_mech")["theta"]
+    rng = np.random.default_rng(seed + 2)
+    g = rng.normal(0, 1, (B, T, 6)).astype(np.float32)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    traj, info, tape = ops.rollout(tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W),
+                                   hidden, layers, solver=solver, kinks=kinks, device=dev,
+                                   save_steps=True, precision=precision, **kw)
+    assert bool((info.status == 0).all())
+    g_y0, g_theta, g_W = ops.rollout_bwd(tape, tt(g).to(dev))
+    again = ops.rollout_bwd(tape, tt(g).to(dev))
+    assert torch.equal(g_W, again[2]) and torch.equal(g_theta, again[1]), "must be bit-reproducible"
+    n, st = ops.saved_steps(tape)
+    n, st = n.cpu().numpy(), st.cpu().numpy()
+    f64 = lambda a, rg=False: torch.tensor(np.asarray(a, np.float64), requires_grad=rg)
+    th64, W64 = f64(theta, True), f64(W, True)
+    gy_ref = np.zeros((B, 6))
+    tr_ref = np.zeros((B, T, 6))
+    for b in range(B):
+        y64 = f64(y0[b], True)
+        ins_b = {k: (v[b] if v.ndim == 2 else np.float64(v[b])) for k, v in ins.items()}
+        tr = R.rollout_on_steps(y64, t, ins_b, th64, W64, hidden, layers, list(st[: n[b], b]), solver)
+        (tr * f64(g[b])).sum().backward()
+        gy_ref[b] = y64.grad.numpy()
+        tr_ref[b] = tr.detach().numpy()
+    # forward sanity: same steps -> same trajectory up to float32 round-off
+    assert relmax(traj.cpu().numpy(), tr_ref) < 2e-5
+    return (relmax(g_y0.cpu().numpy(), gy_ref), relmax(g_theta.cpu().numpy(), th64.grad.numpy()),
+            relmax(g_W.cpu().numpy(), W64.grad.numpy()))
+
+
+@pytest.mark.parametrize("hidden,layers", [(64, 4), (16, 2)])
+def test_rollout_bwd_rk4_matches_autograd(dev, hidden, layers):
+    errs = _adjoint_case(dev, 5, 9, hidden, layers, "rk4", n_substeps=2)
+    assert max(errs) < TOL, errs
+
+
+@pytest.mark.parametrize("kinks", ["clip", "scipy"])
+def test_rollout_bwd_dopri5_matches_autograd(dev, kinks):
+    errs = _adjoint_case(dev, 5, 13, 64, 4, "dopri5", kinks=kinks, seed=3)
+    assert max(errs) < TOL, errs
+
+
+def test_rollout_bwd_dopri5_const_inputs_small_net(dev):
+    errs = _adjoint_case(dev, 4, 7, 32, 3, "dopri5", const_inputs=True, seed=5)
+    assert max(errs) < TOL, errs
+
+
+def test_rollout_bwd_after_tensor_core_forward(dev):
+    """The adjoint runs over the steps a 3xTF32 tensor-core forward recorded."""
+    errs = _adjoint_case(dev, 5, 13, 64, 4, "dopri5", seed=9, precision="tf32x3")
+    assert max(errs) < TOL, errs
+
+
+def test_rollout_bwd_many_blocks_and_parameter_sets(dev):
+    """B spanning several CTAs and S = 3 parameter sets: per-set gradients equal separate launches;
+    a failed trajectory contributes nothing."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T, S = 700, 9, 3
+    y0, t, ins = cohort(B, T, seed=11, horizon=1.0)
+    theta = np.tile(golden("rhs_mech")["theta"], (S, 1))
+    theta[1, 8] = 7.5   # V_max
+    theta[2, 1] = 0.03  # k_I
+    W = np.stack([random_mlp(64, 4, seed=20 + s, out_std=0.05) for s in range(S)])
+    g = np.random.default_rng(12).normal(0, 1, (S, B, T, 6)).astype(np.float32)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    tin = {k: tt(v) for k, v in ins.items()}
+    _, info, tape = ops.rollout(tt(y0), tt(t), tin, tt(theta), tt(W), solver="dopri5", device=dev,
+                                save_steps=True)
+    gy, gth, gW = ops.rollout_bwd(tape, tt(g).to(dev))
+    for s in range(S):
+        _, _, tp = ops.rollout(tt(y0), tt(t), tin, tt(theta[s]), tt(W[s]), solver="dopri5", device=dev,
+                               save_steps=True)
+        gy1, gth1, gW1 = ops.rollout_bwd(tp, tt(g[s]).to(dev))
+        assert relmax(gy[s].cpu().numpy(), gy1.cpu().numpy()) < 1e-6
+        assert relmax(gth[s].cpu().numpy(), gth1.cpu().numpy()) < 2e-5
+        assert relmax(gW[s].cpu().numpy(), gW1.cpu().numpy()) < 2e-5
+    # budget of 3 attempts: every trajectory fails -> all gradients are exactly zero
+    _, info, tape = ops.rollout(tt(y0), tt(t), tin, tt(theta[0]), tt(W[0]), solver="dopri5", device=dev,
+                                save_steps=True, max_steps=3)
+    assert bool((info.status != 0).all())
+    gy, gth, gW = ops.rollout_bwd(tape, tt(g[0]).to(dev))
+    assert float(gy.abs().max()) == 0.0 and float(gth.abs().max()) == 0.0 and float(gW.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------- module-level
+def _load_W(m, W):
+    with torch.no_grad():
+        off = 0
+        for _, p in m.nn_residual.named_parameters():
+            p.copy_(torch.from_numpy(W[off: off + p.numel()]).reshape(p.shape))
+            off += p.numel()
+
+
+@pytest.mark.parametrize("tag", ["nn64x4", "nn16x2"])
+def test_loss_backward_matches_reference(dev, tag):
+    """model.loss(batch).backward() with the reference's semantics (physics residual + L2 carry the
+    gradient; same torch seed -> same physics indices) against the reference's own numbers."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    d = golden(f"loss_{tag}")
+    m = HybridODENN(nn_hidden=int(d["hidden"]), nn_layers=int(d["layers"]), device=dev)
+    _load_W(m, d["W"])
+    m.kinks = "scipy"
+    to = lambda a: torch.from_numpy(a).to(dev)
+    batch = {"initial_state": to(d["y0"]), "observations": to(d["obs"]), "time_points": to(d["t"]),
+             "external_inputs": {"meal": to(d["meal"]), "tVNS": to(d["tvns"])}}
+    torch.manual_seed(int(d["seed"]))
+    loss = m.loss(batch, lambda1=float(d["lambda1"]), lambda2=float(d["lambda2"]))
+    loss.backward()
+    assert abs(loss.item() - float(d["loss"])) <= 1e-4 * abs(float(d["loss"]))
+    gW = torch.cat([p.grad.reshape(-1) for _, p in m.nn_residual.named_parameters()]).cpu().numpy()
+    assert relmax(gW, d["grad_W"]) < TOL
+    for name, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+def test_differentiable_forward_trains_the_data_term(dev):
+    """differentiable=True: the data-MSE term, which carries no gradient in the reference, now
+    reaches the network and initial state; one Adam step lowers it."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    y0, t, ins = cohort(64, 13, seed=31, horizon=1.0)
+    m = HybridODENN(device=dev)
+    m.differentiable = True
+    to = lambda a: torch.from_numpy(a).to(dev)
+    ext = {k: to(v) for k, v in ins.items()}
+    with torch.no_grad():
+        target = m(to(y0), to(t), ext) * 1.02
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    y0t = to(y0).requires_grad_(True)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(m(y0t, to(t), ext), target)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    head = m.nn_residual.linears()[-1]
+    assert head.weight.grad is not None and float(head.weight.grad.abs().max()) > 0
+    assert y0t.grad is not None and float(y0t.grad.abs().max()) > 0
+    assert losses[-1] < losses[0]
