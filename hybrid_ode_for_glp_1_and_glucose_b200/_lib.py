@@ -84,7 +84,7 @@ def lib() -> ctypes.CDLL:
     L.hode_rhs_vjp.restype = ctypes.c_int
     L.hode_rhs_vjp.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12 + [ctypes.c_size_t, _P]
     L.hode_vi_predictive.restype = ctypes.c_int
-    L.hode_vi_predictive.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12
+    L.hode_vi_predictive.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12 + [ctypes.c_size_t, _P]
     L.hode_rhs.restype = ctypes.c_int
     L.hode_rhs.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 9
     L.hode_rollout_fwd_host.restype = ctypes.c_int

@@ -250,10 +250,33 @@ int hode_rhs_vjp(const hode_cfg* cfg, const float* t, const float* state, const 
   return 0;
 }
 
-int hode_vi_predictive(const hode_cfg*, const float*, const float*, const float*, const float*,
-                       const float*, const float*, const float*, float*, float*, int32_t*,
-                       int32_t*, void*) {
-  return fail(HODE_E_UNSUPPORTED, "hode_vi_predictive: not built yet");
+int hode_vi_predictive(const hode_cfg* cfg, const float* y0, const float* t_obs, const float* u_meal,
+                       const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+                       float* mean, float* std_out, int32_t* status, int32_t* counters,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!y0 || !t_obs || !theta || !mean || !std_out)
+    return fail(HODE_E_NULL, "y0/t_obs/theta/mean/std is NULL");
+  rc = check_inputs(cfg, u_meal, u_tvns, u_gd, W);
+  if (rc) return rc;
+  if (cfg->save_steps) return fail(HODE_E_UNSUPPORTED, "save_steps is not available in the fused sweep");
+  if (cfg->n_traj == 0) return 0;
+  hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
+  A.traj = nullptr; A.status = status; A.counters = counters;
+  A.vi_mean = mean; A.vi_m2 = std_out;
+  const Workspace w = fwd_workspace(cfg);
+  if (w.total > 0 && (!workspace || workspace_bytes < w.total))
+    return fail(HODE_E_WORKSPACE, "workspace missing or smaller than hode_workspace_bytes()");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (cfg->mlp == HODE_MLP_NONE || cfg->mlp == HODE_MLP_FP32) {
+    e = hode::launch_rollout_simt(A, cfg->mlp, st);
+  } else {
+    e = hode::launch_rollout_tc(A, cfg->mlp, (char*)workspace + w.off_tc, st);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "hode_vi_predictive launch");
+  return 0;
 }
 
 int hode_rhs(const hode_cfg* cfg, const float* t, const float* state, const float* u_meal,

@@ -38,6 +38,10 @@ struct RolloutArgs {
   int32_t P;            // floats per packed MLP parameter set
   int32_t solver, n_substeps, max_steps, kink_mode, rhs_part;
   float rtol, atol;
+  // fused posterior-predictive mode (hode_vi_predictive): running mean and sum of squared
+  // deviations over the S parameter sets, [B,T,6] each; traj is nullptr in this mode
+  float* vi_mean;
+  float* vi_m2;
 };
 
 // ---- Dormand-Prince 5(4) coefficients (float) --------------------------------------------
@@ -178,6 +182,48 @@ __host__ __device__ inline int mlp_image_floats(int H, int L) {
   for (int l = 1; l < L; ++l) n += H * mlp_ldo(H) + mlp_ldo(H);
   n += H * mlp_ldo(NS) + mlp_ldo(NS);
   return n;
+}
+
+__device__ __forceinline__ void store_row6c(float* p, const float* y) {
+  float2* q = reinterpret_cast<float2*>(p);
+  q[0] = make_float2(y[0], y[1]);
+  q[1] = make_float2(y[2], y[3]);
+  q[2] = make_float2(y[4], y[5]);
+}
+
+// Emit one observation row.  vi_n == 0: store into traj.  vi_n > 0 (fused posterior-predictive
+// mode, reference inference/vi.py:306-310): this is the vi_n-th sample of trajectory b; update the
+// running mean / sum of squared deviations (Welford) in A.vi_mean / A.vi_m2, and turn the latter
+// into the unbiased std on the last sample.  Each (b, ei) element is owned by one thread at a
+// time and the samples of a trajectory are visited in a fixed order: deterministic.
+__device__ __forceinline__ void emit_row(const RolloutArgs& A, float* out, long b, int ei, const float* y,
+                                         int vi_n) {
+  if (vi_n == 0) {
+    if (out) store_row6c(out + (size_t)ei * NS, y);
+    return;
+  }
+  float* pm = A.vi_mean + ((size_t)b * A.T + ei) * NS;
+  float* ps = A.vi_m2 + ((size_t)b * A.T + ei) * NS;
+  float m[NS], q[NS];
+  if (vi_n == 1) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { m[i] = y[i]; q[i] = 0.f; }
+  } else {
+    const float inv = 1.0f / (float)vi_n;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const float d = y[i] - pm[i];
+      m[i] = fmaf(d, inv, pm[i]);
+      q[i] = fmaf(d, y[i] - m[i], ps[i]);
+    }
+  }
+  if (vi_n == A.S) {
+    const float invs = 1.0f / (float)(A.S - 1);   // S == 1: 0 * inf = NaN, as torch.std of one sample
+#pragma unroll
+    for (int i = 0; i < NS; ++i) q[i] = sqrtf(q[i] * invs);
+  }
+  store_row6c(pm, m);
+  store_row6c(ps, q);
 }
 
 // Stage the packed reference-layout parameters (weight [out,in] row-major, bias) of one

@@ -213,42 +213,13 @@ __device__ __forceinline__ float rms6(const float* v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The rollout kernel.  grid = (ceil(B / blockDim.x), S); thread = one (sample, trajectory).
+// One (parameter set s, trajectory b) unit, integrated by one thread.
 // ------------------------------------------------------------------------------------------
 template <int MLP_KIND>
-__global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) {
-  extern __shared__ __align__(16) float smem[];
-  const int s = blockIdx.y;
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSmem& mlp, const float* t_shared,
+                                               int s, long b, int vi_n) {
   const long unit = (long)s * A.B + b;
   const long n_units = (long)A.S * A.B;
-
-  // ---- shared memory carve-up: [MLP image][activation columns][shared time grid] ----------
-  float* sm = smem;
-  MlpSmem mlp;
-  mlp.img = nullptr; mlp.actA = nullptr; mlp.actB = nullptr;
-  mlp.stride = blockDim.x; mlp.H = A.H; mlp.L = A.L;
-  if (MLP_KIND != 0) {
-    const int img_floats = (mlp_image_floats(A.H, A.L) + 3) & ~3;
-    stage_mlp_image(sm, A.W + (size_t)s * A.P, A.H, A.L);
-    mlp.img = sm;
-    sm += img_floats;
-    const int act_rows = A.H > 16 ? A.H : 16;
-    mlp.actA = sm + threadIdx.x;
-    sm += act_rows * blockDim.x;
-    if (MLP_KIND == 1) {
-      mlp.actB = sm + threadIdx.x;
-      sm += act_rows * blockDim.x;
-    }
-  }
-  const float* t_shared = nullptr;
-  if (!A.t_per_traj && A.T <= HODE_SIMT_MAX_SHARED_T) {
-    for (int i = threadIdx.x; i < A.T; i += blockDim.x) sm[i] = A.t_obs[i];
-    t_shared = sm;
-  }
-  __syncthreads();
-  if (b >= A.B) return;
-
   const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
   TrajInputs in;
   in.T = A.T;
@@ -272,7 +243,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
 
   if (A.solver == HODE_SOLVER_RK4) {
     // -------- classical RK4, n_substeps equal steps per observation interval -------------
-    if (out) store_row(out, y);
+    emit_row(A, out, b, 0, y, vi_n);
     ei = 1;
     const int nsub = A.n_substeps > 0 ? A.n_substeps : 1;
     for (int n = 0; n + 1 < T; ++n) {
@@ -312,7 +283,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
         }
         ++n_acc;
       }
-      if (out) store_row(out + (size_t)(n + 1) * NS, y);
+      emit_row(A, out, b, n + 1, y, vi_n);
       ei = n + 2;
     }
   } else {
@@ -325,7 +296,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
     rhs_full<MLP_KIND>(th, mlp, in, t, y, k1);
     // outputs at t_eval <= t0 (ivp.py:701-718 emits t_eval[0] == t0 from the first step)
     while (ei < T && (double)in.t_obs[ei] <= t) {
-      if (out) store_row(out + (size_t)ei * NS, y);
+      emit_row(A, out, b, ei, y, vi_n);
       ++ei;
     }
     double h_abs = 0.0;
@@ -459,7 +430,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
                 yo[i] = fmaf(hf, poly, y[i]);
               }
             }
-            if (out) store_row(out + (size_t)ei * NS, yo);
+            emit_row(A, out, b, ei, yo, vi_n);
             ++ei;
           }
         }
@@ -486,9 +457,9 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
   }
 
   // failure: zero-pad the remaining observation rows (reference models/hybrid_ode_nn.py:252-254)
-  if (out) {
+  if (out || vi_n) {
     const float z[NS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (; ei < T; ++ei) store_row(out + (size_t)ei * NS, z);
+    for (; ei < T; ++ei) emit_row(A, out, b, ei, z, vi_n);
   }
   if (A.status) A.status[unit] = status;
   if (A.counters) {
@@ -496,6 +467,50 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) 
     A.counters[n_units + unit] = n_rej;
   }
   if (A.save_n) A.save_n[unit] = status == HODE_ST_OK ? n_saved : -1 - n_saved;  // < 0: no gradient
+}
+
+// ------------------------------------------------------------------------------------------
+// The rollout kernel.  Normal mode: grid = (ceil(B / blockDim.x), S), thread = one (sample,
+// trajectory) unit.  Fused posterior-predictive mode (A.vi_mean != nullptr): grid =
+// (ceil(B / blockDim.x), 1); the CTA walks through all S parameter sets for its trajectories,
+// restaging the weight image for each, and reduces mean / std on the fly.
+// ------------------------------------------------------------------------------------------
+template <int MLP_KIND>
+__global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vi = A.vi_mean != nullptr;
+  const int n_iter = vi ? A.S : 1;
+
+  // ---- shared memory carve-up: [MLP image][activation columns][shared time grid] ----------
+  float* sm = smem;
+  MlpSmem mlp;
+  mlp.img = nullptr; mlp.actA = nullptr; mlp.actB = nullptr;
+  mlp.stride = blockDim.x; mlp.H = A.H; mlp.L = A.L;
+  if (MLP_KIND != 0) {
+    const int img_floats = (mlp_image_floats(A.H, A.L) + 3) & ~3;
+    mlp.img = sm;
+    sm += img_floats;
+    const int act_rows = A.H > 16 ? A.H : 16;
+    mlp.actA = sm + threadIdx.x;
+    sm += act_rows * blockDim.x;
+    if (MLP_KIND == 1) {
+      mlp.actB = sm + threadIdx.x;
+      sm += act_rows * blockDim.x;
+    }
+  }
+  const float* t_shared = nullptr;
+  if (!A.t_per_traj && A.T <= HODE_SIMT_MAX_SHARED_T) {
+    for (int i = threadIdx.x; i < A.T; i += blockDim.x) sm[i] = A.t_obs[i];
+    t_shared = sm;
+  }
+  for (int si = 0; si < n_iter; ++si) {
+    const int s = vi ? (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S) : (int)blockIdx.y;
+    if (si > 0) __syncthreads();  // every thread is done with the previous parameter set's image
+    if (MLP_KIND != 0) stage_mlp_image(smem, A.W + (size_t)s * A.P, A.H, A.L);
+    __syncthreads();
+    if (b < A.B) simt_integrate<MLP_KIND>(A, mlp, t_shared, s, b, vi ? si + 1 : 0);
+  }
 }
 
 
@@ -575,7 +590,7 @@ cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t
   while (block > 32 && simt_smem_bytes(A, kind, block) > 220 * 1024) block >>= 1;
   const size_t smem = simt_smem_bytes(A, kind, block);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-  dim3 grid((unsigned)((A.B + block - 1) / block), (unsigned)A.S);
+  dim3 grid((unsigned)((A.B + block - 1) / block), A.vi_mean ? 1u : (unsigned)A.S);
   cudaError_t e;
   switch (kind) {
     case 0:

@@ -224,18 +224,12 @@ struct Lane {
   float y[NS], cmp[NS];
   double t;
   long unit;          // flat (sample, trajectory) index, -1 = idle
+  long b;             // trajectory index
   float* out;         // this trajectory's [T,6] output rows (or nullptr)
   int ei;             // next observation index to emit
   int status, n_acc, n_rej, n_saved;
   bool has;
 };
-
-__device__ __forceinline__ void store_row6(float* p, const float* y) {
-  float2* q = reinterpret_cast<float2*>(p);
-  q[0] = make_float2(y[0], y[1]);
-  q[1] = make_float2(y[2], y[3]);
-  q[2] = make_float2(y[4], y[5]);
-}
 
 __device__ __forceinline__ float rms6v(const float* v) {
   float s = 0.f;
@@ -274,6 +268,7 @@ __device__ __forceinline__ void lane_bind(Lane& ln, const RolloutArgs& A, const 
                                           int s, long b) {
   const long unit = (long)s * A.B + b;
   ln.unit = unit;
+  ln.b = b;
   ln.has = true;
   ln.in.T = A.T;
   ln.in.cur = 0;
@@ -292,11 +287,11 @@ __device__ __forceinline__ void lane_bind(Lane& ln, const RolloutArgs& A, const 
   ln.n_acc = ln.n_rej = ln.n_saved = 0;
 }
 
-__device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A) {
+__device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A, int vi_n) {
   const long n_units = (long)A.S * A.B;
-  if (ln.out) {
+  if (ln.out || vi_n) {
     const float z[NS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (; ln.ei < A.T; ++ln.ei) store_row6(ln.out + (size_t)ln.ei * NS, z);
+    for (; ln.ei < A.T; ++ln.ei) emit_row(A, ln.out, ln.b, ln.ei, z, vi_n);
   }
   if (A.status) A.status[ln.unit] = ln.status;
   if (A.counters) {
@@ -354,6 +349,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   __shared__ __align__(8) uint64_t load_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ int tile_active[TILES_PER_CTA][4];
+  __shared__ int cta_queue;   // fused posterior-predictive mode: next trajectory of this CTA's range
 
   const int tid = threadIdx.x, lane_id = tid & 31;
   // warp-uniform by construction; the shuffle lets ptxas keep everything derived from it
@@ -395,10 +391,20 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   const bool clip = (A.kink_mode == HODE_KINK_CLIP);
   uint32_t load_parity = 0;
 
+  // Fused posterior-predictive mode: every trajectory belongs to ONE CTA for all S parameter sets
+  // (the running mean/std of a trajectory is then updated in a fixed order without atomics).
+  const bool vi = A.vi_mean != nullptr;
+  const long per_cta = ((long)A.B + gridDim.x - 1) / gridDim.x;
+  const long b_lo = vi ? (long)blockIdx.x * per_cta : 0;
+  const long b_hi = vi ? (b_lo + per_cta < (long)A.B ? b_lo + per_cta : (long)A.B) : (long)A.B;
+
   for (int si = 0; si < A.S; ++si) {
     const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
+    const int vi_n = vi ? si + 1 : 0;
     // ---- stage this parameter set's weight image (one bulk copy) ------------------------------
-    __syncthreads();  // both tiles are done with the previous image
+    __syncthreads();  // both tiles are done with the previous image (and, in vi mode, sample)
+    if (tid == 0) cta_queue = 0;
+    __syncthreads();
     if (tid == 0) {
       const uint32_t bytes = (uint32_t)img_floats * 4u;
       tc::mbar_expect_tx(&load_bar, bytes);
@@ -411,6 +417,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
     Lane ln;
     ln.has = false;
     ln.unit = -1;
+    ln.b = 0;
     ln.out = nullptr;
     ln.ei = 0;
     ln.status = 0; ln.n_acc = 0; ln.n_rej = 0; ln.n_saved = 0;
@@ -441,11 +448,11 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         if (m) {
           const int leader = __ffs(m) - 1;
           int base = 0;
-          if (lane_id == leader) base = atomicAdd(&queue[s], __popc(m));
+          if (lane_id == leader) base = vi ? atomicAdd(&cta_queue, __popc(m)) : atomicAdd(&queue[s], __popc(m));
           base = __shfl_sync(0xffffffffu, base, leader);
-          const long b = (long)base + __popc(m & ((1u << lane_id) - 1u));
+          const long b = b_lo + (long)base + __popc(m & ((1u << lane_id) - 1u));
           if (want) {
-            if (b < A.B) {
+            if (b < b_hi) {
               lane_bind(ln, A, t_shared, s, b);
               ln.t = (double)ln.in.t_obs[0];
               t_bound = (double)ln.in.t_obs[T - 1];
@@ -453,9 +460,9 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               attempts = 0; kink_cur = 1; h_abs = 0.0;
               rk_n = 0; rk_ss = 0;
               if (SOLVER == HODE_SOLVER_RK4) {
-                if (ln.out) store_row6(ln.out, ln.y);
+                emit_row(A, ln.out, ln.b, 0, ln.y, vi_n);
                 ln.ei = 1;
-                if (T < 2) lane_finish(ln, A);
+                if (T < 2) lane_finish(ln, A, vi_n);
               } else if (clip && T <= 64 && any_series(ln.in)) {
                 kink_mask = build_kink_mask(ln.in);
               }
@@ -603,7 +610,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
 #pragma unroll
             for (int i = 0; i < NS; ++i) k[0][i] = d[i];
             while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t) {
-              if (ln.out) store_row6(ln.out + (size_t)ln.ei * NS, ln.y);
+              emit_row(A, ln.out, ln.b, ln.ei, ln.y, vi_n);
               ++ln.ei;
             }
             float v0[NS], v1[NS];
@@ -651,17 +658,17 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           if (++rk_ss == nsub) {
             rk_ss = 0;
             ++rk_n;
-            if (ln.out) store_row6(ln.out + (size_t)rk_n * NS, ln.y);
+            emit_row(A, ln.out, ln.b, rk_n, ln.y, vi_n);
             ln.ei = rk_n + 1;
-            if (rk_n + 1 >= T) lane_finish(ln, A);
+            if (rk_n + 1 >= T) lane_finish(ln, A, vi_n);
           }
         }
         continue;
       }
       if (init) {
-        if (!(t < t_bound)) lane_finish(ln, A);   // T == 1 or zero-length span
+        if (!(t < t_bound)) lane_finish(ln, A, vi_n);   // T == 1 or zero-length span
       } else if (ln.has && !run) {
-        lane_finish(ln, A);                         // step too small / budget exhausted
+        lane_finish(ln, A, vi_n);                         // step too small / budget exhausted
       } else if (run) {
         float e2 = 0.f;
         bool finite = true;
@@ -703,7 +710,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
                     yo[i] = fmaf(hf, poly, ln.y[i]);
                   }
                 }
-                if (ln.out) store_row6(ln.out + (size_t)ln.ei * NS, yo);
+                emit_row(A, ln.out, ln.b, ln.ei, yo, vi_n);
                 ++ln.ei;
               }
             }
@@ -717,15 +724,15 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             ln.t = t_new;
             h_abs *= (double)factor;
             need_stop = true;
-            if (t_new - t_bound >= 0) lane_finish(ln, A);
+            if (t_new - t_bound >= 0) lane_finish(ln, A, vi_n);
           } else {
-            lane_finish(ln, A);
+            lane_finish(ln, A, vi_n);
           }
         } else {
           ++ln.n_rej;
           if (!finite || !(err == err)) {
             ln.status = HODE_ST_STEP_TOO_SMALL;
-            lane_finish(ln, A);
+            lane_finish(ln, A, vi_n);
           } else {
             h_abs *= (double)fmaxf(0.2f, 0.9f * powf(err, -0.2f));
             prev_rejected = true;

@@ -187,6 +187,19 @@ class HybridODENN(nn.Module):
         """All S sampled parameter sets in ONE launch -> [S,B,T,6] (the VI sweep of
         inference/vi.py:294-304 without the Python loop)."""
         dev = self._cuda_device(initial_state, t_span)
+        theta, W = self._stack_samples(samples, dev)
+        traj, info = ops.rollout(
+            initial_state if initial_state.dim() == 2 else initial_state.unsqueeze(0), t_span,
+            external_inputs, theta, W,
+            hidden=self.nn_residual.hidden_dim, layers=self.nn_residual.n_layers, solver=solver,
+            rtol=rtol, atol=atol, n_substeps=kernel_opts.get("n_substeps", self.rk4_substeps),
+            kinks=kernel_opts.get("kinks", self.kinks),
+            precision=kernel_opts.get("precision", self.precision),
+            max_steps=kernel_opts.get("max_steps", 0), device=dev)
+        self.last_info = info
+        return traj
+
+    def _stack_samples(self, samples: List[Dict[str, torch.Tensor]], dev: torch.device):
         thetas, Ws = [], []
         keep = self.skip_zero_nn
         self.skip_zero_nn = False
@@ -197,16 +210,32 @@ class HybridODENN(nn.Module):
                 Ws.append(W)
         finally:
             self.skip_zero_nn = keep
-        traj, info = ops.rollout(
-            initial_state if initial_state.dim() == 2 else initial_state.unsqueeze(0), t_span,
-            external_inputs, torch.stack(thetas).to(dev), torch.stack(Ws).to(dev),
-            hidden=self.nn_residual.hidden_dim, layers=self.nn_residual.n_layers, solver=solver,
-            rtol=rtol, atol=atol, n_substeps=kernel_opts.get("n_substeps", self.rk4_substeps),
+        return torch.stack(thetas).to(dev), torch.stack(Ws).to(dev)
+
+    def predictive_with_param_samples(self, samples: List[Dict[str, torch.Tensor]],
+                                      initial_state: torch.Tensor, t_span: torch.Tensor,
+                                      external_inputs: Optional[Dict[str, torch.Tensor]] = None,
+                                      solver: str = "dopri5", rtol: float = 1e-6,
+                                      atol: float = 1e-8, **kernel_opts
+                                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Mean and unbiased std over the S sampled parameter sets, reduced inside the kernel
+        (hode_vi_predictive): what inference/vi.py:291-310 and models/bayes.py:196-212 compute
+        with a Python loop, a stack and torch.mean/std."""
+        dev = self._cuda_device(initial_state, t_span)
+        squeeze = initial_state.dim() == 1
+        theta, W = self._stack_samples(samples, dev)
+        mean, std, info = ops.vi_predictive(
+            initial_state.unsqueeze(0) if squeeze else initial_state, t_span, external_inputs,
+            theta, W, hidden=self.nn_residual.hidden_dim, layers=self.nn_residual.n_layers,
+            solver=solver, rtol=rtol, atol=atol,
+            n_substeps=kernel_opts.get("n_substeps", self.rk4_substeps),
             kinks=kernel_opts.get("kinks", self.kinks),
             precision=kernel_opts.get("precision", self.precision),
             max_steps=kernel_opts.get("max_steps", 0), device=dev)
         self.last_info = info
-        return traj
+        if kernel_opts.get("check_status", self.check_status):
+            self._warn_failures(info)
+        return (mean.squeeze(0), std.squeeze(0)) if squeeze else (mean, std)
 
     # ------------------------------------------------------------------ loss
     def loss(self, batch: Dict[str, torch.Tensor], lambda1: float = 1.0, lambda2: float = 1.0,

@@ -233,6 +233,47 @@ def saved_steps(tape: RolloutTape):
     return n, t
 
 
+def vi_predictive(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
+                  theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
+                  solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
+                  kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
+                  device: Optional[torch.device] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor, RolloutInfo]:
+    """Posterior-predictive mean and unbiased std over the S parameter sets theta [S,17] /
+    W [S,P], reduced inside the rollout kernel (hode_vi_predictive); the [S,B,T,6] stack of
+    reference inference/vi.py:306 is never materialised.  Returns (mean, std, info), [B,T,6]."""
+    device = torch.device(device) if device is not None else y0.device
+    _require_cuda(device)
+    if solver.lower() not in SOLVERS:
+        raise HodeError(f"solver '{solver}' is not implemented on the GPU path; available: "
+                        f"{sorted(SOLVERS)}")
+    if theta.dim() != 2:
+        raise ValueError("vi_predictive() needs stacked parameter sets: theta [S,17], W [S,P]")
+    cfg, bufs = prepare(y0, t_obs, inputs, theta, W, hidden, layers, device)
+    cfg.solver = SOLVERS[solver.lower()]
+    cfg.rtol, cfg.atol = float(rtol), float(atol)
+    cfg.n_substeps = int(n_substeps)
+    cfg.max_steps = int(max_steps)
+    cfg.kink_mode = KINKS[kinks]
+    if cfg.mlp != _lib.MLP_NONE:
+        cfg.mlp = PRECISIONS[precision]
+    B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
+    with torch.cuda.device(device):
+        mean = torch.empty((B, T, 6), dtype=torch.float32, device=device)
+        std = torch.empty((B, T, 6), dtype=torch.float32, device=device)
+        status = torch.empty((S, B), dtype=torch.int32, device=device)
+        counters = torch.empty((2, S, B), dtype=torch.int32, device=device)
+        ws_bytes = workspace_bytes(cfg)[0]
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
+        rc = 0 if B == 0 else _lib.lib().hode_vi_predictive(
+            ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
+            _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
+            _ptr(mean), _ptr(std), _ptr(status), _ptr(counters), _ptr(ws), ws_bytes,
+            _stream(device))
+    _lib.check(rc, "hode_vi_predictive")
+    return mean, std, RolloutInfo(status, counters[0], counters[1])
+
+
 def rhs(t: torch.Tensor, state: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
         theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
         device: Optional[torch.device] = None, part: int = 0) -> torch.Tensor:

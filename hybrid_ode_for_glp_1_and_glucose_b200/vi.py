@@ -18,14 +18,9 @@ def predictive_from_samples(model, samples: List[Dict[str, torch.Tensor]], initi
                             time_points, external_inputs=None, **kernel_opts
                             ) -> Tuple[torch.Tensor, torch.Tensor]:
     """mean / unbiased std over parameter samples (reference inference/vi.py:306-310)."""
-    squeeze = initial_state.dim() == 1
     with torch.no_grad():
-        preds = model.forward_with_param_samples(samples, initial_state, time_points,
-                                                 external_inputs, **kernel_opts)
-    mean, std = preds.mean(dim=0), preds.std(dim=0)
-    if squeeze:
-        mean, std = mean.squeeze(0), std.squeeze(0)
-    return mean, std
+        return model.predictive_with_param_samples(samples, initial_state, time_points,
+                                                   external_inputs, **kernel_opts)
 
 
 class VariationalInference:

@@ -182,13 +182,17 @@ int hode_rhs_vjp(const hode_cfg* cfg, const float* t, const float* state, const 
 /*
  * Posterior-predictive sweep with the mean / unbiased std over the S parameter sets
  * reduced on the fly (reference inference/vi.py:291-310, models/bayes.py:196-212):
- * the [S,B,T,6] stack is never materialised.
- *   mean [B,T,6] out, std [B,T,6] out, status [S,B] out (may be NULL).
+ * the [S,B,T,6] stack is never materialised.  Every trajectory is owned by one CTA for all S
+ * sets and updated in a fixed order (Welford): no atomics, bit-reproducible.  Failed
+ * (s, b) units enter the statistics as the zero-padded rows the reference would stack.
+ *   mean [B,T,6] out, std [B,T,6] out (NaN when S == 1, like torch.std), status [S,B] out
+ *   (may be NULL), counters [2,S,B] out (may be NULL); workspace as for hode_rollout_fwd.
  */
 int hode_vi_predictive(const hode_cfg* cfg, const float* y0, const float* t_obs,
                        const float* u_meal, const float* u_tvns, const float* u_gd,
                        const float* theta, const float* W, float* mean, float* std_out,
-                       int32_t* status, int32_t* counters, void* stream);
+                       int32_t* status, int32_t* counters, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /*
  * One batched evaluation of f_physio + g_NN: replaces HybridODENN.ode_residual

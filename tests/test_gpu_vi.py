@@ -1,0 +1,109 @@
+"""GPU tests of the fused posterior-predictive sweep (hode_vi_predictive) and of the VI call
+sites (reference inference/vi.py:60-118,274-312, models/bayes.py:178-214)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cohort, golden, random_mlp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _sets(S, seed=0, spread=0.02):
+    rng = np.random.default_rng(seed)
+    theta0 = golden("rhs_mech")["theta"]
+    theta = np.tile(theta0, (S, 1)) * (1 + spread * rng.normal(0, 1, (S, 17))).astype(np.float32)
+    W0 = random_mlp(64, 4, seed=seed + 1, out_std=0.05)
+    W = (W0[None, :] + 0.01 * rng.normal(0, 1, (S, W0.size))).astype(np.float32)
+    return theta.astype(np.float32), W
+
+
+@pytest.mark.parametrize("precision,solver,B", [("fp32", "dopri5", 300), ("tf32x3", "dopri5", 700),
+                                                ("fp32", "rk4", 130), ("tf32x3", "rk4", 300)])
+def test_fused_mean_std_equals_stack_statistics(dev, precision, solver, B):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    S, T = 7, 21
+    y0, t, ins = cohort(B, T, seed=4, horizon=2.0)
+    theta, W = _sets(S, seed=8)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    tin = {k: tt(v) for k, v in ins.items()}
+    kw = dict(solver=solver, precision=precision, device=dev, n_substeps=2)
+    stack, info = ops.rollout(tt(y0), tt(t), tin, tt(theta), tt(W), **kw)
+    mean, std, info2 = ops.vi_predictive(tt(y0), tt(t), tin, tt(theta), tt(W), **kw)
+    assert bool((info.status == 0).all()) and bool((info2.status == 0).all())
+    assert torch.equal(info.n_accept, info2.n_accept)
+    ref_mean = stack.double().mean(dim=0)
+    ref_std = stack.double().std(dim=0)
+    scale = stack.abs().amax(dim=(0, 2), keepdim=True)[0].double() + 1e-30
+    assert float(((mean.double() - ref_mean).abs() / scale).max()) < 1e-6
+    assert float(((std.double() - ref_std).abs() / scale).max()) < 2e-6
+    # bit-reproducible
+    mean2, std2, _ = ops.vi_predictive(tt(y0), tt(t), tin, tt(theta), tt(W), **kw)
+    assert torch.equal(mean, mean2) and torch.equal(std, std2)
+
+
+def test_fused_edge_cases(dev):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    y0, t, ins = cohort(40, 9, seed=5, horizon=1.0)
+    theta, W = _sets(3, seed=9)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    tin = {k: tt(v) for k, v in ins.items()}
+    # S == 1: mean is the rollout, std is NaN exactly like torch.std over one sample
+    mean, std, _ = ops.vi_predictive(tt(y0), tt(t), tin, tt(theta[:1]), tt(W[:1]), device=dev)
+    one, _ = ops.rollout(tt(y0), tt(t), tin, tt(theta[0]), tt(W[0]), device=dev)
+    assert torch.equal(mean, one) and bool(torch.isnan(std).all())
+    # a failing parameter set enters the statistics as the zero-padded rows the reference stacks
+    theta_bad = theta.copy()
+    theta_bad[1, 9] = -7.0   # K_m < 0: pole of G/(K_m+G) near G = 7
+    stack, info = ops.rollout(tt(y0), tt(t), tin, tt(theta_bad), tt(W), device=dev, max_steps=400)
+    mean, std, info2 = ops.vi_predictive(tt(y0), tt(t), tin, tt(theta_bad), tt(W), device=dev,
+                                         max_steps=400)
+    assert bool((info.status[1] != 0).any()) and torch.equal(info.status, info2.status)
+    ok = torch.isfinite(stack).all(dim=0)
+    ref_mean = stack.double().mean(dim=0)
+    scale = stack.abs().amax().double()
+    assert float(((mean.double() - ref_mean)[ok].abs().max()) / scale) < 1e-6
+
+
+def test_vi_call_sites(dev):
+    """VariationalInference.posterior_predictive / elbo / train_step and
+    compute_posterior_predictive run through the fused sweep with the reference's signatures."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import (HybridODENN, VariationalInference,
+                                                      compute_posterior_predictive)
+    priors = {f"ode_{n}": {"mean": v, "std": 0.05 * v} for n, v in
+              dict(a_GI=0.0104, k_I=0.025, rho=0.003, E_max=0.1, EC_50=50.0, V_max=9.0, K_m=7.0,
+                   k_L=0.02).items()}
+    torch.manual_seed(0)
+    m = HybridODENN(use_variational=True, prior_params=priors, device=dev)
+    y0, t, ins = cohort(16, 13, seed=6, horizon=1.0)
+    to = lambda a: torch.from_numpy(a).to(dev)
+    ext = {k: to(v) for k, v in ins.items()}
+    vi = VariationalInference(m, device=dev)
+    torch.manual_seed(1)
+    mean, std = vi.posterior_predictive(to(y0), to(t), ext, n_samples=6)
+    assert mean.shape == (16, 13, 6) and std.shape == (16, 13, 6)
+    assert bool(torch.isfinite(mean).all()) and bool((std >= 0).all()) and float(std.max()) > 0
+    # same seed, explicit stack: identical draws -> same statistics
+    torch.manual_seed(1)
+    samples = [m.variational_params.sample(1)[0] for _ in range(6)]
+    stack = m.forward_with_param_samples(samples, to(y0), to(t), ext)
+    scale = float(stack.abs().max())
+    assert float((mean - stack.mean(0)).abs().max()) / scale < 1e-6
+    assert float((std - stack.std(0)).abs().max()) / scale < 2e-6
+    mean1, std1 = compute_posterior_predictive(m, to(y0[0]), to(t), {k: v[0:1] for k, v in ext.items()},
+                                               n_samples=4)
+    assert mean1.shape == (13, 6) and std1.shape == (13, 6)
+    batch = {"initial_state": to(y0), "observations": mean.clone(), "time_points": to(t),
+             "external_inputs": ext}
+    elbo, comp = vi.elbo(batch, n_samples=3)
+    assert torch.isfinite(elbo) and set(comp) == {"elbo", "kl", "log_likelihood"}
+    before = {k: v.detach().clone() for k, v in m.variational_params.state_dict().items()}
+    out = vi.train_step(batch, n_samples=2)
+    assert set(out) == {"loss", "elbo", "kl", "log_likelihood"}
+    assert any(not torch.equal(before[k], v) for k, v in m.variational_params.state_dict().items())
