@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hybrid_fwd", choices=["hybrid_fwd", "mech_rk4"])
+    ap.add_argument("--workload", default="hybrid_fwd", choices=["hybrid_fwd", "hybrid_fwdbwd", "mech_rk4"])
     ap.add_argument("--traj-per-gpu", type=int, default=0)
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -50,6 +50,10 @@ WORKLOADS = {
     # 262 144 trajectories (the config's whole cohort on ONE GPU; weak scaling over N)
     "hybrid_fwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip",
                        nn=True, name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd, 262144 traj/GPU, T=61"),
+    # the same with the discrete adjoint (hode_rollout_bwd): 32 768 trajectories per GPU as in
+    # configs/default.yaml on 8 GPUs (262 144 / 8)
+    "hybrid_fwdbwd": dict(B=32768, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip", nn=True, bwd=True,
+                          name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd+adjoint, 32768 traj/GPU, T=61"),
     # configs/ablation_no_nn.yaml-shaped: mechanistic only, RK4, 4 substeps per 5-min interval
     "mech_rk4": dict(B=1048576, T=61, solver="rk4", n_substeps=4, nn=False,
                      name="ablation_no_nn mechanistic rk4 4 substeps, 1048576 traj/GPU, T=61"),
@@ -61,7 +65,7 @@ def make_workload(kind: str, B: int, seed: int):
     w = dict(WORKLOADS[kind])
     if B:
         w["B"] = B
-    y0, t, ins = cohort(w["B"], w["T"], seed=seed, tvns=(kind == "hybrid_fwd"))
+    y0, t, ins = cohort(w["B"], w["T"], seed=seed, tvns=(kind != "mech_rk4"))
     W = random_mlp(64, 4, seed=1234, out_std=0.05) if w["nn"] else None
     w.update(y0=y0, t=t, ins=ins, theta=THETA_DEFAULT.copy(), W=W)
     return w
@@ -212,8 +216,16 @@ def run_ours(args):
     else:
         kw.update(rtol=w["rtol"], atol=w["atol"], kinks=w["kinks"], precision=args.precision)
 
+    bwd = bool(w.get("bwd"))
+    d_g = torch.full((B, T, 6), 1.0 / (B * T * 6), dtype=torch.float32, device=dev) if bwd else None
+    grads = {}
+
     def step():
-        return ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, **kw)
+        if not bwd:
+            return ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, **kw)
+        traj, info, tape = ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, save_steps=True, **kw)
+        grads["out"] = ops.rollout_bwd(tape, d_g)      # grad of mean(traj) w.r.t. y0, theta, W
+        return traj, info
 
     def barrier():
         if world > 1:
@@ -238,7 +250,10 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
-    launches = args.steps
+    # kernels of ours per step: rollout (+ weight-image prep on the tensor-core path)
+    # (+ adjoint sweep + partial-gradient reduction)
+    per_step = (2 if (w["nn"] and args.precision != "fp32") else 1) + (2 if bwd else 0)
+    launches = args.steps * per_step
 
     # ---- e2e: host buffers in, host result out, through the C ABI host entry --------------
     cfg, _ = ops.prepare(h_y0, h_t, h_ins, h_theta, h_W, 64, 4, torch.device("cpu"))
@@ -269,10 +284,55 @@ def run_ours(args):
         e2e_step()          # synchronises its stream before returning
     barrier()
     e2e_s = time.perf_counter() - t0
-    launches += e2e_steps + 1
+    launches += (e2e_steps + 1) * (2 if (w["nn"] and args.precision != "fp32") else 1)
     e2e_attempts = float(h_cnt.sum().item())
     h2d = sum(x.numel() * 4 for x in [h_y0, h_t, h_theta] + list(h_ins.values()) + ([h_W] if h_W is not None else []))
     d2h = h_traj.numel() * 4 + h_status.numel() * 4 + h_cnt.numel() * 4
+
+    # ---- the other legs of the metric, per GPU, short (skipped with --no-extra) -------------
+    also = {}
+    if not args.no_extra and w["nn"] and not bwd:
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n, out
+        Bx = min(B, 32768)
+        sl = slice(0, Bx)
+        x_ins = {k: v[sl].contiguous() for k, v in d_ins.items()}
+        x_g = torch.full((Bx, T, 6), 1.0 / (Bx * T * 6), dtype=torch.float32, device=dev)
+
+        def fwdbwd():
+            _, info_x, tape = ops.rollout(d_y0[sl], d_t, x_ins, d_theta, d_W, save_steps=True, **kw)
+            g = ops.rollout_bwd(tape, x_g)
+            return info_x, g
+        ms, (info_x, _) = timed(fwdbwd, 2)
+        att = float((info_x.n_accept.sum() + info_x.n_reject.sum()).item())
+        also["fwd_bwd"] = {"value": att / (ms * 1e-3), "unit": "trajectory-steps/s", "per": "GPU",
+                           "trajectories": Bx, "ms_per_step": ms,
+                           "what": "hode_rollout_fwd (3xTF32, steps recorded) + hode_rollout_bwd "
+                                   "(FP32 discrete adjoint: grad y0, theta[17], W[13510])",
+                           "algorithmic_tflops": att * 3 * FLOP_ATTEMPT_HYBRID / (ms * 1e-3) / 1e12}
+        launches += 3 * 4
+        Sx = 8
+        rng = np.random.default_rng(7)
+        thS = torch.from_numpy((w["theta"][None, :] * (1 + 0.02 * rng.normal(0, 1, (Sx, 17)))).astype(np.float32)).to(dev)
+        WS = torch.from_numpy((w["W"][None, :] + 0.01 * rng.normal(0, 1, (Sx, w["W"].size))).astype(np.float32)).to(dev)
+
+        def vi():
+            return ops.vi_predictive(d_y0[sl], d_t, x_ins, thS, WS, **kw)
+        ms, (_, _, info_v) = timed(vi, 1)
+        att = float((info_v.n_accept.sum() + info_v.n_reject.sum()).item())
+        also["vi_predictive"] = {"value": att / (ms * 1e-3), "unit": "trajectory-steps/s", "per": "GPU",
+                                 "samples": Sx, "trajectories": Bx, "ms_per_step": ms,
+                                 "what": "hode_vi_predictive: S parameter sets x B trajectories, mean/std "
+                                         "reduced in-kernel (3xTF32)"}
+        launches += 2 * 2
 
     # ---- reduce over ranks: MAX time, SUM work ----------------------------------------------
     stats = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
@@ -295,7 +355,7 @@ def run_ours(args):
         sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         ms_kernel = ms_total / args.steps          # one launch per step, nothing else on the stream
         if w["nn"]:
-            flops = attempts_per_step * FLOP_ATTEMPT_HYBRID
+            flops = attempts_per_step * FLOP_ATTEMPT_HYBRID * (3.0 if bwd else 1.0)
             achieved = flops / (ms_kernel * 1e-3) / 1e12
             if args.precision == "fp32":
                 peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
@@ -312,7 +372,9 @@ def run_ours(args):
                 bound = "tensor"
             roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "kernel": "rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel<x3,dopri5>",
+                    "kernel": ("rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel<x3,dopri5>")
+                              + (" + rollout_bwd_kernel<dopri5> (FP32 CUDA cores; the tensor-pipe peak is "
+                                 "the stated target, see DESIGN.md)" if bwd else ""),
                     "tensor_passes_per_algorithmic_pass": 3 if args.precision == "tf32x3" else 1,
                     "kernel_ms": ms_kernel,
                     "algorithmic_flop_per_launch": flops}
@@ -344,6 +406,8 @@ def run_ours(args):
             "roofline": roof,
             "trajectories_per_sec": B * world * args.steps / (ms_total * 1e-3),
         }
+        if also:
+            line["also"] = also
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n = cpu_sample_size(w, threads, target_s=12.0)

@@ -306,53 +306,122 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   rc = check_inputs(cfg, u_meal_h, u_tvns_h, u_gd_h, W_h);
   if (rc) return rc;
   if (cfg->save_steps) return fail(HODE_E_UNSUPPORTED, "save_steps is not available on the host entry");
-  const Workspace wsp = fwd_workspace(cfg);
+  if (cfg->n_traj == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t B = cfg->n_traj, T = cfg->n_obs, S = cfg->n_samples;
   const size_t P = cfg->mlp != HODE_MLP_NONE ? hode_mlp_param_count(cfg->nn_hidden, cfg->nn_layers) : 0;
   const float* uh[3] = {u_meal_h, u_tvns_h, u_gd_h};
-  size_t ub[3];
+  size_t urow[3];  // bytes per trajectory of each input channel
   for (int ch = 0; ch < 3; ++ch)
-    ub[ch] = cfg->in_mode[ch] == HODE_IN_SERIES ? B * T * 4 : cfg->in_mode[ch] == HODE_IN_CONST ? B * 4 : 0;
-  const size_t sz_y0 = B * 6 * 4, sz_t = (cfg->t_per_traj ? B * T : T) * 4, sz_th = S * 17 * 4,
-               sz_W = S * P * 4, sz_traj = S * B * T * 6 * 4, sz_st = S * B * 4, sz_cn = 2 * S * B * 4;
-  size_t off = 0, o_y0, o_t, o_u[3], o_th, o_W, o_traj, o_st, o_cn;
-  o_y0 = off; off = align_up(off + sz_y0, 256);
-  o_t = off; off = align_up(off + sz_t, 256);
-  for (int ch = 0; ch < 3; ++ch) { o_u[ch] = off; off = align_up(off + ub[ch], 256); }
-  o_th = off; off = align_up(off + sz_th, 256);
-  o_W = off; off = align_up(off + sz_W, 256);
-  o_traj = off; off = align_up(off + sz_traj, 256);
-  o_st = off; off = align_up(off + sz_st, 256);
-  o_cn = off; off = align_up(off + sz_cn, 256);
-  const size_t o_ws = off; off = align_up(off + wsp.total, 256);
+    urow[ch] = cfg->in_mode[ch] == HODE_IN_SERIES ? T * 4 : cfg->in_mode[ch] == HODE_IN_CONST ? 4 : 0;
+
+  // Trajectory chunks are pipelined over a few streams: while chunk c integrates, chunk c+1 is
+  // on its way in and chunk c-1 on its way out (the two copy engines and the SMs overlap, and
+  // the next chunk's CTAs fill SMs that the previous chunk's stragglers have left).  Parameter
+  // sweeps (S > 1) keep the [S,B,...] layouts contiguous and run as one chunk.
+  constexpr int MAX_STREAMS = 3;
+  int n_chunks = 1;
+  if (S == 1) {
+    n_chunks = (int)(B / 49152);
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 8) n_chunks = 8;
+  }
+  const int n_streams = n_chunks < MAX_STREAMS ? n_chunks : MAX_STREAMS;
+  const size_t rows_max = (B + n_chunks - 1) / n_chunks;
+  hode_cfg sub = *cfg;
+  sub.n_traj = (int32_t)rows_max;
+  const Workspace wsp = fwd_workspace(&sub);
+
+  const size_t sz_t_shared = cfg->t_per_traj ? 0 : T * 4, sz_th = S * 17 * 4, sz_W = S * P * 4;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_t = carve(sz_t_shared), o_th = carve(sz_th), o_W = carve(sz_W);
+  const size_t o_y0 = carve(B * 6 * 4), o_trow = carve(cfg->t_per_traj ? B * T * 4 : 0);
+  size_t o_u[3];
+  for (int ch = 0; ch < 3; ++ch) o_u[ch] = carve(B * urow[ch]);
+  const size_t o_traj = carve(S * B * T * 6 * 4), o_st = carve(S * B * 4), o_cn = carve(2 * S * B * 4);
+  size_t o_ws[MAX_STREAMS];
+  for (int i = 0; i < n_streams; ++i) o_ws[i] = carve(wsp.total);
+
   char* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, off ? off : 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
-#define H2D(dst, src, n) \
-  if ((n) && (e = cudaMemcpyAsync(d + (dst), (src), (n), cudaMemcpyHostToDevice, st)) != cudaSuccess) goto done
-  H2D(o_y0, y0_h, sz_y0);
-  H2D(o_t, t_obs_h, sz_t);
-  for (int ch = 0; ch < 3; ++ch) H2D(o_u[ch], uh[ch], ub[ch]);
-  H2D(o_th, theta_h, sz_th);
-  H2D(o_W, W_h, sz_W);
-#undef H2D
-  rc = hode_rollout_fwd(cfg, (float*)(d + o_y0), (float*)(d + o_t),
-                        ub[0] ? (float*)(d + o_u[0]) : nullptr, ub[1] ? (float*)(d + o_u[1]) : nullptr,
-                        ub[2] ? (float*)(d + o_u[2]) : nullptr, (float*)(d + o_th),
-                        sz_W ? (float*)(d + o_W) : nullptr, (float*)(d + o_traj),
-                        (int32_t*)(d + o_st), (int32_t*)(d + o_cn), wsp.total ? d + o_ws : nullptr,
-                        wsp.total, stream);
-  if (rc) { cudaFreeAsync(d, st); cudaStreamSynchronize(st); return rc; }
-  if (sz_traj && (e = cudaMemcpyAsync(traj_h, d + o_traj, sz_traj, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
-  if (status_h && sz_st && (e = cudaMemcpyAsync(status_h, d + o_st, sz_st, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
-  if (counters_h && sz_cn && (e = cudaMemcpyAsync(counters_h, d + o_cn, sz_cn, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto done;
+  cudaStream_t xs[MAX_STREAMS] = {st, nullptr, nullptr};
+  cudaEvent_t ev_ready = nullptr, ev_done[MAX_STREAMS] = {nullptr, nullptr, nullptr};
+  int lib_rc = 0;
+#define CK(call) if ((e = (call)) != cudaSuccess) goto done
+  for (int i = 1; i < n_streams; ++i) CK(cudaStreamCreateWithFlags(&xs[i], cudaStreamNonBlocking));
+  // shared small inputs on the caller's stream, then fork
+  if (sz_t_shared) CK(cudaMemcpyAsync(d + o_t, t_obs_h, sz_t_shared, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_th, theta_h, sz_th, cudaMemcpyHostToDevice, st));
+  if (sz_W) CK(cudaMemcpyAsync(d + o_W, W_h, sz_W, cudaMemcpyHostToDevice, st));
+  if (n_streams > 1) {
+    CK(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_ready, st));
+    for (int i = 1; i < n_streams; ++i) CK(cudaStreamWaitEvent(xs[i], ev_ready, 0));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t lo = (size_t)c * rows_max, hi = lo + rows_max < B ? lo + rows_max : B;
+    if (lo >= hi) break;
+    const size_t rows = hi - lo;
+    cudaStream_t cs = xs[c % n_streams];
+    CK(cudaMemcpyAsync(d + o_y0 + lo * 24, y0_h + lo * 6, rows * 24, cudaMemcpyHostToDevice, cs));
+    if (cfg->t_per_traj)
+      CK(cudaMemcpyAsync(d + o_trow + lo * T * 4, t_obs_h + lo * T, rows * T * 4, cudaMemcpyHostToDevice, cs));
+    for (int ch = 0; ch < 3; ++ch)
+      if (urow[ch])
+        CK(cudaMemcpyAsync(d + o_u[ch] + lo * urow[ch], (const char*)uh[ch] + lo * urow[ch], rows * urow[ch],
+                           cudaMemcpyHostToDevice, cs));
+    sub.n_traj = (int32_t)rows;
+    // S == 1 when chunked: unit index == trajectory index, so every output is a contiguous slice
+    lib_rc = hode_rollout_fwd(
+        &sub, (float*)(d + o_y0 + lo * 24),
+        cfg->t_per_traj ? (float*)(d + o_trow + lo * T * 4) : (float*)(d + o_t),
+        urow[0] ? (float*)(d + o_u[0] + lo * urow[0]) : nullptr,
+        urow[1] ? (float*)(d + o_u[1] + lo * urow[1]) : nullptr,
+        urow[2] ? (float*)(d + o_u[2] + lo * urow[2]) : nullptr, (float*)(d + o_th),
+        sz_W ? (float*)(d + o_W) : nullptr, (float*)(d + o_traj + lo * T * 24), (int32_t*)(d + o_st + lo * 4),
+        // chunk c keeps its [2, rows] counters at byte offset 2 * lo * 4 of the [2, B] buffer
+        (int32_t*)(d + o_cn + lo * 8), wsp.total ? d + o_ws[c % n_streams] : nullptr,
+        wsp.total, (void*)cs);
+    if (lib_rc) goto done;
+    CK(cudaMemcpyAsync(traj_h + lo * T * 6, d + o_traj + lo * T * 24, rows * T * 24 * (n_chunks == 1 ? S : 1),
+                       cudaMemcpyDeviceToHost, cs));
+    if (status_h)
+      CK(cudaMemcpyAsync(status_h + lo, d + o_st + lo * 4, rows * 4 * (n_chunks == 1 ? S : 1),
+                         cudaMemcpyDeviceToHost, cs));
+    if (counters_h) {
+      if (n_chunks == 1) {
+        CK(cudaMemcpyAsync(counters_h, d + o_cn, 2 * S * B * 4, cudaMemcpyDeviceToHost, cs));
+      } else {
+        CK(cudaMemcpyAsync(counters_h + lo, d + o_cn + lo * 8, rows * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(counters_h + B + lo, d + o_cn + lo * 8 + rows * 4, rows * 4, cudaMemcpyDeviceToHost, cs));
+      }
+    }
+  }
+  // join
+  for (int i = 1; i < n_streams; ++i) {
+    CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_done[i], xs[i]));
+    CK(cudaStreamWaitEvent(st, ev_done[i], 0));
+  }
+#undef CK
 done:
   cudaFreeAsync(d, st);
   {
-    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaError_t e2 = cudaSuccess;
+    for (int i = 1; i < n_streams; ++i)
+      if (xs[i]) { cudaError_t e3 = cudaStreamSynchronize(xs[i]); if (e2 == cudaSuccess) e2 = e3; }
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    if (e2 == cudaSuccess) e2 = e3;
     if (e == cudaSuccess) e = e2;
   }
+  for (int i = 1; i < n_streams; ++i) {
+    if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+    if (xs[i]) cudaStreamDestroy(xs[i]);
+  }
+  if (ev_ready) cudaEventDestroy(ev_ready);
+  if (lib_rc) return lib_rc;
   if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_fwd_host");
   return 0;
 }

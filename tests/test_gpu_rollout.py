@@ -225,6 +225,37 @@ def test_host_entry_matches_device_entry(dev, oracle):
     assert np.array_equal(counters[0], na) and np.array_equal(counters[1], nr)
 
 
+@pytest.mark.parametrize("per_row_t", [False, True])
+def test_host_entry_chunked_pipeline(dev, oracle, per_row_t):
+    """Above 2 x 49 152 trajectories the host entry pipelines trajectory chunks over several
+    streams; results must equal the one-launch device path bit for bit (ragged last chunk,
+    constant + series inputs, shared and per-row grids, hybrid net on the tensor-core path)."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, ops
+    B, T = 3 * 49152 + 1234, 7
+    y0, t, ins = cohort(B, T, seed=15, horizon=0.5)
+    ins = {"meal": ins["meal"], "GD": np.linspace(0, 900, B).astype(np.float32)}
+    if per_row_t:
+        t = np.ascontiguousarray(np.tile(t, (B, 1)) + np.linspace(0, 0.01, B, dtype=np.float32)[:, None])
+    W = random_mlp(seed=16)
+    theta = oracle.THETA_DEFAULT
+    ref, st_ref, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="rk4", n_substeps=1,
+                                      precision="tf32x3")
+    cfg, _ = ops.prepare(torch.from_numpy(y0), torch.from_numpy(t),
+                         {k: torch.from_numpy(v) for k, v in ins.items()},
+                         torch.from_numpy(theta), torch.from_numpy(W), 64, 4, torch.device("cpu"))
+    cfg.solver, cfg.n_substeps, cfg.mlp = _lib.SOLVER_RK4, 1, _lib.MLP_TF32X3
+    traj = np.empty((B, T, 6), np.float32)
+    status = np.full(B, -1, np.int32)
+    counters = np.full((2, B), -1, np.int32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = _lib.lib().hode_rollout_fwd_host(ctypes.byref(cfg), p(y0), p(t), p(ins["meal"]), None,
+                                          p(ins["GD"]), p(theta), p(W), p(traj), p(status),
+                                          p(counters), None)
+    _lib.check(rc, "hode_rollout_fwd_host")
+    assert np.array_equal(traj, ref) and np.array_equal(status, st_ref)
+    assert np.array_equal(counters[0], na) and np.array_equal(counters[1], nr)
+
+
 def test_full_size_properties_config2(dev, oracle):
     """BASELINE config 2 at full size (1 048 576 trajectories, RK4): size-independent
     properties + an oracle check on a strided subsample."""
