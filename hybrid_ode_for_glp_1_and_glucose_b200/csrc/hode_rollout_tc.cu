@@ -8,7 +8,7 @@
 // cores.  Replaces reference models/hybrid_ode_nn.py:184-256 + models/nn_residual.py:136-146.
 //
 // CTA = 2 tiles x 128 threads (persistent, one CTA per SM).  Per tile, TMEM columns:
-//   [0,64) accumulator D0 | [64,128) A_hi | [128,192) A_lo | [192,256) accumulator D1
+//   [0,64) accumulator D | [64,128) A_hi | [128,192) A_lo | [192,200) constant [1,1,0..] (bias step)
 // Per layer:  epilogue threads read D (tcgen05.ld), add bias, ReLU, split into TF32 hi/lo
 // (round-to-nearest) and write the next layer's A operand straight back to TMEM
 // (tcgen05.st); one elected thread issues  D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32,
@@ -24,21 +24,22 @@
 #include "hode_common.cuh"
 #include "hode_kernels.h"
 #include "hode_tcgen05.cuh"
+#include "hode_tc_mlp.cuh"
 
 namespace hode {
 
 namespace {
-constexpr int TILE = 128;
 constexpr int TILES_PER_CTA = 2;
-constexpr int H = 64;
-constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_D1 = 192, TM_TILE_STRIDE = 256;
 }  // namespace
 
 // ---- weight image ----------------------------------------------------------------------------------
 // floats: [L0: Bhi 4x64x4, Blo][hidden l=1..L-1: Bhi 16x64x4, Blo][out: Bhi 16x16x4, Blo]
-//         [bias: L x 64][bias_out: 16]
+//         [bias blocks: L x (2x64x4)][bias block out: 2x16x4]
 // B chunk-major: element (n, k) of an [N, K] weight at float ((k/4)*N + n)*4 + k%4.
-int tc_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024 + L * 64 + 16; }
+// A bias block is one K = 8 step whose columns 0/1 hold the TF32 hi/lo parts of the bias; it
+// multiplies a constant A block [1, 1, 0, ...] kept in TMEM, so the bias rides on the tensor
+// pipe instead of costing one FADD per accumulator element in the epilogue.
+int tc_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024 + L * 512 + 128; }
 
 __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
                                      int img_floats) {
@@ -62,160 +63,17 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
       dst[o] = __uint_as_float(hi);
       dst[part + o] = __uint_as_float(lo);
     }
-    for (int j = threadIdx.x; j < n_out; j += blockDim.x) bias_dst[j] = w[n_out * n_in + j];
+    for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+      uint32_t hi, lo;
+      tc::split_tf32(w[n_out * n_in + j], hi, lo);
+      bias_dst[j * 4 + 0] = __uint_as_float(hi);   // (n = j, k = 0)
+      bias_dst[j * 4 + 1] = __uint_as_float(lo);   // (n = j, k = 1)
+    }
     w += n_out * n_in + n_out;
     dst += 2 * part;
-    bias_dst += (l == L) ? 16 : H;
+    bias_dst += (l == L) ? 128 : 512;
     n_in = n_out;
   }
-}
-
-// ---- per-tile context -------------------------------------------------------------------------------
-struct TileCtx {
-  const float* img;     // shared-memory weight image
-  uint64_t* mma_bar;    // this tile's MMA-complete mbarrier
-  uint32_t tmem;        // this tile's TMEM column base (lane field 0)
-  uint32_t lane_base;   // (warp%4)*32 << 16
-  uint32_t parity;      // mbarrier phase to wait for next
-  int bar_id;           // named barrier id of the tile
-  int wq;               // warp index inside the tile (warp-uniform)
-  int L;                // hidden layer count
-};
-
-__device__ __forceinline__ void tile_sync(const TileCtx& c) {
-  asm volatile("bar.sync %0, 128;" ::"r"(c.bar_id) : "memory");
-}
-
-// Issue the MMAs of one layer (one elected thread): D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
-// The two correction products are accumulated FIRST, into a still-small accumulator: the tensor
-// core truncates when it adds into D, and measured on B200 (csrc/probe/tc_probe.cu) this order
-// gives max err/sum|a*b| = 1.7e-7 (a plain fp32 FMA chain gives 2.2e-7), against 4.5e-7 when the
-// products are interleaved per k-step and 6.9e-7 when the large product goes first.
-template <bool X3, int N, int KSTEPS>
-__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t b_hi,
-                                            uint32_t b_lo) {
-  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
-  constexpr uint32_t lbo16 = (uint32_t)N;                 // (N*16 bytes) >> 4
-  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-  const uint32_t lo_hi = ((b_hi >> 4) & 0x3FFFu) | (lbo16 << 16);
-  const uint32_t lo_lo = ((b_lo >> 4) & 0x3FFFu) | (lbo16 << 16);
-  if (X3) {
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks)
-      tc::mma_tf32_ts(d, alo + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
-                      idesc, ks == 0 ? 0u : 1u);
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks)
-      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lo + (uint32_t)ks * 2u * lbo16),
-                      idesc, 1u);
-  }
-#pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks)
-    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
-                    idesc, (!X3 && ks == 0) ? 0u : 1u);
-}
-
-// bias + ReLU + TF32 split of 32 accumulator columns, in place: v -> hi bits, lo -> lo bits.
-// Both parts are rounded to nearest TF32 (the tensor core would truncate), so a ~= hi + lo to 2^-22.
-template <bool X3>
-__device__ __forceinline__ void epilogue32(uint32_t* v, uint32_t* lo, const float* bias) {
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
-    const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j4 * 4 + q;
-      const float a = fmaxf(__uint_as_float(v[j]) + bb[q], 0.f);
-      const uint32_t h = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
-      v[j] = h;
-      if (X3) lo[j] = (__float_as_uint(a - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
-    }
-  }
-}
-
-// The residual MLP for the 128 trajectories of a tile (reference models/nn_residual.py:136-146).
-// Every thread of the tile must call this converged.  x: the 9 input features of this thread's
-// trajectory; r: the 6 residuals.
-template <bool X3>
-__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r) {
-  const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
-  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
-  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
-  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
-  const float* img = c.img;
-  const uint32_t img_s = tc::smem_u32(img);
-  const float* bias = img + 2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024;
-  // ---- layer 0 operand: 9 features zero-padded to K = 16 ----------------------------------------
-  {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (k < HODE_NN_IN) tc::split_tf32(x[k], hi[k], lo[k]);
-      else { hi[k] = 0u; lo[k] = 0u; }
-    }
-    HODE_TMEM_ST_X16(t_ahi, hi);
-    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
-  }
-  tc::wait_st();
-  tc::fence_before_sync();
-  tile_sync(c);
-  if (c.wq == 0) {
-    if (tc::elect_one()) {
-      tc::fence_after_sync();
-      issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, img_s, img_s + 1024 * 4);
-      tc::mma_commit(c.mma_bar);
-    }
-    __syncwarp();
-  }
-  uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
-  // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
-#pragma unroll 1
-  for (int l = 0; l < c.L; ++l) {
-    const bool last = (l + 1 == c.L);
-    const uint32_t b_hi = img_s + w_off * 4;
-    const uint32_t b_lo = b_hi + (last ? 1024u : 4096u) * 4u;
-    tc::mbar_wait(c.mma_bar, c.parity);
-    c.parity ^= 1u;
-    tc::fence_after_sync();
-    uint32_t v0[32], v1[32], lo[32];
-    HODE_TMEM_LD_X32(t_d, v0);
-    HODE_TMEM_LD_X32(t_d + 32, v1);
-    tc::wait_ld();
-    epilogue32<X3>(v0, lo, bias + l * H);
-    HODE_TMEM_ST_X32(t_ahi, v0);
-    if (X3) HODE_TMEM_ST_X32(t_alo, lo);
-    epilogue32<X3>(v1, lo, bias + l * H + 32);
-    HODE_TMEM_ST_X32(t_ahi + 32, v1);
-    if (X3) HODE_TMEM_ST_X32(t_alo + 32, lo);
-    tc::wait_st();
-    tc::fence_before_sync();
-    tile_sync(c);
-    if (c.wq == 0) {
-      if (tc::elect_one()) {
-        tc::fence_after_sync();
-        if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
-        else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, b_hi, b_lo);
-        tc::mma_commit(c.mma_bar);
-      }
-      __syncwarp();
-    }
-    w_off += 2 * 4096;
-  }
-  // ---- output layer epilogue: 6 of the 16 accumulator columns ------------------------------------
-  tc::mbar_wait(c.mma_bar, c.parity);
-  c.parity ^= 1u;
-  tc::fence_after_sync();
-  {
-    uint32_t v[8];
-    HODE_TMEM_LD_X8(t_d, v);
-    tc::wait_ld();
-    const float* bo = bias + c.L * H;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) r[i] = __uint_as_float(v[i]) + bo[i];
-  }
-  // The next call overwrites A (tcgen05.st: every MMA has completed) and its layer-0 MMAs write
-  // D only after a tile barrier that every thread reaches after its wait::ld above.
 }
 
 // ---- per-lane trajectory state ---------------------------------------------------------------------
@@ -229,7 +87,28 @@ struct Lane {
   int ei;             // next observation index to emit
   int status, n_acc, n_rej, n_saved;
   bool has;
+  // Inputs of the current step as one linear piece per channel: value(t) = c_v1 + alpha * c_dv
+  // with alpha = (t - c_t1) / c_dt.  Valid whenever a step cannot cross an input kink (RK4, kink
+  // clipping, or no series inputs): the loads happen once per accepted step instead of once per
+  // RK stage, which takes the L2 latency of the input rows off the stage critical path.
+  bool cached;
+  float c_t1, c_dt, c_v1[3], c_dv[3];
 };
+
+// (i0, i0+1): the grid interval the step starts in.  Flat stretches that a step may cross have
+// c_dv == 0, so the value does not depend on which of their intervals is cached.
+__device__ __forceinline__ void lane_cache_inputs(Lane& ln, int i0) {
+  const float t1 = ln.in.t_obs[i0], t2 = ln.in.t_obs[i0 + 1];
+  ln.c_t1 = t1;
+  ln.c_dt = t2 - t1;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    if (ln.in.mode[ch] != HODE_IN_SERIES) continue;
+    const float v1 = ln.in.u[ch][i0], v2 = ln.in.u[ch][i0 + 1];
+    ln.c_v1[ch] = v1;
+    ln.c_dv[ch] = v2 - v1;
+  }
+}
 
 __device__ __forceinline__ float rms6v(const float* v) {
   float s = 0.f;
@@ -245,11 +124,19 @@ __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln,
   const float t32 = (float)te;
   float meal = 0.f, tvns = 0.f, gd = 0.f;
   if (ln.has) {
-    int idx = 0;
-    if (any_series(ln.in)) idx = grid_index_from(ln.in, t32, ln.in.cur);
-    meal = input_channel(ln.in, HODE_CH_MEAL, t32, idx);
-    tvns = input_channel(ln.in, HODE_CH_TVNS, t32, idx);
-    gd = input_channel(ln.in, HODE_CH_GD, t32, idx);
+    if (ln.cached) {
+      // same arithmetic as input_channel(): v1 + ((t - t1) / (t2 - t1)) * (v2 - v1)
+      const float alpha = __fdiv_rn(t32 - ln.c_t1, ln.c_dt);
+      meal = __fadd_rn(ln.c_v1[HODE_CH_MEAL], __fmul_rn(alpha, ln.c_dv[HODE_CH_MEAL]));
+      tvns = __fadd_rn(ln.c_v1[HODE_CH_TVNS], __fmul_rn(alpha, ln.c_dv[HODE_CH_TVNS]));
+      gd = __fadd_rn(ln.c_v1[HODE_CH_GD], __fmul_rn(alpha, ln.c_dv[HODE_CH_GD]));
+    } else {
+      int idx = 0;
+      if (any_series(ln.in)) idx = grid_index_from(ln.in, t32, ln.in.cur);
+      meal = input_channel(ln.in, HODE_CH_MEAL, t32, idx);
+      tvns = input_channel(ln.in, HODE_CH_TVNS, t32, idx);
+      gd = input_channel(ln.in, HODE_CH_GD, t32, idx);
+    }
   }
   float x[HODE_NN_IN], r[NS];
   x[0] = t32;
@@ -280,6 +167,14 @@ __device__ __forceinline__ void lane_bind(Lane& ln, const RolloutArgs& A, const 
                 : A.in_mode[ch] == HODE_IN_CONST ? A.u[ch] + b : nullptr;
   }
   ln.out = A.traj ? A.traj + (size_t)unit * A.T * NS : nullptr;
+  ln.cached = A.solver == HODE_SOLVER_RK4 || A.kink_mode == HODE_KINK_CLIP || !any_series(ln.in);
+  ln.c_t1 = 0.f;
+  ln.c_dt = 1.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    ln.c_v1[ch] = ln.in.mode[ch] == HODE_IN_CONST ? ln.in.u[ch][0] : 0.f;
+    ln.c_dv[ch] = 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i) { ln.y[i] = A.y0[b * NS + i]; ln.cmp[i] = 0.f; }
   ln.ei = 0;
@@ -340,7 +235,7 @@ __device__ __forceinline__ unsigned long long build_kink_mask(const TrajInputs& 
 // which keeps the kernel small enough for the instruction cache.
 // ---------------------------------------------------------------------------------------------------
 template <bool X3, int SOLVER>
-__global__ void __launch_bounds__(TILE* TILES_PER_CTA, 1)
+__global__ void __launch_bounds__(2 * TILE* TILES_PER_CTA, 1)
 rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_floats, int* queue) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* img = reinterpret_cast<float*>(smem_raw);
@@ -355,7 +250,9 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   // warp-uniform by construction; the shuffle lets ptxas keep everything derived from it
   // (tile, TMEM base, barrier ids) in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int tile = warp >> 2, wq = warp & 3;
+  // warpgroups: 0/1 = main warps of tile 0/1 (one trajectory per thread), 2/3 = their helpers
+  const int tile = (warp >> 2) & 1, wq = warp & 3;
+  const bool helper = (warp >> 3) != 0;
 
   if (tid == 0) {
     tc::mbar_init(&mma_bar[0], 1);
@@ -380,8 +277,14 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   c.lane_base = (uint32_t)(wq * 32) << 16;
   c.parity = 0;
   c.bar_id = 1 + tile;
+  c.bar_all = 3 + tile;
   c.wq = wq;
   c.L = A.L;
+  {  // constant A block of the bias k-step: this thread's TMEM lane gets [1, 1, 0, 0, 0, 0, 0, 0]
+    uint32_t ones[8] = {0x3F800000u, 0x3F800000u, 0u, 0u, 0u, 0u, 0u, 0u};
+    HODE_TMEM_ST_X8(c.tmem + c.lane_base + TM_ONES, ones);
+    tc::wait_st();
+  }
 
   constexpr int NSLOT = (SOLVER == HODE_SOLVER_RK4) ? 4 : 6;
   const int T = A.T;
@@ -398,348 +301,387 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   const long b_lo = vi ? (long)blockIdx.x * per_cta : 0;
   const long b_hi = vi ? (b_lo + per_cta < (long)A.B ? b_lo + per_cta : (long)A.B) : (long)A.B;
 
-  for (int si = 0; si < A.S; ++si) {
-    const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
-    const int vi_n = vi ? si + 1 : 0;
-    // ---- stage this parameter set's weight image (one bulk copy) ------------------------------
-    __syncthreads();  // both tiles are done with the previous image (and, in vi mode, sample)
-    if (tid == 0) cta_queue = 0;
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)img_floats * 4u;
-      tc::mbar_expect_tx(&load_bar, bytes);
-      tc::bulk_g2s(img, img_g + (size_t)s * img_floats, bytes, &load_bar);
-    }
-    tc::mbar_wait(&load_bar, load_parity);
-    load_parity ^= 1u;
-    const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
-
-    Lane ln;
-    ln.has = false;
-    ln.unit = -1;
-    ln.b = 0;
-    ln.out = nullptr;
-    ln.ei = 0;
-    ln.status = 0; ln.n_acc = 0; ln.n_rej = 0; ln.n_saved = 0;
-    ln.t = 0.0;
-    ln.in.T = T; ln.in.cur = 0; ln.in.t_obs = A.t_obs;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) { ln.in.mode[ch] = HODE_IN_ABSENT; ln.in.u[ch] = nullptr; }
-#pragma unroll
-    for (int i = 0; i < NS; ++i) { ln.y[i] = 0.f; ln.cmp[i] = 0.f; }
-    bool queue_dry = false;
-    // stage vectors: k[0] = k1 (FSAL) ... k[6] = k7;  RK4 uses k[0..3]
-    float k[7][NS];
-#pragma unroll
-    for (int j = 0; j < 7; ++j)
-#pragma unroll
-      for (int i = 0; i < NS; ++i) k[j][i] = 0.f;
-    double h_abs = 0.0, t_stop = 0.0, t_bound = 0.0;
-    unsigned long long kink_mask = 0ull;
-    int attempts = 0, kink_cur = 1;
-    bool need_init = false, prev_rejected = false, need_stop = true;
-    int rk_n = 0, rk_ss = 0;
-
-    for (;;) {
-      // ---- refill idle lanes from the global queue (warp-aggregated) --------------------------
-      {
-        const bool want = !ln.has && !queue_dry;
-        const unsigned m = __ballot_sync(0xffffffffu, want);
-        if (m) {
-          const int leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane_id == leader) base = vi ? atomicAdd(&cta_queue, __popc(m)) : atomicAdd(&queue[s], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          const long b = b_lo + (long)base + __popc(m & ((1u << lane_id) - 1u));
-          if (want) {
-            if (b < b_hi) {
-              lane_bind(ln, A, t_shared, s, b);
-              ln.t = (double)ln.in.t_obs[0];
-              t_bound = (double)ln.in.t_obs[T - 1];
-              need_init = true; prev_rejected = false; need_stop = true;
-              attempts = 0; kink_cur = 1; h_abs = 0.0;
-              rk_n = 0; rk_ss = 0;
-              if (SOLVER == HODE_SOLVER_RK4) {
-                emit_row(A, ln.out, ln.b, 0, ln.y, vi_n);
-                ln.ei = 1;
-                if (T < 2) lane_finish(ln, A, vi_n);
-              } else if (clip && T <= 64 && any_series(ln.in)) {
-                kink_mask = build_kink_mask(ln.in);
-              }
-            } else {
-              queue_dry = true;
-            }
-          }
-        }
-      }
-      // ---- does this tile still have work? ------------------------------------------------------
-      {
-        const bool any = __any_sync(0xffffffffu, ln.has);
-        if (lane_id == 0) tile_active[tile][wq] = any ? 1 : 0;
-        tile_sync(c);
+  // 512 threads x 128 registers fill the register file; the helper warpgroups hand most of theirs
+  // to the main warpgroups, which carry the per-trajectory integrator state.  Each role's code is
+  // entirely inside its branch so that ptxas allocates registers against the role's own budget.
+  if (helper) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+    for (int si = 0; si < A.S; ++si) {
+      const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
+      __syncthreads();
+      if (tid == 0) cta_queue = 0;   // (tid 0 is a main thread; kept for symmetry of the barriers)
+      __syncthreads();
+      (void)s;
+      tc::mbar_wait(&load_bar, load_parity);
+      load_parity ^= 1u;
+      // mirror of the main warps' round structure: same tile-wide barriers, NSLOT MLP calls per round
+      for (;;) {
+        tile_sync_all(c);
         const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
                         tile_active[tile][3];
-        tile_sync(c);
+        tile_sync_all(c);
         if (!go) break;
-      }
-
-      // ---- round set-up ---------------------------------------------------------------------------
-      const bool init = (SOLVER == HODE_SOLVER_DOPRI5) && ln.has && need_init;
-      bool run = ln.has && !init;   // lane performs a real step / attempt this round
-      double t = ln.t, h = 0.0, t_new = ln.t, h0 = 0.0;
-      float hf = 0.f, h0f = 0.f, d1 = 0.f;
-      float sc[NS], ynew[NS], incr[NS];
-#pragma unroll
-      for (int i = 0; i < NS; ++i) { sc[i] = 1.f; ynew[i] = ln.y[i]; incr[i] = 0.f; }
-      if (SOLVER == HODE_SOLVER_RK4) {
-        if (run) {
-          const double ta = (double)ln.in.t_obs[rk_n];
-          h = ((double)ln.in.t_obs[rk_n + 1] - ta) / nsub;
-          t = ta + rk_ss * h;
-          t_new = t + h;
-          hf = (float)h;
-          ln.in.cur = rk_n;
-          if (A.save_n && ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
-        }
-      } else if (run) {
-        if (need_stop) {
-          t_stop = t_bound;
-          if (clip && any_series(ln.in)) {
-            if (T <= 64) {
-              unsigned long long m = kink_mask & ~((1ull << kink_cur) - 1ull);
-              while (m) {
-                const int i = __ffsll((long long)m) - 1;
-                if ((double)ln.in.t_obs[i] > t) { t_stop = (double)ln.in.t_obs[i]; kink_cur = i; break; }
-                m &= m - 1ull;
-                kink_cur = i + 1;
-              }
-            } else {
-              while (kink_cur < T - 1 && !((double)ln.in.t_obs[kink_cur] > t && is_kink(ln.in, kink_cur)))
-                ++kink_cur;
-              if (kink_cur < T - 1) t_stop = (double)ln.in.t_obs[kink_cur];
-            }
-          }
-          ln.in.cur = grid_index_from(ln.in, (float)t, ln.in.cur);
-          if (ln.in.cur > 0) --ln.in.cur;
-          need_stop = false;
-        }
-        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
-        if (!prev_rejected && h_abs < min_step) h_abs = min_step;
-        if (h_abs < min_step) { ln.status = HODE_ST_STEP_TOO_SMALL; run = false; }
-        else if (attempts >= max_steps) { ln.status = HODE_ST_MAX_STEPS; run = false; }
-        else {
-          ++attempts;
-          t_new = t + h_abs;
-          if (t_new - t_stop > 0) t_new = t_stop;
-          h = t_new - t;
-          h_abs = h;
-          hf = (float)h;
-        }
-      }
-
-      // ---- the evaluations of this round: ONE call site of the tile MLP ------------------------
 #pragma unroll 1
-      for (int slot = 0; slot < NSLOT; ++slot) {
-        float ys[NS], d[NS];
-        double te;
-        if (SOLVER == HODE_SOLVER_RK4) {
-          const float a = (slot == 0) ? 0.f : (slot == 3 ? hf : 0.5f * hf);
-#pragma unroll
-          for (int i = 0; i < NS; ++i) {
-            const float kv = (slot == 1) ? k[0][i] : (slot == 2 ? k[1][i] : k[2][i]);
-            ys[i] = (slot == 0) ? ln.y[i] : fmaf(a, kv, ln.y[i]);
-          }
-          te = (slot == 0) ? t : (slot == 3 ? t + h : t + 0.5 * h);
-        } else {
-          if (slot == 0) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) ys[i] = init ? ln.y[i] : fmaf(hf, dp::a21 * k[0][i], ln.y[i]);
-            te = init ? t : t + (double)dp::c2 * h;
-          } else if (slot == 1) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-              ys[i] = init ? fmaf(h0f, k[0][i], ln.y[i])
-                           : fmaf(hf, fmaf(dp::a32, k[1][i], dp::a31 * k[0][i]), ln.y[i]);
-            te = init ? t + h0 : t + (double)dp::c3 * h;
-          } else if (slot == 2) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-              ys[i] = fmaf(hf, fmaf(dp::a43, k[2][i], fmaf(dp::a42, k[1][i], dp::a41 * k[0][i])), ln.y[i]);
-            te = t + (double)dp::c4 * h;
-          } else if (slot == 3) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-              ys[i] = fmaf(hf, fmaf(dp::a54, k[3][i], fmaf(dp::a53, k[2][i], fmaf(dp::a52, k[1][i], dp::a51 * k[0][i]))), ln.y[i]);
-            te = t + (double)dp::c5 * h;
-          } else if (slot == 4) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-              ys[i] = fmaf(hf, fmaf(dp::a65, k[4][i], fmaf(dp::a64, k[3][i], fmaf(dp::a63, k[2][i], fmaf(dp::a62, k[1][i], dp::a61 * k[0][i])))), ln.y[i]);
-            te = t_new;
-          } else {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              incr[i] = hf * fmaf(dp::b6, k[5][i], fmaf(dp::b5, k[4][i], fmaf(dp::b4, k[3][i], fmaf(dp::b3, k[2][i], dp::b1 * k[0][i]))));
-              ynew[i] = ln.y[i] + (incr[i] - ln.cmp[i]);
-              ys[i] = ynew[i];
-            }
-            te = t_new;
-          }
-        }
-        lane_eval<X3>(c, th, ln, te, ys, d);
-        if (SOLVER == HODE_SOLVER_RK4) {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) {
-            if (slot == 0) k[0][i] = d[i];
-            else if (slot == 1) k[1][i] = d[i];
-            else if (slot == 2) k[2][i] = d[i];
-            else k[3][i] = d[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) {
-            if (slot == 0) k[1][i] = d[i];
-            else if (slot == 1) k[2][i] = d[i];
-            else if (slot == 2) k[3][i] = d[i];
-            else if (slot == 3) k[4][i] = d[i];
-            else if (slot == 4) k[5][i] = d[i];
-            else k[6][i] = d[i];
-          }
-          if (init && slot == 0) {
-            // f(t0, y0) -> k1; outputs at t_eval <= t0; first part of select_initial_step
-#pragma unroll
-            for (int i = 0; i < NS; ++i) k[0][i] = d[i];
-            while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t) {
-              emit_row(A, ln.out, ln.b, ln.ei, ln.y, vi_n);
-              ++ln.ei;
-            }
-            float v0[NS], v1[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              sc[i] = atol + fabsf(ln.y[i]) * rtol;
-              v0[i] = ln.y[i] / sc[i];
-              v1[i] = d[i] / sc[i];
-            }
-            const float d0 = rms6v(v0);
-            d1 = rms6v(v1);
-            h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
-            const double interval = t_bound - t;
-            if (h0 > interval) h0 = interval;
-            h0f = (float)h0;
-          } else if (init && slot == 1) {
-            const double interval = t_bound - t;
-            if (interval > 0) {
-              float v0[NS];
-#pragma unroll
-              for (int i = 0; i < NS; ++i) v0[i] = (d[i] - k[0][i]) / sc[i];
-              const float d2 = rms6v(v0) / h0f;
-              double h1;
-              if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmax(1e-6, h0 * 1e-3);
-              else h1 = (double)powf(0.01f / fmaxf(d1, d2), 0.2f);
-              h_abs = fmin(fmin(100.0 * h0, h1), interval);
-            }
-            need_init = false;
-          }
-        }
+        for (int slot = 0; slot < NSLOT; ++slot) mlp_tile_helper<X3>(c);
       }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+    for (int si = 0; si < A.S; ++si) {
+      const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
+      const int vi_n = vi ? si + 1 : 0;
+      // ---- stage this parameter set's weight image (one bulk copy) ------------------------------
+      __syncthreads();  // both tiles are done with the previous image (and, in vi mode, sample)
+      if (tid == 0) cta_queue = 0;
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)img_floats * 4u;
+        tc::mbar_expect_tx(&load_bar, bytes);
+        tc::bulk_g2s(img, img_g + (size_t)s * img_floats, bytes, &load_bar);
+      }
+      tc::mbar_wait(&load_bar, load_parity);
+      load_parity ^= 1u;
+      const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
 
-      // ---- close the round ----------------------------------------------------------------------------
-      if (SOLVER == HODE_SOLVER_RK4) {
-        if (run) {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) {
-            const float inc = (hf * (1.0f / 6.0f)) * (k[0][i] + 2.0f * k[1][i] + 2.0f * k[2][i] + k[3][i]);
-            const float yk = inc - ln.cmp[i];
-            const float tn = ln.y[i] + yk;
-            ln.cmp[i] = (tn - ln.y[i]) - yk;
-            ln.y[i] = tn;
-          }
-          ++ln.n_acc;
-          if (++rk_ss == nsub) {
-            rk_ss = 0;
-            ++rk_n;
-            emit_row(A, ln.out, ln.b, rk_n, ln.y, vi_n);
-            ln.ei = rk_n + 1;
-            if (rk_n + 1 >= T) lane_finish(ln, A, vi_n);
-          }
-        }
-        continue;
-      }
-      if (init) {
-        if (!(t < t_bound)) lane_finish(ln, A, vi_n);   // T == 1 or zero-length span
-      } else if (ln.has && !run) {
-        lane_finish(ln, A, vi_n);                         // step too small / budget exhausted
-      } else if (run) {
-        float e2 = 0.f;
-        bool finite = true;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          const float scale = fmaf(fmaxf(fabsf(ln.y[i]), fabsf(ynew[i])), rtol, atol);
-          const float ee = hf * fmaf(dp::e7, k[6][i], fmaf(dp::e6, k[5][i], fmaf(dp::e5, k[4][i], fmaf(dp::e4, k[3][i], fmaf(dp::e3, k[2][i], dp::e1 * k[0][i])))));
-          const float q = ee / scale;
-          e2 = fmaf(q, q, e2);
-          finite = finite && isfinite(ynew[i]);
-        }
-        const float err = sqrtf(e2 * (1.0f / NS));
-        if (err < 1.0f) {
-          float factor = (err == 0.f) ? 10.f : fminf(10.f, 0.9f * powf(err, -0.2f));
-          if (prev_rejected) factor = fminf(1.f, factor);
-          prev_rejected = false;
-          ++ln.n_acc;
-          bool ok = true;
-          if (A.save_n) {
-            if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
-            else { ln.status = HODE_ST_MAX_STEPS; ok = false; }
-          }
-          if (ok) {
-            if (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
-              float Q[NS][4];
-#pragma unroll
-              for (int i = 0; i < NS; ++i) dp::dense_q(k[0][i], k[2][i], k[3][i], k[4][i], k[5][i], k[6][i], Q[i]);
-              while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
-                const double te = (double)ln.in.t_obs[ln.ei];
-                float yo[NS];
-                if (te == t_new) {
-#pragma unroll
-                  for (int i = 0; i < NS; ++i) yo[i] = ynew[i];
-                } else {
-                  const float xq = (float)((te - t) / h);
-#pragma unroll
-                  for (int i = 0; i < NS; ++i) {
-                    const float poly = xq * fmaf(xq, fmaf(xq, fmaf(xq, Q[i][3], Q[i][2]), Q[i][1]), Q[i][0]);
-                    yo[i] = fmaf(hf, poly, ln.y[i]);
-                  }
+      Lane ln;
+      ln.has = false;
+      ln.unit = -1;
+      ln.b = 0;
+      ln.out = nullptr;
+      ln.ei = 0;
+      ln.status = 0; ln.n_acc = 0; ln.n_rej = 0; ln.n_saved = 0;
+      ln.t = 0.0;
+      ln.cached = true; ln.c_t1 = 0.f; ln.c_dt = 1.f;
+  #pragma unroll
+      for (int ch = 0; ch < 3; ++ch) { ln.c_v1[ch] = 0.f; ln.c_dv[ch] = 0.f; }
+      ln.in.T = T; ln.in.cur = 0; ln.in.t_obs = A.t_obs;
+  #pragma unroll
+      for (int ch = 0; ch < 3; ++ch) { ln.in.mode[ch] = HODE_IN_ABSENT; ln.in.u[ch] = nullptr; }
+  #pragma unroll
+      for (int i = 0; i < NS; ++i) { ln.y[i] = 0.f; ln.cmp[i] = 0.f; }
+      bool queue_dry = false;
+      // stage vectors: k[0] = k1 (FSAL) ... k[6] = k7;  RK4 uses k[0..3]
+      float k[7][NS];
+  #pragma unroll
+      for (int j = 0; j < 7; ++j)
+  #pragma unroll
+        for (int i = 0; i < NS; ++i) k[j][i] = 0.f;
+      double h_abs = 0.0, t_stop = 0.0, t_bound = 0.0;
+      unsigned long long kink_mask = 0ull;
+      int attempts = 0, kink_cur = 1;
+      bool need_init = false, prev_rejected = false, need_stop = true;
+      int rk_n = 0, rk_ss = 0;
+
+      for (;;) {
+        // ---- refill idle lanes from the global queue (warp-aggregated) --------------------------
+        {
+          const bool want = !ln.has && !queue_dry;
+          const unsigned m = __ballot_sync(0xffffffffu, want);
+          if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane_id == leader) base = vi ? atomicAdd(&cta_queue, __popc(m)) : atomicAdd(&queue[s], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const long b = b_lo + (long)base + __popc(m & ((1u << lane_id) - 1u));
+            if (want) {
+              if (b < b_hi) {
+                lane_bind(ln, A, t_shared, s, b);
+                ln.t = (double)ln.in.t_obs[0];
+                t_bound = (double)ln.in.t_obs[T - 1];
+                need_init = true; prev_rejected = false; need_stop = true;
+                attempts = 0; kink_cur = 1; h_abs = 0.0;
+                rk_n = 0; rk_ss = 0;
+                if (SOLVER == HODE_SOLVER_RK4) {
+                  emit_row(A, ln.out, ln.b, 0, ln.y, vi_n);
+                  ln.ei = 1;
+                  if (T < 2) lane_finish(ln, A, vi_n);
+                } else if (clip && T <= 64 && any_series(ln.in)) {
+                  kink_mask = build_kink_mask(ln.in);
                 }
-                emit_row(A, ln.out, ln.b, ln.ei, yo, vi_n);
+              } else {
+                queue_dry = true;
+              }
+            }
+          }
+        }
+        // ---- does this tile still have work? ------------------------------------------------------
+        {
+          const bool any = __any_sync(0xffffffffu, ln.has);
+          if (lane_id == 0) tile_active[tile][wq] = any ? 1 : 0;
+          tile_sync_all(c);
+          const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
+                          tile_active[tile][3];
+          tile_sync_all(c);
+          if (!go) break;
+        }
+
+        // ---- round set-up ---------------------------------------------------------------------------
+        const bool init = (SOLVER == HODE_SOLVER_DOPRI5) && ln.has && need_init;
+        bool run = ln.has && !init;   // lane performs a real step / attempt this round
+        double t = ln.t, h = 0.0, t_new = ln.t, h0 = 0.0;
+        float hf = 0.f, h0f = 0.f, d1 = 0.f;
+        float sc[NS], ynew[NS], incr[NS];
+  #pragma unroll
+        for (int i = 0; i < NS; ++i) { sc[i] = 1.f; ynew[i] = ln.y[i]; incr[i] = 0.f; }
+        if (SOLVER == HODE_SOLVER_RK4) {
+          if (run) {
+            const double ta = (double)ln.in.t_obs[rk_n];
+            h = ((double)ln.in.t_obs[rk_n + 1] - ta) / nsub;
+            t = ta + rk_ss * h;
+            t_new = t + h;
+            hf = (float)h;
+            ln.in.cur = rk_n;
+            if (rk_ss == 0 && any_series(ln.in)) lane_cache_inputs(ln, rk_n);
+            if (A.save_n && ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
+          }
+        } else if (run) {
+          if (need_stop) {
+            t_stop = t_bound;
+            if (clip && any_series(ln.in)) {
+              if (T <= 64) {
+                unsigned long long m = kink_mask & ~((1ull << kink_cur) - 1ull);
+                while (m) {
+                  const int i = __ffsll((long long)m) - 1;
+                  if ((double)ln.in.t_obs[i] > t) { t_stop = (double)ln.in.t_obs[i]; kink_cur = i; break; }
+                  m &= m - 1ull;
+                  kink_cur = i + 1;
+                }
+              } else {
+                while (kink_cur < T - 1 && !((double)ln.in.t_obs[kink_cur] > t && is_kink(ln.in, kink_cur)))
+                  ++kink_cur;
+                if (kink_cur < T - 1) t_stop = (double)ln.in.t_obs[kink_cur];
+              }
+            }
+            {
+              const int j = grid_index_from(ln.in, (float)t, ln.in.cur);   // grid points < float(t)
+              ln.in.cur = j > 0 ? j - 1 : 0;
+              if (ln.cached && any_series(ln.in)) {
+                int i0 = (j < T && ln.in.t_obs[j] == (float)t) ? j : j - 1;
+                i0 = i0 < 0 ? 0 : (i0 > T - 2 ? T - 2 : i0);
+                lane_cache_inputs(ln, i0);
+              }
+            }
+            need_stop = false;
+          }
+          const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+          if (!prev_rejected && h_abs < min_step) h_abs = min_step;
+          if (h_abs < min_step) { ln.status = HODE_ST_STEP_TOO_SMALL; run = false; }
+          else if (attempts >= max_steps) { ln.status = HODE_ST_MAX_STEPS; run = false; }
+          else {
+            ++attempts;
+            t_new = t + h_abs;
+            if (t_new - t_stop > 0) t_new = t_stop;
+            h = t_new - t;
+            h_abs = h;
+            hf = (float)h;
+          }
+        }
+
+        // ---- the evaluations of this round: ONE call site of the tile MLP ------------------------
+  #pragma unroll 1
+        for (int slot = 0; slot < NSLOT; ++slot) {
+          float ys[NS], d[NS];
+          double te;
+          if (SOLVER == HODE_SOLVER_RK4) {
+            const float a = (slot == 0) ? 0.f : (slot == 3 ? hf : 0.5f * hf);
+  #pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              const float kv = (slot == 1) ? k[0][i] : (slot == 2 ? k[1][i] : k[2][i]);
+              ys[i] = (slot == 0) ? ln.y[i] : fmaf(a, kv, ln.y[i]);
+            }
+            te = (slot == 0) ? t : (slot == 3 ? t + h : t + 0.5 * h);
+          } else {
+            if (slot == 0) {
+  #pragma unroll
+              for (int i = 0; i < NS; ++i) ys[i] = init ? ln.y[i] : fmaf(hf, dp::a21 * k[0][i], ln.y[i]);
+              te = init ? t : t + (double)dp::c2 * h;
+            } else if (slot == 1) {
+  #pragma unroll
+              for (int i = 0; i < NS; ++i)
+                ys[i] = init ? fmaf(h0f, k[0][i], ln.y[i])
+                             : fmaf(hf, fmaf(dp::a32, k[1][i], dp::a31 * k[0][i]), ln.y[i]);
+              te = init ? t + h0 : t + (double)dp::c3 * h;
+            } else if (slot == 2) {
+  #pragma unroll
+              for (int i = 0; i < NS; ++i)
+                ys[i] = fmaf(hf, fmaf(dp::a43, k[2][i], fmaf(dp::a42, k[1][i], dp::a41 * k[0][i])), ln.y[i]);
+              te = t + (double)dp::c4 * h;
+            } else if (slot == 3) {
+  #pragma unroll
+              for (int i = 0; i < NS; ++i)
+                ys[i] = fmaf(hf, fmaf(dp::a54, k[3][i], fmaf(dp::a53, k[2][i], fmaf(dp::a52, k[1][i], dp::a51 * k[0][i]))), ln.y[i]);
+              te = t + (double)dp::c5 * h;
+            } else if (slot == 4) {
+  #pragma unroll
+              for (int i = 0; i < NS; ++i)
+                ys[i] = fmaf(hf, fmaf(dp::a65, k[4][i], fmaf(dp::a64, k[3][i], fmaf(dp::a63, k[2][i], fmaf(dp::a62, k[1][i], dp::a61 * k[0][i])))), ln.y[i]);
+              te = t_new;
+            } else {
+  #pragma unroll
+              for (int i = 0; i < NS; ++i) {
+                incr[i] = hf * fmaf(dp::b6, k[5][i], fmaf(dp::b5, k[4][i], fmaf(dp::b4, k[3][i], fmaf(dp::b3, k[2][i], dp::b1 * k[0][i]))));
+                ynew[i] = ln.y[i] + (incr[i] - ln.cmp[i]);
+                ys[i] = ynew[i];
+              }
+              te = t_new;
+            }
+          }
+          lane_eval<X3>(c, th, ln, te, ys, d);
+          if (SOLVER == HODE_SOLVER_RK4) {
+  #pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              if (slot == 0) k[0][i] = d[i];
+              else if (slot == 1) k[1][i] = d[i];
+              else if (slot == 2) k[2][i] = d[i];
+              else k[3][i] = d[i];
+            }
+          } else {
+  #pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              if (slot == 0) k[1][i] = d[i];
+              else if (slot == 1) k[2][i] = d[i];
+              else if (slot == 2) k[3][i] = d[i];
+              else if (slot == 3) k[4][i] = d[i];
+              else if (slot == 4) k[5][i] = d[i];
+              else k[6][i] = d[i];
+            }
+            if (init && slot == 0) {
+              // f(t0, y0) -> k1; outputs at t_eval <= t0; first part of select_initial_step
+  #pragma unroll
+              for (int i = 0; i < NS; ++i) k[0][i] = d[i];
+              while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t) {
+                emit_row(A, ln.out, ln.b, ln.ei, ln.y, vi_n);
                 ++ln.ei;
               }
+              float v0[NS], v1[NS];
+  #pragma unroll
+              for (int i = 0; i < NS; ++i) {
+                sc[i] = atol + fabsf(ln.y[i]) * rtol;
+                v0[i] = ln.y[i] / sc[i];
+                v1[i] = d[i] / sc[i];
+              }
+              const float d0 = rms6v(v0);
+              d1 = rms6v(v1);
+              h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)d0 / (double)d1;
+              const double interval = t_bound - t;
+              if (h0 > interval) h0 = interval;
+              h0f = (float)h0;
+            } else if (init && slot == 1) {
+              const double interval = t_bound - t;
+              if (interval > 0) {
+                float v0[NS];
+  #pragma unroll
+                for (int i = 0; i < NS; ++i) v0[i] = (d[i] - k[0][i]) / sc[i];
+                const float d2 = rms6v(v0) / h0f;
+                double h1;
+                if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmax(1e-6, h0 * 1e-3);
+                else h1 = (double)powf(0.01f / fmaxf(d1, d2), 0.2f);
+                h_abs = fmin(fmin(100.0 * h0, h1), interval);
+              }
+              need_init = false;
             }
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              const float yk = incr[i] - ln.cmp[i];
-              ln.cmp[i] = (ynew[i] - ln.y[i]) - yk;
-              ln.y[i] = ynew[i];
-              k[0][i] = k[6][i];
-            }
-            ln.t = t_new;
-            h_abs *= (double)factor;
-            need_stop = true;
-            if (t_new - t_bound >= 0) lane_finish(ln, A, vi_n);
-          } else {
-            lane_finish(ln, A, vi_n);
           }
-        } else {
-          ++ln.n_rej;
-          if (!finite || !(err == err)) {
-            ln.status = HODE_ST_STEP_TOO_SMALL;
-            lane_finish(ln, A, vi_n);
+        }
+
+        // ---- close the round ----------------------------------------------------------------------------
+        if (SOLVER == HODE_SOLVER_RK4) {
+          if (run) {
+  #pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              const float inc = (hf * (1.0f / 6.0f)) * (k[0][i] + 2.0f * k[1][i] + 2.0f * k[2][i] + k[3][i]);
+              const float yk = inc - ln.cmp[i];
+              const float tn = ln.y[i] + yk;
+              ln.cmp[i] = (tn - ln.y[i]) - yk;
+              ln.y[i] = tn;
+            }
+            ++ln.n_acc;
+            if (++rk_ss == nsub) {
+              rk_ss = 0;
+              ++rk_n;
+              emit_row(A, ln.out, ln.b, rk_n, ln.y, vi_n);
+              ln.ei = rk_n + 1;
+              if (rk_n + 1 >= T) lane_finish(ln, A, vi_n);
+            }
+          }
+          continue;
+        }
+        if (init) {
+          if (!(t < t_bound)) lane_finish(ln, A, vi_n);   // T == 1 or zero-length span
+        } else if (ln.has && !run) {
+          lane_finish(ln, A, vi_n);                         // step too small / budget exhausted
+        } else if (run) {
+          float e2 = 0.f;
+          bool finite = true;
+  #pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            const float scale = fmaf(fmaxf(fabsf(ln.y[i]), fabsf(ynew[i])), rtol, atol);
+            const float ee = hf * fmaf(dp::e7, k[6][i], fmaf(dp::e6, k[5][i], fmaf(dp::e5, k[4][i], fmaf(dp::e4, k[3][i], fmaf(dp::e3, k[2][i], dp::e1 * k[0][i])))));
+            const float q = ee / scale;
+            e2 = fmaf(q, q, e2);
+            finite = finite && isfinite(ynew[i]);
+          }
+          const float err = sqrtf(e2 * (1.0f / NS));
+          if (err < 1.0f) {
+            float factor = (err == 0.f) ? 10.f : fminf(10.f, 0.9f * powf(err, -0.2f));
+            if (prev_rejected) factor = fminf(1.f, factor);
+            prev_rejected = false;
+            ++ln.n_acc;
+            bool ok = true;
+            if (A.save_n) {
+              if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
+              else { ln.status = HODE_ST_MAX_STEPS; ok = false; }
+            }
+            if (ok) {
+              if (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
+                float Q[NS][4];
+  #pragma unroll
+                for (int i = 0; i < NS; ++i) dp::dense_q(k[0][i], k[2][i], k[3][i], k[4][i], k[5][i], k[6][i], Q[i]);
+                while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
+                  const double te = (double)ln.in.t_obs[ln.ei];
+                  float yo[NS];
+                  if (te == t_new) {
+  #pragma unroll
+                    for (int i = 0; i < NS; ++i) yo[i] = ynew[i];
+                  } else {
+                    const float xq = (float)((te - t) / h);
+  #pragma unroll
+                    for (int i = 0; i < NS; ++i) {
+                      const float poly = xq * fmaf(xq, fmaf(xq, fmaf(xq, Q[i][3], Q[i][2]), Q[i][1]), Q[i][0]);
+                      yo[i] = fmaf(hf, poly, ln.y[i]);
+                    }
+                  }
+                  emit_row(A, ln.out, ln.b, ln.ei, yo, vi_n);
+                  ++ln.ei;
+                }
+              }
+  #pragma unroll
+              for (int i = 0; i < NS; ++i) {
+                const float yk = incr[i] - ln.cmp[i];
+                ln.cmp[i] = (ynew[i] - ln.y[i]) - yk;
+                ln.y[i] = ynew[i];
+                k[0][i] = k[6][i];
+              }
+              ln.t = t_new;
+              h_abs *= (double)factor;
+              need_stop = true;
+              if (t_new - t_bound >= 0) lane_finish(ln, A, vi_n);
+            } else {
+              lane_finish(ln, A, vi_n);
+            }
           } else {
-            h_abs *= (double)fmaxf(0.2f, 0.9f * powf(err, -0.2f));
-            prev_rejected = true;
+            ++ln.n_rej;
+            if (!finite || !(err == err)) {
+              ln.status = HODE_ST_STEP_TOO_SMALL;
+              lane_finish(ln, A, vi_n);
+            } else {
+              h_abs *= (double)fmaxf(0.2f, 0.9f * powf(err, -0.2f));
+              prev_rejected = true;
+            }
           }
         }
       }
     }
+
   }
 
   tc::fence_before_sync();
@@ -778,7 +720,7 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspac
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    kern<<<grid, TILE * TILES_PER_CTA, smem, stream>>>(A, img, img_floats, queue);
+    kern<<<grid, 2 * TILE * TILES_PER_CTA, smem, stream>>>(A, img, img_floats, queue);
     return cudaSuccess;
   };
   const bool x3 = (mlp_mode == HODE_MLP_TF32X3);

@@ -1,0 +1,212 @@
+// hode_tc_mlp.cuh — the tile-level tensor-core MLP shared by the rollout (hode_rollout_tc.cu) and
+// the adjoint (hode_adjoint_tc.cu): TMEM column map, per-tile context, MMA issue for one layer,
+// the ReLU/TF32-split epilogue, and the main / helper halves of one MLP evaluation.
+#pragma once
+#include "hode_common.cuh"
+#include "hode_tcgen05.cuh"
+
+namespace hode {
+
+namespace {
+constexpr int TILE = 128;
+constexpr int H = 64;
+// TMEM columns of one tile:
+//   [0,64) accumulator D | [64,128) A_hi | [128,192) A_lo | [192,200) constant [1,1,0..] (bias step)
+constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_ONES = 192, TM_TILE_STRIDE = 256;
+}  // namespace
+
+// ---- per-tile context -------------------------------------------------------------------------------
+struct TileCtx {
+  const float* img;     // shared-memory weight image
+  uint64_t* mma_bar;    // this tile's MMA-complete mbarrier
+  uint32_t tmem;        // this tile's TMEM column base (lane field 0)
+  uint32_t lane_base;   // (warp%4)*32 << 16
+  uint32_t parity;      // mbarrier phase to wait for next
+  int bar_id;           // named barrier of the tile's 4 main warps (128 threads)
+  int bar_all;          // named barrier of the tile's 4 main + 4 helper warps (256 threads)
+  int wq;               // warp index inside the tile (warp-uniform)
+  int L;                // hidden layer count
+};
+
+__device__ __forceinline__ void tile_sync(const TileCtx& c) {
+  asm volatile("bar.sync %0, 128;" ::"r"(c.bar_id) : "memory");
+}
+__device__ __forceinline__ void tile_sync_all(const TileCtx& c) {
+  asm volatile("bar.sync %0, 256;" ::"r"(c.bar_all) : "memory");
+}
+
+// Issue the MMAs of one layer (one elected thread): D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// The two correction products are accumulated FIRST, into a still-small accumulator: the tensor
+// core truncates when it adds into D, and measured on B200 (csrc/probe/tc_probe.cu) this order
+// gives max err/sum|a*b| = 1.7e-7 (a plain fp32 FMA chain gives 2.2e-7), against 4.5e-7 when the
+// products are interleaved per k-step and 6.9e-7 when the large product goes first.
+template <bool X3, int N, int KSTEPS>
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t aones,
+                                            uint32_t b_hi, uint32_t b_lo, uint32_t b_bias) {
+  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
+  constexpr uint32_t lbo16 = (uint32_t)N;                 // (N*16 bytes) >> 4
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+  const uint32_t lo_hi = ((b_hi >> 4) & 0x3FFFu) | (lbo16 << 16);
+  const uint32_t lo_lo = ((b_lo >> 4) & 0x3FFFu) | (lbo16 << 16);
+  const uint32_t lo_bias = ((b_bias >> 4) & 0x3FFFu) | (lbo16 << 16);
+  // D = bias (hi + lo through the constant [1,1,0..] block): initialises the accumulator
+  tc::mma_tf32_ts(d, aones, ((uint64_t)desc_hi << 32) | (uint64_t)lo_bias, idesc, 0u);
+  if (X3) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      tc::mma_tf32_ts(d, alo + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
+                      idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lo + (uint32_t)ks * 2u * lbo16),
+                      idesc, 1u);
+  }
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
+                    idesc, 1u);
+}
+
+// ReLU + TF32 split of 16 accumulator columns (the bias is already in the accumulator), in
+// place: v -> hi bits, lo -> lo bits.  hi is rounded to nearest TF32; lo = a - hi is exact in
+// fp32 and is truncated to TF32 by the tensor core: a ~= hi + lo to 2^-22.
+template <bool X3>
+__device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float a = fmaxf(__uint_as_float(v[j]), 0.f);
+    const uint32_t h = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
+    v[j] = h;
+    if (X3) lo[j] = __float_as_uint(a - __uint_as_float(h));
+  }
+}
+
+// The residual MLP for the 128 trajectories of a tile (reference models/nn_residual.py:136-146).
+// Every thread of the tile must call this converged.  x: the 9 input features of this thread's
+// trajectory; r: the 6 residuals.
+template <bool X3>
+__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, float* stash = nullptr,
+                                         size_t stash_stride = 0) {
+  const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
+  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
+  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
+  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+  const uint32_t m_ones = c.tmem + TM_ONES;
+  const float* img = c.img;
+  const uint32_t img_s = tc::smem_u32(img);
+  const uint32_t bias_s = img_s + (uint32_t)(2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024) * 4u;
+  // ---- layer 0 operand: 9 features zero-padded to K = 16 ----------------------------------------
+  {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < HODE_NN_IN) tc::split_tf32(x[k], hi[k], lo[k]);
+      else { hi[k] = 0u; lo[k] = 0u; }
+    }
+    HODE_TMEM_ST_X16(t_ahi, hi);
+    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
+  }
+  tc::wait_st();
+  tc::fence_before_sync();
+  tile_sync(c);
+  if (c.wq == 0) {
+    if (tc::elect_one()) {
+      tc::fence_after_sync();
+      issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, m_ones, img_s, img_s + 1024 * 4, bias_s);
+      tc::mma_commit(c.mma_bar);
+    }
+    __syncwarp();
+  }
+  uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
+  // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
+#pragma unroll 1
+  for (int l = 0; l < c.L; ++l) {
+    const bool last = (l + 1 == c.L);
+    const uint32_t b_hi = img_s + w_off * 4;
+    const uint32_t b_lo = b_hi + (last ? 1024u : 4096u) * 4u;
+    tc::mbar_wait(c.mma_bar, c.parity);
+    c.parity ^= 1u;
+    tc::fence_after_sync();
+    // the main warp owns accumulator columns [0,32) of its 32 lanes, the helper warp of the same
+    // lane quarter columns [32,64) (mlp_tile_helper): the epilogue latency per layer is halved
+    uint32_t v0[32], lo[16];
+    HODE_TMEM_LD_X32(t_d, v0);
+    tc::wait_ld();
+    if (stash) {   // adjoint: keep a_l = relu(z_l) of this thread's trajectory, columns [0,32)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        stash[(size_t)(l * H + j) * stash_stride] = fmaxf(__uint_as_float(v0[j]), 0.f);
+    }
+    epilogue16<X3>(v0, lo);
+    HODE_TMEM_ST_X16(t_ahi, v0);
+    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
+    epilogue16<X3>(v0 + 16, lo);
+    HODE_TMEM_ST_X16(t_ahi + 16, (v0 + 16));
+    if (X3) HODE_TMEM_ST_X16(t_alo + 16, lo);
+    tc::wait_st();
+    tc::fence_before_sync();
+    tile_sync_all(c);
+    if (c.wq == 0) {
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        const uint32_t b_bias = bias_s + (uint32_t)(l + 1) * 512u * 4u;
+        if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
+        else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
+        tc::mma_commit(c.mma_bar);
+      }
+      __syncwarp();
+    }
+    w_off += 2 * 4096;
+  }
+  // ---- output layer epilogue: 6 of the 16 accumulator columns ------------------------------------
+  tc::mbar_wait(c.mma_bar, c.parity);
+  c.parity ^= 1u;
+  tc::fence_after_sync();
+  {
+    uint32_t v[8];
+    HODE_TMEM_LD_X8(t_d, v);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < NS; ++i) r[i] = __uint_as_float(v[i]);
+  }
+  // The next call overwrites A (tcgen05.st: every MMA has completed) and its layer-0 MMAs write
+  // D only after a tile barrier that every thread reaches after its wait::ld above.
+}
+
+// Helper warps: the other half of every hidden-layer epilogue.  Must be called once per
+// mlp_tile() call of the tile's main warps (same number of tile-wide barriers and mbarrier phases).
+template <bool X3>
+__device__ __forceinline__ void mlp_tile_helper(TileCtx& c, float* stash = nullptr, size_t stash_stride = 0) {
+  const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + 32;
+  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI + 32;
+  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO + 32;
+#pragma unroll 1
+  for (int l = 0; l < c.L; ++l) {
+    tc::mbar_wait(c.mma_bar, c.parity);
+    c.parity ^= 1u;
+    tc::fence_after_sync();
+    uint32_t v[32], lo[16];
+    HODE_TMEM_LD_X32(t_d, v);
+    tc::wait_ld();
+    if (stash) {   // columns [32,64)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        stash[(size_t)(l * H + 32 + j) * stash_stride] = fmaxf(__uint_as_float(v[j]), 0.f);
+    }
+    epilogue16<X3>(v, lo);
+    HODE_TMEM_ST_X16(t_ahi, v);
+    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
+    epilogue16<X3>(v + 16, lo);
+    HODE_TMEM_ST_X16(t_ahi + 16, (v + 16));
+    if (X3) HODE_TMEM_ST_X16(t_alo + 16, lo);
+    tc::wait_st();
+    tc::fence_before_sync();
+    tile_sync_all(c);
+  }
+  // the output layer's phase: nothing to read, but the phase must be observed so that the next
+  // call's first wait cannot be satisfied by a stale parity
+  tc::mbar_wait(c.mma_bar, c.parity);
+  c.parity ^= 1u;
+}
+
+}  // namespace hode
