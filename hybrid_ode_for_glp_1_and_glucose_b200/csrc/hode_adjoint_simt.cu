@@ -734,6 +734,13 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int c
   else if (grad_theta) grad_theta[(size_t)s * HODE_N_THETA + (i - P)] = acc;
 }
 
+cudaError_t launch_reduce_partials(const float* partials, int ctas_per_set, int S, int P, float* grad_W,
+                                   float* grad_theta, cudaStream_t stream) {
+  const int n = P + HODE_N_THETA;
+  reduce_partials_kernel<<<dim3((n + 255) / 256, S), 256, 0, stream>>>(partials, ctas_per_set, P, grad_W, grad_theta);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------

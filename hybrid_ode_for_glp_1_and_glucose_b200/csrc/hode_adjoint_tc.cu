@@ -1,0 +1,797 @@
+// hode_adjoint_tc.cu — discrete adjoint of the rollout with the MLP forward recomputation and the
+// delta back-propagation on the tcgen05 tensor cores (BASELINE.json north_star item 3).
+//
+// Same mathematics as hode_adjoint_simt.cu (autograd through the unrolled RK steps with the step
+// sizes frozen); what changes is where the 13 248-MAC network products run:
+//   * one tile of 128 trajectories per CTA: 4 main warps (one trajectory per thread: integrator
+//     state, mechanistic VJP, stage recurrences) + 4 helper warps (the other half of every
+//     epilogue and the weight-gradient products);
+//   * per accepted step, in reverse:  (1) the forward weight image is bulk-copied into shared
+//     memory and the N stages are recomputed with hode_tc_mlp.cuh's mlp_tile, each hidden
+//     activation going to a per-trajectory stash column in global memory (L2 resident);
+//     (2) the TRANSPOSED weight image replaces it (tcgen05 kind::tf32 takes K-major operands only —
+//     csrc/probe/adj_probe.cu — so W^T needs its own image) and every stage is pulled back:
+//     u_{l-1} = delta_l W_l is a [128 x 64] x [64 x 64] 3xTF32 MMA chain with delta in TMEM,
+//     delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue;
+//   * dW_l += delta_l^T a_{l-1} (contraction over the tile's 128 trajectories) is staged through
+//     shared memory and accumulated by the helper warps in REGISTERS for the whole kernel (every
+//     gradient element is owned by one helper thread; fixed summation order, no atomics), while
+//     the tensor pipe works on the next layer's product;
+//   * per-CTA partial gradients -> workspace -> reduce_partials (hode_adjoint_simt.cu), in CTA order.
+// Restrictions: nn_hidden == 64, nn_layers <= 4 (the accumulators are compiled for them); other
+// shapes use the FP32 adjoint.
+#include <math.h>
+
+#include "hode_common.cuh"
+#include "hode_kernels.h"
+#include "hode_tc_mlp.cuh"
+#include "hode_tcgen05.cuh"
+
+namespace hode {
+
+namespace {
+
+constexpr int LD = 68;        // staging row stride (floats): 17 x 16 B, conflict-free own-row float4
+constexpr int MAXL = 4;       // hidden layers supported by the register accumulators
+constexpr int NSTAGE_MAX = 7;
+
+// Butcher tableaux, [solver][..]: 0 = classical RK4, 1 = Dormand-Prince 5(4) (+ stage 7 = FSAL)
+__constant__ float kA[2][7][7] = {
+    {{0}, {0.5f}, {0.f, 0.5f}, {0.f, 0.f, 1.f}},
+    {{0},
+     {dp::a21},
+     {dp::a31, dp::a32},
+     {dp::a41, dp::a42, dp::a43},
+     {dp::a51, dp::a52, dp::a53, dp::a54},
+     {dp::a61, dp::a62, dp::a63, dp::a64, dp::a65},
+     {dp::b1, 0.f, dp::b3, dp::b4, dp::b5, dp::b6}}};
+__constant__ float kB[2][7] = {{1.f / 6, 1.f / 3, 1.f / 3, 1.f / 6}, {dp::b1, 0.f, dp::b3, dp::b4, dp::b5, dp::b6, 0.f}};
+__constant__ float kC[2][7] = {{0.f, 0.5f, 0.5f, 1.f}, {0.f, dp::c2, dp::c3, dp::c4, dp::c5, 1.f, 1.f}};
+__constant__ float kP[7][4] = {{dp::p11, dp::p12, dp::p13, dp::p14}, {0.f, 0.f, 0.f, 0.f},
+                               {0.f, dp::p32, dp::p33, dp::p34},     {0.f, dp::p42, dp::p43, dp::p44},
+                               {0.f, dp::p52, dp::p53, dp::p54},     {0.f, dp::p62, dp::p63, dp::p64},
+                               {0.f, dp::p72, dp::p73, dp::p74}};
+
+// weight-gradient accumulators of one helper thread (t = 0..127):
+//   hidden layer l (1..L-1): rows j = (t>>4)*8 .. +8, columns k = (t&15)*4 .. +4 of dW_l [64][64]
+//   layer 0 [64][9]: elements e = t + 128 m (m = 0..4, e < 576);  output layer [6][64]: e = t + 128 m (m < 3)
+//   biases: thread t < 64 owns db_l[t] of every hidden layer, t < 6 owns db_out[t]
+struct DwAcc {
+  float h[MAXL - 1][32];
+  float w0[5];
+  float wo[3];
+  float bh[MAXL];
+  float bo;
+};
+
+struct BwdCtx {
+  float* Dbuf;          // [128][LD] delta rows (fp32)
+  float* Abuf;          // [128][LD] layer-input rows (fp32)
+  uint32_t img_s;       // shared-memory address of the transposed weight image
+  const float* stash;   // this row's activation column of the current stage; element e at stash[e * ss]
+  size_t ss;
+  int row;              // trajectory slot 0..127
+};
+
+// D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi without a bias step (the first MMA initialises D)
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_nobias(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t b_hi, uint32_t b_lo) {
+  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
+  constexpr uint32_t lbo16 = (uint32_t)N;
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t lo_hi = ((b_hi >> 4) & 0x3FFFu) | (lbo16 << 16);
+  const uint32_t lo_lo = ((b_lo >> 4) & 0x3FFFu) | (lbo16 << 16);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::mma_tf32_ts(d, alo + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc,
+                    ks == 0 ? 0u : 1u);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lo + (uint32_t)ks * 2u * lbo16), idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, 1u);
+}
+
+// split 16 fp32 values into TF32 hi (rounded) / lo (exact remainder, truncated by the tensor core)
+__device__ __forceinline__ void split16(const float* d, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t h = (__float_as_uint(d[j]) + 0x1000u) & 0xFFFFE000u;
+    hi[j] = h;
+    lo[j] = __float_as_uint(d[j] - __uint_as_float(h));
+  }
+}
+
+// ---- helper-warp weight-gradient products over the staged rows -------------------------------------
+__device__ __forceinline__ void gemm_hidden(float* acc /*[32]*/, const float* __restrict__ D,
+                                            const float* __restrict__ A, int t) {
+  const float* dp_ = D + (t >> 4) * 8;
+  const float* ap = A + (t & 15) * 4;
+#pragma unroll 2
+  for (int r = 0; r < TILE; ++r) {
+    const float4 d0 = *reinterpret_cast<const float4*>(dp_ + r * LD);
+    const float4 d1 = *reinterpret_cast<const float4*>(dp_ + r * LD + 4);
+    const float4 a = *reinterpret_cast<const float4*>(ap + r * LD);
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float aa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i * 4 + q] = fmaf(dd[i], aa[q], acc[i * 4 + q]);
+  }
+}
+
+template <int NE, int NIN, int TOTAL>
+__device__ __forceinline__ void gemm_small(float* acc /*[NE]*/, const float* __restrict__ D,
+                                           const float* __restrict__ A, int t) {
+#pragma unroll
+  for (int m = 0; m < NE; ++m) {
+    const int e = t + 128 * m;
+    if (e < TOTAL) {
+      const int j = e / NIN, k = e - j * NIN;
+      float s = 0.f;
+      for (int r = 0; r < TILE; ++r) s = fmaf(D[r * LD + j], A[r * LD + k], s);
+      acc[m] += s;
+    }
+  }
+}
+
+__device__ __forceinline__ float col_sum(const float* __restrict__ D, int j) {
+  float s = 0.f;
+  for (int r = 0; r < TILE; ++r) s += D[r * LD + j];
+  return s;
+}
+
+// ---- MLP backward for one stage (tile-collective: all 256 threads) ------------------------------------
+// MAIN threads own accumulator columns [0,32) of their trajectory, helpers [32,64).
+// g6 (main): cotangent of the 6 network outputs; x9 (main): the stage's input features;
+// gx (main, out): cotangent of the 9 input features.
+template <bool MAIN>
+__device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, const BwdCtx& b, const float* x9, const float* g6,
+                                             float* gx, DwAcc& acc) {
+  constexpr int half = MAIN ? 0 : 32;
+  const int L = c.L;
+  const int ht = threadIdx.x & 127;   // helper index (gemm ownership)
+  float* Drow = b.Dbuf + b.row * LD;
+  float* Arow = b.Abuf + b.row * LD;
+  const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
+  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
+  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
+  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+
+  // ---- prologue: delta_L = g, operands of dW_out, MMA phase L: u_{L-1} = delta_L W_out ----------
+  if (MAIN) {
+    float d[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = (j < NS) ? g6[j] : 0.f;
+    uint32_t hi[16], lo[16];
+    split16(d, hi, lo);
+    HODE_TMEM_ST_X16(t_ahi, hi);
+    HODE_TMEM_ST_X16(t_alo, lo);
+    *reinterpret_cast<float4*>(Drow) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4*>(Drow + 4) = make_float4(d[4], d[5], 0.f, 0.f);
+  }
+#pragma unroll
+  for (int j4 = 0; j4 < 32; j4 += 4) {
+    float4 a;
+    a.x = b.stash[(size_t)((L - 1) * H + half + j4 + 0) * b.ss];
+    a.y = b.stash[(size_t)((L - 1) * H + half + j4 + 1) * b.ss];
+    a.z = b.stash[(size_t)((L - 1) * H + half + j4 + 2) * b.ss];
+    a.w = b.stash[(size_t)((L - 1) * H + half + j4 + 3) * b.ss];
+    *reinterpret_cast<float4*>(Arow + half + j4) = a;
+  }
+  tc::wait_st();
+  tc::fence_before_sync();
+  tile_sync_all(c);
+  if (MAIN && c.wq == 0) {
+    if (tc::elect_one()) {
+      tc::fence_after_sync();
+      issue_nobias<H, 2>(m_d, m_ahi, m_alo, b.img_s, b.img_s + 1024u * 4u);
+      tc::mma_commit(c.mma_bar);
+    }
+    __syncwarp();
+  }
+  if (!MAIN) {
+    gemm_small<3, 64, 384>(acc.wo, b.Dbuf, b.Abuf, ht);
+    if (ht < NS) acc.bo += col_sum(b.Dbuf, ht);
+  }
+  tile_sync_all(c);
+
+  // ---- phases p = L .. 1: delta_{p-1} = u_{p-1} * relu'(a_{p-1}); dW_{p-1}; MMA phase p-1 ----------
+#pragma unroll
+  for (int p = MAXL; p >= 1; --p) {
+    if (p > L) continue;
+    tc::mbar_wait(c.mma_bar, c.parity);
+    c.parity ^= 1u;
+    tc::fence_after_sync();
+    uint32_t u[32];
+    HODE_TMEM_LD_X32(t_d, u);
+    float a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = b.stash[(size_t)((p - 1) * H + half + j) * b.ss];
+    tc::wait_ld();
+    float d[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d[j] = a[j] > 0.f ? __uint_as_float(u[j]) : 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < 32; j4 += 4)
+      *reinterpret_cast<float4*>(Drow + half + j4) = make_float4(d[j4], d[j4 + 1], d[j4 + 2], d[j4 + 3]);
+    {
+      uint32_t hi[16], lo[16];
+      split16(d, hi, lo);
+      HODE_TMEM_ST_X16(t_ahi + half, hi);
+      HODE_TMEM_ST_X16(t_alo + half, lo);
+      split16(d + 16, hi, lo);
+      HODE_TMEM_ST_X16(t_ahi + half + 16, hi);
+      HODE_TMEM_ST_X16(t_alo + half + 16, lo);
+    }
+    if (p >= 2) {   // inputs of layer p-1 are a_{p-2}
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        float4 v;
+        v.x = b.stash[(size_t)((p - 2) * H + half + j4 + 0) * b.ss];
+        v.y = b.stash[(size_t)((p - 2) * H + half + j4 + 1) * b.ss];
+        v.z = b.stash[(size_t)((p - 2) * H + half + j4 + 2) * b.ss];
+        v.w = b.stash[(size_t)((p - 2) * H + half + j4 + 3) * b.ss];
+        *reinterpret_cast<float4*>(Arow + half + j4) = v;
+      }
+    } else if (MAIN) {   // inputs of layer 0 are the 9 stage features
+      *reinterpret_cast<float4*>(Arow) = make_float4(x9[0], x9[1], x9[2], x9[3]);
+      *reinterpret_cast<float4*>(Arow + 4) = make_float4(x9[4], x9[5], x9[6], x9[7]);
+      *reinterpret_cast<float4*>(Arow + 8) = make_float4(x9[8], 0.f, 0.f, 0.f);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    tile_sync_all(c);
+    if (MAIN && c.wq == 0) {
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1} (hidden, 64 x 64)
+          const uint32_t blk = b.img_s + (uint32_t)(2048 + (L - p) * 8192) * 4u;
+          issue_nobias<H, 8>(m_d, m_ahi, m_alo, blk, blk + 4096u * 4u);
+        } else {        // g_x = delta_0 W_0 (N = 16: the 9 features padded)
+          const uint32_t blk = b.img_s + (uint32_t)(2048 + (L - 1) * 8192) * 4u;
+          issue_nobias<16, 8>(m_d, m_ahi, m_alo, blk, blk + 1024u * 4u);
+        }
+        tc::mma_commit(c.mma_bar);
+      }
+      __syncwarp();
+    }
+    if (!MAIN) {
+      if (p >= 2) {
+        gemm_hidden(acc.h[p - 2], b.Dbuf, b.Abuf, ht);
+      } else {
+        gemm_small<5, 9, 576>(acc.w0, b.Dbuf, b.Abuf, ht);
+      }
+      if (ht < H) acc.bh[p - 1] += col_sum(b.Dbuf, ht);
+    }
+    tile_sync_all(c);
+  }
+  // ---- final phase: g_x -------------------------------------------------------------------------
+  tc::mbar_wait(c.mma_bar, c.parity);
+  c.parity ^= 1u;
+  if (MAIN) {
+    tc::fence_after_sync();
+    uint32_t v[16];
+    HODE_TMEM_LD_X16(c.tmem + c.lane_base + TM_D0, v);
+    tc::wait_ld();
+#pragma unroll
+    for (int k = 0; k < HODE_NN_IN; ++k) gx[k] = __uint_as_float(v[k]);
+  }
+}
+
+// closed-form VJP of f_physio — same formulas as hode_adjoint_simt.cu::rhs_mech_vjp
+__device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float GD, bool gd_present,
+                                         const float* c, float* gy, float* gth) {
+  const float G = y[0], I = y[1], Glu = y[2], GLP1 = y[3], FFA = y[5];
+  const float Pi = 1.0f + p.rho * GLP1;
+  const float dG = G - p.G_b, dI = I - p.I_b, dGlu = Glu - p.Glu_b;
+  const float inv_e = 1.0f / (p.EC_50 + GLP1);
+  const float frac_e = GLP1 * inv_e;
+  const float ge = p.E_max * frac_e;
+  const float inv_m = 1.0f / (p.K_m + G);
+  float r = 0.f, dr_du = 0.f, dr_dv = 0.f, u = 0.f;
+  const float v = p.igd_pow;
+  if (gd_present) {
+    u = powf(GD, p.g);
+    const float inv = 1.0f / (v + u);
+    r = u * inv;
+    dr_du = v * inv * inv;
+    dr_dv = -u * inv * inv;
+  }
+  const float k_GE = p.k_GE0 * (1.0f - r);
+  const float lin5 = -p.p_7 - p.p_8 * I + p.p_9 * G;
+  gy[0] += c[1] * Pi * p.a_GI + c[3] * p.V_max * p.K_m * inv_m * inv_m + c[5] * FFA * p.p_9 - c[0] * k_GE;
+  gy[1] += -c[1] * p.k_I - c[5] * FFA * p.p_8 - 0.01f * c[0];
+  gy[2] += -c[2] * ge + 0.005f * c[0];
+  gy[3] += c[1] * p.rho * p.a_GI * dG - c[2] * dGlu * p.E_max * p.EC_50 * inv_e * inv_e - c[3] * p.k_L;
+  gy[5] += c[5] * lin5;
+  gth[0] += c[1] * Pi * dG;
+  gth[1] += -c[1] * dI;
+  gth[2] += c[1] * GLP1 * p.a_GI * dG;
+  gth[3] += -c[1] * Pi * p.a_GI;
+  gth[4] += c[1] * p.k_I + 0.01f * c[0];
+  gth[5] += -c[2] * dGlu * frac_e;
+  gth[6] += c[2] * dGlu * p.E_max * GLP1 * inv_e * inv_e;
+  gth[7] += c[2] * ge - 0.005f * c[0];
+  gth[8] += c[3] * G * inv_m;
+  gth[9] += -c[3] * p.V_max * G * inv_m * inv_m;
+  gth[10] += -c[3] * GLP1;
+  gth[11] += -c[0] * G * (1.0f - r);
+  if (gd_present) {
+    const float g_r = c[0] * p.k_GE0 * G;
+    gth[12] += g_r * dr_dv * p.g * powf(p.IGD_50, p.g - 1.0f);
+    float dg = dr_dv * v * logf(p.IGD_50);
+    if (GD > 0.f) dg += dr_du * u * logf(GD);
+    gth[13] += g_r * dg;
+  }
+  gth[14] += -c[5] * FFA;
+  gth[15] += -c[5] * FFA * I;
+  gth[16] += c[5] * FFA * G;
+}
+
+}  // namespace
+
+struct AdjTcArgs {
+  RolloutArgs R;
+  const float* grad_traj;  // [S,B,T,6]
+  float* grad_y0;          // [S,B,6] or nullptr
+  float* partials;         // [gridDim.y * gridDim.x][P + 17]
+  float* stash;            // [7][L][64][NT] activation stash
+  const float* img_fwd;    // [S][fwd_floats]
+  const float* img_bwd;    // [S][bwd_floats]
+  int fwd_floats, bwd_floats;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// grid = (ctas per parameter set, S), block = 256 (4 main + 4 helper warps), 1 CTA / SM
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ __align__(8) uint64_t load_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_nmax;
+
+  const RolloutArgs& A = G.R;
+  const int tid = threadIdx.x, lane_id = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const bool helper = warp >= 4;
+  const int wq = warp & 3, row = tid & 127;
+  const int s = blockIdx.y, T = A.T, L = A.L;
+  const int solver = A.solver == HODE_SOLVER_RK4 ? 0 : 1;
+  const int N = solver == 0 ? 4 : 7;
+  const long n_units = (long)A.S * A.B;
+
+  float* img = reinterpret_cast<float*>(smem_raw);
+  const int img_cap = ((G.fwd_floats > G.bwd_floats ? G.fwd_floats : G.bwd_floats) + 3) & ~3;
+  float* Dbuf = img + ((img_cap + 255) & ~255);
+  float* Abuf = Dbuf + TILE * LD;
+  float* t_sh_buf = Abuf + TILE * LD;
+
+  if (tid == 0) {
+    tc::mbar_init(&mma_bar, 1);
+    tc::mbar_init(&load_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  const float* t_shared = nullptr;
+  if (!A.t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) {
+    for (int i = tid; i < T; i += blockDim.x) t_sh_buf[i] = A.t_obs[i];
+    t_shared = t_sh_buf;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  TileCtx c;
+  c.img = img;
+  c.mma_bar = &mma_bar;
+  c.tmem = tmem_base_s;
+  c.lane_base = (uint32_t)(wq * 32) << 16;
+  c.parity = 0;
+  c.bar_id = 1;
+  c.bar_all = 2;
+  c.wq = wq;
+  c.L = L;
+  {
+    uint32_t ones[8] = {0x3F800000u, 0x3F800000u, 0u, 0u, 0u, 0u, 0u, 0u};
+    HODE_TMEM_ST_X8(c.tmem + c.lane_base + TM_ONES, ones);
+    tc::wait_st();
+  }
+  uint32_t load_parity = 0;
+  const size_t NT = (size_t)gridDim.x * gridDim.y * TILE;
+  const size_t gt = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE + row;
+  const size_t stage_stride = (size_t)L * H * NT;   // floats between the stash blocks of two stages
+  float* stash0 = G.stash + gt;
+
+  BwdCtx bc;
+  bc.Dbuf = Dbuf; bc.Abuf = Abuf;
+  bc.img_s = tc::smem_u32(img);
+  bc.ss = NT;
+  bc.row = row;
+  bc.stash = stash0;
+
+  DwAcc acc;
+#pragma unroll
+  for (int l = 0; l < MAXL - 1; ++l)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc.h[l][i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) acc.w0[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) acc.wo[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXL; ++i) acc.bh[i] = 0.f;
+  acc.bo = 0.f;
+
+  const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
+  const bool gd_present = A.in_mode[HODE_CH_GD] != HODE_IN_ABSENT;
+  const int nsub = A.n_substeps > 0 ? A.n_substeps : 1;
+  float gth[HODE_N_THETA];
+#pragma unroll
+  for (int i = 0; i < HODE_N_THETA; ++i) gth[i] = 0.f;
+
+  // swap the shared-memory weight image (forward <-> transposed); every thread calls it
+  auto load_image = [&](const float* src, int floats) {
+    tc::fence_before_sync();
+    __syncthreads();   // nobody still reads the old image (all MMAs that did have been waited for)
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)floats * 4u;
+      tc::mbar_expect_tx(&load_bar, bytes);
+      tc::bulk_g2s(img, src, bytes, &load_bar);
+    }
+    tc::mbar_wait(&load_bar, load_parity);
+    load_parity ^= 1u;
+  };
+  const float* fwd_src = G.img_fwd + (size_t)s * G.fwd_floats;
+  const float* bwd_src = G.img_bwd + (size_t)s * G.bwd_floats;
+
+  for (long blk = blockIdx.x; blk * TILE < A.B; blk += gridDim.x) {
+    const long b = blk * TILE + row;
+    const bool valid = b < A.B;
+    const long bs = valid ? b : 0;
+    const long unit = (long)s * A.B + bs;
+    int n = (valid && !helper) ? A.save_n[unit] : 0;
+    const bool ok = valid && n >= 0;
+    if (n < 0) n = 0;
+    if (tid == 0) s_nmax = 0;
+    __syncthreads();
+    if (n > 0) atomicMax(&s_nmax, n);
+    __syncthreads();
+    const int nmax = s_nmax;
+
+    TrajInputs in;
+    in.T = T; in.cur = 0;
+    in.t_obs = A.t_per_traj ? A.t_obs + bs * T : (t_shared ? t_shared : A.t_obs);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      in.mode[ch] = A.in_mode[ch];
+      in.u[ch] = in.mode[ch] == HODE_IN_SERIES ? A.u[ch] + bs * T
+               : in.mode[ch] == HODE_IN_CONST ? A.u[ch] + bs : nullptr;
+    }
+    const float* gtraj = G.grad_traj + (size_t)unit * T * NS;
+    const double t_bound = (double)in.t_obs[T - 1];
+    float lam[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) lam[i] = 0.f;
+    int ei = T - 1;
+
+    for (int it = 0; it < nmax; ++it) {
+      // =========================== forward recomputation =========================================
+      load_image(fwd_src, G.fwd_floats);
+      if (helper) {
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, NT);
+        load_image(bwd_src, G.bwd_floats);
+#pragma unroll 1
+        for (int i = N - 1; i >= 0; --i) {
+          bc.stash = stash0 + (size_t)i * stage_stride;
+          mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr, acc);
+        }
+        continue;
+      }
+      const int sidx = n - 1 - it;
+      const bool act = ok && sidx >= 0;
+      double t = (double)in.t_obs[0], t_new = t, h = 0.0;
+      float y[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) y[i] = 0.f;
+      if (act) {
+        const size_t o = (size_t)sidx * n_units + unit;
+        t = A.save_t[o];
+        if (solver == 0) {
+          h = (double)A.save_h[o];
+          t_new = t + h;
+        } else {
+          t_new = (sidx + 1 < n) ? A.save_t[o + n_units] : t_bound;
+          h = t_new - t;
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) y[i] = A.save_y[((size_t)sidx * NS + i) * n_units + unit];
+      }
+      const float hf = (float)h;
+      {
+        int lo = 0, hi = T;
+        const float t32 = (float)t;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (in.t_obs[mid] < t32) lo = mid + 1; else hi = mid; }
+        in.cur = lo > 0 ? lo - 1 : 0;
+      }
+      float k[NSTAGE_MAX][NS], tv[NSTAGE_MAX], gdv[NSTAGE_MAX];
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) {
+        float ys[NS];
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) {
+          float a_ = 0.f;
+          for (int j = 0; j < i; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);
+          ys[cc] = fmaf(hf, a_, y[cc]);
+        }
+        const float ci = kC[solver][i];
+        const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
+        const float t32 = (float)te;
+        int idx = 0;
+        if (any_series(in)) idx = grid_index_from(in, t32, in.cur);
+        const float meal = input_channel(in, HODE_CH_MEAL, t32, idx);
+        const float tvns = input_channel(in, HODE_CH_TVNS, t32, idx);
+        const float gd = input_channel(in, HODE_CH_GD, t32, idx);
+        tv[i] = tvns; gdv[i] = gd;
+        float x[HODE_NN_IN], r[NS], d[NS];
+        x[0] = t32;
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) x[1 + cc] = ys[cc];
+        x[7] = ys[3];
+        x[8] = tvns;
+        __syncwarp();
+        mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, NT);
+        rhs_mech(th, ys, meal, gd, gd_present, d);
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) k[i][cc] = __fadd_rn(d[cc], r[cc]);
+      }
+      // =========================== reverse sweep ===================================================
+      load_image(bwd_src, G.bwd_floats);
+      float gy[NS], gk[NSTAGE_MAX][NS];
+#pragma unroll
+      for (int i = 0; i < NSTAGE_MAX; ++i)
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) gk[i][cc] = 0.f;
+      if (solver == 0) {
+        if (act && (sidx + 1) % nsub == 0) {
+          const float* g = gtraj + (size_t)((sidx + 1) / nsub) * NS;
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) lam[cc] += g[cc];
+        }
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) gy[cc] = act ? lam[cc] : 0.f;
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) gk[j][cc] = hf * kB[0][j] * gy[cc];
+      } else {
+        float gnew[NS];
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) { gnew[cc] = act ? lam[cc] : 0.f; gy[cc] = 0.f; }
+        if (act) {
+          while (ei >= 0 && (double)in.t_obs[ei] > t) {
+            const double te = (double)in.t_obs[ei];
+            const float* g = gtraj + (size_t)ei * NS;
+            if (te >= t_new) {
+              if (te == t_new) {
+#pragma unroll
+                for (int cc = 0; cc < NS; ++cc) gnew[cc] += g[cc];
+              }
+            } else {
+              const float xq = (float)((te - t) / h);
+#pragma unroll
+              for (int cc = 0; cc < NS; ++cc) gy[cc] += g[cc];
+              for (int i = 0; i < 7; ++i) {
+                const float wgt = hf * xq * fmaf(xq, fmaf(xq, fmaf(xq, kP[i][3], kP[i][2]), kP[i][1]), kP[i][0]);
+#pragma unroll
+                for (int cc = 0; cc < NS; ++cc) gk[i][cc] = fmaf(wgt, g[cc], gk[i][cc]);
+              }
+            }
+            --ei;
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) {
+          gy[cc] += gnew[cc];
+          for (int j = 0; j < 6; ++j) gk[j][cc] = fmaf(hf * kB[1][j], gnew[cc], gk[j][cc]);
+        }
+      }
+#pragma unroll 1
+      for (int i = N - 1; i >= 0; --i) {
+        float ys[NS], gys[NS];
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) {
+          float a_ = 0.f;
+          for (int j = 0; j < i; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);
+          ys[cc] = fmaf(hf, a_, y[cc]);
+          gys[cc] = 0.f;
+        }
+        const float ci = kC[solver][i];
+        const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
+        mech_vjp(th, ys, gdv[i], gd_present, gk[i], gys, gth);
+        float x[HODE_NN_IN], gx[HODE_NN_IN];
+        x[0] = (float)te;
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) x[1 + cc] = ys[cc];
+        x[7] = ys[3];
+        x[8] = tv[i];
+        bc.stash = stash0 + (size_t)i * stage_stride;
+        __syncwarp();
+        mlp_bwd_tile<true>(c, bc, x, gk[i], gx, acc);
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];
+        gys[3] += gx[7];
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) {
+          gy[cc] += gys[cc];
+          for (int j = 0; j < i; ++j) gk[j][cc] = fmaf(hf * kA[solver][i][j], gys[cc], gk[j][cc]);
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) lam[cc] = gy[cc];
+      }
+    }
+    if (!helper) {
+      if (ok) {
+        if (solver == 0) {
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) lam[cc] += gtraj[cc];
+        } else {
+          const double t0 = (double)in.t_obs[0];
+          for (; ei >= 0; --ei) {
+            if ((double)in.t_obs[ei] > t0) continue;
+            const float* g = gtraj + (size_t)ei * NS;
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) lam[cc] += g[cc];
+          }
+        }
+      }
+      if (G.grad_y0 && valid) {
+        float* o = G.grad_y0 + (size_t)unit * NS;
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) o[cc] = ok ? lam[cc] : 0.f;
+      }
+    }
+  }
+
+  // ---- per-CTA partial gradients ------------------------------------------------------------------
+  tc::fence_before_sync();
+  __syncthreads();
+  float* out = G.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(A.P + HODE_N_THETA);
+  if (helper) {
+    const int t = row;
+    // layer 0: weight [64][9] at 0, bias at 576
+#pragma unroll
+    for (int m = 0; m < 5; ++m) { const int e = t + 128 * m; if (e < 576) out[e] = acc.w0[m]; }
+    if (t < H) out[576 + t] = acc.bh[0];
+#pragma unroll
+    for (int l = 1; l < MAXL; ++l) {
+      if (l >= L) continue;
+      const int off = 640 + (l - 1) * 4160;
+      const int j0 = (t >> 4) * 8, k0 = (t & 15) * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[off + (j0 + i) * H + k0 + q] = acc.h[l - 1][i * 4 + q];
+      if (t < H) out[off + 4096 + t] = acc.bh[l];
+    }
+    const int offo = 640 + (L - 1) * 4160;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { const int e = t + 128 * m; if (e < 384) out[offo + e] = acc.wo[m]; }
+    if (t < NS) out[offo + 384 + t] = acc.bo;
+  } else {
+    // deterministic reduction of the theta gradients over the 128 trajectories slots
+#pragma unroll
+    for (int i = 0; i < HODE_N_THETA; ++i) Dbuf[i * TILE + row] = gth[i];
+  }
+  __syncthreads();
+  if (!helper && row < HODE_N_THETA) {
+    float sacc = 0.f;
+    for (int r = 0; r < TILE; ++r) sacc += Dbuf[row * TILE + r];
+    out[A.P + row] = sacc;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 256);
+}
+
+// ---- transposed weight image --------------------------------------------------------------------------
+// floats: [W_out^T: (n=in 64, k=out 16) hi 1024, lo 1024][W_l^T, l = L-1..1: hi 4096, lo 4096][W_0^T: (n=in 16, k=out 64) hi 1024, lo 1024]
+int tc_bwd_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024; }
+
+__global__ void prep_tc_bwd_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
+                                         int img_floats) {
+  const float* w = W + (size_t)blockIdx.x * P;
+  float* out = img + (size_t)blockIdx.x * img_floats;
+  for (int i = threadIdx.x; i < img_floats; i += blockDim.x) out[i] = 0.f;
+  __syncthreads();
+  // packed offsets: layer 0 at 0 (576 + 64), hidden l at 640 + (l-1)*4160, output at 640 + (L-1)*4160
+  float* dst = out;
+  for (int l = L; l >= 0; --l) {
+    const int n_out = (l == L) ? NS : H;          // = K of the transposed operand
+    const int n_in = (l == 0) ? HODE_NN_IN : H;   // = N of the transposed operand
+    const int Npad = (l == 0) ? 16 : H;
+    const int Kpad = (l == L) ? 16 : H;
+    const int part = (Kpad / 4) * Npad * 4;
+    const float* wl = w + (l == 0 ? 0 : 640 + (l - 1) * 4160);
+    for (int i = threadIdx.x; i < n_out * n_in; i += blockDim.x) {
+      const int o = i / n_in, in = i - o * n_in;   // W_l[o][in]  ->  (n = in, k = o)
+      uint32_t hi, lo;
+      tc::split_tf32(wl[i], hi, lo);
+      const int idx = ((o >> 2) * Npad + in) * 4 + (o & 3);
+      dst[idx] = __uint_as_float(hi);
+      dst[part + idx] = __uint_as_float(lo);
+    }
+    dst += 2 * part;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+bool adj_tc_supported(int H_, int L_) { return H_ == 64 && L_ >= 1 && L_ <= MAXL; }
+
+AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
+  AdjTcPlan p{};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms < 1) sms = 148;
+  const long blocks = ((long)B + TILE - 1) / TILE;
+  long gx = sms / (S > 0 ? S : 1);
+  if (gx < 1) gx = 1;
+  if (gx > blocks) gx = blocks;
+  if (gx < 1) gx = 1;
+  p.grid_x = (int)gx;
+  p.grid_y = S;
+  p.fwd_floats = tc_image_floats(L);
+  p.bwd_floats = tc_bwd_image_floats(L);
+  const int img_cap = ((p.fwd_floats > p.bwd_floats ? p.fwd_floats : p.bwd_floats) + 3) & ~3;
+  size_t floats = (size_t)((img_cap + 255) & ~255) + 2 * TILE * LD;
+  if (!t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) floats += T;
+  p.smem = (floats * sizeof(float) + 1023) & ~(size_t)1023;
+  p.partial_floats = (size_t)gx * S * (size_t)(P + HODE_N_THETA);
+  p.stash_floats = (size_t)gx * S * TILE * (size_t)NSTAGE_MAX * L * H;
+  p.img_floats = (size_t)S * (p.fwd_floats + p.bwd_floats);
+  return p;
+}
+
+size_t adj_tc_workspace_bytes(const AdjTcPlan& p) {
+  auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
+  return (al(p.partial_floats) + al(p.stash_floats) + al(p.img_floats)) * sizeof(float);
+}
+
+cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, float* grad_y0,
+                                  float* grad_theta, float* grad_W, void* workspace, cudaStream_t stream) {
+  const AdjTcPlan p = adj_tc_plan(A.B, A.S, A.L, A.P, A.T, A.t_per_traj);
+  if (p.smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
+  AdjTcArgs G{};
+  G.R = A;
+  G.grad_traj = grad_traj;
+  G.grad_y0 = grad_y0;
+  G.partials = reinterpret_cast<float*>(workspace);
+  G.stash = G.partials + al(p.partial_floats);
+  float* imgs = G.stash + al(p.stash_floats);
+  G.img_fwd = imgs;
+  G.img_bwd = imgs + (size_t)A.S * p.fwd_floats;
+  G.fwd_floats = p.fwd_floats;
+  G.bwd_floats = p.bwd_floats;
+  cudaError_t e = tc_prepare_fwd_images(A.W, imgs, A.S, A.L, A.P, stream);
+  if (e != cudaSuccess) return e;
+  prep_tc_bwd_image_kernel<<<A.S, 256, 0, stream>>>(A.W, imgs + (size_t)A.S * p.fwd_floats, A.L, A.P, p.bwd_floats);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(rollout_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return e;
+  rollout_bwd_tc_kernel<<<dim3(p.grid_x, p.grid_y), 256, p.smem, stream>>>(G);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_reduce_partials(G.partials, p.grid_x, A.S, A.P, grad_W, grad_theta, stream);
+}
+
+}  // namespace hode

@@ -142,13 +142,30 @@ static hode::AdjPlan bwd_plan(const hode_cfg* c) {
                         P, has_nn, c->n_obs, c->t_per_traj, 7);
 }
 
+static bool bwd_uses_tensor_cores(const hode_cfg* c) {
+  return uses_tensor_cores(c) && hode::adj_tc_supported(c->nn_hidden, c->nn_layers);
+}
+
+static hode::AdjTcPlan bwd_tc_plan(const hode_cfg* c) {
+  return hode::adj_tc_plan(c->n_traj, c->n_samples, c->nn_layers,
+                           (int)hode_mlp_param_count(c->nn_hidden, c->nn_layers), c->n_obs, c->t_per_traj);
+}
+
 int hode_workspace_bytes(const hode_cfg* cfg, size_t* fwd_bytes, size_t* bwd_bytes) {
   int rc = validate(cfg);
   if (rc) return rc;
   const Workspace w = fwd_workspace(cfg);
   if (fwd_bytes) *fwd_bytes = w.total;
-  // gradient scratch (per-CTA partial gradients + activation stash); also covers hode_rhs_vjp
-  if (bwd_bytes) *bwd_bytes = hode::adj_workspace_bytes(bwd_plan(cfg));
+  // gradient scratch (per-CTA partial gradients + activation stash [+ weight images of the
+  // tensor-core adjoint]); also covers hode_rhs_vjp
+  if (bwd_bytes) {
+    size_t n = hode::adj_workspace_bytes(bwd_plan(cfg));
+    if (bwd_uses_tensor_cores(cfg)) {
+      const size_t m = hode::adj_tc_workspace_bytes(bwd_tc_plan(cfg));
+      if (m > n) n = m;
+    }
+    *bwd_bytes = n;
+  }
   return 0;
 }
 
@@ -202,10 +219,13 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   const Workspace w = fwd_workspace(cfg);
   if (!fwd_workspace_ptr || fwd_workspace_bytes < w.total)
     return fail(HODE_E_WORKSPACE, "forward workspace missing or smaller than hode_workspace_bytes()");
+  const bool tc_adj = bwd_uses_tensor_cores(cfg);
   const hode::AdjPlan plan = bwd_plan(cfg);
-  if (plan.smem > 227 * 1024)
+  if (!tc_adj && plan.smem > 227 * 1024)
     return fail(HODE_E_UNSUPPORTED, "network too large for the shared-memory gradient accumulators");
-  if (!bwd_workspace || bwd_workspace_bytes < hode::adj_workspace_bytes(plan))
+  size_t need = 0;
+  hode_workspace_bytes(cfg, nullptr, &need);
+  if (!bwd_workspace || bwd_workspace_bytes < need)
     return fail(HODE_E_WORKSPACE, "backward workspace missing or smaller than hode_workspace_bytes()");
   if (cfg->n_traj == 0) return 0;
   hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
@@ -215,8 +235,11 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   A.save_h = (float*)(base + w.off_h);
   A.save_y = (float*)(base + w.off_y);
   A.max_saved = w.max_saved;
-  cudaError_t e = hode::launch_rollout_bwd(A, cfg->mlp != HODE_MLP_NONE, grad_traj, grad_y0, grad_theta,
-                                           grad_W, bwd_workspace, (cudaStream_t)stream);
+  // forward on the tensor cores -> adjoint on the tensor cores (3xTF32); FP32 forward -> FP32 adjoint
+  cudaError_t e = tc_adj ? hode::launch_rollout_bwd_tc(A, grad_traj, grad_y0, grad_theta, grad_W, bwd_workspace,
+                                                       (cudaStream_t)stream)
+                         : hode::launch_rollout_bwd(A, cfg->mlp != HODE_MLP_NONE, grad_traj, grad_y0, grad_theta,
+                                                    grad_W, bwd_workspace, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_bwd launch");
   return 0;
 }

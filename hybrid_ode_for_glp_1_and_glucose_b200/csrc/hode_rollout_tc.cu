@@ -76,6 +76,11 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
   }
 }
 
+cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, cudaStream_t stream) {
+  prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats(L));
+  return cudaGetLastError();
+}
+
 // ---- per-lane trajectory state ---------------------------------------------------------------------
 struct Lane {
   TrajInputs in;

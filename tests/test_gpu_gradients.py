@@ -237,3 +237,38 @@ def test_differentiable_forward_trains_the_data_term(dev):
     assert head.weight.grad is not None and float(head.weight.grad.abs().max()) > 0
     assert y0t.grad is not None and float(y0t.grad.abs().max()) > 0
     assert losses[-1] < losses[0]
+
+
+# ---------------------------------------------------------------------------- tensor-core adjoint
+@pytest.mark.parametrize("solver,layers", [("rk4", 4), ("dopri5", 4), ("rk4", 2), ("dopri5", 1)])
+def test_tensor_core_adjoint_matches_autograd(dev, solver, layers):
+    """precision='tf32x3' routes hode_rollout_bwd to the tcgen05 adjoint (hode_adjoint_tc.cu)."""
+    kw = dict(n_substeps=2) if solver == "rk4" else {}
+    errs = _adjoint_case(dev, 6, 11, 64, layers, solver, seed=21 + layers, precision="tf32x3", **kw)
+    assert max(errs) < TOL, errs
+
+
+def test_tensor_core_adjoint_equals_fp32_adjoint_at_scale(dev):
+    """Fixed-step rollouts take identical steps on both paths, so the two adjoints must agree:
+    B spans several tiles per CTA is exercised with a small grid by S = 2 parameter sets."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T, S = 1500, 7, 2
+    y0, t, ins = cohort(B, T, seed=41, horizon=0.6)
+    ins["GD"] = np.linspace(0, 800, B).astype(np.float32)
+    theta = np.tile(golden("rhs_mech")["theta"], (S, 1))
+    theta[1, 8] = 8.0
+    W = np.stack([random_mlp(64, 4, seed=50 + s, out_std=0.05) for s in range(S)])
+    g = np.random.default_rng(42).normal(0, 1, (S, B, T, 6)).astype(np.float32)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    tin = {k: tt(v) for k, v in ins.items()}
+    out = {}
+    for prec in ("fp32", "tf32x3"):
+        _, info, tape = ops.rollout(tt(y0), tt(t), tin, tt(theta), tt(W), solver="rk4", n_substeps=2,
+                                    precision=prec, device=dev, save_steps=True)
+        assert bool((info.status == 0).all())
+        out[prec] = ops.rollout_bwd(tape, tt(g).to(dev))
+        again = ops.rollout_bwd(tape, tt(g).to(dev))
+        assert all(torch.equal(a, b) for a, b in zip(out[prec], again)), "bit-reproducible"
+    for a, b, name in zip(out["tf32x3"], out["fp32"], ("y0", "theta", "W")):
+        for s in range(S):
+            assert relmax(a[s].cpu().numpy(), b[s].cpu().numpy()) < 5e-5, (name, s)
