@@ -31,7 +31,6 @@ namespace hode {
 
 namespace {
 
-constexpr int LD = 68;        // staging row stride (floats): 17 x 16 B, conflict-free own-row float4
 constexpr int MAXL = 4;       // hidden layers supported by the register accumulators
 constexpr int NSTAGE_MAX = 7;
 
@@ -51,27 +50,6 @@ __constant__ float kP[7][4] = {{dp::p11, dp::p12, dp::p13, dp::p14}, {0.f, 0.f, 
                                {0.f, dp::p32, dp::p33, dp::p34},     {0.f, dp::p42, dp::p43, dp::p44},
                                {0.f, dp::p52, dp::p53, dp::p54},     {0.f, dp::p62, dp::p63, dp::p64},
                                {0.f, dp::p72, dp::p73, dp::p74}};
-
-// weight-gradient accumulators of one helper thread (t = 0..127):
-//   hidden layer l (1..L-1): rows j = (t>>4)*8 .. +8, columns k = (t&15)*4 .. +4 of dW_l [64][64]
-//   layer 0 [64][9]: elements e = t + 128 m (m = 0..4, e < 576);  output layer [6][64]: e = t + 128 m (m < 3)
-//   biases: thread t < 64 owns db_l[t] of every hidden layer, t < 6 owns db_out[t]
-struct DwAcc {
-  float h[MAXL - 1][32];
-  float w0[5];
-  float wo[3];
-  float bh[MAXL];
-  float bo;
-};
-
-struct BwdCtx {
-  float* Dbuf;          // [128][LD] delta rows (fp32)
-  float* Abuf;          // [128][LD] layer-input rows (fp32)
-  uint32_t img_s;       // shared-memory address of the transposed weight image
-  const float* stash;   // this row's activation column of the current stage; element e at stash[e * ss]
-  size_t ss;
-  int row;              // trajectory slot 0..127
-};
 
 // D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi without a bias step (the first MMA initialises D)
 template <int N, int KSTEPS>
@@ -103,64 +81,114 @@ __device__ __forceinline__ void split16(const float* d, uint32_t* hi, uint32_t* 
   }
 }
 
-// ---- helper-warp weight-gradient products over the staged rows -------------------------------------
-__device__ __forceinline__ void gemm_hidden(float* acc /*[32]*/, const float* __restrict__ D,
-                                            const float* __restrict__ A, int t) {
-  const float* dp_ = D + (t >> 4) * 8;
-  const float* ap = A + (t & 15) * 4;
-#pragma unroll 2
-  for (int r = 0; r < TILE; ++r) {
-    const float4 d0 = *reinterpret_cast<const float4*>(dp_ + r * LD);
-    const float4 d1 = *reinterpret_cast<const float4*>(dp_ + r * LD + 4);
-    const float4 a = *reinterpret_cast<const float4*>(ap + r * LD);
-    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    const float aa[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[i * 4 + q] = fmaf(dd[i], aa[q], acc[i * 4 + q]);
-  }
+// ---- weight gradients on the tensor cores ---------------------------------------------------------
+// dW_l += delta_l^T a_{l-1} contracts over the 128 trajectories of the tile: an SS-form MMA
+// (both operands in shared memory, K = trajectory).  kind::tf32 needs K-major operands, so every
+// thread writes its trajectory's values TRANSPOSED into the canonical no-swizzle K-major layout
+// (validated by csrc/probe/adj_probe.cu, test 3):
+//   element (feature f, trajectory t) at float  (t % 4) + 4 * (f % 8) + 32 * (f / 8) + CH * (t / 4)
+// with CH = 8-feature groups * 32 + 4 pad floats (the pad makes the 32 lanes of a warp hit 32
+// different banks).  delta arrays hold 64 features (CH_D = 260), input arrays 80: 64 features +
+// one group whose first feature is the constant 1 (its accumulator column is the bias gradient)
+// + one zero group (N must be a multiple of 16) (CH_A = 324).  hi / lo TF32 parts are separate
+// arrays; the product is the usual 3-pass d_lo*a_hi + d_hi*a_lo + d_hi*a_hi.
+// The accumulators live in TMEM for the whole kernel (fp32):
+//   hidden layer l = 1..3 : columns DW_H0 + 80 (l-1) .. +80   D[j][k] = dW_l[j][k], column 64 = db_l[j]
+//   layer 0               : columns DW_0  .. +16               D[j][k] = dW_0[j][k] (k < 9), column 15 = db_0[j]
+//   output layer (transp.): columns DW_O  .. +16               D[k][n] = dW_out[n][k] (n < 6), row 64 = db_out[n]
+constexpr int CH_D = 8 * 32 + 4, CH_A = 10 * 32 + 4;
+constexpr int SD_FLOATS = 32 * CH_D + 256, SA_FLOATS = 32 * CH_A + 256;   // + slack: M = 128 reads 16 groups
+constexpr int WSLOT_FLOATS = 2 * 4096;
+constexpr uint32_t DW_H0 = 208, DW_0 = 448, DW_O = 464;
+
+struct BwdCtx {
+  float* sd_hi; float* sd_lo;   // delta staging (K-major transposed)
+  float* sa_hi; float* sa_lo;   // layer-input staging
+  float* wslot;                 // one layer's transposed weights (hi then lo), streamed per phase
+  const float* wsrc;            // global: this parameter set's transposed weight image
+  uint64_t* wload_bar;          // completion of the weight-slot bulk copy (main warp 0 waits)
+  uint64_t* gemm_bar;           // completion of the weight-gradient MMAs (frees the staging arrays)
+  uint32_t wload_parity, gemm_parity;
+  uint32_t first;               // 1 until the accumulators have been initialised
+  const float* stash;           // this row's activation column of the current stage; element e at stash[e * ss]
+  size_t ss;
+  int row;                      // trajectory slot 0..127
+};
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
 }
 
-template <int NE, int NIN, int TOTAL>
-__device__ __forceinline__ void gemm_small(float* acc /*[NE]*/, const float* __restrict__ D,
-                                           const float* __restrict__ A, int t) {
-#pragma unroll
-  for (int m = 0; m < NE; ++m) {
-    const int e = t + 128 * m;
-    if (e < TOTAL) {
-      const int j = e / NIN, k = e - j * NIN;
-      float s = 0.f;
-      for (int r = 0; r < TILE; ++r) s = fmaf(D[r * LD + j], A[r * LD + k], s);
-      acc[m] += s;
-    }
-  }
+// D[tmem] (+)= A^T B over the 128 trajectories: 3 passes x 16 k-steps of 8 trajectories.
+// (a_hi, a_lo): staging arrays of the operand that becomes the ROWS of D (chunk stride cha floats),
+// (b_hi, b_lo): of the operand that becomes the COLUMNS (chunk stride chb).  `init` = overwrite D.
+template <int N>
+__device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_hi, uint32_t a_lo, int cha, uint32_t b_hi, uint32_t b_lo,
+                                         int chb, uint32_t init) {
+  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
+  const uint64_t da_hi = tc::make_desc(a_hi, (uint32_t)cha * 4u, 128u), da_lo = tc::make_desc(a_lo, (uint32_t)cha * 4u, 128u);
+  const uint64_t db_hi = tc::make_desc(b_hi, (uint32_t)chb * 4u, 128u), db_lo = tc::make_desc(b_lo, (uint32_t)chb * 4u, 128u);
+  // one k-step = 8 trajectories = 2 chunks: the start-address field (16-byte units) advances by 2*CH*4/16
+  const uint64_t sa = (uint64_t)((uint32_t)cha * 8u >> 4), sb = (uint64_t)((uint32_t)chb * 8u >> 4);
+#pragma unroll 4
+  for (int ks = 0; ks < TILE / 8; ++ks)
+    mma_tf32_ss(d, da_lo + sa * ks, db_hi + sb * ks, idesc, (ks == 0 && init) ? 0u : 1u);
+#pragma unroll 4
+  for (int ks = 0; ks < TILE / 8; ++ks) mma_tf32_ss(d, da_hi + sa * ks, db_lo + sb * ks, idesc, 1u);
+#pragma unroll 4
+  for (int ks = 0; ks < TILE / 8; ++ks) mma_tf32_ss(d, da_hi + sa * ks, db_hi + sb * ks, idesc, 1u);
 }
 
-__device__ __forceinline__ float col_sum(const float* __restrict__ D, int j) {
-  float s = 0.f;
-  for (int r = 0; r < TILE; ++r) s += D[r * LD + j];
-  return s;
+// transposed staging of 4 consecutive features f0..f0+3 of trajectory `row` (TF32 hi / lo)
+__device__ __forceinline__ void stage4(float* hi, float* lo, int ch, int row, int f0, float v0, float v1, float v2,
+                                       float v3) {
+  const int base = (row & 3) + ch * (row >> 2) + 32 * (f0 >> 3) + 4 * (f0 & 7);
+  const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t h = (__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u;
+    hi[base + 4 * q] = __uint_as_float(h);
+    lo[base + 4 * q] = v[q] - __uint_as_float(h);
+  }
 }
 
 // ---- MLP backward for one stage (tile-collective: all 256 threads) ------------------------------------
 // MAIN threads own accumulator columns [0,32) of their trajectory, helpers [32,64).
 // g6 (main): cotangent of the 6 network outputs; x9 (main): the stage's input features;
 // gx (main, out): cotangent of the 9 input features.
+// Notation: delta_l = cotangent of the pre-activation of layer l (l = 0..L-1), delta_L = g;
+// phase p issues  dW_p += delta_p^T a_{p-1}  and  u_{p-1} = delta_p W_p  (p = L..1), phase 0 issues
+// dW_0 += delta_0^T x  and  g_x = delta_0 W_0.
 template <bool MAIN>
-__device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, const BwdCtx& b, const float* x9, const float* g6,
-                                             float* gx, DwAcc& acc) {
+__device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float* x9, const float* g6, float* gx) {
   constexpr int half = MAIN ? 0 : 32;
   const int L = c.L;
-  const int ht = threadIdx.x & 127;   // helper index (gemm ownership)
-  float* Drow = b.Dbuf + b.row * LD;
-  float* Arow = b.Abuf + b.row * LD;
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
   const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+  const uint32_t wslot_s = tc::smem_u32(b.wslot);
+  const uint32_t sd_hi = tc::smem_u32(b.sd_hi), sd_lo = tc::smem_u32(b.sd_lo);
+  const uint32_t sa_hi = tc::smem_u32(b.sa_hi), sa_lo = tc::smem_u32(b.sa_lo);
+  const bool issuer_warp = MAIN && c.wq == 0;
 
-  // ---- prologue: delta_L = g, operands of dW_out, MMA phase L: u_{L-1} = delta_L W_out ----------
+  // stream one block of the transposed weight image into the slot (previous reader has completed)
+  auto fetch_w = [&](int float_off, int floats) {
+    if (MAIN && threadIdx.x == 0) {
+      tc::mbar_expect_tx(b.wload_bar, (uint32_t)floats * 4u);
+      tc::bulk_g2s(b.wslot, b.wsrc + float_off, (uint32_t)floats * 4u, b.wload_bar);
+    }
+  };
+
+  // ---- prologue: delta_L = g; operands of dW_out; phase L --------------------------------------------
+  // the staging arrays are free once the previous stage's weight-gradient MMAs have completed
+  tc::mbar_wait(b.gemm_bar, b.gemm_parity ^ 1u);   // (first call: the phase "before 0" counts as complete)
+  fetch_w(0, 2048);
   if (MAIN) {
     float d[16];
 #pragma unroll
@@ -169,42 +197,45 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, const BwdCtx& b, const 
     split16(d, hi, lo);
     HODE_TMEM_ST_X16(t_ahi, hi);
     HODE_TMEM_ST_X16(t_alo, lo);
-    *reinterpret_cast<float4*>(Drow) = make_float4(d[0], d[1], d[2], d[3]);
-    *reinterpret_cast<float4*>(Drow + 4) = make_float4(d[4], d[5], 0.f, 0.f);
+    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 0, d[0], d[1], d[2], d[3]);
+    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 4, d[4], d[5], 0.f, 0.f);
+    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 8, 0.f, 0.f, 0.f, 0.f);    // N = 16: features 8..15 are zero
+    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 12, 0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
-  for (int j4 = 0; j4 < 32; j4 += 4) {
-    float4 a;
-    a.x = b.stash[(size_t)((L - 1) * H + half + j4 + 0) * b.ss];
-    a.y = b.stash[(size_t)((L - 1) * H + half + j4 + 1) * b.ss];
-    a.z = b.stash[(size_t)((L - 1) * H + half + j4 + 2) * b.ss];
-    a.w = b.stash[(size_t)((L - 1) * H + half + j4 + 3) * b.ss];
-    *reinterpret_cast<float4*>(Arow + half + j4) = a;
-  }
+  for (int j4 = 0; j4 < 32; j4 += 4)
+    stage4(b.sa_hi, b.sa_lo, CH_A, b.row, half + j4, b.stash[(size_t)((L - 1) * H + half + j4 + 0) * b.ss],
+           b.stash[(size_t)((L - 1) * H + half + j4 + 1) * b.ss], b.stash[(size_t)((L - 1) * H + half + j4 + 2) * b.ss],
+           b.stash[(size_t)((L - 1) * H + half + j4 + 3) * b.ss]);
   tc::wait_st();
+  tc::fence_proxy_async();
   tc::fence_before_sync();
   tile_sync_all(c);
-  if (MAIN && c.wq == 0) {
+  if (issuer_warp) {
+    tc::mbar_wait(b.wload_bar, b.wload_parity);
     if (tc::elect_one()) {
       tc::fence_after_sync();
-      issue_nobias<H, 2>(m_d, m_ahi, m_alo, b.img_s, b.img_s + 1024u * 4u);
+      issue_nobias<H, 2>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
       tc::mma_commit(c.mma_bar);
+      // dW_out^T [in k][out n] = a_{L-1}^T delta_L  (rows = the 80 staged input features: row 64 = db_out)
+      issue_dw<16>(c.tmem + DW_O, sa_hi, sa_lo, CH_A, sd_hi, sd_lo, CH_D, b.first);
+      tc::mma_commit(b.gemm_bar);
     }
     __syncwarp();
   }
-  if (!MAIN) {
-    gemm_small<3, 64, 384>(acc.wo, b.Dbuf, b.Abuf, ht);
-    if (ht < NS) acc.bo += col_sum(b.Dbuf, ht);
-  }
-  tile_sync_all(c);
+  b.wload_parity ^= 1u;
+  b.gemm_parity ^= 1u;
 
-  // ---- phases p = L .. 1: delta_{p-1} = u_{p-1} * relu'(a_{p-1}); dW_{p-1}; MMA phase p-1 ----------
+  // ---- phases p = L .. 1 ---------------------------------------------------------------------------------
 #pragma unroll
   for (int p = MAXL; p >= 1; --p) {
     if (p > L) continue;
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
+    // the weight slot is free (its reader was the MMA chain just waited for): prefetch the next block
+    if (p >= 2) fetch_w(2048 + (L - p) * 8192, 8192);
+    else fetch_w(2048 + (L - 1) * 8192, 2048);
     uint32_t u[32];
     HODE_TMEM_LD_X32(t_d, u);
     float a[32];
@@ -214,9 +245,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, const BwdCtx& b, const 
     float d[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) d[j] = a[j] > 0.f ? __uint_as_float(u[j]) : 0.f;
-#pragma unroll
-    for (int j4 = 0; j4 < 32; j4 += 4)
-      *reinterpret_cast<float4*>(Drow + half + j4) = make_float4(d[j4], d[j4 + 1], d[j4 + 2], d[j4 + 3]);
     {
       uint32_t hi[16], lo[16];
       split16(d, hi, lo);
@@ -226,47 +254,45 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, const BwdCtx& b, const 
       HODE_TMEM_ST_X16(t_ahi + half + 16, hi);
       HODE_TMEM_ST_X16(t_alo + half + 16, lo);
     }
+    // staging may be rewritten once the previous phase's weight-gradient MMAs are done
+    tc::mbar_wait(b.gemm_bar, b.gemm_parity ^ 1u);
+#pragma unroll
+    for (int j4 = 0; j4 < 32; j4 += 4) stage4(b.sd_hi, b.sd_lo, CH_D, b.row, half + j4, d[j4], d[j4 + 1], d[j4 + 2], d[j4 + 3]);
     if (p >= 2) {   // inputs of layer p-1 are a_{p-2}
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        float4 v;
-        v.x = b.stash[(size_t)((p - 2) * H + half + j4 + 0) * b.ss];
-        v.y = b.stash[(size_t)((p - 2) * H + half + j4 + 1) * b.ss];
-        v.z = b.stash[(size_t)((p - 2) * H + half + j4 + 2) * b.ss];
-        v.w = b.stash[(size_t)((p - 2) * H + half + j4 + 3) * b.ss];
-        *reinterpret_cast<float4*>(Arow + half + j4) = v;
-      }
-    } else if (MAIN) {   // inputs of layer 0 are the 9 stage features
-      *reinterpret_cast<float4*>(Arow) = make_float4(x9[0], x9[1], x9[2], x9[3]);
-      *reinterpret_cast<float4*>(Arow + 4) = make_float4(x9[4], x9[5], x9[6], x9[7]);
-      *reinterpret_cast<float4*>(Arow + 8) = make_float4(x9[8], 0.f, 0.f, 0.f);
+      for (int j4 = 0; j4 < 32; j4 += 4)
+        stage4(b.sa_hi, b.sa_lo, CH_A, b.row, half + j4, b.stash[(size_t)((p - 2) * H + half + j4 + 0) * b.ss],
+               b.stash[(size_t)((p - 2) * H + half + j4 + 1) * b.ss], b.stash[(size_t)((p - 2) * H + half + j4 + 2) * b.ss],
+               b.stash[(size_t)((p - 2) * H + half + j4 + 3) * b.ss]);
+    } else if (MAIN) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
+      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 0, x9[0], x9[1], x9[2], x9[3]);
+      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 4, x9[4], x9[5], x9[6], x9[7]);
+      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 8, x9[8], 0.f, 0.f, 0.f);
+      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 12, 0.f, 0.f, 0.f, 1.f);
     }
     tc::wait_st();
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     tile_sync_all(c);
-    if (MAIN && c.wq == 0) {
+    if (issuer_warp) {
+      tc::mbar_wait(b.wload_bar, b.wload_parity);
       if (tc::elect_one()) {
         tc::fence_after_sync();
-        if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1} (hidden, 64 x 64)
-          const uint32_t blk = b.img_s + (uint32_t)(2048 + (L - p) * 8192) * 4u;
-          issue_nobias<H, 8>(m_d, m_ahi, m_alo, blk, blk + 4096u * 4u);
-        } else {        // g_x = delta_0 W_0 (N = 16: the 9 features padded)
-          const uint32_t blk = b.img_s + (uint32_t)(2048 + (L - 1) * 8192) * 4u;
-          issue_nobias<16, 8>(m_d, m_ahi, m_alo, blk, blk + 1024u * 4u);
+        if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1};  dW_{p-1} += delta_{p-1}^T [a_{p-2} | 1]
+          issue_nobias<H, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 4096u * 4u);
+          tc::mma_commit(c.mma_bar);
+          issue_dw<80>(c.tmem + DW_H0 + 80u * (uint32_t)(p - 2), sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
+        } else {        // g_x = delta_0 W_0;  dW_0 += delta_0^T [x | 1]
+          issue_nobias<16, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
+          tc::mma_commit(c.mma_bar);
+          issue_dw<16>(c.tmem + DW_0, sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
         }
-        tc::mma_commit(c.mma_bar);
+        tc::mma_commit(b.gemm_bar);
       }
       __syncwarp();
     }
-    if (!MAIN) {
-      if (p >= 2) {
-        gemm_hidden(acc.h[p - 2], b.Dbuf, b.Abuf, ht);
-      } else {
-        gemm_small<5, 9, 576>(acc.w0, b.Dbuf, b.Abuf, ht);
-      }
-      if (ht < H) acc.bh[p - 1] += col_sum(b.Dbuf, ht);
-    }
-    tile_sync_all(c);
+    b.wload_parity ^= 1u;
+    b.gemm_parity ^= 1u;
   }
   // ---- final phase: g_x -------------------------------------------------------------------------
   tc::mbar_wait(c.mma_bar, c.parity);
@@ -279,6 +305,7 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, const BwdCtx& b, const 
 #pragma unroll
     for (int k = 0; k < HODE_NN_IN; ++k) gx[k] = __uint_as_float(v[k]);
   }
+  b.first = 0u;
 }
 
 // closed-form VJP of f_physio — same formulas as hode_adjoint_simt.cu::rhs_mech_vjp
@@ -351,6 +378,8 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t load_bar;
+  __shared__ __align__(8) uint64_t wload_bar;
+  __shared__ __align__(8) uint64_t gemm_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_nmax;
 
@@ -364,18 +393,26 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   const int N = solver == 0 ? 4 : 7;
   const long n_units = (long)A.S * A.B;
 
+  // shared memory: the forward weight image during the recomputation; during the reverse sweep the
+  // same bytes hold [weight slot][delta staging hi, lo][input staging hi, lo]
   float* img = reinterpret_cast<float*>(smem_raw);
-  const int img_cap = ((G.fwd_floats > G.bwd_floats ? G.fwd_floats : G.bwd_floats) + 3) & ~3;
-  float* Dbuf = img + ((img_cap + 255) & ~255);
-  float* Abuf = Dbuf + TILE * LD;
-  float* t_sh_buf = Abuf + TILE * LD;
-
+  float* wslot = img;
+  float* sd_hi = wslot + WSLOT_FLOATS;
+  float* sd_lo = sd_hi + SD_FLOATS;
+  float* sa_hi = sd_lo + SD_FLOATS;
+  float* sa_lo = sa_hi + SA_FLOATS;
+  const int bwd_cap = WSLOT_FLOATS + 2 * SD_FLOATS + 2 * SA_FLOATS;
+  const int img_cap = ((G.fwd_floats > bwd_cap ? G.fwd_floats : bwd_cap) + 255) & ~255;
+  float* t_sh_buf = img + img_cap;
+  float* red = sd_hi;   // [17][128] theta-gradient reduction scratch at the very end
   if (tid == 0) {
     tc::mbar_init(&mma_bar, 1);
     tc::mbar_init(&load_bar, 1);
+    tc::mbar_init(&wload_bar, 1);
+    tc::mbar_init(&gemm_bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   const float* t_shared = nullptr;
   if (!A.t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) {
     for (int i = tid; i < T; i += blockDim.x) t_sh_buf[i] = A.t_obs[i];
@@ -407,24 +444,16 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   float* stash0 = G.stash + gt;
 
   BwdCtx bc;
-  bc.Dbuf = Dbuf; bc.Abuf = Abuf;
-  bc.img_s = tc::smem_u32(img);
+  bc.sd_hi = sd_hi; bc.sd_lo = sd_lo; bc.sa_hi = sa_hi; bc.sa_lo = sa_lo;
+  bc.wslot = wslot;
+  bc.wsrc = G.img_bwd + (size_t)s * G.bwd_floats;
+  bc.wload_bar = &wload_bar;
+  bc.gemm_bar = &gemm_bar;
+  bc.wload_parity = 0; bc.gemm_parity = 0;
+  bc.first = 1u;
   bc.ss = NT;
   bc.row = row;
   bc.stash = stash0;
-
-  DwAcc acc;
-#pragma unroll
-  for (int l = 0; l < MAXL - 1; ++l)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc.h[l][i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 5; ++i) acc.w0[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) acc.wo[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXL; ++i) acc.bh[i] = 0.f;
-  acc.bo = 0.f;
 
   const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
   const bool gd_present = A.in_mode[HODE_CH_GD] != HODE_IN_ABSENT;
@@ -435,8 +464,10 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
 
   // swap the shared-memory weight image (forward <-> transposed); every thread calls it
   auto load_image = [&](const float* src, int floats) {
+    // the weight-gradient MMAs of the previous reverse sweep still read the staging arrays
+    tc::mbar_wait(&gemm_bar, bc.gemm_parity ^ 1u);
     tc::fence_before_sync();
-    __syncthreads();   // nobody still reads the old image (all MMAs that did have been waited for)
+    __syncthreads();   // nobody still reads the old contents (all MMAs that did have been waited for)
     if (tid == 0) {
       const uint32_t bytes = (uint32_t)floats * 4u;
       tc::mbar_expect_tx(&load_bar, bytes);
@@ -446,7 +477,18 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
     load_parity ^= 1u;
   };
   const float* fwd_src = G.img_fwd + (size_t)s * G.fwd_floats;
-  const float* bwd_src = G.img_bwd + (size_t)s * G.bwd_floats;
+  // start of a reverse sweep: the forward image is dead; (re)write the constant features of the
+  // input staging (feature 64 = 1 -> bias-gradient column, 65..79 = 0)
+  auto begin_reverse = [&]() {
+    tc::fence_before_sync();
+    __syncthreads();
+    if (!helper) {
+      stage4(sa_hi, sa_lo, CH_A, row, 64, 1.f, 0.f, 0.f, 0.f);
+      stage4(sa_hi, sa_lo, CH_A, row, 68, 0.f, 0.f, 0.f, 0.f);
+      stage4(sa_hi, sa_lo, CH_A, row, 72, 0.f, 0.f, 0.f, 0.f);
+      stage4(sa_hi, sa_lo, CH_A, row, 76, 0.f, 0.f, 0.f, 0.f);
+    }
+  };
 
   for (long blk = blockIdx.x; blk * TILE < A.B; blk += gridDim.x) {
     const long b = blk * TILE + row;
@@ -484,11 +526,11 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
       if (helper) {
 #pragma unroll 1
         for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, NT);
-        load_image(bwd_src, G.bwd_floats);
+        begin_reverse();
 #pragma unroll 1
         for (int i = N - 1; i >= 0; --i) {
           bc.stash = stash0 + (size_t)i * stage_stride;
-          mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr, acc);
+          mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
         }
         continue;
       }
@@ -550,7 +592,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         for (int cc = 0; cc < NS; ++cc) k[i][cc] = __fadd_rn(d[cc], r[cc]);
       }
       // =========================== reverse sweep ===================================================
-      load_image(bwd_src, G.bwd_floats);
+      begin_reverse();
       float gy[NS], gk[NSTAGE_MAX][NS];
 #pragma unroll
       for (int i = 0; i < NSTAGE_MAX; ++i)
@@ -620,7 +662,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         x[8] = tv[i];
         bc.stash = stash0 + (size_t)i * stage_stride;
         __syncwarp();
-        mlp_bwd_tile<true>(c, bc, x, gk[i], gx, acc);
+        mlp_bwd_tile<true>(c, bc, x, gk[i], gx);
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];
         gys[3] += gx[7];
@@ -658,45 +700,68 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
     }
   }
 
-  // ---- per-CTA partial gradients ------------------------------------------------------------------
+  // ---- per-CTA partial gradients: TMEM accumulators -> workspace ---------------------------------
+  tc::mbar_wait(&gemm_bar, bc.gemm_parity ^ 1u);
   tc::fence_before_sync();
   __syncthreads();
+  tc::fence_after_sync();
   float* out = G.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(A.P + HODE_N_THETA);
-  if (helper) {
-    const int t = row;
-    // layer 0: weight [64][9] at 0, bias at 576
+  const bool have = bc.first == 0u;   // false: this CTA processed no step, the accumulators were never written
+  const int offo = 640 + (L - 1) * 4160;
+  if (!helper && wq < 2) {
+    const int j = row;   // TMEM lane = output row of the accumulators (0..63)
+    uint32_t v[16];
+    // layer 0: D[j][k] (k < 9), column 15 = db_0[j]
+    HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_0, v);
+    tc::wait_ld();
 #pragma unroll
-    for (int m = 0; m < 5; ++m) { const int e = t + 128 * m; if (e < 576) out[e] = acc.w0[m]; }
-    if (t < H) out[576 + t] = acc.bh[0];
+    for (int k = 0; k < HODE_NN_IN; ++k) out[j * HODE_NN_IN + k] = have ? __uint_as_float(v[k]) : 0.f;
+    out[576 + j] = have ? __uint_as_float(v[15]) : 0.f;
 #pragma unroll
     for (int l = 1; l < MAXL; ++l) {
       if (l >= L) continue;
       const int off = 640 + (l - 1) * 4160;
-      const int j0 = (t >> 4) * 8, k0 = (t & 15) * 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int cidx = 0; cidx < 5; ++cidx) {
+        HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_H0 + 80u * (uint32_t)(l - 1) + 16u * (uint32_t)cidx, v);
+        tc::wait_ld();
+        if (cidx < 4) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) out[off + (j0 + i) * H + k0 + q] = acc.h[l - 1][i * 4 + q];
-      if (t < H) out[off + 4096 + t] = acc.bh[l];
+          for (int i = 0; i < 16; ++i) out[off + j * H + cidx * 16 + i] = have ? __uint_as_float(v[i]) : 0.f;
+        } else {
+          out[off + 4096 + j] = have ? __uint_as_float(v[0]) : 0.f;
+        }
+      }
     }
-    const int offo = 640 + (L - 1) * 4160;
+    // output layer (transposed): D[k][n] = dW_out[n][k]
+    HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
+    tc::wait_ld();
 #pragma unroll
-    for (int m = 0; m < 3; ++m) { const int e = t + 128 * m; if (e < 384) out[offo + e] = acc.wo[m]; }
-    if (t < NS) out[offo + 384 + t] = acc.bo;
-  } else {
-    // deterministic reduction of the theta gradients over the 128 trajectories slots
+    for (int nn = 0; nn < NS; ++nn) out[offo + nn * H + j] = have ? __uint_as_float(v[nn]) : 0.f;
+  }
+  if (!helper && wq == 2) {   // TMEM lane 64: the constant-1 input feature -> db_out (warp-wide load)
+    uint32_t v[16];
+    HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
+    tc::wait_ld();
+    if (lane_id == 0) {
 #pragma unroll
-    for (int i = 0; i < HODE_N_THETA; ++i) Dbuf[i * TILE + row] = gth[i];
+      for (int nn = 0; nn < NS; ++nn) out[offo + 384 + nn] = have ? __uint_as_float(v[nn]) : 0.f;
+    }
+  }
+  if (!helper) {
+    // deterministic reduction of the theta gradients over the 128 trajectory slots
+#pragma unroll
+    for (int i = 0; i < HODE_N_THETA; ++i) red[i * TILE + row] = gth[i];
   }
   __syncthreads();
   if (!helper && row < HODE_N_THETA) {
     float sacc = 0.f;
-    for (int r = 0; r < TILE; ++r) sacc += Dbuf[row * TILE + r];
+    for (int r = 0; r < TILE; ++r) sacc += red[row * TILE + r];
     out[A.P + row] = sacc;
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
 // ---- transposed weight image --------------------------------------------------------------------------
@@ -750,8 +815,8 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   p.grid_y = S;
   p.fwd_floats = tc_image_floats(L);
   p.bwd_floats = tc_bwd_image_floats(L);
-  const int img_cap = ((p.fwd_floats > p.bwd_floats ? p.fwd_floats : p.bwd_floats) + 3) & ~3;
-  size_t floats = (size_t)((img_cap + 255) & ~255) + 2 * TILE * LD;
+  const int bwd_cap = WSLOT_FLOATS + 2 * SD_FLOATS + 2 * SA_FLOATS;
+  size_t floats = (size_t)(((p.fwd_floats > bwd_cap ? p.fwd_floats : bwd_cap) + 255) & ~255);
   if (!t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) floats += T;
   p.smem = (floats * sizeof(float) + 1023) & ~(size_t)1023;
   p.partial_floats = (size_t)gx * S * (size_t)(P + HODE_N_THETA);
