@@ -366,6 +366,22 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   size_t o_ws[MAX_STREAMS];
   for (int i = 0; i < n_streams; ++i) o_ws[i] = carve(wsp.total);
 
+  {
+    // keep the staging memory in the stream-ordered pool between calls: without a release
+    // threshold the pool hands it back to the driver at every synchronisation and the next call
+    // pays a fresh (hundreds of MB) allocation
+    static thread_local int pool_tuned_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool_tuned_dev != dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_tuned_dev = dev;
+    }
+  }
   char* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, off ? off : 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
