@@ -766,6 +766,12 @@ AdjPlan adj_plan(int B, int S, int H, int L, int P, bool has_nn, int T, int t_pe
   if (gx < 1) gx = 1;
   if (gx > blocks) gx = blocks;
   if (gx < 1) gx = 1;
+  // balance: every CTA walks the same number of trajectory blocks (fewer, equally loaded CTAs
+  // finish at the same time as more, unequally loaded ones, with less scratch)
+  {
+    const long rounds = (blocks + gx - 1) / gx;
+    gx = (blocks + rounds - 1) / rounds;
+  }
   p.grid_x = (int)gx;
   p.grid_y = S;
   const int Tsh = (!t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) ? T : 0;

@@ -554,31 +554,70 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         for (int i = 0; i < NS; ++i) y[i] = A.save_y[((size_t)sidx * NS + i) * n_units + unit];
       }
       const float hf = (float)h;
+      // Inputs of this step as one linear piece per channel (value = c_v1 + alpha * c_dv): valid when a
+      // step cannot cross an input kink (RK4, kink clipping, or no series input), see
+      // hode_rollout_tc.cu::lane_cache_inputs.  Otherwise every stage looks its interval up.
+      const bool cached = solver == 0 || A.kink_mode == HODE_KINK_CLIP || !any_series(in);
+      float c_t1 = 0.f, c_dt = 1.f, c_v1[3], c_dv[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        c_v1[ch] = in.mode[ch] == HODE_IN_CONST ? in.u[ch][0] : 0.f;
+        c_dv[ch] = 0.f;
+      }
       {
         int lo = 0, hi = T;
         const float t32 = (float)t;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (in.t_obs[mid] < t32) lo = mid + 1; else hi = mid; }
         in.cur = lo > 0 ? lo - 1 : 0;
+        if (cached && any_series(in) && T >= 2) {
+          int i0 = (lo < T && in.t_obs[lo] == t32) ? lo : lo - 1;
+          i0 = i0 < 0 ? 0 : (i0 > T - 2 ? T - 2 : i0);
+          c_t1 = in.t_obs[i0];
+          c_dt = in.t_obs[i0 + 1] - c_t1;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            if (in.mode[ch] != HODE_IN_SERIES) continue;
+            const float v1 = in.u[ch][i0], v2 = in.u[ch][i0 + 1];
+            c_v1[ch] = v1;
+            c_dv[ch] = v2 - v1;
+          }
+        }
       }
+      // stage derivatives / cotangents are indexed statically (predicated selects) so that they
+      // live in registers rather than in local memory
       float k[NSTAGE_MAX][NS], tv[NSTAGE_MAX], gdv[NSTAGE_MAX];
+#pragma unroll
+      for (int i = 0; i < NSTAGE_MAX; ++i) {
+        tv[i] = 0.f; gdv[i] = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) k[i][cc] = 0.f;
+      }
 #pragma unroll 1
       for (int i = 0; i < N; ++i) {
         float ys[NS];
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) {
           float a_ = 0.f;
-          for (int j = 0; j < i; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);
+#pragma unroll
+          for (int j = 0; j < NSTAGE_MAX - 1; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);   // zero for j >= i
           ys[cc] = fmaf(hf, a_, y[cc]);
         }
         const float ci = kC[solver][i];
         const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
         const float t32 = (float)te;
-        int idx = 0;
-        if (any_series(in)) idx = grid_index_from(in, t32, in.cur);
-        const float meal = input_channel(in, HODE_CH_MEAL, t32, idx);
-        const float tvns = input_channel(in, HODE_CH_TVNS, t32, idx);
-        const float gd = input_channel(in, HODE_CH_GD, t32, idx);
-        tv[i] = tvns; gdv[i] = gd;
+        float meal, tvns, gd;
+        if (cached) {
+          const float alpha = __fdiv_rn(t32 - c_t1, c_dt);
+          meal = __fadd_rn(c_v1[HODE_CH_MEAL], __fmul_rn(alpha, c_dv[HODE_CH_MEAL]));
+          tvns = __fadd_rn(c_v1[HODE_CH_TVNS], __fmul_rn(alpha, c_dv[HODE_CH_TVNS]));
+          gd = __fadd_rn(c_v1[HODE_CH_GD], __fmul_rn(alpha, c_dv[HODE_CH_GD]));
+        } else {
+          int idx = 0;
+          if (any_series(in)) idx = grid_index_from(in, t32, in.cur);
+          meal = input_channel(in, HODE_CH_MEAL, t32, idx);
+          tvns = input_channel(in, HODE_CH_TVNS, t32, idx);
+          gd = input_channel(in, HODE_CH_GD, t32, idx);
+        }
         float x[HODE_NN_IN], r[NS], d[NS];
         x[0] = t32;
 #pragma unroll
@@ -589,7 +628,13 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, NT);
         rhs_mech(th, ys, meal, gd, gd_present, d);
 #pragma unroll
-        for (int cc = 0; cc < NS; ++cc) k[i][cc] = __fadd_rn(d[cc], r[cc]);
+        for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
+          if (jj == i) {
+            tv[jj] = tvns; gdv[jj] = gd;
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) k[jj][cc] = __fadd_rn(d[cc], r[cc]);
+          }
+        }
       }
       // =========================== reverse sweep ===================================================
       begin_reverse();
@@ -606,7 +651,8 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         }
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) gy[cc] = act ? lam[cc] : 0.f;
-        for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int cc = 0; cc < NS; ++cc) gk[j][cc] = hf * kB[0][j] * gy[cc];
       } else {
@@ -626,6 +672,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
               const float xq = (float)((te - t) / h);
 #pragma unroll
               for (int cc = 0; cc < NS; ++cc) gy[cc] += g[cc];
+#pragma unroll
               for (int i = 0; i < 7; ++i) {
                 const float wgt = hf * xq * fmaf(xq, fmaf(xq, fmaf(xq, kP[i][3], kP[i][2]), kP[i][1]), kP[i][0]);
 #pragma unroll
@@ -638,38 +685,51 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) {
           gy[cc] += gnew[cc];
+#pragma unroll
           for (int j = 0; j < 6; ++j) gk[j][cc] = fmaf(hf * kB[1][j], gnew[cc], gk[j][cc]);
         }
       }
 #pragma unroll 1
       for (int i = N - 1; i >= 0; --i) {
-        float ys[NS], gys[NS];
+        float ys[NS], gys[NS], gki[NS];
+        float tvi = 0.f, gdi = 0.f;
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) {
           float a_ = 0.f;
-          for (int j = 0; j < i; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);
+#pragma unroll
+          for (int j = 0; j < NSTAGE_MAX - 1; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);
           ys[cc] = fmaf(hf, a_, y[cc]);
           gys[cc] = 0.f;
+          gki[cc] = 0.f;
+        }
+#pragma unroll
+        for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
+          if (jj == i) {
+            tvi = tv[jj]; gdi = gdv[jj];
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) gki[cc] = gk[jj][cc];
+          }
         }
         const float ci = kC[solver][i];
         const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
-        mech_vjp(th, ys, gdv[i], gd_present, gk[i], gys, gth);
+        mech_vjp(th, ys, gdi, gd_present, gki, gys, gth);
         float x[HODE_NN_IN], gx[HODE_NN_IN];
         x[0] = (float)te;
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) x[1 + cc] = ys[cc];
         x[7] = ys[3];
-        x[8] = tv[i];
+        x[8] = tvi;
         bc.stash = stash0 + (size_t)i * stage_stride;
         __syncwarp();
-        mlp_bwd_tile<true>(c, bc, x, gk[i], gx);
+        mlp_bwd_tile<true>(c, bc, x, gki, gx);
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];
         gys[3] += gx[7];
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) {
           gy[cc] += gys[cc];
-          for (int j = 0; j < i; ++j) gk[j][cc] = fmaf(hf * kA[solver][i][j], gys[cc], gk[j][cc]);
+#pragma unroll
+          for (int j = 0; j < NSTAGE_MAX - 1; ++j) gk[j][cc] = fmaf(hf * kA[solver][i][j], gys[cc], gk[j][cc]);
         }
       }
       if (act) {
@@ -811,6 +871,12 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   if (gx < 1) gx = 1;
   if (gx > blocks) gx = blocks;
   if (gx < 1) gx = 1;
+  // balance: every CTA walks the same number of trajectory blocks (fewer, equally loaded CTAs
+  // finish at the same time as more, unequally loaded ones, with less scratch)
+  {
+    const long rounds = (blocks + gx - 1) / gx;
+    gx = (blocks + rounds - 1) / rounds;
+  }
   p.grid_x = (int)gx;
   p.grid_y = S;
   p.fwd_floats = tc_image_floats(L);
