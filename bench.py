@@ -374,8 +374,13 @@ def run_ours(args):
                             "emulation issues 3 tensor passes per algorithmic pass"
                             if peaks else "fallback 1400/2 TFLOP/s")
                 bound = "tensor"
+            # dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu
+            # --set full capture of this exact configuration (profiles/r01_rollout_tc_tf32x3_ncu_full.txt)
+            traffic = 526.08e6 if (args.workload == "hybrid_fwd" and B == 262144 and args.precision == "tf32x3") else None
             roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": B * BYTES_PER_TRAJ(T, len(w["ins"]), False),
+                    "peak_source": peak_src,
                     "kernel": ("rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel<x3,dopri5>")
                               + (" + rollout_bwd_tc_kernel" if bwd else ""),
                     "tensor_passes_per_algorithmic_pass": 3 if args.precision == "tf32x3" else 1,

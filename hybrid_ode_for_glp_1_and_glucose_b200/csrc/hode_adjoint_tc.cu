@@ -4,22 +4,21 @@
 // Same mathematics as hode_adjoint_simt.cu (autograd through the unrolled RK steps with the step
 // sizes frozen); what changes is where the 13 248-MAC network products run:
 //   * one tile of 128 trajectories per CTA: 4 main warps (one trajectory per thread: integrator
-//     state, mechanistic VJP, stage recurrences) + 4 helper warps (the other half of every
-//     epilogue and the weight-gradient products);
+//     state, mechanistic VJP, stage recurrences) + 4 helper warps (the other half of every epilogue);
 //   * per accepted step, in reverse:  (1) the forward weight image is bulk-copied into shared
 //     memory and the N stages are recomputed with hode_tc_mlp.cuh's mlp_tile, each hidden
-//     activation going to a per-trajectory stash column in global memory (L2 resident);
-//     (2) the TRANSPOSED weight image replaces it (tcgen05 kind::tf32 takes K-major operands only —
-//     csrc/probe/adj_probe.cu — so W^T needs its own image) and every stage is pulled back:
-//     u_{l-1} = delta_l W_l is a [128 x 64] x [64 x 64] 3xTF32 MMA chain with delta in TMEM,
-//     delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue;
-//   * dW_l += delta_l^T a_{l-1} (contraction over the tile's 128 trajectories) is staged through
-//     shared memory and accumulated by the helper warps in REGISTERS for the whole kernel (every
-//     gradient element is owned by one helper thread; fixed summation order, no atomics), while
-//     the tensor pipe works on the next layer's product;
+//     activation going to a per-trajectory stash column in global memory;
+//     (2) every stage is pulled back: u_{l-1} = delta_l W_l is a [128 x 64] x [64 x 64] 3xTF32 MMA
+//     chain with delta in TMEM and W_l^T streamed layer by layer into a shared-memory slot by the
+//     TMA engine (tcgen05 kind::tf32 takes K-major operands only — csrc/probe/adj_probe.cu — so
+//     W^T needs its own image); delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue;
+//   * dW_l += delta_l^T [a_{l-1} | 1] (contraction over the tile's 128 trajectories) runs on the
+//     tensor cores too: SS-form MMAs over operands that every thread writes TRANSPOSED into the
+//     canonical K-major layout; the accumulators stay in TMEM for the whole kernel, so every
+//     gradient element is summed in one fixed order (no atomics, bit-reproducible);
 //   * per-CTA partial gradients -> workspace -> reduce_partials (hode_adjoint_simt.cu), in CTA order.
-// Restrictions: nn_hidden == 64, nn_layers <= 4 (the accumulators are compiled for them); other
-// shapes use the FP32 adjoint.
+// Restrictions: nn_hidden == 64, nn_layers <= 4 (the TMEM accumulator map is compiled for them);
+// other shapes use the FP32 adjoint.
 #include <math.h>
 
 #include "hode_common.cuh"
