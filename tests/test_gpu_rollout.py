@@ -391,3 +391,66 @@ def test_tc_layouts_failure_and_sweep(dev, oracle):
     tr1, st1, _, _ = gpu_rollout(dev, y0[:5], t[0, :1], None, oracle.THETA_DEFAULT, Ws[0],
                                  solver="dopri5", precision="tf32x3")
     assert tr1.shape == (5, 1, 6) and np.array_equal(tr1[:, 0], y0[:5]) and (st1 == 0).all()
+
+
+# ---------------------------------------------------------------------------- BASELINE configs 3-5
+def test_config5_clinical_shape_long_horizon_per_row_grids(dev, oracle):
+    """mimic_clinical-shaped cohort: T = 577 over 48 h, per-row jittered time
+    grids, irregular meal / tVNS events.  FP32 and tensor-core paths against the all-float64 truth on
+    a subsample, and against each other on the whole batch."""
+    from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import clinical_cohort
+    B = 1024
+    y0, t, ins = clinical_cohort(B, 577, seed=3)
+    # 48 h is long enough for the raw 4GI baselines (glucagon far below Glu_b) plus a random network
+    # to drive glucose into the pole of G / (K_m + G): start insulin / glucagon near their set points
+    # and keep the residual small, so that every trajectory stays physiological (checked on the oracle)
+    rng = np.random.default_rng(5)
+    y0[:, 1] = 60.0 * rng.normal(1, 0.1, B)
+    y0[:, 2] = 80.0 * rng.normal(1, 0.05, B)
+    W = random_mlp(seed=17, out_std=0.001)
+    theta = oracle.THETA_DEFAULT
+    a, st_a, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip")
+    b, st_b, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip", precision="tf32x3")
+    assert (st_a == 0).all() and (st_b == 0).all()
+    assert na.min() > 40 and (na + nr).max() < 20000
+    sub = slice(0, 24)
+    truth, st, _, _ = oracle.rollout(y0[sub], t[sub], {k: v[sub] for k, v in ins.items()}, theta, W,
+                                     rhs="f64", rtol=1e-10, atol=1e-12, kinks="clip", n_threads=8)
+    assert (st == 0).all()
+    assert rel_err(a[sub], truth) < 2e-4, rel_err_report(a[sub], truth)
+    assert rel_err(b[sub], truth) < 2e-4, rel_err_report(b[sub], truth)
+    assert rel_err(b, a.astype(np.float64)) < 2e-4
+    # fixed step on the same grids: 1e-5 against the float32-RHS oracle
+    c, st_c, _, _ = gpu_rollout(dev, y0[:64], t[:64], {k: v[:64] for k, v in ins.items()}, theta, W,
+                                solver="rk4", n_substeps=2, precision="tf32x3")
+    ref, _, _, _ = oracle.rollout(y0[:64], t[:64], {k: v[:64] for k, v in ins.items()}, theta, W,
+                                  solver="rk4", n_substeps=2, n_threads=8)
+    assert (st_c == 0).all() and rel_err(c, ref) < 1e-5, rel_err_report(c, ref)
+
+
+def test_config3_full_size_properties_hybrid(dev, oracle):
+    """BASELINE config 3 at bench size (262 144 trajectories, hybrid 64x4, dopri5 1e-6/1e-8, tensor
+    cores): size-independent properties + an oracle check on a strided subsample."""
+    B = 262144
+    y0, t, ins = cohort(B, seed=1000)
+    W = random_mlp(64, 4, seed=1234, out_std=0.05)
+    theta = oracle.THETA_DEFAULT
+    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", precision="tf32x3")
+    assert (st == 0).all()
+    assert np.array_equal(tr[:, 0], y0)                      # first observation is the initial state
+    assert np.isfinite(tr).all()
+    att = (na + nr).astype(np.int64)
+    assert 20 <= att.min() and att.max() < 400 and 30 < att.mean() < 60
+    # lane refill must not depend on which lane a trajectory lands in: a permuted batch gives the
+    # permuted result bit for bit
+    perm = np.random.default_rng(0).permutation(B)
+    tr2, st2, na2, _ = gpu_rollout(dev, y0[perm], t, {k: v[perm] for k, v in ins.items()}, theta, W,
+                                   solver="dopri5", precision="tf32x3")
+    assert np.array_equal(tr2, tr[perm]) and np.array_equal(na2, na[perm])
+    sub = np.arange(0, B, B // 48)
+    truth, s2, _, _ = oracle.rollout(y0[sub], t, {k: v[sub] for k, v in ins.items()}, theta, W, rhs="f64",
+                                     rtol=1e-10, atol=1e-12, kinks="clip", n_threads=8)
+    ref, _, _, _ = oracle.rollout(y0[sub], t, {k: v[sub] for k, v in ins.items()}, theta, W, rtol=1e-6,
+                                  atol=1e-8, kinks="clip", n_threads=8)
+    e_gpu, e_ref = rel_err(tr[sub], truth), rel_err(ref, truth)
+    assert e_gpu < max(2.0 * e_ref, 2e-5), (e_gpu, e_ref)

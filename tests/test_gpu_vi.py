@@ -107,3 +107,20 @@ def test_vi_call_sites(dev):
     out = vi.train_step(batch, n_samples=2)
     assert set(out) == {"loss", "elbo", "kl", "log_likelihood"}
     assert any(not torch.equal(before[k], v) for k, v in m.variational_params.state_dict().items())
+
+
+def test_config4_sixty_four_identical_sets(dev):
+    """configs/4gi_vi.yaml shape (S = 64): with 64 copies of one parameter set the fused sweep must
+    return that set's rollout as the mean, bit for bit, and a zero std (Welford with d = 0)."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T, S = 2048, 61, 64
+    y0, t, ins = cohort(B, T, seed=12)
+    theta, W = _sets(1, seed=3)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    tin = {k: tt(v) for k, v in ins.items()}
+    one, info = ops.rollout(tt(y0), tt(t), tin, tt(theta[0]), tt(W[0]), precision="tf32x3", device=dev)
+    mean, std, info2 = ops.vi_predictive(tt(y0), tt(t), tin, tt(np.repeat(theta, S, 0)), tt(np.repeat(W, S, 0)),
+                                         precision="tf32x3", device=dev)
+    assert bool((info2.status == 0).all())
+    assert torch.equal(mean, one) and float(std.abs().max()) == 0.0
+    assert int(info2.n_accept.sum()) == S * int(info.n_accept.sum())
