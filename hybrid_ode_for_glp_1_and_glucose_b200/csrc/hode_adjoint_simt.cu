@@ -769,8 +769,8 @@ AdjPlan adj_plan(int B, int S, int H, int L, int P, bool has_nn, int T, int t_pe
   // balance: every CTA walks the same number of trajectory blocks (fewer, equally loaded CTAs
   // finish at the same time as more, unequally loaded ones, with less scratch)
   {
-    const long rounds = (blocks + gx - 1) / gx;
-    gx = (blocks + rounds - 1) / rounds;
+    const long rounds = blocks > 0 ? (blocks + gx - 1) / gx : 1;
+    gx = blocks > 0 ? (blocks + rounds - 1) / rounds : 1;
   }
   p.grid_x = (int)gx;
   p.grid_y = S;

@@ -873,8 +873,8 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   // balance: every CTA walks the same number of trajectory blocks (fewer, equally loaded CTAs
   // finish at the same time as more, unequally loaded ones, with less scratch)
   {
-    const long rounds = (blocks + gx - 1) / gx;
-    gx = (blocks + rounds - 1) / rounds;
+    const long rounds = blocks > 0 ? (blocks + gx - 1) / gx : 1;
+    gx = blocks > 0 ? (blocks + rounds - 1) / rounds : 1;
   }
   p.grid_x = (int)gx;
   p.grid_y = S;

@@ -56,7 +56,7 @@ Workspace fwd_workspace(const hode_cfg* c) {
   if (uses_tensor_cores(c)) {
     // pre-split weight images (one per parameter set) + the per-set trajectory queue counters
     w.off_tc = off;
-    off = align_up(off + hode::tc_workspace_bytes(c->n_samples, c->nn_layers), 256);
+    off = align_up(off + hode::tc_workspace_bytes(c->n_samples, c->nn_layers, c->n_traj), 256);
   }
   w.total = off;
   return w;

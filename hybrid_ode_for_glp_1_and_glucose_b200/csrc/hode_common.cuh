@@ -42,6 +42,9 @@ struct RolloutArgs {
   // deviations over the S parameter sets, [B,T,6] each; traj is nullptr in this mode
   float* vi_mean;
   float* vi_m2;
+  // optional: bit i of kink_masks[b] set <=> grid point i is a kink of some series input of
+  // trajectory b (T <= 64), precomputed by kink_mask_kernel so that lane refill loads one word
+  const unsigned long long* kink_masks;
 };
 
 // ---- Dormand-Prince 5(4) coefficients (float) --------------------------------------------

@@ -16,7 +16,7 @@ cudaError_t launch_rhs(const RolloutArgs& A, int mlp_mode, const float* t, const
                        float* out, cudaStream_t stream);
 
 // 128-trajectory tiles, MLP on tcgen05 tensor cores (hode_rollout_tc.cu)
-size_t tc_workspace_bytes(int S, int L);
+size_t tc_workspace_bytes(int S, int L, int B);
 cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspace, cudaStream_t stream);
 
 // FP32 CUDA-core gradients (hode_adjoint_simt.cu)

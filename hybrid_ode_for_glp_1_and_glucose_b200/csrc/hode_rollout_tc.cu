@@ -365,6 +365,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   #pragma unroll
       for (int i = 0; i < NS; ++i) { ln.y[i] = 0.f; ln.cmp[i] = 0.f; }
       bool queue_dry = false;
+      int q_next = 0, q_end = 0;   // this warp's current chunk of the trajectory queue (warp-uniform)
       // stage vectors: k[0] = k1 (FSAL) ... k[6] = k7;  RK4 uses k[0..3]
       float k[7][NS];
   #pragma unroll
@@ -380,14 +381,26 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       for (;;) {
         // ---- refill idle lanes from the global queue (warp-aggregated) --------------------------
         {
-          const bool want = !ln.has && !queue_dry;
-          const unsigned m = __ballot_sync(0xffffffffu, want);
-          if (m) {
-            const int leader = __ffs(m) - 1;
-            int base = 0;
-            if (lane_id == leader) base = vi ? atomicAdd(&cta_queue, __popc(m)) : atomicAdd(&queue[s], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            const long b = b_lo + (long)base + __popc(m & ((1u << lane_id) - 1u));
+          const bool want_any = !ln.has && !queue_dry;
+          const unsigned m_any = __ballot_sync(0xffffffffu, want_any);
+          bool want = false;
+          long b = 0;
+          if (m_any) {
+            // the warp draws trajectories from the queue in chunks of 32 (one atomic per chunk instead
+            // of one per refill) and hands them to its idle lanes in lane order
+            if (q_next == q_end) {
+              int base = 0;
+              if (lane_id == 0) base = vi ? atomicAdd(&cta_queue, 32) : atomicAdd(&queue[s], 32);
+              q_next = __shfl_sync(0xffffffffu, base, 0);
+              q_end = q_next + 32;
+            }
+            const int rank = __popc(m_any & ((1u << lane_id) - 1u));
+            const int serve = min(q_end - q_next, __popc(m_any));
+            want = want_any && rank < serve;
+            b = b_lo + (long)q_next + rank;
+            q_next += serve;
+          }
+          {
             if (want) {
               if (b < b_hi) {
                 lane_bind(ln, A, t_shared, s, b);
@@ -401,7 +414,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
                   ln.ei = 1;
                   if (T < 2) lane_finish(ln, A, vi_n);
                 } else if (clip && T <= 64 && any_series(ln.in)) {
-                  kink_mask = build_kink_mask(ln.in);
+                  kink_mask = A.kink_masks ? A.kink_masks[ln.b] : build_kink_mask(ln.in);
                 }
               } else {
                 queue_dry = true;
@@ -411,7 +424,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         }
         // ---- does this tile still have work? ------------------------------------------------------
         {
-          const bool any = __any_sync(0xffffffffu, ln.has);
+          // a lane without a trajectory that has not yet seen the end of the queue may still be served
+        const bool any = __any_sync(0xffffffffu, ln.has || !queue_dry);
           if (lane_id == 0) tile_active[tile][wq] = any ? 1 : 0;
           tile_sync_all(c);
           const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
@@ -627,7 +641,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           }
           const float err = sqrtf(e2 * (1.0f / NS));
           if (err < 1.0f) {
-            float factor = (err == 0.f) ? 10.f : fminf(10.f, 0.9f * powf(err, -0.2f));
+            float factor = (err == 0.f) ? 10.f : fminf(10.f, 0.9f * __powf(err, -0.2f));
             if (prev_rejected) factor = fminf(1.f, factor);
             prev_rejected = false;
             ++ln.n_acc;
@@ -679,7 +693,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               ln.status = HODE_ST_STEP_TOO_SMALL;
               lane_finish(ln, A, vi_n);
             } else {
-              h_abs *= (double)fmaxf(0.2f, 0.9f * powf(err, -0.2f));
+              h_abs *= (double)fmaxf(0.2f, 0.9f * __powf(err, -0.2f));
               prev_rejected = true;
             }
           }
@@ -697,17 +711,50 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-size_t tc_workspace_bytes(int S, int L) {
-  return (size_t)S * tc_image_floats(L) * sizeof(float) + 256 + (size_t)S * sizeof(int);
+// One warp per trajectory: bit i of the mask <=> some series input is not flat across (i-1, i, i+1).
+__global__ void kink_mask_kernel(const RolloutArgs A, unsigned long long* __restrict__ masks) {
+  const long b = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= A.B) return;
+  unsigned d0 = 0u, d1 = 0u;   // lane i: v[i] != v[i+1], v[i+32] != v[i+33]
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    if (A.in_mode[ch] != HODE_IN_SERIES) continue;
+    const float* v = A.u[ch] + b * A.T;
+    const int i0 = lane, i1 = lane + 32;
+    if (i0 + 1 < A.T && v[i0] != v[i0 + 1]) d0 = 1u;
+    if (i1 + 1 < A.T && v[i1] != v[i1 + 1]) d1 = 1u;
+  }
+  const unsigned long long diff = (unsigned long long)__ballot_sync(0xffffffffu, d0) |
+                                  ((unsigned long long)__ballot_sync(0xffffffffu, d1) << 32);
+  unsigned long long m = diff | (diff << 1);
+  m &= ~1ull;
+  if (A.T >= 1) m &= ~(1ull << (A.T - 1));
+  if (lane == 0) masks[b] = m;
 }
 
-cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspace, cudaStream_t stream) {
+size_t tc_workspace_bytes(int S, int L, int B) {
+  return (size_t)S * tc_image_floats(L) * sizeof(float) + 256 + (((size_t)S * sizeof(int) + 255) & ~(size_t)255) +
+         (size_t)B * sizeof(unsigned long long);
+}
+
+cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* workspace, cudaStream_t stream) {
+  RolloutArgs A = A_in;
   const int img_floats = tc_image_floats(A.L);
   float* img = reinterpret_cast<float*>(workspace);
   int* queue = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
                                       (((size_t)A.S * img_floats * sizeof(float) + 255) / 256) * 256);
   cudaError_t e = cudaMemsetAsync(queue, 0, (size_t)A.S * sizeof(int), stream);
   if (e != cudaSuccess) return e;
+  if (A.solver == HODE_SOLVER_DOPRI5 && A.kink_mode == HODE_KINK_CLIP && A.T <= 64 &&
+      (A.in_mode[0] == HODE_IN_SERIES || A.in_mode[1] == HODE_IN_SERIES || A.in_mode[2] == HODE_IN_SERIES)) {
+    unsigned long long* masks = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<char*>(queue) + (((size_t)A.S * sizeof(int) + 255) & ~(size_t)255));
+    kink_mask_kernel<<<(unsigned)((A.B + 7) / 8), 256, 0, stream>>>(A, masks);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    A.kink_masks = masks;
+  }
   prep_tc_image_kernel<<<A.S, 256, 0, stream>>>(A.W, img, A.L, A.P, img_floats);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -738,3 +785,16 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A, int mlp_mode, void* workspac
 }
 
 }  // namespace hode
+
+#ifdef HODE_TIMELINE
+extern "C" int hode_debug_timeline(long long* out_host, int max_events) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, hode::g_tl_n, sizeof(int));
+  if (n > max_events) n = max_events;
+  cudaMemcpyFromSymbol(out_host, hode::g_tl, (size_t)n * 2 * sizeof(long long));
+  int zero = 0;
+  cudaMemcpyToSymbol(hode::g_tl_n, &zero, sizeof(int));
+  return n;
+}
+#endif

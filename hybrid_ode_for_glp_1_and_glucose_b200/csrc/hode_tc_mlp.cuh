@@ -7,6 +7,22 @@
 
 namespace hode {
 
+// Optional cycle-level timeline of one main thread (debug builds only: -DHODE_TIMELINE), read back
+// with the hode_debug_timeline export; compiles to nothing otherwise.
+#ifdef HODE_TIMELINE
+__device__ long long g_tl[2 * 16384];
+__device__ int g_tl_n;
+#define HODE_TL(id)                                                                         \
+  do {                                                                                      \
+    if (blockIdx.x == 3 && threadIdx.x == 0) {                                              \
+      const int n_ = g_tl_n;                                                                \
+      if (n_ < 16384) { g_tl[2 * n_] = (id); g_tl[2 * n_ + 1] = clock64(); g_tl_n = n_ + 1; } \
+    }                                                                                       \
+  } while (0)
+#else
+#define HODE_TL(id) do { } while (0)
+#endif
+
 namespace {
 constexpr int TILE = 128;
 constexpr int H = 64;
@@ -95,6 +111,7 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
   const float* img = c.img;
   const uint32_t img_s = tc::smem_u32(img);
   const uint32_t bias_s = img_s + (uint32_t)(2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024) * 4u;
+  HODE_TL(0);
   // ---- layer 0 operand: 9 features zero-padded to K = 16 ----------------------------------------
   {
     uint32_t hi[16], lo[16];
@@ -108,7 +125,9 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
   }
   tc::wait_st();
   tc::fence_before_sync();
+  HODE_TL(1);
   tile_sync(c);
+  HODE_TL(2);
   if (c.wq == 0) {
     if (tc::elect_one()) {
       tc::fence_after_sync();
@@ -117,6 +136,7 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
     }
     __syncwarp();
   }
+  HODE_TL(3);
   uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
   // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
 #pragma unroll 1
@@ -127,11 +147,13 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
+    HODE_TL(10 + 10 * l);
     // the main warp owns accumulator columns [0,32) of its 32 lanes, the helper warp of the same
     // lane quarter columns [32,64) (mlp_tile_helper): the epilogue latency per layer is halved
     uint32_t v0[32], lo[16];
     HODE_TMEM_LD_X32(t_d, v0);
     tc::wait_ld();
+    HODE_TL(11 + 10 * l);
     if (stash) {   // adjoint: keep a_l = relu(z_l) of this thread's trajectory, columns [0,32)
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -145,7 +167,9 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
     if (X3) HODE_TMEM_ST_X16(t_alo + 16, lo);
     tc::wait_st();
     tc::fence_before_sync();
+    HODE_TL(12 + 10 * l);
     tile_sync_all(c);
+    HODE_TL(13 + 10 * l);
     if (c.wq == 0) {
       if (tc::elect_one()) {
         tc::fence_after_sync();
@@ -156,12 +180,14 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
       }
       __syncwarp();
     }
+    HODE_TL(14 + 10 * l);
     w_off += 2 * 4096;
   }
   // ---- output layer epilogue: 6 of the 16 accumulator columns ------------------------------------
   tc::mbar_wait(c.mma_bar, c.parity);
   c.parity ^= 1u;
   tc::fence_after_sync();
+  HODE_TL(90);
   {
     uint32_t v[8];
     HODE_TMEM_LD_X8(t_d, v);
@@ -169,6 +195,7 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
 #pragma unroll
     for (int i = 0; i < NS; ++i) r[i] = __uint_as_float(v[i]);
   }
+  HODE_TL(91);
   // The next call overwrites A (tcgen05.st: every MMA has completed) and its layer-0 MMAs write
   // D only after a tile barrier that every thread reaches after its wait::ld above.
 }

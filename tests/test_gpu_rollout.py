@@ -419,7 +419,8 @@ def test_config5_clinical_shape_long_horizon_per_row_grids(dev, oracle):
     assert (st == 0).all()
     assert rel_err(a[sub], truth) < 2e-4, rel_err_report(a[sub], truth)
     assert rel_err(b[sub], truth) < 2e-4, rel_err_report(b[sub], truth)
-    assert rel_err(b, a.astype(np.float64)) < 2e-4
+    # two independent adaptive step sequences over 48 h: each within 2e-4 of the truth
+    assert rel_err(b, a.astype(np.float64)) < 4e-4
     # fixed step on the same grids: 1e-5 against the float32-RHS oracle
     c, st_c, _, _ = gpu_rollout(dev, y0[:64], t[:64], {k: v[:64] for k, v in ins.items()}, theta, W,
                                 solver="rk4", n_substeps=2, precision="tf32x3")
