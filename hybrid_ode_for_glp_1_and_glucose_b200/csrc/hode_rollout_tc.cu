@@ -97,7 +97,8 @@ struct Lane {
   // clipping, or no series inputs): the loads happen once per accepted step instead of once per
   // RK stage, which takes the L2 latency of the input rows off the stage critical path.
   bool cached;
-  float c_t1, c_dt, c_v1[3], c_dv[3];
+  float c_t1, c_inv_dt, c_v1[3], c_dv[3];
+  bool c_stale;         // the step start has crossed a kink since the cache was loaded
 };
 
 // (i0, i0+1): the grid interval the step starts in.  Flat stretches that a step may cross have
@@ -105,7 +106,7 @@ struct Lane {
 __device__ __forceinline__ void lane_cache_inputs(Lane& ln, int i0) {
   const float t1 = ln.in.t_obs[i0], t2 = ln.in.t_obs[i0 + 1];
   ln.c_t1 = t1;
-  ln.c_dt = t2 - t1;
+  ln.c_inv_dt = 1.0f / (t2 - t1);
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     if (ln.in.mode[ch] != HODE_IN_SERIES) continue;
@@ -122,6 +123,28 @@ __device__ __forceinline__ float rms6v(const float* v) {
   return sqrtf(s * (1.0f / NS));
 }
 
+// f_physio for the tensor-core path: same formulas as rhs_mech (hode_common.cuh), but with
+// reciprocal-based division and free FMA contraction — this path is accurate to float32 round-off,
+// not bit-identical to the CPU evaluation (the 3xTF32 network products are not either), and the
+// three IEEE divisions of rhs_mech sit on the critical path of every RK stage.
+__device__ __forceinline__ void rhs_mech_fast(const Theta& p, const float* y, float meal, float GD,
+                                              bool gd_present, float* d) {
+  const float G = y[0], I = y[1], Glu = y[2], GLP1 = y[3], FFA = y[5];
+  const float Pi = fmaf(p.rho, GLP1, 1.0f);
+  d[1] = Pi * p.a_GI * (G - p.G_b) - p.k_I * (I - p.I_b);
+  const float glp1_effect = p.E_max * __fdividef(GLP1, p.EC_50 + GLP1);
+  d[2] = -glp1_effect * (Glu - p.Glu_b);
+  d[3] = p.V_max * __fdividef(G, p.K_m + G) - p.k_L * GLP1;
+  float k_GE = p.kge0;
+  if (gd_present) {
+    const float gdg = __powf(GD, p.g);
+    k_GE = p.k_GE0 * (1.0f - __fdividef(gdg, p.igd_pow + gdg));
+  }
+  d[5] = FFA * (-p.p_7 - p.p_8 * I + p.p_9 * G);
+  d[0] = meal - 0.01f * (I - p.I_b) + 0.005f * (Glu - p.Glu_b) - k_GE * G;
+  d[4] = 0.0f;
+}
+
 // One evaluation of f_physio + g_NN for this lane (tile-collective).
 template <bool X3>
 __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln, double te,
@@ -131,10 +154,10 @@ __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln,
   if (ln.has) {
     if (ln.cached) {
       // same arithmetic as input_channel(): v1 + ((t - t1) / (t2 - t1)) * (v2 - v1)
-      const float alpha = __fdiv_rn(t32 - ln.c_t1, ln.c_dt);
-      meal = __fadd_rn(ln.c_v1[HODE_CH_MEAL], __fmul_rn(alpha, ln.c_dv[HODE_CH_MEAL]));
-      tvns = __fadd_rn(ln.c_v1[HODE_CH_TVNS], __fmul_rn(alpha, ln.c_dv[HODE_CH_TVNS]));
-      gd = __fadd_rn(ln.c_v1[HODE_CH_GD], __fmul_rn(alpha, ln.c_dv[HODE_CH_GD]));
+      const float alpha = (t32 - ln.c_t1) * ln.c_inv_dt;
+      meal = fmaf(alpha, ln.c_dv[HODE_CH_MEAL], ln.c_v1[HODE_CH_MEAL]);
+      tvns = fmaf(alpha, ln.c_dv[HODE_CH_TVNS], ln.c_v1[HODE_CH_TVNS]);
+      gd = fmaf(alpha, ln.c_dv[HODE_CH_GD], ln.c_v1[HODE_CH_GD]);
     } else {
       int idx = 0;
       if (any_series(ln.in)) idx = grid_index_from(ln.in, t32, ln.in.cur);
@@ -151,7 +174,7 @@ __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln,
   x[8] = tvns;
   __syncwarp();
   mlp_tile<X3>(c, x, r);
-  rhs_mech(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d);
+  rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d);
 #pragma unroll
   for (int i = 0; i < NS; ++i) d[i] = __fadd_rn(d[i], r[i]);
 }
@@ -174,7 +197,8 @@ __device__ __forceinline__ void lane_bind(Lane& ln, const RolloutArgs& A, const 
   ln.out = A.traj ? A.traj + (size_t)unit * A.T * NS : nullptr;
   ln.cached = A.solver == HODE_SOLVER_RK4 || A.kink_mode == HODE_KINK_CLIP || !any_series(ln.in);
   ln.c_t1 = 0.f;
-  ln.c_dt = 1.f;
+  ln.c_inv_dt = 1.f;
+  ln.c_stale = true;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     ln.c_v1[ch] = ln.in.mode[ch] == HODE_IN_CONST ? ln.in.u[ch][0] : 0.f;
@@ -356,7 +380,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       ln.ei = 0;
       ln.status = 0; ln.n_acc = 0; ln.n_rej = 0; ln.n_saved = 0;
       ln.t = 0.0;
-      ln.cached = true; ln.c_t1 = 0.f; ln.c_dt = 1.f;
+      ln.cached = true; ln.c_t1 = 0.f; ln.c_inv_dt = 1.f; ln.c_stale = true;
   #pragma unroll
       for (int ch = 0; ch < 3; ++ch) { ln.c_v1[ch] = 0.f; ln.c_dv[ch] = 0.f; }
       ln.in.T = T; ln.in.cur = 0; ln.in.t_obs = A.t_obs;
@@ -379,6 +403,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       int rk_n = 0, rk_ss = 0;
 
       for (;;) {
+        HODE_TL(100);
         // ---- refill idle lanes from the global queue (warp-aggregated) --------------------------
         {
           const bool want_any = !ln.has && !queue_dry;
@@ -422,6 +447,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             }
           }
         }
+        HODE_TL(101);
         // ---- does this tile still have work? ------------------------------------------------------
         {
           // a lane without a trajectory that has not yet seen the end of the queue may still be served
@@ -434,6 +460,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           if (!go) break;
         }
 
+        HODE_TL(102);
         // ---- round set-up ---------------------------------------------------------------------------
         const bool init = (SOLVER == HODE_SOLVER_DOPRI5) && ln.has && need_init;
         bool run = ln.has && !init;   // lane performs a real step / attempt this round
@@ -474,10 +501,13 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             {
               const int j = grid_index_from(ln.in, (float)t, ln.in.cur);   // grid points < float(t)
               ln.in.cur = j > 0 ? j - 1 : 0;
-              if (ln.cached && any_series(ln.in)) {
+              // Between two kinks the inputs are one linear piece (flat stretches have c_dv == 0), so the
+              // cached piece stays valid until a step has ended on a kink: reload only then.
+              if (ln.cached && any_series(ln.in) && (ln.c_stale || !clip)) {
                 int i0 = (j < T && ln.in.t_obs[j] == (float)t) ? j : j - 1;
                 i0 = i0 < 0 ? 0 : (i0 > T - 2 ? T - 2 : i0);
                 lane_cache_inputs(ln, i0);
+                ln.c_stale = false;
               }
             }
             need_stop = false;
@@ -496,6 +526,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           }
         }
 
+        HODE_TL(103);
         // ---- the evaluations of this round: ONE call site of the tile MLP ------------------------
   #pragma unroll 1
         for (int slot = 0; slot < NSLOT; ++slot) {
@@ -602,6 +633,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           }
         }
 
+        HODE_TL(104);
         // ---- close the round ----------------------------------------------------------------------------
         if (SOLVER == HODE_SOLVER_RK4) {
           if (run) {
@@ -662,7 +694,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   #pragma unroll
                     for (int i = 0; i < NS; ++i) yo[i] = ynew[i];
                   } else {
-                    const float xq = (float)((te - t) / h);
+                    const float xq = __fdividef((float)(te - t), hf);
   #pragma unroll
                     for (int i = 0; i < NS; ++i) {
                       const float poly = xq * fmaf(xq, fmaf(xq, fmaf(xq, Q[i][3], Q[i][2]), Q[i][1]), Q[i][0]);
@@ -683,6 +715,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               ln.t = t_new;
               h_abs *= (double)factor;
               need_stop = true;
+              if (t_new - t_stop >= 0) ln.c_stale = true;   // the next step starts on a kink
               if (t_new - t_bound >= 0) lane_finish(ln, A, vi_n);
             } else {
               lane_finish(ln, A, vi_n);
