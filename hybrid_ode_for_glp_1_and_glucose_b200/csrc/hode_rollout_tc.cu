@@ -667,7 +667,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           for (int i = 0; i < NS; ++i) {
             const float scale = fmaf(fmaxf(fabsf(ln.y[i]), fabsf(ynew[i])), rtol, atol);
             const float ee = hf * fmaf(dp::e7, k[6][i], fmaf(dp::e6, k[5][i], fmaf(dp::e5, k[4][i], fmaf(dp::e4, k[3][i], fmaf(dp::e3, k[2][i], dp::e1 * k[0][i])))));
-            const float q = ee / scale;
+            const float q = __fdividef(ee, scale);
             e2 = fmaf(q, q, e2);
             finite = finite && isfinite(ynew[i]);
           }
