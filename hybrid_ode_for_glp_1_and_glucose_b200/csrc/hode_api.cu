@@ -318,6 +318,137 @@ int hode_rhs(const hode_cfg* cfg, const float* t, const float* state, const floa
   return 0;
 }
 
+namespace {
+
+// Keep the host entries' staging memory in the stream-ordered pool between calls: without a release
+// threshold the pool hands it back to the driver at every synchronisation and the next call pays a
+// fresh (hundreds of MB) allocation.
+void tune_default_pool() {
+  static thread_local int pool_tuned_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (pool_tuned_dev != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_tuned_dev = dev;
+  }
+}
+
+// Host entry, tensor-core path, one parameter set: ONE persistent launch over all trajectories (the
+// lane-refill queue keeps every SM busy to the end; chunked launches lose ~25 % to their tails),
+// with the device->host copy of the results overlapped block by block: the kernel counts finished
+// trajectories per block of STREAM_BLOCK and raises a flag in host-mapped memory when a block is
+// complete; this thread polls the flags and queues that block's copy on a second stream.
+constexpr int STREAM_BLOCK = 8192;
+constexpr int STREAM_MAX_BLOCKS = 1024;
+
+int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const float* t_obs_h,
+                              const float* const uh[3], const float* theta_h, const float* W_h,
+                              float* traj_h, int32_t* status_h, int32_t* counters_h, cudaStream_t st) {
+  const size_t B = cfg->n_traj, T = cfg->n_obs;
+  const size_t P = hode_mlp_param_count(cfg->nn_hidden, cfg->nn_layers);
+  const int n_blk = (int)((B + STREAM_BLOCK - 1) / STREAM_BLOCK);
+  size_t ub[3];
+  for (int ch = 0; ch < 3; ++ch)
+    ub[ch] = cfg->in_mode[ch] == HODE_IN_SERIES ? B * T * 4 : cfg->in_mode[ch] == HODE_IN_CONST ? B * 4 : 0;
+  const Workspace wsp = fwd_workspace(cfg);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_y0 = carve(B * 24), o_t = carve((cfg->t_per_traj ? B * T : T) * 4);
+  size_t o_u[3];
+  for (int ch = 0; ch < 3; ++ch) o_u[ch] = carve(ub[ch]);
+  const size_t o_th = carve(17 * 4), o_W = carve(P * 4), o_traj = carve(B * T * 24), o_st = carve(B * 4),
+               o_cn = carve(2 * B * 4), o_done = carve((size_t)n_blk * 4), o_ws = carve(wsp.total);
+
+  static thread_local int* flags_h = nullptr;     // host-mapped completion flags (allocated once)
+  static thread_local cudaStream_t copy_stream = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (!flags_h) {
+    e = cudaHostAlloc((void**)&flags_h, STREAM_MAX_BLOCKS * sizeof(int), cudaHostAllocMapped);
+    if (e != cudaSuccess) { flags_h = nullptr; return cuda_fail(e, "cudaHostAlloc(flags)"); }
+  }
+  if (!copy_stream) {
+    e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { copy_stream = nullptr; return cuda_fail(e, "cudaStreamCreate"); }
+  }
+  int* flags_d = nullptr;
+  e = cudaHostGetDevicePointer((void**)&flags_d, flags_h, 0);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+  for (int i = 0; i < n_blk; ++i) flags_h[i] = 0;
+
+  char* d = nullptr;
+  e = cudaMallocAsync((void**)&d, off, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+  int lib_rc = 0;
+  int copied = 0;
+#define CK(call) if ((e = (call)) != cudaSuccess) goto done
+  CK(cudaMemcpyAsync(d + o_y0, y0_h, B * 24, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_t, t_obs_h, (cfg->t_per_traj ? B * T : T) * 4, cudaMemcpyHostToDevice, st));
+  for (int ch = 0; ch < 3; ++ch)
+    if (ub[ch]) CK(cudaMemcpyAsync(d + o_u[ch], uh[ch], ub[ch], cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_th, theta_h, 17 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_W, W_h, P * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d + o_done, 0, (size_t)n_blk * 4, st));
+  {
+    hode::RolloutArgs A = make_args(cfg, (float*)(d + o_y0), (float*)(d + o_t),
+                                    ub[0] ? (float*)(d + o_u[0]) : nullptr, ub[1] ? (float*)(d + o_u[1]) : nullptr,
+                                    ub[2] ? (float*)(d + o_u[2]) : nullptr, (float*)(d + o_th), (float*)(d + o_W));
+    A.traj = (float*)(d + o_traj);
+    A.status = (int32_t*)(d + o_st);
+    A.counters = (int32_t*)(d + o_cn);
+    A.done_count = (int*)(d + o_done);
+    A.done_flag = flags_d;
+    A.done_block = STREAM_BLOCK;
+    CK(hode::launch_rollout_tc(A, cfg->mlp, d + o_ws + wsp.off_tc, st));
+  }
+  // copy every block back as soon as the kernel reports it complete
+  {
+    volatile int* vf = flags_h;
+    cudaEvent_t ev_kernel;
+    CK(cudaEventCreateWithFlags(&ev_kernel, cudaEventDisableTiming));
+    e = cudaEventRecord(ev_kernel, st);
+    while (e == cudaSuccess && copied < n_blk) {
+      if (vf[copied]) {
+        const size_t lo = (size_t)copied * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
+        e = cudaMemcpyAsync(traj_h + lo * T * 6, d + o_traj + lo * T * 24, (hi - lo) * T * 24, cudaMemcpyDeviceToHost,
+                            copy_stream);
+        ++copied;
+      } else if (cudaEventQuery(ev_kernel) != cudaErrorNotReady) {
+        // the kernel is over (normally every flag is up by now; on a launch failure none is):
+        // fall through to the plain copies below
+        break;
+      }
+    }
+    cudaEventDestroy(ev_kernel);
+    if (e != cudaSuccess) goto done;
+  }
+  CK(cudaStreamSynchronize(st));
+  for (; copied < n_blk; ++copied) {
+    const size_t lo = (size_t)copied * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
+    CK(cudaMemcpyAsync(traj_h + lo * T * 6, d + o_traj + lo * T * 24, (hi - lo) * T * 24, cudaMemcpyDeviceToHost,
+                       copy_stream));
+  }
+  if (status_h) CK(cudaMemcpyAsync(status_h, d + o_st, B * 4, cudaMemcpyDeviceToHost, st));
+  if (counters_h) CK(cudaMemcpyAsync(counters_h, d + o_cn, 2 * B * 4, cudaMemcpyDeviceToHost, st));
+#undef CK
+done:
+  {
+    cudaError_t e2 = cudaStreamSynchronize(copy_stream);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
+  }
+  cudaFreeAsync(d, st);
+  cudaStreamSynchronize(st);
+  if (lib_rc) return lib_rc;
+  if (e != cudaSuccess) return cuda_fail(e, "hode_rollout_fwd_host (streamed)");
+  return 0;
+}
+
+}  // namespace
+
 int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t_obs_h,
                           const float* u_meal_h, const float* u_tvns_h, const float* u_gd_h,
                           const float* theta_h, const float* W_h, float* traj_h,
@@ -337,6 +468,12 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   size_t urow[3];  // bytes per trajectory of each input channel
   for (int ch = 0; ch < 3; ++ch)
     urow[ch] = cfg->in_mode[ch] == HODE_IN_SERIES ? T * 4 : cfg->in_mode[ch] == HODE_IN_CONST ? 4 : 0;
+
+  if (S == 1 && uses_tensor_cores(cfg) && B >= 2 * (size_t)STREAM_BLOCK &&
+      B <= (size_t)STREAM_BLOCK * STREAM_MAX_BLOCKS) {
+    tune_default_pool();
+    return rollout_fwd_host_streamed(cfg, y0_h, t_obs_h, uh, theta_h, W_h, traj_h, status_h, counters_h, st);
+  }
 
   // Trajectory chunks are pipelined over a few streams: while chunk c integrates, chunk c+1 is
   // on its way in and chunk c-1 on its way out (the two copy engines and the SMs overlap, and
@@ -366,22 +503,7 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   size_t o_ws[MAX_STREAMS];
   for (int i = 0; i < n_streams; ++i) o_ws[i] = carve(wsp.total);
 
-  {
-    // keep the staging memory in the stream-ordered pool between calls: without a release
-    // threshold the pool hands it back to the driver at every synchronisation and the next call
-    // pays a fresh (hundreds of MB) allocation
-    static thread_local int pool_tuned_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (pool_tuned_dev != dev) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-      pool_tuned_dev = dev;
-    }
-  }
+  tune_default_pool();
   char* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, off ? off : 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");

@@ -45,6 +45,13 @@ struct RolloutArgs {
   // optional: bit i of kink_masks[b] set <=> grid point i is a kink of some series input of
   // trajectory b (T <= 64), precomputed by kink_mask_kernel so that lane refill loads one word
   const unsigned long long* kink_masks;
+  // optional completion tracking for the streaming host entry (S == 1): done_count[b / done_block]
+  // counts finished trajectories of a block (device memory); the lane that completes a block raises
+  // done_flag[block] (host-mapped pinned memory) so that the host can start copying that block's
+  // outputs back while the kernel is still integrating the rest
+  int* done_count;
+  volatile int* done_flag;
+  int done_block;
 };
 
 // ---- Dormand-Prince 5(4) coefficients (float) --------------------------------------------

@@ -223,6 +223,16 @@ __device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A, int 
     A.counters[n_units + ln.unit] = ln.n_rej;
   }
   if (A.save_n) A.save_n[ln.unit] = ln.status == HODE_ST_OK ? ln.n_saved : -1 - ln.n_saved;  // < 0: no gradient
+  if (A.done_count) {
+    __threadfence();   // this trajectory's outputs are visible device-wide before it is counted
+    const int blk = (int)(ln.b / A.done_block);
+    const long first = (long)blk * A.done_block;
+    const int size = (int)((first + A.done_block <= (long)A.B) ? A.done_block : (long)A.B - first);
+    if (atomicAdd(&A.done_count[blk], 1) + 1 == size) {
+      __threadfence_system();
+      A.done_flag[blk] = 1;
+    }
+  }
   ln.has = false;
   ln.unit = -1;
 }

@@ -225,11 +225,12 @@ def test_host_entry_matches_device_entry(dev, oracle):
     assert np.array_equal(counters[0], na) and np.array_equal(counters[1], nr)
 
 
-@pytest.mark.parametrize("per_row_t", [False, True])
-def test_host_entry_chunked_pipeline(dev, oracle, per_row_t):
-    """Above 2 x 49 152 trajectories the host entry pipelines trajectory chunks over several
-    streams; results must equal the one-launch device path bit for bit (ragged last chunk,
-    constant + series inputs, shared and per-row grids, hybrid net on the tensor-core path)."""
+@pytest.mark.parametrize("per_row_t,precision", [(False, "tf32x3"), (True, "tf32x3"), (False, "fp32")])
+def test_host_entry_chunked_pipeline(dev, oracle, per_row_t, precision):
+    """Large batches through the host entry: the tensor-core path runs ONE launch and streams result
+    blocks back as the kernel reports them complete; the FP32 path pipelines trajectory chunks over
+    several streams.  Either way the results must equal the device-pointer path bit for bit (ragged
+    last block / chunk, constant + series inputs, shared and per-row grids)."""
     from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, ops
     B, T = 3 * 49152 + 1234, 7
     y0, t, ins = cohort(B, T, seed=15, horizon=0.5)
@@ -239,11 +240,11 @@ def test_host_entry_chunked_pipeline(dev, oracle, per_row_t):
     W = random_mlp(seed=16)
     theta = oracle.THETA_DEFAULT
     ref, st_ref, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="rk4", n_substeps=1,
-                                      precision="tf32x3")
+                                      precision=precision)
     cfg, _ = ops.prepare(torch.from_numpy(y0), torch.from_numpy(t),
                          {k: torch.from_numpy(v) for k, v in ins.items()},
                          torch.from_numpy(theta), torch.from_numpy(W), 64, 4, torch.device("cpu"))
-    cfg.solver, cfg.n_substeps, cfg.mlp = _lib.SOLVER_RK4, 1, _lib.MLP_TF32X3
+    cfg.solver, cfg.n_substeps, cfg.mlp = _lib.SOLVER_RK4, 1, ops.PRECISIONS[precision]
     traj = np.empty((B, T, 6), np.float32)
     status = np.full(B, -1, np.int32)
     counters = np.full((2, B), -1, np.int32)
