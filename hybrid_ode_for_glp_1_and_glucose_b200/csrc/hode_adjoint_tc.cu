@@ -126,10 +126,10 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
 // D[tmem] (+)= A^T B over the 128 trajectories: 3 passes x 16 k-steps of 8 trajectories.
 // (a_hi, a_lo): staging arrays of the operand that becomes the ROWS of D (chunk stride cha floats),
 // (b_hi, b_lo): of the operand that becomes the COLUMNS (chunk stride chb).  `init` = overwrite D.
-template <int N>
+template <int M, int N>
 __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_hi, uint32_t a_lo, int cha, uint32_t b_hi, uint32_t b_lo,
                                          int chb, uint32_t init) {
-  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
+  constexpr uint32_t idesc = tc::make_idesc_tf32(M, N);
   const uint64_t da_hi = tc::make_desc(a_hi, (uint32_t)cha * 4u, 128u), da_lo = tc::make_desc(a_lo, (uint32_t)cha * 4u, 128u);
   const uint64_t db_hi = tc::make_desc(b_hi, (uint32_t)chb * 4u, 128u), db_lo = tc::make_desc(b_lo, (uint32_t)chb * 4u, 128u);
   // one k-step = 8 trajectories = 2 chunks: the start-address field (16-byte units) advances by 2*CH*4/16
@@ -187,6 +187,7 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   // ---- prologue: delta_L = g; operands of dW_out; phase L --------------------------------------------
   // the staging arrays are free once the previous stage's weight-gradient MMAs have completed
   tc::mbar_wait(b.gemm_bar, b.gemm_parity ^ 1u);   // (first call: the phase "before 0" counts as complete)
+  HODE_TL(220);
   fetch_w(0, 2048);
   if (MAIN) {
     float d[16];
@@ -209,7 +210,9 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   tc::wait_st();
   tc::fence_proxy_async();
   tc::fence_before_sync();
+  HODE_TL(221);
   tile_sync_all(c);
+  HODE_TL(222);
   if (issuer_warp) {
     tc::mbar_wait(b.wload_bar, b.wload_parity);
     if (tc::elect_one()) {
@@ -217,13 +220,14 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       issue_nobias<H, 2>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
       tc::mma_commit(c.mma_bar);
       // dW_out^T [in k][out n] = a_{L-1}^T delta_L  (rows = the 80 staged input features: row 64 = db_out)
-      issue_dw<16>(c.tmem + DW_O, sa_hi, sa_lo, CH_A, sd_hi, sd_lo, CH_D, b.first);
+      issue_dw<128, 16>(c.tmem + DW_O, sa_hi, sa_lo, CH_A, sd_hi, sd_lo, CH_D, b.first);
       tc::mma_commit(b.gemm_bar);
     }
     __syncwarp();
   }
   b.wload_parity ^= 1u;
   b.gemm_parity ^= 1u;
+  HODE_TL(223);
 
   // ---- phases p = L .. 1 ---------------------------------------------------------------------------------
 #pragma unroll
@@ -232,6 +236,7 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
+    HODE_TL(230 + 10 * p);
     // the weight slot is free (its reader was the MMA chain just waited for): prefetch the next block
     if (p >= 2) fetch_w(2048 + (L - p) * 8192, 8192);
     else fetch_w(2048 + (L - 1) * 8192, 2048);
@@ -253,8 +258,10 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       HODE_TMEM_ST_X16(t_ahi + half + 16, hi);
       HODE_TMEM_ST_X16(t_alo + half + 16, lo);
     }
+    HODE_TL(231 + 10 * p);
     // staging may be rewritten once the previous phase's weight-gradient MMAs are done
     tc::mbar_wait(b.gemm_bar, b.gemm_parity ^ 1u);
+    HODE_TL(232 + 10 * p);
 #pragma unroll
     for (int j4 = 0; j4 < 32; j4 += 4) stage4(b.sd_hi, b.sd_lo, CH_D, b.row, half + j4, d[j4], d[j4 + 1], d[j4 + 2], d[j4 + 3]);
     if (p >= 2) {   // inputs of layer p-1 are a_{p-2}
@@ -272,7 +279,9 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     tc::wait_st();
     tc::fence_proxy_async();
     tc::fence_before_sync();
+    HODE_TL(233 + 10 * p);
     tile_sync_all(c);
+    HODE_TL(234 + 10 * p);
     if (issuer_warp) {
       tc::mbar_wait(b.wload_bar, b.wload_parity);
       if (tc::elect_one()) {
@@ -280,11 +289,11 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
         if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1};  dW_{p-1} += delta_{p-1}^T [a_{p-2} | 1]
           issue_nobias<H, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 4096u * 4u);
           tc::mma_commit(c.mma_bar);
-          issue_dw<80>(c.tmem + DW_H0 + 80u * (uint32_t)(p - 2), sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
+          issue_dw<64, 80>(c.tmem + DW_H0 + 80u * (uint32_t)(p - 2), sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
         } else {        // g_x = delta_0 W_0;  dW_0 += delta_0^T [x | 1]
           issue_nobias<16, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
           tc::mma_commit(c.mma_bar);
-          issue_dw<16>(c.tmem + DW_0, sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
+          issue_dw<64, 16>(c.tmem + DW_0, sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
         }
         tc::mma_commit(b.gemm_bar);
       }
@@ -292,6 +301,7 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     }
     b.wload_parity ^= 1u;
     b.gemm_parity ^= 1u;
+    HODE_TL(235 + 10 * p);
   }
   // ---- final phase: g_x -------------------------------------------------------------------------
   tc::mbar_wait(c.mma_bar, c.parity);
@@ -521,7 +531,9 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
 
     for (int it = 0; it < nmax; ++it) {
       // =========================== forward recomputation =========================================
+      HODE_TL(200);
       load_image(fwd_src, G.fwd_floats);
+      HODE_TL(201);
       if (helper) {
 #pragma unroll 1
         for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, NT);
@@ -636,7 +648,9 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         }
       }
       // =========================== reverse sweep ===================================================
+      HODE_TL(202);
       begin_reverse();
+      HODE_TL(203);
       float gy[NS], gk[NSTAGE_MAX][NS];
 #pragma unroll
       for (int i = 0; i < NSTAGE_MAX; ++i)
@@ -720,7 +734,9 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
         x[8] = tvi;
         bc.stash = stash0 + (size_t)i * stage_stride;
         __syncwarp();
+        HODE_TL(210);
         mlp_bwd_tile<true>(c, bc, x, gki, gx);
+        HODE_TL(211);
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];
         gys[3] += gx[7];
@@ -735,6 +751,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) lam[cc] = gy[cc];
       }
+      HODE_TL(204);
     }
     if (!helper) {
       if (ok) {
@@ -767,15 +784,20 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   float* out = G.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(A.P + HODE_N_THETA);
   const bool have = bc.first == 0u;   // false: this CTA processed no step, the accumulators were never written
   const int offo = 640 + (L - 1) * 4160;
-  if (!helper && wq < 2) {
-    const int j = row;   // TMEM lane = output row of the accumulators (0..63)
+  // M = 64 accumulators (layer 0 and the hidden layers): row j of D lives in TMEM lane 32 (j / 16) + j % 16
+  // (csrc/probe/adj_probe.cu), i.e. in the first 16 lanes of every main warp.  The loads are warp-wide.
+  if (!helper) {
+    const int j = 16 * wq + lane_id;
+    const bool owner = lane_id < 16;
     uint32_t v[16];
     // layer 0: D[j][k] (k < 9), column 15 = db_0[j]
     HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_0, v);
     tc::wait_ld();
+    if (owner) {
 #pragma unroll
-    for (int k = 0; k < HODE_NN_IN; ++k) out[j * HODE_NN_IN + k] = have ? __uint_as_float(v[k]) : 0.f;
-    out[576 + j] = have ? __uint_as_float(v[15]) : 0.f;
+      for (int k = 0; k < HODE_NN_IN; ++k) out[j * HODE_NN_IN + k] = have ? __uint_as_float(v[k]) : 0.f;
+      out[576 + j] = have ? __uint_as_float(v[15]) : 0.f;
+    }
 #pragma unroll
     for (int l = 1; l < MAXL; ++l) {
       if (l >= L) continue;
@@ -784,15 +806,21 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
       for (int cidx = 0; cidx < 5; ++cidx) {
         HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_H0 + 80u * (uint32_t)(l - 1) + 16u * (uint32_t)cidx, v);
         tc::wait_ld();
-        if (cidx < 4) {
+        if (owner) {
+          if (cidx < 4) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) out[off + j * H + cidx * 16 + i] = have ? __uint_as_float(v[i]) : 0.f;
-        } else {
-          out[off + 4096 + j] = have ? __uint_as_float(v[0]) : 0.f;
+            for (int i = 0; i < 16; ++i) out[off + j * H + cidx * 16 + i] = have ? __uint_as_float(v[i]) : 0.f;
+          } else {
+            out[off + 4096 + j] = have ? __uint_as_float(v[0]) : 0.f;
+          }
         }
       }
     }
-    // output layer (transposed): D[k][n] = dW_out[n][k]
+  }
+  // output layer (transposed, M = 128: lane = row): D[k][n] = dW_out[n][k] for the input features k < 64
+  if (!helper && wq < 2) {
+    const int j = row;
+    uint32_t v[16];
     HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
     tc::wait_ld();
 #pragma unroll

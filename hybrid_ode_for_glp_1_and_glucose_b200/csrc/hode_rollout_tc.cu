@@ -829,15 +829,3 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
 
 }  // namespace hode
 
-#ifdef HODE_TIMELINE
-extern "C" int hode_debug_timeline(long long* out_host, int max_events) {
-  int n = 0;
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, hode::g_tl_n, sizeof(int));
-  if (n > max_events) n = max_events;
-  cudaMemcpyFromSymbol(out_host, hode::g_tl, (size_t)n * 2 * sizeof(long long));
-  int zero = 0;
-  cudaMemcpyToSymbol(hode::g_tl_n, &zero, sizeof(int));
-  return n;
-}
-#endif

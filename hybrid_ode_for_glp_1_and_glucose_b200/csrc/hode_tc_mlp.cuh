@@ -237,3 +237,17 @@ __device__ __forceinline__ void mlp_tile_helper(TileCtx& c, float* stash = nullp
 }
 
 }  // namespace hode
+
+#ifdef HODE_TIMELINE
+// exactly one translation unit is compiled with -DHODE_TIMELINE (tools/timeline.py)
+extern "C" int hode_debug_timeline(long long* out_host, int max_events) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, hode::g_tl_n, sizeof(int));
+  if (n > max_events) n = max_events;
+  cudaMemcpyFromSymbol(out_host, hode::g_tl, (size_t)n * 2 * sizeof(long long));
+  int zero = 0;
+  cudaMemcpyToSymbol(hode::g_tl_n, &zero, sizeof(int));
+  return n;
+}
+#endif
