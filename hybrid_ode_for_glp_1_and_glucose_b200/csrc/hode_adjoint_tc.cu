@@ -21,6 +21,8 @@
 // other shapes use the FP32 adjoint.
 #include <math.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "hode_common.cuh"
 #include "hode_kernels.h"
 #include "hode_tc_mlp.cuh"
@@ -156,6 +158,63 @@ __device__ __forceinline__ void stage4(float* hi, float* lo, int ch, int row, in
   }
 }
 
+// The MMAs of the reverse sweep are issued by a dedicated warp: tcgen05.mma issue blocks while the
+// tensor pipe is busy (measured: ~3 700 cycles for the 72 MMAs of a hidden phase), and a warp
+// that also runs an epilogue would hold the whole tile back for that long.  The 256 epilogue
+// threads only ARRIVE on the named barrier; the issuer warp waits on it.
+constexpr int ISSUE_BAR = 3, ISSUE_BAR_THREADS = 2 * TILE + 32;
+__device__ __forceinline__ void issue_arrive() {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
+}
+__device__ __forceinline__ void issue_wait() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
+}
+
+// Issuer warp: the MMA chains of one stage of the reverse sweep, mirroring mlp_bwd_tile's phases.
+__device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
+  const int L = c.L;
+  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+  const uint32_t wslot_s = tc::smem_u32(b.wslot);
+  const uint32_t sd_hi = tc::smem_u32(b.sd_hi), sd_lo = tc::smem_u32(b.sd_lo);
+  const uint32_t sa_hi = tc::smem_u32(b.sa_hi), sa_lo = tc::smem_u32(b.sa_lo);
+  // phase L: u_{L-1} = delta_L W_out;  dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L (row 64 = db_out)
+  issue_wait();
+  tc::mbar_wait(b.wload_bar, b.wload_parity);
+  if (tc::elect_one()) {
+    tc::fence_after_sync();
+    issue_nobias<H, 2>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
+    tc::mma_commit(c.mma_bar);
+    issue_dw<128, 16>(c.tmem + DW_O, sa_hi, sa_lo, CH_A, sd_hi, sd_lo, CH_D, b.first);
+    tc::mma_commit(b.gemm_bar);
+  }
+  __syncwarp();
+  b.wload_parity ^= 1u;
+  b.gemm_parity ^= 1u;
+#pragma unroll
+  for (int p = MAXL; p >= 1; --p) {
+    if (p > L) continue;
+    issue_wait();
+    tc::mbar_wait(b.wload_bar, b.wload_parity);
+    if (tc::elect_one()) {
+      tc::fence_after_sync();
+      if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1};  dW_{p-1} += delta_{p-1}^T [a_{p-2} | 1]
+        issue_nobias<H, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 4096u * 4u);
+        tc::mma_commit(c.mma_bar);
+        issue_dw<64, 80>(c.tmem + DW_H0 + 80u * (uint32_t)(p - 2), sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
+      } else {        // g_x = delta_0 W_0;  dW_0 += delta_0^T [x | 1]
+        issue_nobias<16, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
+        tc::mma_commit(c.mma_bar);
+        issue_dw<64, 16>(c.tmem + DW_0, sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
+      }
+      tc::mma_commit(b.gemm_bar);
+    }
+    __syncwarp();
+    b.wload_parity ^= 1u;
+    b.gemm_parity ^= 1u;
+  }
+  b.first = 0u;
+}
+
 // ---- MLP backward for one stage (tile-collective: all 256 threads) ------------------------------------
 // MAIN threads own accumulator columns [0,32) of their trajectory, helpers [32,64).
 // g6 (main): cotangent of the 6 network outputs; x9 (main): the stage's input features;
@@ -170,11 +229,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
-  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
-  const uint32_t wslot_s = tc::smem_u32(b.wslot);
-  const uint32_t sd_hi = tc::smem_u32(b.sd_hi), sd_lo = tc::smem_u32(b.sd_lo);
-  const uint32_t sa_hi = tc::smem_u32(b.sa_hi), sa_lo = tc::smem_u32(b.sa_lo);
-  const bool issuer_warp = MAIN && c.wq == 0;
 
   // stream one block of the transposed weight image into the slot (previous reader has completed)
   auto fetch_w = [&](int float_off, int floats) {
@@ -211,20 +265,8 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   tc::fence_proxy_async();
   tc::fence_before_sync();
   HODE_TL(221);
-  tile_sync_all(c);
+  issue_arrive();   // the issuer warp launches phase L (mlp_bwd_issue) once all 256 threads are here
   HODE_TL(222);
-  if (issuer_warp) {
-    tc::mbar_wait(b.wload_bar, b.wload_parity);
-    if (tc::elect_one()) {
-      tc::fence_after_sync();
-      issue_nobias<H, 2>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
-      tc::mma_commit(c.mma_bar);
-      // dW_out^T [in k][out n] = a_{L-1}^T delta_L  (rows = the 80 staged input features: row 64 = db_out)
-      issue_dw<128, 16>(c.tmem + DW_O, sa_hi, sa_lo, CH_A, sd_hi, sd_lo, CH_D, b.first);
-      tc::mma_commit(b.gemm_bar);
-    }
-    __syncwarp();
-  }
   b.wload_parity ^= 1u;
   b.gemm_parity ^= 1u;
   HODE_TL(223);
@@ -280,25 +322,8 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     tc::fence_proxy_async();
     tc::fence_before_sync();
     HODE_TL(233 + 10 * p);
-    tile_sync_all(c);
+    issue_arrive();
     HODE_TL(234 + 10 * p);
-    if (issuer_warp) {
-      tc::mbar_wait(b.wload_bar, b.wload_parity);
-      if (tc::elect_one()) {
-        tc::fence_after_sync();
-        if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1};  dW_{p-1} += delta_{p-1}^T [a_{p-2} | 1]
-          issue_nobias<H, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 4096u * 4u);
-          tc::mma_commit(c.mma_bar);
-          issue_dw<64, 80>(c.tmem + DW_H0 + 80u * (uint32_t)(p - 2), sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
-        } else {        // g_x = delta_0 W_0;  dW_0 += delta_0^T [x | 1]
-          issue_nobias<16, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
-          tc::mma_commit(c.mma_bar);
-          issue_dw<64, 16>(c.tmem + DW_0, sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
-        }
-        tc::mma_commit(b.gemm_bar);
-      }
-      __syncwarp();
-    }
     b.wload_parity ^= 1u;
     b.gemm_parity ^= 1u;
     HODE_TL(235 + 10 * p);
@@ -378,12 +403,17 @@ struct AdjTcArgs {
   const float* img_fwd;    // [S][fwd_floats]
   const float* img_bwd;    // [S][bwd_floats]
   int fwd_floats, bwd_floats;
+  // schedule (adj_schedule_kernel): trajectories sorted by accepted-step count, tiles handed to CTAs
+  const int32_t* perm;        // [S*B] unit index of sorted slot q (within its parameter set)
+  const int32_t* sched_off;   // [S][grid_x + 1] range of sched_tiles owned by CTA (s, x)
+  const int32_t* sched_tiles; // [S][n_tiles] tile indices grouped by owner
+  int n_tiles;
 };
 
 // ---------------------------------------------------------------------------------------------------
 // grid = (ctas per parameter set, S), block = 256 (4 main + 4 helper warps), 1 CTA / SM
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
+__global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t load_bar;
@@ -395,7 +425,8 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   const RolloutArgs& A = G.R;
   const int tid = threadIdx.x, lane_id = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const bool helper = warp >= 4;
+  // warps 0-3: main (one trajectory per thread), 4-7: helpers (other half of every epilogue), 8: MMA issuer
+  const bool main_role = warp < 4, helper = warp >= 4 && warp < 8, issuer = warp == 8;
   const int wq = warp & 3, row = tid & 127;
   const int s = blockIdx.y, T = A.T, L = A.L;
   const int solver = A.solver == HODE_SOLVER_RK4 ? 0 : 1;
@@ -491,7 +522,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   auto begin_reverse = [&]() {
     tc::fence_before_sync();
     __syncthreads();
-    if (!helper) {
+    if (main_role) {
       stage4(sa_hi, sa_lo, CH_A, row, 64, 1.f, 0.f, 0.f, 0.f);
       stage4(sa_hi, sa_lo, CH_A, row, 68, 0.f, 0.f, 0.f, 0.f);
       stage4(sa_hi, sa_lo, CH_A, row, 72, 0.f, 0.f, 0.f, 0.f);
@@ -499,12 +530,15 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
     }
   };
 
-  for (long blk = blockIdx.x; blk * TILE < A.B; blk += gridDim.x) {
-    const long b = blk * TILE + row;
-    const bool valid = b < A.B;
-    const long bs = valid ? b : 0;
-    const long unit = (long)s * A.B + bs;
-    int n = (valid && !helper) ? A.save_n[unit] : 0;
+  const int32_t* my_tiles = G.sched_tiles + (size_t)s * G.n_tiles;
+  const int tile_beg = G.sched_off[(size_t)s * (gridDim.x + 1) + blockIdx.x];
+  const int tile_end = G.sched_off[(size_t)s * (gridDim.x + 1) + blockIdx.x + 1];
+  for (int tk = tile_beg; tk < tile_end; ++tk) {
+    const long q = (long)my_tiles[tk] * TILE + row;   // slot in the step-count-sorted order
+    const bool valid = q < A.B;
+    const long unit = valid ? (long)G.perm[(size_t)s * A.B + q] : (long)s * A.B;
+    const long bs = unit - (long)s * A.B;
+    int n = (valid && main_role) ? A.save_n[unit] : 0;
     const bool ok = valid && n >= 0;
     if (n < 0) n = 0;
     if (tid == 0) s_nmax = 0;
@@ -534,14 +568,20 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
       HODE_TL(200);
       load_image(fwd_src, G.fwd_floats);
       HODE_TL(201);
-      if (helper) {
+      if (!main_role) {
+        if (helper) {
 #pragma unroll 1
-        for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, NT);
+          for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, NT);
+        }
         begin_reverse();
 #pragma unroll 1
         for (int i = N - 1; i >= 0; --i) {
-          bc.stash = stash0 + (size_t)i * stage_stride;
-          mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
+          if (helper) {
+            bc.stash = stash0 + (size_t)i * stage_stride;
+            mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
+          } else {
+            mlp_bwd_issue(c, bc);
+          }
         }
         continue;
       }
@@ -753,7 +793,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
       }
       HODE_TL(204);
     }
-    if (!helper) {
+    if (main_role) {
       if (ok) {
         if (solver == 0) {
 #pragma unroll
@@ -786,7 +826,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
   const int offo = 640 + (L - 1) * 4160;
   // M = 64 accumulators (layer 0 and the hidden layers): row j of D lives in TMEM lane 32 (j / 16) + j % 16
   // (csrc/probe/adj_probe.cu), i.e. in the first 16 lanes of every main warp.  The loads are warp-wide.
-  if (!helper) {
+  if (main_role) {
     const int j = 16 * wq + lane_id;
     const bool owner = lane_id < 16;
     uint32_t v[16];
@@ -818,7 +858,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
     }
   }
   // output layer (transposed, M = 128: lane = row): D[k][n] = dW_out[n][k] for the input features k < 64
-  if (!helper && wq < 2) {
+  if (main_role && wq < 2) {
     const int j = row;
     uint32_t v[16];
     HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
@@ -826,7 +866,7 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
 #pragma unroll
     for (int nn = 0; nn < NS; ++nn) out[offo + nn * H + j] = have ? __uint_as_float(v[nn]) : 0.f;
   }
-  if (!helper && wq == 2) {   // TMEM lane 64: the constant-1 input feature -> db_out (warp-wide load)
+  if (main_role && wq == 2) {   // TMEM lane 64: the constant-1 input feature -> db_out (warp-wide load)
     uint32_t v[16];
     HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
     tc::wait_ld();
@@ -835,13 +875,13 @@ __global__ void __launch_bounds__(256, 1) rollout_bwd_tc_kernel(const AdjTcArgs 
       for (int nn = 0; nn < NS; ++nn) out[offo + 384 + nn] = have ? __uint_as_float(v[nn]) : 0.f;
     }
   }
-  if (!helper) {
+  if (main_role) {
     // deterministic reduction of the theta gradients over the 128 trajectory slots
 #pragma unroll
     for (int i = 0; i < HODE_N_THETA; ++i) red[i * TILE + row] = gth[i];
   }
   __syncthreads();
-  if (!helper && row < HODE_N_THETA) {
+  if (main_role && row < HODE_N_THETA) {
     float sacc = 0.f;
     for (int r = 0; r < TILE; ++r) sacc += red[row * TILE + r];
     out[A.P + row] = sacc;
@@ -882,6 +922,88 @@ __global__ void prep_tc_bwd_image_kernel(const float* __restrict__ W, float* __r
   }
 }
 
+// ---- schedule: sort by accepted-step count, tiles to CTAs by longest-processing-time-first ----------
+// A tile runs for max(accepted steps) iterations over its 128 trajectories, and adaptive step counts
+// differ several-fold inside a cohort (bench cohort: mean 33, mean tile maximum 55).  Trajectories
+// are therefore sorted by step count (stable radix sort: the order, and with it every gradient
+// sum, is a pure function of the inputs), cut into tiles, and the tiles are dealt to the CTAs of
+// their parameter set greedily, longest first, each to the least-loaded CTA.
+constexpr uint32_t SORT_N_BITS = 20, SORT_N_MASK = (1u << SORT_N_BITS) - 1u;
+
+__global__ void adj_sort_keys_kernel(const int32_t* __restrict__ save_n, uint32_t* __restrict__ keys,
+                                     int32_t* __restrict__ vals, long n_units, int B, int sorted) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units) return;
+  int n = save_n[i];
+  n = n < 0 ? 0 : (n > (int)SORT_N_MASK ? (int)SORT_N_MASK : n);
+  const uint32_t s = (uint32_t)(i / B);
+  keys[i] = sorted ? ((s << SORT_N_BITS) | (SORT_N_MASK - (uint32_t)n)) : (uint32_t)n;   // descending n inside a set
+  vals[i] = (int32_t)i;
+}
+
+// one CTA per parameter set; warp 0 runs the greedy assignment, then thread x gathers CTA x's list
+__global__ void __launch_bounds__(256) adj_schedule_kernel(const uint32_t* __restrict__ keys, int B, int n_tiles, int gx,
+                                                           int sorted, int32_t* __restrict__ owner,
+                                                           int32_t* __restrict__ sched_off, int32_t* __restrict__ sched_tiles) {
+  __shared__ int cnt[256];
+  __shared__ int off[257];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const uint32_t* k = keys + (size_t)s * B;
+  int32_t* own = owner + (size_t)s * n_tiles;
+  cnt[tid] = 0;
+  __syncthreads();
+  if (tid < 32) {
+    unsigned load[8];   // CTA x = lane + 32 * slot
+#pragma unroll
+    for (int j = 0; j < 8; ++j) load[j] = (lane + 32 * j) < gx ? 0u : 0xFFFFFFFFu;
+    for (int t = 0; t < n_tiles; ++t) {
+      // cost = iterations of the tile (its largest step count; the slots are sorted descending) + 1
+      unsigned cost = 1u;
+      if (sorted) {
+        cost += SORT_N_MASK - (k[(size_t)t * TILE] & SORT_N_MASK);
+      } else {   // unsorted fallback: scan the tile
+        unsigned m = 0;
+        for (int r = lane; r < TILE && (size_t)t * TILE + r < (size_t)B; r += 32) m = max(m, k[(size_t)t * TILE + r]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        cost += m;
+      }
+      unsigned long long best = ~0ull;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned long long cand = ((unsigned long long)load[j] << 32) | (unsigned)(lane + 32 * j);
+        best = cand < best ? cand : best;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+      }
+      const int x = (int)(best & 0xFFFFFFFFull);
+      if ((x & 31) == lane) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j == (x >> 5)) load[j] += cost;
+        own[t] = x;
+        cnt[x] += 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int x = 0; x < gx; ++x) { off[x] = acc; acc += cnt[x]; }
+    off[gx] = acc;
+  }
+  __syncthreads();
+  if (tid <= gx) sched_off[(size_t)s * (gx + 1) + tid] = off[tid];
+  if (tid < gx) {
+    int o = off[tid];
+    for (int t = 0; t < n_tiles; ++t)
+      if (own[t] == tid) sched_tiles[(size_t)s * n_tiles + o++] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -895,17 +1017,12 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   if (sms < 1) sms = 148;
   const long blocks = ((long)B + TILE - 1) / TILE;
   long gx = sms / (S > 0 ? S : 1);
-  if (gx < 1) gx = 1;
+  if (gx > 256) gx = 256;   // adj_schedule_kernel keeps 8 CTA loads per lane
   if (gx > blocks) gx = blocks;
   if (gx < 1) gx = 1;
-  // balance: every CTA walks the same number of trajectory blocks (fewer, equally loaded CTAs
-  // finish at the same time as more, unequally loaded ones, with less scratch)
-  {
-    const long rounds = blocks > 0 ? (blocks + gx - 1) / gx : 1;
-    gx = blocks > 0 ? (blocks + rounds - 1) / rounds : 1;
-  }
   p.grid_x = (int)gx;
   p.grid_y = S;
+  p.n_tiles = (int)(blocks > 0 ? blocks : 1);
   p.fwd_floats = tc_image_floats(L);
   p.bwd_floats = tc_bwd_image_floats(L);
   const int bwd_cap = WSLOT_FLOATS + 2 * SD_FLOATS + 2 * SA_FLOATS;
@@ -915,12 +1032,20 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   p.partial_floats = (size_t)gx * S * (size_t)(P + HODE_N_THETA);
   p.stash_floats = (size_t)gx * S * TILE * (size_t)NSTAGE_MAX * L * H;
   p.img_floats = (size_t)S * (p.fwd_floats + p.bwd_floats);
+  // schedule scratch: sort keys / values (in, out), tile owners, per-CTA tile lists, cub temporaries
+  const size_t units = (size_t)S * (size_t)(B > 0 ? B : 0);
+  p.sched_ints = 4 * units + (size_t)S * (2 * (size_t)p.n_tiles + gx + 1);
+  p.sort_bytes = 0;
+  if (units > 0)
+    cub::DeviceRadixSort::SortPairs(nullptr, p.sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (long long)units, 0, 32, (cudaStream_t)0);
   return p;
 }
 
 size_t adj_tc_workspace_bytes(const AdjTcPlan& p) {
   auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
-  return (al(p.partial_floats) + al(p.stash_floats) + al(p.img_floats)) * sizeof(float);
+  return (al(p.partial_floats) + al(p.stash_floats) + al(p.img_floats) + al(p.sched_ints)) * sizeof(float) +
+         ((p.sort_bytes + 255) & ~(size_t)255);
 }
 
 cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, float* grad_y0,
@@ -939,14 +1064,53 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, 
   G.img_bwd = imgs + (size_t)A.S * p.fwd_floats;
   G.fwd_floats = p.fwd_floats;
   G.bwd_floats = p.bwd_floats;
+  // schedule scratch
+  const size_t units = (size_t)A.S * (size_t)A.B;
+  uint32_t* keys_in = reinterpret_cast<uint32_t*>(imgs + al(p.img_floats));
+  uint32_t* keys_out = keys_in + units;
+  int32_t* vals_in = reinterpret_cast<int32_t*>(keys_out + units);
+  int32_t* perm = vals_in + units;
+  int32_t* owner = perm + units;
+  int32_t* sched_tiles = owner + (size_t)A.S * p.n_tiles;
+  int32_t* sched_off = sched_tiles + (size_t)A.S * p.n_tiles;
+  void* sort_tmp = reinterpret_cast<float*>(keys_in) + al(p.sched_ints);
+  G.perm = perm;
+  G.sched_off = sched_off;
+  G.sched_tiles = sched_tiles;
+  G.n_tiles = p.n_tiles;
   cudaError_t e = tc_prepare_fwd_images(A.W, imgs, A.S, A.L, A.P, stream);
   if (e != cudaSuccess) return e;
   prep_tc_bwd_image_kernel<<<A.S, 256, 0, stream>>>(A.W, imgs + (size_t)A.S * p.fwd_floats, A.L, A.P, p.bwd_floats);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  {
+    // the composite key holds the parameter-set index above SORT_N_BITS bits of step count
+    int s_bits = 0;
+    while ((1L << s_bits) < (long)A.S) ++s_bits;
+    const int sorted = (s_bits + (int)SORT_N_BITS <= 32) ? 1 : 0;
+    adj_sort_keys_kernel<<<(unsigned)((units + 255) / 256), 256, 0, stream>>>(A.save_n, keys_in, vals_in, (long)units,
+                                                                              A.B, sorted);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint32_t* sched_keys = keys_in;
+    if (sorted) {
+      size_t tmp_bytes = p.sort_bytes;
+      e = cub::DeviceRadixSort::SortPairs(sort_tmp, tmp_bytes, (const uint32_t*)keys_in, keys_out, (const int32_t*)vals_in,
+                                          perm, (long long)units, 0, s_bits + (int)SORT_N_BITS, stream);
+      if (e != cudaSuccess) return e;
+      sched_keys = keys_out;
+    } else {
+      e = cudaMemcpyAsync(perm, vals_in, units * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) return e;
+    }
+    adj_schedule_kernel<<<A.S, 256, 0, stream>>>(sched_keys, A.B, p.n_tiles, p.grid_x, sorted, owner, sched_off,
+                                                 sched_tiles);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   e = cudaFuncSetAttribute(rollout_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return e;
-  rollout_bwd_tc_kernel<<<dim3(p.grid_x, p.grid_y), 256, p.smem, stream>>>(G);
+  rollout_bwd_tc_kernel<<<dim3(p.grid_x, p.grid_y), 2 * TILE + 32, p.smem, stream>>>(G);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_reduce_partials(G.partials, p.grid_x, A.S, A.P, grad_W, grad_theta, stream);

@@ -42,8 +42,10 @@ int tc_image_floats(int L);
 int tc_bwd_image_floats(int L);
 cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, cudaStream_t stream);
 struct AdjTcPlan {
-  int grid_x, grid_y, fwd_floats, bwd_floats;
+  int grid_x, grid_y, fwd_floats, bwd_floats, n_tiles;
   size_t smem, partial_floats, stash_floats, img_floats;
+  size_t sched_ints;   // sort keys / values, tile owners and per-CTA tile lists (int32 words)
+  size_t sort_bytes;   // cub::DeviceRadixSort temporaries
 };
 bool adj_tc_supported(int H, int L);
 AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj);
