@@ -83,85 +83,118 @@ __device__ __forceinline__ void split16(const float* d, uint32_t* hi, uint32_t* 
 }
 
 // ---- weight gradients on the tensor cores ---------------------------------------------------------
-// dW_l += delta_l^T a_{l-1} contracts over the 128 trajectories of the tile: an SS-form MMA
-// (both operands in shared memory, K = trajectory).  kind::tf32 needs K-major operands, so every
-// thread writes its trajectory's values TRANSPOSED into the canonical no-swizzle K-major layout
-// (validated by csrc/probe/adj_probe.cu, test 3):
-//   element (feature f, trajectory t) at float  (t % 4) + 4 * (f % 8) + 32 * (f / 8) + CH * (t / 4)
-// with CH = 8-feature groups * 32 + 4 pad floats (the pad makes the 32 lanes of a warp hit 32
-// different banks).  delta arrays hold 64 features (CH_D = 260), input arrays 80: 64 features +
-// one group whose first feature is the constant 1 (its accumulator column is the bias gradient)
-// + one zero group (N must be a multiple of 16) (CH_A = 324).  hi / lo TF32 parts are separate
-// arrays; the product is the usual 3-pass d_lo*a_hi + d_hi*a_lo + d_hi*a_hi.
-// The accumulators live in TMEM for the whole kernel (fp32):
-//   hidden layer l = 1..3 : columns DW_H0 + 80 (l-1) .. +80   D[j][k] = dW_l[j][k], column 64 = db_l[j]
+// dW_l += delta_l^T [a_{l-1} | 1] contracts over the 128 trajectories of the tile: an SS-form MMA
+// with K = trajectory.  kind::tf32 takes K-major operands only, which would force a transposed
+// staging (4-byte scattered stores); kind::f16 takes MN-major operands, so "thread t owns
+// trajectory t" writes 8 consecutive features as ONE 16-byte vector (csrc/probe/bf16_probe.cu):
+//   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2
+//   descriptor: LBO = 128 B (between 8-trajectory groups), SBO = ST_GRP (between 8-feature groups).
+// Operands are split in two BF16 terms, x ~= hi + mid (2^-17), and the product takes 3 passes
+// mid*hi + hi*mid + hi*hi at the BF16 rate (twice the TF32 rate): measured max error 2.7e-6 of
+// sum|ab| per 128-term product.  The activations a_{l-1} are already stored in this form by the
+// forward recomputation (stash, hode_tc_mlp.cuh) and come back by bulk copy; only delta is written
+// by the threads.  Inputs carry one extra 8-feature group whose first feature is the constant 1
+// (its accumulator column is the bias gradient).
+// Accumulators live in TMEM for the whole kernel (fp32):
+//   hidden layer l = 1..3 : columns DW_H0 + 80 (l-1) .. +72   D[j][k] = dW_l[j][k], column 64 = db_l[j]
 //   layer 0               : columns DW_0  .. +16               D[j][k] = dW_0[j][k] (k < 9), column 15 = db_0[j]
 //   output layer (transp.): columns DW_O  .. +16               D[k][n] = dW_out[n][k] (n < 6), row 64 = db_out[n]
-constexpr int CH_D = 8 * 32 + 4, CH_A = 10 * 32 + 4;
-constexpr int SD_FLOATS = 32 * CH_D + 256, SA_FLOATS = 32 * CH_A + 256;   // + slack: M = 128 reads 16 groups
-constexpr int WSLOT_FLOATS = 2 * 4096;
 constexpr uint32_t DW_H0 = 208, DW_0 = 448, DW_O = 464;
+// shared memory of the reverse sweep (bytes; everything double-buffered by issue phase):
+//   [input operands 2 x (hi, mid) x 9 groups][delta operands 2 x (hi, mid) x 8 groups][W_l^T slots 2 x (hi, lo)]
+constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART;
+constexpr int DB_BYTES = 2 * ST_PART;
+constexpr int WS_BYTES = 2 * 4096 * 4;
+constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_WS = OFF_DB + 2 * DB_BYTES;
+constexpr int BWD_BYTES = OFF_WS + 2 * WS_BYTES;
 
-struct BwdCtx {
-  float* sd_hi; float* sd_lo;   // delta staging (K-major transposed)
-  float* sa_hi; float* sa_lo;   // layer-input staging
-  float* wslot;                 // one layer's transposed weights (hi then lo), streamed per phase
-  const float* wsrc;            // global: this parameter set's transposed weight image
-  uint64_t* wload_bar;          // completion of the weight-slot bulk copy (main warp 0 waits)
-  uint64_t* gemm_bar;           // completion of the weight-gradient MMAs (frees the staging arrays)
-  uint32_t wload_parity, gemm_parity;
-  uint32_t first;               // 1 until the accumulators have been initialised
-  const float* stash;           // this row's activation column of the current stage; element e at stash[e * ss]
-  size_t ss;
-  int row;                      // trajectory slot 0..127
-};
-
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// kind::f16 instruction descriptor: D = f32, A = B = BF16, both MN-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
       "r"(accumulate)
       : "memory");
 }
 
-// D[tmem] (+)= A^T B over the 128 trajectories: 3 passes x 16 k-steps of 8 trajectories.
-// (a_hi, a_lo): staging arrays of the operand that becomes the ROWS of D (chunk stride cha floats),
-// (b_hi, b_lo): of the operand that becomes the COLUMNS (chunk stride chb).  `init` = overwrite D.
+// D[tmem] (+)= R^T C over the 128 trajectories: 3 passes x 8 k-steps of 16 trajectories.
+// r_*: shared-memory byte address of the operand whose features become the ROWS of D, c_*: the COLUMNS.
 template <int M, int N>
-__device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_hi, uint32_t a_lo, int cha, uint32_t b_hi, uint32_t b_lo,
-                                         int chb, uint32_t init) {
-  constexpr uint32_t idesc = tc::make_idesc_tf32(M, N);
-  const uint64_t da_hi = tc::make_desc(a_hi, (uint32_t)cha * 4u, 128u), da_lo = tc::make_desc(a_lo, (uint32_t)cha * 4u, 128u);
-  const uint64_t db_hi = tc::make_desc(b_hi, (uint32_t)chb * 4u, 128u), db_lo = tc::make_desc(b_lo, (uint32_t)chb * 4u, 128u);
-  // one k-step = 8 trajectories = 2 chunks: the start-address field (16-byte units) advances by 2*CH*4/16
-  const uint64_t sa = (uint64_t)((uint32_t)cha * 8u >> 4), sb = (uint64_t)((uint32_t)chb * 8u >> 4);
-#pragma unroll 4
-  for (int ks = 0; ks < TILE / 8; ++ks)
-    mma_tf32_ss(d, da_lo + sa * ks, db_hi + sb * ks, idesc, (ks == 0 && init) ? 0u : 1u);
-#pragma unroll 4
-  for (int ks = 0; ks < TILE / 8; ++ks) mma_tf32_ss(d, da_hi + sa * ks, db_lo + sb * ks, idesc, 1u);
-#pragma unroll 4
-  for (int ks = 0; ks < TILE / 8; ++ks) mma_tf32_ss(d, da_hi + sa * ks, db_hi + sb * ks, idesc, 1u);
+__device__ __forceinline__ void issue_dw(uint32_t d, uint32_t r_hi, uint32_t r_mid, uint32_t c_hi, uint32_t c_mid,
+                                         uint32_t init) {
+  constexpr uint32_t idesc = make_idesc_bf16_mn(M, N);
+  const uint64_t rh = tc::make_desc(r_hi, 128u, ST_GRP), rm = tc::make_desc(r_mid, 128u, ST_GRP);
+  const uint64_t ch = tc::make_desc(c_hi, 128u, ST_GRP), cm = tc::make_desc(c_mid, 128u, ST_GRP);
+  // one k-step = 16 trajectories = 256 B: the start-address field (16-byte units) advances by 16
+#pragma unroll
+  for (int ks = 0; ks < TILE / 16; ++ks) mma_bf16_ss(d, rm + 16u * ks, ch + 16u * ks, idesc, (ks == 0 && init) ? 0u : 1u);
+#pragma unroll
+  for (int ks = 0; ks < TILE / 16; ++ks) mma_bf16_ss(d, rh + 16u * ks, cm + 16u * ks, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < TILE / 16; ++ks) mma_bf16_ss(d, rh + 16u * ks, ch + 16u * ks, idesc, 1u);
 }
 
-// transposed staging of 4 consecutive features f0..f0+3 of trajectory `row` (TF32 hi / lo)
-__device__ __forceinline__ void stage4(float* hi, float* lo, int ch, int row, int f0, float v0, float v1, float v2,
-                                       float v3) {
-  const int base = (row & 3) + ch * (row >> 2) + 32 * (f0 >> 3) + 4 * (f0 & 7);
-  const float v[4] = {v0, v1, v2, v3};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t h = (__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u;
-    hi[base + 4 * q] = __uint_as_float(h);
-    lo[base + 4 * q] = v[q] - __uint_as_float(h);
+// Issue phases of the reverse sweep.  One stage has L + 1 of them, q = L .. 0:
+//   phase q:  u_{q-1} = delta_q W_q  (3xTF32, delta in TMEM, W_q^T in a slot)   and   dW_q += delta_q^T [a_{q-1} | 1]
+// (a_{-1} = the stage's input features x, u_{-1} = the cotangent of x).  Phases are numbered through
+// the whole kernel (`ph`); phase ph uses buffer ph & 1 of every double-buffered region, and its
+// mbarriers complete once per phase, so the parity to wait for is (ph >> 1) & 1.
+struct BwdCtx {
+  uint8_t* smem;              // reverse-sweep layout (OFF_*)
+  const float* wsrc;          // global: this parameter set's transposed weight image
+  uint8_t* stash_cta;         // global: this CTA's activation stash
+  uint8_t* stage_blk;         // stash block of the current stage, layer 0
+  uint64_t* wload_bar;        // [2] W^T slot filled
+  uint64_t* aload_bar;        // [2] input operand filled
+  uint64_t* gemm_bar;         // weight-gradient MMAs of a phase complete
+  uint32_t ph;                // phases issued so far
+  int k, k_end, stage_top;    // phase index inside the current sweep, phases in the sweep, stage of phase 0
+  uint32_t first;             // 1 until the accumulators have been initialised
+  int row;                    // trajectory slot 0..127
+};
+
+// wait until every weight-gradient MMA issued so far has completed (at most the last phase can be
+// pending: its u-chain, which the epilogue threads have waited for, was issued after all earlier ones)
+__device__ __forceinline__ void wait_gemm(const BwdCtx& b) {
+  if (b.ph > 0u) tc::mbar_wait(b.gemm_bar, (b.ph - 1u) & 1u);
+}
+
+// input operand of sweep phase k1 (global phase ph1): bulk copy of the stashed a_{q-1}, hi and mid
+__device__ __forceinline__ void prefetch_A(const BwdCtx& b, int L, int k1, uint32_t ph1) {
+  if (k1 >= b.k_end) return;
+  const int st = b.stage_top - k1 / (L + 1), q = L - k1 % (L + 1);
+  uint64_t* bar = b.aload_bar + (ph1 & 1u);
+  if (q >= 1) {
+    const uint8_t* src = b.stash_cta + ((size_t)st * L + (q - 1)) * ST_BLK;
+    uint8_t* dst = b.smem + OFF_AB + (ph1 & 1u) * AB_BYTES;
+    tc::mbar_expect_tx(bar, 2u * ST_PART);
+    tc::bulk_g2s(dst, src, ST_PART, bar);
+    tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, bar);
+  } else {
+    tc::mbar_arrive(bar);   // phase 0: the main threads write x themselves
   }
+}
+// W_q^T of sweep phase k2 (global phase ph2)
+__device__ __forceinline__ void prefetch_W(const BwdCtx& b, int L, int k2, uint32_t ph2) {
+  if (k2 >= b.k_end) return;
+  const int q = L - k2 % (L + 1);
+  int off, floats;
+  if (q == L) { off = 0; floats = 2048; }
+  else if (q >= 1) { off = 2048 + (L - 1 - q) * 8192; floats = 8192; }
+  else { off = 2048 + (L - 1) * 8192; floats = 2048; }
+  uint64_t* bar = b.wload_bar + (ph2 & 1u);
+  tc::mbar_expect_tx(bar, (uint32_t)floats * 4u);
+  tc::bulk_g2s(b.smem + OFF_WS + (ph2 & 1u) * WS_BYTES, b.wsrc + off, (uint32_t)floats * 4u, bar);
 }
 
 // The MMAs of the reverse sweep are issued by a dedicated warp: tcgen05.mma issue blocks while the
-// tensor pipe is busy (measured: ~3 700 cycles for the 72 MMAs of a hidden phase), and a warp
-// that also runs an epilogue would hold the whole tile back for that long.  The 256 epilogue
-// threads only ARRIVE on the named barrier; the issuer warp waits on it.
+// tensor pipe is busy, and a warp that also runs an epilogue would hold the whole tile back for
+// that long.  The 256 epilogue threads only ARRIVE on the named barrier; the issuer warp waits on it.
 constexpr int ISSUE_BAR = 3, ISSUE_BAR_THREADS = 2 * TILE + 32;
 __device__ __forceinline__ void issue_arrive() {
   asm volatile("bar.arrive %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
@@ -174,75 +207,56 @@ __device__ __forceinline__ void issue_wait() {
 __device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
   const int L = c.L;
   const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
-  const uint32_t wslot_s = tc::smem_u32(b.wslot);
-  const uint32_t sd_hi = tc::smem_u32(b.sd_hi), sd_lo = tc::smem_u32(b.sd_lo);
-  const uint32_t sa_hi = tc::smem_u32(b.sa_hi), sa_lo = tc::smem_u32(b.sa_lo);
-  // phase L: u_{L-1} = delta_L W_out;  dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L (row 64 = db_out)
-  issue_wait();
-  tc::mbar_wait(b.wload_bar, b.wload_parity);
-  if (tc::elect_one()) {
-    tc::fence_after_sync();
-    issue_nobias<H, 2>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
-    tc::mma_commit(c.mma_bar);
-    issue_dw<128, 16>(c.tmem + DW_O, sa_hi, sa_lo, CH_A, sd_hi, sd_lo, CH_D, b.first);
-    tc::mma_commit(b.gemm_bar);
-  }
-  __syncwarp();
-  b.wload_parity ^= 1u;
-  b.gemm_parity ^= 1u;
+  const uint32_t base = tc::smem_u32(b.smem);
 #pragma unroll
-  for (int p = MAXL; p >= 1; --p) {
-    if (p > L) continue;
+  for (int q = MAXL; q >= 0; --q) {
+    if (q > L) continue;
+    const uint32_t buf = b.ph & 1u, par = (b.ph >> 1) & 1u;
+    const uint32_t ws = base + OFF_WS + buf * WS_BYTES;
+    const uint32_t a_hi = base + OFF_AB + buf * AB_BYTES, a_mid = a_hi + AB_PART;
+    const uint32_t d_hi = base + OFF_DB + buf * DB_BYTES, d_mid = d_hi + ST_PART;
     issue_wait();
-    tc::mbar_wait(b.wload_bar, b.wload_parity);
+    tc::mbar_wait(b.wload_bar + buf, par);
     if (tc::elect_one()) {
       tc::fence_after_sync();
-      if (p >= 2) {   // u_{p-2} = delta_{p-1} W_{p-1};  dW_{p-1} += delta_{p-1}^T [a_{p-2} | 1]
-        issue_nobias<H, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 4096u * 4u);
-        tc::mma_commit(c.mma_bar);
-        issue_dw<64, 80>(c.tmem + DW_H0 + 80u * (uint32_t)(p - 2), sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
-      } else {        // g_x = delta_0 W_0;  dW_0 += delta_0^T [x | 1]
-        issue_nobias<16, 8>(m_d, m_ahi, m_alo, wslot_s, wslot_s + 1024u * 4u);
-        tc::mma_commit(c.mma_bar);
-        issue_dw<64, 16>(c.tmem + DW_0, sd_hi, sd_lo, CH_D, sa_hi, sa_lo, CH_A, b.first);
-      }
+      if (q == L) issue_nobias<H, 2>(m_d, m_ahi, m_alo, ws, ws + 1024u * 4u);        // u_{L-1} = delta_L W_out
+      else if (q >= 1) issue_nobias<H, 8>(m_d, m_ahi, m_alo, ws, ws + 4096u * 4u);   // u_{q-1} = delta_q W_q
+      else issue_nobias<16, 8>(m_d, m_ahi, m_alo, ws, ws + 1024u * 4u);              // g_x = delta_0 W_0
+      tc::mma_commit(c.mma_bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(b.aload_bar + buf, par);
+    if (tc::elect_one()) {
+      // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
+      if (q == L) issue_dw<128, 16>(c.tmem + DW_O, a_hi, a_mid, d_hi, d_mid, b.first);
+      else if (q >= 1) issue_dw<64, 72>(c.tmem + DW_H0 + 80u * (uint32_t)(q - 1), d_hi, d_mid, a_hi, a_mid, b.first);
+      else issue_dw<64, 16>(c.tmem + DW_0, d_hi, d_mid, a_hi, a_mid, b.first);
       tc::mma_commit(b.gemm_bar);
     }
     __syncwarp();
-    b.wload_parity ^= 1u;
-    b.gemm_parity ^= 1u;
+    b.ph += 1u;
+    b.k += 1;
   }
   b.first = 0u;
 }
 
-// ---- MLP backward for one stage (tile-collective: all 256 threads) ------------------------------------
+// ---- MLP backward for one stage (tile-collective: all 256 epilogue threads) ---------------------------
 // MAIN threads own accumulator columns [0,32) of their trajectory, helpers [32,64).
 // g6 (main): cotangent of the 6 network outputs; x9 (main): the stage's input features;
 // gx (main, out): cotangent of the 9 input features.
-// Notation: delta_l = cotangent of the pre-activation of layer l (l = 0..L-1), delta_L = g;
-// phase p issues  dW_p += delta_p^T a_{p-1}  and  u_{p-1} = delta_p W_p  (p = L..1), phase 0 issues
-// dW_0 += delta_0^T x  and  g_x = delta_0 W_0.
+// Notation: delta_l = cotangent of the pre-activation of layer l (l = 0..L-1), delta_L = g.
 template <bool MAIN>
 __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float* x9, const float* g6, float* gx) {
   constexpr int half = MAIN ? 0 : 32;
+  constexpr int hidx = MAIN ? 0 : 1;
   const int L = c.L;
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
+  const bool loader = MAIN && threadIdx.x == 0;
 
-  // stream one block of the transposed weight image into the slot (previous reader has completed)
-  auto fetch_w = [&](int float_off, int floats) {
-    if (MAIN && threadIdx.x == 0) {
-      tc::mbar_expect_tx(b.wload_bar, (uint32_t)floats * 4u);
-      tc::bulk_g2s(b.wslot, b.wsrc + float_off, (uint32_t)floats * 4u, b.wload_bar);
-    }
-  };
-
-  // ---- prologue: delta_L = g; operands of dW_out; phase L --------------------------------------------
-  // the staging arrays are free once the previous stage's weight-gradient MMAs have completed
-  tc::mbar_wait(b.gemm_bar, b.gemm_parity ^ 1u);   // (first call: the phase "before 0" counts as complete)
+  // ---- prologue: delta_L = g; phase L (its input operand and W^T slot are already on their way) ------
   HODE_TL(220);
-  fetch_w(0, 2048);
   if (MAIN) {
     float d[16];
 #pragma unroll
@@ -251,46 +265,43 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     split16(d, hi, lo);
     HODE_TMEM_ST_X16(t_ahi, hi);
     HODE_TMEM_ST_X16(t_alo, lo);
-    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 0, d[0], d[1], d[2], d[3]);
-    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 4, d[4], d[5], 0.f, 0.f);
-    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 8, 0.f, 0.f, 0.f, 0.f);    // N = 16: features 8..15 are zero
-    stage4(b.sd_hi, b.sd_lo, CH_D, b.row, 12, 0.f, 0.f, 0.f, 0.f);
+    uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + b.row * 16;
+    uint4 vh, vm;
+    bf16_split8(d, vh, vm);
+    *reinterpret_cast<uint4*>(db) = vh;
+    *reinterpret_cast<uint4*>(db + ST_PART) = vm;
+    *reinterpret_cast<uint4*>(db + ST_GRP) = make_uint4(0u, 0u, 0u, 0u);   // N = 16: features 8..15 are zero
+    *reinterpret_cast<uint4*>(db + ST_GRP + ST_PART) = make_uint4(0u, 0u, 0u, 0u);
+    tc::wait_st();
   }
-#pragma unroll
-  for (int j4 = 0; j4 < 32; j4 += 4)
-    stage4(b.sa_hi, b.sa_lo, CH_A, b.row, half + j4, b.stash[(size_t)((L - 1) * H + half + j4 + 0) * b.ss],
-           b.stash[(size_t)((L - 1) * H + half + j4 + 1) * b.ss], b.stash[(size_t)((L - 1) * H + half + j4 + 2) * b.ss],
-           b.stash[(size_t)((L - 1) * H + half + j4 + 3) * b.ss]);
-  tc::wait_st();
   tc::fence_proxy_async();
   tc::fence_before_sync();
   HODE_TL(221);
   issue_arrive();   // the issuer warp launches phase L (mlp_bwd_issue) once all 256 threads are here
+  b.ph += 1u;
+  b.k += 1;
   HODE_TL(222);
-  b.wload_parity ^= 1u;
-  b.gemm_parity ^= 1u;
-  HODE_TL(223);
 
-  // ---- phases p = L .. 1 ---------------------------------------------------------------------------------
+  // ---- p = L .. 1: u_{p-1} arrives, delta_{p-1} = u_{p-1} * relu'(a_{p-1}) goes out for phase p-1 ------
 #pragma unroll
   for (int p = MAXL; p >= 1; --p) {
     if (p > L) continue;
+    const uint32_t mask = reinterpret_cast<const uint32_t*>(b.stage_blk + (size_t)(p - 1) * ST_BLK + 2 * ST_PART)[hidx * TILE + b.row];
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
     HODE_TL(230 + 10 * p);
-    // the weight slot is free (its reader was the MMA chain just waited for): prefetch the next block
-    if (p >= 2) fetch_w(2048 + (L - p) * 8192, 8192);
-    else fetch_w(2048 + (L - 1) * 8192, 2048);
+    // everything phase b.ph - 2 read is free now (its MMAs precede the chain just waited for)
+    if (loader) {
+      prefetch_A(b, L, b.k, b.ph);
+      prefetch_W(b, L, b.k + 1, b.ph + 1u);
+    }
     uint32_t u[32];
     HODE_TMEM_LD_X32(t_d, u);
-    float a[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = b.stash[(size_t)((p - 1) * H + half + j) * b.ss];
     tc::wait_ld();
     float d[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) d[j] = a[j] > 0.f ? __uint_as_float(u[j]) : 0.f;
+    for (int j = 0; j < 32; ++j) d[j] = ((mask >> j) & 1u) ? __uint_as_float(u[j]) : 0.f;
     {
       uint32_t hi[16], lo[16];
       split16(d, hi, lo);
@@ -301,36 +312,43 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       HODE_TMEM_ST_X16(t_alo + half + 16, lo);
     }
     HODE_TL(231 + 10 * p);
-    // staging may be rewritten once the previous phase's weight-gradient MMAs are done
-    tc::mbar_wait(b.gemm_bar, b.gemm_parity ^ 1u);
-    HODE_TL(232 + 10 * p);
+    {
+      uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + (hidx * 4) * ST_GRP + b.row * 16;
 #pragma unroll
-    for (int j4 = 0; j4 < 32; j4 += 4) stage4(b.sd_hi, b.sd_lo, CH_D, b.row, half + j4, d[j4], d[j4 + 1], d[j4 + 2], d[j4 + 3]);
-    if (p >= 2) {   // inputs of layer p-1 are a_{p-2}
-#pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4)
-        stage4(b.sa_hi, b.sa_lo, CH_A, b.row, half + j4, b.stash[(size_t)((p - 2) * H + half + j4 + 0) * b.ss],
-               b.stash[(size_t)((p - 2) * H + half + j4 + 1) * b.ss], b.stash[(size_t)((p - 2) * H + half + j4 + 2) * b.ss],
-               b.stash[(size_t)((p - 2) * H + half + j4 + 3) * b.ss]);
-    } else if (MAIN) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
-      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 0, x9[0], x9[1], x9[2], x9[3]);
-      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 4, x9[4], x9[5], x9[6], x9[7]);
-      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 8, x9[8], 0.f, 0.f, 0.f);
-      stage4(b.sa_hi, b.sa_lo, CH_A, b.row, 12, 0.f, 0.f, 0.f, 1.f);
+      for (int g = 0; g < 4; ++g) {
+        uint4 vh, vm;
+        bf16_split8(d + 8 * g, vh, vm);
+        *reinterpret_cast<uint4*>(db + g * ST_GRP) = vh;
+        *reinterpret_cast<uint4*>(db + g * ST_GRP + ST_PART) = vm;
+      }
+    }
+    if (p == 1 && MAIN) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
+      uint8_t* ab = b.smem + OFF_AB + (b.ph & 1u) * AB_BYTES + b.row * 16;
+      const float xb[8] = {x9[8], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+      uint4 vh, vm;
+      bf16_split8(x9, vh, vm);
+      *reinterpret_cast<uint4*>(ab) = vh;
+      *reinterpret_cast<uint4*>(ab + AB_PART) = vm;
+      bf16_split8(xb, vh, vm);
+      *reinterpret_cast<uint4*>(ab + ST_GRP) = vh;
+      *reinterpret_cast<uint4*>(ab + ST_GRP + AB_PART) = vm;
     }
     tc::wait_st();
     tc::fence_proxy_async();
     tc::fence_before_sync();
     HODE_TL(233 + 10 * p);
     issue_arrive();
+    b.ph += 1u;
+    b.k += 1;
     HODE_TL(234 + 10 * p);
-    b.wload_parity ^= 1u;
-    b.gemm_parity ^= 1u;
-    HODE_TL(235 + 10 * p);
   }
   // ---- final phase: g_x -------------------------------------------------------------------------
   tc::mbar_wait(c.mma_bar, c.parity);
   c.parity ^= 1u;
+  if (loader) {   // next stage's phase L
+    prefetch_A(b, L, b.k, b.ph);
+    prefetch_W(b, L, b.k + 1, b.ph + 1u);
+  }
   if (MAIN) {
     tc::fence_after_sync();
     uint32_t v[16];
@@ -417,7 +435,8 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t load_bar;
-  __shared__ __align__(8) uint64_t wload_bar;
+  __shared__ __align__(8) uint64_t wload_bar[2];
+  __shared__ __align__(8) uint64_t aload_bar[2];
   __shared__ __align__(8) uint64_t gemm_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_nmax;
@@ -436,19 +455,17 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   // shared memory: the forward weight image during the recomputation; during the reverse sweep the
   // same bytes hold [weight slot][delta staging hi, lo][input staging hi, lo]
   float* img = reinterpret_cast<float*>(smem_raw);
-  float* wslot = img;
-  float* sd_hi = wslot + WSLOT_FLOATS;
-  float* sd_lo = sd_hi + SD_FLOATS;
-  float* sa_hi = sd_lo + SD_FLOATS;
-  float* sa_lo = sa_hi + SA_FLOATS;
-  const int bwd_cap = WSLOT_FLOATS + 2 * SD_FLOATS + 2 * SA_FLOATS;
+  const int bwd_cap = BWD_BYTES / 4;
   const int img_cap = ((G.fwd_floats > bwd_cap ? G.fwd_floats : bwd_cap) + 255) & ~255;
   float* t_sh_buf = img + img_cap;
-  float* red = sd_hi;   // [17][128] theta-gradient reduction scratch at the very end
+  float* red = img;   // [17][128] theta-gradient reduction scratch at the very end
   if (tid == 0) {
     tc::mbar_init(&mma_bar, 1);
     tc::mbar_init(&load_bar, 1);
-    tc::mbar_init(&wload_bar, 1);
+    tc::mbar_init(&wload_bar[0], 1);
+    tc::mbar_init(&wload_bar[1], 1);
+    tc::mbar_init(&aload_bar[0], 1);
+    tc::mbar_init(&aload_bar[1], 1);
     tc::mbar_init(&gemm_bar, 1);
     tc::fence_mbar_init();
   }
@@ -478,22 +495,23 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
     tc::wait_st();
   }
   uint32_t load_parity = 0;
-  const size_t NT = (size_t)gridDim.x * gridDim.y * TILE;
-  const size_t gt = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE + row;
-  const size_t stage_stride = (size_t)L * H * NT;   // floats between the stash blocks of two stages
-  float* stash0 = G.stash + gt;
+  // this CTA's activation stash: [stage][layer] blocks of ST_BLK bytes (hode_tc_mlp.cuh)
+  const size_t stage_stride = (size_t)L * ST_BLK;
+  uint8_t* stash0 = reinterpret_cast<uint8_t*>(G.stash) +
+                    ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)NSTAGE_MAX * stage_stride;
 
   BwdCtx bc;
-  bc.sd_hi = sd_hi; bc.sd_lo = sd_lo; bc.sa_hi = sa_hi; bc.sa_lo = sa_lo;
-  bc.wslot = wslot;
+  bc.smem = smem_raw;
   bc.wsrc = G.img_bwd + (size_t)s * G.bwd_floats;
-  bc.wload_bar = &wload_bar;
+  bc.stash_cta = stash0;
+  bc.stage_blk = stash0;
+  bc.wload_bar = wload_bar;
+  bc.aload_bar = aload_bar;
   bc.gemm_bar = &gemm_bar;
-  bc.wload_parity = 0; bc.gemm_parity = 0;
+  bc.ph = 0u;
+  bc.k = 0; bc.k_end = 0; bc.stage_top = 0;
   bc.first = 1u;
-  bc.ss = NT;
   bc.row = row;
-  bc.stash = stash0;
 
   const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
   const bool gd_present = A.in_mode[HODE_CH_GD] != HODE_IN_ABSENT;
@@ -505,7 +523,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   // swap the shared-memory weight image (forward <-> transposed); every thread calls it
   auto load_image = [&](const float* src, int floats) {
     // the weight-gradient MMAs of the previous reverse sweep still read the staging arrays
-    tc::mbar_wait(&gemm_bar, bc.gemm_parity ^ 1u);
+    wait_gemm(bc);
     tc::fence_before_sync();
     __syncthreads();   // nobody still reads the old contents (all MMAs that did have been waited for)
     if (tid == 0) {
@@ -519,14 +537,28 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   const float* fwd_src = G.img_fwd + (size_t)s * G.fwd_floats;
   // start of a reverse sweep: the forward image is dead; (re)write the constant features of the
   // input staging (feature 64 = 1 -> bias-gradient column, 65..79 = 0)
+  // input-operand group 8 = [1, 0 x 7]: its accumulator column is the bias gradient), and start
+  // the operand pipeline of the sweep's first phases.  The stash was written with ordinary global
+  // stores and is read back by bulk copies: cross-proxy fence before the barrier.
   auto begin_reverse = [&]() {
+    tc::fence_proxy_async_all();
     tc::fence_before_sync();
     __syncthreads();
     if (main_role) {
-      stage4(sa_hi, sa_lo, CH_A, row, 64, 1.f, 0.f, 0.f, 0.f);
-      stage4(sa_hi, sa_lo, CH_A, row, 68, 0.f, 0.f, 0.f, 0.f);
-      stage4(sa_hi, sa_lo, CH_A, row, 72, 0.f, 0.f, 0.f, 0.f);
-      stage4(sa_hi, sa_lo, CH_A, row, 76, 0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int bf = 0; bf < 2; ++bf) {
+        uint8_t* g8 = smem_raw + OFF_AB + bf * AB_BYTES + 8 * ST_GRP + row * 16;
+        *reinterpret_cast<uint4*>(g8) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(g8 + AB_PART) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    bc.k = 0;
+    bc.k_end = N * (L + 1);
+    bc.stage_top = N - 1;
+    if (tid == 0) {
+      prefetch_W(bc, L, 0, bc.ph);
+      prefetch_A(bc, L, 0, bc.ph);
+      prefetch_W(bc, L, 1, bc.ph + 1u);
     }
   };
 
@@ -571,13 +603,13 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
       if (!main_role) {
         if (helper) {
 #pragma unroll 1
-          for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, NT);
+          for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, row);
         }
         begin_reverse();
 #pragma unroll 1
         for (int i = N - 1; i >= 0; --i) {
           if (helper) {
-            bc.stash = stash0 + (size_t)i * stage_stride;
+            bc.stage_blk = stash0 + (size_t)i * stage_stride;
             mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
           } else {
             mlp_bwd_issue(c, bc);
@@ -676,7 +708,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
         x[7] = ys[3];
         x[8] = tvns;
         __syncwarp();
-        mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, NT);
+        mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, row);
         rhs_mech(th, ys, meal, gd, gd_present, d);
 #pragma unroll
         for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
@@ -772,7 +804,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
         for (int cc = 0; cc < NS; ++cc) x[1 + cc] = ys[cc];
         x[7] = ys[3];
         x[8] = tvi;
-        bc.stash = stash0 + (size_t)i * stage_stride;
+        bc.stage_blk = stash0 + (size_t)i * stage_stride;
         __syncwarp();
         HODE_TL(210);
         mlp_bwd_tile<true>(c, bc, x, gki, gx);
@@ -817,7 +849,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   }
 
   // ---- per-CTA partial gradients: TMEM accumulators -> workspace ---------------------------------
-  tc::mbar_wait(&gemm_bar, bc.gemm_parity ^ 1u);
+  wait_gemm(bc);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -1025,12 +1057,12 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   p.n_tiles = (int)(blocks > 0 ? blocks : 1);
   p.fwd_floats = tc_image_floats(L);
   p.bwd_floats = tc_bwd_image_floats(L);
-  const int bwd_cap = WSLOT_FLOATS + 2 * SD_FLOATS + 2 * SA_FLOATS;
+  const int bwd_cap = BWD_BYTES / 4;
   size_t floats = (size_t)(((p.fwd_floats > bwd_cap ? p.fwd_floats : bwd_cap) + 255) & ~255);
   if (!t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) floats += T;
   p.smem = (floats * sizeof(float) + 1023) & ~(size_t)1023;
   p.partial_floats = (size_t)gx * S * (size_t)(P + HODE_N_THETA);
-  p.stash_floats = (size_t)gx * S * TILE * (size_t)NSTAGE_MAX * L * H;
+  p.stash_floats = (size_t)gx * S * (size_t)NSTAGE_MAX * L * (ST_BLK / 4);
   p.img_floats = (size_t)S * (p.fwd_floats + p.bwd_floats);
   // schedule scratch: sort keys / values (in, out), tile owners, per-CTA tile lists, cub temporaries
   const size_t units = (size_t)S * (size_t)(B > 0 ? B : 0);

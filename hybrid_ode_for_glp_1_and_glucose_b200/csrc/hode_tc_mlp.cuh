@@ -29,7 +29,50 @@ constexpr int H = 64;
 // TMEM columns of one tile:
 //   [0,64) accumulator D | [64,128) A_hi | [128,192) A_lo | [192,200) constant [1,1,0..] (bias step)
 constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_ONES = 192, TM_TILE_STRIDE = 256;
+
+// Activation stash of the adjoint (one block per stage and hidden layer, per CTA): the tile's
+// a_l = relu(z_l) as the BF16 operand image the weight-gradient MMAs read (csrc/probe/bf16_probe.cu),
+//   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2,
+// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to
+// 2^-17), followed by the ReLU masks: word [half][t] = bit j set iff a[32 half + j] > 0.
+constexpr int ST_GRP = 2048;                 // one 8-feature group: 128 trajectories x 16 B
+constexpr int ST_PART = 8 * ST_GRP;          // 64 features
+constexpr int ST_BLK = 2 * ST_PART + 1024;   // hi, mid, masks
 }  // namespace
+
+// x[0..7] -> 8 BF16 hi (round to nearest) and 8 BF16 mid = bf16(x - hi); feature 0 in the low half of word 0
+__device__ __forceinline__ void bf16_split8(const float* v, uint4& hi, uint4& mid) {
+  uint32_t h[4], m[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(v[2 * q + 1]), "f"(v[2 * q]));
+    const float r0 = v[2 * q] - __uint_as_float(h[q] << 16);
+    const float r1 = v[2 * q + 1] - __uint_as_float(h[q] & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m[q]) : "f"(r1), "f"(r0));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  mid = make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+// relu of this thread's 32 accumulator columns [32 half, 32 half + 32) -> stash block `blk`
+__device__ __forceinline__ void stash_store32(uint8_t* blk, int row, int half, const uint32_t* acc) {
+  uint32_t mask = 0u;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = fmaxf(__uint_as_float(acc[8 * g + j]), 0.f);
+      mask |= (a[j] > 0.f ? 1u : 0u) << (8 * g + j);
+    }
+    uint4 hi, mid;
+    bf16_split8(a, hi, mid);
+    uint8_t* p = blk + (half * 4 + g) * ST_GRP + row * 16;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + ST_PART) = mid;
+  }
+  reinterpret_cast<uint32_t*>(blk + 2 * ST_PART)[half * TILE + row] = mask;
+}
 
 // ---- per-tile context -------------------------------------------------------------------------------
 struct TileCtx {
@@ -101,8 +144,8 @@ __device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo) {
 // Every thread of the tile must call this converged.  x: the 9 input features of this thread's
 // trajectory; r: the 6 residuals.
 template <bool X3>
-__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, float* stash = nullptr,
-                                         size_t stash_stride = 0) {
+__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash = nullptr,
+                                         int stash_row = 0) {
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
@@ -154,11 +197,8 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
     HODE_TMEM_LD_X32(t_d, v0);
     tc::wait_ld();
     HODE_TL(11 + 10 * l);
-    if (stash) {   // adjoint: keep a_l = relu(z_l) of this thread's trajectory, columns [0,32)
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        stash[(size_t)(l * H + j) * stash_stride] = fmaxf(__uint_as_float(v0[j]), 0.f);
-    }
+    // adjoint: keep a_l = relu(z_l) of this thread's trajectory, columns [0,32)
+    if (stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 0, v0);
     epilogue16<X3>(v0, lo);
     HODE_TMEM_ST_X16(t_ahi, v0);
     if (X3) HODE_TMEM_ST_X16(t_alo, lo);
@@ -203,7 +243,7 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, f
 // Helper warps: the other half of every hidden-layer epilogue.  Must be called once per
 // mlp_tile() call of the tile's main warps (same number of tile-wide barriers and mbarrier phases).
 template <bool X3>
-__device__ __forceinline__ void mlp_tile_helper(TileCtx& c, float* stash = nullptr, size_t stash_stride = 0) {
+__device__ __forceinline__ void mlp_tile_helper(TileCtx& c, uint8_t* stash = nullptr, int stash_row = 0) {
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + 32;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI + 32;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO + 32;
@@ -215,11 +255,7 @@ __device__ __forceinline__ void mlp_tile_helper(TileCtx& c, float* stash = nullp
     uint32_t v[32], lo[16];
     HODE_TMEM_LD_X32(t_d, v);
     tc::wait_ld();
-    if (stash) {   // columns [32,64)
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        stash[(size_t)(l * H + 32 + j) * stash_stride] = fmaxf(__uint_as_float(v[j]), 0.f);
-    }
+    if (stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 1, v);   // columns [32,64)
     epilogue16<X3>(v, lo);
     HODE_TMEM_ST_X16(t_ahi, v);
     if (X3) HODE_TMEM_ST_X16(t_alo, lo);
