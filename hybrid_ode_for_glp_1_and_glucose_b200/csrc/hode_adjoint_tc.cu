@@ -450,6 +450,13 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   const int s = blockIdx.y, T = A.T, L = A.L;
   const int solver = A.solver == HODE_SOLVER_RK4 ? 0 : 1;
   const int N = solver == 0 ? 4 : 7;
+  // DP5(4) is first-same-as-last: stage 1 of step n+1 IS stage 7 of step n.  The rollout saved its
+  // value (save_k), so the recomputation starts at stage 2, and the reverse sweep pulls the shared
+  // evaluation back once, as stage 7 of the earlier step, with both cotangents added (`carry`).
+  // Stage 1 of the very first step is pulled back by one extra iteration: a zero-length step at
+  // (t0, y0) whose stage 7 receives the carry.
+  const bool fsal = solver == 1 && A.save_k != nullptr;
+  const int i0 = fsal ? 1 : 0;
   const long n_units = (long)A.S * A.B;
 
   // shared memory: the forward weight image during the recomputation; during the reverse sweep the
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
       }
     }
     bc.k = 0;
-    bc.k_end = N * (L + 1);
+    bc.k_end = (N - i0) * (L + 1);
     bc.stage_top = N - 1;
     if (tid == 0) {
       prefetch_W(bc, L, 0, bc.ph);
@@ -595,7 +602,11 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
     for (int i = 0; i < NS; ++i) lam[i] = 0.f;
     int ei = T - 1;
 
-    for (int it = 0; it < nmax; ++it) {
+    float carry[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) carry[i] = 0.f;
+    const int n_iter = nmax + (fsal ? 1 : 0);
+    for (int it = 0; it < n_iter; ++it) {
       // =========================== forward recomputation =========================================
       HODE_TL(200);
       load_image(fwd_src, G.fwd_floats);
@@ -603,11 +614,11 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
       if (!main_role) {
         if (helper) {
 #pragma unroll 1
-          for (int i = 0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, row);
+          for (int i = i0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, row);
         }
         begin_reverse();
 #pragma unroll 1
-        for (int i = N - 1; i >= 0; --i) {
+        for (int i = N - 1; i >= i0; --i) {
           if (helper) {
             bc.stage_blk = stash0 + (size_t)i * stage_stride;
             mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
@@ -618,12 +629,17 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
         continue;
       }
       const int sidx = n - 1 - it;
-      const bool act = ok && sidx >= 0;
+      const bool real = ok && sidx >= 0;
+      const bool act = real || (fsal && ok && sidx == -1);   // sidx == -1: the zero-length step at (t0, y0)
       double t = (double)in.t_obs[0], t_new = t, h = 0.0;
-      float y[NS];
+      float y[NS], k1[NS];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) y[i] = 0.f;
-      if (act) {
+      for (int i = 0; i < NS; ++i) { y[i] = 0.f; k1[i] = 0.f; }
+      if (act && !real && n > 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) y[i] = A.save_y[(size_t)i * n_units + unit];
+      }
+      if (real) {
         const size_t o = (size_t)sidx * n_units + unit;
         t = A.save_t[o];
         if (solver == 0) {
@@ -635,6 +651,10 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
         }
 #pragma unroll
         for (int i = 0; i < NS; ++i) y[i] = A.save_y[((size_t)sidx * NS + i) * n_units + unit];
+        if (fsal) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) k1[i] = A.save_k[((size_t)sidx * NS + i) * n_units + unit];
+        }
       }
       const float hf = (float)h;
       // Inputs of this step as one linear piece per channel (value = c_v1 + alpha * c_dv): valid when a
@@ -675,8 +695,10 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) k[i][cc] = 0.f;
       }
+#pragma unroll
+      for (int cc = 0; cc < NS; ++cc) k[0][cc] = k1[cc];
 #pragma unroll 1
-      for (int i = 0; i < N; ++i) {
+      for (int i = i0; i < N; ++i) {
         float ys[NS];
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) {
@@ -772,10 +794,11 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
           gy[cc] += gnew[cc];
 #pragma unroll
           for (int j = 0; j < 6; ++j) gk[j][cc] = fmaf(hf * kB[1][j], gnew[cc], gk[j][cc]);
+          gk[6][cc] += carry[cc];   // stage 1 of the next step = this step's stage 7 (zero unless fsal)
         }
       }
 #pragma unroll 1
-      for (int i = N - 1; i >= 0; --i) {
+      for (int i = N - 1; i >= i0; --i) {
         float ys[NS], gys[NS], gki[NS];
         float tvi = 0.f, gdi = 0.f;
 #pragma unroll
@@ -822,6 +845,10 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
       if (act) {
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) lam[cc] = gy[cc];
+      }
+      if (fsal) {
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) carry[cc] = real ? gk[0][cc] : 0.f;
       }
       HODE_TL(204);
     }

@@ -26,7 +26,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_n, off_t, off_h, off_y, off_tc, total;
+  size_t off_n, off_t, off_h, off_y, off_k, off_tc, total;
   int max_saved;
 };
 
@@ -52,6 +52,10 @@ Workspace fwd_workspace(const hode_cfg* c) {
     w.off_t = off; off = align_up(off + units * w.max_saved * sizeof(double), 256);
     w.off_h = off; off = align_up(off + units * w.max_saved * sizeof(float), 256);
     w.off_y = off; off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
+    // first stage derivative of every step: the tensor-core DP5(4) adjoint reuses it (FSAL)
+    w.off_k = off;
+    if (uses_tensor_cores(c) && c->solver != HODE_SOLVER_RK4)
+      off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
   }
   if (uses_tensor_cores(c)) {
     // pre-split weight images (one per parameter set) + the per-set trajectory queue counters
@@ -190,6 +194,7 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
     A.save_t = (double*)(base + w.off_t);
     A.save_h = (float*)(base + w.off_h);
     A.save_y = (float*)(base + w.off_y);
+    A.save_k = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? (float*)(base + w.off_k) : nullptr;
     A.max_saved = w.max_saved;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -234,6 +239,7 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   A.save_t = (double*)(base + w.off_t);
   A.save_h = (float*)(base + w.off_h);
   A.save_y = (float*)(base + w.off_y);
+  A.save_k = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? (float*)(base + w.off_k) : nullptr;
   A.max_saved = w.max_saved;
   // forward on the tensor cores -> adjoint on the tensor cores (3xTF32); FP32 forward -> FP32 adjoint
   cudaError_t e = tc_adj ? hode::launch_rollout_bwd_tc(A, grad_traj, grad_y0, grad_theta, grad_W, bwd_workspace,

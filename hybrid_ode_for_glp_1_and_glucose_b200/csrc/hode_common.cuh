@@ -29,6 +29,7 @@ struct RolloutArgs {
   double* save_t;       // start time of accepted step n
   float* save_h;        // step size
   float* save_y;        // [max_saved][6][S*B] state at step start
+  float* save_k;        // [max_saved][6][S*B] first stage derivative of the step (tensor-core DP5(4) rollout only, else NULL)
   int32_t* save_n;      // [S*B] number of saved steps
   int32_t max_saved;
   int32_t B, T, S;

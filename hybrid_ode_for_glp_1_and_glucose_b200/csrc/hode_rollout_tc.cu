@@ -237,13 +237,18 @@ __device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A, int 
   ln.unit = -1;
 }
 
-__device__ __forceinline__ void lane_save_step(Lane& ln, const RolloutArgs& A, double t, float hf) {
+// k1: the step's first stage derivative (DP5(4): the adjoint reuses it instead of recomputing it — FSAL)
+__device__ __forceinline__ void lane_save_step(Lane& ln, const RolloutArgs& A, double t, float hf, const float* k1 = nullptr) {
   const long n_units = (long)A.S * A.B;
   const size_t o = (size_t)ln.n_saved * n_units + ln.unit;
   A.save_t[o] = t;
   A.save_h[o] = hf;
 #pragma unroll
   for (int i = 0; i < NS; ++i) A.save_y[((size_t)ln.n_saved * NS + i) * n_units + ln.unit] = ln.y[i];
+  if (k1 && A.save_k) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) A.save_k[((size_t)ln.n_saved * NS + i) * n_units + ln.unit] = k1[i];
+  }
   ++ln.n_saved;
 }
 
@@ -689,7 +694,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             ++ln.n_acc;
             bool ok = true;
             if (A.save_n) {
-              if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
+              if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf, k[0]);
               else { ln.status = HODE_ST_MAX_STEPS; ok = false; }
             }
             if (ok) {
