@@ -431,7 +431,7 @@ struct AdjTcArgs {
 // ---------------------------------------------------------------------------------------------------
 // grid = (ctas per parameter set, S), block = 256 (4 main + 4 helper warps), 1 CTA / SM
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
+__global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t load_bar;
@@ -572,19 +572,72 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   const int32_t* my_tiles = G.sched_tiles + (size_t)s * G.n_tiles;
   const int tile_beg = G.sched_off[(size_t)s * (gridDim.x + 1) + blockIdx.x];
   const int tile_end = G.sched_off[(size_t)s * (gridDim.x + 1) + blockIdx.x + 1];
+  // nmax of a tile: every thread of the CTA passes here (two CTA-wide barriers)
+  auto tile_nmax = [&](int n_) -> int {
+    if (tid == 0) s_nmax = 0;
+    __syncthreads();
+    if (n_ > 0) atomicMax(&s_nmax, n_);
+    __syncthreads();
+    return s_nmax;
+  };
+
+  // Three roles, each entirely inside its own branch so that ptxas allocates registers against
+  // the role's budget: the main warpgroup carries the per-trajectory integrator and adjoint state
+  // (it takes the registers the other two warpgroups give back), the helper warpgroup only runs
+  // epilogue halves, the third warpgroup holds the MMA-issuer warp (its other three warps idle
+  // through the CTA-wide barriers: setmaxnreg works on whole warpgroups).
+  if (helper) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;" ::: "memory");
+  for (int tk = tile_beg; tk < tile_end; ++tk) {
+    const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+    for (int it = 0; it < n_iter; ++it) {
+      load_image(fwd_src, G.fwd_floats);
+#pragma unroll 1
+      for (int i = i0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, row);
+      begin_reverse();
+#pragma unroll 1
+      for (int i = N - 1; i >= i0; --i) {
+        bc.stage_blk = stash0 + (size_t)i * stage_stride;
+        mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
+      }
+    }
+  }
+  wait_gemm(bc);
+  tc::fence_before_sync();
+  __syncthreads();   // accumulators complete
+  __syncthreads();   // theta-gradient scratch written
+  tc::fence_before_sync();
+  __syncthreads();   // TMEM may be released
+  } else if (!main_role) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+  for (int tk = tile_beg; tk < tile_end; ++tk) {
+    const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+    for (int it = 0; it < n_iter; ++it) {
+      load_image(fwd_src, G.fwd_floats);
+      begin_reverse();
+      if (issuer) {
+#pragma unroll 1
+        for (int i = N - 1; i >= i0; --i) mlp_bwd_issue(c, bc);
+      }
+    }
+  }
+  wait_gemm(bc);
+  tc::fence_before_sync();
+  __syncthreads();   // accumulators complete
+  __syncthreads();   // theta-gradient scratch written
+  tc::fence_before_sync();
+  __syncthreads();   // TMEM may be released
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
   for (int tk = tile_beg; tk < tile_end; ++tk) {
     const long q = (long)my_tiles[tk] * TILE + row;   // slot in the step-count-sorted order
     const bool valid = q < A.B;
     const long unit = valid ? (long)G.perm[(size_t)s * A.B + q] : (long)s * A.B;
     const long bs = unit - (long)s * A.B;
-    int n = (valid && main_role) ? A.save_n[unit] : 0;
+    int n = valid ? A.save_n[unit] : 0;
     const bool ok = valid && n >= 0;
     if (n < 0) n = 0;
-    if (tid == 0) s_nmax = 0;
-    __syncthreads();
-    if (n > 0) atomicMax(&s_nmax, n);
-    __syncthreads();
-    const int nmax = s_nmax;
+    const int nmax = tile_nmax(n);
 
     TrajInputs in;
     in.T = T; in.cur = 0;
@@ -611,23 +664,6 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
       HODE_TL(200);
       load_image(fwd_src, G.fwd_floats);
       HODE_TL(201);
-      if (!main_role) {
-        if (helper) {
-#pragma unroll 1
-          for (int i = i0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, row);
-        }
-        begin_reverse();
-#pragma unroll 1
-        for (int i = N - 1; i >= i0; --i) {
-          if (helper) {
-            bc.stage_blk = stash0 + (size_t)i * stage_stride;
-            mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
-          } else {
-            mlp_bwd_issue(c, bc);
-          }
-        }
-        continue;
-      }
       const int sidx = n - 1 - it;
       const bool real = ok && sidx >= 0;
       const bool act = real || (fsal && ok && sidx == -1);   // sidx == -1: the zero-length step at (t0, y0)
@@ -852,7 +888,7 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
       }
       HODE_TL(204);
     }
-    if (main_role) {
+    {
       if (ok) {
         if (solver == 0) {
 #pragma unroll
@@ -947,7 +983,8 @@ __global__ void __launch_bounds__(2 * TILE + 32, 1) rollout_bwd_tc_kernel(const 
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+  }
 }
 
 // ---- transposed weight image --------------------------------------------------------------------------
@@ -1169,7 +1206,7 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, 
   }
   e = cudaFuncSetAttribute(rollout_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return e;
-  rollout_bwd_tc_kernel<<<dim3(p.grid_x, p.grid_y), 2 * TILE + 32, p.smem, stream>>>(G);
+  rollout_bwd_tc_kernel<<<dim3(p.grid_x, p.grid_y), 3 * TILE, p.smem, stream>>>(G);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_reduce_partials(G.partials, p.grid_x, A.S, A.P, grad_W, grad_theta, stream);
