@@ -195,12 +195,24 @@ __device__ __forceinline__ void prefetch_W(const BwdCtx& b, int L, int k2, uint3
 // The MMAs of the reverse sweep are issued by a dedicated warp: tcgen05.mma issue blocks while the
 // tensor pipe is busy, and a warp that also runs an epilogue would hold the whole tile back for
 // that long.  The 256 epilogue threads only ARRIVE on the named barrier; the issuer warp waits on it.
-constexpr int ISSUE_BAR = 3, ISSUE_BAR_THREADS = 2 * TILE + 32;
+// Two barriers per phase: the u-chain only needs delta in TMEM, the weight-gradient MMAs also need the
+// BF16 operand images, which the threads write while the u-chain already runs.  The second barrier
+// alternates between two ids by phase parity: a fast thread can reach its arrival of phase ph + 1
+// while the issuer still waits for a slow thread's arrival of phase ph (nothing orders the two), and
+// on one id the counts would mix.  (On the first barrier they cannot: the u-chain whose completion
+// lets a thread move on is only issued after that barrier has completed.)
+constexpr int ISSUE_BAR = 3, ISSUE_BAR_DW = 4, ISSUE_BAR_THREADS = 2 * TILE + 32;
 __device__ __forceinline__ void issue_arrive() {
   asm volatile("bar.arrive %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
 }
 __device__ __forceinline__ void issue_wait() {
   asm volatile("bar.sync %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
+}
+__device__ __forceinline__ void issue_arrive_dw(uint32_t ph) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(ISSUE_BAR_DW + (int)(ph & 1u)), "n"(ISSUE_BAR_THREADS) : "memory");
+}
+__device__ __forceinline__ void issue_wait_dw(uint32_t ph) {
+  asm volatile("bar.sync %0, %1;" ::"r"(ISSUE_BAR_DW + (int)(ph & 1u)), "n"(ISSUE_BAR_THREADS) : "memory");
 }
 
 // Issuer warp: the MMA chains of one stage of the reverse sweep, mirroring mlp_bwd_tile's phases.
@@ -225,6 +237,7 @@ __device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
       tc::mma_commit(c.mma_bar);
     }
     __syncwarp();
+    issue_wait_dw(b.ph);
     tc::mbar_wait(b.aload_bar + buf, par);
     if (tc::elect_one()) {
       // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
@@ -265,6 +278,9 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     split16(d, hi, lo);
     HODE_TMEM_ST_X16(t_ahi, hi);
     HODE_TMEM_ST_X16(t_alo, lo);
+    tc::wait_st();
+    tc::fence_before_sync();
+    issue_arrive();   // the issuer warp launches the u-chain of phase L once all 256 threads are here
     uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + b.row * 16;
     uint4 vh, vm;
     bf16_split8(d, vh, vm);
@@ -272,12 +288,13 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     *reinterpret_cast<uint4*>(db + ST_PART) = vm;
     *reinterpret_cast<uint4*>(db + ST_GRP) = make_uint4(0u, 0u, 0u, 0u);   // N = 16: features 8..15 are zero
     *reinterpret_cast<uint4*>(db + ST_GRP + ST_PART) = make_uint4(0u, 0u, 0u, 0u);
-    tc::wait_st();
+    tc::fence_proxy_async();
+  } else {
+    tc::fence_before_sync();
+    issue_arrive();
   }
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
   HODE_TL(221);
-  issue_arrive();   // the issuer warp launches phase L (mlp_bwd_issue) once all 256 threads are here
+  issue_arrive_dw(b.ph);   // ... and its weight-gradient MMAs once the BF16 operand is written
   b.ph += 1u;
   b.k += 1;
   HODE_TL(222);
@@ -311,6 +328,9 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       HODE_TMEM_ST_X16(t_ahi + half + 16, hi);
       HODE_TMEM_ST_X16(t_alo + half + 16, lo);
     }
+    tc::wait_st();
+    tc::fence_before_sync();
+    issue_arrive();
     HODE_TL(231 + 10 * p);
     {
       uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + (hidx * 4) * ST_GRP + b.row * 16;
@@ -333,11 +353,9 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       *reinterpret_cast<uint4*>(ab + ST_GRP) = vh;
       *reinterpret_cast<uint4*>(ab + ST_GRP + AB_PART) = vm;
     }
-    tc::wait_st();
     tc::fence_proxy_async();
-    tc::fence_before_sync();
     HODE_TL(233 + 10 * p);
-    issue_arrive();
+    issue_arrive_dw(b.ph);
     b.ph += 1u;
     b.k += 1;
     HODE_TL(234 + 10 * p);

@@ -54,15 +54,16 @@ __device__ __forceinline__ void bf16_split8(const float* v, uint4& hi, uint4& mi
   mid = make_uint4(m[0], m[1], m[2], m[3]);
 }
 
-// relu of this thread's 32 accumulator columns [32 half, 32 half + 32) -> stash block `blk`
-__device__ __forceinline__ void stash_store32(uint8_t* blk, int row, int half, const uint32_t* acc) {
+// this thread's 32 activations a = relu(z) of columns [32 half, 32 half + 32), given as the TF32
+// hi / lo parts the epilogue produced (a = hi + lo exactly) -> stash block `blk`
+__device__ __forceinline__ void stash_store32(uint8_t* blk, int row, int half, const uint32_t* hi_, const uint32_t* lo_) {
   uint32_t mask = 0u;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a[j] = fmaxf(__uint_as_float(acc[8 * g + j]), 0.f);
+      a[j] = __uint_as_float(hi_[8 * g + j]) + __uint_as_float(lo_[8 * g + j]);
       mask |= (a[j] > 0.f ? 1u : 0u) << (8 * g + j);
     }
     uint4 hi, mid;
@@ -193,18 +194,16 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
     HODE_TL(10 + 10 * l);
     // the main warp owns accumulator columns [0,32) of its 32 lanes, the helper warp of the same
     // lane quarter columns [32,64) (mlp_tile_helper): the epilogue latency per layer is halved
-    uint32_t v0[32], lo[16];
+    uint32_t v0[32], lo[32];
     HODE_TMEM_LD_X32(t_d, v0);
     tc::wait_ld();
     HODE_TL(11 + 10 * l);
-    // adjoint: keep a_l = relu(z_l) of this thread's trajectory, columns [0,32)
-    if (stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 0, v0);
     epilogue16<X3>(v0, lo);
     HODE_TMEM_ST_X16(t_ahi, v0);
     if (X3) HODE_TMEM_ST_X16(t_alo, lo);
-    epilogue16<X3>(v0 + 16, lo);
+    epilogue16<X3>(v0 + 16, lo + 16);
     HODE_TMEM_ST_X16(t_ahi + 16, (v0 + 16));
-    if (X3) HODE_TMEM_ST_X16(t_alo + 16, lo);
+    if (X3) HODE_TMEM_ST_X16(t_alo + 16, (lo + 16));
     tc::wait_st();
     tc::fence_before_sync();
     HODE_TL(12 + 10 * l);
@@ -220,6 +219,9 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
       }
       __syncwarp();
     }
+    // adjoint: a_l = relu(z_l) of this thread's trajectory, columns [0,32), goes to the stash AFTER
+    // the next layer's MMAs have been issued (off the critical path)
+    if (X3 && stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 0, v0, lo);
     HODE_TL(14 + 10 * l);
     w_off += 2 * 4096;
   }
@@ -252,19 +254,19 @@ __device__ __forceinline__ void mlp_tile_helper(TileCtx& c, uint8_t* stash = nul
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
-    uint32_t v[32], lo[16];
+    uint32_t v[32], lo[32];
     HODE_TMEM_LD_X32(t_d, v);
     tc::wait_ld();
-    if (stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 1, v);   // columns [32,64)
     epilogue16<X3>(v, lo);
     HODE_TMEM_ST_X16(t_ahi, v);
     if (X3) HODE_TMEM_ST_X16(t_alo, lo);
-    epilogue16<X3>(v + 16, lo);
+    epilogue16<X3>(v + 16, lo + 16);
     HODE_TMEM_ST_X16(t_ahi + 16, (v + 16));
-    if (X3) HODE_TMEM_ST_X16(t_alo + 16, lo);
+    if (X3) HODE_TMEM_ST_X16(t_alo + 16, (lo + 16));
     tc::wait_st();
     tc::fence_before_sync();
     tile_sync_all(c);
+    if (X3 && stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 1, v, lo);   // columns [32,64)
   }
   // the output layer's phase: nothing to read, but the phase must be observed so that the next
   // call's first wait cannot be satisfied by a stale parity
