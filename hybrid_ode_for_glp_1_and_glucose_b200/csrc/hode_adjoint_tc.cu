@@ -1,21 +1,28 @@
-// hode_adjoint_tc.cu — discrete adjoint of the rollout with the MLP forward recomputation and the
-// delta back-propagation on the tcgen05 tensor cores (BASELINE.json north_star item 3).
+// hode_adjoint_tc.cu — discrete adjoint of the rollout with the MLP forward recomputation, the delta
+// back-propagation and the weight gradients on the tcgen05 tensor cores (BASELINE.json north_star item 3).
 //
 // Same mathematics as hode_adjoint_simt.cu (autograd through the unrolled RK steps with the step
-// sizes frozen); what changes is where the 13 248-MAC network products run:
-//   * one tile of 128 trajectories per CTA: 4 main warps (one trajectory per thread: integrator
-//     state, mechanistic VJP, stage recurrences) + 4 helper warps (the other half of every epilogue);
+// sizes frozen); what changes is where the 13 248-MAC network products run and how the work is laid out:
+//   * schedule (device side, deterministic): trajectories are radix-sorted by accepted-step count,
+//     cut into 128-trajectory tiles, and the tiles are dealt to the CTAs longest-first — a tile runs
+//     for the maximum step count of its members, and adaptive step counts differ several-fold;
+//   * one tile per CTA at a time, three warpgroups with their own register budgets (setmaxnreg):
+//     4 main warps (one trajectory per thread: integrator state, mechanistic VJP, stage recurrences),
+//     4 helper warps (the other half of every epilogue), 1 MMA-issuer warp;
 //   * per accepted step, in reverse:  (1) the forward weight image is bulk-copied into shared
-//     memory and the N stages are recomputed with hode_tc_mlp.cuh's mlp_tile, each hidden
-//     activation going to a per-trajectory stash column in global memory;
+//     memory and the stages are recomputed with hode_tc_mlp.cuh's mlp_tile (3xTF32); every hidden
+//     activation goes to a per-CTA stash in global memory, already in the BF16 operand layout of the
+//     weight-gradient MMAs.  DP5(4) is first-same-as-last: the rollout saved k1 of every step, so 6
+//     stages are recomputed and pulled back per step instead of 7;
 //     (2) every stage is pulled back: u_{l-1} = delta_l W_l is a [128 x 64] x [64 x 64] 3xTF32 MMA
-//     chain with delta in TMEM and W_l^T streamed layer by layer into a shared-memory slot by the
-//     TMA engine (tcgen05 kind::tf32 takes K-major operands only — csrc/probe/adj_probe.cu — so
-//     W^T needs its own image); delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue;
-//   * dW_l += delta_l^T [a_{l-1} | 1] (contraction over the tile's 128 trajectories) runs on the
-//     tensor cores too: SS-form MMAs over operands that every thread writes TRANSPOSED into the
-//     canonical K-major layout; the accumulators stay in TMEM for the whole kernel, so every
-//     gradient element is summed in one fixed order (no atomics, bit-reproducible);
+//     chain with delta in TMEM and W_l^T streamed layer by layer into a double-buffered slot by the
+//     TMA engine (kind::tf32 takes K-major operands only — csrc/probe/adj_probe.cu — so W^T needs its
+//     own image); delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue (stashed ReLU bit masks);
+//   * dW_l += delta_l^T [a_{l-1} | 1] (contraction over the tile's 128 trajectories) is an SS-form
+//     kind::f16 MMA over MN-major BF16 operands (csrc/probe/bf16_probe.cu), two-term split, 3 passes:
+//     the stashed activations come back by bulk copy, delta is written by its owner threads as
+//     16-byte vectors; the accumulators stay in TMEM for the whole kernel, so every gradient element
+//     is summed in one fixed order (no atomics, bit-reproducible);
 //   * per-CTA partial gradients -> workspace -> reduce_partials (hode_adjoint_simt.cu), in CTA order.
 // Restrictions: nn_hidden == 64, nn_layers <= 4 (the TMEM accumulator map is compiled for them);
 // other shapes use the FP32 adjoint.
@@ -258,8 +265,11 @@ __device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
 // g6 (main): cotangent of the 6 network outputs; x9 (main): the stage's input features;
 // gx (main, out): cotangent of the 9 input features.
 // Notation: delta_l = cotangent of the pre-activation of layer l (l = 0..L-1), delta_L = g.
-template <bool MAIN>
-__device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float* x9, const float* g6, float* gx) {
+// `overlap` runs after phase L has been handed to the issuer: per-thread work that does not depend on
+// the network's cotangents (the mechanistic VJP) hides behind the first MMA chain.
+template <bool MAIN, class F>
+__device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float* x9, const float* g6, float* gx,
+                                             F&& overlap) {
   constexpr int half = MAIN ? 0 : 32;
   constexpr int hidx = MAIN ? 0 : 1;
   const int L = c.L;
@@ -298,6 +308,8 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   b.ph += 1u;
   b.k += 1;
   HODE_TL(222);
+  overlap();
+  __syncwarp();   // reconverge after per-thread code: tcgen05 .sync.aligned instructions follow
 
   // ---- p = L .. 1: u_{p-1} arrives, delta_{p-1} = u_{p-1} * relu'(a_{p-1}) goes out for phase p-1 ------
 #pragma unroll
@@ -616,7 +628,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
 #pragma unroll 1
       for (int i = N - 1; i >= i0; --i) {
         bc.stage_blk = stash0 + (size_t)i * stage_stride;
-        mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr);
+        mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr, [] {});
       }
     }
   }
@@ -784,8 +796,13 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         x[7] = ys[3];
         x[8] = tvns;
         __syncwarp();
+#ifdef HODE_NO_OVERLAP_F
         mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, row);
         rhs_mech(th, ys, meal, gd, gd_present, d);
+#else
+        mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, row,
+                       [&] { rhs_mech(th, ys, meal, gd, gd_present, d); });
+#endif
 #pragma unroll
         for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
           if (jj == i) {
@@ -874,7 +891,6 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         }
         const float ci = kC[solver][i];
         const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
-        mech_vjp(th, ys, gdi, gd_present, gki, gys, gth);
         float x[HODE_NN_IN], gx[HODE_NN_IN];
         x[0] = (float)te;
 #pragma unroll
@@ -884,7 +900,12 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         bc.stage_blk = stash0 + (size_t)i * stage_stride;
         __syncwarp();
         HODE_TL(210);
-        mlp_bwd_tile<true>(c, bc, x, gki, gx);
+#ifdef HODE_NO_OVERLAP_B
+        mech_vjp(th, ys, gdi, gd_present, gki, gys, gth);
+        mlp_bwd_tile<true>(c, bc, x, gki, gx, [] {});
+#else
+        mlp_bwd_tile<true>(c, bc, x, gki, gx, [&] { mech_vjp(th, ys, gdi, gd_present, gki, gys, gth); });
+#endif
         HODE_TL(211);
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];
@@ -1059,12 +1080,17 @@ __global__ void adj_sort_keys_kernel(const int32_t* __restrict__ save_n, uint32_
 __global__ void __launch_bounds__(256) adj_schedule_kernel(const uint32_t* __restrict__ keys, int B, int n_tiles, int gx,
                                                            int sorted, int32_t* __restrict__ owner,
                                                            int32_t* __restrict__ sched_off, int32_t* __restrict__ sched_tiles) {
+  constexpr int COST_CACHE = 4096;
   __shared__ int cnt[256];
   __shared__ int off[257];
+  __shared__ unsigned cost_sh[COST_CACHE];   // tile costs, fetched in parallel (the greedy loop is serial)
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const uint32_t* k = keys + (size_t)s * B;
   int32_t* own = owner + (size_t)s * n_tiles;
   cnt[tid] = 0;
+  if (sorted)
+    for (int t = tid; t < n_tiles && t < COST_CACHE; t += blockDim.x)
+      cost_sh[t] = 1u + SORT_N_MASK - (k[(size_t)t * TILE] & SORT_N_MASK);
   __syncthreads();
   if (tid < 32) {
     unsigned load[8];   // CTA x = lane + 32 * slot
@@ -1074,7 +1100,7 @@ __global__ void __launch_bounds__(256) adj_schedule_kernel(const uint32_t* __res
       // cost = iterations of the tile (its largest step count; the slots are sorted descending) + 1
       unsigned cost = 1u;
       if (sorted) {
-        cost += SORT_N_MASK - (k[(size_t)t * TILE] & SORT_N_MASK);
+        cost = t < COST_CACHE ? cost_sh[t] : 1u + SORT_N_MASK - (k[(size_t)t * TILE] & SORT_N_MASK);
       } else {   // unsorted fallback: scan the tile
         unsigned m = 0;
         for (int r = lane; r < TILE && (size_t)t * TILE + r < (size_t)B; r += 32) m = max(m, k[(size_t)t * TILE + r]);

@@ -173,8 +173,8 @@ __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln,
   x[7] = ys[3];
   x[8] = tvns;
   __syncwarp();
-  mlp_tile<X3>(c, x, r);
-  rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d);
+  mlp_tile<X3>(c, x, r, nullptr, 0,
+               [&] { rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d); });
 #pragma unroll
   for (int i = 0; i < NS; ++i) d[i] = __fadd_rn(d[i], r[i]);
 }

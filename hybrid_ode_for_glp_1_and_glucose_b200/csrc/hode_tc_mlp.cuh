@@ -143,10 +143,11 @@ __device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo) {
 
 // The residual MLP for the 128 trajectories of a tile (reference models/nn_residual.py:136-146).
 // Every thread of the tile must call this converged.  x: the 9 input features of this thread's
-// trajectory; r: the 6 residuals.
-template <bool X3>
-__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash = nullptr,
-                                         int stash_row = 0) {
+// trajectory; r: the 6 residuals.  `overlap` runs right after the layer-0 MMAs have been issued: per-thread
+// work that does not depend on the network (the mechanistic RHS) hides behind their latency.
+template <bool X3, class F>
+__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash, int stash_row,
+                                         F&& overlap) {
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
@@ -170,7 +171,10 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
   tc::wait_st();
   tc::fence_before_sync();
   HODE_TL(1);
-  tile_sync(c);
+  // main AND helper warps: the helpers arrive here only after they have observed the previous
+  // call's last mbarrier phase, so the layer-0 commit below cannot flip the barrier a second time
+  // under a helper that is still busy (it would then wait for a phase that has already passed)
+  tile_sync_all(c);
   HODE_TL(2);
   if (c.wq == 0) {
     if (tc::elect_one()) {
@@ -181,6 +185,9 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
     __syncwarp();
   }
   HODE_TL(3);
+  overlap();
+  __syncwarp();   // per-thread code may leave the warp diverged (division slow paths); the tcgen05 .sync.aligned
+                  // instructions below need it converged
   uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
   // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
 #pragma unroll 1
@@ -242,6 +249,12 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
   // D only after a tile barrier that every thread reaches after its wait::ld above.
 }
 
+template <bool X3>
+__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash = nullptr,
+                                         int stash_row = 0) {
+  mlp_tile<X3>(c, x, r, stash, stash_row, [] {});
+}
+
 // Helper warps: the other half of every hidden-layer epilogue.  Must be called once per
 // mlp_tile() call of the tile's main warps (same number of tile-wide barriers and mbarrier phases).
 template <bool X3>
@@ -249,6 +262,7 @@ __device__ __forceinline__ void mlp_tile_helper(TileCtx& c, uint8_t* stash = nul
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + 32;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI + 32;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO + 32;
+  tile_sync_all(c);   // pairs with the main warps' barrier before the layer-0 MMAs (see mlp_tile)
 #pragma unroll 1
   for (int l = 0; l < c.L; ++l) {
     tc::mbar_wait(c.mma_bar, c.parity);
