@@ -50,10 +50,11 @@ WORKLOADS = {
     # 262 144 trajectories (the config's whole cohort on ONE GPU; weak scaling over N)
     "hybrid_fwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip",
                        nn=True, name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd, 262144 traj/GPU, T=61"),
-    # the same with the discrete adjoint (hode_rollout_bwd): 32 768 trajectories per GPU as in
-    # configs/default.yaml on 8 GPUs (262 144 / 8)
-    "hybrid_fwdbwd": dict(B=32768, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip", nn=True, bwd=True,
-                          name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd+adjoint, 32768 traj/GPU, T=61"),
+    # the same with the discrete adjoint (hode_rollout_bwd), same cohort per GPU.  (--traj-per-gpu 32768 is
+    # configs/default.yaml's 262 144 trajectories strong-scaled over 8 GPUs: both kernels are then bound by
+    # the latency of the longest trajectories — 221 trajectories per SM — rather than by throughput.)
+    "hybrid_fwdbwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip", nn=True, bwd=True,
+                          name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd+adjoint, 262144 traj/GPU, T=61"),
     # configs/ablation_no_nn.yaml-shaped: mechanistic only, RK4, 4 substeps per 5-min interval
     "mech_rk4": dict(B=1048576, T=61, solver="rk4", n_substeps=4, nn=False,
                      name="ablation_no_nn mechanistic rk4 4 substeps, 1048576 traj/GPU, T=61"),
@@ -308,7 +309,7 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / n, out
-        Bx = min(B, 32768)
+        Bx = min(B, 262144)
         sl = slice(0, Bx)
         x_ins = {k: v[sl].contiguous() for k, v in d_ins.items()}
         x_g = torch.full((Bx, T, 6), 1.0 / (Bx * T * 6), dtype=torch.float32, device=dev)

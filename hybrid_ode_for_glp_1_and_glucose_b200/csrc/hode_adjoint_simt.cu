@@ -524,17 +524,16 @@ __global__ void __launch_bounds__(ABLK, 1) rollout_bwd_kernel(const AdjArgs G) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) y[i] = 0.f;
       if (act) {
-        const size_t o = (size_t)sidx * n_units + unit;
-        t = A.save_t[o];
+        const float* rec = step_rec(A, unit, sidx);
+        float h_rec;
+        step_rec_load(rec, t, h_rec, y, nullptr);
         if (SOLVER == HODE_SOLVER_RK4) {
-          h = (double)A.save_h[o];
+          h = (double)h_rec;
           t_new = t + h;
         } else {
-          t_new = (sidx + 1 < n) ? A.save_t[o + n_units] : t_bound;
+          t_new = (sidx + 1 < n) ? step_rec_t(rec + HODE_REC_FLOATS) : t_bound;
           h = t_new - t;
         }
-#pragma unroll
-        for (int i = 0; i < NS; ++i) y[i] = A.save_y[((size_t)sidx * NS + i) * n_units + unit];
       }
       const float hf = (float)h;
       // input cursor: grid points known to be < any stage time of this step (one point of slack)

@@ -222,14 +222,17 @@ __device__ __forceinline__ void issue_wait_dw(uint32_t ph) {
   asm volatile("bar.sync %0, %1;" ::"r"(ISSUE_BAR_DW + (int)(ph & 1u)), "n"(ISSUE_BAR_THREADS) : "memory");
 }
 
-// Issuer warp: the MMA chains of one stage of the reverse sweep, mirroring mlp_bwd_tile's phases.
-__device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
+// Issuer warp: the MMA chains of one stage of the reverse sweep, mirroring mlp_bwd_tile's phases, and the
+// operand pipeline: once the u-chain of phase ph has completed, everything phase ph - 1 read is free
+// (its MMAs precede that chain), so the input operand of phase ph + 1 and W^T of phase ph + 2 are fetched.
+__device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
   const int L = c.L;
   const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
   const uint32_t base = tc::smem_u32(b.smem);
-#pragma unroll
-  for (int q = MAXL; q >= 0; --q) {
-    if (q > L) continue;
+  // (runtime loops here and in mlp_bwd_tile: unrolled over the phases the kernel outgrows the
+  // instruction cache — three roles run three different code streams on one SM)
+#pragma unroll 1
+  for (int q = L; q >= 0; --q) {
     const uint32_t buf = b.ph & 1u, par = (b.ph >> 1) & 1u;
     const uint32_t ws = base + OFF_WS + buf * WS_BYTES;
     const uint32_t a_hi = base + OFF_AB + buf * AB_BYTES, a_mid = a_hi + AB_PART;
@@ -244,6 +247,8 @@ __device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
       tc::mma_commit(c.mma_bar);
     }
     __syncwarp();
+    const uint32_t u_parity = c.parity;
+    c.parity ^= 1u;
     issue_wait_dw(b.ph);
     tc::mbar_wait(b.aload_bar + buf, par);
     if (tc::elect_one()) {
@@ -252,6 +257,12 @@ __device__ __forceinline__ void mlp_bwd_issue(const TileCtx& c, BwdCtx& b) {
       else if (q >= 1) issue_dw<64, 72>(c.tmem + DW_H0 + 80u * (uint32_t)(q - 1), d_hi, d_mid, a_hi, a_mid, b.first);
       else issue_dw<64, 16>(c.tmem + DW_0, d_hi, d_mid, a_hi, a_mid, b.first);
       tc::mma_commit(b.gemm_bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(c.mma_bar, u_parity);
+    if ((threadIdx.x & 31) == 0) {
+      prefetch_A(b, L, b.k + 1, b.ph + 1u);
+      prefetch_W(b, L, b.k + 2, b.ph + 2u);
     }
     __syncwarp();
     b.ph += 1u;
@@ -276,7 +287,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
-  const bool loader = MAIN && threadIdx.x == 0;
 
   // ---- prologue: delta_L = g; phase L (its input operand and W^T slot are already on their way) ------
   HODE_TL(220);
@@ -312,19 +322,13 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   __syncwarp();   // reconverge after per-thread code: tcgen05 .sync.aligned instructions follow
 
   // ---- p = L .. 1: u_{p-1} arrives, delta_{p-1} = u_{p-1} * relu'(a_{p-1}) goes out for phase p-1 ------
-#pragma unroll
-  for (int p = MAXL; p >= 1; --p) {
-    if (p > L) continue;
+#pragma unroll 1
+  for (int p = L; p >= 1; --p) {
     const uint32_t mask = reinterpret_cast<const uint32_t*>(b.stage_blk + (size_t)(p - 1) * ST_BLK + 2 * ST_PART)[hidx * TILE + b.row];
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
     HODE_TL(230 + 10 * p);
-    // everything phase b.ph - 2 read is free now (its MMAs precede the chain just waited for)
-    if (loader) {
-      prefetch_A(b, L, b.k, b.ph);
-      prefetch_W(b, L, b.k + 1, b.ph + 1u);
-    }
     uint32_t u[32];
     HODE_TMEM_LD_X32(t_d, u);
     tc::wait_ld();
@@ -375,10 +379,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   // ---- final phase: g_x -------------------------------------------------------------------------
   tc::mbar_wait(c.mma_bar, c.parity);
   c.parity ^= 1u;
-  if (loader) {   // next stage's phase L
-    prefetch_A(b, L, b.k, b.ph);
-    prefetch_W(b, L, b.k + 1, b.ph + 1u);
-  }
   if (MAIN) {
     tc::fence_after_sync();
     uint32_t v[16];
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
   // evaluation back once, as stage 7 of the earlier step, with both cotangents added (`carry`).
   // Stage 1 of the very first step is pulled back by one extra iteration: a zero-length step at
   // (t0, y0) whose stage 7 receives the carry.
-  const bool fsal = solver == 1 && A.save_k != nullptr;
+  const bool fsal = solver == 1 && A.save_k1 != 0;
   const int i0 = fsal ? 1 : 0;
   const long n_units = (long)A.S * A.B;
 
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     for (int it = 0; it < n_iter; ++it) {
       load_image(fwd_src, G.fwd_floats);
 #pragma unroll 1
-      for (int i = i0; i < N; ++i) mlp_tile_helper<true>(c, stash0 + (size_t)i * stage_stride, row);
+      for (int i = i0; i < N; ++i) mlp_tile_helper<true, true>(c, stash0 + (size_t)i * stage_stride, row);
       begin_reverse();
 #pragma unroll 1
       for (int i = N - 1; i >= i0; --i) {
@@ -644,6 +644,10 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
     for (int it = 0; it < n_iter; ++it) {
       load_image(fwd_src, G.fwd_floats);
+      if (issuer) {
+#pragma unroll 1
+        for (int i = i0; i < N; ++i) mlp_fwd_issue<true>(c);
+      }
       begin_reverse();
       if (issuer) {
 #pragma unroll 1
@@ -688,6 +692,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     float carry[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) carry[i] = 0.f;
+    double t_next = 0.0;
     const int n_iter = nmax + (fsal ? 1 : 0);
     for (int it = 0; it < n_iter; ++it) {
       // =========================== forward recomputation =========================================
@@ -701,28 +706,29 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
       float y[NS], k1[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) { y[i] = 0.f; k1[i] = 0.f; }
-      if (act && !real && n > 0) {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) y[i] = A.save_y[(size_t)i * n_units + unit];
+      if (act && !real && n > 0) {   // the zero-length step: y0 = the state the first record starts from
+        double t_;
+        float h_;
+        step_rec_load(step_rec(A, unit, 0), t_, h_, y, nullptr);
       }
       if (real) {
-        const size_t o = (size_t)sidx * n_units + unit;
-        t = A.save_t[o];
+        const float* rec = step_rec(A, unit, sidx);
+        float h_rec;
+        step_rec_load(rec, t, h_rec, y, fsal ? k1 : nullptr);
         if (solver == 0) {
-          h = (double)A.save_h[o];
+          h = (double)h_rec;
           t_new = t + h;
         } else {
-          t_new = (sidx + 1 < n) ? A.save_t[o + n_units] : t_bound;
+          t_new = (sidx + 1 < n) ? t_next : t_bound;   // the next record's start time, seen one iteration ago
           h = t_new - t;
         }
-#pragma unroll
-        for (int i = 0; i < NS; ++i) y[i] = A.save_y[((size_t)sidx * NS + i) * n_units + unit];
-        if (fsal) {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) k1[i] = A.save_k[((size_t)sidx * NS + i) * n_units + unit];
-        }
+        t_next = t;
       }
       const float hf = (float)h;
+#ifdef HODE_TIMELINE
+      if (hf + y[0] + k1[5] == 123456.f) HODE_TL(299);   // (forces the loads to complete before the next mark)
+#endif
+      HODE_TL(205);
       // Inputs of this step as one linear piece per channel (value = c_v1 + alpha * c_dv): valid when a
       // step cannot cross an input kink (RK4, kink clipping, or no series input), see
       // hode_rollout_tc.cu::lane_cache_inputs.  Otherwise every stage looks its interval up.
@@ -752,6 +758,10 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
           }
         }
       }
+#ifdef HODE_TIMELINE
+      if (c_v1[0] + c_dv[1] + c_dt == 123456.f) HODE_TL(299);
+#endif
+      HODE_TL(206);
       // stage derivatives / cotangents are indexed statically (predicated selects) so that they
       // live in registers rather than in local memory
       float k[NSTAGE_MAX][NS], tv[NSTAGE_MAX], gdv[NSTAGE_MAX];
@@ -796,13 +806,9 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         x[7] = ys[3];
         x[8] = tvns;
         __syncwarp();
-#ifdef HODE_NO_OVERLAP_F
-        mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, row);
-        rhs_mech(th, ys, meal, gd, gd_present, d);
-#else
-        mlp_tile<true>(c, x, r, stash0 + (size_t)i * stage_stride, row,
-                       [&] { rhs_mech(th, ys, meal, gd, gd_present, d); });
-#endif
+        HODE_TL(207);
+        mlp_tile<true, true>(c, x, r, stash0 + (size_t)i * stage_stride, row,
+                             [&] { rhs_mech(th, ys, meal, gd, gd_present, d); });
 #pragma unroll
         for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
           if (jj == i) {
@@ -814,6 +820,8 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
       }
       // =========================== reverse sweep ===================================================
       HODE_TL(202);
+      // the next iteration's step record: pull it into L2 while this sweep runs
+      if (real && sidx > 0) tc::prefetch_l2(step_rec(A, unit, sidx - 1));
       begin_reverse();
       HODE_TL(203);
       float gy[NS], gk[NSTAGE_MAX][NS];
@@ -900,12 +908,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         bc.stage_blk = stash0 + (size_t)i * stage_stride;
         __syncwarp();
         HODE_TL(210);
-#ifdef HODE_NO_OVERLAP_B
-        mech_vjp(th, ys, gdi, gd_present, gki, gys, gth);
-        mlp_bwd_tile<true>(c, bc, x, gki, gx, [] {});
-#else
         mlp_bwd_tile<true>(c, bc, x, gki, gx, [&] { mech_vjp(th, ys, gdi, gd_present, gki, gys, gth); });
-#endif
         HODE_TL(211);
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];

@@ -26,7 +26,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_n, off_t, off_h, off_y, off_k, off_tc, total;
+  size_t off_n, off_rec, off_tc, total;
   int max_saved;
 };
 
@@ -49,13 +49,8 @@ Workspace fwd_workspace(const hode_cfg* c) {
   size_t off = 0;
   if (c->save_steps) {
     w.off_n = off; off = align_up(off + units * sizeof(int32_t), 256);
-    w.off_t = off; off = align_up(off + units * w.max_saved * sizeof(double), 256);
-    w.off_h = off; off = align_up(off + units * w.max_saved * sizeof(float), 256);
-    w.off_y = off; off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
-    // first stage derivative of every step: the tensor-core DP5(4) adjoint reuses it (FSAL)
-    w.off_k = off;
-    if (uses_tensor_cores(c) && c->solver != HODE_SOLVER_RK4)
-      off = align_up(off + units * w.max_saved * HODE_N_STATE * sizeof(float), 256);
+    // one 64-byte record per (unit, step): t, h, y[6], k1[6] (hode_common.cuh step_rec)
+    w.off_rec = off; off = align_up(off + units * w.max_saved * 64, 256);
   }
   if (uses_tensor_cores(c)) {
     // pre-split weight images (one per parameter set) + the per-set trajectory queue counters
@@ -191,10 +186,8 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
   if (cfg->save_steps) {
     char* base = (char*)workspace;
     A.save_n = (int32_t*)(base + w.off_n);
-    A.save_t = (double*)(base + w.off_t);
-    A.save_h = (float*)(base + w.off_h);
-    A.save_y = (float*)(base + w.off_y);
-    A.save_k = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? (float*)(base + w.off_k) : nullptr;
+    A.save_rec = (float*)(base + w.off_rec);
+    A.save_k1 = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? 1 : 0;   // the tensor-core adjoint reuses k1 (FSAL)
     A.max_saved = w.max_saved;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -236,10 +229,8 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
   char* base = (char*)fwd_workspace_ptr;
   A.save_n = (int32_t*)(base + w.off_n);
-  A.save_t = (double*)(base + w.off_t);
-  A.save_h = (float*)(base + w.off_h);
-  A.save_y = (float*)(base + w.off_y);
-  A.save_k = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? (float*)(base + w.off_k) : nullptr;
+  A.save_rec = (float*)(base + w.off_rec);
+  A.save_k1 = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? 1 : 0;
   A.max_saved = w.max_saved;
   // forward on the tensor cores -> adjoint on the tensor cores (3xTF32); FP32 forward -> FP32 adjoint
   cudaError_t e = tc_adj ? hode::launch_rollout_bwd_tc(A, grad_traj, grad_y0, grad_theta, grad_W, bwd_workspace,

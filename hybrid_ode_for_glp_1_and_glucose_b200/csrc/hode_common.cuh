@@ -24,12 +24,11 @@ struct RolloutArgs {
   float* traj;          // [S,B,T,6] (or nullptr in fused-statistics mode)
   int32_t* status;      // [S,B] or nullptr
   int32_t* counters;    // [2,S,B] or nullptr
-  // saved accepted steps (discrete adjoint): step-major [max_saved][S*B] so that the
-  // lanes of a warp write/read consecutive addresses
-  double* save_t;       // start time of accepted step n
-  float* save_h;        // step size
-  float* save_y;        // [max_saved][6][S*B] state at step start
-  float* save_k;        // [max_saved][6][S*B] first stage derivative of the step (tensor-core DP5(4) rollout only, else NULL)
+  // saved accepted steps (discrete adjoint): one 64-byte record per (unit, step), unit-major
+  // [S*B][max_saved][16 floats] = { t (f64), h, pad, y[6], k1[6] } — a trajectory's steps are contiguous
+  // (the adjoint walks them backwards: one TLB entry and 2 sectors per step instead of 14 of each)
+  float* save_rec;
+  int32_t save_k1;      // records carry k1, the step's first stage derivative (tensor-core DP5(4) rollout)
   int32_t* save_n;      // [S*B] number of saved steps
   int32_t max_saved;
   int32_t B, T, S;
@@ -54,6 +53,36 @@ struct RolloutArgs {
   volatile int* done_flag;
   int done_block;
 };
+
+// ---- step records ---------------------------------------------------------------------------------------
+constexpr int HODE_REC_FLOATS = 16;
+__device__ __forceinline__ float* step_rec(const RolloutArgs& A, long unit, int step) {
+  return A.save_rec + ((size_t)unit * A.max_saved + step) * HODE_REC_FLOATS;
+}
+__device__ __forceinline__ void step_rec_store(float* r, double t, float h, const float* y, const float* k1) {
+  float4* r4 = reinterpret_cast<float4*>(r);
+  const long long tb = __double_as_longlong(t);
+  r4[0] = make_float4(__int_as_float((int)(tb & 0xFFFFFFFFll)), __int_as_float((int)(tb >> 32)), h, 0.f);
+  r4[1] = make_float4(y[0], y[1], y[2], y[3]);
+  if (k1) {
+    r4[2] = make_float4(y[4], y[5], k1[0], k1[1]);
+    r4[3] = make_float4(k1[2], k1[3], k1[4], k1[5]);
+  } else {
+    r4[2] = make_float4(y[4], y[5], 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ double step_rec_t(const float* r) { return *reinterpret_cast<const double*>(r); }
+__device__ __forceinline__ void step_rec_load(const float* r, double& t, float& h, float* y, float* k1) {
+  const float4* r4 = reinterpret_cast<const float4*>(r);
+  const float4 a = r4[0], b = r4[1], c = r4[2];
+  t = __longlong_as_double(((long long)__float_as_int(a.y) << 32) | (long long)(unsigned)__float_as_int(a.x));
+  h = a.z;
+  y[0] = b.x; y[1] = b.y; y[2] = b.z; y[3] = b.w; y[4] = c.x; y[5] = c.y;
+  if (k1) {
+    const float4 d = r4[3];
+    k1[0] = c.z; k1[1] = c.w; k1[2] = d.x; k1[3] = d.y; k1[4] = d.z; k1[5] = d.w;
+  }
+}
 
 // ---- Dormand-Prince 5(4) coefficients (float) --------------------------------------------
 namespace dp {

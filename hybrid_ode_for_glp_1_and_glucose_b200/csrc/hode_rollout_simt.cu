@@ -254,11 +254,7 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
       for (int ss = 0; ss < nsub; ++ss) {
         const double t = ta + ss * h;
         if (A.save_n && n_saved < A.max_saved) {
-          const size_t o = (size_t)n_saved * n_units + unit;
-          A.save_t[o] = t;
-          A.save_h[o] = hf;
-#pragma unroll
-          for (int i = 0; i < NS; ++i) A.save_y[((size_t)n_saved * NS + i) * n_units + unit] = y[i];
+          step_rec_store(step_rec(A, unit, n_saved), t, hf, y, nullptr);
           ++n_saved;
         }
         float k1[NS], k2[NS], k3[NS], k4[NS], ys[NS];
@@ -399,12 +395,7 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
         ++n_acc;
         if (A.save_n) {
           if (n_saved < A.max_saved) {
-            const size_t o = (size_t)n_saved * n_units + unit;
-            A.save_t[o] = t;
-            A.save_h[o] = hf;
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-              A.save_y[((size_t)n_saved * NS + i) * n_units + unit] = y[i];
+            step_rec_store(step_rec(A, unit, n_saved), t, hf, y, nullptr);
             ++n_saved;
           } else {
             status = HODE_ST_MAX_STEPS;
@@ -476,7 +467,7 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
 // restaging the weight image for each, and reduces mean / std on the fly.
 // ------------------------------------------------------------------------------------------
 template <int MLP_KIND>
-__global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs A) {
+__global__ void __launch_bounds__(128, MLP_KIND == 0 ? 4 : 1) rollout_simt_kernel(const RolloutArgs A) {   // mechanistic: 4 CTAs per SM (<= 128 registers)
   extern __shared__ __align__(16) float smem[];
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool vi = A.vi_mean != nullptr;

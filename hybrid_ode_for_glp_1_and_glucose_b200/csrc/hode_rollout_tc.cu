@@ -239,16 +239,7 @@ __device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A, int 
 
 // k1: the step's first stage derivative (DP5(4): the adjoint reuses it instead of recomputing it — FSAL)
 __device__ __forceinline__ void lane_save_step(Lane& ln, const RolloutArgs& A, double t, float hf, const float* k1 = nullptr) {
-  const long n_units = (long)A.S * A.B;
-  const size_t o = (size_t)ln.n_saved * n_units + ln.unit;
-  A.save_t[o] = t;
-  A.save_h[o] = hf;
-#pragma unroll
-  for (int i = 0; i < NS; ++i) A.save_y[((size_t)ln.n_saved * NS + i) * n_units + ln.unit] = ln.y[i];
-  if (k1 && A.save_k) {
-#pragma unroll
-    for (int i = 0; i < NS; ++i) A.save_k[((size_t)ln.n_saved * NS + i) * n_units + ln.unit] = k1[i];
-  }
+  step_rec_store(step_rec(A, ln.unit, ln.n_saved), t, hf, ln.y, A.save_k1 ? k1 : nullptr);
   ++ln.n_saved;
 }
 

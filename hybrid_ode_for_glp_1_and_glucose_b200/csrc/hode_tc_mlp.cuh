@@ -94,6 +94,16 @@ __device__ __forceinline__ void tile_sync(const TileCtx& c) {
 __device__ __forceinline__ void tile_sync_all(const TileCtx& c) {
   asm volatile("bar.sync %0, 256;" ::"r"(c.bar_all) : "memory");
 }
+// External-issue mode (the adjoint): a dedicated warp issues every MMA chain, so that no epilogue
+// warp is held in a blocking tcgen05.mma issue while it still has stores to do.  The 256 epilogue
+// threads ARRIVE on this named barrier, the issuer warp waits on it (mlp_fwd_issue).
+constexpr int EXT_ISSUE_BAR = 3, EXT_ISSUE_THREADS = 2 * TILE + 32;
+__device__ __forceinline__ void ext_issue_arrive() {
+  asm volatile("bar.arrive %0, %1;" ::"n"(EXT_ISSUE_BAR), "n"(EXT_ISSUE_THREADS) : "memory");
+}
+__device__ __forceinline__ void ext_issue_wait() {
+  asm volatile("bar.sync %0, %1;" ::"n"(EXT_ISSUE_BAR), "n"(EXT_ISSUE_THREADS) : "memory");
+}
 
 // Issue the MMAs of one layer (one elected thread): D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
 // The two correction products are accumulated FIRST, into a still-small accumulator: the tensor
@@ -145,7 +155,7 @@ __device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo) {
 // Every thread of the tile must call this converged.  x: the 9 input features of this thread's
 // trajectory; r: the 6 residuals.  `overlap` runs right after the layer-0 MMAs have been issued: per-thread
 // work that does not depend on the network (the mechanistic RHS) hides behind their latency.
-template <bool X3, class F>
+template <bool X3, bool EXT = false, class F>
 __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash, int stash_row,
                                          F&& overlap) {
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
@@ -174,15 +184,19 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
   // main AND helper warps: the helpers arrive here only after they have observed the previous
   // call's last mbarrier phase, so the layer-0 commit below cannot flip the barrier a second time
   // under a helper that is still busy (it would then wait for a phase that has already passed)
-  tile_sync_all(c);
-  HODE_TL(2);
-  if (c.wq == 0) {
-    if (tc::elect_one()) {
-      tc::fence_after_sync();
-      issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, m_ones, img_s, img_s + 1024 * 4, bias_s);
-      tc::mma_commit(c.mma_bar);
+  if (EXT) {
+    ext_issue_arrive();
+  } else {
+    tile_sync_all(c);
+    HODE_TL(2);
+    if (c.wq == 0) {
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, m_ones, img_s, img_s + 1024 * 4, bias_s);
+        tc::mma_commit(c.mma_bar);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   HODE_TL(3);
   overlap();
@@ -214,17 +228,21 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
     tc::wait_st();
     tc::fence_before_sync();
     HODE_TL(12 + 10 * l);
-    tile_sync_all(c);
-    HODE_TL(13 + 10 * l);
-    if (c.wq == 0) {
-      if (tc::elect_one()) {
-        tc::fence_after_sync();
-        const uint32_t b_bias = bias_s + (uint32_t)(l + 1) * 512u * 4u;
-        if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
-        else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
-        tc::mma_commit(c.mma_bar);
+    if (EXT) {
+      ext_issue_arrive();
+    } else {
+      tile_sync_all(c);
+      HODE_TL(13 + 10 * l);
+      if (c.wq == 0) {
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          const uint32_t b_bias = bias_s + (uint32_t)(l + 1) * 512u * 4u;
+          if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
+          else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
+          tc::mma_commit(c.mma_bar);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     // adjoint: a_l = relu(z_l) of this thread's trajectory, columns [0,32), goes to the stash AFTER
     // the next layer's MMAs have been issued (off the critical path)
@@ -252,17 +270,54 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
 template <bool X3>
 __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash = nullptr,
                                          int stash_row = 0) {
-  mlp_tile<X3>(c, x, r, stash, stash_row, [] {});
+  mlp_tile<X3, false>(c, x, r, stash, stash_row, [] {});
+}
+
+// External-issue mode: the MMA chains of one mlp_tile<X3, true>() call, issued by a dedicated (converged)
+// warp.  Every chain is committed to the tile's mbarrier; c.parity tracks the phase of the last commit.
+template <bool X3>
+__device__ __forceinline__ void mlp_fwd_issue(TileCtx& c) {
+  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+  const uint32_t m_ones = c.tmem + TM_ONES;
+  const uint32_t img_s = tc::smem_u32(c.img);
+  const uint32_t bias_s = img_s + (uint32_t)(2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024) * 4u;
+  ext_issue_wait();
+  if (tc::elect_one()) {
+    tc::fence_after_sync();
+    issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, m_ones, img_s, img_s + 1024 * 4, bias_s);
+    tc::mma_commit(c.mma_bar);
+  }
+  __syncwarp();
+  c.parity ^= 1u;
+  uint32_t w_off = 2 * 1024;
+#pragma unroll 1
+  for (int l = 0; l < c.L; ++l) {
+    const bool last = (l + 1 == c.L);
+    const uint32_t b_hi = img_s + w_off * 4;
+    const uint32_t b_lo = b_hi + (last ? 1024u : 4096u) * 4u;
+    ext_issue_wait();
+    if (tc::elect_one()) {
+      tc::fence_after_sync();
+      const uint32_t b_bias = bias_s + (uint32_t)(l + 1) * 512u * 4u;
+      if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
+      else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
+      tc::mma_commit(c.mma_bar);
+    }
+    __syncwarp();
+    c.parity ^= 1u;
+    w_off += 2 * 4096;
+  }
 }
 
 // Helper warps: the other half of every hidden-layer epilogue.  Must be called once per
 // mlp_tile() call of the tile's main warps (same number of tile-wide barriers and mbarrier phases).
-template <bool X3>
+template <bool X3, bool EXT = false>
 __device__ __forceinline__ void mlp_tile_helper(TileCtx& c, uint8_t* stash = nullptr, int stash_row = 0) {
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + 32;
   const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI + 32;
   const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO + 32;
-  tile_sync_all(c);   // pairs with the main warps' barrier before the layer-0 MMAs (see mlp_tile)
+  if (EXT) ext_issue_arrive();
+  else tile_sync_all(c);   // pairs with the main warps' barrier before the layer-0 MMAs (see mlp_tile)
 #pragma unroll 1
   for (int l = 0; l < c.L; ++l) {
     tc::mbar_wait(c.mma_bar, c.parity);
@@ -279,7 +334,8 @@ __device__ __forceinline__ void mlp_tile_helper(TileCtx& c, uint8_t* stash = nul
     if (X3) HODE_TMEM_ST_X16(t_alo + 16, (lo + 16));
     tc::wait_st();
     tc::fence_before_sync();
-    tile_sync_all(c);
+    if (EXT) ext_issue_arrive();
+    else tile_sync_all(c);
     if (X3 && stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 1, v, lo);   // columns [32,64)
   }
   // the output layer's phase: nothing to read, but the phase must be observed so that the next

@@ -131,6 +131,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // all state spaces: generic-proxy GLOBAL stores that a later bulk copy (async proxy) reads
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");

@@ -185,9 +185,24 @@ class HybridODENN(nn.Module):
                                    solver: str = "dopri5", rtol: float = 1e-6,
                                    atol: float = 1e-8, **kernel_opts) -> torch.Tensor:
         """All S sampled parameter sets in ONE launch -> [S,B,T,6] (the VI sweep of
-        inference/vi.py:294-304 without the Python loop)."""
+        inference/vi.py:294-304 without the Python loop).  With `differentiable=True` (and grad
+        mode on) the launch records its steps and the result carries a graph back to the sample
+        tensors through hode_rollout_bwd, which returns one gradient per parameter set — the
+        pathwise (reparameterisation) gradient the reference's ELBO is missing."""
         dev = self._cuda_device(initial_state, t_span)
         theta, W = self._stack_samples(samples, dev)
+        if kernel_opts.get("differentiable", False) and torch.is_grad_enabled():
+            y0 = initial_state if initial_state.dim() == 2 else initial_state.unsqueeze(0)
+            traj, info = autograd_ops.rollout(
+                y0.to(dev), t_span, external_inputs, theta, W,
+                hidden=self.nn_residual.hidden_dim, layers=self.nn_residual.n_layers, solver=solver,
+                rtol=rtol, atol=atol, n_substeps=kernel_opts.get("n_substeps", self.rk4_substeps),
+                kinks=kernel_opts.get("kinks", self.kinks),
+                precision=kernel_opts.get("precision", self.precision),
+                max_steps=kernel_opts.get("max_steps", 0),
+                max_saved_steps=kernel_opts.get("max_saved_steps", 0))
+            self.last_info = info
+            return traj
         traj, info = ops.rollout(
             initial_state if initial_state.dim() == 2 else initial_state.unsqueeze(0), t_span,
             external_inputs, theta, W,

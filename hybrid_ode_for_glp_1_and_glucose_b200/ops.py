@@ -228,9 +228,10 @@ def saved_steps(tape: RolloutTape):
     al = lambda x: (x + 255) // 256 * 256
     ws = tape.workspace
     n = ws[: units * 4].view(torch.int32)
-    off_t = al(units * 4)
-    t = ws[off_t: off_t + units * max_saved * 8].view(torch.float64).reshape(max_saved, units)
-    return n, t
+    # one 64-byte record per (unit, step): { t f64, h f32, pad, y[6], k1[6] } (csrc/hode_common.cuh step_rec)
+    off_rec = al(units * 4)
+    rec = ws[off_rec: off_rec + units * max_saved * 64].view(torch.float64).reshape(units, max_saved, 8)
+    return n, rec[:, :, 0].permute(1, 0)
 
 
 def vi_predictive(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],

@@ -38,17 +38,30 @@ class VariationalInference:
         self.optimizer = torch.optim.Adam(self.variational_params.parameters(), lr=learning_rate)
         self.history = {"elbo": [], "kl": [], "log_likelihood": []}
 
-    def elbo(self, batch: Dict[str, torch.Tensor], n_samples: int = 5, noise_sigma: float = 1.0
-             ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    def elbo(self, batch: Dict[str, torch.Tensor], n_samples: int = 5, noise_sigma: float = 1.0,
+             reparam_gradient: Optional[bool] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
         """ELBO = E_q[log p(x|psi)] - KL (reference inference/vi.py:60-118).  The n_samples
-        rollouts run as one [S,B] launch.  As in the reference the likelihood term carries no
-        gradient (forward returns a graph-free tensor); the KL term does."""
+        rollouts run as one [S,B] launch.
+
+        Default (`reparam_gradient` False): as in the reference the likelihood term carries no
+        gradient (forward returns a graph-free tensor); only the KL term does.
+        `reparam_gradient=True` (or `self.reparam_gradient = True`): the sweep records its steps
+        and the likelihood back-propagates through hode_rollout_bwd into every sampled parameter
+        set, i.e. into the means and log-stds via psi = mu + eps * sigma — the estimator
+        SURVEY §8f row 2 asks for; same value, same sampling order."""
         y0, obs = batch["initial_state"], batch["observations"]
         t, ext = batch["time_points"], batch.get("external_inputs", None)
         kl = self.variational_params.kl_divergence()
         samples = [self.variational_params.sample(1)[0] for _ in range(n_samples)]
-        with torch.no_grad():
-            preds = self.model.forward_with_param_samples(samples, y0, t, ext)
+        if reparam_gradient is None:
+            reparam_gradient = getattr(self, "reparam_gradient", False)
+        if reparam_gradient and torch.is_grad_enabled():
+            preds = self.model.forward_with_param_samples(samples, y0, t, ext, differentiable=True,
+                                                          **getattr(self, "kernel_opts", {}))
+        else:
+            with torch.no_grad():
+                preds = self.model.forward_with_param_samples(samples, y0, t, ext,
+                                                              **getattr(self, "kernel_opts", {}))
         obs = obs.to(preds.device)
         sq = ((obs.unsqueeze(0) - preds) / noise_sigma).pow(2).sum(dim=(1, 2, 3))
         ll = (-0.5 * sq).sum() / n_samples
@@ -56,9 +69,10 @@ class VariationalInference:
         elbo = ll - kl
         return elbo, {"elbo": elbo, "kl": kl, "log_likelihood": ll}
 
-    def train_step(self, batch: Dict[str, torch.Tensor], n_samples: int = 5) -> Dict[str, float]:
+    def train_step(self, batch: Dict[str, torch.Tensor], n_samples: int = 5,
+                   reparam_gradient: Optional[bool] = None) -> Dict[str, float]:
         self.optimizer.zero_grad()
-        elbo, comp = self.elbo(batch, n_samples=n_samples)
+        elbo, comp = self.elbo(batch, n_samples=n_samples, reparam_gradient=reparam_gradient)
         loss = -elbo
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.variational_params.parameters(), max_norm=5.0)

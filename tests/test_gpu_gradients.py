@@ -301,3 +301,27 @@ def test_config3_gradient_properties_at_size(dev):
     # (3) GE has zero mechanistic derivative and enters the network: its y0-gradient is finite and the
     #     FFA row of theta (p_7..p_9) receives gradient
     assert float(a[1][14:].abs().max()) > 0
+
+
+def test_tensor_core_adjoint_repeatable_over_many_launches(dev):
+    """Several tiles per CTA, every launch scheduled from scratch: 15 fwd + adjoint passes must return
+    bit-identical gradients.  (Regression test for a phase race between the main and helper warps of a
+    tile that showed up as an occasional hang or a wrong gradient, never in single-tile cases.)"""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T = 32768, 61
+    y0, t, ins = cohort(B, T, seed=1000)
+    W = random_mlp(64, 4, seed=1234, out_std=0.05)
+    theta = golden("rhs_mech")["theta"]
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    args = (tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W))
+    g = torch.randn((B, T, 6), device=dev, generator=torch.Generator(dev).manual_seed(3)) / (B * T)
+    ref = None
+    for _ in range(15):
+        _, info, tape = ops.rollout(*args, solver="dopri5", precision="tf32x3", device=dev, save_steps=True)
+        out = ops.rollout_bwd(tape, g)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = [o.clone() for o in out]
+            assert bool((info.status == 0).all()) and all(bool(torch.isfinite(o).all()) for o in out)
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(ref, out))
