@@ -470,7 +470,6 @@ __global__ void __launch_bounds__(ABLK, 1) rollout_bwd_kernel(const AdjArgs G) {
   __shared__ int s_nmax;
   const RolloutArgs& A = G.R;
   const int tid = threadIdx.x, s = blockIdx.y, T = A.T;
-  const long n_units = (long)A.S * A.B;
 
   float* red = smem;                         // [17][ABLK] (only carved out when there is no MLP)
   float* sm = smem + (G.has_nn ? 0 : HODE_N_THETA * ABLK);

@@ -59,34 +59,14 @@ __constant__ float kP[7][4] = {{dp::p11, dp::p12, dp::p13, dp::p14}, {0.f, 0.f, 
                                {0.f, dp::p52, dp::p53, dp::p54},     {0.f, dp::p62, dp::p63, dp::p64},
                                {0.f, dp::p72, dp::p73, dp::p74}};
 
-// D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi without a bias step (the first MMA initialises D)
-template <int N, int KSTEPS>
-__device__ __forceinline__ void issue_nobias(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t b_hi, uint32_t b_lo) {
-  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
-  constexpr uint32_t lbo16 = (uint32_t)N;
-  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
-  const uint32_t lo_hi = ((b_hi >> 4) & 0x3FFFu) | (lbo16 << 16);
-  const uint32_t lo_lo = ((b_lo >> 4) & 0x3FFFu) | (lbo16 << 16);
-#pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks)
-    tc::mma_tf32_ts(d, alo + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc,
-                    ks == 0 ? 0u : 1u);
-#pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks)
-    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lo + (uint32_t)ks * 2u * lbo16), idesc, 1u);
-#pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks)
-    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, 1u);
-}
-
-// split 16 fp32 values into TF32 hi (rounded) / lo (exact remainder, truncated by the tensor core)
-__device__ __forceinline__ void split16(const float* d, uint32_t* hi, uint32_t* lo) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const uint32_t h = (__float_as_uint(d[j]) + 0x1000u) & 0xFFFFE000u;
-    hi[j] = h;
-    lo[j] = __float_as_uint(d[j] - __uint_as_float(h));
-  }
+// x -> BF16 hi (round to nearest) and BF16 mid = bf16(x - hi)
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& mid) {
+  uint32_t h, m;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(0.f), "f"(x));
+  const float r = x - __uint_as_float(h << 16);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(0.f), "f"(r));
+  hi = (uint16_t)(h & 0xFFFFu);
+  mid = (uint16_t)(m & 0xFFFFu);
 }
 
 // ---- weight gradients on the tensor cores ---------------------------------------------------------
@@ -111,14 +91,17 @@ constexpr uint32_t DW_H0 = 208, DW_0 = 448, DW_O = 464;
 //   [input operands 2 x (hi, mid) x 9 groups][delta operands 2 x (hi, mid) x 8 groups][W_l^T slots 2 x (hi, lo)]
 constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART;
 constexpr int DB_BYTES = 2 * ST_PART;
-constexpr int WS_BYTES = 2 * 4096 * 4;
+constexpr int WS_BYTES = 2 * 64 * 64 * 2;   // one layer's W^T: BF16 hi, mid
 constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_WS = OFF_DB + 2 * DB_BYTES;
 constexpr int BWD_BYTES = OFF_WS + 2 * WS_BYTES;
 
-// kind::f16 instruction descriptor: D = f32, A = B = BF16, both MN-major
+// kind::f16 instruction descriptors: D = f32, A = B = BF16; both operands MN-major / both K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_k(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -146,8 +129,27 @@ __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t r_hi, uint32_t r_m
   for (int ks = 0; ks < TILE / 16; ++ks) mma_bf16_ss(d, rh + 16u * ks, ch + 16u * ks, idesc, 1u);
 }
 
+// u[128 x N] = delta[128 x 16 KSTEPS] W: the delta image read as a K-major A operand (K-chunk = one
+// 8-feature group, LBO = ST_GRP, 8-trajectory row groups SBO = 128 B) against the K-major BF16 image of
+// W^T: element (n, k) at byte (k / 8) * (N * 16) + n * 16 + (k % 8) * 2 (csrc/probe/bf16_probe.cu test 3);
+// same two-term split and pass order as the weight gradients.  The first MMA initialises D.
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_u(uint32_t d, uint32_t a_hi, uint32_t a_mid, uint32_t b_hi, uint32_t b_mid) {
+  constexpr uint32_t idesc = make_idesc_bf16_k(TILE, N);
+  const uint64_t ah = tc::make_desc(a_hi, ST_GRP, 128u), am = tc::make_desc(a_mid, ST_GRP, 128u);
+  const uint64_t bh = tc::make_desc(b_hi, (uint32_t)N * 16u, 128u), bm = tc::make_desc(b_mid, (uint32_t)N * 16u, 128u);
+  // one k-step = 16 features = 2 K-chunks: A advances 2 ST_GRP bytes, B 2 * N * 16 bytes (16-byte units)
+  constexpr uint32_t sa = 2u * ST_GRP / 16u, sb = 2u * (uint32_t)N;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_ss(d, am + sa * ks, bh + sb * ks, idesc, ks == 0 ? 0u : 1u);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_ss(d, ah + sa * ks, bm + sb * ks, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_ss(d, ah + sa * ks, bh + sb * ks, idesc, 1u);
+}
+
 // Issue phases of the reverse sweep.  One stage has L + 1 of them, q = L .. 0:
-//   phase q:  u_{q-1} = delta_q W_q  (3xTF32, delta in TMEM, W_q^T in a slot)   and   dW_q += delta_q^T [a_{q-1} | 1]
+//   phase q:  u_{q-1} = delta_q W_q  (delta image x W_q^T slot)   and   dW_q += delta_q^T [a_{q-1} | 1]
 // (a_{-1} = the stage's input features x, u_{-1} = the cotangent of x).  Phases are numbered through
 // the whole kernel (`ph`); phase ph uses buffer ph & 1 of every double-buffered region, and its
 // mbarriers complete once per phase, so the parity to wait for is (ph >> 1) & 1.
@@ -191,9 +193,9 @@ __device__ __forceinline__ void prefetch_W(const BwdCtx& b, int L, int k2, uint3
   if (k2 >= b.k_end) return;
   const int q = L - k2 % (L + 1);
   int off, floats;
-  if (q == L) { off = 0; floats = 2048; }
-  else if (q >= 1) { off = 2048 + (L - 1 - q) * 8192; floats = 8192; }
-  else { off = 2048 + (L - 1) * 8192; floats = 2048; }
+  if (q == L) { off = 0; floats = 1024; }
+  else if (q >= 1) { off = 1024 + (L - 1 - q) * 4096; floats = 4096; }
+  else { off = 1024 + (L - 1) * 4096; floats = 1024; }
   uint64_t* bar = b.wload_bar + (ph2 & 1u);
   tc::mbar_expect_tx(bar, (uint32_t)floats * 4u);
   tc::bulk_g2s(b.smem + OFF_WS + (ph2 & 1u) * WS_BYTES, b.wsrc + off, (uint32_t)floats * 4u, bar);
@@ -202,24 +204,14 @@ __device__ __forceinline__ void prefetch_W(const BwdCtx& b, int L, int k2, uint3
 // The MMAs of the reverse sweep are issued by a dedicated warp: tcgen05.mma issue blocks while the
 // tensor pipe is busy, and a warp that also runs an epilogue would hold the whole tile back for
 // that long.  The 256 epilogue threads only ARRIVE on the named barrier; the issuer warp waits on it.
-// Two barriers per phase: the u-chain only needs delta in TMEM, the weight-gradient MMAs also need the
-// BF16 operand images, which the threads write while the u-chain already runs.  The second barrier
-// alternates between two ids by phase parity: a fast thread can reach its arrival of phase ph + 1
-// while the issuer still waits for a slow thread's arrival of phase ph (nothing orders the two), and
-// on one id the counts would mix.  (On the first barrier they cannot: the u-chain whose completion
-// lets a thread move on is only issued after that barrier has completed.)
-constexpr int ISSUE_BAR = 3, ISSUE_BAR_DW = 4, ISSUE_BAR_THREADS = 2 * TILE + 32;
+// (One barrier per phase is race-free: the u-chain whose completion lets a thread move on to its next
+// arrival is only issued after the barrier has completed, so arrivals of two phases never mix.)
+constexpr int ISSUE_BAR = 3, ISSUE_BAR_THREADS = 2 * TILE + 32;
 __device__ __forceinline__ void issue_arrive() {
   asm volatile("bar.arrive %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
 }
 __device__ __forceinline__ void issue_wait() {
   asm volatile("bar.sync %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
-}
-__device__ __forceinline__ void issue_arrive_dw(uint32_t ph) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(ISSUE_BAR_DW + (int)(ph & 1u)), "n"(ISSUE_BAR_THREADS) : "memory");
-}
-__device__ __forceinline__ void issue_wait_dw(uint32_t ph) {
-  asm volatile("bar.sync %0, %1;" ::"r"(ISSUE_BAR_DW + (int)(ph & 1u)), "n"(ISSUE_BAR_THREADS) : "memory");
 }
 
 // Issuer warp: the MMA chains of one stage of the reverse sweep, mirroring mlp_bwd_tile's phases, and the
@@ -227,7 +219,7 @@ __device__ __forceinline__ void issue_wait_dw(uint32_t ph) {
 // (its MMAs precede that chain), so the input operand of phase ph + 1 and W^T of phase ph + 2 are fetched.
 __device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
   const int L = c.L;
-  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
+  const uint32_t m_d = c.tmem + TM_D0;
   const uint32_t base = tc::smem_u32(b.smem);
   // (runtime loops here and in mlp_bwd_tile: unrolled over the phases the kernel outgrows the
   // instruction cache — three roles run three different code streams on one SM)
@@ -241,15 +233,14 @@ __device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
     tc::mbar_wait(b.wload_bar + buf, par);
     if (tc::elect_one()) {
       tc::fence_after_sync();
-      if (q == L) issue_nobias<H, 2>(m_d, m_ahi, m_alo, ws, ws + 1024u * 4u);        // u_{L-1} = delta_L W_out
-      else if (q >= 1) issue_nobias<H, 8>(m_d, m_ahi, m_alo, ws, ws + 4096u * 4u);   // u_{q-1} = delta_q W_q
-      else issue_nobias<16, 8>(m_d, m_ahi, m_alo, ws, ws + 1024u * 4u);              // g_x = delta_0 W_0
+      if (q == L) issue_u<H, 1>(m_d, d_hi, d_mid, ws, ws + 2048u);          // u_{L-1} = delta_L W_out   (K = 16)
+      else if (q >= 1) issue_u<H, 4>(m_d, d_hi, d_mid, ws, ws + 8192u);     // u_{q-1} = delta_q W_q
+      else issue_u<16, 4>(m_d, d_hi, d_mid, ws, ws + 2048u);                // g_x = delta_0 W_0
       tc::mma_commit(c.mma_bar);
     }
     __syncwarp();
     const uint32_t u_parity = c.parity;
     c.parity ^= 1u;
-    issue_wait_dw(b.ph);
     tc::mbar_wait(b.aload_bar + buf, par);
     if (tc::elect_one()) {
       // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
@@ -285,8 +276,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
   constexpr int hidx = MAIN ? 0 : 1;
   const int L = c.L;
   const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
-  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
-  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
 
   // ---- prologue: delta_L = g; phase L (its input operand and W^T slot are already on their way) ------
   HODE_TL(220);
@@ -294,13 +283,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     float d[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) d[j] = (j < NS) ? g6[j] : 0.f;
-    uint32_t hi[16], lo[16];
-    split16(d, hi, lo);
-    HODE_TMEM_ST_X16(t_ahi, hi);
-    HODE_TMEM_ST_X16(t_alo, lo);
-    tc::wait_st();
-    tc::fence_before_sync();
-    issue_arrive();   // the issuer warp launches the u-chain of phase L once all 256 threads are here
     uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + b.row * 16;
     uint4 vh, vm;
     bf16_split8(d, vh, vm);
@@ -309,12 +291,10 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     *reinterpret_cast<uint4*>(db + ST_GRP) = make_uint4(0u, 0u, 0u, 0u);   // N = 16: features 8..15 are zero
     *reinterpret_cast<uint4*>(db + ST_GRP + ST_PART) = make_uint4(0u, 0u, 0u, 0u);
     tc::fence_proxy_async();
-  } else {
-    tc::fence_before_sync();
-    issue_arrive();
   }
+  tc::fence_before_sync();
   HODE_TL(221);
-  issue_arrive_dw(b.ph);   // ... and its weight-gradient MMAs once the BF16 operand is written
+  issue_arrive();   // the issuer warp launches phase L (mlp_bwd_issue) once all 256 threads are here
   b.ph += 1u;
   b.k += 1;
   HODE_TL(222);
@@ -335,18 +315,6 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
     float d[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) d[j] = ((mask >> j) & 1u) ? __uint_as_float(u[j]) : 0.f;
-    {
-      uint32_t hi[16], lo[16];
-      split16(d, hi, lo);
-      HODE_TMEM_ST_X16(t_ahi + half, hi);
-      HODE_TMEM_ST_X16(t_alo + half, lo);
-      split16(d + 16, hi, lo);
-      HODE_TMEM_ST_X16(t_ahi + half + 16, hi);
-      HODE_TMEM_ST_X16(t_alo + half + 16, lo);
-    }
-    tc::wait_st();
-    tc::fence_before_sync();
-    issue_arrive();
     HODE_TL(231 + 10 * p);
     {
       uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + (hidx * 4) * ST_GRP + b.row * 16;
@@ -370,8 +338,9 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       *reinterpret_cast<uint4*>(ab + ST_GRP + AB_PART) = vm;
     }
     tc::fence_proxy_async();
+    tc::fence_before_sync();
     HODE_TL(233 + 10 * p);
-    issue_arrive_dw(b.ph);
+    issue_arrive();
     b.ph += 1u;
     b.k += 1;
     HODE_TL(234 + 10 * p);
@@ -487,10 +456,9 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
   // (t0, y0) whose stage 7 receives the carry.
   const bool fsal = solver == 1 && A.save_k1 != 0;
   const int i0 = fsal ? 1 : 0;
-  const long n_units = (long)A.S * A.B;
 
   // shared memory: the forward weight image during the recomputation; during the reverse sweep the
-  // same bytes hold [weight slot][delta staging hi, lo][input staging hi, lo]
+  // same bytes hold the double-buffered operand images and W^T slots (OFF_AB / OFF_DB / OFF_WS)
   float* img = reinterpret_cast<float*>(smem_raw);
   const int bwd_cap = BWD_BYTES / 4;
   const int img_cap = ((G.fwd_floats > bwd_cap ? G.fwd_floats : bwd_cap) + 255) & ~255;
@@ -1030,8 +998,9 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
 }
 
 // ---- transposed weight image --------------------------------------------------------------------------
-// floats: [W_out^T: (n=in 64, k=out 16) hi 1024, lo 1024][W_l^T, l = L-1..1: hi 4096, lo 4096][W_0^T: (n=in 16, k=out 64) hi 1024, lo 1024]
-int tc_bwd_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024; }
+// BF16 hi / mid, K-major: element (n, k) of a block at byte (k / 8) * (N * 16) + n * 16 + (k % 8) * 2.  Bytes:
+// [W_out^T: (n = in 64, k = out 16) hi 2048, mid 2048][W_l^T, l = L-1..1: hi 8192, mid 8192][W_0^T: (n = in 16, k = out 64) hi 2048, mid 2048]
+int tc_bwd_image_floats(int L) { return 1024 + (L - 1) * 4096 + 1024; }
 
 __global__ void prep_tc_bwd_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
                                          int img_floats) {
@@ -1040,21 +1009,21 @@ __global__ void prep_tc_bwd_image_kernel(const float* __restrict__ W, float* __r
   for (int i = threadIdx.x; i < img_floats; i += blockDim.x) out[i] = 0.f;
   __syncthreads();
   // packed offsets: layer 0 at 0 (576 + 64), hidden l at 640 + (l-1)*4160, output at 640 + (L-1)*4160
-  float* dst = out;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out);
   for (int l = L; l >= 0; --l) {
     const int n_out = (l == L) ? NS : H;          // = K of the transposed operand
     const int n_in = (l == 0) ? HODE_NN_IN : H;   // = N of the transposed operand
     const int Npad = (l == 0) ? 16 : H;
     const int Kpad = (l == L) ? 16 : H;
-    const int part = (Kpad / 4) * Npad * 4;
+    const int part = (Kpad / 8) * Npad * 16;      // bytes of the hi (or mid) part
     const float* wl = w + (l == 0 ? 0 : 640 + (l - 1) * 4160);
     for (int i = threadIdx.x; i < n_out * n_in; i += blockDim.x) {
       const int o = i / n_in, in = i - o * n_in;   // W_l[o][in]  ->  (n = in, k = o)
-      uint32_t hi, lo;
-      tc::split_tf32(wl[i], hi, lo);
-      const int idx = ((o >> 2) * Npad + in) * 4 + (o & 3);
-      dst[idx] = __uint_as_float(hi);
-      dst[part + idx] = __uint_as_float(lo);
+      uint16_t hi, mid;
+      split_bf16(wl[i], hi, mid);
+      const int off = (o >> 3) * (Npad * 16) + in * 16 + (o & 7) * 2;
+      *reinterpret_cast<uint16_t*>(dst + off) = hi;
+      *reinterpret_cast<uint16_t*>(dst + part + off) = mid;
     }
     dst += 2 * part;
   }

@@ -120,6 +120,71 @@ __global__ void __launch_bounds__(128) dw_bf16_probe(const float* __restrict__ D
   if (warp == 0) tc::tmem_dealloc(tb, 128);
 }
 
+// ---- test 3: the SAME delta image read as a K-major A operand (M = 128 trajectories, K = 64 features):
+// u[t][n] = sum_f delta[t][f] * Wt[n][f] with B = W^T image [N][K] K-major: element (n, k) at byte
+// (k / 8) * (N * 16) + n * 16 + (k % 8) * 2.  variant 0: LBO = K-chunk stride, SBO = 128 B; variant 1: swapped.
+__global__ void __launch_bounds__(128) u_bf16_probe(const float* __restrict__ Dl, const float* __restrict__ Wt /*[N=64][K=64]*/,
+                                                    float* __restrict__ out /*[128][64]*/, int passes, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sd_hi = smem;
+  uint8_t* sd_mid = sd_hi + 8 * GRP;
+  uint8_t* sw_hi = sd_mid + 8 * GRP;     // 8 K-chunks x (64 n x 16 B) = 8 KB
+  uint8_t* sw_mid = sw_hi + 8 * 1024;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int g = 0; g < 8; ++g) {
+    uint4 hi, mid;
+    bf16_split8(Dl + tid * 64 + g * 8, hi, mid);
+    *reinterpret_cast<uint4*>(sd_hi + g * GRP + tid * 16) = hi;
+    *reinterpret_cast<uint4*>(sd_mid + g * GRP + tid * 16) = mid;
+  }
+  if (tid < 64) {
+    for (int kc = 0; kc < 8; ++kc) {
+      uint4 hi, mid;
+      bf16_split8(Wt + tid * 64 + kc * 8, hi, mid);
+      *reinterpret_cast<uint4*>(sw_hi + kc * 1024 + tid * 16) = hi;
+      *reinterpret_cast<uint4*>(sw_mid + kc * 1024 + tid * 16) = mid;
+    }
+  }
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tb = tmem_base_s, lane_base = (uint32_t)(warp * 32) << 16;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16(128, 64, 0, 0);
+    const uint32_t a_lbo = variant == 0 ? (uint32_t)GRP : 128u, a_sbo = variant == 0 ? 128u : (uint32_t)GRP;
+    const uint32_t b_lbo = variant == 0 ? 1024u : 128u, b_sbo = variant == 0 ? 128u : 1024u;
+    const uint32_t a_hi = tc::smem_u32(sd_hi), a_mid = tc::smem_u32(sd_mid), b_hi = tc::smem_u32(sw_hi), b_mid = tc::smem_u32(sw_mid);
+    uint32_t acc = 0u;
+    // one MMA = K 16 = 2 K-chunks: A advances 2 * GRP, B advances 2 * 1024
+    if (passes == 3) {
+      for (int ks = 0; ks < 4; ++ks, acc = 1u)
+        mma_bf16_ss(tb, tc::make_desc(a_mid + ks * 2 * GRP, a_lbo, a_sbo), tc::make_desc(b_hi + ks * 2048, b_lbo, b_sbo), idesc, acc);
+      for (int ks = 0; ks < 4; ++ks)
+        mma_bf16_ss(tb, tc::make_desc(a_hi + ks * 2 * GRP, a_lbo, a_sbo), tc::make_desc(b_mid + ks * 2048, b_lbo, b_sbo), idesc, 1u);
+    }
+    for (int ks = 0; ks < 4; ++ks, acc = 1u)
+      mma_bf16_ss(tb, tc::make_desc(a_hi + ks * 2 * GRP, a_lbo, a_sbo), tc::make_desc(b_hi + ks * 2048, b_lbo, b_sbo), idesc, acc);
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  uint32_t v[16];
+  for (int c16 = 0; c16 < 4; ++c16) {
+    HODE_TMEM_LD_X16(tb + lane_base + c16 * 16, v);
+    tc::wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[tid * 64 + c16 * 16 + j] = __uint_as_float(v[j]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tb, 64);
+}
+
 static float bf16r(float x) {
   uint32_t u; memcpy(&u, &x, 4);
   u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
@@ -190,6 +255,38 @@ int main() {
             if (l1 > 0) worst = fmax(worst, fabs(O[k * 80 + j] - r) / l1);
           }
         printf("passes %d  D[128 x 16] = [a|1]^T delta  variant %d: max err/sum|ab| %.3e\n", passes, variant, worst);
+      }
+    }
+  }
+  // ---- test 3: K-major A (the delta image) x K-major B (W^T image)
+  {
+    std::vector<float> Wt(64 * 64), Wr(64 * 64);
+    for (auto& x : Wt) x = rnd() * 0.3f;
+    for (size_t i = 0; i < Wt.size(); ++i) Wr[i] = bf16r(Wt[i]);
+    float *dWt, *dU;
+    CK(cudaMalloc(&dWt, Wt.size() * 4)); CK(cudaMalloc(&dU, 128 * 64 * 4));
+    const size_t smem3 = 2 * 8 * GRP + 2 * 8 * 1024;
+    CK(cudaFuncSetAttribute(u_bf16_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    std::vector<float> U(128 * 64);
+    for (int passes : {1, 3}) {
+      const std::vector<float>& Din = passes == 1 ? Dr : Dl;
+      const std::vector<float>& Win = passes == 1 ? Wr : Wt;
+      CK(cudaMemcpy(dDl, Din.data(), Din.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dWt, Win.data(), Win.size() * 4, cudaMemcpyHostToDevice));
+      for (int variant = 0; variant < 2; ++variant) {
+        CK(cudaMemset(dU, 0, 128 * 64 * 4));
+        u_bf16_probe<<<1, 128, smem3>>>(dDl, dWt, dU, passes, variant);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("test3 variant %d: CUDA error %s\n", variant, cudaGetErrorString(e)); return 1; }
+        CK(cudaMemcpy(U.data(), dU, U.size() * 4, cudaMemcpyDeviceToHost));
+        double worst = 0;
+        for (int t = 0; t < 128; ++t)
+          for (int n = 0; n < 64; ++n) {
+            double s = 0, l1 = 0;
+            for (int f = 0; f < 64; ++f) { const double p = (double)Din[t * 64 + f] * (double)Win[n * 64 + f]; s += p; l1 += fabs(p); }
+            if (l1 > 0) worst = fmax(worst, fabs(U[t * 64 + n] - s) / l1);
+          }
+        printf("passes %d  u[128 x 64] = delta W (K-major A and B)  variant %d: max err/sum|ab| %.3e\n", passes, variant, worst);
       }
     }
   }
