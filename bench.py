@@ -225,7 +225,14 @@ def run_ours(args):
         if not bwd:
             return ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, **kw)
         traj, info, tape = ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, save_steps=True, **kw)
-        grads["out"] = ops.rollout_bwd(tape, d_g)      # grad of mean(traj) w.r.t. y0, theta, W
+        g_y0, g_theta, g_W = ops.rollout_bwd(tape, d_g)      # grad of mean(traj) w.r.t. y0, theta, W
+        if world > 1:
+            # the path's one exchange step: gradients of the shared parameters + a loss slot,
+            # one packed float32 buffer (54 KB), one NCCL all-reduce
+            packed = torch.cat([g_theta.reshape(-1), g_W.reshape(-1), traj.new_zeros(1)])
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            grads["packed"] = packed
+        grads["out"] = (g_y0, g_theta, g_W)
         return traj, info
 
     def barrier():

@@ -213,6 +213,27 @@ def test_loss_backward_matches_reference(dev, tag):
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
 
 
+def test_loss_stacked_physics_launch_equals_the_loop(dev):
+    """loss() runs the physics re-solves as one stacked launch (fused_physics); the reference-shaped
+    Python loop must give the same value and the same gradients on the same physics indices."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    d = golden("loss_nn64x4")
+    to = lambda a: torch.from_numpy(a).to(dev)
+    batch = {"initial_state": to(d["y0"]), "observations": to(d["obs"]), "time_points": to(d["t"]),
+             "external_inputs": {"meal": to(d["meal"]), "tVNS": to(d["tvns"])}}
+    out = {}
+    for fused in (True, False):
+        m = HybridODENN(nn_hidden=64, nn_layers=4, device=dev)
+        _load_W(m, d["W"])
+        m.fused_physics = fused
+        torch.manual_seed(7)
+        loss = m.loss(batch, lambda1=1.0, lambda2=1.0)
+        loss.backward()
+        out[fused] = (loss.item(), torch.cat([p.grad.reshape(-1) for _, p in m.nn_residual.named_parameters()]).cpu().numpy())
+    assert abs(out[True][0] - out[False][0]) <= 1e-6 * abs(out[False][0])
+    assert relmax(out[True][1], out[False][1]) < 1e-5
+
+
 def test_differentiable_forward_trains_the_data_term(dev):
     """differentiable=True: the data-MSE term, which carries no gradient in the reference, now
     reaches the network and initial state; one Adam step lowers it."""
