@@ -241,6 +241,97 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   return 0;
 }
 
+// ---- fused data-loss step ---------------------------------------------------------------------------
+namespace {
+constexpr int MSE_BLOCK = 256, MSE_ELEMS_PER_BLOCK = 256 * 16;
+
+// grad[s][i] = scale * (traj[s][i] - obs[i]);  partial[s][block] = sum of squared residuals of the block's
+// elements, reduced in a fixed tree order
+__global__ void __launch_bounds__(MSE_BLOCK) mse_grad_kernel(const float* __restrict__ traj, const float* __restrict__ obs,
+                                                             float* __restrict__ grad, float* __restrict__ partial,
+                                                             long n_per_set, float scale) {
+  __shared__ float red[MSE_BLOCK];
+  const int s = blockIdx.y;
+  const long base = (long)blockIdx.x * MSE_ELEMS_PER_BLOCK;
+  const float* tr = traj + (size_t)s * n_per_set;
+  float* g = grad + (size_t)s * n_per_set;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < MSE_ELEMS_PER_BLOCK / MSE_BLOCK; ++j) {
+    const long i = base + (long)j * MSE_BLOCK + threadIdx.x;
+    if (i < n_per_set) {
+      const float d = tr[i] - obs[i];
+      g[i] = scale * d;
+      acc = fmaf(d, d, acc);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = MSE_BLOCK / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)s * gridDim.x + blockIdx.x] = red[0];
+}
+
+// loss[s] = inv_n * sum of the set's block partials, accumulated in double in block order
+__global__ void __launch_bounds__(MSE_BLOCK) mse_final_kernel(const float* __restrict__ partial, int n_blocks, double inv_n,
+                                                              float* __restrict__ loss) {
+  __shared__ double red[MSE_BLOCK];
+  const int s = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_blocks; i += MSE_BLOCK) acc += (double)partial[(size_t)s * n_blocks + i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = MSE_BLOCK / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[s] = (float)(red[0] * inv_n);
+}
+}  // namespace
+
+int hode_loss_fused_fwd_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, const float* u_meal,
+                            const float* u_tvns, const float* u_gd, const float* theta, const float* W,
+                            const float* obs, float* traj, int32_t* status, int32_t* counters, float* loss,
+                            float* grad_traj_scratch, float* grad_y0, float* grad_theta, float* grad_W,
+                            void* fwd_workspace, size_t fwd_workspace_bytes, void* bwd_workspace,
+                            size_t bwd_workspace_bytes, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!obs || !loss || !grad_traj_scratch) return fail(HODE_E_NULL, "obs/loss/grad_traj_scratch is NULL");
+  if (!cfg->save_steps)
+    return fail(HODE_E_UNSUPPORTED, "hode_loss_fused_fwd_bwd needs cfg.save_steps = 1");
+  const int S = cfg->n_samples > 0 ? cfg->n_samples : 1;
+  const long n_per_set = (long)cfg->n_traj * cfg->n_obs * HODE_N_STATE;
+  const int n_blocks = (int)((n_per_set + MSE_ELEMS_PER_BLOCK - 1) / MSE_ELEMS_PER_BLOCK);
+  size_t need_bwd = 0;
+  hode_workspace_bytes(cfg, nullptr, &need_bwd);
+  // the block partials live at the head of the backward workspace: consumed (stream order) before
+  // hode_rollout_bwd overwrites it
+  if (!bwd_workspace || bwd_workspace_bytes < need_bwd || bwd_workspace_bytes < (size_t)S * n_blocks * sizeof(float))
+    return fail(HODE_E_WORKSPACE, "backward workspace missing or too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfg->n_traj == 0) {
+    cudaError_t e = cudaMemsetAsync(loss, 0, (size_t)S * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "hode_loss_fused_fwd_bwd memset");
+    return 0;
+  }
+  rc = hode_rollout_fwd(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W, traj, status, counters, fwd_workspace,
+                        fwd_workspace_bytes, stream);
+  if (rc) return rc;
+  float* partial = reinterpret_cast<float*>(bwd_workspace);
+  mse_grad_kernel<<<dim3((unsigned)n_blocks, (unsigned)S), MSE_BLOCK, 0, st>>>(traj, obs, grad_traj_scratch, partial,
+                                                                             n_per_set, (float)(2.0 / (double)n_per_set));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "hode_loss_fused_fwd_bwd residual launch");
+  mse_final_kernel<<<S, MSE_BLOCK, 0, st>>>(partial, n_blocks, 1.0 / (double)n_per_set, loss);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "hode_loss_fused_fwd_bwd reduction launch");
+  return hode_rollout_bwd(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W, grad_traj_scratch, grad_y0, grad_theta,
+                          grad_W, fwd_workspace, fwd_workspace_bytes, bwd_workspace, bwd_workspace_bytes, stream);
+}
+
 int hode_rhs_vjp(const hode_cfg* cfg, const float* t, const float* state, const float* u_meal,
                  const float* u_tvns, const float* u_gd, const float* theta, const float* W,
                  const float* grad_out, float* grad_state, float* grad_theta, float* grad_W,

@@ -216,6 +216,56 @@ def rollout_bwd(tape: RolloutTape, grad_traj: torch.Tensor, need_y0: bool = True
     return g_y0, g_theta, g_W
 
 
+def data_loss_step(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
+                   theta: torch.Tensor, W: Optional[torch.Tensor], obs: torch.Tensor, hidden: int = 64,
+                   layers: int = 4, solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8,
+                   n_substeps: int = 4, kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
+                   device: Optional[torch.device] = None, max_saved_steps: int = 0, need_y0: bool = False):
+    """loss = mean((rollout - obs)^2) and its gradients in ONE library call (hode_loss_fused_fwd_bwd):
+    returns (loss [S] or scalar, grad_y0 or None, grad_theta, grad_W or None, traj, RolloutInfo)."""
+    device = torch.device(device) if device is not None else y0.device
+    _require_cuda(device)
+    if solver.lower() not in SOLVERS:
+        raise HodeError(f"solver '{solver}' is not implemented on the GPU path; available: {sorted(SOLVERS)}")
+    squeeze_s = theta.dim() == 1
+    cfg, bufs = prepare(y0, t_obs, inputs, theta, W, hidden, layers, device)
+    cfg.solver = SOLVERS[solver.lower()]
+    cfg.rtol, cfg.atol = float(rtol), float(atol)
+    cfg.n_substeps = int(n_substeps)
+    cfg.max_steps = int(max_steps)
+    cfg.kink_mode = KINKS[kinks]
+    cfg.save_steps = 1
+    cfg.max_saved_steps = int(max_saved_steps)
+    if cfg.mlp != _lib.MLP_NONE:
+        cfg.mlp = PRECISIONS[precision]
+    B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
+    P = 0 if bufs["W"] is None else bufs["W"].shape[1]
+    o = _f32c(obs.reshape(B, T, 6), device)
+    with torch.cuda.device(device):
+        traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
+        g_traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
+        status = torch.empty((S, B), dtype=torch.int32, device=device)
+        counters = torch.empty((2, S, B), dtype=torch.int32, device=device)
+        loss = torch.empty(S, dtype=torch.float32, device=device)
+        g_y0 = torch.empty((S, B, 6), dtype=torch.float32, device=device) if need_y0 else None
+        g_theta = torch.empty((S, _lib.N_THETA), dtype=torch.float32, device=device)
+        g_W = torch.empty((S, P), dtype=torch.float32, device=device) if P else None
+        fwd_bytes, bwd_bytes = workspace_bytes(cfg)
+        bwd_bytes = max(bwd_bytes, 4 * S * ((B * T * 6 + 4095) // 4096), 16)
+        ws = torch.empty(max(fwd_bytes, 16), dtype=torch.uint8, device=device)
+        bws = torch.empty(bwd_bytes, dtype=torch.uint8, device=device)
+        rc = _lib.lib().hode_loss_fused_fwd_bwd(
+            ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]), _ptr(bufs["tVNS"]),
+            _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]), _ptr(o), _ptr(traj), _ptr(status),
+            _ptr(counters), _ptr(loss), _ptr(g_traj), _ptr(g_y0), _ptr(g_theta), _ptr(g_W), _ptr(ws), fwd_bytes,
+            _ptr(bws), bwd_bytes, _stream(device))
+    _lib.check(rc, "hode_loss_fused_fwd_bwd")
+    if squeeze_s:
+        return (loss[0], None if g_y0 is None else g_y0[0], g_theta[0], None if g_W is None else g_W[0], traj[0],
+                RolloutInfo(status[0], counters[0, 0], counters[1, 0]))
+    return loss, g_y0, g_theta, g_W, traj, RolloutInfo(status, counters[0], counters[1])
+
+
 def saved_steps(tape: RolloutTape):
     """(n [S*B] int32, t [max_saved, S*B] float64) views of the recorded accepted steps
     (diagnostics / tests: the step sequence the adjoint differentiates)."""

@@ -168,6 +168,29 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
                      void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
 
 /*
+ * One training-shaped step of the data term in a single call: rollout with recorded steps,
+ * loss[s] = mean((traj[s] - obs)^2) over [B,T,6] and its discrete-adjoint gradients.  Replaces
+ * `predictions = self.forward(...)`, `F.mse_loss(predictions, observations)` (reference
+ * models/hybrid_ode_nn.py:284-288) and the backward of that term in train_epoch
+ * (train/train_hybrid.py:244-252) — which in the reference carries no gradient because forward
+ * returns a graph-free tensor (:248).  Same contracts as hode_rollout_fwd / hode_rollout_bwd
+ * (cfg.save_steps must be 1); between them the residual 2 (traj - obs) / (B T 6) is formed on
+ * the device and the loss is reduced in a fixed order (bit-reproducible).
+ *   obs [B,T,6] in (shared by the S parameter sets);  traj [S,B,T,6] out;  loss [S] out (device);
+ *   grad_traj_scratch [S,B,T,6] (caller-owned scratch, holds dloss/dtraj on return);
+ *   grad_y0 [S,B,6] / grad_theta [S,17] / grad_W [S,P] out (each may be NULL).
+ * The physics-residual and L2 / KL terms of the reference's loss are parameter-side sums the
+ * caller adds (hode_rhs + hode_rhs_vjp; models/hybrid_ode_nn.py:327-345).
+ */
+int hode_loss_fused_fwd_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
+                            const float* u_meal, const float* u_tvns, const float* u_gd,
+                            const float* theta, const float* W, const float* obs, float* traj,
+                            int32_t* status, int32_t* counters, float* loss,
+                            float* grad_traj_scratch, float* grad_y0, float* grad_theta,
+                            float* grad_W, void* fwd_workspace, size_t fwd_workspace_bytes,
+                            void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
+
+/*
  * Vector-Jacobian product of hode_rhs: the backward of HybridODENN.ode_residual, the only
  * differentiable model call of the reference's loss (models/hybrid_ode_nn.py:327 -> :330,
  * loss.backward() at train/train_hybrid.py:252).

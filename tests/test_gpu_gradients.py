@@ -346,3 +346,26 @@ def test_tensor_core_adjoint_repeatable_over_many_launches(dev):
             assert bool((info.status == 0).all()) and all(bool(torch.isfinite(o).all()) for o in out)
         else:
             assert all(torch.equal(a, b) for a, b in zip(ref, out))
+
+
+@pytest.mark.parametrize("precision,S", [("tf32x3", 1), ("fp32", 2)])
+def test_fused_data_loss_step_equals_the_composition(dev, precision, S):
+    """hode_loss_fused_fwd_bwd = hode_rollout_fwd + mean squared residual + hode_rollout_bwd: identical
+    trajectories and gradients, loss equal to torch's mse_loss."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T = 700, 13
+    y0, t, ins = cohort(B, T, seed=5, horizon=1.0)
+    theta = np.tile(golden("rhs_mech")["theta"], (S, 1)) if S > 1 else golden("rhs_mech")["theta"]
+    W = np.stack([random_mlp(64, 4, seed=60 + s, out_std=0.05) for s in range(S)]) if S > 1 else random_mlp(64, 4, seed=60, out_std=0.05)
+    obs = (np.repeat(y0[:, None, :], T, 1) * (1 + 0.1 * np.random.default_rng(6).normal(0, 1, (B, T, 6)))).astype(np.float32)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    args = (tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W))
+    kw = dict(solver="dopri5", precision=precision, device=dev)
+    loss, g_y0, g_theta, g_W, traj, info = ops.data_loss_step(*args, tt(obs), need_y0=True, **kw)
+    traj2, info2, tape = ops.rollout(*args, save_steps=True, **kw)
+    assert torch.equal(traj, traj2) and torch.equal(info.status, info2.status)
+    resid = traj2 - tt(obs)
+    ref_loss = (resid.double() ** 2).mean(dim=tuple(range(resid.dim() - 3, resid.dim())))
+    assert float((loss.double() - ref_loss).abs().max()) <= 1e-6 * float(ref_loss.abs().max())
+    r_y0, r_theta, r_W = ops.rollout_bwd(tape, resid * (2.0 / (B * T * 6)))   # one fp32 multiply, as in the kernel
+    assert torch.equal(g_theta, r_theta) and torch.equal(g_W, r_W) and torch.equal(g_y0, r_y0)
