@@ -30,7 +30,7 @@ STATUS_TEXT = {
 EXPORTS = [
     "hode_version", "hode_last_error_string", "hode_mlp_param_count", "hode_workspace_bytes",
     "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs", "hode_rhs_vjp",
-    "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd",
+    "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd", "hode_generate_4gi",
 ]
 
 
@@ -84,6 +84,9 @@ def lib() -> ctypes.CDLL:
     L.hode_loss_fused_fwd_bwd.restype = ctypes.c_int
     L.hode_loss_fused_fwd_bwd.argtypes = ([ctypes.POINTER(HodeCfg)] + [_P] * 16
                                           + [_P, ctypes.c_size_t, _P, ctypes.c_size_t, _P])
+    L.hode_generate_4gi.restype = ctypes.c_int
+    L.hode_generate_4gi.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_int32, ctypes.c_double,
+                                    ctypes.c_double, _P, _P, _P, _P, _P]
     L.hode_rhs_vjp.restype = ctypes.c_int
     L.hode_rhs_vjp.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 12 + [ctypes.c_size_t, _P]
     L.hode_vi_predictive.restype = ctypes.c_int

@@ -241,6 +241,21 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   return 0;
 }
 
+int hode_generate_4gi(int32_t n_subjects, int32_t n_obs, double interval_hours, int32_t patient_type, double rtol,
+                      double atol, const float* baselines, const float* meal_rate, float* out, int32_t* status,
+                      void* stream) {
+  if (n_subjects < 0 || n_obs < 1) return fail(HODE_E_SIZE, "n_subjects < 0 or n_obs < 1");
+  if (!(interval_hours > 0.0)) return fail(HODE_E_SIZE, "interval_hours must be positive");
+  if (patient_type != 0 && patient_type != 1) return fail(HODE_E_UNSUPPORTED, "patient_type must be 0 (T2DM) or 1 (HV)");
+  if (n_subjects == 0) return 0;
+  if (!baselines || !out) return fail(HODE_E_NULL, "baselines/out is NULL");
+  cudaError_t e = hode::launch_gen4gi(n_subjects, n_obs, interval_hours, patient_type, rtol > 0.0 ? rtol : 1e-9,
+                                      atol > 0.0 ? atol : 1e-12, baselines, meal_rate, out, status,
+                                      (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "hode_generate_4gi launch");
+  return 0;
+}
+
 // ---- fused data-loss step ---------------------------------------------------------------------------
 namespace {
 constexpr int MSE_BLOCK = 256, MSE_ELEMS_PER_BLOCK = 256 * 16;

@@ -53,4 +53,9 @@ size_t adj_tc_workspace_bytes(const AdjTcPlan& p);
 cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, float* grad_y0,
                                   float* grad_theta, float* grad_W, void* workspace, cudaStream_t stream);
 
+// on-device cohort generation (hode_gen4gi.cu)
+cudaError_t launch_gen4gi(int n, int T, double dt_hours, int patient_type, double rtol, double atol,
+                          const float* baselines, const float* meal_rate, float* out, int32_t* status,
+                          cudaStream_t stream);
+
 }  // namespace hode

@@ -266,6 +266,34 @@ def data_loss_step(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[
     return loss, g_y0, g_theta, g_W, traj, RolloutInfo(status, counters[0], counters[1])
 
 
+PATIENT_TYPES = {"T2DM": 0, "HV": 1}
+
+
+def generate_4gi(baselines: torch.Tensor, meal_rate: Optional[torch.Tensor] = None, n_obs: int = 61,
+                 interval_hours: float = 5.0 / 60.0, patient_type: str = "T2DM", rtol: float = 0.0, atol: float = 0.0,
+                 device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's 4GI simulator for a whole cohort in one launch (hode_generate_4gi; reference
+    data/generate4GI.py FourGIModel.simulate).  baselines [N,5] (glucose, insulin, GLP-1, glucagon, GIP),
+    meal_rate [N, n_obs-1] in mmol/h per sampling interval (None = no meals).
+    Returns (concentrations [N, n_obs, 5], status [N])."""
+    device = torch.device(device) if device is not None else baselines.device
+    _require_cuda(device)
+    if patient_type not in PATIENT_TYPES:
+        raise HodeError(f"patient_type must be one of {sorted(PATIENT_TYPES)}")
+    b = _f32c(baselines.reshape(-1, 5), device)
+    N = b.shape[0]
+    m = None
+    if meal_rate is not None:
+        m = _f32c(meal_rate.reshape(N, n_obs - 1), device)
+    with torch.cuda.device(device):
+        out = torch.empty((N, n_obs, 5), dtype=torch.float32, device=device)
+        status = torch.empty(N, dtype=torch.int32, device=device)
+        rc = _lib.lib().hode_generate_4gi(N, int(n_obs), float(interval_hours), PATIENT_TYPES[patient_type], float(rtol),
+                                          float(atol), _ptr(b), _ptr(m), _ptr(out), _ptr(status), _stream(device))
+    _lib.check(rc, "hode_generate_4gi")
+    return out, status
+
+
 def saved_steps(tape: RolloutTape):
     """(n [S*B] int32, t [max_saved, S*B] float64) views of the recorded accepted steps
     (diagnostics / tests: the step sequence the adjoint differentiates)."""

@@ -78,3 +78,41 @@ def random_mlp(hidden: int = 64, layers: int = 4, seed: int = 0, out_std: float 
 
 THETA_DEFAULT = np.array([0.0104, 0.025, 0.003, 5.0, 60.0, 0.1, 50.0, 80.0, 9.0, 7.0, 0.02,
                           0.01, 1000.0, 2.0, 0.05, 0.001, 0.01], dtype=np.float32)
+
+
+def meal_rate_from_events(meal_times, meal_sizes, n_obs: int = 61, interval_hours: float = 5.0 / 60.0,
+                          n_subjects: int = 1) -> np.ndarray:
+    """[n_subjects, n_obs-1] glucose input (mmol/h) per sampling interval, the way the reference spreads a
+    meal over the interval that contains it (data/generate4GI.py:193-197: the last matching meal wins)."""
+    t = np.arange(n_obs) * interval_hours
+    rate = np.zeros(n_obs - 1, dtype=np.float32)
+    for i in range(n_obs - 1):
+        for mt, ms in zip(meal_times, meal_sizes):
+            if t[i] <= mt < t[i + 1]:
+                rate[i] = ms / (t[i + 1] - t[i])
+    return np.tile(rate[None, :], (n_subjects, 1))
+
+
+def fourgi_baselines(n_subjects: int, seed: int = 0) -> np.ndarray:
+    """[n,5] per-subject baselines with generate_dataset's variability (data/generate4GI.py:64-70, :231-235):
+    glucose 7.0 (cv 0.10), insulin 50, GLP-1 10, glucagon 25, GIP 20 (cv 0.15)."""
+    rng = np.random.default_rng(seed)
+    base = np.array([7.0, 50.0, 10.0, 25.0, 20.0])
+    cv = np.array([0.1, 0.15, 0.15, 0.15, 0.15])
+    return (base * (1.0 + cv * rng.normal(0, 1, (n_subjects, 5)))).astype(np.float32)
+
+
+def fourgi_states(conc):
+    """[N,T,5] generator output (glucose, insulin, GLP-1, glucagon, GIP) -> [N,T,6] model states in
+    GlucoseDataset's column order [glucose, insulin, glucagon, GLP-1, ge = 0, ffa = 1]
+    (train/train_hybrid.py:70-83).  Works on numpy arrays and torch tensors."""
+    if isinstance(conc, np.ndarray):
+        out = np.zeros(conc.shape[:-1] + (6,), dtype=conc.dtype)
+    else:
+        out = conc.new_zeros(conc.shape[:-1] + (6,))
+    out[..., 0] = conc[..., 0]
+    out[..., 1] = conc[..., 1]
+    out[..., 2] = conc[..., 3]
+    out[..., 3] = conc[..., 2]
+    out[..., 5] = 1.0
+    return out

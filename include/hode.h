@@ -227,6 +227,25 @@ int hode_rhs(const hode_cfg* cfg, const float* t, const float* state, const floa
              float* out, void* stream);
 
 /*
+ * Cohort generation on the device (the step before the path): the reference's
+ * 8-state 4GI simulator FourGIModel.simulate (data/generate4GI.py:72-211 — equations :72-160, one
+ * scipy.integrate.odeint call per sampling interval with the meal spread over that interval
+ * :188-200) for n_subjects subjects at once, one thread per subject, adaptive DP5(4) in float64.
+ *   patient_type  0 = 'T2DM', 1 = 'HV' (:19-24, :103-106)
+ *   baselines [n,5]       glucose, insulin, GLP-1, glucagon, GIP baselines (BSL*, :64-70; generate_dataset
+ *                         perturbs them per subject, :231-235)
+ *   meal_rate [n,T-1]     glucose input (mmol/h) during sampling interval k, or NULL (no meals);
+ *                         the reference's value is meal_size / interval_hours for the interval holding meal_time
+ *   out [n,T,5]           concentrations at the sampling times: glucose (mmol/L), insulin, GLP-1,
+ *                         glucagon, GIP (pmol/L) — simulate()'s return values (:204-210)
+ *   status [n] (may be NULL): HODE_ST_*; rows after a failure are zero
+ * rtol / atol <= 0 select 1e-9 / 1e-12.
+ */
+int hode_generate_4gi(int32_t n_subjects, int32_t n_obs, double interval_hours, int32_t patient_type,
+                      double rtol, double atol, const float* baselines, const float* meal_rate,
+                      float* out, int32_t* status, void* stream);
+
+/*
  * Host-buffer convenience entry (the e2e path timed by bench.py): same contract as
  * hode_rollout_fwd but every pointer is HOST memory (pinned or pageable); the call
  * stages H2D copies, runs the rollout and copies traj/status/counters back, all on

@@ -122,3 +122,27 @@ def test_variational_parameters_follow_the_reference_formulas():
     assert mu.shape == (7,) and ls.shape == (7,)
     with pytest.raises(TypeError):
         hode.bayes_loss(None, torch.zeros(1))
+
+
+def test_generator_host_helpers():
+    """Meal spreading and the state-column mapping of the cohort generator (no GPU): the reference puts a meal of
+    size s at time m into the sampling interval [t_i, t_i+1) that contains m, as the rate s / (t_i+1 - t_i)
+    (data/generate4GI.py:193-197); GlucoseDataset orders the states glucose, insulin, glucagon, GLP-1, ge, ffa
+    (train/train_hybrid.py:70-83)."""
+    import numpy as np
+    from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import fourgi_baselines, fourgi_states, meal_rate_from_events
+    r = meal_rate_from_events([0.5, 2.5], [75, 50], 61, 5 / 60, 3)
+    assert r.shape == (3, 60)
+    nz = np.nonzero(r[0])[0].tolist()
+    assert nz == [6, 30]
+    assert abs(r[0, 6] - 75 / (5 / 60)) < 1e-3 and abs(r[0, 30] - 50 / (5 / 60)) < 1e-3
+    assert np.array_equal(r[0], r[2])
+    assert float(meal_rate_from_events([5.0], [10], 61, 5 / 60)[0].sum()) == 0.0      # a meal at t_end falls in no interval
+    conc = np.arange(2 * 3 * 5, dtype=np.float32).reshape(2, 3, 5)
+    st = fourgi_states(conc)
+    assert st.shape == (2, 3, 6)
+    assert np.array_equal(st[..., 0], conc[..., 0]) and np.array_equal(st[..., 1], conc[..., 1])
+    assert np.array_equal(st[..., 2], conc[..., 3]) and np.array_equal(st[..., 3], conc[..., 2])
+    assert float(np.abs(st[..., 4]).max()) == 0.0 and float(st[..., 5].min()) == 1.0
+    b = fourgi_baselines(1000, seed=1)
+    assert b.shape == (1000, 5) and abs(float(b[:, 0].mean()) - 7.0) < 0.1 and abs(float(b[:, 1].std()) / 50.0 - 0.15) < 0.02
