@@ -269,6 +269,41 @@ def test_tensor_core_adjoint_matches_autograd(dev, solver, layers):
     assert max(errs) < TOL, errs
 
 
+def test_tensor_core_adjoint_scipy_kinks_and_constant_inputs(dev):
+    """The tensor-core adjoint away from its cached-input fast path: kinks='scipy' (steps may straddle input
+    kinks, every stage looks its interval up) and per-trajectory constant inputs with GD present."""
+    errs = _adjoint_case(dev, 6, 11, 64, 3, "dopri5", kinks="scipy", seed=31, precision="tf32x3")
+    assert max(errs) < TOL, errs
+    errs = _adjoint_case(dev, 5, 9, 64, 4, "dopri5", const_inputs=True, seed=33, precision="tf32x3")
+    assert max(errs) < TOL, errs
+
+
+def test_tensor_core_adjoint_parameter_sets_dopri5(dev):
+    """S = 3 parameter sets with adaptive steps (per-set step counts, per-set sort and schedule): every set's
+    gradients equal a single-set launch of the same inputs up to summation order."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T, S = 700, 13, 3
+    y0, t, ins = cohort(B, T, seed=71, horizon=1.0)
+    theta = np.tile(golden("rhs_mech")["theta"], (S, 1))
+    theta[1, 8] = 8.0
+    theta[2, 0] *= 1.1
+    W = np.stack([random_mlp(64, 4, seed=80 + s, out_std=0.05) for s in range(S)])
+    g = np.random.default_rng(72).normal(0, 1, (S, B, T, 6)).astype(np.float32)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tin = {k: tt(v) for k, v in ins.items()}
+    kw = dict(solver="dopri5", precision="tf32x3", device=dev, save_steps=True)
+    _, info, tape = ops.rollout(tt(y0), tt(t), tin, tt(theta), tt(W), **kw)
+    assert bool((info.status == 0).all())
+    gy, gth, gW = ops.rollout_bwd(tape, tt(g))
+    for s in range(S):
+        _, info1, tape1 = ops.rollout(tt(y0), tt(t), tin, tt(theta[s]), tt(W[s]), **kw)
+        assert torch.equal(info1.n_accept, info.n_accept[s])
+        y1, th1, W1 = ops.rollout_bwd(tape1, tt(g[s]))
+        assert relmax(gy[s].cpu().numpy(), y1.cpu().numpy()) < 1e-5
+        assert relmax(gth[s].cpu().numpy(), th1.cpu().numpy()) < 1e-5
+        assert relmax(gW[s].cpu().numpy(), W1.cpu().numpy()) < 1e-5
+
+
 def test_tensor_core_adjoint_equals_fp32_adjoint_at_scale(dev):
     """Fixed-step rollouts take identical steps on both paths, so the two adjoints must agree:
     B spans several tiles per CTA is exercised with a small grid by S = 2 parameter sets."""
