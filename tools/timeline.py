@@ -10,7 +10,7 @@ flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "--expt-relaxed-constexpr"]
 subprocess.run(["nvcc", *flags, "-DHODE_TIMELINE", "-c", os.path.join(CSRC, "hode_rollout_tc.cu"), "-o",
                 "/tmp/hode_rollout_tc_tl.o"], check=True)
-objs = [os.path.join(CSRC, f) for f in ("hode_api.o", "hode_rollout_simt.o", "hode_adjoint_simt.o", "hode_adjoint_tc.o")]
+objs = [os.path.join(CSRC, f) for f in ("hode_api.o", "hode_rollout_simt.o", "hode_adjoint_simt.o", "hode_adjoint_tc.o", "hode_gen4gi.o")]
 lib = os.path.join(ROOT, "hybrid_ode_for_glp_1_and_glucose_b200", "libhode.so")
 os.rename(lib, lib + ".bak")
 try:
