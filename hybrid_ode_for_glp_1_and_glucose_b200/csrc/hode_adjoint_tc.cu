@@ -92,7 +92,8 @@ constexpr uint32_t DW_H0 = 208, DW_0 = 448, DW_O = 464;
 constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART;
 constexpr int DB_BYTES = 2 * ST_PART;
 constexpr int WS_BYTES = 2 * 64 * 64 * 2;   // one layer's W^T: BF16 hi, mid
-constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_WS = OFF_DB + 2 * DB_BYTES;
+constexpr int N_AB = 3;   // input operands are fetched TWO phases ahead (they stream from HBM: the stash of 148 CTAs exceeds L2)
+constexpr int OFF_AB = 0, OFF_DB = OFF_AB + N_AB * AB_BYTES, OFF_WS = OFF_DB + 2 * DB_BYTES;
 constexpr int BWD_BYTES = OFF_WS + 2 * WS_BYTES;
 
 // kind::f16 instruction descriptors: D = f32, A = B = BF16; both operands MN-major / both K-major
@@ -159,7 +160,7 @@ struct BwdCtx {
   uint8_t* stash_cta;         // global: this CTA's activation stash
   uint8_t* stage_blk;         // stash block of the current stage, layer 0
   uint64_t* wload_bar;        // [2] W^T slot filled
-  uint64_t* aload_bar;        // [2] input operand filled
+  uint64_t* aload_bar;        // [N_AB] input operand filled (phase ph uses buffer ph % N_AB, parity (ph / N_AB) & 1)
   uint64_t* gemm_bar;         // weight-gradient MMAs of a phase complete
   uint32_t ph;                // phases issued so far
   int k, k_end, stage_top;    // phase index inside the current sweep, phases in the sweep, stage of phase 0
@@ -177,10 +178,10 @@ __device__ __forceinline__ void wait_gemm(const BwdCtx& b) {
 __device__ __forceinline__ void prefetch_A(const BwdCtx& b, int L, int k1, uint32_t ph1) {
   if (k1 >= b.k_end) return;
   const int st = b.stage_top - k1 / (L + 1), q = L - k1 % (L + 1);
-  uint64_t* bar = b.aload_bar + (ph1 & 1u);
+  uint64_t* bar = b.aload_bar + (ph1 % N_AB);
   if (q >= 1) {
     const uint8_t* src = b.stash_cta + ((size_t)st * L + (q - 1)) * ST_BLK;
-    uint8_t* dst = b.smem + OFF_AB + (ph1 & 1u) * AB_BYTES;
+    uint8_t* dst = b.smem + OFF_AB + (ph1 % N_AB) * AB_BYTES;
     tc::mbar_expect_tx(bar, 2u * ST_PART);
     tc::bulk_g2s(dst, src, ST_PART, bar);
     tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, bar);
@@ -227,7 +228,8 @@ __device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
   for (int q = L; q >= 0; --q) {
     const uint32_t buf = b.ph & 1u, par = (b.ph >> 1) & 1u;
     const uint32_t ws = base + OFF_WS + buf * WS_BYTES;
-    const uint32_t a_hi = base + OFF_AB + buf * AB_BYTES, a_mid = a_hi + AB_PART;
+    const uint32_t abuf = b.ph % N_AB, apar = (b.ph / N_AB) & 1u;
+    const uint32_t a_hi = base + OFF_AB + abuf * AB_BYTES, a_mid = a_hi + AB_PART;
     const uint32_t d_hi = base + OFF_DB + buf * DB_BYTES, d_mid = d_hi + ST_PART;
     issue_wait();
     tc::mbar_wait(b.wload_bar + buf, par);
@@ -241,7 +243,7 @@ __device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
     __syncwarp();
     const uint32_t u_parity = c.parity;
     c.parity ^= 1u;
-    tc::mbar_wait(b.aload_bar + buf, par);
+    tc::mbar_wait(b.aload_bar + abuf, apar);
     if (tc::elect_one()) {
       // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
       if (q == L) issue_dw<128, 16>(c.tmem + DW_O, a_hi, a_mid, d_hi, d_mid, b.first);
@@ -252,7 +254,7 @@ __device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
     __syncwarp();
     tc::mbar_wait(c.mma_bar, u_parity);
     if ((threadIdx.x & 31) == 0) {
-      prefetch_A(b, L, b.k + 1, b.ph + 1u);
+      prefetch_A(b, L, b.k + 2, b.ph + 2u);   // its buffer was last read by phase ph - 1, complete before this u-chain
       prefetch_W(b, L, b.k + 2, b.ph + 2u);
     }
     __syncwarp();
@@ -327,7 +329,7 @@ __device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float*
       }
     }
     if (p == 1 && MAIN) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
-      uint8_t* ab = b.smem + OFF_AB + (b.ph & 1u) * AB_BYTES + b.row * 16;
+      uint8_t* ab = b.smem + OFF_AB + (b.ph % N_AB) * AB_BYTES + b.row * 16;
       const float xb[8] = {x9[8], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
       uint4 vh, vm;
       bf16_split8(x9, vh, vm);
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t load_bar;
   __shared__ __align__(8) uint64_t wload_bar[2];
-  __shared__ __align__(8) uint64_t aload_bar[2];
+  __shared__ __align__(8) uint64_t aload_bar[N_AB];
   __shared__ __align__(8) uint64_t gemm_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_nmax;
@@ -469,8 +471,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     tc::mbar_init(&load_bar, 1);
     tc::mbar_init(&wload_bar[0], 1);
     tc::mbar_init(&wload_bar[1], 1);
-    tc::mbar_init(&aload_bar[0], 1);
-    tc::mbar_init(&aload_bar[1], 1);
+    for (int i = 0; i < N_AB; ++i) tc::mbar_init(&aload_bar[i], 1);
     tc::mbar_init(&gemm_bar, 1);
     tc::fence_mbar_init();
   }
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     __syncthreads();
     if (main_role) {
 #pragma unroll
-      for (int bf = 0; bf < 2; ++bf) {
+      for (int bf = 0; bf < N_AB; ++bf) {
         uint8_t* g8 = smem_raw + OFF_AB + bf * AB_BYTES + 8 * ST_GRP + row * 16;
         *reinterpret_cast<uint4*>(g8) = make_uint4(0x00003F80u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(g8 + AB_PART) = make_uint4(0u, 0u, 0u, 0u);
@@ -563,6 +564,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     if (tid == 0) {
       prefetch_W(bc, L, 0, bc.ph);
       prefetch_A(bc, L, 0, bc.ph);
+      prefetch_A(bc, L, 1, bc.ph + 1u);
       prefetch_W(bc, L, 1, bc.ph + 1u);
     }
   };
