@@ -464,7 +464,10 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
   float* img = reinterpret_cast<float*>(smem_raw);
   const int bwd_cap = BWD_BYTES / 4;
   const int img_cap = ((G.fwd_floats > bwd_cap ? G.fwd_floats : bwd_cap) + 255) & ~255;
-  float* t_sh_buf = img + img_cap;
+  // next step's record of every main thread, fetched while the current reverse sweep runs (the streaming
+  // stash traffic evicts an L2 prefetch long before it is used: the plain load cost 4.8 k cycles per step)
+  float* rec_sh = img + img_cap;                       // [128][HODE_REC_FLOATS]
+  float* t_sh_buf = rec_sh + TILE * HODE_REC_FLOATS;
   float* red = img;   // [17][128] theta-gradient reduction scratch at the very end
   if (tid == 0) {
     tc::mbar_init(&mma_bar, 1);
@@ -683,6 +686,10 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
       }
       if (real) {
         const float* rec = step_rec(A, unit, sidx);
+        if (it > 0) {   // fetched into shared memory during the previous iteration (it was `real` there too)
+          tc::cp_async_wait_all();
+          rec = rec_sh + row * HODE_REC_FLOATS;
+        }
         float h_rec;
         step_rec_load(rec, t, h_rec, y, fsal ? k1 : nullptr);
         if (solver == 0) {
@@ -790,8 +797,13 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
       }
       // =========================== reverse sweep ===================================================
       HODE_TL(202);
-      // the next iteration's step record: pull it into L2 while this sweep runs
-      if (real && sidx > 0) tc::prefetch_l2(step_rec(A, unit, sidx - 1));
+      // the next iteration's step record: fetch it into shared memory while this sweep runs
+      if (real && sidx > 0) {
+        const float* nxt = step_rec(A, unit, sidx - 1);
+#pragma unroll
+        for (int q4 = 0; q4 < HODE_REC_FLOATS / 4; ++q4) tc::cp_async16(rec_sh + row * HODE_REC_FLOATS + 4 * q4, nxt + 4 * q4);
+        tc::cp_async_commit();
+      }
       begin_reverse();
       HODE_TL(203);
       float gy[NS], gk[NSTAGE_MAX][NS];
@@ -1141,6 +1153,7 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   p.bwd_floats = tc_bwd_image_floats(L);
   const int bwd_cap = BWD_BYTES / 4;
   size_t floats = (size_t)(((p.fwd_floats > bwd_cap ? p.fwd_floats : bwd_cap) + 255) & ~255);
+  floats += TILE * HODE_REC_FLOATS;
   if (!t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) floats += T;
   p.smem = (floats * sizeof(float) + 1023) & ~(size_t)1023;
   p.partial_floats = (size_t)gx * S * (size_t)(P + HODE_N_THETA);
