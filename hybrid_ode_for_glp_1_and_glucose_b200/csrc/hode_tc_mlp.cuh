@@ -88,9 +88,6 @@ struct TileCtx {
   int L;                // hidden layer count
 };
 
-__device__ __forceinline__ void tile_sync(const TileCtx& c) {
-  asm volatile("bar.sync %0, 128;" ::"r"(c.bar_id) : "memory");
-}
 __device__ __forceinline__ void tile_sync_all(const TileCtx& c) {
   asm volatile("bar.sync %0, 256;" ::"r"(c.bar_all) : "memory");
 }

@@ -131,7 +131,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // all state spaces: generic-proxy GLOBAL stores that a later bulk copy (async proxy) reads
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // per-thread 16-byte asynchronous copy global -> shared (LDGSTS) and its completion wait
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
