@@ -14,15 +14,16 @@
 //     activation goes to a per-CTA stash in global memory, already in the BF16 operand layout of the
 //     weight-gradient MMAs.  DP5(4) is first-same-as-last: the rollout saved k1 of every step, so 6
 //     stages are recomputed and pulled back per step instead of 7;
-//     (2) every stage is pulled back: u_{l-1} = delta_l W_l is a [128 x 64] x [64 x 64] 3xTF32 MMA
-//     chain with delta in TMEM and W_l^T streamed layer by layer into a double-buffered slot by the
-//     TMA engine (kind::tf32 takes K-major operands only — csrc/probe/adj_probe.cu — so W^T needs its
-//     own image); delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue (stashed ReLU bit masks);
-//   * dW_l += delta_l^T [a_{l-1} | 1] (contraction over the tile's 128 trajectories) is an SS-form
-//     kind::f16 MMA over MN-major BF16 operands (csrc/probe/bf16_probe.cu), two-term split, 3 passes:
-//     the stashed activations come back by bulk copy, delta is written by its owner threads as
-//     16-byte vectors; the accumulators stay in TMEM for the whole kernel, so every gradient element
-//     is summed in one fixed order (no atomics, bit-reproducible);
+//     (2) every stage is pulled back through L + 1 issue phases; the issuer warp issues every MMA chain
+//     and runs the operand pipeline (W_l^T and the stashed activations arrive by TMA two phases ahead);
+//     delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue (stashed ReLU bit masks);
+//   * delta is written ONCE per phase, by its owner threads, as a two-term BF16 image in shared memory
+//     (16-byte vectors) that serves both products of the phase (csrc/probe/bf16_probe.cu), 3 passes each:
+//       u_{l-1} = delta_l W_l            reads it as a K-major A operand against the BF16 image of W_l^T,
+//       dW_l += delta_l^T [a_{l-1} | 1]  reads it MN-major (contraction over the tile's 128 trajectories)
+//     against the stashed activations; the weight-gradient accumulators stay in TMEM for the whole kernel, so
+//     every gradient element is summed in one fixed order (no atomics, bit-reproducible).  The recomputation
+//     stays at 3xTF32: two-term BF16 there put the weight gradient 2.6e-4 off float64 autograd;
 //   * per-CTA partial gradients -> workspace -> reduce_partials (hode_adjoint_simt.cu), in CTA order.
 // Restrictions: nn_hidden == 64, nn_layers <= 4 (the TMEM accumulator map is compiled for them);
 // other shapes use the FP32 adjoint.
