@@ -431,3 +431,38 @@ def test_tensor_core_adjoint_more_sets_than_the_sort_key_holds(dev):
         assert relmax(gy[s].cpu().numpy(), y1.cpu().numpy()) < 1e-5, s
         assert relmax(gth[s].cpu().numpy(), th1.cpu().numpy()) < 1e-5, s
         assert relmax(gW[s].cpu().numpy(), W1.cpu().numpy()) < 1e-5, s
+
+
+def test_tensor_core_adjoint_per_trajectory_time_grids(dev):
+    """Per-row observation grids (t_span [B,T], the clinical-shaped configuration) through the tensor-core
+    adjoint, against float64 autograd over the recorded steps of every trajectory."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    from oracle import torch_restate as R
+    B, T = 5, 9
+    y0, t, ins = cohort(B, T, seed=101, horizon=1.5)
+    rng = np.random.default_rng(102)
+    tb = np.tile(t[None, :], (B, 1)).astype(np.float64)
+    tb[:, 1:-1] += rng.uniform(-0.02, 0.02, (B, T - 2))          # jittered interior points, still increasing
+    tb = np.sort(tb, axis=1).astype(np.float32)
+    W = random_mlp(64, 4, seed=103, out_std=0.05)
+    theta = golden("rhs_mech")["theta"]
+    g = rng.normal(0, 1, (B, T, 6)).astype(np.float32)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    traj, info, tape = ops.rollout(tt(y0), tt(tb), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W),
+                                   solver="dopri5", precision="tf32x3", device=dev, save_steps=True)
+    assert bool((info.status == 0).all())
+    g_y0, g_theta, g_W = ops.rollout_bwd(tape, tt(g).to(dev))
+    n, st = ops.saved_steps(tape)
+    n, st = n.cpu().numpy(), st.cpu().numpy()
+    f64 = lambda a, rg=False: torch.tensor(np.asarray(a, np.float64), requires_grad=rg)
+    th64, W64 = f64(theta, True), f64(W, True)
+    gy_ref = np.zeros((B, 6))
+    for b in range(B):
+        y64 = f64(y0[b], True)
+        ins_b = {k: (v[b] if v.ndim == 2 else np.float64(v[b])) for k, v in ins.items()}
+        tr = R.rollout_on_steps(y64, tb[b], ins_b, th64, W64, 64, 4, list(st[: n[b], b]), "dopri5")
+        (tr * f64(g[b])).sum().backward()
+        gy_ref[b] = y64.grad.numpy()
+    assert relmax(g_y0.cpu().numpy(), gy_ref) < TOL
+    assert relmax(g_theta.cpu().numpy(), th64.grad.numpy()) < TOL
+    assert relmax(g_W.cpu().numpy(), W64.grad.numpy()) < TOL
