@@ -466,3 +466,37 @@ def test_tensor_core_adjoint_per_trajectory_time_grids(dev):
     assert relmax(g_y0.cpu().numpy(), gy_ref) < TOL
     assert relmax(g_theta.cpu().numpy(), th64.grad.numpy()) < TOL
     assert relmax(g_W.cpu().numpy(), W64.grad.numpy()) < TOL
+
+
+def test_config5_clinical_shape_adjoint_properties(dev):
+    """mimic_clinical-shaped cohort (T = 577 over 48 h, per-row jittered grids, irregular meal / dose events):
+    the tensor-core adjoint over 100+ recorded steps per trajectory and a non-default record capacity — exact
+    properties that need no oracle (linearity in the cotangent for a power-of-two scale, the t0 row is the
+    identity, finiteness)."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import clinical_cohort
+    B, T = 384, 577
+    y0, t, ins = clinical_cohort(B, T, seed=5)
+    # as in test_config5_clinical_shape_long_horizon_per_row_grids: start insulin / glucagon near their set points and
+    # keep the residual small, so that every trajectory stays physiological over 48 h
+    rng = np.random.default_rng(5)
+    y0[:, 1] = 60.0 * rng.normal(1, 0.1, B)
+    y0[:, 2] = 80.0 * rng.normal(1, 0.05, B)
+    W = random_mlp(seed=17, out_std=0.001)
+    theta = golden("rhs_mech")["theta"]
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    args = (tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W))
+    _, info, tape = ops.rollout(*args, solver="dopri5", precision="tf32x3", device=dev, save_steps=True,
+                                max_saved_steps=8192)
+    assert bool((info.status == 0).all()), (torch.unique(info.status).tolist(), int(info.n_accept.max()))
+    assert int(info.n_accept.max()) > 100      # long records (the 5 h cohorts take ~33 steps)
+    g = torch.zeros((B, T, 6), device=dev)
+    g[:, 0, :] = torch.randn((B, 6), device=dev, generator=torch.Generator(dev).manual_seed(1))
+    gy, gth, gW = ops.rollout_bwd(tape, g)
+    assert torch.equal(gy, g[:, 0, :]) and float(gth.abs().max()) == 0.0 and float(gW.abs().max()) == 0.0
+    g = torch.randn((B, T, 6), device=dev, generator=torch.Generator(dev).manual_seed(2)) / (B * T)
+    a = ops.rollout_bwd(tape, g)
+    b = ops.rollout_bwd(tape, 0.5 * g)
+    for x, y in zip(a, b):
+        assert bool(torch.isfinite(x).all()) and torch.equal(0.5 * x, y)
+    assert float(a[2].abs().max()) > 0 and float(a[1].abs().max()) > 0
