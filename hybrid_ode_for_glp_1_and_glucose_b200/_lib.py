@@ -12,25 +12,27 @@ from typing import Optional
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libhode.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 N_STATE, N_THETA, NN_IN = 6, 17, 9
 SOLVER_RK4, SOLVER_DOPRI5 = 0, 1
 IN_ABSENT, IN_CONST, IN_SERIES = 0, 1, 2
-MLP_NONE, MLP_FP32, MLP_TF32X3, MLP_TF32 = 0, 1, 2, 3
+MLP_NONE, MLP_FP32, MLP_TF32X3, MLP_TF32, MLP_TF32BF16 = 0, 1, 2, 3, 4
 KINK_SCIPY, KINK_CLIP = 0, 1
-ST_OK, ST_STEP_TOO_SMALL, ST_MAX_STEPS, ST_NONFINITE = 0, 1, 2, 3
+ST_OK, ST_STEP_TOO_SMALL, ST_MAX_STEPS, ST_NONFINITE, ST_REC_OVERFLOW = 0, 1, 2, 3, 4
 
 STATUS_TEXT = {
     ST_OK: "ok",
     ST_STEP_TOO_SMALL: "Required step size is less than spacing between numbers.",
     ST_MAX_STEPS: "step budget exhausted",
     ST_NONFINITE: "state became non-finite",
+    ST_REC_OVERFLOW: "accepted-step record capacity exhausted (max_saved_steps): zero-padded, no gradient",
 }
 
 EXPORTS = [
     "hode_version", "hode_last_error_string", "hode_mlp_param_count", "hode_workspace_bytes",
     "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs", "hode_rhs_vjp",
     "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd", "hode_generate_4gi",
+    "hode_step_record_floats", "hode_step_record_capacity",
 ]
 
 
@@ -76,6 +78,9 @@ def lib() -> ctypes.CDLL:
     L.hode_workspace_bytes.restype = ctypes.c_int
     L.hode_workspace_bytes.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(ctypes.c_size_t),
                                        ctypes.POINTER(ctypes.c_size_t)]
+    for fn in (L.hode_step_record_floats, L.hode_step_record_capacity):
+        fn.restype = ctypes.c_int32
+        fn.argtypes = [ctypes.POINTER(HodeCfg)]
     L.hode_rollout_fwd.restype = ctypes.c_int
     L.hode_rollout_fwd.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 11 + [ctypes.c_size_t, _P]
     L.hode_rollout_bwd.restype = ctypes.c_int

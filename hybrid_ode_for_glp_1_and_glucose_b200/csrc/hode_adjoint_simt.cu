@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(ABLK, 1) rollout_bwd_kernel(const AdjArgs G) {
           h = (double)h_rec;
           t_new = t + h;
         } else {
-          t_new = (sidx + 1 < n) ? step_rec_t(rec + HODE_REC_FLOATS) : t_bound;
+          t_new = (sidx + 1 < n) ? step_rec_t(rec + A.rec_floats) : t_bound;
           h = t_new - t;
         }
       }

@@ -1,29 +1,33 @@
 // hode_adjoint_tc.cu — discrete adjoint of the rollout with the MLP forward recomputation, the delta
 // back-propagation and the weight gradients on the tcgen05 tensor cores (BASELINE.json north_star item 3).
 //
-// Same mathematics as hode_adjoint_simt.cu (autograd through the unrolled RK steps with the step
-// sizes frozen); what changes is where the 13 248-MAC network products run and how the work is laid out:
-//   * schedule (device side, deterministic): trajectories are radix-sorted by accepted-step count,
-//     cut into 128-trajectory tiles, and the tiles are dealt to the CTAs longest-first — a tile runs
-//     for the maximum step count of its members, and adaptive step counts differ several-fold;
-//   * one tile per CTA at a time, three warpgroups with their own register budgets (setmaxnreg):
-//     4 main warps (one trajectory per thread: integrator state, mechanistic VJP, stage recurrences),
-//     4 helper warps (the other half of every epilogue), 1 MMA-issuer warp;
-//   * per accepted step, in reverse:  (1) the forward weight image is bulk-copied into shared
-//     memory and the stages are recomputed with hode_tc_mlp.cuh's mlp_tile (3xTF32); every hidden
-//     activation goes to a per-CTA stash in global memory, already in the BF16 operand layout of the
-//     weight-gradient MMAs.  DP5(4) is first-same-as-last: the rollout saved k1 of every step, so 6
-//     stages are recomputed and pulled back per step instead of 7;
-//     (2) every stage is pulled back through L + 1 issue phases; the issuer warp issues every MMA chain
-//     and runs the operand pipeline (W_l^T and the stashed activations arrive by TMA two phases ahead);
-//     delta_{l-1} = u_{l-1} * relu'(a_{l-1}) in the epilogue (stashed ReLU bit masks);
+// Same mathematics as hode_adjoint_simt.cu (autograd through the unrolled RK steps with the step sizes
+// frozen).  Round-2 data flow — no activation ever travels through HBM:
+//   * the tensor-core rollout records, with every accepted step, its stage derivatives k1..k6 (192-byte
+//     record, hode_common.cuh).  Every stage INPUT of a step is then a linear combination of recorded values,
+//     so the stages are independent of one another: the adjoint treats every (step, stage) pair as one ITEM,
+//     walks the items in reverse order and, per item, recomputes the hidden activations of that ONE stage
+//     (the output layer is not needed) and pulls the stage's cotangent back through them.  The activations of
+//     one stage (4 x 32 KB as BF16 operand images) live in a per-CTA scratch that is written and read back
+//     within microseconds: 38 MB for the whole grid, L2-resident (round 1 stashed all 6 stages of a step and
+//     streamed 78 GB through HBM per launch);
+//   * the recomputation F of item e+1 is INTERLEAVED with the pull-back B of item e on the same 128
+//     trajectories: the two are independent (F needs no cotangent), so while the epilogue threads work on one
+//     chain the tensor pipe runs the MMAs of the other — the overlap the rollout gets from its second tile;
+//   * roles (warp-specialised, setmaxnreg): 4 main warps (one trajectory per thread: records, stage inputs,
+//     mechanistic VJP, RK recurrences), 4 helper warps (the other half of every epilogue), 1 MMA-issuer warp,
+//     3 loader warps (TMA: forward weights by layer, W^T by phase, stashed activations by phase) that run
+//     ahead of the issuer as far as the buffers allow (full / free mbarrier pairs, free = tcgen05.commit);
+//   * schedule (device side, deterministic): trajectories are radix-sorted by accepted-step count, cut into
+//     128-trajectory tiles, and the tiles are dealt to the CTAs longest-first;
 //   * delta is written ONCE per phase, by its owner threads, as a two-term BF16 image in shared memory
 //     (16-byte vectors) that serves both products of the phase (csrc/probe/bf16_probe.cu), 3 passes each:
 //       u_{l-1} = delta_l W_l            reads it as a K-major A operand against the BF16 image of W_l^T,
 //       dW_l += delta_l^T [a_{l-1} | 1]  reads it MN-major (contraction over the tile's 128 trajectories)
 //     against the stashed activations; the weight-gradient accumulators stay in TMEM for the whole kernel, so
 //     every gradient element is summed in one fixed order (no atomics, bit-reproducible).  The recomputation
-//     stays at 3xTF32: two-term BF16 there put the weight gradient 2.6e-4 off float64 autograd;
+//     uses the rollout's own arithmetic on the rollout's own stage inputs: its activations (and ReLU masks)
+//     are the forward pass's, bit for bit;
 //   * per-CTA partial gradients -> workspace -> reduce_partials (hode_adjoint_simt.cu), in CTA order.
 // Restrictions: nn_hidden == 64, nn_layers <= 4 (the TMEM accumulator map is compiled for them);
 // other shapes use the FP32 adjoint.
@@ -40,7 +44,7 @@ namespace hode {
 
 namespace {
 
-constexpr int MAXL = 4;       // hidden layers supported by the register accumulators
+constexpr int MAXL = 4;       // hidden layers supported by the TMEM accumulator map
 constexpr int NSTAGE_MAX = 7;
 
 // Butcher tableaux, [solver][..]: 0 = classical RK4, 1 = Dormand-Prince 5(4) (+ stage 7 = FSAL)
@@ -70,32 +74,39 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& mid)
   mid = (uint16_t)(m & 0xFFFFu);
 }
 
-// ---- weight gradients on the tensor cores ---------------------------------------------------------
-// dW_l += delta_l^T [a_{l-1} | 1] contracts over the 128 trajectories of the tile: an SS-form MMA
-// with K = trajectory.  kind::tf32 takes K-major operands only, which would force a transposed
-// staging (4-byte scattered stores); kind::f16 takes MN-major operands, so "thread t owns
-// trajectory t" writes 8 consecutive features as ONE 16-byte vector (csrc/probe/bf16_probe.cu):
-//   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2
-//   descriptor: LBO = 128 B (between 8-trajectory groups), SBO = ST_GRP (between 8-feature groups).
-// Operands are split in two BF16 terms, x ~= hi + mid (2^-17), and the product takes 3 passes
-// mid*hi + hi*mid + hi*hi at the BF16 rate (twice the TF32 rate): measured max error 2.7e-6 of
-// sum|ab| per 128-term product.  The activations a_{l-1} are already stored in this form by the
-// forward recomputation (stash, hode_tc_mlp.cuh) and come back by bulk copy; only delta is written
-// by the threads.  Inputs carry one extra 8-feature group whose first feature is the constant 1
-// (its accumulator column is the bias gradient).
-// Accumulators live in TMEM for the whole kernel (fp32):
-//   hidden layer l = 1..3 : columns DW_H0 + 80 (l-1) .. +72   D[j][k] = dW_l[j][k], column 64 = db_l[j]
-//   layer 0               : columns DW_0  .. +16               D[j][k] = dW_0[j][k] (k < 9), column 15 = db_0[j]
-//   output layer (transp.): columns DW_O  .. +16               D[k][n] = dW_out[n][k] (n < 6), row 64 = db_out[n]
-constexpr uint32_t DW_H0 = 208, DW_0 = 448, DW_O = 464;
-// shared memory of the reverse sweep (bytes; everything double-buffered by issue phase):
-//   [input operands 2 x (hi, mid) x 9 groups][delta operands 2 x (hi, mid) x 8 groups][W_l^T slots 2 x (hi, lo)]
+// ---- TMEM column map (all 512 columns; csrc/probe/mix_probe.cu test 3: accumulators at any multiple of 8) --------
+//   [0,200)    the recomputation's tile (hode_tc_mlp.cuh: D, A_hi, A_lo / BF16 operands, constant block)
+//   [200,264)  D_B: accumulator of the delta chain u_{q-1} = delta_q W_q
+//   weight-gradient accumulators, resident for the whole kernel (fp32):
+//   hidden layer l = 1..3 : columns DW_H0 + 72 (l-1) .. +72   D[j][k] = dW_l[j][k], column 64 = db_l[j]      (M = 64)
+//   layer 0               : columns DW_0  .. +16               D[j][k] = dW_0[j][k] (k < 9), column 15 = db_0[j] (M = 64)
+//   output layer (transp.): columns DW_O  .. +16               D[k][n] = dW_out[n][k] (n < 6), row 64 = db_out[n] (M = 128)
+constexpr uint32_t TM_DB = 200, DW_H0 = 264, DW_HS = 72, DW_0 = 480, DW_O = 496;
+
+// ---- shared memory (bytes) ------------------------------------------------------------------------------------
+//   AB  2 x [hi: 8 feature groups + the constant-1 group][mid: likewise]: input operand a_{q-1} of the weight gradients
+//   DB  2 x [hi][mid]: the delta image of a phase (both buffered by phase parity)
+//   WT  2 x one layer's W^T (BF16 hi, mid)         WF  one layer's forward image + its bias block
+//   REC the NEXT step's record of every main thread, [12 chunks][128 threads][16 B] (conflict-free LDS.128)
 constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART;
 constexpr int DB_BYTES = 2 * ST_PART;
-constexpr int WS_BYTES = 2 * 64 * 64 * 2;   // one layer's W^T: BF16 hi, mid
-constexpr int N_AB = 3;   // input operands are fetched TWO phases ahead (they stream from HBM: the stash of 148 CTAs exceeds L2)
-constexpr int OFF_AB = 0, OFF_DB = OFF_AB + N_AB * AB_BYTES, OFF_WS = OFF_DB + 2 * DB_BYTES;
-constexpr int BWD_BYTES = OFF_WS + 2 * WS_BYTES;
+constexpr int WT_BYTES = 2 * 64 * 64 * 2;
+constexpr int WF_FLOATS = 8192 + 512, WF_BYTES = WF_FLOATS * 4;
+constexpr int REC_CHUNKS = HODE_REC_FLOATS_K / 4, REC_BYTES = REC_CHUNKS * TILE * 16;
+constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_WT = OFF_DB + 2 * DB_BYTES, OFF_WF = OFF_WT + 2 * WT_BYTES,
+              OFF_REC = OFF_WF + WF_BYTES, OFF_T = OFF_REC + REC_BYTES;
+constexpr int ADJ_SMEM_BASE = OFF_T;            // + 4 T bytes when the shared time grid fits
+constexpr int ADJ_SMEM_MAX = 227 * 1024 - 256;  // (static shared memory: the mbarriers, padded to the dynamic part's alignment)
+
+struct Bars {
+  uint64_t f_bar;        // recomputation: a layer's MMAs complete
+  uint64_t b_bar;        // pull-back: a phase's delta chain complete
+  uint64_t wf_full, wf_free;
+  uint64_t wt_full[2], wt_free[2];
+  uint64_t ab_full[2], ab_free[2];
+  uint64_t st_done[MAXL];   // 256 arrivals: the tile's a_l of the item being recomputed is in the stash
+  uint64_t done;
+};
 
 // kind::f16 instruction descriptors: D = f32, A = B = BF16; both operands MN-major / both K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
@@ -114,8 +125,15 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
-// D[tmem] (+)= R^T C over the 128 trajectories: 3 passes x 8 k-steps of 16 trajectories.
-// r_*: shared-memory byte address of the operand whose features become the ROWS of D, c_*: the COLUMNS.
+// ---- weight gradients on the tensor cores ---------------------------------------------------------
+// dW_l += delta_l^T [a_{l-1} | 1] contracts over the 128 trajectories of the tile: an SS-form MMA
+// with K = trajectory.  kind::f16 takes MN-major operands, so "thread t owns trajectory t" writes 8
+// consecutive features as ONE 16-byte vector (csrc/probe/bf16_probe.cu):
+//   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2
+//   descriptor: LBO = 128 B (between 8-trajectory groups), SBO = ST_GRP (between 8-feature groups).
+// Operands are split in two BF16 terms, x ~= hi + mid (2^-17), and the product takes 3 passes
+// mid*hi + hi*mid + hi*hi at the BF16 rate: measured max error 2.7e-6 of sum|ab| per 128-term product.
+// D[tmem] (+)= R^T C: r_*: the operand whose features become the ROWS of D, c_*: the COLUMNS.
 template <int M, int N>
 __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t r_hi, uint32_t r_mid, uint32_t c_hi, uint32_t c_mid,
                                          uint32_t init) {
@@ -140,7 +158,6 @@ __device__ __forceinline__ void issue_u(uint32_t d, uint32_t a_hi, uint32_t a_mi
   constexpr uint32_t idesc = make_idesc_bf16_k(TILE, N);
   const uint64_t ah = tc::make_desc(a_hi, ST_GRP, 128u), am = tc::make_desc(a_mid, ST_GRP, 128u);
   const uint64_t bh = tc::make_desc(b_hi, (uint32_t)N * 16u, 128u), bm = tc::make_desc(b_mid, (uint32_t)N * 16u, 128u);
-  // one k-step = 16 features = 2 K-chunks: A advances 2 ST_GRP bytes, B 2 * N * 16 bytes (16-byte units)
   constexpr uint32_t sa = 2u * ST_GRP / 16u, sb = 2u * (uint32_t)N;
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_ss(d, am + sa * ks, bh + sb * ks, idesc, ks == 0 ? 0u : 1u);
@@ -150,217 +167,14 @@ __device__ __forceinline__ void issue_u(uint32_t d, uint32_t a_hi, uint32_t a_mi
   for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_ss(d, ah + sa * ks, bh + sb * ks, idesc, 1u);
 }
 
-// Issue phases of the reverse sweep.  One stage has L + 1 of them, q = L .. 0:
-//   phase q:  u_{q-1} = delta_q W_q  (delta image x W_q^T slot)   and   dW_q += delta_q^T [a_{q-1} | 1]
-// (a_{-1} = the stage's input features x, u_{-1} = the cotangent of x).  Phases are numbered through
-// the whole kernel (`ph`); phase ph uses buffer ph & 1 of every double-buffered region, and its
-// mbarriers complete once per phase, so the parity to wait for is (ph >> 1) & 1.
-struct BwdCtx {
-  uint8_t* smem;              // reverse-sweep layout (OFF_*)
-  const float* wsrc;          // global: this parameter set's transposed weight image
-  uint8_t* stash_cta;         // global: this CTA's activation stash
-  uint8_t* stage_blk;         // stash block of the current stage, layer 0
-  uint64_t* wload_bar;        // [2] W^T slot filled
-  uint64_t* aload_bar;        // [N_AB] input operand filled (phase ph uses buffer ph % N_AB, parity (ph / N_AB) & 1)
-  uint64_t* gemm_bar;         // weight-gradient MMAs of a phase complete
-  uint32_t ph;                // phases issued so far
-  int k, k_end, stage_top;    // phase index inside the current sweep, phases in the sweep, stage of phase 0
-  uint32_t first;             // 1 until the accumulators have been initialised
-  int row;                    // trajectory slot 0..127
-};
-
-// wait until every weight-gradient MMA issued so far has completed (at most the last phase can be
-// pending: its u-chain, which the epilogue threads have waited for, was issued after all earlier ones)
-__device__ __forceinline__ void wait_gemm(const BwdCtx& b) {
-  if (b.ph > 0u) tc::mbar_wait(b.gemm_bar, (b.ph - 1u) & 1u);
-}
-
-// input operand of sweep phase k1 (global phase ph1): bulk copy of the stashed a_{q-1}, hi and mid
-__device__ __forceinline__ void prefetch_A(const BwdCtx& b, int L, int k1, uint32_t ph1) {
-  if (k1 >= b.k_end) return;
-  const int st = b.stage_top - k1 / (L + 1), q = L - k1 % (L + 1);
-  uint64_t* bar = b.aload_bar + (ph1 % N_AB);
-  if (q >= 1) {
-    const uint8_t* src = b.stash_cta + ((size_t)st * L + (q - 1)) * ST_BLK;
-    uint8_t* dst = b.smem + OFF_AB + (ph1 % N_AB) * AB_BYTES;
-    tc::mbar_expect_tx(bar, 2u * ST_PART);
-    tc::bulk_g2s(dst, src, ST_PART, bar);
-    tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, bar);
-  } else {
-    tc::mbar_arrive(bar);   // phase 0: the main threads write x themselves
-  }
-}
-// W_q^T of sweep phase k2 (global phase ph2)
-__device__ __forceinline__ void prefetch_W(const BwdCtx& b, int L, int k2, uint32_t ph2) {
-  if (k2 >= b.k_end) return;
-  const int q = L - k2 % (L + 1);
-  int off, floats;
-  if (q == L) { off = 0; floats = 1024; }
-  else if (q >= 1) { off = 1024 + (L - 1 - q) * 4096; floats = 4096; }
-  else { off = 1024 + (L - 1) * 4096; floats = 1024; }
-  uint64_t* bar = b.wload_bar + (ph2 & 1u);
-  tc::mbar_expect_tx(bar, (uint32_t)floats * 4u);
-  tc::bulk_g2s(b.smem + OFF_WS + (ph2 & 1u) * WS_BYTES, b.wsrc + off, (uint32_t)floats * 4u, bar);
-}
-
-// The MMAs of the reverse sweep are issued by a dedicated warp: tcgen05.mma issue blocks while the
-// tensor pipe is busy, and a warp that also runs an epilogue would hold the whole tile back for
-// that long.  The 256 epilogue threads only ARRIVE on the named barrier; the issuer warp waits on it.
-// (One barrier per phase is race-free: the u-chain whose completion lets a thread move on to its next
-// arrival is only issued after the barrier has completed, so arrivals of two phases never mix.)
-constexpr int ISSUE_BAR = 3, ISSUE_BAR_THREADS = 2 * TILE + 32;
-__device__ __forceinline__ void issue_arrive() {
-  asm volatile("bar.arrive %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
-}
-__device__ __forceinline__ void issue_wait() {
-  asm volatile("bar.sync %0, %1;" ::"n"(ISSUE_BAR), "n"(ISSUE_BAR_THREADS) : "memory");
-}
-
-// Issuer warp: the MMA chains of one stage of the reverse sweep, mirroring mlp_bwd_tile's phases, and the
-// operand pipeline: once the u-chain of phase ph has completed, everything phase ph - 1 read is free
-// (its MMAs precede that chain), so the input operand of phase ph + 1 and W^T of phase ph + 2 are fetched.
-__device__ __forceinline__ void mlp_bwd_issue(TileCtx& c, BwdCtx& b) {
-  const int L = c.L;
-  const uint32_t m_d = c.tmem + TM_D0;
-  const uint32_t base = tc::smem_u32(b.smem);
-  // (runtime loops here and in mlp_bwd_tile: unrolled over the phases the kernel outgrows the
-  // instruction cache — three roles run three different code streams on one SM)
-#pragma unroll 1
-  for (int q = L; q >= 0; --q) {
-    const uint32_t buf = b.ph & 1u, par = (b.ph >> 1) & 1u;
-    const uint32_t ws = base + OFF_WS + buf * WS_BYTES;
-    const uint32_t abuf = b.ph % N_AB, apar = (b.ph / N_AB) & 1u;
-    const uint32_t a_hi = base + OFF_AB + abuf * AB_BYTES, a_mid = a_hi + AB_PART;
-    const uint32_t d_hi = base + OFF_DB + buf * DB_BYTES, d_mid = d_hi + ST_PART;
-    issue_wait();
-    tc::mbar_wait(b.wload_bar + buf, par);
-    if (tc::elect_one()) {
-      tc::fence_after_sync();
-      if (q == L) issue_u<H, 1>(m_d, d_hi, d_mid, ws, ws + 2048u);          // u_{L-1} = delta_L W_out   (K = 16)
-      else if (q >= 1) issue_u<H, 4>(m_d, d_hi, d_mid, ws, ws + 8192u);     // u_{q-1} = delta_q W_q
-      else issue_u<16, 4>(m_d, d_hi, d_mid, ws, ws + 2048u);                // g_x = delta_0 W_0
-      tc::mma_commit(c.mma_bar);
-    }
-    __syncwarp();
-    const uint32_t u_parity = c.parity;
-    c.parity ^= 1u;
-    tc::mbar_wait(b.aload_bar + abuf, apar);
-    if (tc::elect_one()) {
-      // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
-      if (q == L) issue_dw<128, 16>(c.tmem + DW_O, a_hi, a_mid, d_hi, d_mid, b.first);
-      else if (q >= 1) issue_dw<64, 72>(c.tmem + DW_H0 + 80u * (uint32_t)(q - 1), d_hi, d_mid, a_hi, a_mid, b.first);
-      else issue_dw<64, 16>(c.tmem + DW_0, d_hi, d_mid, a_hi, a_mid, b.first);
-      tc::mma_commit(b.gemm_bar);
-    }
-    __syncwarp();
-    tc::mbar_wait(c.mma_bar, u_parity);
-    if ((threadIdx.x & 31) == 0) {
-      prefetch_A(b, L, b.k + 2, b.ph + 2u);   // its buffer was last read by phase ph - 1, complete before this u-chain
-      prefetch_W(b, L, b.k + 2, b.ph + 2u);
-    }
-    __syncwarp();
-    b.ph += 1u;
-    b.k += 1;
-  }
-  b.first = 0u;
-}
-
-// ---- MLP backward for one stage (tile-collective: all 256 epilogue threads) ---------------------------
-// MAIN threads own accumulator columns [0,32) of their trajectory, helpers [32,64).
-// g6 (main): cotangent of the 6 network outputs; x9 (main): the stage's input features;
-// gx (main, out): cotangent of the 9 input features.
-// Notation: delta_l = cotangent of the pre-activation of layer l (l = 0..L-1), delta_L = g.
-// `overlap` runs after phase L has been handed to the issuer: per-thread work that does not depend on
-// the network's cotangents (the mechanistic VJP) hides behind the first MMA chain.
-template <bool MAIN, class F>
-__device__ __forceinline__ void mlp_bwd_tile(TileCtx& c, BwdCtx& b, const float* x9, const float* g6, float* gx,
-                                             F&& overlap) {
-  constexpr int half = MAIN ? 0 : 32;
-  constexpr int hidx = MAIN ? 0 : 1;
-  const int L = c.L;
-  const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + half;
-
-  // ---- prologue: delta_L = g; phase L (its input operand and W^T slot are already on their way) ------
-  HODE_TL(220);
-  if (MAIN) {
-    float d[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) d[j] = (j < NS) ? g6[j] : 0.f;
-    uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + b.row * 16;
-    uint4 vh, vm;
-    bf16_split8(d, vh, vm);
-    *reinterpret_cast<uint4*>(db) = vh;
-    *reinterpret_cast<uint4*>(db + ST_PART) = vm;
-    *reinterpret_cast<uint4*>(db + ST_GRP) = make_uint4(0u, 0u, 0u, 0u);   // N = 16: features 8..15 are zero
-    *reinterpret_cast<uint4*>(db + ST_GRP + ST_PART) = make_uint4(0u, 0u, 0u, 0u);
-    tc::fence_proxy_async();
-  }
-  tc::fence_before_sync();
-  HODE_TL(221);
-  issue_arrive();   // the issuer warp launches phase L (mlp_bwd_issue) once all 256 threads are here
-  b.ph += 1u;
-  b.k += 1;
-  HODE_TL(222);
-  overlap();
-  __syncwarp();   // reconverge after per-thread code: tcgen05 .sync.aligned instructions follow
-
-  // ---- p = L .. 1: u_{p-1} arrives, delta_{p-1} = u_{p-1} * relu'(a_{p-1}) goes out for phase p-1 ------
-#pragma unroll 1
-  for (int p = L; p >= 1; --p) {
-    const uint32_t mask = reinterpret_cast<const uint32_t*>(b.stage_blk + (size_t)(p - 1) * ST_BLK + 2 * ST_PART)[hidx * TILE + b.row];
-    tc::mbar_wait(c.mma_bar, c.parity);
-    c.parity ^= 1u;
-    tc::fence_after_sync();
-    HODE_TL(230 + 10 * p);
-    uint32_t u[32];
-    HODE_TMEM_LD_X32(t_d, u);
-    tc::wait_ld();
-    float d[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) d[j] = ((mask >> j) & 1u) ? __uint_as_float(u[j]) : 0.f;
-    HODE_TL(231 + 10 * p);
-    {
-      uint8_t* db = b.smem + OFF_DB + (b.ph & 1u) * DB_BYTES + (hidx * 4) * ST_GRP + b.row * 16;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 vh, vm;
-        bf16_split8(d + 8 * g, vh, vm);
-        *reinterpret_cast<uint4*>(db + g * ST_GRP) = vh;
-        *reinterpret_cast<uint4*>(db + g * ST_GRP + ST_PART) = vm;
-      }
-    }
-    if (p == 1 && MAIN) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
-      uint8_t* ab = b.smem + OFF_AB + (b.ph % N_AB) * AB_BYTES + b.row * 16;
-      const float xb[8] = {x9[8], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-      uint4 vh, vm;
-      bf16_split8(x9, vh, vm);
-      *reinterpret_cast<uint4*>(ab) = vh;
-      *reinterpret_cast<uint4*>(ab + AB_PART) = vm;
-      bf16_split8(xb, vh, vm);
-      *reinterpret_cast<uint4*>(ab + ST_GRP) = vh;
-      *reinterpret_cast<uint4*>(ab + ST_GRP + AB_PART) = vm;
-    }
-    tc::fence_proxy_async();
-    tc::fence_before_sync();
-    HODE_TL(233 + 10 * p);
-    issue_arrive();
-    b.ph += 1u;
-    b.k += 1;
-    HODE_TL(234 + 10 * p);
-  }
-  // ---- final phase: g_x -------------------------------------------------------------------------
-  tc::mbar_wait(c.mma_bar, c.parity);
-  c.parity ^= 1u;
-  if (MAIN) {
-    tc::fence_after_sync();
-    uint32_t v[16];
-    HODE_TMEM_LD_X16(c.tmem + c.lane_base + TM_D0, v);
-    tc::wait_ld();
-#pragma unroll
-    for (int k = 0; k < HODE_NN_IN; ++k) gx[k] = __uint_as_float(v[k]);
-  }
-  b.first = 0u;
-}
+// ---- named barriers: the 256 epilogue threads ARRIVE, the issuer warp waits (bar.sync) ---------------------------
+// One barrier per chain.  Race-free: the MMA chain whose completion lets a thread move on to its next arrival
+// on a barrier is only issued after the barrier's previous generation has completed.
+constexpr int BAR_F = 3, BAR_B = 4, BAR_THREADS = 2 * TILE + 32;
+template <int ID>
+__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(BAR_THREADS) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_wait() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(BAR_THREADS) : "memory"); }
 
 // closed-form VJP of f_physio — same formulas as hode_adjoint_simt.cu::rhs_mech_vjp
 __device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float GD, bool gd_present,
@@ -412,6 +226,97 @@ __device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float G
   gth[16] += c[5] * FFA * G;
 }
 
+// runtime-indexed access to four per-thread registers without local memory
+__device__ __forceinline__ uint32_t sel4(const uint32_t* m, int l) {
+  return l == 0 ? m[0] : (l == 1 ? m[1] : (l == 2 ? m[2] : m[3]));
+}
+__device__ __forceinline__ void put4(uint32_t* m, int l, uint32_t v) {
+  if (l == 0) m[0] = v;
+  else if (l == 1) m[1] = v;
+  else if (l == 2) m[2] = v;
+  else m[3] = v;
+}
+
+// ---- epilogue halves shared by the main (columns [0,32)) and helper (columns [32,64)) warps --------------------------
+struct EpiCtx {
+  Bars* bars;
+  uint8_t* smem;
+  uint8_t* stash_cta;   // global: this CTA's activation scratch, [2 sets][L][ST_BLK]
+  uint32_t tmem, lane_base;
+  uint32_t f_cnt, b_cnt;   // completions of f_bar / b_bar observed so far
+  uint32_t ph;             // pull-back phases handed to the issuer so far (buffer = ph & 1)
+  int row, L;
+};
+
+// recomputation, hidden layer l of the item in scratch set `set`: a_l = relu(z_l) -> next layer's A operand (TMEM)
+// and -> the scratch as the weight gradients' BF16 operand image; returns this thread's ReLU mask
+template <int MODE, bool MAIN>
+__device__ __forceinline__ uint32_t fwd_epilogue(EpiCtx& e, int l, int set) {
+  tc::mbar_wait(&e.bars->f_bar, e.f_cnt & 1u);
+  e.f_cnt += 1u;
+  tc::fence_after_sync();
+  HODE_TL(300 + l);
+  uint32_t v[32], lo[32];
+  const bool last = (l + 1 == e.L);
+  epilogue32_to_tmem<MODE>(e.tmem + e.lane_base, MAIN ? 0u : 32u, v, lo, !last);
+  if (!last) bar_arrive<BAR_F>();
+  const uint32_t mask = stash_store32(e.stash_cta + ((size_t)set * e.L + l) * ST_BLK, e.row, MAIN ? 0 : 1, v, lo);
+  tc::fence_proxy_async_all();   // generic-proxy global stores, read back by a bulk copy (async proxy)
+  tc::mbar_arrive(&e.bars->st_done[l]);
+  HODE_TL(310 + l);
+  return mask;
+}
+
+// pull-back, phase p (L..1) has delivered u_{p-1} in D_B: delta_{p-1} = u_{p-1} * relu'(a_{p-1}) -> delta image of
+// phase p-1; at p == 1 the main thread also writes the stage's input features as the input operand of dW_0
+template <bool MAIN>
+__device__ __forceinline__ void bwd_epilogue(EpiCtx& e, int p, uint32_t mask, const float* x9) {
+  tc::mbar_wait(&e.bars->b_bar, e.b_cnt & 1u);
+  e.b_cnt += 1u;
+  tc::fence_after_sync();
+  HODE_TL(320 + p);
+  uint32_t u[32];
+  HODE_TMEM_LD_X32(e.tmem + e.lane_base + TM_DB + (MAIN ? 0u : 32u), u);
+  tc::wait_ld();
+  float d[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) d[j] = ((mask >> j) & 1u) ? __uint_as_float(u[j]) : 0.f;
+  {
+    uint8_t* db = e.smem + OFF_DB + (e.ph & 1u) * DB_BYTES + ((MAIN ? 0 : 4)) * ST_GRP + e.row * 16;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 vh, vm;
+      bf16_split8(d + 8 * g, vh, vm);
+      *reinterpret_cast<uint4*>(db + g * ST_GRP) = vh;
+      *reinterpret_cast<uint4*>(db + g * ST_GRP + ST_PART) = vm;
+    }
+  }
+  if (MAIN && p == 1) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
+    uint8_t* ab = e.smem + OFF_AB + (e.ph & 1u) * AB_BYTES + e.row * 16;
+    const float xb[8] = {x9[8], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    uint4 vh, vm;
+    bf16_split8(x9, vh, vm);
+    *reinterpret_cast<uint4*>(ab) = vh;
+    *reinterpret_cast<uint4*>(ab + AB_PART) = vm;
+    bf16_split8(xb, vh, vm);
+    *reinterpret_cast<uint4*>(ab + ST_GRP) = vh;
+    *reinterpret_cast<uint4*>(ab + ST_GRP + AB_PART) = vm;
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  bar_arrive<BAR_B>();
+  e.ph += 1u;
+  HODE_TL(330 + p);
+}
+
+// items of one tile: iteration it = 0..n_iter-1 (one accepted step each, last step first), stages i = N-1 .. i_lo(it).
+// DP5(4) is first-same-as-last: stage 1 of step n+1 IS stage 7 of step n, pulled back once, as stage 7 of the
+// earlier step, with both cotangents added; stage 1 of the very first step is pulled back by one extra iteration (a
+// zero-length step at (t0, y0)) of which only stage 7 carries a cotangent.
+__device__ __forceinline__ int item_i_lo(int it, int n_iter, int N, int i0, bool fsal) {
+  return (fsal && it == n_iter - 1) ? N - 1 : i0;
+}
+
 }  // namespace
 
 struct AdjTcArgs {
@@ -419,10 +324,11 @@ struct AdjTcArgs {
   const float* grad_traj;  // [S,B,T,6]
   float* grad_y0;          // [S,B,6] or nullptr
   float* partials;         // [gridDim.y * gridDim.x][P + 17]
-  float* stash;            // [7][L][64][NT] activation stash
-  const float* img_fwd;    // [S][fwd_floats]
+  uint8_t* stash;          // [ctas][2][L][ST_BLK] activation scratch (L2-resident)
+  const float* img_fwd;    // [S][fwd_floats] (hode_rollout_tc.cu prep_tc_image_kernel)
   const float* img_bwd;    // [S][bwd_floats]
   int fwd_floats, bwd_floats;
+  int t_in_smem;           // the shared time grid is staged in shared memory
   // schedule (adj_schedule_kernel): trajectories sorted by accepted-step count, tiles handed to CTAs
   const int32_t* perm;        // [S*B] unit index of sorted slot q (within its parameter set)
   const int32_t* sched_off;   // [S][grid_x + 1] range of sched_tiles owned by CTA (s, x)
@@ -431,147 +337,74 @@ struct AdjTcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// grid = (ctas per parameter set, S), block = 256 (4 main + 4 helper warps), 1 CTA / SM
+// grid = (ctas per parameter set, S), block = 384: warps 0-3 main, 4-7 helpers, 8 issuer, 9-11 loaders; 1 CTA / SM
 // ---------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ __align__(8) uint64_t load_bar;
-  __shared__ __align__(8) uint64_t wload_bar[2];
-  __shared__ __align__(8) uint64_t aload_bar[N_AB];
-  __shared__ __align__(8) uint64_t gemm_bar;
+  extern __shared__ __align__(128) uint8_t smem_raw[];   // (operand descriptors without swizzle need 16-byte alignment)
+  __shared__ __align__(8) Bars bars;
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_nmax;
 
   const RolloutArgs& A = G.R;
   const int tid = threadIdx.x, lane_id = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  // warps 0-3: main (one trajectory per thread), 4-7: helpers (other half of every epilogue), 8: MMA issuer
-  const bool main_role = warp < 4, helper = warp >= 4 && warp < 8, issuer = warp == 8;
+  const bool main_role = warp < 4, helper = warp >= 4 && warp < 8;
   const int wq = warp & 3, row = tid & 127;
   const int s = blockIdx.y, T = A.T, L = A.L;
   const int solver = A.solver == HODE_SOLVER_RK4 ? 0 : 1;
   const int N = solver == 0 ? 4 : 7;
-  // DP5(4) is first-same-as-last: stage 1 of step n+1 IS stage 7 of step n.  The rollout saved its
-  // value (save_k), so the recomputation starts at stage 2, and the reverse sweep pulls the shared
-  // evaluation back once, as stage 7 of the earlier step, with both cotangents added (`carry`).
-  // Stage 1 of the very first step is pulled back by one extra iteration: a zero-length step at
-  // (t0, y0) whose stage 7 receives the carry.
-  const bool fsal = solver == 1 && A.save_k1 != 0;
+  const bool fsal = solver == 1;   // (the records of this path always carry the stage derivatives)
   const int i0 = fsal ? 1 : 0;
 
-  // shared memory: the forward weight image during the recomputation; during the reverse sweep the
-  // same bytes hold the double-buffered operand images and W^T slots (OFF_AB / OFF_DB / OFF_WS)
-  float* img = reinterpret_cast<float*>(smem_raw);
-  const int bwd_cap = BWD_BYTES / 4;
-  const int img_cap = ((G.fwd_floats > bwd_cap ? G.fwd_floats : bwd_cap) + 255) & ~255;
-  // next step's record of every main thread, fetched while the current reverse sweep runs (the streaming
-  // stash traffic evicts an L2 prefetch long before it is used: the plain load cost 4.8 k cycles per step)
-  float* rec_sh = img + img_cap;                       // [128][HODE_REC_FLOATS]
-  float* t_sh_buf = rec_sh + TILE * HODE_REC_FLOATS;
-  float* red = img;   // [17][128] theta-gradient reduction scratch at the very end
+  float4* rec_sh = reinterpret_cast<float4*>(smem_raw + OFF_REC);
+  float* t_sh_buf = reinterpret_cast<float*>(smem_raw + OFF_T);
   if (tid == 0) {
-    tc::mbar_init(&mma_bar, 1);
-    tc::mbar_init(&load_bar, 1);
-    tc::mbar_init(&wload_bar[0], 1);
-    tc::mbar_init(&wload_bar[1], 1);
-    for (int i = 0; i < N_AB; ++i) tc::mbar_init(&aload_bar[i], 1);
-    tc::mbar_init(&gemm_bar, 1);
+    tc::mbar_init(&bars.f_bar, 1);
+    tc::mbar_init(&bars.b_bar, 1);
+    tc::mbar_init(&bars.wf_full, 1);
+    tc::mbar_init(&bars.wf_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars.wt_full[i], 1);
+      tc::mbar_init(&bars.wt_free[i], 1);
+      tc::mbar_init(&bars.ab_full[i], 1);
+      tc::mbar_init(&bars.ab_free[i], 1);
+    }
+    for (int i = 0; i < MAXL; ++i) tc::mbar_init(&bars.st_done[i], 2 * TILE);
+    tc::mbar_init(&bars.done, 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   const float* t_shared = nullptr;
-  if (!A.t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) {
+  if (G.t_in_smem) {
     for (int i = tid; i < T; i += blockDim.x) t_sh_buf[i] = A.t_obs[i];
     t_shared = t_sh_buf;
+  }
+  if (main_role) {
+    // the constant-1 input feature of the weight gradients (its accumulator column is the bias gradient):
+    // group 8 of both input-operand buffers = [1, 0 x 7] (hi) / 0 (mid); the bulk copies only touch groups 0..7
+#pragma unroll
+    for (int bf = 0; bf < 2; ++bf) {
+      uint8_t* g8 = smem_raw + OFF_AB + bf * AB_BYTES + 8 * ST_GRP + row * 16;
+      *reinterpret_cast<uint4*>(g8) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(g8 + AB_PART) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc::fence_proxy_async();
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
 
-  TileCtx c;
-  c.img = img;
-  c.mma_bar = &mma_bar;
-  c.tmem = tmem_base_s;
-  c.lane_base = (uint32_t)(wq * 32) << 16;
-  c.parity = 0;
-  c.bar_id = 1;
-  c.bar_all = 2;
-  c.wq = wq;
-  c.L = L;
-  {
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+  if (main_role) {
     uint32_t ones[8] = {0x3F800000u, 0x3F800000u, 0u, 0u, 0u, 0u, 0u, 0u};
-    HODE_TMEM_ST_X8(c.tmem + c.lane_base + TM_ONES, ones);
+    HODE_TMEM_ST_X8(tmem + lane_base + TM_ONES, ones);
     tc::wait_st();
   }
-  uint32_t load_parity = 0;
-  // this CTA's activation stash: [stage][layer] blocks of ST_BLK bytes (hode_tc_mlp.cuh)
-  const size_t stage_stride = (size_t)L * ST_BLK;
-  uint8_t* stash0 = reinterpret_cast<uint8_t*>(G.stash) +
-                    ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)NSTAGE_MAX * stage_stride;
-
-  BwdCtx bc;
-  bc.smem = smem_raw;
-  bc.wsrc = G.img_bwd + (size_t)s * G.bwd_floats;
-  bc.stash_cta = stash0;
-  bc.stage_blk = stash0;
-  bc.wload_bar = wload_bar;
-  bc.aload_bar = aload_bar;
-  bc.gemm_bar = &gemm_bar;
-  bc.ph = 0u;
-  bc.k = 0; bc.k_end = 0; bc.stage_top = 0;
-  bc.first = 1u;
-  bc.row = row;
-
-  const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
-  const bool gd_present = A.in_mode[HODE_CH_GD] != HODE_IN_ABSENT;
-  const int nsub = A.n_substeps > 0 ? A.n_substeps : 1;
-  float gth[HODE_N_THETA];
-#pragma unroll
-  for (int i = 0; i < HODE_N_THETA; ++i) gth[i] = 0.f;
-
-  // swap the shared-memory weight image (forward <-> transposed); every thread calls it
-  auto load_image = [&](const float* src, int floats) {
-    // the weight-gradient MMAs of the previous reverse sweep still read the staging arrays
-    wait_gemm(bc);
-    tc::fence_before_sync();
-    __syncthreads();   // nobody still reads the old contents (all MMAs that did have been waited for)
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)floats * 4u;
-      tc::mbar_expect_tx(&load_bar, bytes);
-      tc::bulk_g2s(img, src, bytes, &load_bar);
-    }
-    tc::mbar_wait(&load_bar, load_parity);
-    load_parity ^= 1u;
-  };
+  uint8_t* stash0 = G.stash + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(2 * L) * ST_BLK;
   const float* fwd_src = G.img_fwd + (size_t)s * G.fwd_floats;
-  // start of a reverse sweep: the forward image is dead; (re)write the constant features of the
-  // input staging (feature 64 = 1 -> bias-gradient column, 65..79 = 0)
-  // input-operand group 8 = [1, 0 x 7]: its accumulator column is the bias gradient), and start
-  // the operand pipeline of the sweep's first phases.  The stash was written with ordinary global
-  // stores and is read back by bulk copies: cross-proxy fence before the barrier.
-  auto begin_reverse = [&]() {
-    tc::fence_proxy_async_all();
-    tc::fence_before_sync();
-    __syncthreads();
-    if (main_role) {
-#pragma unroll
-      for (int bf = 0; bf < N_AB; ++bf) {
-        uint8_t* g8 = smem_raw + OFF_AB + bf * AB_BYTES + 8 * ST_GRP + row * 16;
-        *reinterpret_cast<uint4*>(g8) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(g8 + AB_PART) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    bc.k = 0;
-    bc.k_end = (N - i0) * (L + 1);
-    bc.stage_top = N - 1;
-    if (tid == 0) {
-      prefetch_W(bc, L, 0, bc.ph);
-      prefetch_A(bc, L, 0, bc.ph);
-      prefetch_A(bc, L, 1, bc.ph + 1u);
-      prefetch_W(bc, L, 1, bc.ph + 1u);
-    }
-  };
+  const float* bwd_src = G.img_bwd + (size_t)s * G.bwd_floats;
 
   const int32_t* my_tiles = G.sched_tiles + (size_t)s * G.n_tiles;
   const int tile_beg = G.sched_off[(size_t)s * (gridDim.x + 1) + blockIdx.x];
@@ -584,432 +417,690 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     __syncthreads();
     return s_nmax;
   };
+  bool have = false;   // this CTA has issued at least one item: the accumulators are initialised
 
-  // Three roles, each entirely inside its own branch so that ptxas allocates registers against
-  // the role's budget: the main warpgroup carries the per-trajectory integrator and adjoint state
-  // (it takes the registers the other two warpgroups give back), the helper warpgroup only runs
-  // epilogue halves, the third warpgroup holds the MMA-issuer warp (its other three warps idle
-  // through the CTA-wide barriers: setmaxnreg works on whole warpgroups).
+  // Roles: each entirely inside its own branch so that ptxas allocates registers against the role's budget.
   if (helper) {
+    // ================================ helper warps: the other half of every epilogue ========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 128;" ::: "memory");
-  for (int tk = tile_beg; tk < tile_end; ++tk) {
-    const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-    for (int it = 0; it < n_iter; ++it) {
-      load_image(fwd_src, G.fwd_floats);
+    EpiCtx e{&bars, smem_raw, stash0, tmem, lane_base, 0u, 0u, 0u, row, L};
+    uint32_t m_f = 0u, mcur[4] = {0u, 0u, 0u, 0u}, mnext[4] = {0u, 0u, 0u, 0u};
+    for (int tk = tile_beg; tk < tile_end; ++tk) {
+      const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+      if (n_iter == 0) continue;
+      have = true;
+      bar_arrive<BAR_F>();   // first item's input operand (written by the main threads)
 #pragma unroll 1
-      for (int i = i0; i < N; ++i) mlp_tile_helper<true, true>(c, stash0 + (size_t)i * stage_stride, row);
-      begin_reverse();
+      for (int l = 0; l < L; ++l) put4(mnext, l, fwd_epilogue<MODE, false>(e, l, (int)(m_f & 1u)));
+      m_f += 1u;
+      for (int it = 0; it < n_iter; ++it) {
+        const int i_lo = item_i_lo(it, n_iter, N, i0, fsal);
 #pragma unroll 1
-      for (int i = N - 1; i >= i0; --i) {
-        bc.stage_blk = stash0 + (size_t)i * stage_stride;
-        mlp_bwd_tile<false>(c, bc, nullptr, nullptr, nullptr, [] {});
+        for (int i = N - 1; i >= i_lo; --i) {
+          const bool has_F = !(it == n_iter - 1 && i == i_lo);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) mcur[l] = mnext[l];
+          bar_arrive<BAR_B>();   // delta_L (main threads)
+          e.ph += 1u;
+          if (has_F) bar_arrive<BAR_F>();
+#pragma unroll 1
+          for (int l = 0; l < L; ++l) {
+            if (has_F) put4(mnext, l, fwd_epilogue<MODE, false>(e, l, (int)(m_f & 1u)));
+            bwd_epilogue<false>(e, L - l, sel4(mcur, L - l - 1), nullptr);
+          }
+          tc::mbar_wait(&bars.b_bar, e.b_cnt & 1u);   // g_x: nothing to read, but the phase must be observed
+          e.b_cnt += 1u;
+          if (has_F) m_f += 1u;
+        }
       }
     }
-  }
-  wait_gemm(bc);
-  tc::fence_before_sync();
-  __syncthreads();   // accumulators complete
-  __syncthreads();   // theta-gradient scratch written
-  tc::fence_before_sync();
-  __syncthreads();   // TMEM may be released
   } else if (!main_role) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
-  for (int tk = tile_beg; tk < tile_end; ++tk) {
-    const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-    for (int it = 0; it < n_iter; ++it) {
-      load_image(fwd_src, G.fwd_floats);
-      if (issuer) {
-#pragma unroll 1
-        for (int i = i0; i < N; ++i) mlp_fwd_issue<true>(c);
-      }
-      begin_reverse();
-      if (issuer) {
-#pragma unroll 1
-        for (int i = N - 1; i >= i0; --i) mlp_bwd_issue(c, bc);
-      }
-    }
-  }
-  wait_gemm(bc);
-  tc::fence_before_sync();
-  __syncthreads();   // accumulators complete
-  __syncthreads();   // theta-gradient scratch written
-  tc::fence_before_sync();
-  __syncthreads();   // TMEM may be released
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
-  for (int tk = tile_beg; tk < tile_end; ++tk) {
-    const long q = (long)my_tiles[tk] * TILE + row;   // slot in the step-count-sorted order
-    const bool valid = q < A.B;
-    const long unit = valid ? (long)G.perm[(size_t)s * A.B + q] : (long)s * A.B;
-    const long bs = unit - (long)s * A.B;
-    int n = valid ? A.save_n[unit] : 0;
-    const bool ok = valid && n >= 0;
-    if (n < 0) n = 0;
-    const int nmax = tile_nmax(n);
-
-    TrajInputs in;
-    in.T = T; in.cur = 0;
-    in.t_obs = A.t_per_traj ? A.t_obs + bs * T : (t_shared ? t_shared : A.t_obs);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      in.mode[ch] = A.in_mode[ch];
-      in.u[ch] = in.mode[ch] == HODE_IN_SERIES ? A.u[ch] + bs * T
-               : in.mode[ch] == HODE_IN_CONST ? A.u[ch] + bs : nullptr;
-    }
-    const float* gtraj = G.grad_traj + (size_t)unit * T * NS;
-    const double t_bound = (double)in.t_obs[T - 1];
-    float lam[NS];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) lam[i] = 0.f;
-    int ei = T - 1;
-
-    float carry[NS];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) carry[i] = 0.f;
-    double t_next = 0.0;
-    const int n_iter = nmax + (fsal ? 1 : 0);
-    for (int it = 0; it < n_iter; ++it) {
-      // =========================== forward recomputation =========================================
-      HODE_TL(200);
-      load_image(fwd_src, G.fwd_floats);
-      HODE_TL(201);
-      const int sidx = n - 1 - it;
-      const bool real = ok && sidx >= 0;
-      const bool act = real || (fsal && ok && sidx == -1);   // sidx == -1: the zero-length step at (t0, y0)
-      double t = (double)in.t_obs[0], t_new = t, h = 0.0;
-      float y[NS], k1[NS];
-#pragma unroll
-      for (int i = 0; i < NS; ++i) { y[i] = 0.f; k1[i] = 0.f; }
-      if (act && !real && n > 0) {   // the zero-length step: y0 = the state the first record starts from
-        double t_;
-        float h_;
-        step_rec_load(step_rec(A, unit, 0), t_, h_, y, nullptr);
-      }
-      if (real) {
-        const float* rec = step_rec(A, unit, sidx);
-        if (it > 0) {   // fetched into shared memory during the previous iteration (it was `real` there too)
-          tc::cp_async_wait_all();
-          rec = rec_sh + row * HODE_REC_FLOATS;
+    if (warp == 8) {
+      // ================================ MMA issuer ============================================================
+      const uint32_t base = tc::smem_u32(smem_raw);
+      const uint32_t wf_s = base + OFF_WF;
+      uint32_t n_f = 0u, ph = 0u, first = 1u;
+      auto issue_F = [&](int l) {
+        bar_wait<BAR_F>();
+        tc::mbar_wait(&bars.wf_full, n_f & 1u);
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          if (l == 0) issue_layer<MODE, H, 16, false>(tmem, wf_s, wf_s + 1024u * 4u, 0u);
+          else issue_layer<MODE, H, 64, true>(tmem, wf_s, wf_s + 4096u * 4u, wf_s + 8192u * 4u);
+          tc::mma_commit(&bars.f_bar);
+          tc::mma_commit(&bars.wf_free);
         }
-        float h_rec;
-        step_rec_load(rec, t, h_rec, y, fsal ? k1 : nullptr);
-        if (solver == 0) {
-          h = (double)h_rec;
-          t_new = t + h;
-        } else {
-          t_new = (sidx + 1 < n) ? t_next : t_bound;   // the next record's start time, seen one iteration ago
-          h = t_new - t;
+        __syncwarp();
+        n_f += 1u;
+      };
+      // phase q:  u_{q-1} = delta_q W_q (delta image x W_q^T slot)  and  dW_q += delta_q^T [a_{q-1} | 1]
+      // (a_{-1} = the stage's input features x, u_{-1} = the cotangent of x)
+      auto issue_B = [&](int q) {
+        const uint32_t buf = ph & 1u, par = (ph >> 1) & 1u;
+        const uint32_t ws = base + OFF_WT + buf * WT_BYTES;
+        const uint32_t a_hi = base + OFF_AB + buf * AB_BYTES, a_mid = a_hi + AB_PART;
+        const uint32_t d_hi = base + OFF_DB + buf * DB_BYTES, d_mid = d_hi + ST_PART;
+        bar_wait<BAR_B>();
+        tc::mbar_wait(&bars.wt_full[buf], par);
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          if (q == L) issue_u<H, 1>(tmem + TM_DB, d_hi, d_mid, ws, ws + 2048u);          // u_{L-1} = delta_L W_out (K = 16)
+          else if (q >= 1) issue_u<H, 4>(tmem + TM_DB, d_hi, d_mid, ws, ws + 8192u);     // u_{q-1} = delta_q W_q
+          else issue_u<16, 4>(tmem + TM_DB, d_hi, d_mid, ws, ws + 2048u);                // g_x = delta_0 W_0
+          tc::mma_commit(&bars.b_bar);
+          tc::mma_commit(&bars.wt_free[buf]);
         }
-        t_next = t;
-      }
-      const float hf = (float)h;
-#ifdef HODE_TIMELINE
-      if (hf + y[0] + k1[5] == 123456.f) HODE_TL(299);   // (forces the loads to complete before the next mark)
-#endif
-      HODE_TL(205);
-      // Inputs of this step as one linear piece per channel (value = c_v1 + alpha * c_dv): valid when a
-      // step cannot cross an input kink (RK4, kink clipping, or no series input), see
-      // hode_rollout_tc.cu::lane_cache_inputs.  Otherwise every stage looks its interval up.
-      const bool cached = solver == 0 || A.kink_mode == HODE_KINK_CLIP || !any_series(in);
-      float c_t1 = 0.f, c_dt = 1.f, c_v1[3], c_dv[3];
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        c_v1[ch] = in.mode[ch] == HODE_IN_CONST ? in.u[ch][0] : 0.f;
-        c_dv[ch] = 0.f;
-      }
-      {
-        int lo = 0, hi = T;
-        const float t32 = (float)t;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (in.t_obs[mid] < t32) lo = mid + 1; else hi = mid; }
-        in.cur = lo > 0 ? lo - 1 : 0;
-        if (cached && any_series(in) && T >= 2) {
-          int i0 = (lo < T && in.t_obs[lo] == t32) ? lo : lo - 1;
-          i0 = i0 < 0 ? 0 : (i0 > T - 2 ? T - 2 : i0);
-          c_t1 = in.t_obs[i0];
-          c_dt = in.t_obs[i0 + 1] - c_t1;
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            if (in.mode[ch] != HODE_IN_SERIES) continue;
-            const float v1 = in.u[ch][i0], v2 = in.u[ch][i0 + 1];
-            c_v1[ch] = v1;
-            c_dv[ch] = v2 - v1;
+        __syncwarp();
+        tc::mbar_wait(&bars.ab_full[buf], par);
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
+          if (q == L) issue_dw<128, 16>(tmem + DW_O, a_hi, a_mid, d_hi, d_mid, first);
+          else if (q >= 1) issue_dw<64, 72>(tmem + DW_H0 + DW_HS * (uint32_t)(q - 1), d_hi, d_mid, a_hi, a_mid, first);
+          else issue_dw<64, 16>(tmem + DW_0, d_hi, d_mid, a_hi, a_mid, first);
+          tc::mma_commit(&bars.ab_free[buf]);
+        }
+        __syncwarp();
+        ph += 1u;
+      };
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        if (n_iter == 0) continue;
+        have = true;
+#pragma unroll 1
+        for (int l = 0; l < L; ++l) issue_F(l);
+        for (int it = 0; it < n_iter; ++it) {
+          const int i_lo = item_i_lo(it, n_iter, N, i0, fsal);
+#pragma unroll 1
+          for (int i = N - 1; i >= i_lo; --i) {
+            const bool has_F = !(it == n_iter - 1 && i == i_lo);
+            issue_B(L);
+            if (has_F) issue_F(0);
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+              if (has_F && l + 1 < L) issue_F(l + 1);
+              issue_B(L - 1 - l);
+            }
+            first = 0u;
           }
         }
       }
-#ifdef HODE_TIMELINE
-      if (c_v1[0] + c_dv[1] + c_dt == 123456.f) HODE_TL(299);
-#endif
-      HODE_TL(206);
-      // stage derivatives / cotangents are indexed statically (predicated selects) so that they
-      // live in registers rather than in local memory
-      float k[NSTAGE_MAX][NS], tv[NSTAGE_MAX], gdv[NSTAGE_MAX];
-#pragma unroll
-      for (int i = 0; i < NSTAGE_MAX; ++i) {
-        tv[i] = 0.f; gdv[i] = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) k[i][cc] = 0.f;
-      }
-#pragma unroll
-      for (int cc = 0; cc < NS; ++cc) k[0][cc] = k1[cc];
+      if (tc::elect_one()) tc::mma_commit(&bars.done);   // every MMA of this CTA has completed when this arrives
+      __syncwarp();
+    } else if (warp == 9) {
+      // ================================ loader: forward weights, one layer at a time =========================
+      uint32_t n = 0u;
+      const int bias_off = (int)(IMG_L0 + (uint32_t)(L - 1) * IMG_HID + IMG_OUT);
+      auto load_layer = [&](int l) {
+        if (n >= 1u) tc::mbar_wait(&bars.wf_free, (n - 1u) & 1u);
+        if (lane_id == 0) {
+          uint8_t* dst = smem_raw + OFF_WF;
+          if (l == 0) {
+            tc::mbar_expect_tx(&bars.wf_full, IMG_L0 * 4u);
+            tc::bulk_g2s(dst, fwd_src, IMG_L0 * 4u, &bars.wf_full);
+          } else {
+            tc::mbar_expect_tx(&bars.wf_full, (IMG_HID + 512u) * 4u);
+            tc::bulk_g2s(dst, fwd_src + IMG_L0 + (size_t)(l - 1) * IMG_HID, IMG_HID * 4u, &bars.wf_full);
+            tc::bulk_g2s(dst + IMG_HID * 4u, fwd_src + bias_off + l * 512, 512u * 4u, &bars.wf_full);
+          }
+        }
+        __syncwarp();
+        n += 1u;
+      };
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        if (n_iter == 0) continue;
+        int items = 0;
+        for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
 #pragma unroll 1
-      for (int i = i0; i < N; ++i) {
-        float ys[NS];
+        for (int m = 0; m < items; ++m)
+#pragma unroll 1
+          for (int l = 0; l < L; ++l) load_layer(l);
+      }
+    } else if (warp == 10) {
+      // ================================ loader: W_q^T of every pull-back phase ================================
+      uint32_t ph = 0u;
+      auto load_wt = [&](int q) {
+        const uint32_t buf = ph & 1u, k = ph >> 1;
+        if (k >= 1u) tc::mbar_wait(&bars.wt_free[buf], (k - 1u) & 1u);
+        if (lane_id == 0) {
+          int off, floats;
+          if (q == L) { off = 0; floats = 1024; }
+          else if (q >= 1) { off = 1024 + (L - 1 - q) * 4096; floats = 4096; }
+          else { off = 1024 + (L - 1) * 4096; floats = 1024; }
+          tc::mbar_expect_tx(&bars.wt_full[buf], (uint32_t)floats * 4u);
+          tc::bulk_g2s(smem_raw + OFF_WT + buf * WT_BYTES, bwd_src + off, (uint32_t)floats * 4u, &bars.wt_full[buf]);
+        }
+        __syncwarp();
+        ph += 1u;
+      };
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        if (n_iter == 0) continue;
+        int items = 0;
+        for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
+#pragma unroll 1
+        for (int m = 0; m < items; ++m)
+#pragma unroll 1
+          for (int q = L; q >= 0; --q) load_wt(q);
+      }
+    } else {
+      // ================================ loader: stashed activations a_{q-1} of every pull-back phase ============
+      uint32_t ph = 0u, m_all = 0u;
+      auto load_ab = [&](int q) {
+        const uint32_t buf = ph & 1u, k = ph >> 1;
+        if (q >= 1) tc::mbar_wait(&bars.st_done[q - 1], m_all & 1u);   // written by the epilogue threads (generic proxy + fence)
+        if (k >= 1u) tc::mbar_wait(&bars.ab_free[buf], (k - 1u) & 1u);
+        if (lane_id == 0) {
+          if (q >= 1) {
+            const uint8_t* src = stash0 + ((size_t)(m_all & 1u) * L + (q - 1)) * ST_BLK;
+            uint8_t* dst = smem_raw + OFF_AB + buf * AB_BYTES;
+            tc::mbar_expect_tx(&bars.ab_full[buf], 2u * ST_PART);
+            tc::bulk_g2s(dst, src, ST_PART, &bars.ab_full[buf]);
+            tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, &bars.ab_full[buf]);
+          } else {
+            tc::mbar_arrive(&bars.ab_full[buf]);   // phase 0: the main threads write x themselves
+          }
+        }
+        __syncwarp();
+        ph += 1u;
+      };
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        if (n_iter == 0) continue;
+        int items = 0;
+        for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
+#pragma unroll 1
+        for (int m = 0; m < items; ++m) {
+#pragma unroll 1
+          for (int q = L; q >= 0; --q) load_ab(q);
+          m_all += 1u;
+        }
+      }
+    }
+  } else {
+    // ================================ main warps: one trajectory per thread ====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
+    EpiCtx e{&bars, smem_raw, stash0, tmem, lane_base, 0u, 0u, 0u, row, L};
+    uint32_t m_f = 0u, mcur[4] = {0u, 0u, 0u, 0u}, mnext[4] = {0u, 0u, 0u, 0u};
+    const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
+    const bool gd_present = A.in_mode[HODE_CH_GD] != HODE_IN_ABSENT;
+    const int nsub = A.n_substeps > 0 ? A.n_substeps : 1;
+    float gth[HODE_N_THETA];
+#pragma unroll
+    for (int i = 0; i < HODE_N_THETA; ++i) gth[i] = 0.f;
+
+    for (int tk = tile_beg; tk < tile_end; ++tk) {
+      const long q = (long)my_tiles[tk] * TILE + row;   // slot in the step-count-sorted order
+      const bool valid = q < A.B;
+      const long unit = valid ? (long)G.perm[(size_t)s * A.B + q] : (long)s * A.B;
+      const long bs = unit - (long)s * A.B;
+      int n = valid ? A.save_n[unit] : 0;
+      const bool ok = valid && n >= 0;
+      if (n < 0) n = 0;
+      const int nmax = tile_nmax(n);
+      const int n_iter = nmax + (fsal ? 1 : 0);
+      if (n_iter == 0) {
+        if (G.grad_y0 && valid) {   // no steps at all (T == 1): the gradient of y0 is the cotangent of the first row
+          float* o = G.grad_y0 + (size_t)unit * NS;
+          const float* g = G.grad_traj + (size_t)unit * T * NS;
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) o[cc] = ok ? g[cc] : 0.f;
+        }
+        continue;
+      }
+      have = true;
+
+      TrajInputs in;
+      in.T = T; in.cur = 0;
+      in.t_obs = A.t_per_traj ? A.t_obs + bs * T : (t_shared ? t_shared : A.t_obs);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        in.mode[ch] = A.in_mode[ch];
+        in.u[ch] = in.mode[ch] == HODE_IN_SERIES ? A.u[ch] + bs * T
+                 : in.mode[ch] == HODE_IN_CONST ? A.u[ch] + bs : nullptr;
+      }
+      // Inputs of a step as one linear piece per channel (value = v1 + alpha * dv, the rollout's own formula,
+      // hode_rollout_tc.cu::lane_eval): valid when a step cannot cross an input kink (RK4, kink clipping, or no
+      // series input).  Otherwise every stage looks its interval up.  Channels: [0] = tVNS, [1] = GD (the meal
+      // input enters f additively and has no parameter: the adjoint does not need it).
+      const bool cached = solver == 0 || A.kink_mode == HODE_KINK_CLIP || !any_series(in);
+      const float* gtraj = G.grad_traj + (size_t)unit * T * NS;
+      const double t_bound = (double)in.t_obs[T - 1];
+      const double t_first = (double)in.t_obs[0];
+      float lam[NS], carry[NS], y_later[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { lam[i] = 0.f; carry[i] = 0.f; y_later[i] = 0.f; }
+      double t_later = 0.0;
+      int ei = T - 1;
+
+      // ---- the step being pulled back ("context") and the input piece of it / of the next (earlier) step --------
+      double t = t_first, t_new = t_first, h = 0.0;
+      float hf = 0.f, y[NS], k[6][NS];
+      bool real = false, act = false;
+      float pc_t1 = 0.f, pc_inv = 1.f, pc_v1[2], pc_dv[2];   // current piece
+      float pn_t1 = 0.f, pn_inv = 1.f, pn_v1[2], pn_dv[2];   // piece of the step of the next iteration
+      auto piece_for = [&](double tt, float& t1, float& inv, float* v1, float* dv) {
+        t1 = 0.f; inv = 1.f;
+        v1[0] = in.mode[HODE_CH_TVNS] == HODE_IN_CONST ? in.u[HODE_CH_TVNS][0] : 0.f;
+        v1[1] = in.mode[HODE_CH_GD] == HODE_IN_CONST ? in.u[HODE_CH_GD][0] : 0.f;
+        dv[0] = 0.f; dv[1] = 0.f;
+        if (cached && any_series(in) && T >= 2) {
+          int lo = 0, hi = T;
+          const float t32 = (float)tt;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (in.t_obs[mid] < t32) lo = mid + 1; else hi = mid; }
+          int j0 = (lo < T && in.t_obs[lo] == t32) ? lo : lo - 1;
+          j0 = j0 < 0 ? 0 : (j0 > T - 2 ? T - 2 : j0);
+          t1 = in.t_obs[j0];
+          inv = 1.0f / (in.t_obs[j0 + 1] - t1);
+          if (in.mode[HODE_CH_TVNS] == HODE_IN_SERIES) {
+            const float a_ = in.u[HODE_CH_TVNS][j0], b_ = in.u[HODE_CH_TVNS][j0 + 1];
+            v1[0] = a_; dv[0] = b_ - a_;
+          }
+          if (in.mode[HODE_CH_GD] == HODE_IN_SERIES) {
+            const float a_ = in.u[HODE_CH_GD][j0], b_ = in.u[HODE_CH_GD][j0 + 1];
+            v1[1] = a_; dv[1] = b_ - a_;
+          }
+        }
+      };
+      // tVNS and GD at time t32 (piece = the step's cached piece)
+      auto inputs_at = [&](float t32, float t1, float inv, const float* v1, const float* dv, float& tvns, float& gd) {
+        if (cached) {
+          const float alpha = (t32 - t1) * inv;
+          tvns = fmaf(alpha, dv[0], v1[0]);
+          gd = fmaf(alpha, dv[1], v1[1]);
+        } else {
+          int lo = 0, hi = T;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (in.t_obs[mid] < t32) lo = mid + 1; else hi = mid; }
+          tvns = input_channel(in, HODE_CH_TVNS, t32, lo);
+          gd = input_channel(in, HODE_CH_GD, t32, lo);
+        }
+      };
+      // record of step sidx -> context; chunk(c) yields 16-byte chunk c of the record
+      auto set_ctx = [&](int it, auto&& chunk) {
+        const int sidx = n - 1 - it;
+        real = ok && sidx >= 0;
+        act = real || (fsal && ok && sidx == -1);   // sidx == -1: the zero-length step at (t0, y0)
+        t = t_first; t_new = t_first; h = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NS; ++cc) {
+          y[cc] = (act && !real) ? y_later[cc] : 0.f;   // the zero-length step starts from the state the first record holds
+#pragma unroll
+          for (int j = 0; j < 6; ++j) k[j][cc] = 0.f;
+        }
+        if (real) {
+          float r[HODE_REC_FLOATS_K];
+#pragma unroll
+          for (int c4 = 0; c4 < REC_CHUNKS; ++c4) {
+            const float4 v = chunk(c4);
+            r[4 * c4] = v.x; r[4 * c4 + 1] = v.y; r[4 * c4 + 2] = v.z; r[4 * c4 + 3] = v.w;
+          }
+          t = __longlong_as_double(((long long)__float_as_int(r[1]) << 32) | (long long)(unsigned)__float_as_int(r[0]));
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) {
+            y[cc] = r[4 + cc];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) k[j][cc] = r[10 + 6 * j + cc];
+          }
+          if (solver == 0) {
+            h = (double)r[2];
+            t_new = t + h;
+          } else {
+            t_new = (sidx + 1 < n) ? t_later : t_bound;   // the later record's start time, seen one iteration ago
+            h = t_new - t;
+          }
+        }
+        hf = (float)h;
+        // the record of the next iteration's step: into shared memory while this step is pulled back
+        if (ok && sidx >= 1) {
+          const float* nxt = step_rec(A, unit, sidx - 1);
+#pragma unroll
+          for (int c4 = 0; c4 < REC_CHUNKS; ++c4) tc::cp_async16(&rec_sh[c4 * TILE + row], nxt + 4 * c4);
+        }
+        tc::cp_async_commit();
+      };
+      // input features of stage i of the current step: x = [t_i, ys_i, ys_i[3], tVNS(t_i)]
+      auto stage_x = [&](int i, float* ys, float* x, float& gd) {
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) {
           float a_ = 0.f;
 #pragma unroll
-          for (int j = 0; j < NSTAGE_MAX - 1; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);   // zero for j >= i
+          for (int j = 0; j < 6; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);   // zero for j >= i
           ys[cc] = fmaf(hf, a_, y[cc]);
         }
         const float ci = kC[solver][i];
         const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
         const float t32 = (float)te;
-        float meal, tvns, gd;
-        if (cached) {
-          const float alpha = __fdiv_rn(t32 - c_t1, c_dt);
-          meal = __fadd_rn(c_v1[HODE_CH_MEAL], __fmul_rn(alpha, c_dv[HODE_CH_MEAL]));
-          tvns = __fadd_rn(c_v1[HODE_CH_TVNS], __fmul_rn(alpha, c_dv[HODE_CH_TVNS]));
-          gd = __fadd_rn(c_v1[HODE_CH_GD], __fmul_rn(alpha, c_dv[HODE_CH_GD]));
-        } else {
-          int idx = 0;
-          if (any_series(in)) idx = grid_index_from(in, t32, in.cur);
-          meal = input_channel(in, HODE_CH_MEAL, t32, idx);
-          tvns = input_channel(in, HODE_CH_TVNS, t32, idx);
-          gd = input_channel(in, HODE_CH_GD, t32, idx);
-        }
-        float x[HODE_NN_IN], r[NS], d[NS];
+        float tvns;
+        inputs_at(t32, pc_t1, pc_inv, pc_v1, pc_dv, tvns, gd);
+        if (!act) { tvns = 0.f; gd = 0.f; }
         x[0] = t32;
 #pragma unroll
         for (int cc = 0; cc < NS; ++cc) x[1 + cc] = ys[cc];
         x[7] = ys[3];
         x[8] = tvns;
+      };
+
+      // ---- first iteration's context straight from global memory; its top stage is recomputed un-overlapped --------
+      {
+        const int sidx0 = n - 1;
+        const float4* r4 = reinterpret_cast<const float4*>(step_rec(A, unit, sidx0 > 0 ? sidx0 : 0));
+        set_ctx(0, [&](int c4) { return r4[c4]; });
+        piece_for(t, pc_t1, pc_inv, pc_v1, pc_dv);
+      }
+      bool later_valid = false;   // y_later / t_later hold the start of the step pulled back one iteration ago
+      {
+        float ys[NS], x[HODE_NN_IN], gd;
+        stage_x(N - 1, ys, x, gd);
         __syncwarp();
-        HODE_TL(207);
-        mlp_tile<true, true>(c, x, r, stash0 + (size_t)i * stage_stride, row,
-                             [&] { rhs_mech(th, ys, meal, gd, gd_present, d); });
-#pragma unroll
-        for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
-          if (jj == i) {
-            tv[jj] = tvns; gdv[jj] = gd;
-#pragma unroll
-            for (int cc = 0; cc < NS; ++cc) k[jj][cc] = __fadd_rn(d[cc], r[cc]);
-          }
-        }
-      }
-      // =========================== reverse sweep ===================================================
-      HODE_TL(202);
-      // the next iteration's step record: fetch it into shared memory while this sweep runs
-      if (real && sidx > 0) {
-        const float* nxt = step_rec(A, unit, sidx - 1);
-#pragma unroll
-        for (int q4 = 0; q4 < HODE_REC_FLOATS / 4; ++q4) tc::cp_async16(rec_sh + row * HODE_REC_FLOATS + 4 * q4, nxt + 4 * q4);
-        tc::cp_async_commit();
-      }
-      begin_reverse();
-      HODE_TL(203);
-      float gy[NS], gk[NSTAGE_MAX][NS];
-#pragma unroll
-      for (int i = 0; i < NSTAGE_MAX; ++i)
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) gk[i][cc] = 0.f;
-      if (solver == 0) {
-        if (act && (sidx + 1) % nsub == 0) {
-          const float* g = gtraj + (size_t)((sidx + 1) / nsub) * NS;
-#pragma unroll
-          for (int cc = 0; cc < NS; ++cc) lam[cc] += g[cc];
-        }
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) gy[cc] = act ? lam[cc] : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int cc = 0; cc < NS; ++cc) gk[j][cc] = hf * kB[0][j] * gy[cc];
-      } else {
-        float gnew[NS];
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) { gnew[cc] = act ? lam[cc] : 0.f; gy[cc] = 0.f; }
-        if (act) {
-          while (ei >= 0 && (double)in.t_obs[ei] > t) {
-            const double te = (double)in.t_obs[ei];
-            const float* g = gtraj + (size_t)ei * NS;
-            if (te >= t_new) {
-              if (te == t_new) {
-#pragma unroll
-                for (int cc = 0; cc < NS; ++cc) gnew[cc] += g[cc];
-              }
-            } else {
-              const float xq = (float)((te - t) / h);
-#pragma unroll
-              for (int cc = 0; cc < NS; ++cc) gy[cc] += g[cc];
-#pragma unroll
-              for (int i = 0; i < 7; ++i) {
-                const float wgt = hf * xq * fmaf(xq, fmaf(xq, fmaf(xq, kP[i][3], kP[i][2]), kP[i][1]), kP[i][0]);
-#pragma unroll
-                for (int cc = 0; cc < NS; ++cc) gk[i][cc] = fmaf(wgt, g[cc], gk[i][cc]);
-              }
-            }
-            --ei;
-          }
-        }
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) {
-          gy[cc] += gnew[cc];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) gk[j][cc] = fmaf(hf * kB[1][j], gnew[cc], gk[j][cc]);
-          gk[6][cc] += carry[cc];   // stage 1 of the next step = this step's stage 7 (zero unless fsal)
-        }
-      }
+        store_input_operand<MODE>(tmem + lane_base, x);
+        bar_arrive<BAR_F>();
 #pragma unroll 1
-      for (int i = N - 1; i >= i0; --i) {
-        float ys[NS], gys[NS], gki[NS];
-        float tvi = 0.f, gdi = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) {
-          float a_ = 0.f;
-#pragma unroll
-          for (int j = 0; j < NSTAGE_MAX - 1; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);
-          ys[cc] = fmaf(hf, a_, y[cc]);
-          gys[cc] = 0.f;
-          gki[cc] = 0.f;
-        }
-#pragma unroll
-        for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
-          if (jj == i) {
-            tvi = tv[jj]; gdi = gdv[jj];
-#pragma unroll
-            for (int cc = 0; cc < NS; ++cc) gki[cc] = gk[jj][cc];
-          }
-        }
-        const float ci = kC[solver][i];
-        const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
-        float x[HODE_NN_IN], gx[HODE_NN_IN];
-        x[0] = (float)te;
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) x[1 + cc] = ys[cc];
-        x[7] = ys[3];
-        x[8] = tvi;
-        bc.stage_blk = stash0 + (size_t)i * stage_stride;
-        __syncwarp();
-        HODE_TL(210);
-        mlp_bwd_tile<true>(c, bc, x, gki, gx, [&] { mech_vjp(th, ys, gdi, gd_present, gki, gys, gth); });
-        HODE_TL(211);
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) gys[cc] += gx[1 + cc];
-        gys[3] += gx[7];
-#pragma unroll
-        for (int cc = 0; cc < NS; ++cc) {
-          gy[cc] += gys[cc];
-#pragma unroll
-          for (int j = 0; j < NSTAGE_MAX - 1; ++j) gk[j][cc] = fmaf(hf * kA[solver][i][j], gys[cc], gk[j][cc]);
-        }
+        for (int l = 0; l < L; ++l) put4(mnext, l, fwd_epilogue<MODE, true>(e, l, (int)(m_f & 1u)));
+        m_f += 1u;
       }
-      if (act) {
+
+      for (int it = 0; it < n_iter; ++it) {
+        HODE_TL(200);
+        const int sidx = n - 1 - it;
+        const int i_lo = item_i_lo(it, n_iter, N, i0, fsal);
+        // ---- cotangents of this step's result and stage derivatives -------------------------------------------
+        float gy[NS], gk[NSTAGE_MAX][NS];
 #pragma unroll
-        for (int cc = 0; cc < NS; ++cc) lam[cc] = gy[cc];
-      }
-      if (fsal) {
+        for (int i = 0; i < NSTAGE_MAX; ++i)
 #pragma unroll
-        for (int cc = 0; cc < NS; ++cc) carry[cc] = real ? gk[0][cc] : 0.f;
-      }
-      HODE_TL(204);
-    }
-    {
-      if (ok) {
+          for (int cc = 0; cc < NS; ++cc) gk[i][cc] = 0.f;
         if (solver == 0) {
-#pragma unroll
-          for (int cc = 0; cc < NS; ++cc) lam[cc] += gtraj[cc];
-        } else {
-          const double t0 = (double)in.t_obs[0];
-          for (; ei >= 0; --ei) {
-            if ((double)in.t_obs[ei] > t0) continue;
-            const float* g = gtraj + (size_t)ei * NS;
+          if (act && (sidx + 1) % nsub == 0) {
+            const float* g = gtraj + (size_t)((sidx + 1) / nsub) * NS;
 #pragma unroll
             for (int cc = 0; cc < NS; ++cc) lam[cc] += g[cc];
           }
-        }
-      }
-      if (G.grad_y0 && valid) {
-        float* o = G.grad_y0 + (size_t)unit * NS;
 #pragma unroll
-        for (int cc = 0; cc < NS; ++cc) o[cc] = ok ? lam[cc] : 0.f;
-      }
-    }
-  }
-
-  // ---- per-CTA partial gradients: TMEM accumulators -> workspace ---------------------------------
-  wait_gemm(bc);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  float* out = G.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(A.P + HODE_N_THETA);
-  const bool have = bc.first == 0u;   // false: this CTA processed no step, the accumulators were never written
-  const int offo = 640 + (L - 1) * 4160;
-  // M = 64 accumulators (layer 0 and the hidden layers): row j of D lives in TMEM lane 32 (j / 16) + j % 16
-  // (csrc/probe/adj_probe.cu), i.e. in the first 16 lanes of every main warp.  The loads are warp-wide.
-  if (main_role) {
-    const int j = 16 * wq + lane_id;
-    const bool owner = lane_id < 16;
-    uint32_t v[16];
-    // layer 0: D[j][k] (k < 9), column 15 = db_0[j]
-    HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_0, v);
-    tc::wait_ld();
-    if (owner) {
+          for (int cc = 0; cc < NS; ++cc) gy[cc] = act ? lam[cc] : 0.f;
 #pragma unroll
-      for (int k = 0; k < HODE_NN_IN; ++k) out[j * HODE_NN_IN + k] = have ? __uint_as_float(v[k]) : 0.f;
-      out[576 + j] = have ? __uint_as_float(v[15]) : 0.f;
-    }
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int l = 1; l < MAXL; ++l) {
-      if (l >= L) continue;
-      const int off = 640 + (l - 1) * 4160;
+            for (int cc = 0; cc < NS; ++cc) gk[j][cc] = hf * kB[0][j] * gy[cc];
+        } else {
+          float gnew[NS];
 #pragma unroll
-      for (int cidx = 0; cidx < 5; ++cidx) {
-        HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_H0 + 80u * (uint32_t)(l - 1) + 16u * (uint32_t)cidx, v);
-        tc::wait_ld();
-        if (owner) {
-          if (cidx < 4) {
+          for (int cc = 0; cc < NS; ++cc) { gnew[cc] = act ? lam[cc] : 0.f; gy[cc] = 0.f; }
+          if (act) {
+            while (ei >= 0 && (double)in.t_obs[ei] > t) {
+              const double te = (double)in.t_obs[ei];
+              const float* g = gtraj + (size_t)ei * NS;
+              if (te >= t_new) {
+                if (te == t_new) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) out[off + j * H + cidx * 16 + i] = have ? __uint_as_float(v[i]) : 0.f;
-          } else {
-            out[off + 4096 + j] = have ? __uint_as_float(v[0]) : 0.f;
+                  for (int cc = 0; cc < NS; ++cc) gnew[cc] += g[cc];
+                }
+              } else {
+                const float xq = (float)((te - t) / h);
+#pragma unroll
+                for (int cc = 0; cc < NS; ++cc) gy[cc] += g[cc];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                  const float wgt = hf * xq * fmaf(xq, fmaf(xq, fmaf(xq, kP[i][3], kP[i][2]), kP[i][1]), kP[i][0]);
+#pragma unroll
+                  for (int cc = 0; cc < NS; ++cc) gk[i][cc] = fmaf(wgt, g[cc], gk[i][cc]);
+                }
+              }
+              --ei;
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) {
+            gy[cc] += gnew[cc];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) gk[j][cc] = fmaf(hf * kB[1][j], gnew[cc], gk[j][cc]);
+            gk[6][cc] += carry[cc];   // stage 1 of the later step = this step's stage 7
           }
         }
+
+#pragma unroll 1
+        for (int i = N - 1; i >= i_lo; --i) {
+          HODE_TL(201);
+          const bool has_F = !(it == n_iter - 1 && i == i_lo);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) mcur[l] = mnext[l];
+          float ys[NS], x[HODE_NN_IN], gys[NS], gki[NS], gdi;
+          stage_x(i, ys, x, gdi);
+          if (fsal && i == N - 1 && real && later_valid) {
+            // stage 7 is evaluated at the step's result = the state the later step started from (its record), bit for bit
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) { ys[cc] = y_later[cc]; x[1 + cc] = y_later[cc]; }
+            x[7] = y_later[3];
+          }
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) { gys[cc] = 0.f; gki[cc] = 0.f; }
+#pragma unroll
+          for (int jj = 0; jj < NSTAGE_MAX; ++jj) {
+            if (jj == i) {
+#pragma unroll
+              for (int cc = 0; cc < NS; ++cc) gki[cc] = gk[jj][cc];
+            }
+          }
+          // ---- pull-back prologue: delta_L = the cotangent of the 6 network outputs -> phase L --------------------
+          {
+            float d[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = (j < NS) ? gki[j] : 0.f;
+            uint8_t* db = smem_raw + OFF_DB + (e.ph & 1u) * DB_BYTES + row * 16;
+            uint4 vh, vm;
+            bf16_split8(d, vh, vm);
+            *reinterpret_cast<uint4*>(db) = vh;
+            *reinterpret_cast<uint4*>(db + ST_PART) = vm;
+            *reinterpret_cast<uint4*>(db + ST_GRP) = make_uint4(0u, 0u, 0u, 0u);   // N = 16: features 8..15 are zero
+            *reinterpret_cast<uint4*>(db + ST_GRP + ST_PART) = make_uint4(0u, 0u, 0u, 0u);
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            bar_arrive<BAR_B>();
+            e.ph += 1u;
+          }
+          HODE_TL(202);
+          // ---- recomputation of the NEXT item: its input operand ---------------------------------------------------
+          if (has_F) {
+            float xf[HODE_NN_IN];
+            if (i > i_lo) {
+              float ysf[NS], gdf;
+              stage_x(i - 1, ysf, xf, gdf);
+            } else {
+              // top stage of the next iteration's step (one step earlier in time)
+              const int sn = sidx - 1;
+              const bool act_n = ok && (sn >= 0 || (fsal && sn == -1));
+              float ysf[NS];
+              double te;
+              if (solver == 1) {
+                // DP5(4): its stage 7 is evaluated at ITS result = the state and time this step starts from
+#pragma unroll
+                for (int cc = 0; cc < NS; ++cc) ysf[cc] = y[cc];
+                te = t;
+              } else {
+                // RK4: stage 4 at y' + h' k3', t' + h' from the prefetched record
+                tc::cp_async_wait_all();
+                const float4 c0 = rec_sh[0 * TILE + row], c1 = rec_sh[1 * TILE + row], c2 = rec_sh[2 * TILE + row];
+                const float4 c5 = rec_sh[5 * TILE + row], c6 = rec_sh[6 * TILE + row];
+                const double tp = __longlong_as_double(((long long)__float_as_int(c0.y) << 32) | (long long)(unsigned)__float_as_int(c0.x));
+                const float hp = c0.z;
+                const float yp[NS] = {c1.x, c1.y, c1.z, c1.w, c2.x, c2.y};
+                const float k3[NS] = {c5.z, c5.w, c6.x, c6.y, c6.z, c6.w};
+#pragma unroll
+                for (int cc = 0; cc < NS; ++cc) ysf[cc] = fmaf(hp, fmaf(1.0f, k3[cc], 0.f), yp[cc]);
+                te = tp + (double)hp;
+              }
+              const float t32 = (float)te;
+              float tvns, gdf;
+              inputs_at(t32, pn_t1, pn_inv, pn_v1, pn_dv, tvns, gdf);
+              xf[0] = act_n ? t32 : 0.f;
+#pragma unroll
+              for (int cc = 0; cc < NS; ++cc) xf[1 + cc] = act_n ? ysf[cc] : 0.f;
+              xf[7] = act_n ? ysf[3] : 0.f;
+              xf[8] = act_n ? tvns : 0.f;
+            }
+            __syncwarp();
+            store_input_operand<MODE>(tmem + lane_base, xf);
+            bar_arrive<BAR_F>();
+          }
+          HODE_TL(203);
+          // ---- behind the first MMA chains: the mechanistic VJP, and (once per step) the next step's input piece ----
+          mech_vjp(th, ys, gdi, gd_present, gki, gys, gth);
+          if (i == N - 2 && it + 1 < n_iter) {
+            const int sn = sidx - 1;
+            double tn = t_first;
+            if (ok && sn >= 0) {
+              tc::cp_async_wait_all();
+              const float4 c0 = rec_sh[0 * TILE + row];
+              tn = __longlong_as_double(((long long)__float_as_int(c0.y) << 32) | (long long)(unsigned)__float_as_int(c0.x));
+            }
+            piece_for(tn, pn_t1, pn_inv, pn_v1, pn_dv);
+          }
+          __syncwarp();   // reconverge after per-thread code: tcgen05 .sync.aligned instructions follow
+          HODE_TL(204);
+#pragma unroll 1
+          for (int l = 0; l < L; ++l) {
+            if (has_F) put4(mnext, l, fwd_epilogue<MODE, true>(e, l, (int)(m_f & 1u)));
+            bwd_epilogue<true>(e, L - l, sel4(mcur, L - l - 1), x);
+          }
+          // ---- final phase: g_x -----------------------------------------------------------------------------------
+          tc::mbar_wait(&bars.b_bar, e.b_cnt & 1u);
+          e.b_cnt += 1u;
+          tc::fence_after_sync();
+          HODE_TL(205);
+          {
+            uint32_t v[16];
+            HODE_TMEM_LD_X16(tmem + lane_base + TM_DB, v);
+            tc::wait_ld();
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) gys[cc] += __uint_as_float(v[1 + cc]);
+            gys[3] += __uint_as_float(v[7]);
+          }
+          if (has_F) m_f += 1u;
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) {
+            gy[cc] += gys[cc];
+#pragma unroll
+            for (int j = 0; j < NSTAGE_MAX - 1; ++j) gk[j][cc] = fmaf(hf * kA[solver][i][j], gys[cc], gk[j][cc]);
+          }
+          HODE_TL(206);
+        }
+        if (act) {
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) lam[cc] = gy[cc];
+        }
+        if (fsal) {
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) carry[cc] = real ? gk[0][cc] : 0.f;
+        }
+        if (real) {
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) y_later[cc] = y[cc];
+          t_later = t;
+          later_valid = true;
+        }
+        // ---- next iteration's context (its record was prefetched into shared memory) ------------------------------
+        if (it + 1 < n_iter) {
+          tc::cp_async_wait_all();
+          set_ctx(it + 1, [&](int c4) { return rec_sh[c4 * TILE + row]; });
+          pc_t1 = pn_t1; pc_inv = pn_inv;
+          pc_v1[0] = pn_v1[0]; pc_v1[1] = pn_v1[1]; pc_dv[0] = pn_dv[0]; pc_dv[1] = pn_dv[1];
+        }
+        HODE_TL(207);
+      }
+      {
+        if (ok) {
+          if (solver == 0) {
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) lam[cc] += gtraj[cc];
+          } else {
+            for (; ei >= 0; --ei) {
+              if ((double)in.t_obs[ei] > t_first) continue;
+              const float* g = gtraj + (size_t)ei * NS;
+#pragma unroll
+              for (int cc = 0; cc < NS; ++cc) lam[cc] += g[cc];
+            }
+          }
+        }
+        if (G.grad_y0 && valid) {
+          float* o = G.grad_y0 + (size_t)unit * NS;
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) o[cc] = ok ? lam[cc] : 0.f;
+        }
       }
     }
-  }
-  // output layer (transposed, M = 128: lane = row): D[k][n] = dW_out[n][k] for the input features k < 64
-  if (main_role && wq < 2) {
-    const int j = row;
-    uint32_t v[16];
-    HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
-    tc::wait_ld();
+
+    // ---- per-CTA partial gradients: TMEM accumulators -> workspace ---------------------------------
+    tc::mbar_wait(&bars.done, 0u);
+    tc::fence_after_sync();
+    float* out = G.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(A.P + HODE_N_THETA);
+    const int offo = 640 + (L - 1) * 4160;
+    // M = 64 accumulators (layer 0 and the hidden layers): row j of D lives in TMEM lane 32 (j / 16) + j % 16
+    // (csrc/probe/adj_probe.cu), i.e. in the first 16 lanes of every main warp.  The loads are warp-wide.
+    {
+      const int j = 16 * wq + lane_id;
+      const bool owner = lane_id < 16;
+      uint32_t v[16];
+      // layer 0: D[j][k] (k < 9), column 15 = db_0[j]
+      HODE_TMEM_LD_X16(tmem + lane_base + DW_0, v);
+      tc::wait_ld();
+      if (owner) {
 #pragma unroll
-    for (int nn = 0; nn < NS; ++nn) out[offo + nn * H + j] = have ? __uint_as_float(v[nn]) : 0.f;
-  }
-  if (main_role && wq == 2) {   // TMEM lane 64: the constant-1 input feature -> db_out (warp-wide load)
-    uint32_t v[16];
-    HODE_TMEM_LD_X16(c.tmem + c.lane_base + DW_O, v);
-    tc::wait_ld();
-    if (lane_id == 0) {
+        for (int kk = 0; kk < HODE_NN_IN; ++kk) out[j * HODE_NN_IN + kk] = have ? __uint_as_float(v[kk]) : 0.f;
+        out[576 + j] = have ? __uint_as_float(v[15]) : 0.f;
+      }
 #pragma unroll
-      for (int nn = 0; nn < NS; ++nn) out[offo + 384 + nn] = have ? __uint_as_float(v[nn]) : 0.f;
+      for (int l = 1; l < MAXL; ++l) {
+        if (l >= L) continue;
+        const int off = 640 + (l - 1) * 4160;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          HODE_TMEM_LD_X16(tmem + lane_base + DW_H0 + DW_HS * (uint32_t)(l - 1) + 16u * (uint32_t)cidx, v);
+          tc::wait_ld();
+          if (owner) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) out[off + j * H + cidx * 16 + i] = have ? __uint_as_float(v[i]) : 0.f;
+          }
+        }
+        uint32_t v8[8];
+        HODE_TMEM_LD_X8(tmem + lane_base + DW_H0 + DW_HS * (uint32_t)(l - 1) + 64u, v8);
+        tc::wait_ld();
+        if (owner) out[off + 4096 + j] = have ? __uint_as_float(v8[0]) : 0.f;
+      }
     }
-  }
-  if (main_role) {
-    // deterministic reduction of the theta gradients over the 128 trajectory slots
+    // output layer (transposed, M = 128: lane = row): D[k][n] = dW_out[n][k] for the input features k < 64
+    if (wq < 2) {
+      const int j = row;
+      uint32_t v[16];
+      HODE_TMEM_LD_X16(tmem + lane_base + DW_O, v);
+      tc::wait_ld();
+#pragma unroll
+      for (int nn = 0; nn < NS; ++nn) out[offo + nn * H + j] = have ? __uint_as_float(v[nn]) : 0.f;
+    }
+    if (wq == 2) {   // TMEM lane 64: the constant-1 input feature -> db_out (warp-wide load)
+      uint32_t v[16];
+      HODE_TMEM_LD_X16(tmem + lane_base + DW_O, v);
+      tc::wait_ld();
+      if (lane_id == 0) {
+#pragma unroll
+        for (int nn = 0; nn < NS; ++nn) out[offo + 384 + nn] = have ? __uint_as_float(v[nn]) : 0.f;
+      }
+    }
+    // deterministic reduction of the theta gradients over the 128 trajectory slots (the operand buffers are dead:
+    // every MMA has completed)
+    float* red = reinterpret_cast<float*>(smem_raw);
 #pragma unroll
     for (int i = 0; i < HODE_N_THETA; ++i) red[i * TILE + row] = gth[i];
-  }
-  __syncthreads();
-  if (main_role && row < HODE_N_THETA) {
-    float sacc = 0.f;
-    for (int r = 0; r < TILE; ++r) sacc += red[row * TILE + r];
-    out[A.P + row] = sacc;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (row < HODE_N_THETA) {
+      float sacc = 0.f;
+      for (int r = 0; r < TILE; ++r) sacc += red[row * TILE + r];
+      out[A.P + row] = sacc;
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
-  }
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
 // ---- transposed weight image --------------------------------------------------------------------------
@@ -1137,6 +1228,7 @@ __global__ void __launch_bounds__(256) adj_schedule_kernel(const uint32_t* __res
 bool adj_tc_supported(int H_, int L_) { return H_ == 64 && L_ >= 1 && L_ <= MAXL; }
 
 AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
+  // (the plan does not depend on the MLP arithmetic: both split-precision images have the same size)
   AdjTcPlan p{};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -1152,13 +1244,11 @@ AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj) {
   p.n_tiles = (int)(blocks > 0 ? blocks : 1);
   p.fwd_floats = tc_image_floats(L);
   p.bwd_floats = tc_bwd_image_floats(L);
-  const int bwd_cap = BWD_BYTES / 4;
-  size_t floats = (size_t)(((p.fwd_floats > bwd_cap ? p.fwd_floats : bwd_cap) + 255) & ~255);
-  floats += TILE * HODE_REC_FLOATS;
-  if (!t_per_traj && T <= HODE_SIMT_MAX_SHARED_T) floats += T;
-  p.smem = (floats * sizeof(float) + 1023) & ~(size_t)1023;
+  p.t_in_smem = (!t_per_traj && ADJ_SMEM_BASE + 4 * T <= ADJ_SMEM_MAX) ? 1 : 0;
+  p.smem = (size_t)ADJ_SMEM_BASE + (p.t_in_smem ? (size_t)4 * T : 0);
   p.partial_floats = (size_t)gx * S * (size_t)(P + HODE_N_THETA);
-  p.stash_floats = (size_t)gx * S * (size_t)NSTAGE_MAX * L * (ST_BLK / 4);
+  // activation scratch: per CTA two sets (the item being recomputed / the item being pulled back) of L operand images
+  p.stash_floats = (size_t)gx * S * (size_t)2 * L * (ST_BLK / 4);
   p.img_floats = (size_t)S * (p.fwd_floats + p.bwd_floats);
   // schedule scratch: sort keys / values (in, out), tile owners, per-CTA tile lists, cub temporaries
   const size_t units = (size_t)S * (size_t)(B > 0 ? B : 0);
@@ -1176,8 +1266,9 @@ size_t adj_tc_workspace_bytes(const AdjTcPlan& p) {
          ((p.sort_bytes + 255) & ~(size_t)255);
 }
 
-cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, float* grad_y0,
+cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const float* grad_traj, float* grad_y0,
                                   float* grad_theta, float* grad_W, void* workspace, cudaStream_t stream) {
+  if (A.rec_floats < HODE_REC_FLOATS_K || !A.save_k1) return cudaErrorInvalidValue;   // needs the stage derivatives
   const AdjTcPlan p = adj_tc_plan(A.B, A.S, A.L, A.P, A.T, A.t_per_traj);
   if (p.smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
@@ -1186,8 +1277,9 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, 
   G.grad_traj = grad_traj;
   G.grad_y0 = grad_y0;
   G.partials = reinterpret_cast<float*>(workspace);
-  G.stash = G.partials + al(p.partial_floats);
-  float* imgs = G.stash + al(p.stash_floats);
+  G.stash = reinterpret_cast<uint8_t*>(G.partials + al(p.partial_floats));
+  float* imgs = G.partials + al(p.partial_floats) + al(p.stash_floats);
+  G.t_in_smem = p.t_in_smem;
   G.img_fwd = imgs;
   G.img_bwd = imgs + (size_t)A.S * p.fwd_floats;
   G.fwd_floats = p.fwd_floats;
@@ -1206,7 +1298,10 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, 
   G.sched_off = sched_off;
   G.sched_tiles = sched_tiles;
   G.n_tiles = p.n_tiles;
-  cudaError_t e = tc_prepare_fwd_images(A.W, imgs, A.S, A.L, A.P, stream);
+  // the recomputation uses the rollout's arithmetic (its activations are then the forward pass's, bit for bit); a
+  // single-pass TF32 rollout is differentiated with the 3xTF32 recomputation
+  const int fwd_mode = mlp_mode == HODE_MLP_TF32BF16 ? HODE_MLP_TF32BF16 : HODE_MLP_TF32X3;
+  cudaError_t e = tc_prepare_fwd_images(A.W, imgs, A.S, A.L, A.P, fwd_mode, stream);
   if (e != cudaSuccess) return e;
   prep_tc_bwd_image_kernel<<<A.S, 256, 0, stream>>>(A.W, imgs + (size_t)A.S * p.fwd_floats, A.L, A.P, p.bwd_floats);
   e = cudaGetLastError();
@@ -1236,9 +1331,15 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, 
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  e = cudaFuncSetAttribute(rollout_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e != cudaSuccess) return e;
-  rollout_bwd_tc_kernel<<<dim3(p.grid_x, p.grid_y), 3 * TILE, p.smem, stream>>>(G);
+  if (fwd_mode == HODE_MLP_TF32BF16) {
+    e = cudaFuncSetAttribute(rollout_bwd_tc_kernel<MLP_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    rollout_bwd_tc_kernel<MLP_MIXED><<<dim3(p.grid_x, p.grid_y), 3 * TILE, p.smem, stream>>>(G);
+  } else {
+    e = cudaFuncSetAttribute(rollout_bwd_tc_kernel<MLP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    rollout_bwd_tc_kernel<MLP_X3><<<dim3(p.grid_x, p.grid_y), 3 * TILE, p.smem, stream>>>(G);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_reduce_partials(G.partials, p.grid_x, A.S, A.P, grad_W, grad_theta, stream);

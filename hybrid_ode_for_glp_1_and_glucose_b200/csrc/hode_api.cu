@@ -31,7 +31,7 @@ struct Workspace {
 };
 
 bool uses_tensor_cores(const hode_cfg* c) {
-  return c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32;
+  return c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32 || c->mlp == HODE_MLP_TF32BF16;
 }
 
 int max_saved_steps(const hode_cfg* c) {
@@ -39,8 +39,19 @@ int max_saved_steps(const hode_cfg* c) {
     const int nsub = c->n_substeps > 0 ? c->n_substeps : 1;
     return (c->n_obs - 1) * nsub;
   }
-  return c->max_saved_steps > 0 ? c->max_saved_steps : 256;
+  if (c->max_saved_steps > 0) return c->max_saved_steps;
+  // default: derived from the problem.  With kink clipping a series input that changes at every grid point
+  // forces at least T - 1 accepted steps; 2 (T - 1) leaves room for the controller's own steps in between.
+  const int by_grid = 2 * (c->n_obs - 1);
+  return by_grid > 128 ? by_grid : 128;
 }
+
+bool adjoint_on_tensor_cores(const hode_cfg* c) {
+  return uses_tensor_cores(c) && hode::adj_tc_supported(c->nn_hidden, c->nn_layers);
+}
+
+// floats per accepted-step record: the tensor-core adjoint reads the stage derivatives from the record
+int rec_floats(const hode_cfg* c) { return adjoint_on_tensor_cores(c) ? hode::HODE_REC_FLOATS_K : hode::HODE_REC_FLOATS; }
 
 Workspace fwd_workspace(const hode_cfg* c) {
   Workspace w{};
@@ -49,8 +60,8 @@ Workspace fwd_workspace(const hode_cfg* c) {
   size_t off = 0;
   if (c->save_steps) {
     w.off_n = off; off = align_up(off + units * sizeof(int32_t), 256);
-    // one 64-byte record per (unit, step): t, h, y[6], k1[6] (hode_common.cuh step_rec)
-    w.off_rec = off; off = align_up(off + units * w.max_saved * 64, 256);
+    // one record per (unit, step): t, h, y[6], k1[6] (+ k2..k6 for the tensor-core adjoint), hode_common.cuh step_rec
+    w.off_rec = off; off = align_up(off + units * w.max_saved * (size_t)rec_floats(c) * sizeof(float), 256);
   }
   if (uses_tensor_cores(c)) {
     // pre-split weight images (one per parameter set) + the per-set trajectory queue counters
@@ -72,15 +83,15 @@ int validate(const hode_cfg* c) {
       return fail(HODE_E_SHAPE, "in_mode out of range");
   if (c->solver != HODE_SOLVER_RK4 && c->solver != HODE_SOLVER_DOPRI5)
     return fail(HODE_E_UNSUPPORTED, "unknown solver");
-  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_TF32)
+  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_TF32BF16)
     return fail(HODE_E_UNSUPPORTED, "unknown mlp arithmetic");
   if (c->mlp != HODE_MLP_NONE) {
     if (c->nn_hidden < 1 || c->nn_hidden > HODE_MAX_HIDDEN || c->nn_layers < 1 ||
         c->nn_layers > HODE_MAX_LAYERS)
       return fail(HODE_E_UNSUPPORTED, "nn_hidden must be in [1,128] and nn_layers in [1,8]");
-    if ((c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32) &&
-        (c->nn_hidden != 64 || c->nn_layers > 7))
-      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 7");
+    if (uses_tensor_cores(c) && (c->nn_hidden != 64 || c->nn_layers > 6))
+      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 6 (the weight image of "
+                                      "deeper networks does not fit the 227 KB of shared memory)");
   }
   if (c->solver == HODE_SOLVER_DOPRI5 && (!(c->rtol > 0) || !(c->atol >= 0)))
     return fail(HODE_E_SIZE, "rtol must be > 0 and atol >= 0");
@@ -141,8 +152,16 @@ static hode::AdjPlan bwd_plan(const hode_cfg* c) {
                         P, has_nn, c->n_obs, c->t_per_traj, 7);
 }
 
-static bool bwd_uses_tensor_cores(const hode_cfg* c) {
-  return uses_tensor_cores(c) && hode::adj_tc_supported(c->nn_hidden, c->nn_layers);
+static bool bwd_uses_tensor_cores(const hode_cfg* c) { return adjoint_on_tensor_cores(c); }
+
+int32_t hode_step_record_floats(const hode_cfg* cfg) {
+  if (validate(cfg) || !cfg->save_steps) return 0;
+  return rec_floats(cfg);
+}
+
+int32_t hode_step_record_capacity(const hode_cfg* cfg) {
+  if (validate(cfg) || !cfg->save_steps) return 0;
+  return max_saved_steps(cfg);
 }
 
 static hode::AdjTcPlan bwd_tc_plan(const hode_cfg* c) {
@@ -187,7 +206,8 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
     char* base = (char*)workspace;
     A.save_n = (int32_t*)(base + w.off_n);
     A.save_rec = (float*)(base + w.off_rec);
-    A.save_k1 = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? 1 : 0;   // the tensor-core adjoint reuses k1 (FSAL)
+    A.save_k1 = uses_tensor_cores(cfg) ? 1 : 0;   // the tensor-core rollout records its stage derivatives
+    A.rec_floats = rec_floats(cfg);
     A.max_saved = w.max_saved;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -230,10 +250,11 @@ int hode_rollout_bwd(const hode_cfg* cfg, const float* y0, const float* t_obs, c
   char* base = (char*)fwd_workspace_ptr;
   A.save_n = (int32_t*)(base + w.off_n);
   A.save_rec = (float*)(base + w.off_rec);
-  A.save_k1 = (uses_tensor_cores(cfg) && cfg->solver != HODE_SOLVER_RK4) ? 1 : 0;
+  A.save_k1 = uses_tensor_cores(cfg) ? 1 : 0;
+  A.rec_floats = rec_floats(cfg);
   A.max_saved = w.max_saved;
   // forward on the tensor cores -> adjoint on the tensor cores (3xTF32); FP32 forward -> FP32 adjoint
-  cudaError_t e = tc_adj ? hode::launch_rollout_bwd_tc(A, grad_traj, grad_y0, grad_theta, grad_W, bwd_workspace,
+  cudaError_t e = tc_adj ? hode::launch_rollout_bwd_tc(A, cfg->mlp, grad_traj, grad_y0, grad_theta, grad_W, bwd_workspace,
                                                        (cudaStream_t)stream)
                          : hode::launch_rollout_bwd(A, cfg->mlp != HODE_MLP_NONE, grad_traj, grad_y0, grad_theta,
                                                     grad_W, bwd_workspace, (cudaStream_t)stream);
@@ -328,7 +349,11 @@ int hode_loss_fused_fwd_bwd(const hode_cfg* cfg, const float* y0, const float* t
     return fail(HODE_E_WORKSPACE, "backward workspace missing or too small");
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg->n_traj == 0) {
+    // no trajectories: the loss and every gradient are zero (grad_y0 has no rows)
     cudaError_t e = cudaMemsetAsync(loss, 0, (size_t)S * sizeof(float), st);
+    if (e == cudaSuccess && grad_theta) e = cudaMemsetAsync(grad_theta, 0, (size_t)S * HODE_N_THETA * sizeof(float), st);
+    if (e == cudaSuccess && grad_W && cfg->mlp != HODE_MLP_NONE)
+      e = cudaMemsetAsync(grad_W, 0, (size_t)S * (size_t)hode_mlp_param_count(cfg->nn_hidden, cfg->nn_layers) * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "hode_loss_fused_fwd_bwd memset");
     return 0;
   }

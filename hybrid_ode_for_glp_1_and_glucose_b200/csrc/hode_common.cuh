@@ -24,11 +24,15 @@ struct RolloutArgs {
   float* traj;          // [S,B,T,6] (or nullptr in fused-statistics mode)
   int32_t* status;      // [S,B] or nullptr
   int32_t* counters;    // [2,S,B] or nullptr
-  // saved accepted steps (discrete adjoint): one 64-byte record per (unit, step), unit-major
-  // [S*B][max_saved][16 floats] = { t (f64), h, pad, y[6], k1[6] } — a trajectory's steps are contiguous
-  // (the adjoint walks them backwards: one TLB entry and 2 sectors per step instead of 14 of each)
+  // saved accepted steps (discrete adjoint): one record of rec_floats floats per (unit, step), unit-major
+  // [S*B][max_saved][rec_floats] — a trajectory's steps are contiguous (the adjoint walks them backwards).
+  //   rec_floats = 16: { t (f64), h, pad, y[6], k1[6] }                       (FP32 adjoint: recomputes the stages)
+  //   rec_floats = 48: the same + the stage derivatives k2..k6 (DP5(4)) / k2, k3 (RK4) at floats 16.. :
+  //                    the tensor-core adjoint then evaluates every stage INPUT directly from the record, so the
+  //                    stages of a step can be recomputed one at a time, in reverse, next to their own pull-back
   float* save_rec;
-  int32_t save_k1;      // records carry k1, the step's first stage derivative (tensor-core DP5(4) rollout)
+  int32_t rec_floats;
+  int32_t save_k1;      // records carry the stage derivatives (tensor-core rollout)
   int32_t* save_n;      // [S*B] number of saved steps
   int32_t max_saved;
   int32_t B, T, S;
@@ -55,9 +59,10 @@ struct RolloutArgs {
 };
 
 // ---- step records ---------------------------------------------------------------------------------------
-constexpr int HODE_REC_FLOATS = 16;
+constexpr int HODE_REC_FLOATS = 16;        // base record (and the FP32 path's whole record)
+constexpr int HODE_REC_FLOATS_K = 48;      // with the stage derivatives k2..k6 (tensor-core path)
 __device__ __forceinline__ float* step_rec(const RolloutArgs& A, long unit, int step) {
-  return A.save_rec + ((size_t)unit * A.max_saved + step) * HODE_REC_FLOATS;
+  return A.save_rec + ((size_t)unit * A.max_saved + step) * A.rec_floats;
 }
 __device__ __forceinline__ void step_rec_store(float* r, double t, float h, const float* y, const float* k1) {
   float4* r4 = reinterpret_cast<float4*>(r);
@@ -70,6 +75,18 @@ __device__ __forceinline__ void step_rec_store(float* r, double t, float h, cons
   } else {
     r4[2] = make_float4(y[4], y[5], 0.f, 0.f);
   }
+}
+// stage derivatives k2..k(1+n_extra) -> floats 16.. of a 48-float record (k_j component c at float 10 + 6 (j-1) + c)
+__device__ __forceinline__ void step_rec_store_stages(float* r, const float (*k)[NS], int n_extra) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int c = 0; c < NS; ++c) v[6 * j + c] = (j < n_extra) ? k[1 + j][c] : 0.f;
+  v[30] = 0.f; v[31] = 0.f;
+  float4* r4 = reinterpret_cast<float4*>(r) + 4;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) r4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 __device__ __forceinline__ double step_rec_t(const float* r) { return *reinterpret_cast<const double*>(r); }
 __device__ __forceinline__ void step_rec_load(const float* r, double& t, float& h, float* y, float* k1) {

@@ -40,9 +40,9 @@ cudaError_t launch_reduce_partials(const float* partials, int ctas_per_set, int 
 // tensor-core discrete adjoint (hode_adjoint_tc.cu)
 int tc_image_floats(int L);
 int tc_bwd_image_floats(int L);
-cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, cudaStream_t stream);
+cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, int mlp_mode, cudaStream_t stream);
 struct AdjTcPlan {
-  int grid_x, grid_y, fwd_floats, bwd_floats, n_tiles;
+  int grid_x, grid_y, fwd_floats, bwd_floats, n_tiles, t_in_smem;
   size_t smem, partial_floats, stash_floats, img_floats;
   size_t sched_ints;   // sort keys / values, tile owners and per-CTA tile lists (int32 words)
   size_t sort_bytes;   // cub::DeviceRadixSort temporaries
@@ -50,7 +50,7 @@ struct AdjTcPlan {
 bool adj_tc_supported(int H, int L);
 AdjTcPlan adj_tc_plan(int B, int S, int L, int P, int T, int t_per_traj);
 size_t adj_tc_workspace_bytes(const AdjTcPlan& p);
-cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, const float* grad_traj, float* grad_y0,
+cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const float* grad_traj, float* grad_y0,
                                   float* grad_theta, float* grad_W, void* workspace, cudaStream_t stream);
 
 // on-device cohort generation (hode_gen4gi.cu)

@@ -398,7 +398,7 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
             step_rec_store(step_rec(A, unit, n_saved), t, hf, y, nullptr);
             ++n_saved;
           } else {
-            status = HODE_ST_MAX_STEPS;
+            status = HODE_ST_REC_OVERFLOW;
             break;
           }
         }

@@ -8,11 +8,14 @@
 // cores.  Replaces reference models/hybrid_ode_nn.py:184-256 + models/nn_residual.py:136-146.
 //
 // CTA = 2 tiles x 128 threads (persistent, one CTA per SM).  Per tile, TMEM columns:
-//   [0,64) accumulator D | [64,128) A_hi | [128,192) A_lo | [192,200) constant [1,1,0..] (bias step)
-// Per layer:  epilogue threads read D (tcgen05.ld), add bias, ReLU, split into TF32 hi/lo
-// (round-to-nearest) and write the next layer's A operand straight back to TMEM
-// (tcgen05.st); one elected thread issues  D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32,
-// fp32-equivalent accuracy; single pass in HODE_MLP_TF32 mode) with B = pre-split weights in
+//   [0,64) accumulator D | [64,128) A_hi (TF32) | [128,160) bf16(A_hi) | [160,192) bf16(A - A_hi) |
+//   [192,200) constant [1,1,0..] (bias step)
+// Per layer:  epilogue threads read D (tcgen05.ld; the bias is already in it), ReLU, split into a TF32
+// high part and the BF16 operands of the two cross terms, and write the next layer's A operand straight
+// back to TMEM (tcgen05.st); one elected thread issues
+//   D = bias + bf16(A_lo)*bf16(B_hi) + bf16(A_hi)*bf16(B_lo) + A_hi*B_hi
+// (one kind::tf32 pass + two kind::f16 BF16 passes at twice its rate: fp32-equivalent accuracy for 2
+// pass-equivalents, hode_tc_mlp.cuh; single TF32 pass in HODE_MLP_TF32 mode) with B = pre-split weights in
 // shared memory (K-major, no swizzle), then tcgen05.commit -> mbarrier.  The two tiles of a
 // CTA run out of phase, so one tile's epilogue overlaps the other tile's MMAs.
 // Weights are staged once per (CTA, parameter set) with one bulk async copy (TMA engine) of a
@@ -33,16 +36,19 @@ constexpr int TILES_PER_CTA = 2;
 }  // namespace
 
 // ---- weight image ----------------------------------------------------------------------------------
-// floats: [L0: Bhi 4x64x4, Blo][hidden l=1..L-1: Bhi 16x64x4, Blo][out: Bhi 16x16x4, Blo]
-//         [bias blocks: L x (2x64x4)][bias block out: 2x16x4]
-// B chunk-major: element (n, k) of an [N, K] weight at float ((k/4)*N + n)*4 + k%4.
-// A bias block is one K = 8 step whose columns 0/1 hold the TF32 hi/lo parts of the bias; it
-// multiplies a constant A block [1, 1, 0, ...] kept in TMEM, so the bias rides on the tensor
-// pipe instead of costing one FADD per accumulator element in the epilogue.
+// Per layer (hode_tc_mlp.cuh IMG_*): [B_hi: TF32 rounding of W, fp32 words][second half], K-major without swizzle.
+// Element (n, k) of an [N, K] weight:
+//   TF32 parts at float  ((k / 4) * N + n) * 4 + k % 4         (16-byte K chunks of 4 floats)
+//   BF16 parts at 2-byte ((k / 8) * N + n) * 8 + k % 8         (16-byte K chunks of 8 halves)
+// second half: 3xTF32 -> B_lo = TF32 of (W - B_hi); mixed -> bf16(B_hi) then bf16(W - B_hi).
+// Layer 0 is K = 16: the 9 input features, then feature 9 = the constant 1 whose weight column is the layer's
+// bias, then zero padding.  The other layers get a bias block: one K = 8 TF32 step whose columns 0/1 hold the
+// TF32 hi/lo parts of the bias; it multiplies a constant A block [1, 1, 0, ...] kept in TMEM, so the bias rides
+// on the tensor pipe instead of costing one FADD per accumulator element in the epilogue.
 int tc_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024 + L * 512 + 128; }
 
 __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
-                                     int img_floats) {
+                                     int img_floats, int mixed) {
   const float* w = W + (size_t)blockIdx.x * P;
   float* out = img + (size_t)blockIdx.x * img_floats;
   for (int i = threadIdx.x; i < img_floats; i += blockDim.x) out[i] = 0.f;
@@ -54,20 +60,32 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
     const int n_out = (l == L) ? NS : H;
     const int Npad = (l == L) ? 16 : H;
     const int Kpad = (l == 0) ? 16 : H;
-    const int part = (Kpad / 4) * Npad * 4;
-    for (int i = threadIdx.x; i < n_out * n_in; i += blockDim.x) {
-      const int n = i / n_in, k = i - n * n_in;
+    const int part = Kpad * Npad;   // floats of each half
+    uint16_t* hib = reinterpret_cast<uint16_t*>(dst + part);
+    uint16_t* lob = reinterpret_cast<uint16_t*>(dst + part + part / 2);
+    const int n_cols = n_in + (l == 0 ? 1 : 0);   // layer 0: column n_in is the bias
+    for (int i = threadIdx.x; i < n_out * n_cols; i += blockDim.x) {
+      const int n = i / n_cols, k = i - n * n_cols;
+      const float wv = (k < n_in) ? w[n * n_in + k] : w[n_out * n_in + n];
       uint32_t hi, lo;
-      tc::split_tf32(w[i], hi, lo);
+      tc::split_tf32(wv, hi, lo);
       const int o = ((k >> 2) * Npad + n) * 4 + (k & 3);
       dst[o] = __uint_as_float(hi);
-      dst[part + o] = __uint_as_float(lo);
+      if (mixed) {
+        const int ob = ((k >> 3) * Npad + n) * 8 + (k & 7);
+        hib[ob] = (uint16_t)(pack_bf16x2(__uint_as_float(hi), 0.f) & 0xFFFFu);
+        lob[ob] = (uint16_t)(pack_bf16x2(wv - __uint_as_float(hi), 0.f) & 0xFFFFu);
+      } else {
+        dst[part + o] = __uint_as_float(lo);
+      }
     }
-    for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
-      uint32_t hi, lo;
-      tc::split_tf32(w[n_out * n_in + j], hi, lo);
-      bias_dst[j * 4 + 0] = __uint_as_float(hi);   // (n = j, k = 0)
-      bias_dst[j * 4 + 1] = __uint_as_float(lo);   // (n = j, k = 1)
+    if (l > 0) {
+      for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+        uint32_t hi, lo;
+        tc::split_tf32(w[n_out * n_in + j], hi, lo);
+        bias_dst[j * 4 + 0] = __uint_as_float(hi);   // (n = j, k = 0)
+        bias_dst[j * 4 + 1] = __uint_as_float(lo);   // (n = j, k = 1)
+      }
     }
     w += n_out * n_in + n_out;
     dst += 2 * part;
@@ -76,8 +94,8 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
   }
 }
 
-cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, cudaStream_t stream) {
-  prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats(L));
+cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, int mlp_mode, cudaStream_t stream) {
+  prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats(L), mlp_mode == HODE_MLP_TF32BF16 ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -146,7 +164,7 @@ __device__ __forceinline__ void rhs_mech_fast(const Theta& p, const float* y, fl
 }
 
 // One evaluation of f_physio + g_NN for this lane (tile-collective).
-template <bool X3>
+template <int X3>
 __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln, double te,
                                           const float* ys, float* d) {
   const float t32 = (float)te;
@@ -173,8 +191,7 @@ __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln,
   x[7] = ys[3];
   x[8] = tvns;
   __syncwarp();
-  mlp_tile<X3>(c, x, r, nullptr, 0,
-               [&] { rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d); });
+  mlp_tile<X3>(c, x, r, [&] { rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d); });
 #pragma unroll
   for (int i = 0; i < NS; ++i) d[i] = __fadd_rn(d[i], r[i]);
 }
@@ -237,9 +254,14 @@ __device__ __forceinline__ void lane_finish(Lane& ln, const RolloutArgs& A, int 
   ln.unit = -1;
 }
 
-// k1: the step's first stage derivative (DP5(4): the adjoint reuses it instead of recomputing it — FSAL)
-__device__ __forceinline__ void lane_save_step(Lane& ln, const RolloutArgs& A, double t, float hf, const float* k1 = nullptr) {
-  step_rec_store(step_rec(A, ln.unit, ln.n_saved), t, hf, ln.y, A.save_k1 ? k1 : nullptr);
+// The step's record: start time, size, start state and — for the tensor-core adjoint — its stage derivatives
+// k1 .. k(1 + n_extra) (DP5(4): k1..k6; RK4: k1..k3): with them every stage INPUT of the step is a linear
+// combination the adjoint evaluates directly, so it recomputes the stages one at a time, in reverse order.
+__device__ __forceinline__ void lane_save_step(Lane& ln, const RolloutArgs& A, double t, float hf, const float (*k)[NS],
+                                               int n_extra) {
+  float* r = step_rec(A, ln.unit, ln.n_saved);
+  step_rec_store(r, t, hf, ln.y, A.save_k1 ? k[0] : nullptr);
+  if (A.rec_floats >= HODE_REC_FLOATS_K) step_rec_store_stages(r, k, n_extra);
   ++ln.n_saved;
 }
 
@@ -269,7 +291,7 @@ __device__ __forceinline__ unsigned long long build_kink_mask(const TrajInputs& 
 // of the tile; the evaluations of a round go through ONE call site of the tile MLP (slot loop),
 // which keeps the kernel small enough for the instruction cache.
 // ---------------------------------------------------------------------------------------------------
-template <bool X3, int SOLVER>
+template <int X3, int SOLVER>
 __global__ void __launch_bounds__(2 * TILE* TILES_PER_CTA, 1)
 rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_floats, int* queue) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -444,8 +466,12 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
                   emit_row(A, ln.out, ln.b, 0, ln.y, vi_n);
                   ln.ei = 1;
                   if (T < 2) lane_finish(ln, A, vi_n);
-                } else if (clip && T <= 64 && any_series(ln.in)) {
-                  kink_mask = A.kink_masks ? A.kink_masks[ln.b] : build_kink_mask(ln.in);
+                } else {
+                  if (clip && T <= 64 && any_series(ln.in))
+                    kink_mask = A.kink_masks ? A.kink_masks[ln.b] : build_kink_mask(ln.in);
+                  // the two evaluations of select_initial_step (at t0 and t0 + h0) read the inputs through the
+                  // cached piece: load the first grid interval now (the first real attempt reloads it)
+                  if (ln.cached && any_series(ln.in) && T >= 2) lane_cache_inputs(ln, 0);
                 }
               } else {
                 queue_dry = true;
@@ -484,7 +510,6 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             hf = (float)h;
             ln.in.cur = rk_n;
             if (rk_ss == 0 && any_series(ln.in)) lane_cache_inputs(ln, rk_n);
-            if (A.save_n && ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf);
           }
         } else if (run) {
           if (need_stop) {
@@ -643,6 +668,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         // ---- close the round ----------------------------------------------------------------------------
         if (SOLVER == HODE_SOLVER_RK4) {
           if (run) {
+            if (A.save_n && ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf, k, 2);
   #pragma unroll
             for (int i = 0; i < NS; ++i) {
               const float inc = (hf * (1.0f / 6.0f)) * (k[0][i] + 2.0f * k[1][i] + 2.0f * k[2][i] + k[3][i]);
@@ -685,8 +711,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             ++ln.n_acc;
             bool ok = true;
             if (A.save_n) {
-              if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf, k[0]);
-              else { ln.status = HODE_ST_MAX_STEPS; ok = false; }
+              if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf, k, 5);
+              else { ln.status = HODE_ST_REC_OVERFLOW; ok = false; }
             }
             if (ok) {
               if (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
@@ -794,8 +820,7 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
     if (e != cudaSuccess) return e;
     A.kink_masks = masks;
   }
-  prep_tc_image_kernel<<<A.S, 256, 0, stream>>>(A.W, img, A.L, A.P, img_floats);
-  e = cudaGetLastError();
+  e = tc_prepare_fwd_images(A.W, img, A.S, A.L, A.P, mlp_mode, stream);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -814,11 +839,13 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
     kern<<<grid, 2 * TILE * TILES_PER_CTA, smem, stream>>>(A, img, img_floats, queue);
     return cudaSuccess;
   };
-  const bool x3 = (mlp_mode == HODE_MLP_TF32X3);
-  if (A.solver == HODE_SOLVER_RK4)
-    e = x3 ? launch(rollout_tc_kernel<true, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<false, HODE_SOLVER_RK4>);
+  const bool rk4 = A.solver == HODE_SOLVER_RK4;
+  if (mlp_mode == HODE_MLP_TF32X3)
+    e = rk4 ? launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_DOPRI5>);
+  else if (mlp_mode == HODE_MLP_TF32BF16)
+    e = rk4 ? launch(rollout_tc_kernel<MLP_MIXED, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_MIXED, HODE_SOLVER_DOPRI5>);
   else
-    e = x3 ? launch(rollout_tc_kernel<true, HODE_SOLVER_DOPRI5>) : launch(rollout_tc_kernel<false, HODE_SOLVER_DOPRI5>);
+    e = rk4 ? launch(rollout_tc_kernel<MLP_TF32, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_TF32, HODE_SOLVER_DOPRI5>);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }

@@ -26,18 +26,35 @@ __device__ int g_tl_n;
 namespace {
 constexpr int TILE = 128;
 constexpr int H = 64;
+// Arithmetic of the tile MLP (template parameter MODE; `true` / `false` of older call sites = 3xTF32 / TF32):
+//   MLP_TF32   one kind::tf32 pass (~1e-3 on the residual: "fast" mode, never the default)
+//   MLP_X3     3xTF32: D = A_lo B_hi + A_hi B_lo + A_hi B_hi, three kind::tf32 passes (the default: max error
+//              1.7e-7 of sum|a b|, better than an FP32 FMA chain)
+//   MLP_MIXED  D = bf16(A_lo) bf16(B_hi) + bf16(A_hi) bf16(B_lo) + A_hi B_hi: one kind::tf32 pass + two
+//              kind::f16 BF16 passes at twice its rate = 2 pass-equivalents (opt-in: max error 4.5e-7 of
+//              sum|a b|, 2x an FP32 FMA chain — csrc/probe/mix_probe.cu)
+constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2;
 // TMEM columns of one tile:
-//   [0,64) accumulator D | [64,128) A_hi | [128,192) A_lo | [192,200) constant [1,1,0..] (bias step)
-constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_ONES = 192, TM_TILE_STRIDE = 256;
+//   [0,64) accumulator D | [64,128) A_hi (TF32) | [192,200) constant [1,1,0..] (bias step) |
+//   MLP_X3:    [128,192) A_lo = A - A_hi (TF32)
+//   MLP_MIXED: [128,160) bf16(A_hi), two features per column | [160,192) bf16(A - A_hi)
+constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_AHB = 128, TM_ALB = 160, TM_ONES = 192, TM_TILE_STRIDE = 256;
+// float offsets inside the shared-memory weight image (prep_tc_image_kernel, hode_rollout_tc.cu):
+//   layer 0 (K = 16: 9 features, feature 9 = constant 1 whose weight column is the bias, zero padding):
+//     [B_hi tf32 1024][second half 1024]
+//   hidden layer l = 1..L-1 (K = 64, N = 64): [B_hi 4096][second half 4096]
+//   output layer (K = 64, N = 16):            [B_hi 1024][second half 1024]
+//   second half = B_lo (TF32 of B - B_hi; MLP_X3) or [bf16(B_hi)][bf16(B - B_hi)] (half as many floats each; MLP_MIXED)
+//   bias blocks (one K = 8 TF32 step, columns 0/1 = hi/lo): L x 512 (block 0 unused) + 128
+constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
 
-// Activation stash of the adjoint (one block per stage and hidden layer, per CTA): the tile's
+// Activation stash of the adjoint (one block per hidden layer, per CTA): the tile's
 // a_l = relu(z_l) as the BF16 operand image the weight-gradient MMAs read (csrc/probe/bf16_probe.cu),
 //   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2,
-// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to
-// 2^-17), followed by the ReLU masks: word [half][t] = bit j set iff a[32 half + j] > 0.
+// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to 2^-17).
 constexpr int ST_GRP = 2048;                 // one 8-feature group: 128 trajectories x 16 B
 constexpr int ST_PART = 8 * ST_GRP;          // 64 features
-constexpr int ST_BLK = 2 * ST_PART + 1024;   // hi, mid, masks
+constexpr int ST_BLK = 2 * ST_PART;          // hi, mid
 }  // namespace
 
 // x[0..7] -> 8 BF16 hi (round to nearest) and 8 BF16 mid = bf16(x - hi); feature 0 in the low half of word 0
@@ -55,8 +72,9 @@ __device__ __forceinline__ void bf16_split8(const float* v, uint4& hi, uint4& mi
 }
 
 // this thread's 32 activations a = relu(z) of columns [32 half, 32 half + 32), given as the TF32
-// hi / lo parts the epilogue produced (a = hi + lo exactly) -> stash block `blk`
-__device__ __forceinline__ void stash_store32(uint8_t* blk, int row, int half, const uint32_t* hi_, const uint32_t* lo_) {
+// hi / lo parts the epilogue produced (a = hi + lo exactly) -> stash block `blk`; returns the ReLU mask
+// (bit j set iff a[32 half + j] > 0), which the thread keeps in a register until the pull-back needs it
+__device__ __forceinline__ uint32_t stash_store32(uint8_t* blk, int row, int half, const uint32_t* hi_, const uint32_t* lo_) {
   uint32_t mask = 0u;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -72,7 +90,7 @@ __device__ __forceinline__ void stash_store32(uint8_t* blk, int row, int half, c
     *reinterpret_cast<uint4*>(p) = hi;
     *reinterpret_cast<uint4*>(p + ST_PART) = mid;
   }
-  reinterpret_cast<uint32_t*>(blk + 2 * ST_PART)[half * TILE + row] = mask;
+  return mask;
 }
 
 // ---- per-tile context -------------------------------------------------------------------------------
@@ -91,121 +109,200 @@ struct TileCtx {
 __device__ __forceinline__ void tile_sync_all(const TileCtx& c) {
   asm volatile("bar.sync %0, 256;" ::"r"(c.bar_all) : "memory");
 }
-// External-issue mode (the adjoint): a dedicated warp issues every MMA chain, so that no epilogue
-// warp is held in a blocking tcgen05.mma issue while it still has stores to do.  The 256 epilogue
-// threads ARRIVE on this named barrier, the issuer warp waits on it (mlp_fwd_issue).
-constexpr int EXT_ISSUE_BAR = 3, EXT_ISSUE_THREADS = 2 * TILE + 32;
-__device__ __forceinline__ void ext_issue_arrive() {
-  asm volatile("bar.arrive %0, %1;" ::"n"(EXT_ISSUE_BAR), "n"(EXT_ISSUE_THREADS) : "memory");
+// kind::f16 instruction descriptor, BF16 operands, FP32 accumulation, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void ext_issue_wait() {
-  asm volatile("bar.sync %0, %1;" ::"n"(EXT_ISSUE_BAR), "n"(EXT_ISSUE_THREADS) : "memory");
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
-// Issue the MMAs of one layer (one elected thread): D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
-// The two correction products are accumulated FIRST, into a still-small accumulator: the tensor
-// core truncates when it adds into D, and measured on B200 (csrc/probe/tc_probe.cu) this order
-// gives max err/sum|a*b| = 1.7e-7 (a plain fp32 FMA chain gives 2.2e-7), against 4.5e-7 when the
-// products are interleaved per k-step and 6.9e-7 when the large product goes first.
-template <bool X3, int N, int KSTEPS>
-__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t aones,
-                                            uint32_t b_hi, uint32_t b_lo, uint32_t b_bias) {
-  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N);
-  constexpr uint32_t lbo16 = (uint32_t)N;                 // (N*16 bytes) >> 4
+// Issue the MMAs of one layer (one elected thread): split-precision products with FP32-equivalent accuracy.
+// The correction products are accumulated FIRST, into a still-small accumulator: the tensor core truncates when
+// it adds into D, and measured on B200 (csrc/probe/tc_probe.cu, mix_probe.cu) this order gives max err / sum|a b| =
+// 1.7e-7 for 3xTF32 (a plain FP32 FMA chain: 2.2e-7; 6.9e-7 with the large product first) and 4.5e-7 for the mixed
+// split (8.0e-7 with the large product first).
+// The bias rides on the tensor pipe: one K = 8 TF32 step against a constant [1,1,0..] block (hidden and output
+// layers) or, in layer 0, the weight column of the constant-1 input feature.
+// b_hi: TF32 image of the weights; b_2: the second half of the layer's image (IMG_* above).
+template <int MODE, int N, int K, bool BIAS>
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32_t b_2, uint32_t b_bias) {
+  constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N), idesc_b = make_idesc_bf16(TILE, N);
+  constexpr uint32_t lbo16 = (uint32_t)N;                 // (N*16 bytes) >> 4: stride between 16-byte K chunks
   constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+  const uint32_t d = tmem + TM_D0, ahi = tmem + TM_AHI;
   const uint32_t lo_hi = ((b_hi >> 4) & 0x3FFFu) | (lbo16 << 16);
-  const uint32_t lo_lo = ((b_lo >> 4) & 0x3FFFu) | (lbo16 << 16);
+  const uint32_t lo_2 = ((b_2 >> 4) & 0x3FFFu) | (lbo16 << 16);
   const uint32_t lo_bias = ((b_bias >> 4) & 0x3FFFu) | (lbo16 << 16);
-  // D = bias (hi + lo through the constant [1,1,0..] block): initialises the accumulator
-  tc::mma_tf32_ts(d, aones, ((uint64_t)desc_hi << 32) | (uint64_t)lo_bias, idesc, 0u);
-  if (X3) {
+  uint32_t acc = 0u;
+  if (BIAS) {   // D = bias (hi + lo through the constant [1,1,0..] block): initialises the accumulator
+    tc::mma_tf32_ts(d, tmem + TM_ONES, ((uint64_t)desc_hi << 32) | (uint64_t)lo_bias, idesc, 0u);
+    acc = 1u;
+  }
+  if (MODE == MLP_X3) {
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks)
-      tc::mma_tf32_ts(d, alo + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
-                      idesc, 1u);
+    for (int ks = 0; ks < K / 8; ++ks) {   // A_lo B_hi
+      tc::mma_tf32_ts(d, tmem + TM_ALO + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, acc);
+      acc = 1u;
+    }
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks)
-      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lo + (uint32_t)ks * 2u * lbo16),
-                      idesc, 1u);
+    for (int ks = 0; ks < K / 8; ++ks)     // A_hi B_lo
+      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_2 + (uint32_t)ks * 2u * lbo16), idesc, 1u);
+  }
+  if (MODE == MLP_MIXED) {
+    // one BF16 MMA contracts K = 16 = 8 TMEM columns of A and two 16-byte K chunks of B; bf16(B - B_hi) follows
+    // bf16(B_hi) after K * N * 2 bytes
+    const uint32_t lo_lob = lo_2 + ((uint32_t)(K * N * 2) >> 4);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {  // bf16(A_lo) bf16(B_hi)
+      mma_bf16_ts(d, tmem + TM_ALB + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_2 + (uint32_t)ks * 2u * lbo16), idesc_b, acc);
+      acc = 1u;
+    }
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks)    // bf16(A_hi) bf16(B_lo)
+      mma_bf16_ts(d, tmem + TM_AHB + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lob + (uint32_t)ks * 2u * lbo16), idesc_b, 1u);
   }
 #pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks)
-    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16),
-                    idesc, 1u);
+  for (int ks = 0; ks < K / 8; ++ks) {     // A_hi B_hi
+    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, acc);
+    acc = 1u;
+  }
 }
 
-// ReLU + TF32 split of 16 accumulator columns (the bias is already in the accumulator), in
-// place: v -> hi bits, lo -> lo bits.  hi is rounded to nearest TF32; lo = a - hi is exact in
-// fp32 and is truncated to TF32 by the tensor core: a ~= hi + lo to 2^-22.
-template <bool X3>
-__device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float a = fmaxf(__uint_as_float(v[j]), 0.f);
-    const uint32_t h = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
-    v[j] = h;
-    if (X3) lo[j] = __float_as_uint(a - __uint_as_float(h));
+// the MMAs of layer `next` (0 = input layer .. L = output layer) of a tile, from its shared-memory weight image
+template <int MODE>
+__device__ __forceinline__ void issue_mlp_layer(uint32_t tmem, uint32_t img_s, int L, int next) {
+  const uint32_t bias_s = img_s + (IMG_L0 + (uint32_t)(L - 1) * IMG_HID + IMG_OUT) * 4u;
+  if (next == 0) {
+    issue_layer<MODE, H, 16, false>(tmem, img_s, img_s + 1024u * 4u, 0u);
+  } else if (next < L) {
+    const uint32_t b = img_s + (IMG_L0 + (uint32_t)(next - 1) * IMG_HID) * 4u;
+    issue_layer<MODE, H, 64, true>(tmem, b, b + 4096u * 4u, bias_s + (uint32_t)next * 512u * 4u);
+  } else {
+    const uint32_t b = img_s + (IMG_L0 + (uint32_t)(L - 1) * IMG_HID) * 4u;
+    issue_layer<MODE, 16, 64, true>(tmem, b, b + 1024u * 4u, bias_s + (uint32_t)L * 512u * 4u);
   }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // feature 2c in the low half (mix_probe test 1)
+  return r;
+}
+
+// ReLU + split of 16 accumulator columns (the bias is already in the accumulator): v -> TF32 hi bits (in place,
+// round to nearest), lo = a - hi (exact in FP32; the tensor core truncates it to TF32: a ~= hi + lo to 2^-22),
+// hb / lb = the BF16 operands of the mixed split's two cross terms (8 columns each).
+template <int MODE>
+__device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo, uint32_t* hb, uint32_t* lb) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float a0 = fmaxf(__uint_as_float(v[j]), 0.f), a1 = fmaxf(__uint_as_float(v[j + 1]), 0.f);
+    const uint32_t h0 = (__float_as_uint(a0) + 0x1000u) & 0xFFFFE000u, h1 = (__float_as_uint(a1) + 0x1000u) & 0xFFFFE000u;
+    v[j] = h0;
+    v[j + 1] = h1;
+    if (MODE != MLP_TF32) {
+      const float l0 = a0 - __uint_as_float(h0), l1 = a1 - __uint_as_float(h1);
+      lo[j] = __float_as_uint(l0);
+      lo[j + 1] = __float_as_uint(l1);
+      if (MODE == MLP_MIXED) {
+        hb[j >> 1] = pack_bf16x2(__uint_as_float(h0), __uint_as_float(h1));
+        lb[j >> 1] = pack_bf16x2(l0, l1);
+      }
+    }
+  }
+}
+
+// The hidden-layer epilogue of one thread: 32 accumulator columns [col0, col0 + 32) of its TMEM lane -> the next
+// layer's A operand.  v / lo keep a = v + lo for the adjoint's stash.  Ends with wait::st + fence: the caller
+// signals the MMA issuer next.  store = false: only v / lo are produced (the last hidden layer of the adjoint's
+// recomputation feeds no further product).
+template <int MODE>
+__device__ __forceinline__ void epilogue32_to_tmem(uint32_t t_lane, uint32_t col0, uint32_t* v, uint32_t* lo, bool store = true) {
+  const uint32_t t_ahi = t_lane + TM_AHI + col0, t_alo = t_lane + TM_ALO + col0;
+  const uint32_t t_ahb = t_lane + TM_AHB + (col0 >> 1), t_alb = t_lane + TM_ALB + (col0 >> 1);
+  HODE_TMEM_LD_X32(t_lane + TM_D0 + col0, v);
+  tc::wait_ld();
+  uint32_t hb[16], lb[16];
+  epilogue16<MODE>(v, lo, hb, lb);
+  if (store) {
+    HODE_TMEM_ST_X16(t_ahi, v);
+    if (MODE == MLP_X3) HODE_TMEM_ST_X16(t_alo, lo);
+    if (MODE == MLP_MIXED) { HODE_TMEM_ST_X8(t_ahb, hb); HODE_TMEM_ST_X8(t_alb, lb); }
+  }
+  epilogue16<MODE>(v + 16, lo + 16, hb + 8, lb + 8);
+  if (store) {
+    HODE_TMEM_ST_X16(t_ahi + 16, (v + 16));
+    if (MODE == MLP_X3) HODE_TMEM_ST_X16(t_alo + 16, (lo + 16));
+    if (MODE == MLP_MIXED) { HODE_TMEM_ST_X8(t_ahb + 8, (hb + 8)); HODE_TMEM_ST_X8(t_alb + 8, (lb + 8)); }
+    tc::wait_st();
+  }
+  tc::fence_before_sync();
+}
+
+// layer-0 operand of one thread: its 9 input features, feature 9 = 1 (its weight column is the layer's bias),
+// zero padding to K = 16
+template <int MODE>
+__device__ __forceinline__ void store_input_operand(uint32_t t_lane, const float* x) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float xv = (k < HODE_NN_IN) ? x[k] : (k == HODE_NN_IN ? 1.0f : 0.0f);
+    hi[k] = (__float_as_uint(xv) + 0x1000u) & 0xFFFFE000u;
+    lo[k] = __float_as_uint(xv - __uint_as_float(hi[k]));
+  }
+  HODE_TMEM_ST_X16(t_lane + TM_AHI, hi);
+  if (MODE == MLP_X3) HODE_TMEM_ST_X16(t_lane + TM_ALO, lo);
+  if (MODE == MLP_MIXED) {
+    uint32_t hb[8], lb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      hb[c] = pack_bf16x2(__uint_as_float(hi[2 * c]), __uint_as_float(hi[2 * c + 1]));
+      lb[c] = pack_bf16x2(__uint_as_float(lo[2 * c]), __uint_as_float(lo[2 * c + 1]));
+    }
+    HODE_TMEM_ST_X8(t_lane + TM_AHB, hb);
+    HODE_TMEM_ST_X8(t_lane + TM_ALB, lb);
+  }
+  tc::wait_st();
+  tc::fence_before_sync();
 }
 
 // The residual MLP for the 128 trajectories of a tile (reference models/nn_residual.py:136-146).
 // Every thread of the tile must call this converged.  x: the 9 input features of this thread's
 // trajectory; r: the 6 residuals.  `overlap` runs right after the layer-0 MMAs have been issued: per-thread
 // work that does not depend on the network (the mechanistic RHS) hides behind their latency.
-template <bool X3, bool EXT = false, class F>
-__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash, int stash_row,
-                                         F&& overlap) {
-  const uint32_t t_d = c.tmem + c.lane_base + TM_D0;
-  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI;
-  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO;
-  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
-  const uint32_t m_ones = c.tmem + TM_ONES;
-  const float* img = c.img;
-  const uint32_t img_s = tc::smem_u32(img);
-  const uint32_t bias_s = img_s + (uint32_t)(2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024) * 4u;
+// (The adjoint, hode_adjoint_tc.cu, builds its own recomputation from the same pieces: store_input_operand,
+// issue_layer, epilogue32_to_tmem.)
+template <int X3, class F>
+__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, F&& overlap) {
+  const uint32_t t_lane = c.tmem + c.lane_base;
+  const uint32_t img_s = tc::smem_u32(c.img);
   HODE_TL(0);
-  // ---- layer 0 operand: 9 features zero-padded to K = 16 ----------------------------------------
-  {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (k < HODE_NN_IN) tc::split_tf32(x[k], hi[k], lo[k]);
-      else { hi[k] = 0u; lo[k] = 0u; }
-    }
-    HODE_TMEM_ST_X16(t_ahi, hi);
-    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
-  }
-  tc::wait_st();
-  tc::fence_before_sync();
+  store_input_operand<X3>(t_lane, x);
   HODE_TL(1);
   // main AND helper warps: the helpers arrive here only after they have observed the previous
   // call's last mbarrier phase, so the layer-0 commit below cannot flip the barrier a second time
   // under a helper that is still busy (it would then wait for a phase that has already passed)
-  if (EXT) {
-    ext_issue_arrive();
-  } else {
-    tile_sync_all(c);
-    HODE_TL(2);
-    if (c.wq == 0) {
-      if (tc::elect_one()) {
-        tc::fence_after_sync();
-        issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, m_ones, img_s, img_s + 1024 * 4, bias_s);
-        tc::mma_commit(c.mma_bar);
-      }
-      __syncwarp();
+  tile_sync_all(c);
+  HODE_TL(2);
+  if (c.wq == 0) {
+    if (tc::elect_one()) {
+      tc::fence_after_sync();
+      issue_mlp_layer<X3>(c.tmem, img_s, c.L, 0);
+      tc::mma_commit(c.mma_bar);
     }
+    __syncwarp();
   }
   HODE_TL(3);
   overlap();
   __syncwarp();   // per-thread code may leave the warp diverged (division slow paths); the tcgen05 .sync.aligned
                   // instructions below need it converged
-  uint32_t w_off = 2 * 1024;  // float offset of the next layer's weights inside the image
   // ---- hidden layers: epilogue of layer l feeds the MMAs of layer l+1 ---------------------------
 #pragma unroll 1
   for (int l = 0; l < c.L; ++l) {
-    const bool last = (l + 1 == c.L);
-    const uint32_t b_hi = img_s + w_off * 4;
-    const uint32_t b_lo = b_hi + (last ? 1024u : 4096u) * 4u;
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
@@ -213,39 +310,19 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
     // the main warp owns accumulator columns [0,32) of its 32 lanes, the helper warp of the same
     // lane quarter columns [32,64) (mlp_tile_helper): the epilogue latency per layer is halved
     uint32_t v0[32], lo[32];
-    HODE_TMEM_LD_X32(t_d, v0);
-    tc::wait_ld();
-    HODE_TL(11 + 10 * l);
-    epilogue16<X3>(v0, lo);
-    HODE_TMEM_ST_X16(t_ahi, v0);
-    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
-    epilogue16<X3>(v0 + 16, lo + 16);
-    HODE_TMEM_ST_X16(t_ahi + 16, (v0 + 16));
-    if (X3) HODE_TMEM_ST_X16(t_alo + 16, (lo + 16));
-    tc::wait_st();
-    tc::fence_before_sync();
+    epilogue32_to_tmem<X3>(t_lane, 0u, v0, lo);
     HODE_TL(12 + 10 * l);
-    if (EXT) {
-      ext_issue_arrive();
-    } else {
-      tile_sync_all(c);
-      HODE_TL(13 + 10 * l);
-      if (c.wq == 0) {
-        if (tc::elect_one()) {
-          tc::fence_after_sync();
-          const uint32_t b_bias = bias_s + (uint32_t)(l + 1) * 512u * 4u;
-          if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
-          else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
-          tc::mma_commit(c.mma_bar);
-        }
-        __syncwarp();
+    tile_sync_all(c);
+    HODE_TL(13 + 10 * l);
+    if (c.wq == 0) {
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        issue_mlp_layer<X3>(c.tmem, img_s, c.L, l + 1);
+        tc::mma_commit(c.mma_bar);
       }
+      __syncwarp();
     }
-    // adjoint: a_l = relu(z_l) of this thread's trajectory, columns [0,32), goes to the stash AFTER
-    // the next layer's MMAs have been issued (off the critical path)
-    if (X3 && stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 0, v0, lo);
     HODE_TL(14 + 10 * l);
-    w_off += 2 * 4096;
   }
   // ---- output layer epilogue: 6 of the 16 accumulator columns ------------------------------------
   tc::mbar_wait(c.mma_bar, c.parity);
@@ -254,7 +331,7 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
   HODE_TL(90);
   {
     uint32_t v[8];
-    HODE_TMEM_LD_X8(t_d, v);
+    HODE_TMEM_LD_X8(t_lane + TM_D0, v);
     tc::wait_ld();
 #pragma unroll
     for (int i = 0; i < NS; ++i) r[i] = __uint_as_float(v[i]);
@@ -264,76 +341,20 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, u
   // D only after a tile barrier that every thread reaches after its wait::ld above.
 }
 
-template <bool X3>
-__device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, uint8_t* stash = nullptr,
-                                         int stash_row = 0) {
-  mlp_tile<X3, false>(c, x, r, stash, stash_row, [] {});
-}
-
-// External-issue mode: the MMA chains of one mlp_tile<X3, true>() call, issued by a dedicated (converged)
-// warp.  Every chain is committed to the tile's mbarrier; c.parity tracks the phase of the last commit.
-template <bool X3>
-__device__ __forceinline__ void mlp_fwd_issue(TileCtx& c) {
-  const uint32_t m_d = c.tmem + TM_D0, m_ahi = c.tmem + TM_AHI, m_alo = c.tmem + TM_ALO;
-  const uint32_t m_ones = c.tmem + TM_ONES;
-  const uint32_t img_s = tc::smem_u32(c.img);
-  const uint32_t bias_s = img_s + (uint32_t)(2 * 1024 + (c.L - 1) * 2 * 4096 + 2 * 1024) * 4u;
-  ext_issue_wait();
-  if (tc::elect_one()) {
-    tc::fence_after_sync();
-    issue_layer<X3, H, 2>(m_d, m_ahi, m_alo, m_ones, img_s, img_s + 1024 * 4, bias_s);
-    tc::mma_commit(c.mma_bar);
-  }
-  __syncwarp();
-  c.parity ^= 1u;
-  uint32_t w_off = 2 * 1024;
-#pragma unroll 1
-  for (int l = 0; l < c.L; ++l) {
-    const bool last = (l + 1 == c.L);
-    const uint32_t b_hi = img_s + w_off * 4;
-    const uint32_t b_lo = b_hi + (last ? 1024u : 4096u) * 4u;
-    ext_issue_wait();
-    if (tc::elect_one()) {
-      tc::fence_after_sync();
-      const uint32_t b_bias = bias_s + (uint32_t)(l + 1) * 512u * 4u;
-      if (!last) issue_layer<X3, H, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
-      else issue_layer<X3, 16, 8>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, b_bias);
-      tc::mma_commit(c.mma_bar);
-    }
-    __syncwarp();
-    c.parity ^= 1u;
-    w_off += 2 * 4096;
-  }
-}
-
 // Helper warps: the other half of every hidden-layer epilogue.  Must be called once per
 // mlp_tile() call of the tile's main warps (same number of tile-wide barriers and mbarrier phases).
-template <bool X3, bool EXT = false>
-__device__ __forceinline__ void mlp_tile_helper(TileCtx& c, uint8_t* stash = nullptr, int stash_row = 0) {
-  const uint32_t t_d = c.tmem + c.lane_base + TM_D0 + 32;
-  const uint32_t t_ahi = c.tmem + c.lane_base + TM_AHI + 32;
-  const uint32_t t_alo = c.tmem + c.lane_base + TM_ALO + 32;
-  if (EXT) ext_issue_arrive();
-  else tile_sync_all(c);   // pairs with the main warps' barrier before the layer-0 MMAs (see mlp_tile)
+template <int X3>
+__device__ __forceinline__ void mlp_tile_helper(TileCtx& c) {
+  const uint32_t t_lane = c.tmem + c.lane_base;
+  tile_sync_all(c);   // pairs with the main warps' barrier before the layer-0 MMAs (see mlp_tile)
 #pragma unroll 1
   for (int l = 0; l < c.L; ++l) {
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
     uint32_t v[32], lo[32];
-    HODE_TMEM_LD_X32(t_d, v);
-    tc::wait_ld();
-    epilogue16<X3>(v, lo);
-    HODE_TMEM_ST_X16(t_ahi, v);
-    if (X3) HODE_TMEM_ST_X16(t_alo, lo);
-    epilogue16<X3>(v + 16, lo + 16);
-    HODE_TMEM_ST_X16(t_ahi + 16, (v + 16));
-    if (X3) HODE_TMEM_ST_X16(t_alo + 16, (lo + 16));
-    tc::wait_st();
-    tc::fence_before_sync();
-    if (EXT) ext_issue_arrive();
-    else tile_sync_all(c);
-    if (X3 && stash) stash_store32(stash + (size_t)l * ST_BLK, stash_row, 1, v, lo);   // columns [32,64)
+    epilogue32_to_tmem<X3>(t_lane, 32u, v, lo);
+    tile_sync_all(c);
   }
   // the output layer's phase: nothing to read, but the phase must be observed so that the next
   // call's first wait cannot be satisfied by a stale parity

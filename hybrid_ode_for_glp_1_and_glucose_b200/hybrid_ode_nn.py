@@ -52,7 +52,9 @@ class HybridODENN(nn.Module):
         self.state_names = list(STATE_NAMES)
         # kernel behaviour defaults (not part of the reference's surface)
         self.kinks = "clip"
-        self.precision = "fp32"
+        # 'auto': the tcgen05 kernels whenever the network is 64 wide with <= 4 hidden layers (the reference's
+        # default shape), the FP32 CUDA-core kernels otherwise (ops.default_precision); 'fp32' = parity mode
+        self.precision = "auto"
         self.rk4_substeps = 4
         # loss(): run the (up to 20) physics re-solves as ONE stacked launch instead of a Python loop
         self.fused_physics = True
@@ -204,6 +206,8 @@ class HybridODENN(nn.Module):
                 max_steps=kernel_opts.get("max_steps", 0),
                 max_saved_steps=kernel_opts.get("max_saved_steps", 0))
             self.last_info = info
+            if kernel_opts.get("check_status", self.check_status):
+                self._warn_failures(info)
             return traj
         traj, info = ops.rollout(
             initial_state if initial_state.dim() == 2 else initial_state.unsqueeze(0), t_span,
@@ -214,6 +218,8 @@ class HybridODENN(nn.Module):
             precision=kernel_opts.get("precision", self.precision),
             max_steps=kernel_opts.get("max_steps", 0), device=dev)
         self.last_info = info
+        if kernel_opts.get("check_status", self.check_status):
+            self._warn_failures(info)
         return traj
 
     def _stack_samples(self, samples: List[Dict[str, torch.Tensor]], dev: torch.device):

@@ -20,7 +20,23 @@ SOLVERS = {
     # BASELINE.json's north_star specifies, 'dopri5' is Dormand-Prince 5(4) (= SciPy 'RK45').
     "dopri5": _lib.SOLVER_DOPRI5, "rk45": _lib.SOLVER_DOPRI5, "rk4": _lib.SOLVER_RK4,
 }
-PRECISIONS = {"fp32": _lib.MLP_FP32, "tf32x3": _lib.MLP_TF32X3, "tf32": _lib.MLP_TF32}
+PRECISIONS = {"fp32": _lib.MLP_FP32, "tf32x3": _lib.MLP_TF32X3, "tf32": _lib.MLP_TF32, "tf32bf16": _lib.MLP_TF32BF16}
+
+
+def default_precision(hidden: int, layers: int) -> str:
+    """'auto' resolves to the tcgen05 kernels (split-precision passes, float32-equivalent accuracy) whenever
+    the network has the shape both tensor-core kernels are compiled for (64 wide, <= 4 hidden layers: the
+    reference's default, models/nn_residual.py:28-36), and to the FP32 CUDA-core kernels for any other shape.
+    precision='fp32' stays available as the bit-conservative parity mode."""
+    return "tf32x3" if hidden == 64 and 1 <= layers <= 4 else "fp32"
+
+
+def _mlp_mode(precision: str, hidden: int, layers: int) -> int:
+    if precision == "auto":
+        precision = default_precision(hidden, layers)
+    if precision not in PRECISIONS:
+        raise HodeError(f"precision '{precision}' is not one of {sorted(PRECISIONS) + ['auto']}")
+    return PRECISIONS[precision]
 KINKS = {"scipy": _lib.KINK_SCIPY, "clip": _lib.KINK_CLIP}
 
 
@@ -138,7 +154,7 @@ class RolloutTape:
 def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
             theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
             solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
-            kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
+            kinks: str = "clip", precision: str = "auto", max_steps: int = 0,
             device: Optional[torch.device] = None, save_steps: bool = False,
             max_saved_steps: int = 0):
     """Batched IVP solve on the GPU (hode_rollout_fwd).
@@ -161,7 +177,7 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
     cfg.save_steps = 1 if save_steps else 0
     cfg.max_saved_steps = int(max_saved_steps)
     if cfg.mlp != _lib.MLP_NONE:
-        cfg.mlp = PRECISIONS[precision]
+        cfg.mlp = _mlp_mode(precision, hidden, layers)
     B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
     with torch.cuda.device(device):
         traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
@@ -174,6 +190,16 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
             _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
             _ptr(traj), _ptr(status), _ptr(counters), _ptr(ws), ws_bytes, _stream(device))
     _lib.check(rc, "hode_rollout_fwd")
+    if save_steps and B > 0 and cfg.solver == _lib.SOLVER_DOPRI5 and max_saved_steps <= 0:
+        # The record capacity was left to the library (max(128, 2 (T - 1)) accepted steps per trajectory).  A
+        # trajectory that needs more is reported as ST_REC_OVERFLOW, zero-padded and left without gradient — unlike
+        # the same call without save_steps.  Re-run with a larger capacity instead of returning that (one status
+        # read-back per differentiable rollout; pass max_saved_steps explicitly to skip the check).
+        cap = int(_lib.lib().hode_step_record_capacity(ctypes.byref(cfg)))
+        limit = max_steps if max_steps > 0 else 100000
+        if bool((status == _lib.ST_REC_OVERFLOW).any()) and cap < limit:
+            return rollout(y0, t_obs, inputs, theta, W, hidden, layers, solver, rtol, atol, n_substeps, kinks,
+                           precision, max_steps, device, save_steps, min(4 * cap, limit))
     if squeeze_s:
         out = traj[0], RolloutInfo(status[0], counters[0, 0], counters[1, 0])
     else:
@@ -219,7 +245,7 @@ def rollout_bwd(tape: RolloutTape, grad_traj: torch.Tensor, need_y0: bool = True
 def data_loss_step(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
                    theta: torch.Tensor, W: Optional[torch.Tensor], obs: torch.Tensor, hidden: int = 64,
                    layers: int = 4, solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8,
-                   n_substeps: int = 4, kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
+                   n_substeps: int = 4, kinks: str = "clip", precision: str = "auto", max_steps: int = 0,
                    device: Optional[torch.device] = None, max_saved_steps: int = 0, need_y0: bool = False):
     """loss = mean((rollout - obs)^2) and its gradients in ONE library call (hode_loss_fused_fwd_bwd):
     returns (loss [S] or scalar, grad_y0 or None, grad_theta, grad_W or None, traj, RolloutInfo)."""
@@ -237,7 +263,7 @@ def data_loss_step(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[
     cfg.save_steps = 1
     cfg.max_saved_steps = int(max_saved_steps)
     if cfg.mlp != _lib.MLP_NONE:
-        cfg.mlp = PRECISIONS[precision]
+        cfg.mlp = _mlp_mode(precision, hidden, layers)
     B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
     P = 0 if bufs["W"] is None else bufs["W"].shape[1]
     o = _f32c(obs.reshape(B, T, 6), device)
@@ -299,23 +325,22 @@ def saved_steps(tape: RolloutTape):
     (diagnostics / tests: the step sequence the adjoint differentiates)."""
     cfg = tape.cfg
     units = cfg.n_samples * cfg.n_traj
-    if cfg.solver == _lib.SOLVER_RK4:
-        max_saved = (cfg.n_obs - 1) * max(cfg.n_substeps, 1)
-    else:
-        max_saved = cfg.max_saved_steps if cfg.max_saved_steps > 0 else 256
+    L = _lib.lib()
+    max_saved = int(L.hode_step_record_capacity(ctypes.byref(cfg)))
+    rec_bytes = 4 * int(L.hode_step_record_floats(ctypes.byref(cfg)))
     al = lambda x: (x + 255) // 256 * 256
     ws = tape.workspace
     n = ws[: units * 4].view(torch.int32)
-    # one 64-byte record per (unit, step): { t f64, h f32, pad, y[6], k1[6] } (csrc/hode_common.cuh step_rec)
+    # one record per (unit, step): { t f64, h f32, pad, y[6], k1[6] (, k2..k6) } (csrc/hode_common.cuh step_rec)
     off_rec = al(units * 4)
-    rec = ws[off_rec: off_rec + units * max_saved * 64].view(torch.float64).reshape(units, max_saved, 8)
+    rec = ws[off_rec: off_rec + units * max_saved * rec_bytes].view(torch.float64).reshape(units, max_saved, rec_bytes // 8)
     return n, rec[:, :, 0].permute(1, 0)
 
 
 def vi_predictive(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
                   theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int = 64, layers: int = 4,
                   solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
-                  kinks: str = "clip", precision: str = "fp32", max_steps: int = 0,
+                  kinks: str = "clip", precision: str = "auto", max_steps: int = 0,
                   device: Optional[torch.device] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor, RolloutInfo]:
     """Posterior-predictive mean and unbiased std over the S parameter sets theta [S,17] /
@@ -335,7 +360,7 @@ def vi_predictive(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[s
     cfg.max_steps = int(max_steps)
     cfg.kink_mode = KINKS[kinks]
     if cfg.mlp != _lib.MLP_NONE:
-        cfg.mlp = PRECISIONS[precision]
+        cfg.mlp = _mlp_mode(precision, hidden, layers)
     B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
     with torch.cuda.device(device):
         mean = torch.empty((B, T, 6), dtype=torch.float32, device=device)

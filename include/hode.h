@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HODE_ABI_VERSION 2
+#define HODE_ABI_VERSION 3
 #define HODE_N_STATE 6
 #define HODE_N_THETA 17
 #define HODE_NN_IN 9
@@ -63,7 +63,9 @@ enum {
   HODE_MLP_NONE = 0,   /* no residual network (ablation no_nn, train/train_hybrid.py:423-427) */
   HODE_MLP_FP32 = 1,   /* FP32 FMA on CUDA cores: parity mode                                */
   HODE_MLP_TF32X3 = 2, /* tcgen05 tensor cores, 3xTF32 split (fp32-equivalent accuracy)      */
-  HODE_MLP_TF32 = 3    /* tcgen05 tensor cores, single TF32 pass (fast, ~1e-3 on residual)   */
+  HODE_MLP_TF32 = 3,   /* tcgen05 tensor cores, single TF32 pass (fast, ~1e-3 on residual)   */
+  HODE_MLP_TF32BF16 = 4 /* tcgen05: one TF32 pass + two BF16 cross-term passes (2 pass-equivalents; max
+                           error 4.5e-7 of sum|ab| per product against 1.7e-7 for TF32X3: opt-in)   */
 };
 
 /*
@@ -83,7 +85,9 @@ enum {
   HODE_ST_OK = 0,
   HODE_ST_STEP_TOO_SMALL = 1, /* SciPy: "Required step size is less than spacing between numbers." */
   HODE_ST_MAX_STEPS = 2,      /* attempt budget (cfg.max_steps) exhausted                        */
-  HODE_ST_NONFINITE = 3       /* state became NaN/Inf                                            */
+  HODE_ST_NONFINITE = 3,      /* state became NaN/Inf                                            */
+  HODE_ST_REC_OVERFLOW = 4    /* save_steps: more accepted steps than cfg.max_saved_steps records (the
+                                 trajectory is zero-padded and gets no gradient; raise the capacity)  */
 };
 
 /* argument errors */
@@ -113,7 +117,9 @@ typedef struct hode_cfg {
   double atol;           /* DOPRI5 (reference default 1e-8); both at byte offset 56/64         */
   int32_t save_steps;    /* 1: record accepted steps in the workspace for hode_rollout_bwd     */
   int32_t kink_mode;     /* DOPRI5: HODE_KINK_* (how input-slope discontinuities are handled)  */
-  int32_t max_saved_steps; /* DOPRI5 + save_steps: accepted-step capacity per trajectory (0 -> 256) */
+  int32_t max_saved_steps; /* DOPRI5 + save_steps: accepted-step record capacity per trajectory;
+                              0 -> max(128, 2 (T - 1)): with kink clipping a series input that changes at
+                              every grid point forces T - 1 accepted steps                          */
   int32_t rhs_part;      /* hode_rhs only: HODE_RHS_FULL or HODE_RHS_NN_ONLY                    */
 } hode_cfg;
 
@@ -125,6 +131,13 @@ const char* hode_last_error_string(void);
 
 /* Number of floats in one packed MLP parameter set (13 510 for hidden=64, layers=4). */
 int64_t hode_mlp_param_count(int32_t nn_hidden, int32_t nn_layers);
+
+/* Floats per accepted-step record in the forward workspace for this cfg (16, or 48 when the tensor-core
+ * adjoint will consume them: the record then carries the step's stage derivatives); 0 without save_steps. */
+int32_t hode_step_record_floats(const hode_cfg* cfg);
+
+/* Accepted-step record capacity per trajectory hode_rollout_fwd will use for this cfg (see max_saved_steps). */
+int32_t hode_step_record_capacity(const hode_cfg* cfg);
 
 /* Bytes of device workspace hode_rollout_fwd needs (saved steps when save_steps = 1, tensor-core
  * weight images) and of gradient scratch hode_rollout_bwd / hode_rhs_vjp need. */

@@ -20,6 +20,7 @@ def dev(built_lib):
 
 def gpu_rollout(dev, y0, t, ins, theta, W, hidden=64, layers=4, **kw):
     from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    kw.setdefault("precision", "fp32")   # the FP32 parity kernels unless a test names the tensor-core ones
     tin = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in (ins or {}).items()}
     traj, info = ops.rollout(torch.from_numpy(y0), torch.from_numpy(t), tin,
                              torch.from_numpy(theta), None if W is None else torch.from_numpy(W),
@@ -456,3 +457,26 @@ def test_config3_full_size_properties_hybrid(dev, oracle):
                                   atol=1e-8, kinks="clip", n_threads=8)
     e_gpu, e_ref = rel_err(tr[sub], truth), rel_err(ref, truth)
     assert e_gpu < max(2.0 * e_ref, 2e-5), (e_gpu, e_ref)
+
+
+def test_module_default_reaches_the_tensor_core_kernel(dev):
+    """The drop-in class, constructed the way the reference's call sites construct it (64 x 4 network), must run the
+    tcgen05 rollout by default: its output is bit-identical to precision='tf32x3' and not to the FP32 kernels'.
+    Other network shapes default to the FP32 kernels."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN, ops
+    assert ops.default_precision(64, 4) == "tf32x3" and ops.default_precision(64, 1) == "tf32x3"
+    assert ops.default_precision(32, 3) == "fp32" and ops.default_precision(64, 5) == "fp32"
+    y0, t, ins = cohort(300, seed=41)
+    m = HybridODENN(device=dev)
+    assert m.precision == "auto"
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for p in m.nn_residual.parameters():
+            p.copy_(0.05 * torch.randn_like(p))
+    tin = {k: torch.from_numpy(v).to(dev) for k, v in ins.items()}
+    a = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin)
+    b = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin, precision="tf32x3")
+    c = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin, precision="fp32")
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    assert float((a - c).abs().max() / c.abs().max()) < 1e-4
