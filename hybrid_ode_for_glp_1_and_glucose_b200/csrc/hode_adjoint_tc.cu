@@ -11,13 +11,15 @@
 //     one stage (4 x 32 KB as BF16 operand images) live in a per-CTA scratch that is written and read back
 //     within microseconds: 38 MB for the whole grid, L2-resident (round 1 stashed all 6 stages of a step and
 //     streamed 78 GB through HBM per launch);
-//   * the recomputation F of item e+1 is INTERLEAVED with the pull-back B of item e on the same 128
-//     trajectories: the two are independent (F needs no cotangent), so while the epilogue threads work on one
-//     chain the tensor pipe runs the MMAs of the other — the overlap the rollout gets from its second tile;
-//   * roles (warp-specialised, setmaxnreg): 4 main warps (one trajectory per thread: records, stage inputs,
-//     mechanistic VJP, RK recurrences), 4 helper warps (the other half of every epilogue), 1 MMA-issuer warp,
-//     3 loader warps (TMA: forward weights by layer, W^T by phase, stashed activations by phase) that run
-//     ahead of the issuer as far as the buffers allow (full / free mbarrier pairs, free = tcgen05.commit);
+//   * the recomputation F of item e+1 runs CONCURRENTLY with the pull-back B of item e on the same 128
+//     trajectories: the two are independent (F needs no cotangent).  Each chain has its own epilogue warps and its
+//     own MMA-issuer warp, so neither waits for the other; the tensor pipe interleaves their MMAs;
+//   * roles (warp-specialised, setmaxnreg), 768 threads: 4 main warps (one trajectory per thread: records, stage
+//     inputs, cotangent of the network outputs, mechanistic VJP, RK recurrences), 8 recomputation-epilogue warps
+//     (ReLU / operand split / activation scratch, 32 columns each), 8 pull-back-epilogue warps (ReLU mask / delta
+//     image, 32 columns each), and one warp each for: F issue + forward-weight loads, B issue, W^T loads (TMA),
+//     activation loads (TMA); loaders run ahead as far as the buffers allow (full / free mbarrier pairs,
+//     free = tcgen05.commit);
 //   * schedule (device side, deterministic): trajectories are radix-sorted by accepted-step count, cut into
 //     128-trajectory tiles, and the tiles are dealt to the CTAs longest-first;
 //   * delta is written ONCE per phase, by its owner threads, as a two-term BF16 image in shared memory
@@ -85,26 +87,32 @@ constexpr uint32_t TM_DB = 200, DW_H0 = 264, DW_HS = 72, DW_0 = 480, DW_O = 496;
 
 // ---- shared memory (bytes) ------------------------------------------------------------------------------------
 //   AB  2 x [hi: 8 feature groups + the constant-1 group][mid: likewise]: input operand a_{q-1} of the weight gradients
-//   DB  2 x [hi][mid]: the delta image of a phase (both buffered by phase parity)
+//   DB  2 x [hi][mid]: the delta image of a phase (buffered by phase parity)
+//   XB  2 x [hi: 2 groups][mid: 2 groups]: the stage's input features x, input operand of dW_0 (buffered by item parity)
 //   WT  2 x one layer's W^T (BF16 hi, mid)         WF  one layer's forward image + its bias block
-//   REC the NEXT step's record of every main thread, [12 chunks][128 threads][16 B] (conflict-free LDS.128)
-constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART;
+constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART + 1024;   // hi, mid, ReLU masks of a_{q-1}
 constexpr int DB_BYTES = 2 * ST_PART;
+constexpr int XB_PART = 2 * ST_GRP, XB_BYTES = 2 * XB_PART;
 constexpr int WT_BYTES = 2 * 64 * 64 * 2;
 constexpr int WF_FLOATS = 8192 + 512, WF_BYTES = WF_FLOATS * 4;
-constexpr int REC_CHUNKS = HODE_REC_FLOATS_K / 4, REC_BYTES = REC_CHUNKS * TILE * 16;
-constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_WT = OFF_DB + 2 * DB_BYTES, OFF_WF = OFF_WT + 2 * WT_BYTES,
-              OFF_REC = OFF_WF + WF_BYTES, OFF_T = OFF_REC + REC_BYTES;
+constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_XB = OFF_DB + 2 * DB_BYTES, OFF_WT = OFF_XB + 2 * XB_BYTES,
+              OFF_WF = OFF_WT + 2 * WT_BYTES, OFF_T = OFF_WF + WF_BYTES;
 constexpr int ADJ_SMEM_BASE = OFF_T;            // + 4 T bytes when the shared time grid fits
 constexpr int ADJ_SMEM_MAX = 227 * 1024 - 256;  // (static shared memory: the mbarriers, padded to the dynamic part's alignment)
+constexpr int ADJ_THREADS = 6 * TILE;
 
 struct Bars {
-  uint64_t f_bar;        // recomputation: a layer's MMAs complete
-  uint64_t b_bar;        // pull-back: a phase's delta chain complete
+  uint64_t f_bar;        // recomputation: a layer's MMAs complete (observed by the F-epilogue warps)
+  uint64_t fl_bar;       // recomputation: the LAST layer's MMAs of an item complete (observed by the main warps)
+  uint64_t b_bar;        // pull-back: a phase's delta chain complete (observed by the B-epilogue warps)
+  uint64_t gx_bar;       // pull-back: the final phase (g_x) of an item complete (observed by the main warps)
   uint64_t wf_full, wf_free;
   uint64_t wt_full[2], wt_free[2];
   uint64_t ab_full[2], ab_free[2];
-  uint64_t st_done[MAXL];   // 256 arrivals: the tile's a_l of the item being recomputed is in the stash
+  // 256 arrivals: a_l of the item being recomputed is in scratch set (item & 1).  One barrier per SET and layer: the
+  // recomputation runs up to one item ahead of the pull-back, so a per-layer barrier could complete twice before
+  // its waiter looks (parity aliasing); a per-set one completes once per two items
+  uint64_t st_done[2][MAXL];
   uint64_t done;
 };
 
@@ -167,14 +175,17 @@ __device__ __forceinline__ void issue_u(uint32_t d, uint32_t a_hi, uint32_t a_mi
   for (int ks = 0; ks < KSTEPS; ++ks) mma_bf16_ss(d, ah + sa * ks, bh + sb * ks, idesc, 1u);
 }
 
-// ---- named barriers: the 256 epilogue threads ARRIVE, the issuer warp waits (bar.sync) ---------------------------
-// One barrier per chain.  Race-free: the MMA chain whose completion lets a thread move on to its next arrival
-// on a barrier is only issued after the barrier's previous generation has completed.
-constexpr int BAR_F = 3, BAR_B = 4, BAR_THREADS = 2 * TILE + 32;
-template <int ID>
-__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(BAR_THREADS) : "memory"); }
-template <int ID>
-__device__ __forceinline__ void bar_wait() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(BAR_THREADS) : "memory"); }
+// ---- named barriers: producers ARRIVE, the issuer warp of the chain waits (bar.sync) ---------------------------------
+//   BAR_X  main -> F issuer: the item's input operand is in TMEM          BAR_F  F-epilogue warps -> F issuer
+//   BAR_BX main -> B issuer: delta_L and the dW_0 input operand are written BAR_B  B-epilogue warps -> B issuer
+// Race-free: the MMA chain whose completion lets a thread move on to its next arrival on a barrier is only issued
+// after the barrier's previous generation has completed.
+constexpr int BAR_X = 1, BAR_F = 2, BAR_BX = 3, BAR_B = 4, BAR_MAIN = 5;
+template <int ID, int THREADS>
+__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(THREADS) : "memory"); }
+template <int ID, int THREADS>
+__device__ __forceinline__ void bar_wait() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory"); }
+constexpr int N_MAIN = TILE + 32, N_EPI = 2 * TILE + 32;
 
 // closed-form VJP of f_physio — same formulas as hode_adjoint_simt.cu::rhs_mech_vjp
 __device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float GD, bool gd_present,
@@ -226,87 +237,19 @@ __device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float G
   gth[16] += c[5] * FFA * G;
 }
 
-// runtime-indexed access to four per-thread registers without local memory
-__device__ __forceinline__ uint32_t sel4(const uint32_t* m, int l) {
-  return l == 0 ? m[0] : (l == 1 ? m[1] : (l == 2 ? m[2] : m[3]));
-}
-__device__ __forceinline__ void put4(uint32_t* m, int l, uint32_t v) {
-  if (l == 0) m[0] = v;
-  else if (l == 1) m[1] = v;
-  else if (l == 2) m[2] = v;
-  else m[3] = v;
-}
-
-// ---- epilogue halves shared by the main (columns [0,32)) and helper (columns [32,64)) warps --------------------------
-struct EpiCtx {
-  Bars* bars;
-  uint8_t* smem;
-  uint8_t* stash_cta;   // global: this CTA's activation scratch, [2 sets][L][ST_BLK]
-  uint32_t tmem, lane_base;
-  uint32_t f_cnt, b_cnt;   // completions of f_bar / b_bar observed so far
-  uint32_t ph;             // pull-back phases handed to the issuer so far (buffer = ph & 1)
-  int row, L;
-};
-
-// recomputation, hidden layer l of the item in scratch set `set`: a_l = relu(z_l) -> next layer's A operand (TMEM)
-// and -> the scratch as the weight gradients' BF16 operand image; returns this thread's ReLU mask
-template <int MODE, bool MAIN>
-__device__ __forceinline__ uint32_t fwd_epilogue(EpiCtx& e, int l, int set) {
-  tc::mbar_wait(&e.bars->f_bar, e.f_cnt & 1u);
-  e.f_cnt += 1u;
-  tc::fence_after_sync();
-  HODE_TL(300 + l);
+// ---- recomputation epilogue (F-epilogue warps; half 0 = columns [0,32), half 1 = [32,64)) ---------------------------
+// hidden layer l of the item in scratch set `set`: a_l = relu(z_l) -> next layer's A operand (TMEM) and -> the scratch
+// as the weight gradients' BF16 operand image.  16 columns at a time (these warps run on 88 registers).
+template <int MODE>
+__device__ __forceinline__ void fwd_epilogue(Bars* bars, uint32_t t_lane, int half, int row, uint8_t* blk, bool last,
+                                             bool arrive) {
+  const uint32_t col0 = (uint32_t)half * 32u;
   uint32_t v[32], lo[32];
-  const bool last = (l + 1 == e.L);
-  epilogue32_to_tmem<MODE>(e.tmem + e.lane_base, MAIN ? 0u : 32u, v, lo, !last);
-  if (!last) bar_arrive<BAR_F>();
-  const uint32_t mask = stash_store32(e.stash_cta + ((size_t)set * e.L + l) * ST_BLK, e.row, MAIN ? 0 : 1, v, lo);
+  epilogue32_to_tmem<MODE>(t_lane, col0, v, lo, !last);
+  if (arrive) bar_arrive<BAR_F, N_EPI>();
+  const uint32_t mask = stash_store32(blk, row, half, v, lo);
+  reinterpret_cast<uint32_t*>(blk + 2 * ST_PART)[half * TILE + row] = mask;
   tc::fence_proxy_async_all();   // generic-proxy global stores, read back by a bulk copy (async proxy)
-  tc::mbar_arrive(&e.bars->st_done[l]);
-  HODE_TL(310 + l);
-  return mask;
-}
-
-// pull-back, phase p (L..1) has delivered u_{p-1} in D_B: delta_{p-1} = u_{p-1} * relu'(a_{p-1}) -> delta image of
-// phase p-1; at p == 1 the main thread also writes the stage's input features as the input operand of dW_0
-template <bool MAIN>
-__device__ __forceinline__ void bwd_epilogue(EpiCtx& e, int p, uint32_t mask, const float* x9) {
-  tc::mbar_wait(&e.bars->b_bar, e.b_cnt & 1u);
-  e.b_cnt += 1u;
-  tc::fence_after_sync();
-  HODE_TL(320 + p);
-  uint32_t u[32];
-  HODE_TMEM_LD_X32(e.tmem + e.lane_base + TM_DB + (MAIN ? 0u : 32u), u);
-  tc::wait_ld();
-  float d[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) d[j] = ((mask >> j) & 1u) ? __uint_as_float(u[j]) : 0.f;
-  {
-    uint8_t* db = e.smem + OFF_DB + (e.ph & 1u) * DB_BYTES + ((MAIN ? 0 : 4)) * ST_GRP + e.row * 16;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 vh, vm;
-      bf16_split8(d + 8 * g, vh, vm);
-      *reinterpret_cast<uint4*>(db + g * ST_GRP) = vh;
-      *reinterpret_cast<uint4*>(db + g * ST_GRP + ST_PART) = vm;
-    }
-  }
-  if (MAIN && p == 1) {   // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
-    uint8_t* ab = e.smem + OFF_AB + (e.ph & 1u) * AB_BYTES + e.row * 16;
-    const float xb[8] = {x9[8], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-    uint4 vh, vm;
-    bf16_split8(x9, vh, vm);
-    *reinterpret_cast<uint4*>(ab) = vh;
-    *reinterpret_cast<uint4*>(ab + AB_PART) = vm;
-    bf16_split8(xb, vh, vm);
-    *reinterpret_cast<uint4*>(ab + ST_GRP) = vh;
-    *reinterpret_cast<uint4*>(ab + ST_GRP + AB_PART) = vm;
-  }
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  bar_arrive<BAR_B>();
-  e.ph += 1u;
-  HODE_TL(330 + p);
 }
 
 // items of one tile: iteration it = 0..n_iter-1 (one accepted step each, last step first), stages i = N-1 .. i_lo(it).
@@ -337,10 +280,12 @@ struct AdjTcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// grid = (ctas per parameter set, S), block = 384: warps 0-3 main, 4-7 helpers, 8 issuer, 9-11 loaders; 1 CTA / SM
+// grid = (ctas per parameter set, S), block = 768 = 6 warpgroups, 1 CTA / SM:
+//   WG0 main | WG1, WG2 recomputation epilogues (columns [0,32) / [32,64)) | WG3, WG4 pull-back epilogues |
+//   WG5: warp 20 F issuer + forward-weight loads, 21 B issuer, 22 W^T loader, 23 activation loader
 // ---------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
+__global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const AdjTcArgs G) {
   extern __shared__ __align__(128) uint8_t smem_raw[];   // (operand descriptors without swizzle need 16-byte alignment)
   __shared__ __align__(8) Bars bars;
   __shared__ uint32_t tmem_base_s;
@@ -349,7 +294,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
   const RolloutArgs& A = G.R;
   const int tid = threadIdx.x, lane_id = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const bool main_role = warp < 4, helper = warp >= 4 && warp < 8;
+  const int wg = warp >> 2;
   const int wq = warp & 3, row = tid & 127;
   const int s = blockIdx.y, T = A.T, L = A.L;
   const int solver = A.solver == HODE_SOLVER_RK4 ? 0 : 1;
@@ -357,11 +302,12 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
   const bool fsal = solver == 1;   // (the records of this path always carry the stage derivatives)
   const int i0 = fsal ? 1 : 0;
 
-  float4* rec_sh = reinterpret_cast<float4*>(smem_raw + OFF_REC);
   float* t_sh_buf = reinterpret_cast<float*>(smem_raw + OFF_T);
   if (tid == 0) {
     tc::mbar_init(&bars.f_bar, 1);
+    tc::mbar_init(&bars.fl_bar, 1);
     tc::mbar_init(&bars.b_bar, 1);
+    tc::mbar_init(&bars.gx_bar, 1);
     tc::mbar_init(&bars.wf_full, 1);
     tc::mbar_init(&bars.wf_free, 1);
     for (int i = 0; i < 2; ++i) {
@@ -370,7 +316,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
       tc::mbar_init(&bars.ab_full[i], 1);
       tc::mbar_init(&bars.ab_free[i], 1);
     }
-    for (int i = 0; i < MAXL; ++i) tc::mbar_init(&bars.st_done[i], 2 * TILE);
+    for (int i = 0; i < MAXL; ++i) { tc::mbar_init(&bars.st_done[0][i], 2 * TILE); tc::mbar_init(&bars.st_done[1][i], 2 * TILE); }
     tc::mbar_init(&bars.done, 1);
     tc::fence_mbar_init();
   }
@@ -380,7 +326,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     for (int i = tid; i < T; i += blockDim.x) t_sh_buf[i] = A.t_obs[i];
     t_shared = t_sh_buf;
   }
-  if (main_role) {
+  if (wg == 0) {
     // the constant-1 input feature of the weight gradients (its accumulator column is the bias gradient):
     // group 8 of both input-operand buffers = [1, 0 x 7] (hi) / 0 (mid); the bulk copies only touch groups 0..7
 #pragma unroll
@@ -397,7 +343,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
 
   const uint32_t tmem = tmem_base_s;
   const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-  if (main_role) {
+  if (wg == 0) {
     uint32_t ones[8] = {0x3F800000u, 0x3F800000u, 0u, 0u, 0u, 0u, 0u, 0u};
     HODE_TMEM_ST_X8(tmem + lane_base + TM_ONES, ones);
     tc::wait_st();
@@ -417,123 +363,90 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     __syncthreads();
     return s_nmax;
   };
-  bool have = false;   // this CTA has issued at least one item: the accumulators are initialised
+  auto tile_items = [&](int n_iter) -> int {
+    int items = 0;
+    for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
+    return items;
+  };
 
   // Roles: each entirely inside its own branch so that ptxas allocates registers against the role's budget.
-  if (helper) {
-    // ================================ helper warps: the other half of every epilogue ========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;" ::: "memory");
-    EpiCtx e{&bars, smem_raw, stash0, tmem, lane_base, 0u, 0u, 0u, row, L};
-    uint32_t m_f = 0u, mcur[4] = {0u, 0u, 0u, 0u}, mnext[4] = {0u, 0u, 0u, 0u};
+  if (wg == 1 || wg == 2) {
+    // ================================ recomputation epilogues ==================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;" ::: "memory");
+    const int half = wg - 1;
+    uint32_t f_cnt = 0u, m_f = 0u;
     for (int tk = tile_beg; tk < tile_end; ++tk) {
       const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-      if (n_iter == 0) continue;
-      have = true;
-      bar_arrive<BAR_F>();   // first item's input operand (written by the main threads)
+      const int items = tile_items(n_iter);
 #pragma unroll 1
-      for (int l = 0; l < L; ++l) put4(mnext, l, fwd_epilogue<MODE, false>(e, l, (int)(m_f & 1u)));
-      m_f += 1u;
-      for (int it = 0; it < n_iter; ++it) {
-        const int i_lo = item_i_lo(it, n_iter, N, i0, fsal);
+      for (int m = 0; m < items; ++m) {
 #pragma unroll 1
-        for (int i = N - 1; i >= i_lo; --i) {
-          const bool has_F = !(it == n_iter - 1 && i == i_lo);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) mcur[l] = mnext[l];
-          bar_arrive<BAR_B>();   // delta_L (main threads)
-          e.ph += 1u;
-          if (has_F) bar_arrive<BAR_F>();
-#pragma unroll 1
-          for (int l = 0; l < L; ++l) {
-            if (has_F) put4(mnext, l, fwd_epilogue<MODE, false>(e, l, (int)(m_f & 1u)));
-            bwd_epilogue<false>(e, L - l, sel4(mcur, L - l - 1), nullptr);
-          }
-          tc::mbar_wait(&bars.b_bar, e.b_cnt & 1u);   // g_x: nothing to read, but the phase must be observed
-          e.b_cnt += 1u;
-          if (has_F) m_f += 1u;
+        for (int l = 0; l < L; ++l) {
+          tc::mbar_wait(&bars.f_bar, f_cnt & 1u);
+          f_cnt += 1u;
+          tc::fence_after_sync();
+          fwd_epilogue<MODE>(&bars, tmem + lane_base, half, row, stash0 + ((size_t)(m_f & 1u) * L + l) * ST_BLK, l + 1 == L, true);
+          tc::mbar_arrive(&bars.st_done[m_f & 1u][l]);
         }
+        m_f += 1u;
       }
     }
-  } else if (!main_role) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
-    if (warp == 8) {
-      // ================================ MMA issuer ============================================================
-      const uint32_t base = tc::smem_u32(smem_raw);
-      const uint32_t wf_s = base + OFF_WF;
-      uint32_t n_f = 0u, ph = 0u, first = 1u;
-      auto issue_F = [&](int l) {
-        bar_wait<BAR_F>();
-        tc::mbar_wait(&bars.wf_full, n_f & 1u);
-        if (tc::elect_one()) {
-          tc::fence_after_sync();
-          if (l == 0) issue_layer<MODE, H, 16, false>(tmem, wf_s, wf_s + 1024u * 4u, 0u);
-          else issue_layer<MODE, H, 64, true>(tmem, wf_s, wf_s + 4096u * 4u, wf_s + 8192u * 4u);
-          tc::mma_commit(&bars.f_bar);
-          tc::mma_commit(&bars.wf_free);
-        }
-        __syncwarp();
-        n_f += 1u;
-      };
-      // phase q:  u_{q-1} = delta_q W_q (delta image x W_q^T slot)  and  dW_q += delta_q^T [a_{q-1} | 1]
-      // (a_{-1} = the stage's input features x, u_{-1} = the cotangent of x)
-      auto issue_B = [&](int q) {
-        const uint32_t buf = ph & 1u, par = (ph >> 1) & 1u;
-        const uint32_t ws = base + OFF_WT + buf * WT_BYTES;
-        const uint32_t a_hi = base + OFF_AB + buf * AB_BYTES, a_mid = a_hi + AB_PART;
-        const uint32_t d_hi = base + OFF_DB + buf * DB_BYTES, d_mid = d_hi + ST_PART;
-        bar_wait<BAR_B>();
-        tc::mbar_wait(&bars.wt_full[buf], par);
-        if (tc::elect_one()) {
-          tc::fence_after_sync();
-          if (q == L) issue_u<H, 1>(tmem + TM_DB, d_hi, d_mid, ws, ws + 2048u);          // u_{L-1} = delta_L W_out (K = 16)
-          else if (q >= 1) issue_u<H, 4>(tmem + TM_DB, d_hi, d_mid, ws, ws + 8192u);     // u_{q-1} = delta_q W_q
-          else issue_u<16, 4>(tmem + TM_DB, d_hi, d_mid, ws, ws + 2048u);                // g_x = delta_0 W_0
-          tc::mma_commit(&bars.b_bar);
-          tc::mma_commit(&bars.wt_free[buf]);
-        }
-        __syncwarp();
-        tc::mbar_wait(&bars.ab_full[buf], par);
-        if (tc::elect_one()) {
-          tc::fence_after_sync();
-          // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
-          if (q == L) issue_dw<128, 16>(tmem + DW_O, a_hi, a_mid, d_hi, d_mid, first);
-          else if (q >= 1) issue_dw<64, 72>(tmem + DW_H0 + DW_HS * (uint32_t)(q - 1), d_hi, d_mid, a_hi, a_mid, first);
-          else issue_dw<64, 16>(tmem + DW_0, d_hi, d_mid, a_hi, a_mid, first);
-          tc::mma_commit(&bars.ab_free[buf]);
-        }
-        __syncwarp();
-        ph += 1u;
-      };
-      for (int tk = tile_beg; tk < tile_end; ++tk) {
-        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-        if (n_iter == 0) continue;
-        have = true;
+  } else if (wg == 3 || wg == 4) {
+    // ================================ pull-back epilogues ======================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+    const int half = wg - 3;
+    uint32_t b_cnt = 0u, ph = 0u;
+    for (int tk = tile_beg; tk < tile_end; ++tk) {
+      const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+      const int items = tile_items(n_iter);
 #pragma unroll 1
-        for (int l = 0; l < L; ++l) issue_F(l);
-        for (int it = 0; it < n_iter; ++it) {
-          const int i_lo = item_i_lo(it, n_iter, N, i0, fsal);
+      for (int m = 0; m < items; ++m) {
+        // phase p = L..1 has delivered u_{p-1} in D_B: delta_{p-1} = u_{p-1} * relu'(a_{p-1}) -> delta image of phase p-1
 #pragma unroll 1
-          for (int i = N - 1; i >= i_lo; --i) {
-            const bool has_F = !(it == n_iter - 1 && i == i_lo);
-            issue_B(L);
-            if (has_F) issue_F(0);
-#pragma unroll 1
-            for (int l = 0; l < L; ++l) {
-              if (has_F && l + 1 < L) issue_F(l + 1);
-              issue_B(L - 1 - l);
+        for (int p = L; p >= 1; --p) {
+          const uint32_t buf = ph & 1u;
+          tc::mbar_wait(&bars.b_bar, b_cnt & 1u);
+          b_cnt += 1u;
+          tc::fence_after_sync();
+          // ReLU mask of a_{p-1}: rides with the stashed operand of this phase's weight gradient
+          tc::mbar_wait(&bars.ab_full[buf], (ph >> 1) & 1u);
+          const uint32_t mask = reinterpret_cast<const uint32_t*>(smem_raw + OFF_AB + buf * AB_BYTES + 2 * AB_PART)[half * TILE + row];
+          uint8_t* db = smem_raw + OFF_DB + ((ph + 1u) & 1u) * DB_BYTES + (half * 4) * ST_GRP + row * 16;
+#pragma unroll
+          for (int c16 = 0; c16 < 2; ++c16) {
+            uint32_t u[16];
+            HODE_TMEM_LD_X16(tmem + lane_base + TM_DB + (uint32_t)(half * 32 + c16 * 16), u);
+            tc::wait_ld();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float d[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] = ((mask >> (c16 * 16 + g * 8 + j)) & 1u) ? __uint_as_float(u[g * 8 + j]) : 0.f;
+              uint4 vh, vm;
+              bf16_split8(d, vh, vm);
+              *reinterpret_cast<uint4*>(db + (c16 * 2 + g) * ST_GRP) = vh;
+              *reinterpret_cast<uint4*>(db + (c16 * 2 + g) * ST_GRP + ST_PART) = vm;
             }
-            first = 0u;
           }
+          tc::fence_proxy_async();
+          tc::fence_before_sync();
+          bar_arrive<BAR_B, N_EPI>();
+          ph += 1u;
         }
+        tc::mbar_wait(&bars.b_bar, b_cnt & 1u);   // g_x (read by the main warps): the phase must be observed
+        b_cnt += 1u;
+        ph += 1u;
       }
-      if (tc::elect_one()) tc::mma_commit(&bars.done);   // every MMA of this CTA has completed when this arrives
-      __syncwarp();
-    } else if (warp == 9) {
-      // ================================ loader: forward weights, one layer at a time =========================
-      uint32_t n = 0u;
+    }
+  } else if (wg == 5) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+    const uint32_t base = tc::smem_u32(smem_raw);
+    if (warp == 20) {
+      // ================================ F issuer (+ forward weights, one layer at a time) ========================
+      const uint32_t wf_s = base + OFF_WF;
       const int bias_off = (int)(IMG_L0 + (uint32_t)(L - 1) * IMG_HID + IMG_OUT);
-      auto load_layer = [&](int l) {
-        if (n >= 1u) tc::mbar_wait(&bars.wf_free, (n - 1u) & 1u);
+      uint32_t n_f = 0u;
+      auto load_layer = [&](int l) {   // the slot is free: its previous user's MMAs have completed
         if (lane_id == 0) {
           uint8_t* dst = smem_raw + OFF_WF;
           if (l == 0) {
@@ -546,87 +459,163 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
           }
         }
         __syncwarp();
-        n += 1u;
       };
+      bool any = false;
       for (int tk = tile_beg; tk < tile_end; ++tk) {
         const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-        if (n_iter == 0) continue;
-        int items = 0;
-        for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
-#pragma unroll 1
-        for (int m = 0; m < items; ++m)
-#pragma unroll 1
-          for (int l = 0; l < L; ++l) load_layer(l);
-      }
-    } else if (warp == 10) {
-      // ================================ loader: W_q^T of every pull-back phase ================================
-      uint32_t ph = 0u;
-      auto load_wt = [&](int q) {
-        const uint32_t buf = ph & 1u, k = ph >> 1;
-        if (k >= 1u) tc::mbar_wait(&bars.wt_free[buf], (k - 1u) & 1u);
-        if (lane_id == 0) {
-          int off, floats;
-          if (q == L) { off = 0; floats = 1024; }
-          else if (q >= 1) { off = 1024 + (L - 1 - q) * 4096; floats = 4096; }
-          else { off = 1024 + (L - 1) * 4096; floats = 1024; }
-          tc::mbar_expect_tx(&bars.wt_full[buf], (uint32_t)floats * 4u);
-          tc::bulk_g2s(smem_raw + OFF_WT + buf * WT_BYTES, bwd_src + off, (uint32_t)floats * 4u, &bars.wt_full[buf]);
-        }
-        __syncwarp();
-        ph += 1u;
-      };
-      for (int tk = tile_beg; tk < tile_end; ++tk) {
-        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-        if (n_iter == 0) continue;
-        int items = 0;
-        for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
-#pragma unroll 1
-        for (int m = 0; m < items; ++m)
-#pragma unroll 1
-          for (int q = L; q >= 0; --q) load_wt(q);
-      }
-    } else {
-      // ================================ loader: stashed activations a_{q-1} of every pull-back phase ============
-      uint32_t ph = 0u, m_all = 0u;
-      auto load_ab = [&](int q) {
-        const uint32_t buf = ph & 1u, k = ph >> 1;
-        if (q >= 1) tc::mbar_wait(&bars.st_done[q - 1], m_all & 1u);   // written by the epilogue threads (generic proxy + fence)
-        if (k >= 1u) tc::mbar_wait(&bars.ab_free[buf], (k - 1u) & 1u);
-        if (lane_id == 0) {
-          if (q >= 1) {
-            const uint8_t* src = stash0 + ((size_t)(m_all & 1u) * L + (q - 1)) * ST_BLK;
-            uint8_t* dst = smem_raw + OFF_AB + buf * AB_BYTES;
-            tc::mbar_expect_tx(&bars.ab_full[buf], 2u * ST_PART);
-            tc::bulk_g2s(dst, src, ST_PART, &bars.ab_full[buf]);
-            tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, &bars.ab_full[buf]);
-          } else {
-            tc::mbar_arrive(&bars.ab_full[buf]);   // phase 0: the main threads write x themselves
-          }
-        }
-        __syncwarp();
-        ph += 1u;
-      };
-      for (int tk = tile_beg; tk < tile_end; ++tk) {
-        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
-        if (n_iter == 0) continue;
-        int items = 0;
-        for (int it = 0; it < n_iter; ++it) items += N - item_i_lo(it, n_iter, N, i0, fsal);
+        const int items = tile_items(n_iter);
 #pragma unroll 1
         for (int m = 0; m < items; ++m) {
 #pragma unroll 1
-          for (int q = L; q >= 0; --q) load_ab(q);
+          for (int l = 0; l < L; ++l) {
+            if (n_f == 0u) load_layer(0);   // (every later load is started right after its predecessor's MMAs, below)
+            if (l == 0) {
+              bar_wait<BAR_X, N_MAIN>();               // the item's input operand (main warps)
+              if (any) bar_wait<BAR_F, N_EPI>();       // the previous item's last accumulator has been read
+            } else {
+              bar_wait<BAR_F, N_EPI>();
+            }
+            tc::mbar_wait(&bars.wf_full, n_f & 1u);
+            if (tc::elect_one()) {
+              tc::fence_after_sync();
+              if (l == 0) issue_layer<MODE, H, 16, false>(tmem, wf_s, wf_s + 1024u * 4u, 0u);
+              else issue_layer<MODE, H, 64, true>(tmem, wf_s, wf_s + 4096u * 4u, wf_s + 8192u * 4u);
+              tc::mma_commit(&bars.f_bar);
+              tc::mma_commit(&bars.wf_free);
+              if (l + 1 == L) tc::mma_commit(&bars.fl_bar);
+            }
+            __syncwarp();
+            any = true;
+            // next layer's weights as soon as this layer's MMAs have read theirs (the epilogue runs meanwhile)
+            const bool more = !(tk == tile_end - 1 && m == items - 1 && l == L - 1);
+            tc::mbar_wait(&bars.wf_free, n_f & 1u);
+            if (more) load_layer(l + 1 == L ? 0 : l + 1);
+            n_f += 1u;
+          }
+        }
+      }
+      if (any) bar_wait<BAR_F, N_EPI>();   // the last item's last arrival
+    } else if (warp == 21) {
+      // ================================ B issuer ===================================================================
+      // phase q:  u_{q-1} = delta_q W_q (delta image x W_q^T slot)  and  dW_q += delta_q^T [a_{q-1} | 1]
+      // (a_{-1} = the stage's input features x, u_{-1} = the cotangent of x)
+      uint32_t ph = 0u, first = 1u, m_b = 0u;
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        const int items = tile_items(n_iter);
+#pragma unroll 1
+        for (int m = 0; m < items; ++m) {
+#pragma unroll 1
+          for (int q = L; q >= 0; --q) {
+            const uint32_t buf = ph & 1u, par = (ph >> 1) & 1u;
+            const uint32_t ws = base + OFF_WT + buf * WT_BYTES;
+            const uint32_t a_hi = base + OFF_AB + buf * AB_BYTES, a_mid = a_hi + AB_PART;
+            const uint32_t x_hi = base + OFF_XB + (m_b & 1u) * XB_BYTES, x_mid = x_hi + XB_PART;
+            const uint32_t d_hi = base + OFF_DB + buf * DB_BYTES, d_mid = d_hi + ST_PART;
+            if (q == L) bar_wait<BAR_BX, N_MAIN>();
+            else bar_wait<BAR_B, N_EPI>();
+            tc::mbar_wait(&bars.wt_full[buf], par);
+            if (tc::elect_one()) {
+              tc::fence_after_sync();
+              if (q == L) issue_u<H, 1>(tmem + TM_DB, d_hi, d_mid, ws, ws + 2048u);          // u_{L-1} = delta_L W_out (K = 16)
+              else if (q >= 1) issue_u<H, 4>(tmem + TM_DB, d_hi, d_mid, ws, ws + 8192u);     // u_{q-1} = delta_q W_q
+              else issue_u<16, 4>(tmem + TM_DB, d_hi, d_mid, ws, ws + 2048u);                // g_x = delta_0 W_0
+              tc::mma_commit(&bars.b_bar);
+              tc::mma_commit(&bars.wt_free[buf]);
+              if (q == 0) tc::mma_commit(&bars.gx_bar);
+            }
+            __syncwarp();
+            tc::mbar_wait(&bars.ab_full[buf], par);
+            if (tc::elect_one()) {
+              tc::fence_after_sync();
+              // dW_out^T [in k][out n] = [a_{L-1} | 1]^T delta_L;  dW_q += delta_q^T [a_{q-1} | 1];  dW_0 += delta_0^T [x | 1]
+              if (q == L) issue_dw<128, 16>(tmem + DW_O, a_hi, a_mid, d_hi, d_mid, first);
+              else if (q >= 1) issue_dw<64, 72>(tmem + DW_H0 + DW_HS * (uint32_t)(q - 1), d_hi, d_mid, a_hi, a_mid, first);
+              else issue_dw<64, 16>(tmem + DW_0, d_hi, d_mid, x_hi, x_mid, first);
+              tc::mma_commit(&bars.ab_free[buf]);
+            }
+            __syncwarp();
+            ph += 1u;
+          }
+          first = 0u;
+          m_b += 1u;
+        }
+      }
+      if (tc::elect_one()) tc::mma_commit(&bars.done);   // every pull-back MMA of this CTA has completed when this arrives
+      __syncwarp();
+    } else if (warp == 22) {
+      // ================================ loader: W_q^T of every pull-back phase ====================================
+      uint32_t ph = 0u;
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        const int items = tile_items(n_iter);
+#pragma unroll 1
+        for (int m = 0; m < items; ++m) {
+#pragma unroll 1
+          for (int q = L; q >= 0; --q) {
+            const uint32_t buf = ph & 1u, k = ph >> 1;
+            if (k >= 1u) tc::mbar_wait(&bars.wt_free[buf], (k - 1u) & 1u);
+            if (lane_id == 0) {
+              int off, floats;
+              if (q == L) { off = 0; floats = 1024; }
+              else if (q >= 1) { off = 1024 + (L - 1 - q) * 4096; floats = 4096; }
+              else { off = 1024 + (L - 1) * 4096; floats = 1024; }
+              tc::mbar_expect_tx(&bars.wt_full[buf], (uint32_t)floats * 4u);
+              tc::bulk_g2s(smem_raw + OFF_WT + buf * WT_BYTES, bwd_src + off, (uint32_t)floats * 4u, &bars.wt_full[buf]);
+            }
+            __syncwarp();
+            ph += 1u;
+          }
+        }
+      }
+    } else {
+      // ================================ loader: stashed activations a_{q-1} (+ ReLU masks) of every phase ==========
+      uint32_t ph = 0u, m_all = 0u;
+      for (int tk = tile_beg; tk < tile_end; ++tk) {
+        const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
+        const int items = tile_items(n_iter);
+#pragma unroll 1
+        for (int m = 0; m < items; ++m) {
+#pragma unroll 1
+          for (int q = L; q >= 0; --q) {
+            const uint32_t buf = ph & 1u, k = ph >> 1;
+            // written by the F-epilogue warps (generic proxy + fence); item m_all is the (m_all >> 1)-th user of its set
+            if (q >= 1) tc::mbar_wait(&bars.st_done[m_all & 1u][q - 1], (m_all >> 1) & 1u);
+            if (k >= 1u) {
+              tc::mbar_wait(&bars.ab_free[buf], (k - 1u) & 1u);             // the buffer's previous weight-gradient MMAs are done
+              // ... and its ReLU masks have been read: the delta chain of phase ph - 1 is only issued after the
+              // epilogue of phase ph - 2 (which read them) has arrived
+              tc::mbar_wait(&bars.wt_free[(ph - 1u) & 1u], ((ph - 1u) >> 1) & 1u);
+            }
+            if (lane_id == 0) {
+              if (q >= 1) {
+                const uint8_t* src = stash0 + ((size_t)(m_all & 1u) * L + (q - 1)) * ST_BLK;
+                uint8_t* dst = smem_raw + OFF_AB + buf * AB_BYTES;
+                tc::mbar_expect_tx(&bars.ab_full[buf], 2u * ST_PART + 1024u);
+                tc::bulk_g2s(dst, src, ST_PART, &bars.ab_full[buf]);
+                tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, &bars.ab_full[buf]);
+                tc::bulk_g2s(dst + 2 * AB_PART, src + 2 * ST_PART, 1024u, &bars.ab_full[buf]);
+              } else {
+                tc::mbar_arrive(&bars.ab_full[buf]);   // phase 0: its input operand is x (XB, written by the main warps)
+              }
+            }
+            __syncwarp();
+            ph += 1u;
+          }
           m_all += 1u;
         }
       }
     }
   } else {
     // ================================ main warps: one trajectory per thread ====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
-    EpiCtx e{&bars, smem_raw, stash0, tmem, lane_base, 0u, 0u, 0u, row, L};
-    uint32_t m_f = 0u, mcur[4] = {0u, 0u, 0u, 0u}, mnext[4] = {0u, 0u, 0u, 0u};
+    // register pool of the CTA = 768 threads x 80 registers at launch; after the role split it must not grow:
+    // 128 x 168 (main) + 256 x 88 (F epilogues) + 256 x 56 (B epilogues) + 128 x 24 (issuers, loaders) = 61 440
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
+    uint32_t m_all = 0u;   // items handed to the chains so far (recomputation runs one item ahead of the pull-back)
     const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
     const bool gd_present = A.in_mode[HODE_CH_GD] != HODE_IN_ABSENT;
     const int nsub = A.n_substeps > 0 ? A.n_substeps : 1;
+    bool have = false;
     float gth[HODE_N_THETA];
 #pragma unroll
     for (int i = 0; i < HODE_N_THETA; ++i) gth[i] = 0.f;
@@ -673,6 +662,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
 #pragma unroll
       for (int i = 0; i < NS; ++i) { lam[i] = 0.f; carry[i] = 0.f; y_later[i] = 0.f; }
       double t_later = 0.0;
+      bool later_valid = false;   // y_later / t_later hold the start of the step pulled back one iteration ago
       int ei = T - 1;
 
       // ---- the step being pulled back ("context") and the input piece of it / of the next (earlier) step --------
@@ -717,8 +707,8 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
           gd = input_channel(in, HODE_CH_GD, t32, lo);
         }
       };
-      // record of step sidx -> context; chunk(c) yields 16-byte chunk c of the record
-      auto set_ctx = [&](int it, auto&& chunk) {
+      // record of step sidx -> context (the records come from L2: the next one is prefetched a step ahead)
+      auto set_ctx = [&](int it) {
         const int sidx = n - 1 - it;
         real = ok && sidx >= 0;
         act = real || (fsal && ok && sidx == -1);   // sidx == -1: the zero-length step at (t0, y0)
@@ -730,10 +720,11 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
           for (int j = 0; j < 6; ++j) k[j][cc] = 0.f;
         }
         if (real) {
+          const float4* r4 = reinterpret_cast<const float4*>(step_rec(A, unit, sidx));
           float r[HODE_REC_FLOATS_K];
 #pragma unroll
-          for (int c4 = 0; c4 < REC_CHUNKS; ++c4) {
-            const float4 v = chunk(c4);
+          for (int c4 = 0; c4 < HODE_REC_FLOATS_K / 4; ++c4) {
+            const float4 v = r4[c4];
             r[4 * c4] = v.x; r[4 * c4 + 1] = v.y; r[4 * c4 + 2] = v.z; r[4 * c4 + 3] = v.w;
           }
           t = __longlong_as_double(((long long)__float_as_int(r[1]) << 32) | (long long)(unsigned)__float_as_int(r[0]));
@@ -752,13 +743,11 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
           }
         }
         hf = (float)h;
-        // the record of the next iteration's step: into shared memory while this step is pulled back
-        if (ok && sidx >= 1) {
-          const float* nxt = step_rec(A, unit, sidx - 1);
-#pragma unroll
-          for (int c4 = 0; c4 < REC_CHUNKS; ++c4) tc::cp_async16(&rec_sh[c4 * TILE + row], nxt + 4 * c4);
+        if (ok && sidx >= 1) {   // the next iteration's record: pull it into L2 now (192 bytes: two or three 64-byte halves of lines)
+          const char* nxt = reinterpret_cast<const char*>(step_rec(A, unit, sidx - 1));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
         }
-        tc::cp_async_commit();
       };
       // input features of stage i of the current step: x = [t_i, ys_i, ys_i[3], tVNS(t_i)]
       auto stage_x = [&](int i, float* ys, float* x, float& gd) {
@@ -768,6 +757,11 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
 #pragma unroll
           for (int j = 0; j < 6; ++j) a_ = fmaf(kA[solver][i][j], k[j][cc], a_);   // zero for j >= i
           ys[cc] = fmaf(hf, a_, y[cc]);
+        }
+        if (fsal && i == N - 1 && real && later_valid) {
+          // stage 7 is evaluated at the step's result = the state the later step started from (its record), bit for bit
+#pragma unroll
+          for (int cc = 0; cc < NS; ++cc) ys[cc] = y_later[cc];
         }
         const float ci = kC[solver][i];
         const double te = (i == 0) ? t : (ci == 1.0f ? t_new : t + (double)ci * h);
@@ -781,25 +775,26 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         x[7] = ys[3];
         x[8] = tvns;
       };
+      // hand the recomputation of an item to the F chain: its input operand -> TMEM (the A operand region is free
+      // once the previous item's last layer has completed)
+      auto start_F = [&](const float* xf) {
+        if (m_all >= 1u) tc::mbar_wait(&bars.fl_bar, (m_all - 1u) & 1u);
+        tc::fence_after_sync();
+        __syncwarp();
+        store_input_operand<MODE>(tmem + lane_base, xf);
+        bar_arrive<BAR_X, N_MAIN>();
+        m_all += 1u;
+      };
 
-      // ---- first iteration's context straight from global memory; its top stage is recomputed un-overlapped --------
-      {
-        const int sidx0 = n - 1;
-        const float4* r4 = reinterpret_cast<const float4*>(step_rec(A, unit, sidx0 > 0 ? sidx0 : 0));
-        set_ctx(0, [&](int c4) { return r4[c4]; });
-        piece_for(t, pc_t1, pc_inv, pc_v1, pc_dv);
-      }
-      bool later_valid = false;   // y_later / t_later hold the start of the step pulled back one iteration ago
+      // ---- first iteration's context; its top stage goes to the recomputation chain right away --------------------
+      set_ctx(0);
+      piece_for(t, pc_t1, pc_inv, pc_v1, pc_dv);
       {
         float ys[NS], x[HODE_NN_IN], gd;
         stage_x(N - 1, ys, x, gd);
-        __syncwarp();
-        store_input_operand<MODE>(tmem + lane_base, x);
-        bar_arrive<BAR_F>();
-#pragma unroll 1
-        for (int l = 0; l < L; ++l) put4(mnext, l, fwd_epilogue<MODE, true>(e, l, (int)(m_f & 1u)));
-        m_f += 1u;
+        start_F(x);
       }
+      uint32_t m_b = m_all - 1u;   // index of the item whose pull-back starts next
 
       for (int it = 0; it < n_iter; ++it) {
         HODE_TL(200);
@@ -863,16 +858,8 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
         for (int i = N - 1; i >= i_lo; --i) {
           HODE_TL(201);
           const bool has_F = !(it == n_iter - 1 && i == i_lo);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) mcur[l] = mnext[l];
           float ys[NS], x[HODE_NN_IN], gys[NS], gki[NS], gdi;
           stage_x(i, ys, x, gdi);
-          if (fsal && i == N - 1 && real && later_valid) {
-            // stage 7 is evaluated at the step's result = the state the later step started from (its record), bit for bit
-#pragma unroll
-            for (int cc = 0; cc < NS; ++cc) { ys[cc] = y_later[cc]; x[1 + cc] = y_later[cc]; }
-            x[7] = y_later[3];
-          }
 #pragma unroll
           for (int cc = 0; cc < NS; ++cc) { gys[cc] = 0.f; gki[cc] = 0.f; }
 #pragma unroll
@@ -882,22 +869,32 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
               for (int cc = 0; cc < NS; ++cc) gki[cc] = gk[jj][cc];
             }
           }
-          // ---- pull-back prologue: delta_L = the cotangent of the 6 network outputs -> phase L --------------------
+          // ---- pull-back of this item: delta_L = the cotangent of the 6 network outputs, and x as the input operand
+          // of dW_0 -> B chain (the chain's previous item is complete: its g_x has been read below)
           {
             float d[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[j] = (j < NS) ? gki[j] : 0.f;
-            uint8_t* db = smem_raw + OFF_DB + (e.ph & 1u) * DB_BYTES + row * 16;
+            const uint32_t ph0 = m_b * (uint32_t)(L + 1);   // first phase of this item (buffers alternate by phase)
+            uint8_t* db = smem_raw + OFF_DB + (ph0 & 1u) * DB_BYTES + row * 16;
             uint4 vh, vm;
             bf16_split8(d, vh, vm);
             *reinterpret_cast<uint4*>(db) = vh;
             *reinterpret_cast<uint4*>(db + ST_PART) = vm;
             *reinterpret_cast<uint4*>(db + ST_GRP) = make_uint4(0u, 0u, 0u, 0u);   // N = 16: features 8..15 are zero
             *reinterpret_cast<uint4*>(db + ST_GRP + ST_PART) = make_uint4(0u, 0u, 0u, 0u);
+            // inputs of layer 0: the 9 stage features, zero padding, feature 15 = 1 (bias column)
+            uint8_t* xb = smem_raw + OFF_XB + (m_b & 1u) * XB_BYTES + row * 16;
+            const float xt[8] = {x[8], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+            bf16_split8(x, vh, vm);
+            *reinterpret_cast<uint4*>(xb) = vh;
+            *reinterpret_cast<uint4*>(xb + XB_PART) = vm;
+            bf16_split8(xt, vh, vm);
+            *reinterpret_cast<uint4*>(xb + ST_GRP) = vh;
+            *reinterpret_cast<uint4*>(xb + ST_GRP + XB_PART) = vm;
             tc::fence_proxy_async();
             tc::fence_before_sync();
-            bar_arrive<BAR_B>();
-            e.ph += 1u;
+            bar_arrive<BAR_BX, N_MAIN>();
           }
           HODE_TL(202);
           // ---- recomputation of the NEXT item: its input operand ---------------------------------------------------
@@ -918,16 +915,21 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
                 for (int cc = 0; cc < NS; ++cc) ysf[cc] = y[cc];
                 te = t;
               } else {
-                // RK4: stage 4 at y' + h' k3', t' + h' from the prefetched record
-                tc::cp_async_wait_all();
-                const float4 c0 = rec_sh[0 * TILE + row], c1 = rec_sh[1 * TILE + row], c2 = rec_sh[2 * TILE + row];
-                const float4 c5 = rec_sh[5 * TILE + row], c6 = rec_sh[6 * TILE + row];
-                const double tp = __longlong_as_double(((long long)__float_as_int(c0.y) << 32) | (long long)(unsigned)__float_as_int(c0.x));
-                const float hp = c0.z;
-                const float yp[NS] = {c1.x, c1.y, c1.z, c1.w, c2.x, c2.y};
-                const float k3[NS] = {c5.z, c5.w, c6.x, c6.y, c6.z, c6.w};
+                // RK4: stage 4 at y' + h' k3', t' + h' from the (prefetched) next record
+                double tp = t_first;
+                float hp = 0.f, yp[NS], k3[NS];
 #pragma unroll
-                for (int cc = 0; cc < NS; ++cc) ysf[cc] = fmaf(hp, fmaf(1.0f, k3[cc], 0.f), yp[cc]);
+                for (int cc = 0; cc < NS; ++cc) { yp[cc] = 0.f; k3[cc] = 0.f; }
+                if (ok && sn >= 0) {
+                  const float4* r4 = reinterpret_cast<const float4*>(step_rec(A, unit, sn));
+                  const float4 c0 = r4[0], c1 = r4[1], c2 = r4[2], c5 = r4[5], c6 = r4[6];
+                  tp = __longlong_as_double(((long long)__float_as_int(c0.y) << 32) | (long long)(unsigned)__float_as_int(c0.x));
+                  hp = c0.z;
+                  yp[0] = c1.x; yp[1] = c1.y; yp[2] = c1.z; yp[3] = c1.w; yp[4] = c2.x; yp[5] = c2.y;
+                  k3[0] = c5.z; k3[1] = c5.w; k3[2] = c6.x; k3[3] = c6.y; k3[4] = c6.z; k3[5] = c6.w;
+                }
+#pragma unroll
+                for (int cc = 0; cc < NS; ++cc) ysf[cc] = fmaf(hp, k3[cc], yp[cc]);
                 te = tp + (double)hp;
               }
               const float t32 = (float)te;
@@ -939,33 +941,21 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
               xf[7] = act_n ? ysf[3] : 0.f;
               xf[8] = act_n ? tvns : 0.f;
             }
-            __syncwarp();
-            store_input_operand<MODE>(tmem + lane_base, xf);
-            bar_arrive<BAR_F>();
+            start_F(xf);
           }
           HODE_TL(203);
-          // ---- behind the first MMA chains: the mechanistic VJP, and (once per step) the next step's input piece ----
+          // ---- while the chains run: the mechanistic VJP, and (once per step) the next step's input piece ------------
           mech_vjp(th, ys, gdi, gd_present, gki, gys, gth);
           if (i == N - 2 && it + 1 < n_iter) {
             const int sn = sidx - 1;
             double tn = t_first;
-            if (ok && sn >= 0) {
-              tc::cp_async_wait_all();
-              const float4 c0 = rec_sh[0 * TILE + row];
-              tn = __longlong_as_double(((long long)__float_as_int(c0.y) << 32) | (long long)(unsigned)__float_as_int(c0.x));
-            }
+            if (ok && sn >= 0) tn = step_rec_t(step_rec(A, unit, sn));
             piece_for(tn, pn_t1, pn_inv, pn_v1, pn_dv);
           }
           __syncwarp();   // reconverge after per-thread code: tcgen05 .sync.aligned instructions follow
           HODE_TL(204);
-#pragma unroll 1
-          for (int l = 0; l < L; ++l) {
-            if (has_F) put4(mnext, l, fwd_epilogue<MODE, true>(e, l, (int)(m_f & 1u)));
-            bwd_epilogue<true>(e, L - l, sel4(mcur, L - l - 1), x);
-          }
-          // ---- final phase: g_x -----------------------------------------------------------------------------------
-          tc::mbar_wait(&bars.b_bar, e.b_cnt & 1u);
-          e.b_cnt += 1u;
+          // ---- the pull-back's result: g_x ---------------------------------------------------------------------------
+          tc::mbar_wait(&bars.gx_bar, m_b & 1u);
           tc::fence_after_sync();
           HODE_TL(205);
           {
@@ -976,7 +966,8 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
             for (int cc = 0; cc < NS; ++cc) gys[cc] += __uint_as_float(v[1 + cc]);
             gys[3] += __uint_as_float(v[7]);
           }
-          if (has_F) m_f += 1u;
+          tc::fence_before_sync();
+          m_b += 1u;
 #pragma unroll
           for (int cc = 0; cc < NS; ++cc) {
             gy[cc] += gys[cc];
@@ -999,10 +990,9 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
           t_later = t;
           later_valid = true;
         }
-        // ---- next iteration's context (its record was prefetched into shared memory) ------------------------------
+        // ---- next iteration's context ------------------------------------------------------------------------------
         if (it + 1 < n_iter) {
-          tc::cp_async_wait_all();
-          set_ctx(it + 1, [&](int c4) { return rec_sh[c4 * TILE + row]; });
+          set_ctx(it + 1);
           pc_t1 = pn_t1; pc_inv = pn_inv;
           pc_v1[0] = pn_v1[0]; pc_v1[1] = pn_v1[1]; pc_dv[0] = pn_dv[0]; pc_dv[1] = pn_dv[1];
         }
@@ -1091,7 +1081,7 @@ __global__ void __launch_bounds__(3 * TILE, 1) rollout_bwd_tc_kernel(const AdjTc
     float* red = reinterpret_cast<float*>(smem_raw);
 #pragma unroll
     for (int i = 0; i < HODE_N_THETA; ++i) red[i * TILE + row] = gth[i];
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"n"(BAR_MAIN) : "memory");
     if (row < HODE_N_THETA) {
       float sacc = 0.f;
       for (int r = 0; r < TILE; ++r) sacc += red[row * TILE + r];
@@ -1334,11 +1324,11 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const floa
   if (fwd_mode == HODE_MLP_TF32BF16) {
     e = cudaFuncSetAttribute(rollout_bwd_tc_kernel<MLP_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
-    rollout_bwd_tc_kernel<MLP_MIXED><<<dim3(p.grid_x, p.grid_y), 3 * TILE, p.smem, stream>>>(G);
+    rollout_bwd_tc_kernel<MLP_MIXED><<<dim3(p.grid_x, p.grid_y), ADJ_THREADS, p.smem, stream>>>(G);
   } else {
     e = cudaFuncSetAttribute(rollout_bwd_tc_kernel<MLP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
-    rollout_bwd_tc_kernel<MLP_X3><<<dim3(p.grid_x, p.grid_y), 3 * TILE, p.smem, stream>>>(G);
+    rollout_bwd_tc_kernel<MLP_X3><<<dim3(p.grid_x, p.grid_y), ADJ_THREADS, p.smem, stream>>>(G);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -1346,3 +1336,10 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const floa
 }
 
 }  // namespace hode
+
+#ifdef HODE_DEBUG_WAIT
+// debug build only (tools/debug_wait_adj.py): where stuck mbarrier waits are recorded (host-mapped memory)
+extern "C" int hode_debug_set_buffer(int* buf) {
+  return (int)cudaMemcpyToSymbol(hode::tc::g_dbg_buf, &buf, sizeof(int*));
+}
+#endif

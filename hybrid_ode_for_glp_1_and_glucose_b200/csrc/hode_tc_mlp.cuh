@@ -51,10 +51,11 @@ constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
 // Activation stash of the adjoint (one block per hidden layer, per CTA): the tile's
 // a_l = relu(z_l) as the BF16 operand image the weight-gradient MMAs read (csrc/probe/bf16_probe.cu),
 //   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2,
-// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to 2^-17).
+// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to 2^-17),
+// followed by the ReLU masks: word [half][t] = bit j set iff a[32 half + j] > 0.
 constexpr int ST_GRP = 2048;                 // one 8-feature group: 128 trajectories x 16 B
 constexpr int ST_PART = 8 * ST_GRP;          // 64 features
-constexpr int ST_BLK = 2 * ST_PART;          // hi, mid
+constexpr int ST_BLK = 2 * ST_PART + 1024;   // hi, mid, masks
 }  // namespace
 
 // x[0..7] -> 8 BF16 hi (round to nearest) and 8 BF16 mid = bf16(x - hi); feature 0 in the low half of word 0
@@ -73,7 +74,7 @@ __device__ __forceinline__ void bf16_split8(const float* v, uint4& hi, uint4& mi
 
 // this thread's 32 activations a = relu(z) of columns [32 half, 32 half + 32), given as the TF32
 // hi / lo parts the epilogue produced (a = hi + lo exactly) -> stash block `blk`; returns the ReLU mask
-// (bit j set iff a[32 half + j] > 0), which the thread keeps in a register until the pull-back needs it
+// (bit j set iff a[32 half + j] > 0)
 __device__ __forceinline__ uint32_t stash_store32(uint8_t* blk, int row, int half, const uint32_t* hi_, const uint32_t* lo_) {
   uint32_t mask = 0u;
 #pragma unroll

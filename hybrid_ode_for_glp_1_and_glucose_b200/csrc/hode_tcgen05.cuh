@@ -94,7 +94,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 #ifdef HODE_DEBUG_WAIT
-// debug build: a wait that does not complete within ~2 s reports where it is stuck and traps
+// debug build: a wait that does not complete within ~0.5 s records where it is stuck in a host-mapped buffer
+// (hode_debug_set_buffer; it survives the trap) and traps
+__device__ int* g_dbg_buf = nullptr;   // [0] = count, then {block x, block y, thread, line, parity} per record
 __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
   const long long t0 = clock64();
   for (;;) {
@@ -102,8 +104,17 @@ __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, in
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("HODE stuck: block (%d,%d) thread %d line %d parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x, line, parity);
+    if (clock64() - t0 > 1000000000LL) {
+      if (g_dbg_buf) {
+        const int i = atomicAdd(g_dbg_buf, 1);
+        if (i < 4000) {
+          int* r = g_dbg_buf + 1 + 5 * i;
+          r[0] = blockIdx.x; r[1] = blockIdx.y; r[2] = threadIdx.x; r[3] = line; r[4] = (int)parity;
+        }
+        __threadfence_system();
+      }
+      const long long t1 = clock64();
+      while (clock64() - t1 < 200000000LL) { }   // let the other stuck threads report too
       __trap();
     }
   }
