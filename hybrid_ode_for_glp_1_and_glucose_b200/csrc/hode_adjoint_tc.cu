@@ -90,13 +90,15 @@ constexpr uint32_t TM_DB = 200, DW_H0 = 264, DW_HS = 72, DW_0 = 480, DW_O = 496;
 //   DB  2 x [hi][mid]: the delta image of a phase (buffered by phase parity)
 //   XB  2 x [hi: 2 groups][mid: 2 groups]: the stage's input features x, input operand of dW_0 (buffered by item parity)
 //   WT  2 x one layer's W^T (BF16 hi, mid)         WF  one layer's forward image + its bias block
-constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART + 1024;   // hi, mid, ReLU masks of a_{q-1}
+//   MK  2 x [L][2 halves][128] ReLU masks of the item being recomputed / pulled back (word: bit j <=> a[32 half + j] > 0)
+constexpr int AB_PART = 9 * ST_GRP, AB_BYTES = 2 * AB_PART;
 constexpr int DB_BYTES = 2 * ST_PART;
 constexpr int XB_PART = 2 * ST_GRP, XB_BYTES = 2 * XB_PART;
 constexpr int WT_BYTES = 2 * 64 * 64 * 2;
 constexpr int WF_FLOATS = 8192 + 512, WF_BYTES = WF_FLOATS * 4;
+constexpr int MK_BYTES = MAXL * 2 * TILE * 4;
 constexpr int OFF_AB = 0, OFF_DB = OFF_AB + 2 * AB_BYTES, OFF_XB = OFF_DB + 2 * DB_BYTES, OFF_WT = OFF_XB + 2 * XB_BYTES,
-              OFF_WF = OFF_WT + 2 * WT_BYTES, OFF_T = OFF_WF + WF_BYTES;
+              OFF_WF = OFF_WT + 2 * WT_BYTES, OFF_MK = OFF_WF + WF_BYTES, OFF_T = OFF_MK + 2 * MK_BYTES;
 constexpr int ADJ_SMEM_BASE = OFF_T;            // + 4 T bytes when the shared time grid fits
 constexpr int ADJ_SMEM_MAX = 227 * 1024 - 256;  // (static shared memory: the mbarriers, padded to the dynamic part's alignment)
 constexpr int ADJ_THREADS = 6 * TILE;
@@ -193,10 +195,10 @@ __device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float G
   const float G = y[0], I = y[1], Glu = y[2], GLP1 = y[3], FFA = y[5];
   const float Pi = 1.0f + p.rho * GLP1;
   const float dG = G - p.G_b, dI = I - p.I_b, dGlu = Glu - p.Glu_b;
-  const float inv_e = 1.0f / (p.EC_50 + GLP1);
+  const float inv_e = __frcp_rn(p.EC_50 + GLP1);
   const float frac_e = GLP1 * inv_e;
   const float ge = p.E_max * frac_e;
-  const float inv_m = 1.0f / (p.K_m + G);
+  const float inv_m = __frcp_rn(p.K_m + G);
   float r = 0.f, dr_du = 0.f, dr_dv = 0.f, u = 0.f;
   const float v = p.igd_pow;
   if (gd_present) {
@@ -238,18 +240,29 @@ __device__ __forceinline__ void mech_vjp(const Theta& p, const float* y, float G
 }
 
 // ---- recomputation epilogue (F-epilogue warps; half 0 = columns [0,32), half 1 = [32,64)) ---------------------------
-// hidden layer l of the item in scratch set `set`: a_l = relu(z_l) -> next layer's A operand (TMEM) and -> the scratch
-// as the weight gradients' BF16 operand image.  16 columns at a time (these warps run on 88 registers).
+// hidden layer l of an item: a_l = relu(z_l) -> next layer's A operand (TMEM), -> the scratch as the weight gradients'
+// BF16 operand image (global, L2-resident) and its ReLU mask -> shared memory.  The scratch is read back by bulk copies
+// (async proxy), so its generic-proxy stores need a cross-proxy fence before the "stashed" signal.  That fence costs
+// ~1 k cycles whenever it is issued (measured: profiles/r02_timeline_*), and the pull-back needs the item's operands
+// only one slot later: ONE fence per item, after the last layer, then all L signals.
 template <int MODE>
-__device__ __forceinline__ void fwd_epilogue(Bars* bars, uint32_t t_lane, int half, int row, uint8_t* blk, bool last,
-                                             bool arrive) {
+__device__ __forceinline__ void fwd_epilogue(Bars* bars, uint8_t* smem, uint32_t t_lane, int half, int row, uint8_t* stash_set,
+                                             int set, int l, int L) {
   const uint32_t col0 = (uint32_t)half * 32u;
+  const bool last = (l + 1 == L);
   uint32_t v[32], lo[32];
+  HODE_TL(300);
   epilogue32_to_tmem<MODE>(t_lane, col0, v, lo, !last);
-  if (arrive) bar_arrive<BAR_F, N_EPI>();
-  const uint32_t mask = stash_store32(blk, row, half, v, lo);
-  reinterpret_cast<uint32_t*>(blk + 2 * ST_PART)[half * TILE + row] = mask;
-  tc::fence_proxy_async_all();   // generic-proxy global stores, read back by a bulk copy (async proxy)
+  bar_arrive<BAR_F, N_EPI>();
+  HODE_TL(301);
+  const uint32_t mask = stash_store32(stash_set + (size_t)l * ST_BLK, row, half, v, lo);
+  reinterpret_cast<uint32_t*>(smem + OFF_MK + set * MK_BYTES)[(l * 2 + half) * TILE + row] = mask;
+  HODE_TL(302);
+  if (last) {
+    tc::fence_proxy_async_all();
+    for (int ll = 0; ll < L; ++ll) tc::mbar_arrive(&bars->st_done[set][ll]);
+  }
+  HODE_TL(303);
 }
 
 // items of one tile: iteration it = 0..n_iter-1 (one accepted step each, last step first), stages i = N-1 .. i_lo(it).
@@ -385,8 +398,7 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
           tc::mbar_wait(&bars.f_bar, f_cnt & 1u);
           f_cnt += 1u;
           tc::fence_after_sync();
-          fwd_epilogue<MODE>(&bars, tmem + lane_base, half, row, stash0 + ((size_t)(m_f & 1u) * L + l) * ST_BLK, l + 1 == L, true);
-          tc::mbar_arrive(&bars.st_done[m_f & 1u][l]);
+          fwd_epilogue<MODE>(&bars, smem_raw, tmem + lane_base, half, row, stash0 + (size_t)(m_f & 1u) * L * ST_BLK, (int)(m_f & 1u), l, L);
         }
         m_f += 1u;
       }
@@ -395,22 +407,23 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
     // ================================ pull-back epilogues ======================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     const int half = wg - 3;
-    uint32_t b_cnt = 0u, ph = 0u;
+    uint32_t b_cnt = 0u, ph = 0u, m_b = 0u;
     for (int tk = tile_beg; tk < tile_end; ++tk) {
       const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
       const int items = tile_items(n_iter);
 #pragma unroll 1
-      for (int m = 0; m < items; ++m) {
+      for (int m = 0; m < items; ++m, ++m_b) {
         // phase p = L..1 has delivered u_{p-1} in D_B: delta_{p-1} = u_{p-1} * relu'(a_{p-1}) -> delta image of phase p-1
 #pragma unroll 1
         for (int p = L; p >= 1; --p) {
-          const uint32_t buf = ph & 1u;
           tc::mbar_wait(&bars.b_bar, b_cnt & 1u);
           b_cnt += 1u;
           tc::fence_after_sync();
-          // ReLU mask of a_{p-1}: rides with the stashed operand of this phase's weight gradient
-          tc::mbar_wait(&bars.ab_full[buf], (ph >> 1) & 1u);
-          const uint32_t mask = reinterpret_cast<const uint32_t*>(smem_raw + OFF_AB + buf * AB_BYTES + 2 * AB_PART)[half * TILE + row];
+          HODE_TL(320);
+          // ReLU mask of a_{p-1}: written to shared memory by the F-epilogue warps when the item was recomputed
+          tc::mbar_wait(&bars.st_done[m_b & 1u][p - 1], (m_b >> 1) & 1u);
+          HODE_TL(321);
+          const uint32_t mask = reinterpret_cast<const uint32_t*>(smem_raw + OFF_MK + (m_b & 1u) * MK_BYTES)[((p - 1) * 2 + half) * TILE + row];
           uint8_t* db = smem_raw + OFF_DB + ((ph + 1u) & 1u) * DB_BYTES + (half * 4) * ST_GRP + row * 16;
 #pragma unroll
           for (int c16 = 0; c16 < 2; ++c16) {
@@ -428,12 +441,15 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
               *reinterpret_cast<uint4*>(db + (c16 * 2 + g) * ST_GRP + ST_PART) = vm;
             }
           }
+          HODE_TL(322);
           tc::fence_proxy_async();
           tc::fence_before_sync();
           bar_arrive<BAR_B, N_EPI>();
+          HODE_TL(323);
           ph += 1u;
         }
         tc::mbar_wait(&bars.b_bar, b_cnt & 1u);   // g_x (read by the main warps): the phase must be observed
+        HODE_TL(324);
         b_cnt += 1u;
         ph += 1u;
       }
@@ -569,7 +585,7 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
         }
       }
     } else {
-      // ================================ loader: stashed activations a_{q-1} (+ ReLU masks) of every phase ==========
+      // ================================ loader: stashed activations a_{q-1} of every pull-back phase ==================
       uint32_t ph = 0u, m_all = 0u;
       for (int tk = tile_beg; tk < tile_end; ++tk) {
         const int n_iter = tile_nmax(0) + (fsal ? 1 : 0);
@@ -581,20 +597,14 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
             const uint32_t buf = ph & 1u, k = ph >> 1;
             // written by the F-epilogue warps (generic proxy + fence); item m_all is the (m_all >> 1)-th user of its set
             if (q >= 1) tc::mbar_wait(&bars.st_done[m_all & 1u][q - 1], (m_all >> 1) & 1u);
-            if (k >= 1u) {
-              tc::mbar_wait(&bars.ab_free[buf], (k - 1u) & 1u);             // the buffer's previous weight-gradient MMAs are done
-              // ... and its ReLU masks have been read: the delta chain of phase ph - 1 is only issued after the
-              // epilogue of phase ph - 2 (which read them) has arrived
-              tc::mbar_wait(&bars.wt_free[(ph - 1u) & 1u], ((ph - 1u) >> 1) & 1u);
-            }
+            if (k >= 1u) tc::mbar_wait(&bars.ab_free[buf], (k - 1u) & 1u);   // the buffer's previous weight-gradient MMAs are done
             if (lane_id == 0) {
               if (q >= 1) {
                 const uint8_t* src = stash0 + ((size_t)(m_all & 1u) * L + (q - 1)) * ST_BLK;
                 uint8_t* dst = smem_raw + OFF_AB + buf * AB_BYTES;
-                tc::mbar_expect_tx(&bars.ab_full[buf], 2u * ST_PART + 1024u);
+                tc::mbar_expect_tx(&bars.ab_full[buf], 2u * ST_PART);
                 tc::bulk_g2s(dst, src, ST_PART, &bars.ab_full[buf]);
                 tc::bulk_g2s(dst + AB_PART, src + ST_PART, ST_PART, &bars.ab_full[buf]);
-                tc::bulk_g2s(dst + 2 * AB_PART, src + 2 * ST_PART, 1024u, &bars.ab_full[buf]);
               } else {
                 tc::mbar_arrive(&bars.ab_full[buf]);   // phase 0: its input operand is x (XB, written by the main warps)
               }
@@ -789,11 +799,11 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
       // ---- first iteration's context; its top stage goes to the recomputation chain right away --------------------
       set_ctx(0);
       piece_for(t, pc_t1, pc_inv, pc_v1, pc_dv);
-      {
-        float ys[NS], x[HODE_NN_IN], gd;
-        stage_x(N - 1, ys, x, gd);
-        start_F(x);
-      }
+      // stage inputs of the item whose pull-back starts next: computed ONCE, when the item is handed to the
+      // recomputation chain (one slot earlier), and kept in registers
+      float ys[NS], x[HODE_NN_IN], gdi;
+      stage_x(N - 1, ys, x, gdi);
+      start_F(x);
       uint32_t m_b = m_all - 1u;   // index of the item whose pull-back starts next
 
       for (int it = 0; it < n_iter; ++it) {
@@ -832,7 +842,7 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
                   for (int cc = 0; cc < NS; ++cc) gnew[cc] += g[cc];
                 }
               } else {
-                const float xq = (float)((te - t) / h);
+                const float xq = __fdividef((float)(te - t), hf);   // (the rollout's own formula)
 #pragma unroll
                 for (int cc = 0; cc < NS; ++cc) gy[cc] += g[cc];
 #pragma unroll
@@ -858,8 +868,7 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
         for (int i = N - 1; i >= i_lo; --i) {
           HODE_TL(201);
           const bool has_F = !(it == n_iter - 1 && i == i_lo);
-          float ys[NS], x[HODE_NN_IN], gys[NS], gki[NS], gdi;
-          stage_x(i, ys, x, gdi);
+          float gys[NS], gki[NS];
 #pragma unroll
           for (int cc = 0; cc < NS; ++cc) { gys[cc] = 0.f; gki[cc] = 0.f; }
 #pragma unroll
@@ -898,16 +907,14 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
           }
           HODE_TL(202);
           // ---- recomputation of the NEXT item: its input operand ---------------------------------------------------
+          float xf[HODE_NN_IN], ysf[NS], gdf = 0.f;
           if (has_F) {
-            float xf[HODE_NN_IN];
             if (i > i_lo) {
-              float ysf[NS], gdf;
               stage_x(i - 1, ysf, xf, gdf);
             } else {
               // top stage of the next iteration's step (one step earlier in time)
               const int sn = sidx - 1;
               const bool act_n = ok && (sn >= 0 || (fsal && sn == -1));
-              float ysf[NS];
               double te;
               if (solver == 1) {
                 // DP5(4): its stage 7 is evaluated at ITS result = the state and time this step starts from
@@ -933,13 +940,18 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
                 te = tp + (double)hp;
               }
               const float t32 = (float)te;
-              float tvns, gdf;
+              float tvns;
               inputs_at(t32, pn_t1, pn_inv, pn_v1, pn_dv, tvns, gdf);
-              xf[0] = act_n ? t32 : 0.f;
+              if (!act_n) {
+                tvns = 0.f; gdf = 0.f;
 #pragma unroll
-              for (int cc = 0; cc < NS; ++cc) xf[1 + cc] = act_n ? ysf[cc] : 0.f;
-              xf[7] = act_n ? ysf[3] : 0.f;
-              xf[8] = act_n ? tvns : 0.f;
+                for (int cc = 0; cc < NS; ++cc) ysf[cc] = 0.f;
+              }
+              xf[0] = t32;
+#pragma unroll
+              for (int cc = 0; cc < NS; ++cc) xf[1 + cc] = ysf[cc];
+              xf[7] = ysf[3];
+              xf[8] = tvns;
             }
             start_F(xf);
           }
@@ -973,6 +985,13 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
             gy[cc] += gys[cc];
 #pragma unroll
             for (int j = 0; j < NSTAGE_MAX - 1; ++j) gk[j][cc] = fmaf(hf * kA[solver][i][j], gys[cc], gk[j][cc]);
+          }
+          if (has_F) {   // the next item's stage inputs become the current ones
+#pragma unroll
+            for (int cc = 0; cc < NS; ++cc) ys[cc] = ysf[cc];
+#pragma unroll
+            for (int kk = 0; kk < HODE_NN_IN; ++kk) x[kk] = xf[kk];
+            gdi = gdf;
           }
           HODE_TL(206);
         }

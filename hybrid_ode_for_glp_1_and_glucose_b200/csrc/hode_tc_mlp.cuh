@@ -12,9 +12,12 @@ namespace hode {
 #ifdef HODE_TIMELINE
 __device__ long long g_tl[2 * 16384];
 __device__ int g_tl_n;
+#ifndef HODE_TL_TID
+#define HODE_TL_TID 0   // the thread whose marks are recorded (-DHODE_TL_TID=...: another role's warp)
+#endif
 #define HODE_TL(id)                                                                         \
   do {                                                                                      \
-    if (blockIdx.x == 3 && threadIdx.x == 0) {                                              \
+    if (blockIdx.x == 3 && threadIdx.x == HODE_TL_TID) {                                              \
       const int n_ = g_tl_n;                                                                \
       if (n_ < 16384) { g_tl[2 * n_] = (id); g_tl[2 * n_ + 1] = clock64(); g_tl_n = n_ + 1; } \
     }                                                                                       \
@@ -51,11 +54,10 @@ constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
 // Activation stash of the adjoint (one block per hidden layer, per CTA): the tile's
 // a_l = relu(z_l) as the BF16 operand image the weight-gradient MMAs read (csrc/probe/bf16_probe.cu),
 //   element (trajectory t, feature f) at byte (f / 8) * ST_GRP + t * 16 + (f % 8) * 2,
-// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to 2^-17),
-// followed by the ReLU masks: word [half][t] = bit j set iff a[32 half + j] > 0.
+// a "hi" part (BF16 round-to-nearest) and a "mid" part (BF16 of the remainder; a ~= hi + mid to 2^-17).
 constexpr int ST_GRP = 2048;                 // one 8-feature group: 128 trajectories x 16 B
 constexpr int ST_PART = 8 * ST_GRP;          // 64 features
-constexpr int ST_BLK = 2 * ST_PART + 1024;   // hi, mid, masks
+constexpr int ST_BLK = 2 * ST_PART;          // hi, mid
 }  // namespace
 
 // x[0..7] -> 8 BF16 hi (round to nearest) and 8 BF16 mid = bf16(x - hi); feature 0 in the low half of word 0

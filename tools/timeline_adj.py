@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 CSRC = os.path.join(ROOT, "hybrid_ode_for_glp_1_and_glucose_b200", "csrc")
 flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
-subprocess.run(["nvcc", *flags, "-DHODE_TIMELINE", "-c", os.path.join(CSRC, "hode_adjoint_tc.cu"), "-o",
+subprocess.run(["nvcc", *flags, "-DHODE_TIMELINE", *os.environ.get("HODE_TL_FLAGS", "").split(), "-c", os.path.join(CSRC, "hode_adjoint_tc.cu"), "-o",
                 "/tmp/hode_adjoint_tc_tl.o"], check=True)
 objs = [os.path.join(CSRC, f) for f in ("hode_api.o", "hode_rollout_simt.o", "hode_adjoint_simt.o", "hode_rollout_tc.o", "hode_gen4gi.o")]
 lib = os.path.join(ROOT, "hybrid_ode_for_glp_1_and_glucose_b200", "libhode.so")
@@ -38,7 +38,7 @@ try:
     names = {}
     for a, b, d in zip(ids[s:-1], ids[s + 1:], np.diff(clk[s:])):
         names.setdefault((int(a), int(b)), []).append(int(d))
-    n_steps = sum(1 for x in ids[s:] if x == 200)
+    n_steps = sum(1 for x in ids[s:] if x == 200) or max(1, sum(1 for x in ids[s:] if x in (300, 324)) // (24 if any(x == 300 for x in ids[s:]) else 6))
     print(f"events {n}, steps analysed {n_steps}")
     tot = 0.0
     for k, v in sorted(names.items()):
