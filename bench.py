@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — trajectory-steps/s of the hybrid ODE-NN rollout on N B200s (BASELINE.json metric).
+"""bench.py — trajectory-steps/s of the hybrid ODE-NN rollout and gradient path on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hybrid_fwd|mech_rk4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hybrid_fwd|hybrid_fwdbwd|vi_predictive|mech_rk4]
     python bench.py --impl reference ...      # the CPU restatement of the reference path
 
-A "step" is one pass of the hot path (one libhode rollout launch) over one batch of
-synthetic 4GI-shaped trajectories.  One JSON line is printed by rank 0.  Definitions of
-every reported quantity are in DESIGN.md §Measurement.
+A "step" is one pass of the hot path over one batch of synthetic 4GI-shaped trajectories.  One JSON line is
+printed by rank 0.  The headline (`value`, `e2e`, `roofline`) is the workload named in config.workload; the
+default run (hybrid_fwd) also times the other legs of the metric and keeps them under `roofline.legs`:
+forward + discrete adjoint (+ the packed NCCL gradient all-reduce when N > 1, inside the timed region), the
+same on config 3's real per-GPU shard, and the 64-sample x 1 048 576-trajectory posterior-predictive sweep of
+config 4.  Definitions of every reported quantity are in DESIGN.md §Measurement.
 """
 from __future__ import annotations
 
@@ -29,6 +32,8 @@ FLOP_MLP_EVAL = 26496.0          # 13 248 MAC
 FLOP_ATTEMPT_HYBRID = 6 * FLOP_MLP_EVAL + 700.0   # DP5(4) attempt, FSAL: 158 976 + ~700
 FLOP_STEP_RK4_MECH = 310.0
 BYTES_PER_TRAJ = lambda T, n_in, per_row_t: 24 + 4 * T * n_in + (4 * T if per_row_t else 0) + 24 * T
+VI_SAMPLES, VI_TRAJ_PER_BOX = 64, 1048576     # config 4 (configs/4gi_vi.yaml-shaped posterior predictive)
+REC_CAPACITY = 128                            # accepted-step records per trajectory (bench cohort: max ~100)
 
 
 def parse_args():
@@ -37,39 +42,57 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hybrid_fwd", choices=["hybrid_fwd", "hybrid_fwdbwd", "mech_rk4"])
+    ap.add_argument("--workload", default="hybrid_fwd",
+                    choices=["hybrid_fwd", "hybrid_fwdbwd", "vi_predictive", "mech_rk4"])
     ap.add_argument("--traj-per-gpu", type=int, default=0)
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "tf32bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs of the default run")
     return ap.parse_args()
 
 
 WORKLOADS = {
     # configs/default.yaml-shaped: hybrid 64x4 net with a non-zero head, dopri5 1e-6/1e-8,
     # 262 144 trajectories (the config's whole cohort on ONE GPU; weak scaling over N)
-    "hybrid_fwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip",
-                       nn=True, name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd, 262144 traj/GPU, T=61"),
-    # the same with the discrete adjoint (hode_rollout_bwd), same cohort per GPU.  (--traj-per-gpu 32768 is
-    # configs/default.yaml's 262 144 trajectories strong-scaled over 8 GPUs: both kernels are then bound by
-    # the latency of the longest trajectories — 221 trajectories per SM — rather than by throughput.)
+    "hybrid_fwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip", nn=True,
+                       name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd, {B} traj/GPU, T=61"),
+    # the same with the discrete adjoint (hode_rollout_bwd) and, when N > 1, the packed gradient all-reduce
     "hybrid_fwdbwd": dict(B=262144, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip", nn=True, bwd=True,
-                          name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd+adjoint, 262144 traj/GPU, T=61"),
+                          name="default.yaml hybrid 64x4 dopri5 rtol1e-6 fwd+adjoint(+allreduce), {B} traj/GPU, T=61"),
+    # configs/4gi_vi.yaml-shaped posterior predictive: 64 parameter samples x 1 048 576 trajectories PER BOX
+    # (B = 1 048 576 / N per GPU: the sweep is partitioned by trajectory, all samples of a trajectory on one GPU)
+    "vi_predictive": dict(B=VI_TRAJ_PER_BOX, T=61, solver="dopri5", rtol=1e-6, atol=1e-8, kinks="clip", nn=True, vi=True,
+                          name="4gi_vi.yaml posterior predictive 64 samples x {B} traj/GPU, hybrid 64x4 dopri5 rtol1e-6, T=61"),
     # configs/ablation_no_nn.yaml-shaped: mechanistic only, RK4, 4 substeps per 5-min interval
     "mech_rk4": dict(B=1048576, T=61, solver="rk4", n_substeps=4, nn=False,
-                     name="ablation_no_nn mechanistic rk4 4 substeps, 1048576 traj/GPU, T=61"),
+                     name="ablation_no_nn mechanistic rk4 4 substeps, {B} traj/GPU, T=61"),
 }
 
 
-def make_workload(kind: str, B: int, seed: int):
+def make_workload(kind: str, B: int, seed: int, world: int = 1):
     from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import THETA_DEFAULT, cohort, random_mlp
     w = dict(WORKLOADS[kind])
     if B:
         w["B"] = B
+    elif w.get("vi"):
+        w["B"] = VI_TRAJ_PER_BOX // world
     y0, t, ins = cohort(w["B"], w["T"], seed=seed, tvns=(kind != "mech_rk4"))
     W = random_mlp(64, 4, seed=1234, out_std=0.05) if w["nn"] else None
-    w.update(y0=y0, t=t, ins=ins, theta=THETA_DEFAULT.copy(), W=W)
+    w.update(y0=y0, t=t, ins=ins, theta=THETA_DEFAULT.copy(), W=W, name=w["name"].format(B=w["B"]))
     return w
+
+
+def vi_posterior_samples(theta, W, S, seed=7):
+    """S draws from a diagonal Gaussian posterior shaped like the reference's (models/bayes.py:99-127): mean = the
+    point parameters, std = 0.1 x prior std; ODE priors of configs/4gi_vi.yaml:26-33 (EC_50: the default 1.0),
+    the other ODE parameters fixed; network prior std 0.1."""
+    rng = np.random.default_rng(seed)
+    prior = {0: 0.002, 1: 0.005, 2: 0.001, 5: 0.02, 6: 1.0, 8: 2.0, 9: 1.5, 10: 0.005}   # index into theta (include/hode.h)
+    th = np.repeat(theta[None, :], S, 0).astype(np.float64)
+    for i, sd in prior.items():
+        th[:, i] += 0.1 * sd * rng.normal(0, 1, S)
+    Ws = W[None, :] + 0.1 * 0.1 * rng.normal(0, 1, (S, W.size))
+    return th.astype(np.float32), Ws.astype(np.float32)
 
 
 # ---------------------------------------------------------------------------------- clocks
@@ -154,7 +177,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    w = make_workload(args.workload, args.traj_per_gpu, seed=1000)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = make_workload(args.workload, args.traj_per_gpu, seed=1000, world=world)
     from oracle import cpu_oracle as o
     o.build()
     n = cpu_sample_size(w, threads, target_s=6.0)
@@ -166,7 +190,8 @@ def run_reference_arm(args):
         steps_total += s
         t_total += dt
     value = steps_total / t_total
-    sample = (f"{n} of {w['B']} trajectories per step, C restatement of the reference path "
+    what = "one parameter set of the sweep (the reference loops over the samples)" if w.get("vi") else "forward rollout"
+    sample = (f"{n} of {w['B']} trajectories per step, {what}, C restatement of the reference path "
               f"(oracle/hode_oracle.c: float32 RHS, float64 SciPy-RK45 stepping), {threads} pthreads")
     line = {
         "impl": "reference", "metric": "trajectory_steps_per_sec", "value": value,
@@ -185,9 +210,7 @@ def run_reference_arm(args):
 
 def bind_to_gpu_numa_node(local: int):
     """Pin this rank's host threads (and with them the first-touch placement of its pinned buffers) to the
-    NUMA node its GPU hangs off.  torchrun leaves ranks unbound; with 8 ranks moving 0.5 GB per step each
-    through host memory the e2e leg is otherwise bound by cross-socket traffic.  Best effort: any failure
-    leaves the affinity as it was.  Returns the node or None."""
+    NUMA node its GPU hangs off.  Best effort: any failure leaves the affinity as it was.  Returns the node or None."""
     try:
         out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
                              capture_output=True, text=True, timeout=10).stdout.strip().lower()
@@ -210,6 +233,13 @@ def bind_to_gpu_numa_node(local: int):
         return None
 
 
+def load_json(path):
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 # ---------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -228,246 +258,361 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     build.build()
     L = _lib.lib()
+    L.hode_launch_count.restype = ctypes.c_int64
 
-    w = make_workload(args.workload, args.traj_per_gpu, seed=1000 + rank)
+    w = make_workload(args.workload, args.traj_per_gpu, seed=1000 + rank, world=world)
     B, T = w["B"], w["T"]
-    # host copies in pinned memory (the e2e path starts from these)
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_y0, h_t, h_theta = pin(w["y0"]), pin(w["t"]), pin(w["theta"])
-    h_ins = {k: pin(v) for k, v in w["ins"].items()}
-    h_W = pin(w["W"]) if w["W"] is not None else None
-    d_y0, d_t, d_theta = h_y0.to(dev), h_t.to(dev), h_theta.to(dev)
-    d_ins = {k: v.to(dev) for k, v in h_ins.items()}
-    d_W = h_W.to(dev) if h_W is not None else None
-    kw = dict(solver=w["solver"], device=dev)
-    if w["solver"] == "rk4":
-        kw.update(n_substeps=w["n_substeps"])
-    else:
-        kw.update(rtol=w["rtol"], atol=w["atol"], kinks=w["kinks"], precision=args.precision)
-
-    bwd = bool(w.get("bwd"))
-    d_g = torch.full((B, T, 6), 1.0 / (B * T * 6), dtype=torch.float32, device=dev) if bwd else None
-    grads = {}
-
-    def step():
-        if not bwd:
-            return ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, **kw)
-        traj, info, tape = ops.rollout(d_y0, d_t, d_ins, d_theta, d_W, save_steps=True, **kw)
-        g_y0, g_theta, g_W = ops.rollout_bwd(tape, d_g)      # grad of mean(traj) w.r.t. y0, theta, W
-        if world > 1:
-            # the path's one exchange step: gradients of the shared parameters + a loss slot,
-            # one packed float32 buffer (54 KB), one NCCL all-reduce
-            packed = torch.cat([g_theta.reshape(-1), g_W.reshape(-1), traj.new_zeros(1)])
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
-            grads["packed"] = packed
-        grads["out"] = (g_y0, g_theta, g_W)
-        return traj, info
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        traj, info = step()
-    barrier()
-    attempts_per_step = float((info.n_accept.sum() + info.n_reject.sum()).item())
-    assert bool((info.status == 0).all()), "synthetic workload must integrate without failures"
+    def reduce_max_sum(ms, work):
+        """MAX time over ranks, SUM of work."""
+        st = torch.tensor([ms], dtype=torch.float64, device=dev)
+        wk = torch.tensor([work], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+            dist.all_reduce(wk, op=dist.ReduceOp.SUM)
+        return float(st.item()), float(wk.item())
 
-    # ---- kernel-resident timing: inputs already in HBM, K launches, CUDA events ------------
+    def timed(fn, steps, warmup):
+        """W untimed + K timed calls of fn on torch's current stream, CUDA events, barrier + synchronize on both sides.
+        Returns (ms for the K steps on this rank, last result, kernels of ours launched in the timed region)."""
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = int(L.hode_launch_count())
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), out, int(L.hode_launch_count()) - n0
+
+    class Cohort:
+        """One rank's device-resident inputs of a workload (+ pinned host copies for the e2e leg)."""
+        def __init__(self, wl, keep_host=False):
+            self.w = wl
+            h = dict(y0=pin(wl["y0"]), t=pin(wl["t"]), theta=pin(wl["theta"]), ins={k: pin(v) for k, v in wl["ins"].items()},
+                     W=pin(wl["W"]) if wl["W"] is not None else None)
+            self.y0, self.t, self.theta = h["y0"].to(dev), h["t"].to(dev), h["theta"].to(dev)
+            self.ins = {k: v.to(dev) for k, v in h["ins"].items()}
+            self.W = h["W"].to(dev) if h["W"] is not None else None
+            self.host = h if keep_host else None
+            self.kw = dict(solver=wl["solver"], device=dev)
+            if wl["solver"] == "rk4":
+                self.kw.update(n_substeps=wl["n_substeps"])
+            else:
+                self.kw.update(rtol=wl["rtol"], atol=wl["atol"], kinks=wl["kinks"], precision=args.precision)
+
+    def attempts_of(info):
+        return float((info.n_accept.sum() + info.n_reject.sum()).item())
+
+    def fwd_step(c):
+        return lambda: ops.rollout(c.y0, c.t, c.ins, c.theta, c.W, **c.kw)
+
+    def fwdbwd_step(c, d_g):
+        def step():
+            traj, info, tape = ops.rollout(c.y0, c.t, c.ins, c.theta, c.W, save_steps=True, max_saved_steps=REC_CAPACITY, **c.kw)
+            g_y0, g_theta, g_W = ops.rollout_bwd(tape, d_g)      # grad of mean(traj) w.r.t. y0, theta, W
+            if world > 1:
+                # the path's one exchange step (SURVEY §8e): gradients of the shared parameters + a loss slot,
+                # one packed float32 buffer (54 KB), one NCCL all-reduce — INSIDE the timed region
+                packed = torch.cat([g_theta.reshape(-1), g_W.reshape(-1), traj.new_zeros(1)])
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            return traj, info
+        return step
+
+    def vi_step(c, thS, WS):
+        return lambda: ops.vi_predictive(c.y0, c.t, c.ins, thS, WS, **c.kw)
+
+    peaks_box = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    peaks_r2 = load_json(os.path.join(ROOT, "profiles", "r02_measured_peaks.json"))
+    traffic_db = load_json(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))
+    tf32_peak = (peaks_r2.get("tf32") or {}).get("sustained_tflops")
+    if tf32_peak:
+        tensor_peak, tensor_src = float(tf32_peak), (
+            "MEASURED cuBLAS TF32 dense, sustained (torch.matmul 8192^3 float32 with allow_tf32, back to back for 4 s; "
+            f"burst {(peaks_r2['tf32']).get('burst_tflops', 0):.0f}): profiles/r02_measured_peaks.json, made by tools/measure_peaks.py "
+            "on this pool's B200 the way MEASURED_PEAKS.json was made.  achieved counts ALGORITHMIC flops (158 976 + 700 per "
+            "attempt); the 3xTF32 split issues 3 tensor passes per algorithmic pass")
+    else:
+        tensor_peak = float(peaks_box.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        tensor_src = "fallback: MEASURED_PEAKS.json bf16_tflops_sustained / 2 (no measured TF32 figure found)"
+    fp32_peak = (peaks_r2.get("fp32_simt") or {}).get("sustained_tflops")
+
+    def tensor_roof(attempts, ms_kernel, factor, kernel, passes=3):
+        flops = attempts * FLOP_ATTEMPT_HYBRID * factor
+        ach = flops / (ms_kernel * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+                "kernel": kernel, "kernel_ms": ms_kernel, "algorithmic_flop_per_launch": flops,
+                "tensor_passes_per_algorithmic_pass": passes}
+
+    c = Cohort(w, keep_host=True)
+    bwd, vi = bool(w.get("bwd")), bool(w.get("vi"))
+    warm = max(args.warmup, 3)
+    steps = args.steps
+    if vi:
+        thS_np, WS_np = vi_posterior_samples(w["theta"], w["W"], VI_SAMPLES)
+        thS, WS = torch.from_numpy(thS_np).to(dev), torch.from_numpy(WS_np).to(dev)
+        step = vi_step(c, thS, WS)
+        warm, steps = max(1, min(args.warmup, 1)), max(1, min(args.steps, 3))   # one step = 64 x 1 M rollouts (~seconds)
+    elif bwd:
+        d_g = torch.full((B, T, 6), 1.0 / (B * T * 6), dtype=torch.float32, device=dev)
+        step = fwdbwd_step(c, d_g)
+    else:
+        step = fwd_step(c)
+
+    # ---- headline: kernel-resident timing, inputs already in HBM, K steps, CUDA events ------------
     sampler = ClockSampler(local)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        traj, info = step()
-    ev1.record()
-    barrier()
+    ms_total, out, launches = timed(step, steps, warm)
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    # kernels of ours per step: rollout (+ weight-image prep on the tensor-core path); the adjoint adds
-    # two image preps, the sort-key and schedule kernels, the sweep and the partial-gradient reduction
-    # (cub's radix-sort kernels are library code and are not counted)
-    BWD_LAUNCHES = 6
-    per_step = (2 if (w["nn"] and args.precision != "fp32") else 1) + (BWD_LAUNCHES if bwd else 0)
-    launches = args.steps * per_step
+    info = out[-1]
+    attempts_per_step = attempts_of(info)
+    if not vi:
+        assert bool((info.status == 0).all()), "synthetic workload must integrate without failures"
+    ms_total, attempts_all = reduce_max_sum(ms_total, attempts_per_step)
+    value = attempts_all * steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers in, host result out, through the C ABI host entry --------------
-    cfg, _ = ops.prepare(h_y0, h_t, h_ins, h_theta, h_W, 64, 4, torch.device("cpu"))
-    cfg.solver = ops.SOLVERS[w["solver"]]
-    cfg.n_substeps = w.get("n_substeps", 1)
-    cfg.rtol, cfg.atol = w.get("rtol", 1e-6), w.get("atol", 1e-8)
-    cfg.kink_mode = ops.KINKS[w.get("kinks", "clip")]
-    if cfg.mlp != _lib.MLP_NONE:
-        cfg.mlp = ops.PRECISIONS[args.precision]
-    h_traj = torch.empty((B, T, 6), dtype=torch.float32).pin_memory()
-    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
-    h_cnt = torch.empty((2, B), dtype=torch.int32).pin_memory()
-    vp = lambda x: None if x is None else ctypes.c_void_p(x.data_ptr())
-    stream = torch.cuda.current_stream(dev)
+    # ---- e2e: host buffers in, host result out, through the C ABI host entry (forward workloads) ----
+    e2e = None
+    if not bwd and not vi:
+        h = c.host
+        cfg, _ = ops.prepare(h["y0"], h["t"], h["ins"], h["theta"], h["W"], 64, 4, torch.device("cpu"))
+        cfg.solver = ops.SOLVERS[w["solver"]]
+        cfg.n_substeps = w.get("n_substeps", 1)
+        cfg.rtol, cfg.atol = w.get("rtol", 1e-6), w.get("atol", 1e-8)
+        cfg.kink_mode = ops.KINKS[w.get("kinks", "clip")]
+        if cfg.mlp != _lib.MLP_NONE:
+            cfg.mlp = ops.PRECISIONS[args.precision]
+        h_traj = torch.empty((B, T, 6), dtype=torch.float32).pin_memory()
+        h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+        h_cnt = torch.empty((2, B), dtype=torch.int32).pin_memory()
+        vp = lambda x: None if x is None else ctypes.c_void_p(x.data_ptr())
+        stream = torch.cuda.current_stream(dev)
 
-    def e2e_step():
-        rc = L.hode_rollout_fwd_host(ctypes.byref(cfg), vp(h_y0), vp(h_t), vp(h_ins.get("meal")),
-                                     vp(h_ins.get("tVNS")), vp(h_ins.get("GD")), vp(h_theta), vp(h_W),
-                                     vp(h_traj), vp(h_status), vp(h_cnt),
-                                     ctypes.c_void_p(stream.cuda_stream))
-        _lib.check(rc, "hode_rollout_fwd_host")
+        def e2e_step():
+            rc = L.hode_rollout_fwd_host(ctypes.byref(cfg), vp(h["y0"]), vp(h["t"]), vp(h["ins"].get("meal")),
+                                         vp(h["ins"].get("tVNS")), vp(h["ins"].get("GD")), vp(h["theta"]), vp(h["W"]),
+                                         vp(h_traj), vp(h_status), vp(h_cnt), ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "hode_rollout_fwd_host")
 
-    e2e_warm = max(args.warmup, 3)
-    for _ in range(e2e_warm):
-        e2e_step()          # warm-up: stream-ordered pool growth, first touch of the pinned buffers
-    barrier()
-    e2e_steps = max(3, min(args.steps, 5))
-    e2e_each = []
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        t1 = time.perf_counter()
-        e2e_step()          # synchronises its stream before returning
-        e2e_each.append(1e3 * (time.perf_counter() - t1))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    launches += (e2e_steps + e2e_warm) * (2 if (w["nn"] and args.precision != "fp32") else 1)
-    e2e_attempts = float(h_cnt.sum().item())
-    h2d = sum(x.numel() * 4 for x in [h_y0, h_t, h_theta] + list(h_ins.values()) + ([h_W] if h_W is not None else []))
-    d2h = h_traj.numel() * 4 + h_status.numel() * 4 + h_cnt.numel() * 4
+        for _ in range(3):
+            e2e_step()          # warm-up: stream-ordered pool growth, first touch of the pinned buffers
+        barrier()
+        e2e_steps = max(3, min(args.steps, 5))
+        e2e_each = []
+        n0 = int(L.hode_launch_count())
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            t1 = time.perf_counter()
+            e2e_step()          # synchronises its stream before returning
+            e2e_each.append(1e3 * (time.perf_counter() - t1))
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        launches += int(L.hode_launch_count()) - n0
+        e2e_s, e2e_attempts_all = reduce_max_sum(e2e_s, float(h_cnt.sum().item()))
+        h2d = sum(x.numel() * 4 for x in [h["y0"], h["t"], h["theta"]] + list(h["ins"].values()) + ([h["W"]] if h["W"] is not None else []))
+        d2h = h_traj.numel() * 4 + h_status.numel() * 4 + h_cnt.numel() * 4
+        e2e = {"value": e2e_attempts_all * e2e_steps / e2e_s, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_each_rank0": [round(x, 2) for x in e2e_each],
+               "api": "hode_rollout_fwd_host (pinned host buffers in, host trajectories out)",
+               "host_numa_node_rank0": numa_node}
+        del h_traj
+    elif bwd:
+        # the gradient path's e2e: host inputs in (pinned), loss + gradients out to the host — what a training step moves
+        h = c.host
+        h_out = torch.empty(17 + w["W"].size + 1, dtype=torch.float32).pin_memory()
+        obs = torch.zeros((B, T, 6), dtype=torch.float32, device=dev)
 
-    # ---- the other legs of the metric, per GPU, short (skipped with --no-extra) -------------
-    also = {}
-    if not args.no_extra and w["nn"] and not bwd:
-        def timed(fn, n):
-            fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(n):
-                out = fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / n, out
-        Bx = min(B, 262144)
-        sl = slice(0, Bx)
-        x_ins = {k: v[sl].contiguous() for k, v in d_ins.items()}
-        x_g = torch.full((Bx, T, 6), 1.0 / (Bx * T * 6), dtype=torch.float32, device=dev)
+        def e2e_step():
+            y0 = h["y0"].to(dev, non_blocking=True)
+            ins = {k: v.to(dev, non_blocking=True) for k, v in h["ins"].items()}
+            loss, _, g_theta, g_W, _, info_e = ops.data_loss_step(y0, h["t"].to(dev, non_blocking=True), ins,
+                                                                  h["theta"].to(dev, non_blocking=True),
+                                                                  h["W"].to(dev, non_blocking=True), obs,
+                                                                  max_saved_steps=REC_CAPACITY, **c.kw)
+            packed = torch.cat([g_theta.reshape(-1), g_W.reshape(-1), loss.reshape(-1)])
+            if world > 1:
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            h_out.copy_(packed, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return info_e
+        for _ in range(2):
+            info_e = e2e_step()
+        barrier()
+        e2e_steps = max(3, min(args.steps, 5))
+        n0 = int(L.hode_launch_count())
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            info_e = e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        launches += int(L.hode_launch_count()) - n0
+        e2e_s, e2e_attempts_all = reduce_max_sum(e2e_s, attempts_of(info_e))
+        h2d = sum(x.numel() * 4 for x in [h["y0"], h["t"], h["theta"], h["W"]] + list(h["ins"].values()))
+        e2e = {"value": e2e_attempts_all * e2e_steps / e2e_s, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": h_out.numel() * 4, "steps": e2e_steps,
+               "api": "ops.data_loss_step = hode_loss_fused_fwd_bwd (pinned host inputs copied in, loss + packed gradients copied out)"}
+        del obs
+    else:
+        # posterior-predictive sweep end to end: host inputs and the S parameter sets in, mean / std out to the host
+        h = c.host
+        h_mean = torch.empty((B, T, 6), dtype=torch.float32).pin_memory()
+        h_std = torch.empty((B, T, 6), dtype=torch.float32).pin_memory()
+        h_thS, h_WS = pin(thS_np), pin(WS_np)
 
-        def fwdbwd():
-            _, info_x, tape = ops.rollout(d_y0[sl], d_t, x_ins, d_theta, d_W, save_steps=True, **kw)
-            g = ops.rollout_bwd(tape, x_g)
-            return info_x, g
-        ms, (info_x, _) = timed(fwdbwd, 2)
-        att = float((info_x.n_accept.sum() + info_x.n_reject.sum()).item())
-        also["fwd_bwd"] = {"value": att / (ms * 1e-3), "unit": "trajectory-steps/s", "per": "GPU",
-                           "trajectories": Bx, "ms_per_step": ms,
-                           "what": "hode_rollout_fwd (3xTF32, steps recorded) + hode_rollout_bwd (tcgen05 discrete "
-                                   "adjoint: 3xTF32 recomputation and delta chain, BF16x3 weight gradients; "
-                                   "grad y0, theta[17], W[13510])",
-                           "algorithmic_tflops": att * 3 * FLOP_ATTEMPT_HYBRID / (ms * 1e-3) / 1e12}
-        launches += 3 * (2 + BWD_LAUNCHES)
-        Sx = 8
-        Bv = min(B, 131072)
-        slv = slice(0, Bv)
-        v_ins = {k: v[slv].contiguous() for k, v in d_ins.items()}
-        rng = np.random.default_rng(7)
-        thS = torch.from_numpy((w["theta"][None, :] * (1 + 0.02 * rng.normal(0, 1, (Sx, 17)))).astype(np.float32)).to(dev)
-        WS = torch.from_numpy((w["W"][None, :] + 0.01 * rng.normal(0, 1, (Sx, w["W"].size))).astype(np.float32)).to(dev)
+        def e2e_step():
+            y0 = h["y0"].to(dev, non_blocking=True)
+            ins = {k: v.to(dev, non_blocking=True) for k, v in h["ins"].items()}
+            mean, std, info_e = ops.vi_predictive(y0, h["t"].to(dev, non_blocking=True), ins, h_thS.to(dev, non_blocking=True),
+                                                  h_WS.to(dev, non_blocking=True), **c.kw)
+            h_mean.copy_(mean, non_blocking=True)
+            h_std.copy_(std, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return info_e
+        info_e = e2e_step()
+        barrier()
+        n0 = int(L.hode_launch_count())
+        t0 = time.perf_counter()
+        info_e = e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        launches += int(L.hode_launch_count()) - n0
+        e2e_s, e2e_attempts_all = reduce_max_sum(e2e_s, attempts_of(info_e))
+        h2d = sum(x.numel() * 4 for x in [h["y0"], h["t"], h_thS, h_WS] + list(h["ins"].values()))
+        e2e = {"value": e2e_attempts_all / e2e_s, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 2 * h_mean.numel() * 4, "steps": 1,
+               "api": "ops.vi_predictive = hode_vi_predictive (pinned host inputs + 64 parameter sets copied in, mean / std copied out)"}
+        del h_mean, h_std
 
-        def vi():
-            return ops.vi_predictive(d_y0[slv], d_t, v_ins, thS, WS, **kw)
-        ms, (_, _, info_v) = timed(vi, 1)
-        att = float((info_v.n_accept.sum() + info_v.n_reject.sum()).item())
-        also["vi_predictive"] = {"value": att / (ms * 1e-3), "unit": "trajectory-steps/s", "per": "GPU",
-                                 "samples": Sx, "trajectories": Bv, "ms_per_step": ms,
-                                 "what": "hode_vi_predictive: S parameter sets x B trajectories, mean/std "
-                                         "reduced in-kernel (3xTF32)"}
-        launches += 2 * 2
-
-    # ---- reduce over ranks: MAX time, SUM work ----------------------------------------------
-    stats = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
-    work = torch.tensor([attempts_per_step, e2e_attempts], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    ms_total, e2e_s = stats.tolist()
-    attempts_all, e2e_attempts_all = work.tolist()
-    value = attempts_all * args.steps / (ms_total * 1e-3)
-    e2e_value = e2e_attempts_all * e2e_steps / e2e_s
+    # ---- the other legs of the metric (default run only), each timed like the headline ----------------
+    legs = {}
+    if not args.no_extra and args.workload == "hybrid_fwd" and not args.traj_per_gpu:
+        # (1) forward + discrete adjoint on the same cohort, with the packed gradient all-reduce when N > 1
+        d_g = torch.full((B, T, 6), 1.0 / (B * T * 6), dtype=torch.float32, device=dev)
+        ms, o2, n_l = timed(fwdbwd_step(c, d_g), min(args.steps, 5), 2)
+        launches += n_l
+        ms, att = reduce_max_sum(ms, attempts_of(o2[-1]))
+        k2 = min(args.steps, 5)
+        leg = tensor_roof(att / world, ms / k2, 3.0, "rollout_tc_kernel<x3,dopri5> (steps recorded) + rollout_bwd_tc_kernel")
+        legs["fwd_bwd"] = {"value": att * k2 / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world, "scaling": "weak",
+                           "trajectories_per_gpu": B, "ms_per_step": ms / k2, "steps": k2,
+                           "collective": "packed NCCL all-reduce of grad theta[17] + grad W[13510] + loss slot inside the timed region"
+                                         if world > 1 else "none (single GPU)",
+                           "what": "hode_rollout_fwd (3xTF32, accepted steps + stage derivatives recorded) + hode_rollout_bwd "
+                                   "(tcgen05 discrete adjoint: grad y0, theta[17], W[13510])",
+                           "roofline": {k: leg[k] for k in ("achieved", "peak", "frac", "unit")}}
+        del d_g
+        # (2) config 3 as BASELINE.json states it: 262 144 trajectories in total over the N GPUs (strong scaling);
+        #     at N = 1 the real per-GPU shard of the 8-GPU job (32 768) is timed instead
+        Bs = 262144 // world if world > 1 else 32768
+        ws = make_workload("hybrid_fwdbwd", Bs, seed=2000 + rank, world=world)
+        cs = Cohort(ws)
+        d_gs = torch.full((Bs, T, 6), 1.0 / (Bs * T * 6), dtype=torch.float32, device=dev)
+        for name, fn, fac in (("fwd", fwd_step(cs), 1.0), ("fwd_bwd", fwdbwd_step(cs, d_gs), 3.0)):
+            ms, o3, n_l = timed(fn, 5, 2)
+            launches += n_l
+            ms, att = reduce_max_sum(ms, attempts_of(o3[-1]))
+            legs[f"config3_shard_{name}"] = {
+                "value": att * 5 / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world,
+                "scaling": "strong (262 144 trajectories in total)" if world > 1 else "n/a (one 32 768-trajectory shard of the 8-GPU job)",
+                "trajectories_per_gpu": Bs, "ms_per_step": ms / 5, "steps": 5,
+                "frac": att / world * FLOP_ATTEMPT_HYBRID * fac / (ms / 5 * 1e-3) / 1e12 / tensor_peak}
+        del cs, d_gs
+        # (3) config 4: 64 posterior samples x 1 048 576 trajectories per box, mean / std reduced in the kernel
+        wv = make_workload("vi_predictive", 0, seed=3000 + rank, world=world)
+        cv = Cohort(wv)
+        th_np, W_np = vi_posterior_samples(wv["theta"], wv["W"], VI_SAMPLES)
+        thS, WS = torch.from_numpy(th_np).to(dev), torch.from_numpy(W_np).to(dev)
+        ms, o4, n_l = timed(vi_step(cv, thS, WS), 1, 1)
+        launches += n_l
+        info_v = o4[-1]
+        ms, att = reduce_max_sum(ms, attempts_of(info_v))
+        n_fail = torch.tensor([float((info_v.status != 0).sum().item())], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(n_fail)
+        leg = tensor_roof(att / world, ms, 1.0, "rollout_tc_kernel<x3,dopri5> (fused Welford mean/std)")
+        legs["vi_predictive_64x1M"] = {
+            "value": att / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world, "scaling": "strong (1 048 576 trajectories per box)",
+            "samples": VI_SAMPLES, "trajectories_per_gpu": wv["B"], "trajectories_total": wv["B"] * world, "ms_per_step": ms, "steps": 1,
+            "failed_units": float(n_fail.item()),
+            "what": "hode_vi_predictive: 64 parameter sets x B trajectories, unbiased mean / std over the samples reduced in the kernel; "
+                    "posterior = point parameters with std 0.1 x prior (configs/4gi_vi.yaml priors, network prior std 0.1)",
+            "roofline": {k: leg[k] for k in ("achieved", "peak", "frac", "unit")}}
+        del cv, thS, WS
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-        sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-        ms_kernel = ms_total / args.steps          # one launch per step, nothing else on the stream
-        if w["nn"]:
-            flops = attempts_per_step * FLOP_ATTEMPT_HYBRID * (3.0 if bwd else 1.0)
-            achieved = flops / (ms_kernel * 1e-3) / 1e12
-            if args.precision == "fp32":
-                peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
-                peak_src = (f"FP32 FMA pipe: {sm_count} SM x 128 lanes x 2 flop x {sm_max:.0f} MHz "
-                            "(derived; MEASURED_PEAKS.json has no FP32 CUDA-core figure)")
-                bound = "fp32"
-            else:
-                peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
-                peak_src = ("TF32 dense = measured sustained cuBLAS bf16 / 2 (MEASURED_PEAKS.json "
-                            "bf16_tflops_sustained; the kernel is timed inside a long step). achieved "
-                            "counts ALGORITHMIC flops (158 976 + 700 per attempt); the 3xTF32 "
-                            "emulation issues 3 tensor passes per algorithmic pass"
-                            if peaks else "fallback 1400/2 TFLOP/s")
-                bound = "tensor"
-            # dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu
-            # --set full capture of this exact configuration (profiles/r01_rollout_tc_tf32x3_ncu_full.txt)
-            traffic = 532.13e6 if (args.workload == "hybrid_fwd" and B == 262144 and args.precision == "tf32x3") else None
-            roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "algorithmic_bytes_per_launch": B * BYTES_PER_TRAJ(T, len(w["ins"]), False),
-                    "peak_source": peak_src,
-                    "kernel": ("rollout_simt_kernel<2>" if args.precision == "fp32" else "rollout_tc_kernel<x3,dopri5>")
-                              + (" + rollout_bwd_tc_kernel" if bwd else ""),
-                    "tensor_passes_per_algorithmic_pass": 3 if args.precision == "tf32x3" else 1,
-                    "kernel_ms": ms_kernel,
-                    "algorithmic_flop_per_launch": flops}
+        sm_max = clocks.get("sm_max_mhz") or peaks_box.get("sm_max_mhz") or 1965.0
+        ms_step = ms_total / steps
+        n_in = len(w["ins"])
+        alg_bytes = B * BYTES_PER_TRAJ(T, n_in, False)
+        if w["nn"] and args.precision != "fp32":
+            kname = ("rollout_tc_kernel<x3,dopri5> (fused Welford mean/std)" if vi else
+                     "rollout_tc_kernel<x3,dopri5>" + (" + rollout_bwd_tc_kernel" if bwd else ""))
+            passes = {"tf32x3": 3, "tf32bf16": 2, "tf32": 1}[args.precision]
+            roof = tensor_roof(attempts_per_step, ms_step, 3.0 if bwd else 1.0, kname, passes)
+            roof["peak_source"] = tensor_src
+            key = f"{args.workload}:{B}:{args.precision}"
+            roof["traffic"] = traffic_db.get(key, {}).get("dram_bytes")
+            roof["traffic_source"] = traffic_db.get(key, {}).get("source")
+            roof["algorithmic_bytes_per_launch"] = alg_bytes if not vi else B * (24 + 4 * T * n_in + 2 * 24 * T)
+        elif w["nn"]:
+            peak = float(fp32_peak) if fp32_peak else sm_count * 128 * 2 * sm_max * 1e6 / 1e12
+            flops = attempts_per_step * FLOP_ATTEMPT_HYBRID
+            ach = flops / (ms_step * 1e-3) / 1e12
+            roof = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "kernel": "rollout_simt_kernel<2>", "kernel_ms": ms_step, "traffic": None,
+                    "peak_source": "measured cuBLAS SGEMM without TF32 (profiles/r02_measured_peaks.json fp32_simt)" if fp32_peak
+                                   else f"derived: {sm_count} SM x 128 lanes x 2 flop x {sm_max:.0f} MHz"}
         else:
-            nbytes = B * BYTES_PER_TRAJ(T, len(w["ins"]), False)
-            achieved = nbytes / (ms_kernel * 1e-3) / 1e9
-            peak = float(peaks.get("hbm_gbs", 6650.0))
+            # mechanistic RK4: FP32-issue-bound (3 divisions and up to 3 pow per RHS), outputs only at the observation times
+            peak = float(fp32_peak) if fp32_peak else sm_count * 128 * 2 * sm_max * 1e6 / 1e12
             flops = attempts_per_step * FLOP_STEP_RK4_MECH
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "kernel": "rollout_simt_kernel<0>", "kernel_ms": ms_kernel,
-                    "algorithmic_bytes_per_launch": nbytes,
-                    "fp32_tflops": flops / (ms_kernel * 1e-3) / 1e12}
+            ach = flops / (ms_step * 1e-3) / 1e12
+            roof = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "kernel": "rollout_simt_kernel<0>", "kernel_ms": ms_step,
+                    "traffic": traffic_db.get(f"{args.workload}:{B}:fp32", {}).get("dram_bytes"),
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "hbm_gbs": alg_bytes / (ms_step * 1e-3) / 1e9, "hbm_peak_gbs": float(peaks_box.get("hbm_gbs", 6650.0)),
+                    "peak_source": ("FP32 pipe: measured cuBLAS SGEMM without TF32 (profiles/r02_measured_peaks.json fp32_simt); the kernel is "
+                                    "FP32-issue-bound (ncu: profiles/r02_rollout_simt_mech_ncu_full.txt), its HBM traffic is "
+                                    "inputs + observation-time outputs only (hbm_gbs / hbm_peak_gbs)") if fp32_peak
+                                   else f"derived: {sm_count} SM x 128 lanes x 2 flop x {sm_max:.0f} MHz"}
+        if legs:
+            roof["legs"] = legs
         line = {
             "metric": "trajectory_steps_per_sec", "value": value, "unit": "trajectory-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if vi else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "mlp_arithmetic": args.precision if w["nn"] else "none",
-                       "trajectories_total": B * world, "attempts_per_trajectory": attempts_per_step / B,
+                       "trajectories_per_gpu": B, "trajectories_total": B * world,
+                       "attempts_per_trajectory": attempts_per_step / B / (VI_SAMPLES if vi else 1),
                        "l2_policy": "inputs+outputs per step exceed L2 (no flush needed): "
-                                    f"{(B * BYTES_PER_TRAJ(T, len(w['ins']), False)) / 2**20:.0f} MiB"},
+                                    f"{alg_bytes / 2**20:.0f} MiB"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_each_rank0": [round(x, 2) for x in e2e_each],
-                    "api": "hode_rollout_fwd_host (pinned host buffers in, host trajectories out)",
-                    "host_numa_node_rank0": numa_node},
+            "e2e": e2e,
             "gpu_launches": launches,
+            "gpu_launches_how": "hode_launch_count(): every kernel libhode.so launched inside the timed regions (headline, e2e, legs)",
             "roofline": roof,
-            "trajectories_per_sec": B * world * args.steps / (ms_total * 1e-3),
+            "trajectories_per_sec": B * world * steps / (ms_total * 1e-3) * (VI_SAMPLES if vi else 1),
         }
-        if also:
-            line["also"] = also
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n = cpu_sample_size(w, threads, target_s=12.0)
             s, dt = cpu_oracle_run(w, n, threads)
             line["cpu_baseline"] = {
                 "value": s / dt, "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
-                "sample": f"{n} of {B} trajectories of the same workload, oracle/hode_oracle.c "
+                "sample": f"{n} of {B} trajectories of the same workload (forward rollout, one parameter set), oracle/hode_oracle.c "
                           f"(float32 RHS + float64 SciPy-RK45 stepping), {threads} pthreads, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -32,7 +32,7 @@ EXPORTS = [
     "hode_version", "hode_last_error_string", "hode_mlp_param_count", "hode_workspace_bytes",
     "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs", "hode_rhs_vjp",
     "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd", "hode_generate_4gi",
-    "hode_step_record_floats", "hode_step_record_capacity",
+    "hode_step_record_floats", "hode_step_record_capacity", "hode_launch_count",
 ]
 
 
@@ -72,6 +72,7 @@ def lib() -> ctypes.CDLL:
         if not hasattr(L, name):
             raise HodeError(f"libhode.so does not export {name}")
     L.hode_version.restype = ctypes.c_int
+    L.hode_launch_count.restype = ctypes.c_int64
     L.hode_last_error_string.restype = ctypes.c_char_p
     L.hode_mlp_param_count.restype = ctypes.c_int64
     L.hode_mlp_param_count.argtypes = [ctypes.c_int32, ctypes.c_int32]

@@ -735,6 +735,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int c
 cudaError_t launch_reduce_partials(const float* partials, int ctas_per_set, int S, int P, float* grad_W,
                                    float* grad_theta, cudaStream_t stream) {
   const int n = P + HODE_N_THETA;
+  count_launch();
   reduce_partials_kernel<<<dim3((n + 255) / 256, S), 256, 0, stream>>>(partials, ctas_per_set, P, grad_W, grad_theta);
   return cudaGetLastError();
 }
@@ -795,6 +796,7 @@ cudaError_t launch_rollout_bwd(const RolloutArgs& A, bool has_nn, const float* g
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
+    count_launch();
     kern<<<grid, ABLK, p.smem, stream>>>(G);
     return cudaGetLastError();
   };
@@ -805,6 +807,7 @@ cudaError_t launch_rollout_bwd(const RolloutArgs& A, bool has_nn, const float* g
     e = has_nn ? launch(rollout_bwd_kernel<HODE_SOLVER_DOPRI5, true>) : launch(rollout_bwd_kernel<HODE_SOLVER_DOPRI5, false>);
   if (e != cudaSuccess) return e;
   const int n = A.P + HODE_N_THETA;
+  count_launch();
   reduce_partials_kernel<<<dim3((n + 255) / 256, A.S), 256, 0, stream>>>(G.partials, p.grid_x, A.P, grad_W, grad_theta);
   return cudaGetLastError();
 }
@@ -825,12 +828,14 @@ cudaError_t launch_rhs_vjp(const RolloutArgs& A, bool has_nn, const float* t, co
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
+    count_launch();
     kern<<<grid, ABLK, p.smem, stream>>>(G);
     return cudaGetLastError();
   };
   cudaError_t e = has_nn ? launch(rhs_vjp_kernel<true>) : launch(rhs_vjp_kernel<false>);
   if (e != cudaSuccess) return e;
   const int n = A.P + HODE_N_THETA;
+  count_launch();
   reduce_partials_kernel<<<dim3((n + 255) / 256, 1), 256, 0, stream>>>(G.partials, p.grid_x, A.P, grad_W, grad_theta);
   return cudaGetLastError();
 }

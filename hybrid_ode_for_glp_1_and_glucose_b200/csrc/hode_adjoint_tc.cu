@@ -1312,6 +1312,7 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const floa
   const int fwd_mode = mlp_mode == HODE_MLP_TF32BF16 ? HODE_MLP_TF32BF16 : HODE_MLP_TF32X3;
   cudaError_t e = tc_prepare_fwd_images(A.W, imgs, A.S, A.L, A.P, fwd_mode, stream);
   if (e != cudaSuccess) return e;
+  count_launch();
   prep_tc_bwd_image_kernel<<<A.S, 256, 0, stream>>>(A.W, imgs + (size_t)A.S * p.fwd_floats, A.L, A.P, p.bwd_floats);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -1320,6 +1321,7 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const floa
     int s_bits = 0;
     while ((1L << s_bits) < (long)A.S) ++s_bits;
     const int sorted = (s_bits + (int)SORT_N_BITS <= 32) ? 1 : 0;
+    count_launch();
     adj_sort_keys_kernel<<<(unsigned)((units + 255) / 256), 256, 0, stream>>>(A.save_n, keys_in, vals_in, (long)units,
                                                                               A.B, sorted);
     e = cudaGetLastError();
@@ -1335,6 +1337,7 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const floa
       e = cudaMemcpyAsync(perm, vals_in, units * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
       if (e != cudaSuccess) return e;
     }
+    count_launch();
     adj_schedule_kernel<<<A.S, 256, 0, stream>>>(sched_keys, A.B, p.n_tiles, p.grid_x, sorted, owner, sched_off,
                                                  sched_tiles);
     e = cudaGetLastError();
@@ -1343,10 +1346,12 @@ cudaError_t launch_rollout_bwd_tc(const RolloutArgs& A, int mlp_mode, const floa
   if (fwd_mode == HODE_MLP_TF32BF16) {
     e = cudaFuncSetAttribute(rollout_bwd_tc_kernel<MLP_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
+    count_launch();
     rollout_bwd_tc_kernel<MLP_MIXED><<<dim3(p.grid_x, p.grid_y), ADJ_THREADS, p.smem, stream>>>(G);
   } else {
     e = cudaFuncSetAttribute(rollout_bwd_tc_kernel<MLP_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
+    count_launch();
     rollout_bwd_tc_kernel<MLP_X3><<<dim3(p.grid_x, p.grid_y), ADJ_THREADS, p.smem, stream>>>(G);
   }
   e = cudaGetLastError();

@@ -7,7 +7,15 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "hode_kernels.h"
+
+namespace hode {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace hode
+using hode::count_launch;
 
 namespace {
 
@@ -134,6 +142,8 @@ int check_inputs(const hode_cfg* c, const float* u_meal, const float* u_tvns, co
 extern "C" {
 
 int hode_version(void) { return HODE_ABI_VERSION; }
+
+int64_t hode_launch_count(void) { return (int64_t)hode::g_launches.load(std::memory_order_relaxed); }
 
 const char* hode_last_error_string(void) { return g_err; }
 
@@ -361,10 +371,12 @@ int hode_loss_fused_fwd_bwd(const hode_cfg* cfg, const float* y0, const float* t
                         fwd_workspace_bytes, stream);
   if (rc) return rc;
   float* partial = reinterpret_cast<float*>(bwd_workspace);
+  count_launch();
   mse_grad_kernel<<<dim3((unsigned)n_blocks, (unsigned)S), MSE_BLOCK, 0, st>>>(traj, obs, grad_traj_scratch, partial,
                                                                              n_per_set, (float)(2.0 / (double)n_per_set));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "hode_loss_fused_fwd_bwd residual launch");
+  count_launch();
   mse_final_kernel<<<S, MSE_BLOCK, 0, st>>>(partial, n_blocks, 1.0 / (double)n_per_set, loss);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "hode_loss_fused_fwd_bwd reduction launch");

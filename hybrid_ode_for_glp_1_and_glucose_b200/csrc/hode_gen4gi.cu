@@ -174,6 +174,7 @@ cudaError_t launch_gen4gi(int n, int T, double dt_hours, int patient_type, doubl
   d.Ke0ins = exp(-0.159); d.VM_GLP = exp(7.97); d.KM_GLP = exp(4.91);
   d.EMAX_1 = exp(2.37); d.EC50_1 = exp(3.29); d.EC50_4 = exp(4.59);
   if (n <= 0) return cudaSuccess;
+  count_launch();
   gen4gi_kernel<<<(n + 127) / 128, 128, 0, stream>>>(g, d, n, T, dt_hours, rtol, atol, baselines, meal_rate, out, status);
   return cudaGetLastError();
 }

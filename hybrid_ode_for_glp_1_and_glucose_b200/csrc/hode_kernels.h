@@ -8,6 +8,9 @@
 
 namespace hode {
 
+// every kernel launch of the library is counted (hode_launch_count: what bench.py reports as gpu_launches)
+void count_launch();
+
 // one trajectory per thread, FP32 CUDA cores (hode_rollout_simt.cu)
 cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t stream);
 

@@ -585,16 +585,19 @@ cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t
   cudaError_t e;
   switch (kind) {
     case 0:
+      count_launch();
       rollout_simt_kernel<0><<<grid, block, smem, stream>>>(A);
       break;
     case 1:
       e = cudaFuncSetAttribute(rollout_simt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
+      count_launch();
       rollout_simt_kernel<1><<<grid, block, smem, stream>>>(A);
       break;
     default:
       e = cudaFuncSetAttribute(rollout_simt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
+      count_launch();
       rollout_simt_kernel<2><<<grid, block, smem, stream>>>(A);
       break;
   }
@@ -614,16 +617,19 @@ cudaError_t launch_rhs(const RolloutArgs& A, int mlp_mode, const float* t, const
   cudaError_t e;
   switch (kind) {
     case 0:
+      count_launch();
       rhs_kernel<0><<<grid, block, smem, stream>>>(R, t, state, out);
       break;
     case 1:
       e = cudaFuncSetAttribute(rhs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
+      count_launch();
       rhs_kernel<1><<<grid, block, smem, stream>>>(R, t, state, out);
       break;
     default:
       e = cudaFuncSetAttribute(rhs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
+      count_launch();
       rhs_kernel<2><<<grid, block, smem, stream>>>(R, t, state, out);
       break;
   }

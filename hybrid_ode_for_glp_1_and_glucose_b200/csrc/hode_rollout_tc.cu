@@ -95,6 +95,7 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
 }
 
 cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, int mlp_mode, cudaStream_t stream) {
+  count_launch();
   prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats(L), mlp_mode == HODE_MLP_TF32BF16 ? 1 : 0);
   return cudaGetLastError();
 }
@@ -815,6 +816,7 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
       (A.in_mode[0] == HODE_IN_SERIES || A.in_mode[1] == HODE_IN_SERIES || A.in_mode[2] == HODE_IN_SERIES)) {
     unsigned long long* masks = reinterpret_cast<unsigned long long*>(
         reinterpret_cast<char*>(queue) + (((size_t)A.S * sizeof(int) + 255) & ~(size_t)255));
+    count_launch();
     kink_mask_kernel<<<(unsigned)((A.B + 7) / 8), 256, 0, stream>>>(A, masks);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -836,6 +838,7 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+    count_launch();
     kern<<<grid, 2 * TILE * TILES_PER_CTA, smem, stream>>>(A, img, img_floats, queue);
     return cudaSuccess;
   };

@@ -82,8 +82,12 @@ class VariationalInference:
 
     def train(self, train_loader, val_loader=None, epochs: int = 100, n_samples: int = 5,
               early_stopping_patience: int = 10, verbose: bool = True):
-        """Epoch loop with early stopping on the validation ELBO (reference :157-260)."""
-        best, wait, self.best_state = -float("inf"), 0, None
+        """Epoch loop of the reference (inference/vi.py:157-260), statement for statement where it matters: early
+        stopping and the best-state bookkeeping run ONLY with a validation loader; the history is appended after
+        the early-stop check (a run that stops early does not record its last epoch); `best_state` is the live
+        state_dict, as in the reference (:237) — its tensors alias the parameters, so the final `load_state_dict`
+        leaves the last epoch's values in place, exactly as the reference does."""
+        best_val_elbo, patience_counter = -float("inf"), 0
         for epoch in range(epochs):
             sums = {"elbo": 0.0, "kl": 0.0, "log_likelihood": 0.0}
             n = 0
@@ -93,23 +97,28 @@ class VariationalInference:
                     sums[k] += m[k]
                 n += 1
             for k in sums:
-                self.history[k].append(sums[k] / max(n, 1))
-            score = self.history["elbo"][-1]
+                sums[k] /= max(n, 1)
+            val_elbo = None
             if val_loader is not None:
                 with torch.no_grad():
                     vals = [self.elbo(self._to_device(b), n_samples)[0].item() for b in val_loader]
-                score = float(np.mean(vals)) if vals else score
-            if verbose:
-                logger.info(f"epoch {epoch}: elbo {self.history['elbo'][-1]:.4f} score {score:.4f}")
-            if score > best:
-                best, wait = score, 0
-                self.best_state = {k: v.detach().clone()
-                                   for k, v in self.variational_params.state_dict().items()}
-            else:
-                wait += 1
-                if wait >= early_stopping_patience:
+                val_elbo = float(np.sum(vals)) / max(len(vals), 1)
+                if val_elbo > best_val_elbo:
+                    best_val_elbo, patience_counter = val_elbo, 0
+                    self.best_state = self.variational_params.state_dict()
+                else:
+                    patience_counter += 1
+                if patience_counter >= early_stopping_patience:
+                    logger.info(f"Early stopping at epoch {epoch + 1}")
                     break
-        if self.best_state is not None:
+            for k in sums:
+                self.history[k].append(sums[k])
+            if verbose and (epoch + 1) % 10 == 0:
+                logger.info(f"Epoch {epoch + 1}: Train ELBO={sums['elbo']:.4f}, KL={sums['kl']:.4f}, "
+                            f"LL={sums['log_likelihood']:.4f}")
+                if val_elbo is not None:
+                    logger.info(f"  Val ELBO={val_elbo:.4f}")
+        if val_loader is not None and hasattr(self, "best_state"):
             self.variational_params.load_state_dict(self.best_state)
 
     def _to_device(self, batch):

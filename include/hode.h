@@ -126,6 +126,10 @@ typedef struct hode_cfg {
 /* ABI version of the loaded library. */
 int hode_version(void);
 
+/* Number of CUDA kernels this library has launched in this process so far (library kernels such as cub's radix
+ * sort are not counted): bench.py reports the difference over its timed regions as gpu_launches. */
+int64_t hode_launch_count(void);
+
 /* Human-readable text for the last non-zero return on this host thread. */
 const char* hode_last_error_string(void);
 

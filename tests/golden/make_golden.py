@@ -254,8 +254,60 @@ def loss_cases():
              loss=np.float64(loss.item()), grad_W=g_W.astype(np.float32))
 
 
+def vi_cases():
+    """The reference's variational family and VI driver on a tiny problem: VariationalParameters.sample under a
+    fixed seed, kl_divergence, get_flattened_params (models/bayes.py:103-175), VariationalInference.elbo and
+    posterior_predictive (inference/vi.py:60-118,274-312).  The reference integrates with its default solver
+    ('dopri5' -> SciPy DOP853, rtol 1e-6): the mirrors are compared at 1e-4."""
+    from inference.vi import VariationalInference
+    prior = {"ode_a_GI": {"mean": 0.0104, "std": 0.002}, "ode_k_I": {"mean": 0.025, "std": 0.005},
+             "ode_rho": {"mean": 0.003, "std": 0.001}, "ode_E_max": {"mean": 0.1, "std": 0.02},
+             "ode_EC_50": {"mean": 50.0, "std": 5.0}, "ode_V_max": {"mean": 9.0, "std": 2.0},
+             "ode_K_m": {"mean": 7.0, "std": 1.5}, "ode_k_L": {"mean": 0.02, "std": 0.005}}   # configs/4gi_vi.yaml:26-33 (+ EC_50)
+    torch.manual_seed(3)
+    m = HybridODENN(nn_hidden=16, nn_layers=2, use_variational=True, prior_params=prior, device=CPU)
+    vp = m.variational_params
+    names = list(vp.param_shapes.keys())
+    with torch.no_grad():   # a posterior whose network does something and whose widths differ per tensor
+        for n in names:
+            if n.startswith("nn_"):
+                vp.means[n].normal_(0.0, 0.08)
+                vp.log_stds[n].fill_(float(np.log(0.01)))
+            vp.log_stds[n].add_(0.2 * torch.randn_like(vp.log_stds[n]))
+    flat = lambda d: np.concatenate([d[n].detach().numpy().reshape(-1).astype(np.float32) for n in names])
+    sizes = np.array([int(np.prod(vp.param_shapes[n])) if len(vp.param_shapes[n]) else 1 for n in names])
+    torch.manual_seed(5)
+    smp = vp.sample(2)
+    kl = float(vp.kl_divergence())
+    mu_f, ls_f = vp.get_flattened_params()
+    rng = np.random.default_rng(31)
+    B, T = 2, 7
+    y0 = np.stack([7.0 * rng.normal(1, 0.1, B), 50.0 * rng.normal(1, 0.15, B), 25.0 * rng.normal(1, 0.15, B),
+                   10.0 * rng.normal(1, 0.15, B), np.zeros(B), np.ones(B)], axis=1).astype(np.float32)
+    t = np.linspace(0, 0.5, T).astype(np.float32)
+    meal = np.zeros((B, T), dtype=np.float32)
+    meal[:, 2] = 1.0
+    tv = np.zeros((B, T), dtype=np.float32)
+    tv[0, 3:] = 1.0
+    obs = (y0[:, None, :] * (1 + 0.05 * rng.normal(0, 1, (B, T, 6)))).astype(np.float32)
+    batch = {"initial_state": torch.tensor(y0), "observations": torch.tensor(obs), "time_points": torch.tensor(t),
+             "external_inputs": {"meal": torch.tensor(meal), "tVNS": torch.tensor(tv)}}
+    vi = VariationalInference(m, device=CPU)
+    torch.manual_seed(7)
+    elbo, comp = vi.elbo(batch, n_samples=2, noise_sigma=0.7)
+    torch.manual_seed(9)
+    mean, std = vi.posterior_predictive(batch["initial_state"], batch["time_points"], batch["external_inputs"], n_samples=3)
+    save("vi_bayes", names=np.array(names), sizes=sizes, prior_names=np.array(sorted(prior)),
+         prior_mean=np.array([prior[k]["mean"] for k in sorted(prior)]), prior_std=np.array([prior[k]["std"] for k in sorted(prior)]),
+         means=flat(vp.means), log_stds=flat(vp.log_stds), sample_seed=5, sample0=flat(smp[0]), sample1=flat(smp[1]),
+         kl=np.float64(kl), flat_mu=mu_f.detach().numpy(), flat_log_std=ls_f.detach().numpy(),
+         y0=y0, t=t, meal=meal, tvns=tv, obs=obs, hidden=16, layers=2,
+         elbo_seed=7, noise_sigma=0.7, elbo=np.float64(float(elbo)), elbo_kl=np.float64(float(comp["kl"])),
+         elbo_ll=np.float64(float(comp["log_likelihood"])), pp_seed=9, pp_mean=mean.numpy(), pp_std=std.numpy())
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (rhs_cases, rollout_fig2, rollout_4gi, rollout_physio, rhs_vjp_cases, loss_cases):
+    for fn in (rhs_cases, rollout_fig2, rollout_4gi, rollout_physio, rhs_vjp_cases, loss_cases, vi_cases):
         if not only or fn.__name__ in only:
             fn()

@@ -134,8 +134,10 @@ def test_dopri5_hybrid_as_accurate_as_the_oracle(dev, oracle, kinks):
     sc = 1e-8 + 1e-6 * np.abs(truth)
     e_gpu = (np.abs(tr - truth) / sc).max(axis=(1, 2))
     e_cpu = (np.abs(orc - truth) / sc).max(axis=(1, 2))
-    assert np.median(e_gpu) < 2 * np.median(e_cpu) + 50
-    assert np.percentile(e_gpu, 90) < 3 * np.percentile(e_cpu, 90) + 100
+    # per-trajectory error against the float64 truth, GPU kernel vs the oracle (= the reference's arithmetic): measured
+    # ratios on these cohorts are 0.9-1.07 at the median and 0.55-1.17 at p90 (profiles/r02_adaptive_error_distributions.txt)
+    assert np.median(e_gpu) <= 1.25 * np.median(e_cpu)
+    assert np.percentile(e_gpu, 90) <= 1.5 * np.percentile(e_cpu, 90)
     att_gpu, att_cpu = (na + nr).mean(), (cn[0] + cn[1]).mean()
     assert abs(att_gpu - att_cpu) / att_cpu < 0.2
 
@@ -356,8 +358,10 @@ def test_tc_dopri5_accuracy_and_refill(dev, oracle):
     sc = 1e-8 + 1e-6 * np.abs(truth)
     e_gpu = (np.abs(tr - truth) / sc).max(axis=(1, 2))
     e_cpu = (np.abs(orc - truth) / sc).max(axis=(1, 2))
-    assert np.median(e_gpu) < 2 * np.median(e_cpu) + 50
-    assert np.percentile(e_gpu, 90) < 3 * np.percentile(e_cpu, 90) + 100
+    # per-trajectory error against the float64 truth, GPU kernel vs the oracle (= the reference's arithmetic): measured
+    # ratios on these cohorts are 0.9-1.07 at the median and 0.55-1.17 at p90 (profiles/r02_adaptive_error_distributions.txt)
+    assert np.median(e_gpu) <= 1.25 * np.median(e_cpu)
+    assert np.percentile(e_gpu, 90) <= 1.5 * np.percentile(e_cpu, 90)
     att_gpu, att_cpu = (na + nr).mean(), (cn[0] + cn[1]).mean()
     assert abs(att_gpu - att_cpu) / att_cpu < 0.2
     assert np.array_equal(tr[:, 0], y0)

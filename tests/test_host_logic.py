@@ -124,6 +124,41 @@ def test_variational_parameters_follow_the_reference_formulas():
         hode.bayes_loss(None, torch.zeros(1))
 
 
+def _vi_model_from_fixture(d, device):
+    """The fixture's posterior loaded into our mirror (same constructor arguments as the reference run)."""
+    prior = {str(k): {"mean": float(m), "std": float(sd)} for k, m, sd in zip(d["prior_names"], d["prior_mean"], d["prior_std"])}
+    m = hode.HybridODENN(nn_hidden=int(d["hidden"]), nn_layers=int(d["layers"]), use_variational=True, prior_params=prior,
+                         device=device)
+    vp = m.variational_params
+    names = [str(n) for n in d["names"]]
+    assert list(vp.param_shapes.keys()) == names, "same parameter names in the same (insertion) order as the reference"
+    off = 0
+    with torch.no_grad():
+        for n, sz in zip(names, d["sizes"]):
+            vp.means[n].copy_(torch.from_numpy(d["means"][off: off + sz]).reshape(vp.means[n].shape))
+            vp.log_stds[n].copy_(torch.from_numpy(d["log_stds"][off: off + sz]).reshape(vp.log_stds[n].shape))
+            off += int(sz)
+    return m, names
+
+
+def test_variational_parameters_match_reference_outputs():
+    """VariationalParameters.sample under the reference's seed, kl_divergence and get_flattened_params against
+    outputs of the reference itself (tests/golden/make_golden.py::vi_cases -> vi_bayes.npz; models/bayes.py:103-175)."""
+    from helpers import golden
+    d = golden("vi_bayes")
+    m, names = _vi_model_from_fixture(d, torch.device("cpu"))
+    vp = m.variational_params
+    torch.manual_seed(int(d["sample_seed"]))
+    smp = vp.sample(2)
+    for k, key in enumerate(("sample0", "sample1")):
+        got = np.concatenate([smp[k][n].detach().numpy().reshape(-1) for n in names])
+        np.testing.assert_array_equal(got.astype(np.float32), d[key])        # same draws, same arithmetic: bit-identical
+    assert abs(float(vp.kl_divergence()) - float(d["kl"])) <= 1e-6 * abs(float(d["kl"]))
+    mu, ls = vp.get_flattened_params()
+    np.testing.assert_array_equal(mu.detach().numpy(), d["flat_mu"])
+    np.testing.assert_array_equal(ls.detach().numpy(), d["flat_log_std"])
+
+
 def test_generator_host_helpers():
     """Meal spreading and the state-column mapping of the cohort generator (no GPU): the reference puts a meal of
     size s at time m into the sampling interval [t_i, t_i+1) that contains m, as the rate s / (t_i+1 - t_i)
