@@ -111,13 +111,14 @@ def test_dopri5_mechanistic_clip_within_tolerance_of_truth(dev, oracle):
                                     kinks="clip", n_threads=8)
     tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, None, solver="dopri5", kinks="clip")
     assert (st == 0).all()
-    # global error after ~15 steps: tens of local-tolerance units (the reference's own error on
-    # its Fig-2 scenario is 18-99 units)
-    assert scaled_err(tr, truth.astype(np.float64)) < 150
+    # without a network every step is smooth and cheap to integrate: the kernel stays within ONE local-tolerance unit
+    # of the float64 truth over the whole horizon (measured 0.38; the float64-stepping oracle: 0.25 —
+    # profiles/r02_adaptive_error_distributions.txt, tools/golden_err_stats.py); bound = 2x the measured value
+    assert scaled_err(tr, truth.astype(np.float64)) < 0.8
     orc, _, cn, _ = oracle.rollout(y0, t, ins, theta, None, kinks="clip", n_threads=8)
     att_gpu, att_cpu = (na + nr).mean(), (cn[0] + cn[1]).mean()
     assert abs(att_gpu - att_cpu) / att_cpu < 0.15
-    assert scaled_err(tr, orc.astype(np.float64)) < 150
+    assert scaled_err(tr, orc.astype(np.float64)) < 0.9          # measured 0.44
 
 
 @pytest.mark.parametrize("kinks", ["clip", "scipy"])
@@ -148,15 +149,17 @@ def test_dopri5_against_reference_golden(dev, oracle):
     tr, st, _, _ = gpu_rollout(dev, d["y0"], d["t"], golden_inputs(d), d["theta"], d["W"],
                                solver="rk45", kinks="scipy")
     assert (st == 0).all()
-    assert scaled_err(tr, d["out_rk45"]) < 100
-    assert scaled_err(tr, d["out_dopri5"]) < 100
+    # measured 40.3 / 39.5 local-tolerance units; the reference's own two solvers differ by 15.3 here (tools/golden_err_stats.py)
+    assert scaled_err(tr, d["out_rk45"]) < 80
+    assert scaled_err(tr, d["out_dopri5"]) < 80
     # Fig-2 scenario: the reference caught the meal spike here; clip mode must agree with it
     d = golden("rollout_fig2")
     tr, st, _, _ = gpu_rollout(dev, d["y0"], d["t"], golden_inputs(d), d["theta"], None,
                                solver="dopri5", kinks="clip")
     assert st[0] == 0
-    assert scaled_err(tr, d["out_rk45"]) < 300
-    assert scaled_err(tr, d["out_dopri5"]) < 300
+    # measured 49.0 / 20.5; the reference's RK45 and DOP853 outputs differ by 47.9 from each other
+    assert scaled_err(tr, d["out_rk45"]) < 100
+    assert scaled_err(tr, d["out_dopri5"]) < 50
     # real 4GI windows: reference steps over the pulses (see tests/test_oracle.py); the kernel
     # in clip mode converges to the truth
     d = golden("rollout_4gi_mech")
@@ -165,7 +168,7 @@ def test_dopri5_against_reference_golden(dev, oracle):
     tr, st, _, _ = gpu_rollout(dev, d["y0"], d["t"], golden_inputs(d), d["theta"], None,
                                solver="dopri5", kinks="clip")
     assert (st == 0).all()
-    assert scaled_err(tr, truth.astype(np.float64)) < 150
+    assert scaled_err(tr, truth.astype(np.float64)) < 140     # measured 70.2 (float32 stepping; the float64-stepping oracle: 31.1)
 
 
 def test_failure_status_and_zero_padding(dev, oracle):
