@@ -33,6 +33,7 @@ EXPORTS = [
     "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs", "hode_rhs_vjp",
     "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd", "hode_generate_4gi",
     "hode_step_record_floats", "hode_step_record_capacity", "hode_launch_count",
+    "hode_rollout_fwd_ex", "hode_rollout_fwd_host_ex",
 ]
 
 
@@ -47,6 +48,21 @@ class HodeCfg(ctypes.Structure):
         ("save_steps", ctypes.c_int32), ("kink_mode", ctypes.c_int32),
         ("max_saved_steps", ctypes.c_int32), ("rhs_part", ctypes.c_int32),
     ]
+
+
+class HodeFwdOpts(ctypes.Structure):
+    """Mirror of `struct hode_fwd_opts` (include/hode.h)."""
+    _fields_ = [("struct_bytes", ctypes.c_int32), ("theta_per_traj", ctypes.c_int32), ("order", ctypes.c_void_p),
+                ("out_state_mask", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+def new_fwd_opts(theta_per_traj: bool = False, order_ptr: Optional[int] = None, out_state_mask: int = 0) -> HodeFwdOpts:
+    o = HodeFwdOpts()
+    o.struct_bytes = ctypes.sizeof(HodeFwdOpts)
+    o.theta_per_traj = 1 if theta_per_traj else 0
+    o.order = order_ptr
+    o.out_state_mask = int(out_state_mask)
+    return o
 
 
 class HodeError(RuntimeError):
@@ -84,6 +100,10 @@ def lib() -> ctypes.CDLL:
         fn.argtypes = [ctypes.POINTER(HodeCfg)]
     L.hode_rollout_fwd.restype = ctypes.c_int
     L.hode_rollout_fwd.argtypes = [ctypes.POINTER(HodeCfg)] + [_P] * 11 + [ctypes.c_size_t, _P]
+    L.hode_rollout_fwd_ex.restype = ctypes.c_int
+    L.hode_rollout_fwd_ex.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeFwdOpts)] + [_P] * 11 + [ctypes.c_size_t, _P]
+    L.hode_rollout_fwd_host_ex.restype = ctypes.c_int
+    L.hode_rollout_fwd_host_ex.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeFwdOpts)] + [_P] * 11
     L.hode_rollout_bwd.restype = ctypes.c_int
     L.hode_rollout_bwd.argtypes = ([ctypes.POINTER(HodeCfg)] + [_P] * 11
                                    + [_P, ctypes.c_size_t, _P, ctypes.c_size_t, _P])

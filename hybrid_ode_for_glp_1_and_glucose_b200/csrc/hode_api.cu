@@ -197,11 +197,33 @@ int hode_workspace_bytes(const hode_cfg* cfg, size_t* fwd_bytes, size_t* bwd_byt
   return 0;
 }
 
+static int check_opts(const hode_cfg* cfg, const hode_fwd_opts* o) {
+  if (!o) return 0;
+  if (o->struct_bytes != (int32_t)sizeof(hode_fwd_opts))
+    return fail(HODE_E_SIZE, "opts.struct_bytes != sizeof(hode_fwd_opts): header/library mismatch");
+  if (o->theta_per_traj && cfg->n_samples != 1)
+    return fail(HODE_E_UNSUPPORTED, "theta_per_traj needs n_samples == 1 (theta is [B,17], W is shared)");
+  if (o->theta_per_traj && cfg->save_steps)
+    return fail(HODE_E_UNSUPPORTED, "theta_per_traj is forward-only (no gradient with respect to a per-trajectory theta)");
+  if (o->out_state_mask >> HODE_N_STATE) return fail(HODE_E_SHAPE, "out_state_mask has bits beyond the 6 states");
+  return 0;
+}
+
 int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
                      const float* u_meal, const float* u_tvns, const float* u_gd,
                      const float* theta, const float* W, float* traj, int32_t* status,
                      int32_t* counters, void* workspace, size_t workspace_bytes, void* stream) {
+  return hode_rollout_fwd_ex(cfg, nullptr, y0, t_obs, u_meal, u_tvns, u_gd, theta, W, traj, status, counters, workspace,
+                             workspace_bytes, stream);
+}
+
+int hode_rollout_fwd_ex(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0, const float* t_obs,
+                        const float* u_meal, const float* u_tvns, const float* u_gd,
+                        const float* theta, const float* W, float* traj, int32_t* status,
+                        int32_t* counters, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate(cfg);
+  if (rc) return rc;
+  rc = check_opts(cfg, opts);
   if (rc) return rc;
   if (!y0 || !t_obs || !theta || !traj) return fail(HODE_E_NULL, "y0/t_obs/theta/traj is NULL");
   rc = check_inputs(cfg, u_meal, u_tvns, u_gd, W);
@@ -209,6 +231,14 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
   if (cfg->n_traj == 0) return 0;
   hode::RolloutArgs A = make_args(cfg, y0, t_obs, u_meal, u_tvns, u_gd, theta, W);
   A.traj = traj; A.status = status; A.counters = counters;
+  if (opts) {
+    A.theta_per_traj = opts->theta_per_traj ? 1 : 0;
+    A.order = opts->order;
+    if (opts->out_state_mask && opts->out_state_mask != 0x3Fu) {
+      A.out_mask = opts->out_state_mask;
+      A.out_nc = __builtin_popcount(opts->out_state_mask);
+    }
+  }
   const Workspace w = fwd_workspace(cfg);
   if (w.total > 0 && (!workspace || workspace_bytes < w.total))
     return fail(HODE_E_WORKSPACE, "workspace missing or smaller than hode_workspace_bytes()");
@@ -485,10 +515,13 @@ void tune_default_pool() {
 constexpr int STREAM_BLOCK = 8192;
 constexpr int STREAM_MAX_BLOCKS = 1024;
 
-int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const float* t_obs_h,
+int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0_h, const float* t_obs_h,
                               const float* const uh[3], const float* theta_h, const float* W_h,
                               float* traj_h, int32_t* status_h, int32_t* counters_h, cudaStream_t st) {
   const size_t B = cfg->n_traj, T = cfg->n_obs;
+  const uint32_t mask = (opts && opts->out_state_mask && opts->out_state_mask != 0x3Fu) ? opts->out_state_mask : 0u;
+  const size_t nc = mask ? (size_t)__builtin_popcount(mask) : 6;   // state columns copied back
+  const size_t n_theta = (opts && opts->theta_per_traj) ? B : 1;
   const size_t P = hode_mlp_param_count(cfg->nn_hidden, cfg->nn_layers);
   const int n_blk = (int)((B + STREAM_BLOCK - 1) / STREAM_BLOCK);
   size_t ub[3];
@@ -500,7 +533,7 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const floa
   const size_t o_y0 = carve(B * 24), o_t = carve((cfg->t_per_traj ? B * T : T) * 4);
   size_t o_u[3];
   for (int ch = 0; ch < 3; ++ch) o_u[ch] = carve(ub[ch]);
-  const size_t o_th = carve(17 * 4), o_W = carve(P * 4), o_traj = carve(B * T * 24), o_st = carve(B * 4),
+  const size_t o_th = carve(n_theta * 17 * 4), o_W = carve(P * 4), o_traj = carve(B * T * nc * 4), o_st = carve(B * 4),
                o_cn = carve(2 * B * 4), o_done = carve((size_t)n_blk * 4), o_ws = carve(wsp.total);
 
   static thread_local int* flags_h = nullptr;     // host-mapped completion flags (allocated once)
@@ -529,7 +562,7 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const floa
   CK(cudaMemcpyAsync(d + o_t, t_obs_h, (cfg->t_per_traj ? B * T : T) * 4, cudaMemcpyHostToDevice, st));
   for (int ch = 0; ch < 3; ++ch)
     if (ub[ch]) CK(cudaMemcpyAsync(d + o_u[ch], uh[ch], ub[ch], cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + o_th, theta_h, 17 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_th, theta_h, n_theta * 17 * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d + o_W, W_h, P * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d + o_done, 0, (size_t)n_blk * 4, st));
   {
@@ -542,6 +575,9 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const floa
     A.done_count = (int*)(d + o_done);
     A.done_flag = flags_d;
     A.done_block = STREAM_BLOCK;
+    A.out_mask = mask;
+    A.out_nc = mask ? (int)nc : 0;
+    A.theta_per_traj = n_theta > 1 ? 1 : 0;
     CK(hode::launch_rollout_tc(A, cfg->mlp, d + o_ws + wsp.off_tc, st));
   }
   // copy every block back as soon as the kernel reports it complete
@@ -553,7 +589,7 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const floa
     while (e == cudaSuccess && copied < n_blk) {
       if (vf[copied]) {
         const size_t lo = (size_t)copied * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
-        e = cudaMemcpyAsync(traj_h + lo * T * 6, d + o_traj + lo * T * 24, (hi - lo) * T * 24, cudaMemcpyDeviceToHost,
+        e = cudaMemcpyAsync(traj_h + lo * T * nc, d + o_traj + lo * T * nc * 4, (hi - lo) * T * nc * 4, cudaMemcpyDeviceToHost,
                             copy_stream);
         ++copied;
       } else if (cudaEventQuery(ev_kernel) != cudaErrorNotReady) {
@@ -568,7 +604,7 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const float* y0_h, const floa
   CK(cudaStreamSynchronize(st));
   for (; copied < n_blk; ++copied) {
     const size_t lo = (size_t)copied * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
-    CK(cudaMemcpyAsync(traj_h + lo * T * 6, d + o_traj + lo * T * 24, (hi - lo) * T * 24, cudaMemcpyDeviceToHost,
+    CK(cudaMemcpyAsync(traj_h + lo * T * nc, d + o_traj + lo * T * nc * 4, (hi - lo) * T * nc * 4, cudaMemcpyDeviceToHost,
                        copy_stream));
   }
   if (status_h) CK(cudaMemcpyAsync(status_h, d + o_st, B * 4, cudaMemcpyDeviceToHost, st));
@@ -593,8 +629,25 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
                           const float* u_meal_h, const float* u_tvns_h, const float* u_gd_h,
                           const float* theta_h, const float* W_h, float* traj_h,
                           int32_t* status_h, int32_t* counters_h, void* stream) {
+  return hode_rollout_fwd_host_ex(cfg, nullptr, y0_h, t_obs_h, u_meal_h, u_tvns_h, u_gd_h, theta_h, W_h, traj_h, status_h,
+                                  counters_h, stream);
+}
+
+int hode_rollout_fwd_host_ex(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0_h, const float* t_obs_h,
+                             const float* u_meal_h, const float* u_tvns_h, const float* u_gd_h,
+                             const float* theta_h, const float* W_h, float* traj_h,
+                             int32_t* status_h, int32_t* counters_h, void* stream) {
   int rc = validate(cfg);
   if (rc) return rc;
+  rc = check_opts(cfg, opts);
+  if (rc) return rc;
+  const uint32_t mask = (opts && opts->out_state_mask && opts->out_state_mask != 0x3Fu) ? opts->out_state_mask : 0u;
+  const size_t nc = mask ? (size_t)__builtin_popcount(mask) : 6;
+  const bool th_per_traj = opts && opts->theta_per_traj;
+  hode_fwd_opts dev_opts{};
+  dev_opts.struct_bytes = (int32_t)sizeof(hode_fwd_opts);
+  dev_opts.theta_per_traj = th_per_traj ? 1 : 0;
+  dev_opts.out_state_mask = mask;
   if (!y0_h || !t_obs_h || !theta_h || !traj_h)
     return fail(HODE_E_NULL, "y0/t_obs/theta/traj host pointer is NULL");
   rc = check_inputs(cfg, u_meal_h, u_tvns_h, u_gd_h, W_h);
@@ -612,7 +665,7 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   if (S == 1 && uses_tensor_cores(cfg) && B >= 2 * (size_t)STREAM_BLOCK &&
       B <= (size_t)STREAM_BLOCK * STREAM_MAX_BLOCKS) {
     tune_default_pool();
-    return rollout_fwd_host_streamed(cfg, y0_h, t_obs_h, uh, theta_h, W_h, traj_h, status_h, counters_h, st);
+    return rollout_fwd_host_streamed(cfg, opts, y0_h, t_obs_h, uh, theta_h, W_h, traj_h, status_h, counters_h, st);
   }
 
   // Trajectory chunks are pipelined over a few streams: while chunk c integrates, chunk c+1 is
@@ -632,14 +685,14 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
   sub.n_traj = (int32_t)rows_max;
   const Workspace wsp = fwd_workspace(&sub);
 
-  const size_t sz_t_shared = cfg->t_per_traj ? 0 : T * 4, sz_th = S * 17 * 4, sz_W = S * P * 4;
+  const size_t sz_t_shared = cfg->t_per_traj ? 0 : T * 4, sz_th = (th_per_traj ? B : S) * 17 * 4, sz_W = S * P * 4;
   size_t off = 0;
   auto carve = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_t = carve(sz_t_shared), o_th = carve(sz_th), o_W = carve(sz_W);
   const size_t o_y0 = carve(B * 6 * 4), o_trow = carve(cfg->t_per_traj ? B * T * 4 : 0);
   size_t o_u[3];
   for (int ch = 0; ch < 3; ++ch) o_u[ch] = carve(B * urow[ch]);
-  const size_t o_traj = carve(S * B * T * 6 * 4), o_st = carve(S * B * 4), o_cn = carve(2 * S * B * 4);
+  const size_t o_traj = carve(S * B * T * nc * 4), o_st = carve(S * B * 4), o_cn = carve(2 * S * B * 4);
   size_t o_ws[MAX_STREAMS];
   for (int i = 0; i < n_streams; ++i) o_ws[i] = carve(wsp.total);
 
@@ -675,18 +728,18 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_h, const float* t
                            cudaMemcpyHostToDevice, cs));
     sub.n_traj = (int32_t)rows;
     // S == 1 when chunked: unit index == trajectory index, so every output is a contiguous slice
-    lib_rc = hode_rollout_fwd(
-        &sub, (float*)(d + o_y0 + lo * 24),
+    lib_rc = hode_rollout_fwd_ex(
+        &sub, &dev_opts, (float*)(d + o_y0 + lo * 24),
         cfg->t_per_traj ? (float*)(d + o_trow + lo * T * 4) : (float*)(d + o_t),
         urow[0] ? (float*)(d + o_u[0] + lo * urow[0]) : nullptr,
         urow[1] ? (float*)(d + o_u[1] + lo * urow[1]) : nullptr,
-        urow[2] ? (float*)(d + o_u[2] + lo * urow[2]) : nullptr, (float*)(d + o_th),
-        sz_W ? (float*)(d + o_W) : nullptr, (float*)(d + o_traj + lo * T * 24), (int32_t*)(d + o_st + lo * 4),
+        urow[2] ? (float*)(d + o_u[2] + lo * urow[2]) : nullptr, (float*)(d + o_th + (th_per_traj ? lo * 17 * 4 : 0)),
+        sz_W ? (float*)(d + o_W) : nullptr, (float*)(d + o_traj + lo * T * nc * 4), (int32_t*)(d + o_st + lo * 4),
         // chunk c keeps its [2, rows] counters at byte offset 2 * lo * 4 of the [2, B] buffer
         (int32_t*)(d + o_cn + lo * 8), wsp.total ? d + o_ws[c % n_streams] : nullptr,
         wsp.total, (void*)cs);
     if (lib_rc) goto done;
-    CK(cudaMemcpyAsync(traj_h + lo * T * 6, d + o_traj + lo * T * 24, rows * T * 24 * (n_chunks == 1 ? S : 1),
+    CK(cudaMemcpyAsync(traj_h + lo * T * nc, d + o_traj + lo * T * nc * 4, rows * T * nc * 4 * (n_chunks == 1 ? S : 1),
                        cudaMemcpyDeviceToHost, cs));
     if (status_h)
       CK(cudaMemcpyAsync(status_h + lo, d + o_st + lo * 4, rows * 4 * (n_chunks == 1 ? S : 1),

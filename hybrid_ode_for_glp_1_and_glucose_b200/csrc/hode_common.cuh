@@ -46,6 +46,16 @@ struct RolloutArgs {
   // deviations over the S parameter sets, [B,T,6] each; traj is nullptr in this mode
   float* vi_mean;
   float* vi_m2;
+  // hode_rollout_fwd_ex options:
+  //   theta_per_traj: theta is [B,17], one mechanistic parameter set PER TRAJECTORY (S == 1; the network stays shared) —
+  //                   parameter sweeps such as the Sobol analysis of the reference's plots/plot_all.py:124-224
+  //   order:          optional [B] launch order of the trajectories (tensor-core rollout: longest first, from the
+  //                   previous pass's attempt counters, removes the tail of small cohorts)
+  int32_t theta_per_traj;
+  const int32_t* order;
+  // host entry with an output-state mask: traj rows hold only the out_nc selected columns (0 = all six)
+  uint32_t out_mask;
+  int32_t out_nc;
   // optional: bit i of kink_masks[b] set <=> grid point i is a kink of some series input of
   // trajectory b (T <= 64), precomputed by kink_mask_kernel so that lane refill loads one word
   const unsigned long long* kink_masks;
@@ -256,7 +266,17 @@ __device__ __forceinline__ void store_row6c(float* p, const float* y) {
 __device__ __forceinline__ void emit_row(const RolloutArgs& A, float* out, long b, int ei, const float* y,
                                          int vi_n) {
   if (vi_n == 0) {
-    if (out) store_row6c(out + (size_t)ei * NS, y);
+    if (out) {
+      if (A.out_nc == 0) {
+        store_row6c(out + (size_t)ei * NS, y);
+      } else {
+        float* o = out + (size_t)ei * A.out_nc;
+        int j = 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+          if ((A.out_mask >> i) & 1u) o[j++] = y[i];
+      }
+    }
     return;
   }
   float* pm = A.vi_mean + ((size_t)b * A.T + ei) * NS;

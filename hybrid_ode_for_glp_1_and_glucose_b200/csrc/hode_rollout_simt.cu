@@ -220,7 +220,7 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
                                                int s, long b, int vi_n) {
   const long unit = (long)s * A.B + b;
   const long n_units = (long)A.S * A.B;
-  const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
+  const Theta th = load_theta(A.theta + (A.theta_per_traj ? (size_t)b : (size_t)s) * HODE_N_THETA);
   TrajInputs in;
   in.T = A.T;
   in.cur = 0;
@@ -231,7 +231,7 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
     in.u[ch] = in.mode[ch] == HODE_IN_SERIES ? A.u[ch] + b * A.T
              : in.mode[ch] == HODE_IN_CONST ? A.u[ch] + b : nullptr;
   }
-  float* out = A.traj ? A.traj + (size_t)unit * A.T * NS : nullptr;
+  float* out = A.traj ? A.traj + (size_t)unit * A.T * (A.out_nc ? A.out_nc : NS) : nullptr;
   const int T = A.T;
 
   float y[NS], cmp[NS];

@@ -212,7 +212,7 @@ __device__ __forceinline__ void lane_bind(Lane& ln, const RolloutArgs& A, const 
     ln.in.u[ch] = A.in_mode[ch] == HODE_IN_SERIES ? A.u[ch] + b * A.T
                 : A.in_mode[ch] == HODE_IN_CONST ? A.u[ch] + b : nullptr;
   }
-  ln.out = A.traj ? A.traj + (size_t)unit * A.T * NS : nullptr;
+  ln.out = A.traj ? A.traj + (size_t)unit * A.T * (A.out_nc ? A.out_nc : NS) : nullptr;
   ln.cached = A.solver == HODE_SOLVER_RK4 || A.kink_mode == HODE_KINK_CLIP || !any_series(ln.in);
   ln.c_t1 = 0.f;
   ln.c_inv_dt = 1.f;
@@ -399,7 +399,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       }
       tc::mbar_wait(&load_bar, load_parity);
       load_parity ^= 1u;
-      const Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);
+      Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);   // (reloaded per trajectory in theta_per_traj mode)
 
       Lane ln;
       ln.has = false;
@@ -457,6 +457,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           {
             if (want) {
               if (b < b_hi) {
+                if (A.order) b = (long)A.order[b];   // launch order hint: queue position -> trajectory
+                if (A.theta_per_traj) th = load_theta(A.theta + (size_t)b * HODE_N_THETA);
                 lane_bind(ln, A, t_shared, s, b);
                 ln.t = (double)ln.in.t_obs[0];
                 t_bound = (double)ln.in.t_obs[T - 1];

@@ -71,7 +71,7 @@ def _require_cuda(device: torch.device) -> None:
 
 def prepare(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, torch.Tensor]],
             theta: torch.Tensor, W: Optional[torch.Tensor], hidden: int, layers: int,
-            device: torch.device):
+            device: torch.device, theta_per_traj: bool = False):
     """Normalise shapes/dtypes, fill a hode_cfg.  Pure host logic (testable without a GPU)."""
     if y0.dim() != 2 or y0.shape[1] != _lib.N_STATE:
         raise ValueError(f"initial_state must be [B,6], got {tuple(y0.shape)}")
@@ -114,6 +114,10 @@ def prepare(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
     if theta2.shape[1] != _lib.N_THETA:
         raise ValueError(f"theta must have 17 entries per set, got {tuple(theta.shape)}")
     S = theta2.shape[0]
+    if theta_per_traj:
+        if S != B:
+            raise ValueError(f"theta_per_traj: theta must be [B,17] = ({B},17), got {tuple(theta.shape)}")
+        S = 1
     cfg.n_samples = S
     bufs["theta"] = _f32c(theta2, device)
     if W is None:
@@ -156,19 +160,22 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
             solver: str = "dopri5", rtol: float = 1e-6, atol: float = 1e-8, n_substeps: int = 4,
             kinks: str = "clip", precision: str = "auto", max_steps: int = 0,
             device: Optional[torch.device] = None, save_steps: bool = False,
-            max_saved_steps: int = 0):
-    """Batched IVP solve on the GPU (hode_rollout_fwd).
+            max_saved_steps: int = 0, theta_per_traj: bool = False, order: Optional[torch.Tensor] = None,
+            out_state_mask: int = 0):
+    """Batched IVP solve on the GPU (hode_rollout_fwd / hode_rollout_fwd_ex).
 
     Returns traj [B,T,6] (or [S,B,T,6] when theta is [S,17]) and a RolloutInfo; with
     save_steps=True also a RolloutTape for rollout_bwd().
-    """
+    theta_per_traj: theta is [B,17], one mechanistic parameter set per trajectory (parameter sweeps; the network is
+    shared).  order: int32 [B] launch order of the trajectories (see launch_order()).  out_state_mask: bit i set =
+    keep state column i (traj is then [..., T, popcount])."""
     device = torch.device(device) if device is not None else y0.device
     _require_cuda(device)
     if solver.lower() not in SOLVERS:
         raise HodeError(f"solver '{solver}' is not implemented on the GPU path; available: "
                         f"{sorted(SOLVERS)}")
-    squeeze_s = theta.dim() == 1
-    cfg, bufs = prepare(y0, t_obs, inputs, theta, W, hidden, layers, device)
+    squeeze_s = theta.dim() == 1 or theta_per_traj
+    cfg, bufs = prepare(y0, t_obs, inputs, theta, W, hidden, layers, device, theta_per_traj)
     cfg.solver = SOLVERS[solver.lower()]
     cfg.rtol, cfg.atol = float(rtol), float(atol)
     cfg.n_substeps = int(n_substeps)
@@ -179,17 +186,24 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
     if cfg.mlp != _lib.MLP_NONE:
         cfg.mlp = _mlp_mode(precision, hidden, layers)
     B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
+    nc = bin(out_state_mask & 0x3F).count("1") if (out_state_mask & 0x3F) not in (0, 0x3F) else 6
+    d_order = None
+    if order is not None:
+        d_order = order.detach().to(device=device, dtype=torch.int32).contiguous()
+        if d_order.numel() != B:
+            raise ValueError(f"order must have B={B} entries, got {d_order.numel()}")
+    opts = _lib.new_fwd_opts(theta_per_traj, None if d_order is None else d_order.data_ptr(), out_state_mask & 0x3F)
     with torch.cuda.device(device):
-        traj = torch.empty((S, B, T, 6), dtype=torch.float32, device=device)
+        traj = torch.empty((S, B, T, nc), dtype=torch.float32, device=device)
         status = torch.empty((S, B), dtype=torch.int32, device=device)
         counters = torch.empty((2, S, B), dtype=torch.int32, device=device)
         ws_bytes = workspace_bytes(cfg)[0]
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
-        rc = 0 if B == 0 else _lib.lib().hode_rollout_fwd(
-            ctypes.byref(cfg), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
+        rc = 0 if B == 0 else _lib.lib().hode_rollout_fwd_ex(
+            ctypes.byref(cfg), ctypes.byref(opts), _ptr(bufs["y0"]), _ptr(bufs["t_obs"]), _ptr(bufs["meal"]),
             _ptr(bufs["tVNS"]), _ptr(bufs["GD"]), _ptr(bufs["theta"]), _ptr(bufs["W"]),
             _ptr(traj), _ptr(status), _ptr(counters), _ptr(ws), ws_bytes, _stream(device))
-    _lib.check(rc, "hode_rollout_fwd")
+    _lib.check(rc, "hode_rollout_fwd_ex")
     if save_steps and B > 0 and cfg.solver == _lib.SOLVER_DOPRI5 and max_saved_steps <= 0:
         # The record capacity was left to the library (max(128, 2 (T - 1)) accepted steps per trajectory).  A
         # trajectory that needs more is reported as ST_REC_OVERFLOW, zero-padded and left without gradient — unlike
@@ -199,7 +213,8 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
         limit = max_steps if max_steps > 0 else 100000
         if bool((status == _lib.ST_REC_OVERFLOW).any()) and cap < limit:
             return rollout(y0, t_obs, inputs, theta, W, hidden, layers, solver, rtol, atol, n_substeps, kinks,
-                           precision, max_steps, device, save_steps, min(4 * cap, limit))
+                           precision, max_steps, device, save_steps, min(4 * cap, limit), theta_per_traj, order,
+                           out_state_mask)
     if squeeze_s:
         out = traj[0], RolloutInfo(status[0], counters[0, 0], counters[1, 0])
     else:
@@ -207,6 +222,16 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
     if save_steps:
         return out + (RolloutTape(cfg, bufs, ws, squeeze_s),)
     return out
+
+
+def launch_order(info: RolloutInfo) -> torch.Tensor:
+    """int32 [B] launch order for the next rollout of the same cohort: trajectories by descending attempt count of
+    the pass `info` came from (stable).  Training re-integrates a cohort every epoch (reference
+    train/train_hybrid.py:225-275); handing the long trajectories out first removes the tail that bounds small
+    cohorts on the tensor-core rollout."""
+    att = (info.n_accept + info.n_reject).reshape(-1, info.n_accept.shape[-1])
+    att = att.sum(dim=0) if att.shape[0] > 1 else att[0]
+    return torch.argsort(att, descending=True, stable=True).to(torch.int32)
 
 
 def rollout_bwd(tape: RolloutTape, grad_traj: torch.Tensor, need_y0: bool = True

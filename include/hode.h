@@ -166,6 +166,35 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
                      int32_t* counters, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Options of the extended rollout entry (all optional; a zeroed struct = hode_rollout_fwd).
+ *   theta_per_traj  1: theta is [B,17], one mechanistic parameter set per TRAJECTORY (n_samples must be 1; the
+ *                   network parameters W [1,P] stay shared).  Replaces the loop of the reference's Sobol sweep, which
+ *                   overwrites the ode_core buffers and calls forward() once per parameter set
+ *                   (plots/plot_all.py:168-187: 16 384 sets x 1 trajectory).  Forward only.
+ *   order           device pointer to [B] trajectory indices (a permutation of 0..B-1), or NULL: the order in which
+ *                   the tensor-core rollout hands trajectories to its lanes.  Longest first (descending attempt
+ *                   counters of the previous pass over the same cohort — training re-integrates a cohort every
+ *                   epoch, train/train_hybrid.py:225-275) removes the tail that bounds small cohorts.  Results do not
+ *                   depend on it.  Ignored by the FP32 kernels and by the fused posterior-predictive sweep.
+ *   out_state_mask  hode_rollout_fwd_host only: bit i set = state column i is copied back to the host; traj_host is
+ *                   then [B,T,popcount(mask)] (0 = all six columns).  The loss of the reference consumes all columns,
+ *                   but its figures and metrics read glucose-centric ones (plots/plot_all.py:183-187).
+ */
+typedef struct hode_fwd_opts {
+  int32_t struct_bytes;    /* = sizeof(hode_fwd_opts); checked */
+  int32_t theta_per_traj;
+  const int32_t* order;
+  uint32_t out_state_mask;
+  uint32_t reserved;
+} hode_fwd_opts;
+
+/* hode_rollout_fwd with options (opts == NULL: identical to hode_rollout_fwd). */
+int hode_rollout_fwd_ex(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0, const float* t_obs,
+                        const float* u_meal, const float* u_tvns, const float* u_gd,
+                        const float* theta, const float* W, float* traj, int32_t* status,
+                        int32_t* counters, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Discrete adjoint of hode_rollout_fwd over the recorded accepted steps (step sizes
  * frozen): the gradient autograd would give through the unrolled RK steps.  The reference
  * has no through-solver gradient (models/hybrid_ode_nn.py:248 returns a graph-free tensor);
@@ -273,6 +302,13 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_host, const float
                           const float* u_gd_host, const float* theta_host, const float* W_host,
                           float* traj_host, int32_t* status_host, int32_t* counters_host,
                           void* stream);
+
+/* hode_rollout_fwd_host with options: opts->out_state_mask selects the state columns copied back (traj_host is
+ * [B,T,popcount(mask)]); theta_per_traj as in hode_rollout_fwd_ex (theta_host is then [B,17]); order is ignored. */
+int hode_rollout_fwd_host_ex(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0_host,
+                             const float* t_obs_host, const float* u_meal_host, const float* u_tvns_host,
+                             const float* u_gd_host, const float* theta_host, const float* W_host,
+                             float* traj_host, int32_t* status_host, int32_t* counters_host, void* stream);
 
 #ifdef __cplusplus
 }
