@@ -313,12 +313,13 @@ def run_ours(args):
     def attempts_of(info):
         return float((info.n_accept.sum() + info.n_reject.sum()).item())
 
-    def fwd_step(c):
-        return lambda: ops.rollout(c.y0, c.t, c.ins, c.theta, c.W, **c.kw)
+    def fwd_step(c, order=None):
+        return lambda: ops.rollout(c.y0, c.t, c.ins, c.theta, c.W, order=order, **c.kw)
 
-    def fwdbwd_step(c, d_g):
+    def fwdbwd_step(c, d_g, order=None):
         def step():
-            traj, info, tape = ops.rollout(c.y0, c.t, c.ins, c.theta, c.W, save_steps=True, max_saved_steps=REC_CAPACITY, **c.kw)
+            traj, info, tape = ops.rollout(c.y0, c.t, c.ins, c.theta, c.W, save_steps=True, max_saved_steps=REC_CAPACITY,
+                                           order=order, **c.kw)
             g_y0, g_theta, g_W = ops.rollout_bwd(tape, d_g)      # grad of mean(traj) w.r.t. y0, theta, W
             if world > 1:
                 # the path's one exchange step: gradients of the shared parameters + a loss slot,
@@ -516,12 +517,17 @@ def run_ours(args):
         ws = make_workload("hybrid_fwdbwd", Bs, seed=2000 + rank, world=world)
         cs = Cohort(ws)
         d_gs = torch.full((Bs, T, 6), 1.0 / (Bs * T * 6), dtype=torch.float32, device=dev)
-        for name, fn, fac in (("fwd", fwd_step(cs), 1.0), ("fwd_bwd", fwdbwd_step(cs, d_gs), 3.0)):
+        # a small cohort is bound by its longest trajectories: hand them out first, in the order of the previous pass's
+        # attempt counters (training re-integrates the same cohort every epoch)
+        order = ops.launch_order(fwd_step(cs)()[1])
+        for name, fn, fac in (("fwd", fwd_step(cs, order), 1.0), ("fwd_bwd", fwdbwd_step(cs, d_gs, order), 3.0),
+                              ("fwd_unordered", fwd_step(cs), 1.0)):
             ms, o3, n_l = timed(fn, 5, 2)
             launches += n_l
             ms, att = reduce_max_sum(ms, attempts_of(o3[-1]))
             legs[f"config3_shard_{name}"] = {
                 "value": att * 5 / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world,
+                "launch_order": "arrival" if name.endswith("unordered") else "longest first (previous pass's attempt counters)",
                 "scaling": "strong (262 144 trajectories in total)" if world > 1 else "n/a (one 32 768-trajectory shard of the 8-GPU job)",
                 "trajectories_per_gpu": Bs, "ms_per_step": ms / 5, "steps": 5,
                 "frac": att / world * FLOP_ATTEMPT_HYBRID * fac / (ms / 5 * 1e-3) / 1e12 / tensor_peak}
@@ -547,6 +553,28 @@ def run_ours(args):
                     "posterior = point parameters with std 0.1 x prior (configs/4gi_vi.yaml priors, network prior std 0.1)",
             "roofline": {k: leg[k] for k in ("achieved", "peak", "frac", "unit")}}
         del cv, thS, WS
+        # (4) the reference's Sobol sweep (plots/plot_all.py:124-224): 16 384 parameter sets x 1 trajectory, per-trajectory theta
+        if rank == 0:
+            from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN, sensitivity
+            mdl = HybridODENN(device=dev)
+            with torch.no_grad():
+                off = 0
+                Wt = torch.from_numpy(w["W"])
+                for _, p_ in mdl.nn_residual.named_parameters():
+                    p_.copy_(Wt[off: off + p_.numel()].reshape(p_.shape)); off += p_.numel()
+            names = ["a_GI", "k_I", "rho", "E_max", "V_max", "K_m", "k_L"]
+            lo = np.array([0.008, 0.02, 0.002, 0.08, 7.0, 5.5, 0.015]); hi = np.array([0.012, 0.03, 0.004, 0.12, 11.0, 8.5, 0.025])
+            smp = torch.from_numpy((lo + np.random.default_rng(5).uniform(0, 1, (16384, 7)) * (hi - lo)).astype(np.float32))
+            sob = lambda: sensitivity.sobol_outputs(mdl, names, smp)
+            sob(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = int(L.hode_launch_count())
+            e0.record(); sob(); e1.record(); torch.cuda.synchronize()
+            launches += int(L.hode_launch_count()) - n0
+            att = attempts_of(mdl.last_info)
+            legs["sobol_16384_sets"] = {"value": att / (e0.elapsed_time(e1) * 1e-3), "unit": "trajectory-steps/s", "n_gpus": 1,
+                                        "ms_per_step": e0.elapsed_time(e1), "parameter_sets": 16384,
+                                        "what": "sensitivity.sobol_outputs: per-trajectory theta on the tensor-core rollout, rank 0 only"}
 
     if rank == 0:
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count

@@ -6,7 +6,7 @@ of OliverDOU776/Hybrid-ODE-for-GLP-1-and-Glucose.
 The compute lives in libhode.so (csrc/, C ABI in include/hode.h); this package is the
 host-side mirror of the reference's Python interface for that path.
 """
-from . import _lib, distributed, ops, sensitivity
+from . import _lib, distributed, ops, sensitivity, training
 from ._lib import HodeError
 from .bayes import VariationalParameters, bayes_loss, compute_posterior_predictive
 from .hybrid_ode_nn import HybridODENN
@@ -15,4 +15,4 @@ from .ode_core import ODECore
 from .vi import VariationalInference
 
 __all__ = ["HybridODENN", "ODECore", "NNResidual", "VariationalParameters", "bayes_loss",
-           "compute_posterior_predictive", "VariationalInference", "HodeError", "ops", "distributed", "sensitivity"]
+           "compute_posterior_predictive", "VariationalInference", "HodeError", "ops", "distributed", "sensitivity", "training"]

@@ -33,7 +33,7 @@ EXPORTS = [
     "hode_rollout_fwd", "hode_rollout_bwd", "hode_vi_predictive", "hode_rhs", "hode_rhs_vjp",
     "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd", "hode_generate_4gi",
     "hode_step_record_floats", "hode_step_record_capacity", "hode_launch_count",
-    "hode_rollout_fwd_ex", "hode_rollout_fwd_host_ex",
+    "hode_rollout_fwd_ex", "hode_rollout_fwd_host_ex", "hode_train_step", "hode_train_step_workspace_bytes",
 ]
 
 
@@ -63,6 +63,14 @@ def new_fwd_opts(theta_per_traj: bool = False, order_ptr: Optional[int] = None, 
     o.order = order_ptr
     o.out_state_mask = int(out_state_mask)
     return o
+
+
+class HodeTrainCfg(ctypes.Structure):
+    """Mirror of `struct hode_train_cfg` (include/hode.h)."""
+    _fields_ = [("struct_bytes", ctypes.c_int32), ("n_physics", ctypes.c_int32), ("data_gradient", ctypes.c_int32),
+                ("adam_step", ctypes.c_int32), ("lambda1", ctypes.c_float), ("lambda2", ctypes.c_float),
+                ("grad_clip", ctypes.c_float), ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
+                ("eps", ctypes.c_float), ("physics_dt", ctypes.c_float)]
 
 
 class HodeError(RuntimeError):
@@ -104,6 +112,10 @@ def lib() -> ctypes.CDLL:
     L.hode_rollout_fwd_ex.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeFwdOpts)] + [_P] * 11 + [ctypes.c_size_t, _P]
     L.hode_rollout_fwd_host_ex.restype = ctypes.c_int
     L.hode_rollout_fwd_host_ex.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeFwdOpts)] + [_P] * 11
+    L.hode_train_step_workspace_bytes.restype = ctypes.c_int
+    L.hode_train_step_workspace_bytes.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeTrainCfg), ctypes.POINTER(ctypes.c_size_t)]
+    L.hode_train_step.restype = ctypes.c_int
+    L.hode_train_step.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeTrainCfg)] + [_P] * 16 + [ctypes.c_size_t, _P]
     L.hode_rollout_bwd.restype = ctypes.c_int
     L.hode_rollout_bwd.argtypes = ([ctypes.POINTER(HodeCfg)] + [_P] * 11
                                    + [_P, ctypes.c_size_t, _P, ctypes.c_size_t, _P])

@@ -237,6 +237,46 @@ int hode_loss_fused_fwd_bwd(const hode_cfg* cfg, const float* y0, const float* t
                             void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
 
 /*
+ * One training step of the reference in a single call: HybridODENN.loss (reference models/hybrid_ode_nn.py:263-351) plus the
+ * batch body of train_epoch (train/train_hybrid.py:244-261: backward, clip_grad_norm_, Adam.step) on the packed network
+ * parameters.  Stream-ordered, allocation-free (one workspace), no host synchronisation: capturable in a CUDA graph.
+ *   loss = MSE(rollout, obs) + lambda1 * physics + lambda2 * (lambda2 * sum ||Linear.weight||^2)       (the reference
+ *   applies lambda2 twice, :336-345), physics = mean over the n_physics drawn grid indices k of
+ *   MSE((Phi_dt(x_k) - x_k) / dt, f(t_k, x_k)) with the inputs frozen at index k (:297-333); the (index, trajectory) pairs
+ *   are stacked into ONE re-solve, ONE RHS and ONE RHS-VJP launch.
+ *   Gradient: as in the reference only the physics residual (through f) and the L2 term carry gradient (the solves are
+ *   graph-free, :248); data_gradient = 1 adds the discrete adjoint of the data term (hode_rollout_bwd).
+ *   Then ||g|| clipping (torch.nn.utils.clip_grad_norm_) and torch.optim.Adam's update (weight_decay 0), in place.
+ */
+typedef struct hode_train_cfg {
+  int32_t struct_bytes;   /* = sizeof(hode_train_cfg); checked                                                    */
+  int32_t n_physics;      /* number of physics grid indices (the reference: min(20, len(time_points))); 0 = no term */
+  int32_t data_gradient;  /* 0: reference semantics (no gradient through the solver); 1: + adjoint of the data term */
+  int32_t adam_step;      /* 1-based count of this update; 0 = loss and gradient only (validate()); < 0 = the count
+                             lives on the device (scalars[6], incremented by the call): CUDA-graph replays          */
+  float lambda1, lambda2;
+  float grad_clip;        /* max gradient norm (config training.gradient_clip); <= 0: no clipping                  */
+  float lr, beta1, beta2, eps;
+  float physics_dt;       /* local-time horizon of the re-solve (0.1 in the reference; <= 0 selects it)             */
+} hode_train_cfg;
+
+int hode_train_step_workspace_bytes(const hode_cfg* cfg, const hode_train_cfg* tc, size_t* bytes);
+
+/*
+ *   W [P] in/out (updated when adam_step > 0); obs [B,T,6]; physics_idx DEVICE int32 [n_physics] (grid indices, drawn by
+ *   the caller the way the reference draws them: torch.randperm(len(time_points))[:n]); adam_m / adam_v [P] in/out;
+ *   grad_W [P] out (the clipped gradient, what p.grad holds after clip_grad_norm_); scalars [9] (device): out [0..5] =
+ *   total loss, data, physics, reg (= lambda2 * sum w^2), gradient norm before clipping, clip coefficient; [6] = update
+ *   count (in/out when adam_step < 0), [7], [8] scratch;
+ *   traj [B,T,6] out (the predictions); status [B] out (may be NULL).  cfg.n_samples must be 1, cfg.mlp != NONE.
+ */
+int hode_train_step(const hode_cfg* cfg, const hode_train_cfg* tc, const float* y0, const float* t_obs,
+                    const float* u_meal, const float* u_tvns, const float* u_gd, const float* theta, float* W,
+                    const float* obs, const int32_t* physics_idx, float* adam_m, float* adam_v, float* grad_W,
+                    float* scalars, float* traj, int32_t* status, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/*
  * Vector-Jacobian product of hode_rhs: the backward of HybridODENN.ode_residual, the only
  * differentiable model call of the reference's loss (models/hybrid_ode_nn.py:327 -> :330,
  * loss.backward() at train/train_hybrid.py:252).

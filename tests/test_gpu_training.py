@@ -1,0 +1,147 @@
+"""GPU tests of the one-call training step (hode_train_step, training.py): loss and gradient against the reference's own
+loss().backward() (fixtures tests/golden/loss_*.npz), clipping and Adam against torch's, the train_epoch / validate
+mirrors against the unfused loop, and CUDA-graph replays against eager calls."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cohort, golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def relmax(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(a - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+def _load_W(m, W):
+    with torch.no_grad():
+        off = 0
+        for _, p in m.nn_residual.named_parameters():
+            p.copy_(torch.from_numpy(W[off: off + p.numel()]).reshape(p.shape))
+            off += p.numel()
+
+
+def _batch(d, dev):
+    to = lambda a: torch.from_numpy(a).to(dev)
+    return {"initial_state": to(d["y0"]), "observations": to(d["obs"]), "time_points": to(d["t"]),
+            "external_inputs": {"meal": to(d["meal"]), "tVNS": to(d["tvns"])}}
+
+
+@pytest.mark.parametrize("tag", ["nn64x4", "nn16x2"])
+def test_fused_step_matches_reference_loss_backward(dev, tag):
+    """Loss value and every network-parameter gradient of the reference's model.loss(batch).backward() (same torch
+    seed -> same physics indices), through ONE hode_train_step call (no update)."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    from hybrid_ode_for_glp_1_and_glucose_b200.training import FusedTrainer
+    d = golden(f"loss_{tag}")
+    m = HybridODENN(nn_hidden=int(d["hidden"]), nn_layers=int(d["layers"]), device=dev)
+    _load_W(m, d["W"])
+    m.kinks = "scipy"
+    tr = FusedTrainer(m)
+    torch.manual_seed(int(d["seed"]))
+    out = tr.step(_batch(d, dev), lambda1=float(d["lambda1"]), lambda2=float(d["lambda2"]), update=False)
+    assert abs(float(out["loss"]) - float(d["loss"])) <= TOL * abs(float(d["loss"]))
+    assert relmax(tr.grad.cpu().numpy(), d["grad_W"]) < TOL
+    # per tensor, as the reference's parameters see it (p.grad aliases the packed gradient).  Both sides are float32
+    # sums over the same few hundred rows; tensors whose gradient is 1000x smaller than the largest one (hidden biases)
+    # agree to 5e-4 of their own scale
+    off = 0
+    for _, p in m.nn_residual.named_parameters():
+        ref = d["grad_W"][off: off + p.numel()]
+        if np.abs(ref).max() > 0:
+            assert relmax(p.grad.detach().cpu().numpy().reshape(-1), ref) < 5e-4
+        off += p.numel()
+    assert float(out["clip_coef"]) == 1.0
+    assert np.array_equal(tr.flat.cpu().numpy(), d["W"]), "update=False must not touch the parameters"
+
+
+def test_fused_clip_and_adam_match_torch(dev):
+    """Three updates with a tight gradient clip: the fused step == model.loss().backward(), clip_grad_norm_, Adam.step()
+    of the unfused drop-in (reference train/train_hybrid.py:244-261), on the same physics indices."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    from hybrid_ode_for_glp_1_and_glucose_b200.training import FusedTrainer
+    d = golden("loss_nn64x4")
+    batch = _batch(d, dev)
+    ma, mb = HybridODENN(device=dev), HybridODENN(device=dev)
+    _load_W(ma, d["W"]); _load_W(mb, d["W"])
+    opt_a = torch.optim.Adam(ma.parameters(), lr=3e-3)
+    opt_b = torch.optim.Adam(mb.parameters(), lr=3e-3)
+    tr = FusedTrainer(ma, opt_a)
+    clip = None
+    for it in range(3):
+        torch.manual_seed(100 + it)
+        lb = mb.loss(batch, lambda1=1.0, lambda2=0.5)
+        opt_b.zero_grad()
+        lb.backward()
+        if clip is None:   # half the first gradient norm: clipping is active
+            clip = 0.5 * float(torch.sqrt(sum((p.grad ** 2).sum() for p in mb.parameters())))
+        torch.nn.utils.clip_grad_norm_(mb.parameters(), clip)
+        opt_b.step()
+        torch.manual_seed(100 + it)
+        out = tr.step(batch, lambda1=1.0, lambda2=0.5, grad_clip=clip, update=True)
+        assert abs(float(out["loss"]) - float(lb)) <= 2e-5 * abs(float(lb))
+        if it == 0:
+            assert abs(float(out["clip_coef"]) - 0.5) < 1e-3
+        Wb = torch.cat([p.detach().reshape(-1) for _, p in mb.nn_residual.named_parameters()])
+        assert relmax(tr.flat.cpu().numpy(), Wb.cpu().numpy()) < 2e-5, it
+    st = opt_a.state[next(iter(ma.nn_residual.parameters()))]
+    assert float(st["step"]) == 3.0 and st["exp_avg"].data_ptr() == tr.m.data_ptr()
+
+
+def test_train_epoch_and_validate_mirrors(dev):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN, training
+    y0, t, ins = cohort(48, 13, seed=61, horizon=1.0)
+    rng = np.random.default_rng(62)
+    obs = (y0[:, None, :] * (1 + 0.05 * rng.normal(0, 1, (48, 13, 6)))).astype(np.float32)
+    tt = lambda a: torch.from_numpy(a)
+    loader = [{"initial_state": tt(y0[i: i + 16]), "observations": tt(obs[i: i + 16]), "time_points": tt(np.tile(t, (16, 1))),
+               "external_inputs": {k: tt(v[i: i + 16]) for k, v in ins.items()}} for i in range(0, 48, 16)]
+    config = {"training": {"lambda1": 1.0, "lambda2": 0.1, "gradient_clip": 1.0}, "ablation": {"no_physics": False}}
+    m = HybridODENN(device=dev)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for p in m.nn_residual.parameters():
+            p.copy_(0.05 * torch.randn_like(p))
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 1, gamma=0.5)
+    torch.manual_seed(5)
+    v0 = training.validate(m, [dict(b) for b in loader], config, dev)
+    W0 = m._fused_trainer.flat.clone() if getattr(m, "_fused_trainer", None) is not None else None
+    torch.manual_seed(5)
+    l1 = training.train_epoch(m, [dict(b) for b in loader], opt, sched, config, None, 0, dev)
+    assert np.isfinite(v0) and np.isfinite(l1) and abs(l1 - v0) < 0.05 * abs(v0)   # first epoch: nearly the untrained loss
+    assert abs(opt.param_groups[0]["lr"] - 5e-4) < 1e-12                           # the scheduler was stepped
+    assert not torch.equal(m._fused_trainer.flat, W0) if W0 is not None else True
+    assert m._fused_trainer.t == 3
+    torch.manual_seed(5)
+    v1 = training.validate(m, [dict(b) for b in loader], config, dev)
+    assert v1 < v0, "three Adam updates on the physics + L2 terms lower the loss"
+
+
+def test_cuda_graph_replay_equals_eager_steps(dev):
+    """The whole update captured once and replayed: parameters after 3 replays == after 3 eager calls."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN
+    from hybrid_ode_for_glp_1_and_glucose_b200.training import FusedTrainer
+    d = golden("loss_nn64x4")
+    batch = _batch(d, dev)
+    ma, mb = HybridODENN(device=dev), HybridODENN(device=dev)
+    _load_W(ma, d["W"]); _load_W(mb, d["W"])
+    ta, tb = FusedTrainer(ma, lr=2e-3, data_gradient=True), FusedTrainer(mb, lr=2e-3, data_gradient=True)
+    replay = ta.capture(batch, lambda1=1.0, lambda2=0.5, grad_clip=0.0)
+    for it in range(3):
+        torch.manual_seed(300 + it)
+        oa = replay(batch)
+        torch.manual_seed(300 + it)
+        ob = tb.step(batch, lambda1=1.0, lambda2=0.5, update=True)
+        assert torch.equal(oa["loss"], ob["loss"]), it
+    assert torch.equal(ta.flat, tb.flat)
+    assert not np.array_equal(ta.flat.cpu().numpy(), d["W"])
