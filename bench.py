@@ -553,6 +553,7 @@ def run_ours(args):
                     "posterior = point parameters with std 0.1 x prior (configs/4gi_vi.yaml priors, network prior std 0.1)",
             "roofline": {k: leg[k] for k in ("achieved", "peak", "frac", "unit")}}
         del cv, thS, WS
+        # (5 below) ...
         # (4) the reference's Sobol sweep (plots/plot_all.py:124-224): 16 384 parameter sets x 1 trajectory, per-trajectory theta
         if rank == 0:
             from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN, sensitivity
@@ -572,6 +573,31 @@ def run_ours(args):
             e0.record(); sob(); e1.record(); torch.cuda.synchronize()
             launches += int(L.hode_launch_count()) - n0
             att = attempts_of(mdl.last_info)
+            # (5) one whole training step (reference train_epoch batch body) as ONE call: data + physics (20 stacked
+            #     re-solves) + L2 loss, adjoint of the data term, clip, Adam — eager and as a CUDA-graph replay
+            from hybrid_ode_for_glp_1_and_glucose_b200.training import FusedTrainer
+            Bt = 32768
+            wt_ = make_workload("hybrid_fwdbwd", Bt, seed=4000, world=1)
+            tb = lambda a: torch.from_numpy(a).to(dev)
+            batch = {"initial_state": tb(wt_["y0"]), "observations": tb(np.repeat(wt_["y0"][:, None, :], T, 1).copy()),
+                     "time_points": tb(wt_["t"]), "external_inputs": {k: tb(v) for k, v in wt_["ins"].items()}}
+            trn = FusedTrainer(mdl, lr=1e-4, data_gradient=True)
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for mode in ("eager", "cuda_graph"):
+                fn = (lambda: trn.step(batch, 1.0, 1.0, True, 1.0, True)) if mode == "eager" else (lambda r=trn.capture(batch, 1.0, 1.0, True, 1.0): r(batch))
+                fn(); torch.cuda.synchronize()
+                n0 = int(L.hode_launch_count())
+                t0_ = time.perf_counter()
+                e2.record()
+                for _ in range(3):
+                    fn()
+                e3.record(); torch.cuda.synchronize()
+                wall = (time.perf_counter() - t0_) / 3
+                launches += int(L.hode_launch_count()) - n0
+                legs[f"train_step_{mode}"] = {"value": None, "unit": "ms", "ms_per_step": e2.elapsed_time(e3) / 3, "host_ms_per_step": 1e3 * wall,
+                                              "trajectories": Bt, "physics_rows": 20 * Bt, "n_gpus": 1,
+                                              "what": "hode_train_step: rollout + adjoint of the data term + 20 stacked physics re-solves + RHS + "
+                                                      "RHS-VJP + L2 + clip + Adam on 32 768 trajectories, rank 0 only"}
             legs["sobol_16384_sets"] = {"value": att / (e0.elapsed_time(e1) * 1e-3), "unit": "trajectory-steps/s", "n_gpus": 1,
                                         "ms_per_step": e0.elapsed_time(e1), "parameter_sets": 16384,
                                         "what": "sensitivity.sobol_outputs: per-trajectory theta on the tensor-core rollout, rank 0 only"}

@@ -34,6 +34,7 @@ EXPORTS = [
     "hode_rollout_fwd_host", "hode_loss_fused_fwd_bwd", "hode_generate_4gi",
     "hode_step_record_floats", "hode_step_record_capacity", "hode_launch_count",
     "hode_rollout_fwd_ex", "hode_rollout_fwd_host_ex", "hode_train_step", "hode_train_step_workspace_bytes",
+    "hode_window_count", "hode_window_dataset", "hode_eval_metrics",
 ]
 
 
@@ -112,6 +113,12 @@ def lib() -> ctypes.CDLL:
     L.hode_rollout_fwd_ex.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeFwdOpts)] + [_P] * 11 + [ctypes.c_size_t, _P]
     L.hode_rollout_fwd_host_ex.restype = ctypes.c_int
     L.hode_rollout_fwd_host_ex.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeFwdOpts)] + [_P] * 11
+    L.hode_window_count.restype = ctypes.c_int
+    L.hode_window_count.argtypes = [ctypes.c_int32] * 3
+    L.hode_window_dataset.restype = ctypes.c_int
+    L.hode_window_dataset.argtypes = [ctypes.c_int32] * 7 + [_P] * 9 + [ctypes.c_size_t, _P]
+    L.hode_eval_metrics.restype = ctypes.c_int
+    L.hode_eval_metrics.argtypes = [ctypes.c_int64, _P, _P, _P, ctypes.c_float, _P, ctypes.c_int32, _P, _P, ctypes.c_size_t, _P]
     L.hode_train_step_workspace_bytes.restype = ctypes.c_int
     L.hode_train_step_workspace_bytes.argtypes = [ctypes.POINTER(HodeCfg), ctypes.POINTER(HodeTrainCfg), ctypes.POINTER(ctypes.c_size_t)]
     L.hode_train_step.restype = ctypes.c_int

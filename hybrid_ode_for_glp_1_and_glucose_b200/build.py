@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhode.so")
 SOURCES = ["hode_api.cu", "hode_rollout_simt.cu", "hode_rollout_tc.cu", "hode_adjoint_simt.cu", "hode_adjoint_tc.cu",
-           "hode_gen4gi.cu", "hode_train.cu"]
+           "hode_gen4gi.cu", "hode_train.cu", "hode_data.cu"]
 HEADERS = ["hode_common.cuh", "hode_kernels.h", "hode_tcgen05.cuh", "hode_tc_mlp.cuh", os.path.join("..", "..", "include", "hode.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

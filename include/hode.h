@@ -332,6 +332,38 @@ int hode_generate_4gi(int32_t n_subjects, int32_t n_obs, double interval_hours, 
                       float* out, int32_t* status, void* stream);
 
 /*
+ * The step before the path on the device: GlucoseDataset's sliding windows and z-scoring (reference
+ * train/train_hybrid.py:43-155) for a cohort of n_subjects equally long records (what hode_generate_4gi produces).
+ * Windows start at 0, stride, 2 stride, ... <= n_t - sequence_length per subject (:104-115); the normalisation statistics
+ * are the mean and population std (+ 1e-6) over ALL rows of ALL windows, overlapping rows counted once per window, in
+ * float64 (:117-120); initial_state is the first row of each normalised window (:141).
+ *   states [n_subjects, n_t, 6], inputs [n_subjects, n_t, n_inputs] (may be NULL when n_inputs == 0), time [n_t] shared
+ *   or [n_subjects, n_t] (time_per_subject);  with W = n_subjects * hode_window_count(...):
+ *   obs [W, L, 6], initial_state [W, 6], win_inputs [W, L, n_inputs], win_time [W, L] out; mean_std [12] DOUBLE out
+ *   (device: 6 means then 6 stds; mean 0 / std 1 when normalize == 0); workspace >= 32 KiB.
+ */
+int hode_window_count(int32_t n_t, int32_t sequence_length, int32_t stride);
+int hode_window_dataset(int32_t n_subjects, int32_t n_t, int32_t n_inputs, int32_t sequence_length, int32_t stride,
+                        int32_t normalize, int32_t time_per_subject, const float* states, const float* inputs,
+                        const float* time, float* obs, float* initial_state, float* win_inputs, float* win_time,
+                        double* mean_std, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The reductions of the batch consumers after the path: compute_rmse / compute_mae per state and
+ * overall, the calibration sums of compute_calibration_error and the target moments behind evaluate_model's normalised
+ * RMSE (reference eval/evaluate.py:26-181, :262-286), in one pass over pred / target / unc [n_rows, 6].
+ *   unc NULL: unc_const is used for every element (the reference's fixed 0.1 for non-Bayesian models, :239); unc NULL
+ *   and unc_const <= 0: no calibration sums.  thresholds [n_bins] (n_bins <= 32): the normalised-error thresholds of the
+ *   calibration curve (host-computed the reference's way, :139-143).
+ *   out [60] DOUBLE (device): [0,6) sum (p-t)^2 per state, [6,12) sum |p-t|, [12,18) sum t, [18,24) sum t^2, [24] sum of
+ *   interval width + penalty (MSIS numerator), [25] sum unc, [26] count inside the 95 % interval, [27] sum of normalised
+ *   errors, [28 + i] count(normalised error <= thresholds[i]).  workspace >= 160 KiB.
+ */
+int hode_eval_metrics(int64_t n_rows, const float* pred, const float* target, const float* unc, float unc_const,
+                      const float* thresholds, int32_t n_bins, double* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/*
  * Host-buffer convenience entry (the e2e path timed by bench.py): same contract as
  * hode_rollout_fwd but every pointer is HOST memory (pinned or pageable); the call
  * stages H2D copies, runs the rollout and copies traj/status/counters back, all on

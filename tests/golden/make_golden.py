@@ -306,8 +306,59 @@ def vi_cases():
          elbo_ll=np.float64(float(comp["log_likelihood"])), pp_seed=9, pp_mean=mean.numpy(), pp_std=std.numpy())
 
 
+def data_eval_cases():
+    """GlucoseDataset (train/train_hybrid.py:43-155) on a small synthetic CSV, and the metric functions of
+    eval/evaluate.py:26-181 on random predictions: the reference's own outputs for the device mirrors
+    (hode_window_dataset / hode_eval_metrics)."""
+    import tempfile
+    import pandas as pd
+    from eval.evaluate import compute_calibration_error, compute_mae, compute_rmse
+    rng = np.random.default_rng(41)
+    N, n_t = 3, 100
+    rows = []
+    st = np.empty((N, n_t, 4), dtype=np.float32)
+    meal = np.zeros((N, n_t), dtype=np.float32)
+    tv = np.zeros((N, n_t), dtype=np.float32)
+    for sidx in range(N):
+        base = np.array([7.0, 50.0, 25.0, 10.0]) * (1 + 0.1 * rng.normal(0, 1, 4))
+        st[sidx] = (base[None, :] * (1 + 0.2 * rng.normal(0, 1, (n_t, 4)))).astype(np.float32)
+        meal[sidx, rng.integers(1, n_t - 1, 4)] = 1.0
+        tv[sidx, 40:70] = float(sidx % 2)
+        for j in range(n_t):
+            rows.append({"subject_id": sidx, "time_minutes": 5.0 * j, "glucose_mmol_L": float(st[sidx, j, 0]),
+                         "insulin_pmol_L": float(st[sidx, j, 1]), "glucagon_pmol_L": float(st[sidx, j, 2]),
+                         "glp1_pmol_L": float(st[sidx, j, 3]), "meal_indicator": float(meal[sidx, j]), "tvns": float(tv[sidx, j])})
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "cohort.csv")
+        pd.DataFrame(rows).to_csv(path, index=False)
+        out = {}
+        for tag, L_, stride, norm in (("a", 61, 30, True), ("b", 25, 7, True), ("c", 61, 30, False)):
+            ds = GlucoseDataset(path, L_, stride, norm)
+            items = [ds[i] for i in range(len(ds))]
+            out[f"obs_{tag}"] = np.stack([it["observations"].numpy() for it in items])
+            out[f"init_{tag}"] = np.stack([it["initial_state"].numpy() for it in items])
+            out[f"time_{tag}"] = np.stack([it["time_points"].numpy() for it in items])
+            out[f"meal_{tag}"] = np.stack([it["external_inputs"]["meal"].numpy() for it in items])
+            out[f"tvns_{tag}"] = np.stack([it["external_inputs"]["tVNS"].numpy() for it in items])
+            out[f"mean_{tag}"], out[f"std_{tag}"] = np.asarray(ds.state_mean, np.float64), np.asarray(ds.state_std, np.float64)
+            out[f"cfg_{tag}"] = np.array([L_, stride, int(norm)])
+    states6 = np.concatenate([st, np.zeros((N, n_t, 1), np.float32), np.ones((N, n_t, 1), np.float32)], axis=2)
+    # metrics
+    pred = (rng.normal(0, 1, (40, 61, 6)) * np.array([2, 50, 20, 10, 0.1, 0.3]) + np.array([7, 50, 25, 10, 0, 1])).astype(np.float32)
+    targ = (pred + rng.normal(0, 1, pred.shape) * np.array([0.5, 10, 5, 2, 0.05, 0.1])).astype(np.float32)
+    unc = (np.abs(rng.normal(1, 0.3, pred.shape)) * np.array([0.5, 10, 5, 2, 0.05, 0.1])).astype(np.float32)
+    tp, tt_, tu = torch.tensor(pred), torch.tensor(targ), torch.tensor(unc)
+    np.random.seed(77)
+    cal = compute_calibration_error(tp, tu, tt_)
+    save("data_eval", states=states6, meal=meal, tvns=tv, time_hours=(np.arange(n_t) * 5.0 / 60.0).astype(np.float32),
+         pred=pred, target=targ, unc=unc, rmse=np.float64(compute_rmse(tp, tt_)), mae=np.float64(compute_mae(tp, tt_)),
+         rmse_state=compute_rmse(tp, tt_, per_state=True), mae_state=compute_mae(tp, tt_, per_state=True),
+         cal_seed=77, cal_keys=np.array(sorted(cal)), cal_vals=np.array([cal[k] for k in sorted(cal)], dtype=np.float64),
+         target_std=tt_.std(dim=(0, 1)).numpy(), **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (rhs_cases, rollout_fig2, rollout_4gi, rollout_physio, rhs_vjp_cases, loss_cases, vi_cases):
+    for fn in (rhs_cases, rollout_fig2, rollout_4gi, rollout_physio, rhs_vjp_cases, loss_cases, vi_cases, data_eval_cases):
         if not only or fn.__name__ in only:
             fn()
