@@ -97,6 +97,11 @@ int validate(const hode_cfg* c) {
     if (c->nn_hidden < 1 || c->nn_hidden > HODE_MAX_HIDDEN || c->nn_layers < 1 ||
         c->nn_layers > HODE_MAX_LAYERS)
       return fail(HODE_E_UNSUPPORTED, "nn_hidden must be in [1,128] and nn_layers in [1,8]");
+    // the FP32 kernels (rollout, RHS, RHS-VJP: reachable from every mode) keep the weight image and one activation
+    // column per thread in shared memory
+    if (hode::simt_min_smem_bytes(c->nn_hidden, c->nn_layers) > 227 * 1024)
+      return fail(HODE_E_UNSUPPORTED, "network too large: its weight image and activation columns exceed the 227 KB of "
+                                      "shared memory per CTA (e.g. 128 x 4 needs 239 KB)");
     if (uses_tensor_cores(c) && (c->nn_hidden != 64 || c->nn_layers > 6))
       return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 6 (the weight image of "
                                       "deeper networks does not fit the 227 KB of shared memory)");

@@ -13,6 +13,7 @@ void count_launch();
 
 // one trajectory per thread, FP32 CUDA cores (hode_rollout_simt.cu)
 cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t stream);
+size_t simt_min_smem_bytes(int H, int L);
 
 // batched single RHS evaluation (hode_rollout_simt.cu)
 cudaError_t launch_rhs(const RolloutArgs& A, int mlp_mode, const float* t, const float* state,

@@ -573,6 +573,15 @@ size_t simt_smem_bytes(const RolloutArgs& A, int mlp_kind, int block) {
   return floats * sizeof(float);
 }
 
+// smallest dynamic shared memory any FP32 kernel launch of this network shape needs (32-thread CTAs, per-row time
+// grid): the API rejects shapes whose weight image + activation columns cannot fit (HODE_E_UNSUPPORTED)
+size_t simt_min_smem_bytes(int H, int L) {
+  RolloutArgs A{};
+  A.H = H; A.L = L; A.t_per_traj = 1;
+  const int kind = (H == 64 && L >= 1) ? 2 : 1;
+  return simt_smem_bytes(A, kind, 32);
+}
+
 cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t stream) {
   int kind = 0;
   if (mlp_mode != HODE_MLP_NONE) kind = (A.H == 64 && A.L >= 1) ? 2 : 1;
@@ -613,6 +622,7 @@ cudaError_t launch_rhs(const RolloutArgs& A, int mlp_mode, const float* t, const
   int block = 128;
   while (block > 32 && simt_smem_bytes(R, kind, block) > 220 * 1024) block >>= 1;
   const size_t smem = simt_smem_bytes(R, kind, block);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   dim3 grid((unsigned)((A.B + block - 1) / block), (unsigned)A.S);
   cudaError_t e;
   switch (kind) {

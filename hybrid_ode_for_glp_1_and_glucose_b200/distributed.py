@@ -71,19 +71,21 @@ class PackedGradients:
                                                  else torch.device("cpu"))
         self.buffer = torch.zeros(sum(self.sizes) + n_scalars, dtype=torch.float32, device=dev)
 
-    def pack(self, scalars: Sequence[float | torch.Tensor] = ()) -> torch.Tensor:
-        off = 0
-        for p, n in zip(self.params, self.sizes):
-            seg = self.buffer[off: off + n]
-            if p.grad is None:
-                seg.zero_()
-            else:
-                seg.copy_(p.grad.reshape(-1))
-            off += n
+    def pack(self, scalars: Sequence[float | torch.Tensor] = (), weight: float = 1.0) -> torch.Tensor:
+        """Gradients (times `weight`) and scalars into the persistent buffer: one torch.cat, one copy."""
         if len(scalars) != self.n_scalars:
             raise ValueError(f"expected {self.n_scalars} scalars, got {len(scalars)}")
-        for i, v in enumerate(scalars):
-            self.buffer[off + i] = v if torch.is_tensor(v) else float(v)
+        dev = self.buffer.device
+        parts = [(torch.zeros(n, dtype=torch.float32, device=dev) if p.grad is None
+                  else p.grad.detach().reshape(-1).to(device=dev, dtype=torch.float32))
+                 for p, n in zip(self.params, self.sizes)]
+        if self.n_scalars:
+            parts.append(torch.stack([(v.detach().to(device=dev, dtype=torch.float32).reshape(()) if torch.is_tensor(v)
+                                       else torch.tensor(float(v), dtype=torch.float32, device=dev)) for v in scalars]))
+        if parts:
+            torch.cat(parts, out=self.buffer)
+            if weight != 1.0:
+                self.buffer[: sum(self.sizes)].mul_(weight)
         return self.buffer
 
     def unpack(self, scale: float = 1.0) -> torch.Tensor:
@@ -114,15 +116,33 @@ def allreduce_gradients(params: Iterable[torch.Tensor], scalars: Sequence = (), 
 
 def sharded_loss_step(model, batch: Dict, optimizer, lambda1: float = 1.0, lambda2: float = 1.0,
                       gradient_clip: Optional[float] = None, use_physics_loss: bool = True) -> float:
-    """One data-parallel optimiser step of train/train_hybrid.py:244-261: every rank evaluates
-    model.loss on its shard of the batch, gradients and the loss are averaged with one packed
-    all-reduce, then every rank applies the identical update."""
+    """One data-parallel optimiser step of train/train_hybrid.py:244-261: every rank evaluates model.loss on its shard
+    of the batch; loss and gradients are combined with ONE packed all-reduce, each rank weighted by its shard size —
+    the result is the loss / gradient of the global-batch means the reference computes (shards differ in size when B
+    is not a multiple of the world size, and a rank whose shard is empty contributes nothing).  The physics indices
+    are drawn from ONE generator state on every rank (rank 0's seed is broadcast), as a single process would draw
+    them.  Then every rank applies the identical update."""
+    rank, w = world()
     local = shard_batch(batch)
+    n_local = int(local["initial_state"].shape[0])
+    n_total = int(batch["initial_state"].shape[0])
+    if w > 1:   # the same torch.randperm draw on every rank
+        seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64)
+        dist.broadcast(seed, src=0)
+        torch.manual_seed(int(seed.item()))
     optimizer.zero_grad()
-    loss = model.loss(local, lambda1=lambda1, lambda2=lambda2, use_physics_loss=use_physics_loss)
-    loss.backward()
     params = [p for p in model.parameters() if p.requires_grad]
-    red = allreduce_gradients(params, [loss.detach()], average=True)
+    if n_local > 0:
+        loss = model.loss(local, lambda1=lambda1, lambda2=lambda2, use_physics_loss=use_physics_loss)
+        loss.backward()
+        loss_v = loss.detach()
+    else:
+        loss_v = torch.zeros(())
+    packed = PackedGradients(params, 2)
+    buf = packed.pack([loss_v * n_local, float(n_local)], weight=float(n_local))
+    if w > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    red = packed.unpack(1.0 / max(n_total, 1))
     if gradient_clip is not None and gradient_clip > 0:
         torch.nn.utils.clip_grad_norm_(params, gradient_clip)
     optimizer.step()

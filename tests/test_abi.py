@@ -75,3 +75,21 @@ def test_oracle_and_product_agree_on_the_struct(oracle):
     assert ctypes.sizeof(oracle.HodeCfg) == ctypes.sizeof(_lib.HodeCfg)
     for (n1, _), (n2, _) in zip(oracle.HodeCfg._fields_, _lib.HodeCfg._fields_):
         assert n1 == n2
+
+
+def test_network_shapes_that_cannot_fit_shared_memory_are_rejected(built_lib):
+    """128 x 4 needs 239 KB for the FP32 kernels' weight image + activation columns (> 227 KB per CTA): the library says
+    so (HODE_E_UNSUPPORTED) instead of failing at launch with 'invalid configuration argument'."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import _lib
+    L = _lib.lib()
+    for H, layers, ok in ((64, 4, True), (128, 3, True), (128, 4, False), (128, 8, False), (96, 6, True)):
+        cfg = _lib.new_cfg()
+        cfg.n_traj, cfg.n_obs, cfg.mlp, cfg.nn_hidden, cfg.nn_layers = 4, 3, _lib.MLP_FP32, H, layers
+        f, b = ctypes.c_size_t(), ctypes.c_size_t()
+        rc = L.hode_workspace_bytes(ctypes.byref(cfg), ctypes.byref(f), ctypes.byref(b))
+        assert (rc == 0) == ok, (H, layers, rc)
+        if not ok:
+            assert rc == -4 and b"shared memory" in L.hode_last_error_string()
+    cfg = _lib.new_cfg()
+    cfg.n_traj, cfg.n_obs, cfg.mlp, cfg.nn_hidden, cfg.nn_layers = 4, 3, _lib.MLP_TF32X3, 64, 7
+    assert L.hode_workspace_bytes(ctypes.byref(cfg), None, None) == -4     # the tensor-core image of 7 layers does not fit

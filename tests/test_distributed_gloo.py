@@ -51,6 +51,15 @@ def _worker(rank, world_size, port, results):
         ok = ok and torch.equal(loc["external_inputs"]["meal"], batch["external_inputs"]["meal"][lo:hi])
         ok = ok and torch.equal(loc["external_inputs"]["dose"], batch["external_inputs"]["dose"][lo:hi])
         ok = ok and loc["time_points"].shape == (T,)
+        # pack(weight): gradients scaled by the shard size, scalars untouched (sharded_loss_step's global-batch mean)
+        for p in params:
+            p.grad = torch.full_like(p, 2.0)
+        pg = D.PackedGradients(params, 2)
+        buf = pg.pack([5.0 * (rank + 1), float(rank + 1)], weight=float(rank + 1))
+        dist.all_reduce(buf)
+        sc = pg.unpack(1.0 / 3.0)
+        ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 2.0)) for p in params)   # (1*2 + 2*2) / 3
+        ok = ok and abs(float(sc[0]) - 5.0) < 1e-6 and abs(float(sc[1]) - 1.0) < 1e-6
         sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world_size)]
         dist.all_gather(sizes, torch.tensor([hi - lo]))
         ok = ok and int(sum(s.item() for s in sizes)) == B
