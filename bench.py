@@ -426,6 +426,32 @@ def run_ours(args):
                "api": "hode_rollout_fwd_host (pinned host buffers in, host trajectories out)",
                "host_numa_node_rank0": numa_node}
         del h_traj
+        # the same call with an output-state mask: only the glucose column travels back (what the reference's figures
+        # and glucose metrics read, plots/plot_all.py:183; 1/6 of the D2H bytes)
+        if w["nn"] and args.precision != "fp32":
+            h_g = torch.empty((B, T, 1), dtype=torch.float32).pin_memory()
+            opts = _lib.new_fwd_opts(out_state_mask=0b000001)
+
+            def e2e_masked():
+                rc = L.hode_rollout_fwd_host_ex(ctypes.byref(cfg), ctypes.byref(opts), vp(h["y0"]), vp(h["t"]), vp(h["ins"].get("meal")),
+                                                vp(h["ins"].get("tVNS")), vp(h["ins"].get("GD")), vp(h["theta"]), vp(h["W"]),
+                                                vp(h_g), vp(h_status), vp(h_cnt), ctypes.c_void_p(stream.cuda_stream))
+                _lib.check(rc, "hode_rollout_fwd_host_ex")
+            for _ in range(2):
+                e2e_masked()
+            barrier()
+            n0 = int(L.hode_launch_count())
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_masked()
+            barrier()
+            m_s = time.perf_counter() - t0
+            launches += int(L.hode_launch_count()) - n0
+            m_s, m_att = reduce_max_sum(m_s, float(h_cnt.sum().item()))
+            e2e["glucose_column_only"] = {"value": m_att * e2e_steps / m_s, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+                                          "d2h_bytes_per_step": h_g.numel() * 4 + h_status.numel() * 4 + h_cnt.numel() * 4,
+                                          "api": "hode_rollout_fwd_host_ex, out_state_mask = 0b000001"}
+            del h_g
     elif bwd:
         # the gradient path's e2e: host inputs in (pinned), loss + gradients out to the host — what a training step moves
         h = c.host
