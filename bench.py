@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="hybrid_fwd",
                     choices=["hybrid_fwd", "hybrid_fwdbwd", "vi_predictive", "mech_rk4"])
     ap.add_argument("--traj-per-gpu", type=int, default=0)
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "tf32bf16"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "tf32bf16", "tf32x2bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs of the default run")
     return ap.parse_args()
@@ -637,7 +637,7 @@ def run_ours(args):
         if w["nn"] and args.precision != "fp32":
             kname = ("rollout_tc_kernel<x3,dopri5> (fused Welford mean/std)" if vi else
                      "rollout_tc_kernel<x3,dopri5>" + (" + rollout_bwd_tc_kernel" if bwd else ""))
-            passes = {"tf32x3": 3, "tf32bf16": 2, "tf32": 1}[args.precision]
+            passes = {"tf32x3": 3, "tf32bf16": 2, "tf32x2bf16": 2.5, "tf32": 1}[args.precision]
             roof = tensor_roof(attempts_per_step, ms_step, 3.0 if bwd else 1.0, kname, passes)
             roof["peak_source"] = tensor_src
             key = f"{args.workload}:{B}:{args.precision}"

@@ -14,9 +14,9 @@ LIB_PATH = os.path.join(_PKG, "libhode.so")
 
 ABI_VERSION = 3
 N_STATE, N_THETA, NN_IN = 6, 17, 9
-SOLVER_RK4, SOLVER_DOPRI5 = 0, 1
+SOLVER_RK4, SOLVER_DOPRI5, SOLVER_DOP853 = 0, 1, 2
 IN_ABSENT, IN_CONST, IN_SERIES = 0, 1, 2
-MLP_NONE, MLP_FP32, MLP_TF32X3, MLP_TF32, MLP_TF32BF16 = 0, 1, 2, 3, 4
+MLP_NONE, MLP_FP32, MLP_TF32X3, MLP_TF32, MLP_TF32BF16, MLP_TF32X2BF16 = 0, 1, 2, 3, 4, 5
 KINK_SCIPY, KINK_CLIP = 0, 1
 ST_OK, ST_STEP_TOO_SMALL, ST_MAX_STEPS, ST_NONFINITE, ST_REC_OVERFLOW = 0, 1, 2, 3, 4
 

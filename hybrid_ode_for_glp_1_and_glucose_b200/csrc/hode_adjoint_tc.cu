@@ -494,8 +494,8 @@ __global__ void __launch_bounds__(ADJ_THREADS, 1) rollout_bwd_tc_kernel(const Ad
             tc::mbar_wait(&bars.wf_full, n_f & 1u);
             if (tc::elect_one()) {
               tc::fence_after_sync();
-              if (l == 0) issue_layer<MODE, H, 16, false>(tmem, wf_s, wf_s + 1024u * 4u, 0u);
-              else issue_layer<MODE, H, 64, true>(tmem, wf_s, wf_s + 4096u * 4u, wf_s + 8192u * 4u);
+              if (l == 0) issue_layer<MODE, H, 16, false>(tmem, wf_s, wf_s + 1024u * 4u, 0u, tmem + TM_ONES);
+              else issue_layer<MODE, H, 64, true>(tmem, wf_s, wf_s + 4096u * 4u, wf_s + 8192u * 4u, tmem + TM_ONES);
               tc::mma_commit(&bars.f_bar);
               tc::mma_commit(&bars.wf_free);
               if (l + 1 == L) tc::mma_commit(&bars.fl_bar);

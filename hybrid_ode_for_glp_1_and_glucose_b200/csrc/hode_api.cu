@@ -39,7 +39,8 @@ struct Workspace {
 };
 
 bool uses_tensor_cores(const hode_cfg* c) {
-  return c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32 || c->mlp == HODE_MLP_TF32BF16;
+  return c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32 || c->mlp == HODE_MLP_TF32BF16 ||
+         c->mlp == HODE_MLP_TF32X2BF16;
 }
 
 int max_saved_steps(const hode_cfg* c) {
@@ -89,9 +90,16 @@ int validate(const hode_cfg* c) {
   for (int ch = 0; ch < 3; ++ch)
     if (c->in_mode[ch] < HODE_IN_ABSENT || c->in_mode[ch] > HODE_IN_SERIES)
       return fail(HODE_E_SHAPE, "in_mode out of range");
-  if (c->solver != HODE_SOLVER_RK4 && c->solver != HODE_SOLVER_DOPRI5)
+  if (c->solver != HODE_SOLVER_RK4 && c->solver != HODE_SOLVER_DOPRI5 && c->solver != HODE_SOLVER_DOP853)
     return fail(HODE_E_UNSUPPORTED, "unknown solver");
-  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_TF32BF16)
+  if (c->solver == HODE_SOLVER_DOP853) {
+    // the compatibility solver: FP32 CUDA-core kernels, forward only
+    if (c->mlp != HODE_MLP_NONE && c->mlp != HODE_MLP_FP32)
+      return fail(HODE_E_UNSUPPORTED, "HODE_SOLVER_DOP853 runs on the FP32 kernels: mlp must be HODE_MLP_NONE or HODE_MLP_FP32");
+    if (c->save_steps)
+      return fail(HODE_E_UNSUPPORTED, "HODE_SOLVER_DOP853 is forward only (no step records / adjoint)");
+  }
+  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_TF32X2BF16)
     return fail(HODE_E_UNSUPPORTED, "unknown mlp arithmetic");
   if (c->mlp != HODE_MLP_NONE) {
     if (c->nn_hidden < 1 || c->nn_hidden > HODE_MAX_HIDDEN || c->nn_layers < 1 ||
@@ -102,11 +110,13 @@ int validate(const hode_cfg* c) {
     if (hode::simt_min_smem_bytes(c->nn_hidden, c->nn_layers) > 227 * 1024)
       return fail(HODE_E_UNSUPPORTED, "network too large: its weight image and activation columns exceed the 227 KB of "
                                       "shared memory per CTA (e.g. 128 x 4 needs 239 KB)");
-    if (uses_tensor_cores(c) && (c->nn_hidden != 64 || c->nn_layers > 6))
-      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 6 (the weight image of "
-                                      "deeper networks does not fit the 227 KB of shared memory)");
+    if (uses_tensor_cores(c) && (c->nn_hidden != 64 || c->nn_layers > 5))
+      return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 5 (the weight image of "
+                                      "deeper networks and the stage store do not fit the 227 KB of shared memory)");
+    if (c->mlp == HODE_MLP_TF32X2BF16 && c->nn_layers > 4)
+      return fail(HODE_E_UNSUPPORTED, "HODE_MLP_TF32X2BF16 (three tiles per SM) requires nn_layers <= 4");
   }
-  if (c->solver == HODE_SOLVER_DOPRI5 && (!(c->rtol > 0) || !(c->atol >= 0)))
+  if (c->solver != HODE_SOLVER_RK4 && (!(c->rtol > 0) || !(c->atol >= 0)))
     return fail(HODE_E_SIZE, "rtol must be > 0 and atol >= 0");
   if (c->kink_mode != HODE_KINK_SCIPY && c->kink_mode != HODE_KINK_CLIP)
     return fail(HODE_E_UNSUPPORTED, "unknown kink_mode");

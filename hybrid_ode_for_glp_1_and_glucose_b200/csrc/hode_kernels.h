@@ -42,7 +42,8 @@ cudaError_t launch_reduce_partials(const float* partials, int ctas_per_set, int 
                                    float* grad_theta, cudaStream_t stream);
 
 // tensor-core discrete adjoint (hode_adjoint_tc.cu)
-int tc_image_floats(int L);
+int tc_image_floats(int L);                      // 3xTF32 / TF32+BF16 images (what the adjoint recomputes from)
+int tc_image_floats_mode(int L, int mlp_mode);   // ... and the larger HODE_MLP_TF32X2BF16 image
 int tc_bwd_image_floats(int L);
 cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, int mlp_mode, cudaStream_t stream);
 struct AdjTcPlan {

@@ -11,6 +11,8 @@
 #include "hode_common.cuh"
 #include "hode_kernels.h"
 
+#include "hode_dop853_coef.cuh"
+
 namespace hode {
 
 // ------------------------------------------------------------------------------------------
@@ -461,13 +463,223 @@ __device__ __forceinline__ void simt_integrate(const RolloutArgs& A, const MlpSm
 }
 
 // ------------------------------------------------------------------------------------------
+// DOP853 — what the reference's solver='dopri5' and 'dop853' really run (models/hybrid_ode_nn.py:174-181 ->
+// scipy rk.py:568-720).  One unit per thread, the reference's own arithmetic: float32 RHS, float64 stepping.
+// 12 stages + the 8(5,3) error norm (rk.py:683-691), the RK45 controller with exponent -1/8, and the
+// 7th-order dense output from three extra stages (rk.py:693-712, 739-765), evaluated only for steps that
+// contain observation times (ivp.py:701-718).  The 16 x 6 stage derivatives live in local memory: this is
+// the compatibility solver, not the throughput path (HODE_SOLVER_DOPRI5 on the tensor cores is).
+// ------------------------------------------------------------------------------------------
+template <int MLP_KIND>
+__device__ __noinline__ void dop853_integrate(const RolloutArgs& A, const MlpSmem& mlp, const float* t_shared,
+                                              int s, long b, int vi_n) {
+  const long unit = (long)s * A.B + b;
+  const long n_units = (long)A.S * A.B;
+  const Theta th = load_theta(A.theta + (A.theta_per_traj ? (size_t)b : (size_t)s) * HODE_N_THETA);
+  TrajInputs in;
+  in.T = A.T;
+  in.cur = 0;
+  in.t_obs = A.t_per_traj ? A.t_obs + b * A.T : (t_shared ? t_shared : A.t_obs);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    in.mode[ch] = A.in_mode[ch];
+    in.u[ch] = in.mode[ch] == HODE_IN_SERIES ? A.u[ch] + b * A.T
+             : in.mode[ch] == HODE_IN_CONST ? A.u[ch] + b : nullptr;
+  }
+  float* out = A.traj ? A.traj + (size_t)unit * A.T * (A.out_nc ? A.out_nc : NS) : nullptr;
+  const int T = A.T;
+  const double rtol = (double)A.rtol, atol = (double)A.atol;
+  const int max_steps = A.max_steps > 0 ? A.max_steps : 100000;
+  const double t0 = (double)in.t_obs[0], t_bound = (double)in.t_obs[T - 1];
+
+  double y[NS], K[DOP853_N_STAGES_EXT][NS];
+  float yf[NS], df[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) { yf[i] = A.y0[b * NS + i]; y[i] = (double)yf[i]; }
+  int status = HODE_ST_OK, n_acc = 0, n_rej = 0, ei = 0;
+  double t = t0;
+  rhs_full<MLP_KIND>(th, mlp, in, t, yf, df);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) K[0][i] = (double)df[i];
+  while (ei < T && (double)in.t_obs[ei] <= t) {
+    emit_row(A, out, b, ei, yf, vi_n);
+    ++ei;
+  }
+  bool alive = t < t_bound;
+  double h_abs = 0.0;
+  if (alive) {
+    // select_initial_step, common.py:68-134 (order = error_estimator_order = 7)
+    double sc[NS], s0 = 0, s1 = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      sc[i] = atol + fabs(y[i]) * rtol;
+      const double a = y[i] / sc[i], c = K[0][i] / sc[i];
+      s0 += a * a; s1 += c * c;
+    }
+    const double d0 = sqrt(s0) / sqrt((double)NS), d1 = sqrt(s1) / sqrt((double)NS);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    const double interval = t_bound - t0;
+    if (h0 > interval) h0 = interval;
+    float y1[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) y1[i] = (float)(y[i] + h0 * K[0][i]);
+    rhs_full<MLP_KIND>(th, mlp, in, t0 + h0, y1, df);
+    double s2 = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { const double a = ((double)df[i] - K[0][i]) / sc[i]; s2 += a * a; }
+    const double d2 = sqrt(s2) / sqrt((double)NS) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 8.0);
+    h_abs = fmin(fmin(100.0 * h0, h1), interval);
+  }
+  int attempts = 0, kink_cur = 1;
+  bool prev_rejected = false, need_stop = true;
+  double t_stop = t_bound;
+  while (alive) {
+    if (need_stop) {
+      t_stop = t_bound;
+      if (A.kink_mode == HODE_KINK_CLIP && any_series(in)) {
+        while (kink_cur < T - 1 && !((double)in.t_obs[kink_cur] > t && is_kink(in, kink_cur))) ++kink_cur;
+        if (kink_cur < T - 1) t_stop = (double)in.t_obs[kink_cur];
+      }
+      in.cur = grid_index_from(in, (float)t, in.cur);
+      if (in.cur > 0) --in.cur;
+      need_stop = false;
+    }
+    const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+    if (!prev_rejected && h_abs < min_step) h_abs = min_step;
+    if (h_abs < min_step) { status = HODE_ST_STEP_TOO_SMALL; break; }
+    if (attempts >= max_steps) { status = HODE_ST_MAX_STEPS; break; }
+    ++attempts;
+    double t_new = t + h_abs;
+    if (t_new - t_stop > 0) t_new = t_stop;
+    const double h = t_new - t;
+    h_abs = h;
+    // ---- rk_step, rk.py:14-71 ---------------------------------------------------------------
+#pragma unroll 1
+    for (int st = 1; st < DOP853_N_STAGES; ++st) {
+      float ysf[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        double dy = 0;
+        for (int j = 0; j < st; ++j) dy += K[j][i] * DOP853_A[st][j];
+        ysf[i] = (float)(y[i] + dy * h);
+      }
+      rhs_full<MLP_KIND>(th, mlp, in, t + DOP853_C[st] * h, ysf, df);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) K[st][i] = (double)df[i];
+    }
+    double y_new[NS];
+    float ynf[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      double acc = 0;
+      for (int j = 0; j < DOP853_N_STAGES; ++j) acc += K[j][i] * DOP853_B[j];
+      y_new[i] = y[i] + h * acc;
+      ynf[i] = (float)y_new[i];
+    }
+    rhs_full<MLP_KIND>(th, mlp, in, t + h, ynf, df);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) K[DOP853_N_STAGES][i] = (double)df[i];
+    // ---- _estimate_error_norm, rk.py:683-691 -----------------------------------------------------
+    double e5n = 0, e3n = 0;
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const double scale = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+      double a5 = 0, a3 = 0;
+      for (int j = 0; j <= DOP853_N_STAGES; ++j) { a5 += K[j][i] * DOP853_E5[j]; a3 += K[j][i] * DOP853_E3[j]; }
+      a5 /= scale; a3 /= scale;
+      e5n += a5 * a5; e3n += a3 * a3;
+      finite = finite && isfinite(y_new[i]);
+    }
+    const double err = (e5n == 0 && e3n == 0) ? 0.0 : fabs(h) * e5n / sqrt((e5n + 0.01 * e3n) * NS);
+    if (err < 1.0) {
+      double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -1.0 / 8.0));
+      if (prev_rejected) factor = fmin(1.0, factor);
+      prev_rejected = false;
+      ++n_acc;
+      if (ei < T && (double)in.t_obs[ei] <= t_new) {
+        // ---- _dense_output_impl, rk.py:693-712 -------------------------------------------------------
+#pragma unroll 1
+        for (int st = DOP853_N_STAGES + 1; st < DOP853_N_STAGES_EXT; ++st) {
+          float ysf[NS];
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            double dy = 0;
+            for (int j = 0; j < st; ++j) dy += K[j][i] * DOP853_A[st][j];
+            ysf[i] = (float)(y[i] + dy * h);
+          }
+          rhs_full<MLP_KIND>(th, mlp, in, t + DOP853_C[st] * h, ysf, df);
+#pragma unroll
+          for (int i = 0; i < NS; ++i) K[st][i] = (double)df[i];
+        }
+        double F[7][NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          const double dy = y_new[i] - y[i];
+          F[0][i] = dy;
+          F[1][i] = h * K[0][i] - dy;
+          F[2][i] = 2 * dy - h * (K[DOP853_N_STAGES][i] + K[0][i]);
+          for (int q = 0; q < 4; ++q) {
+            double acc = 0;
+            for (int j = 0; j < DOP853_N_STAGES_EXT; ++j) acc += DOP853_D[q][j] * K[j][i];
+            F[3 + q][i] = h * acc;
+          }
+        }
+        while (ei < T && (double)in.t_obs[ei] <= t_new) {
+          // Dop853DenseOutput._call_impl, rk.py:746-765
+          const double x = ((double)in.t_obs[ei] - t) / h;
+          float yo[NS];
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            double v = 0;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+              v += F[6 - q][i];
+              v *= (q % 2 == 0) ? x : 1 - x;
+            }
+            yo[i] = (float)(v + y[i]);
+          }
+          emit_row(A, out, b, ei, yo, vi_n);
+          ++ei;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { y[i] = y_new[i]; K[0][i] = K[DOP853_N_STAGES][i]; }
+      t = t_new;
+      h_abs *= factor;
+      need_stop = true;
+      if (t - t_bound >= 0) alive = false;
+    } else {
+      ++n_rej;
+      if (!finite || !(err == err)) { status = HODE_ST_STEP_TOO_SMALL; break; }
+      h_abs *= fmax(0.2, 0.9 * pow(err, -1.0 / 8.0));
+      prev_rejected = true;
+    }
+  }
+  if (out || vi_n) {
+    const float z[NS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (; ei < T; ++ei) emit_row(A, out, b, ei, z, vi_n);
+  }
+  if (A.status) A.status[unit] = status;
+  if (A.counters) {
+    A.counters[unit] = n_acc;
+    A.counters[n_units + unit] = n_rej;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // The rollout kernel.  Normal mode: grid = (ceil(B / blockDim.x), S), thread = one (sample,
 // trajectory) unit.  Fused posterior-predictive mode (A.vi_mean != nullptr): grid =
 // (ceil(B / blockDim.x), 1); the CTA walks through all S parameter sets for its trajectories,
 // restaging the weight image for each, and reduces mean / std on the fly.
 // ------------------------------------------------------------------------------------------
-template <int MLP_KIND>
-__global__ void __launch_bounds__(128, MLP_KIND == 0 ? 4 : 1) rollout_simt_kernel(const RolloutArgs A) {   // mechanistic: 4 CTAs per SM (<= 128 registers)
+// SOLVER853: the DOP853 instantiation (its own kernel, so that its local-memory stage store does not touch the
+// register allocation of the RK4 / DP5(4) kernels)
+template <int MLP_KIND, bool SOLVER853 = false>
+__global__ void __launch_bounds__(128, (MLP_KIND == 0 && !SOLVER853) ? 4 : 1) rollout_simt_kernel(const RolloutArgs A) {   // mechanistic: 4 CTAs per SM (<= 128 registers)
   extern __shared__ __align__(16) float smem[];
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool vi = A.vi_mean != nullptr;
@@ -500,7 +712,10 @@ __global__ void __launch_bounds__(128, MLP_KIND == 0 ? 4 : 1) rollout_simt_kerne
     if (si > 0) __syncthreads();  // every thread is done with the previous parameter set's image
     if (MLP_KIND != 0) stage_mlp_image(smem, A.W + (size_t)s * A.P, A.H, A.L);
     __syncthreads();
-    if (b < A.B) simt_integrate<MLP_KIND>(A, mlp, t_shared, s, b, vi ? si + 1 : 0);
+    if (b < A.B) {
+      if (SOLVER853) dop853_integrate<MLP_KIND>(A, mlp, t_shared, s, b, vi ? si + 1 : 0);
+      else simt_integrate<MLP_KIND>(A, mlp, t_shared, s, b, vi ? si + 1 : 0);
+    }
   }
 }
 
@@ -592,6 +807,17 @@ cudaError_t launch_rollout_simt(const RolloutArgs& A, int mlp_mode, cudaStream_t
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   dim3 grid((unsigned)((A.B + block - 1) / block), A.vi_mean ? 1u : (unsigned)A.S);
   cudaError_t e;
+  if (A.solver == HODE_SOLVER_DOP853) {
+    auto launch853 = [&](auto kern) -> cudaError_t {
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess) return err;
+      count_launch();
+      kern<<<grid, block, smem, stream>>>(A);
+      return cudaGetLastError();
+    };
+    return kind == 0 ? launch853(rollout_simt_kernel<0, true>)
+         : kind == 1 ? launch853(rollout_simt_kernel<1, true>) : launch853(rollout_simt_kernel<2, true>);
+  }
   switch (kind) {
     case 0:
       count_launch();

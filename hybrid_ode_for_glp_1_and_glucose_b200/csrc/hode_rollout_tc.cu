@@ -32,7 +32,12 @@
 namespace hode {
 
 namespace {
-constexpr int TILES_PER_CTA = 2;
+// MLP_MIX3: three tiles of 128 trajectories per CTA and no helper warps (384 threads x 168 registers; 3 x 160 + 8 TMEM
+// columns); the other modes: two tiles, each with a helper warpgroup (512 threads, setmaxnreg 200 / 56).
+template <int MODE> constexpr int tiles_per_cta() { return MODE == MLP_MIX3 ? 3 : 2; }
+template <int MODE> constexpr bool has_helpers() { return MODE != MLP_MIX3; }
+template <int MODE> constexpr int cta_threads() { return tiles_per_cta<MODE>() * TILE * (has_helpers<MODE>() ? 2 : 1); }
+constexpr int N_KSTAGE = 7 * NS;   // floats of the stage-derivative store per trajectory (k1..k7)
 }  // namespace
 
 // ---- weight image ----------------------------------------------------------------------------------
@@ -46,7 +51,14 @@ constexpr int TILES_PER_CTA = 2;
 // TF32 hi/lo parts of the bias; it multiplies a constant A block [1, 1, 0, ...] kept in TMEM, so the bias rides
 // on the tensor pipe instead of costing one FADD per accumulator element in the epilogue.
 int tc_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024 + L * 512 + 128; }
+// MLP_MIX3 image: [B_hi tf32][B_lo tf32][bf16(B_hi)] per layer
+int tc_image_floats_mode(int L, int mlp_mode) {
+  if (mlp_mode != HODE_MLP_TF32X2BF16) return tc_image_floats(L);
+  return (int)(img_l0<MLP_MIX3>() + (uint32_t)(L - 1) * img_hid<MLP_MIX3>() + img_out<MLP_MIX3>()) + L * 512 + 128;
+}
 
+// mixed: 0 = 3xTF32 (second half B_lo), 1 = MLP_MIXED (second half bf16(B_hi), bf16(B_lo)),
+//        2 = MLP_MIX3 (B_lo, then bf16(B_hi): 2.5 parts per layer)
 __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
                                      int img_floats, int mixed) {
   const float* w = W + (size_t)blockIdx.x * P;
@@ -55,13 +67,13 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
   __syncthreads();
   int n_in = HODE_NN_IN;
   float* dst = out;
-  float* bias_dst = out + 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024;
+  float* bias_dst = out + img_floats - (L * 512 + 128);
   for (int l = 0; l <= L; ++l) {
     const int n_out = (l == L) ? NS : H;
     const int Npad = (l == L) ? 16 : H;
     const int Kpad = (l == 0) ? 16 : H;
     const int part = Kpad * Npad;   // floats of each half
-    uint16_t* hib = reinterpret_cast<uint16_t*>(dst + part);
+    uint16_t* hib = reinterpret_cast<uint16_t*>(dst + (mixed == 2 ? 2 * part : part));
     uint16_t* lob = reinterpret_cast<uint16_t*>(dst + part + part / 2);
     const int n_cols = n_in + (l == 0 ? 1 : 0);   // layer 0: column n_in is the bias
     for (int i = threadIdx.x; i < n_out * n_cols; i += blockDim.x) {
@@ -71,12 +83,13 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
       tc::split_tf32(wv, hi, lo);
       const int o = ((k >> 2) * Npad + n) * 4 + (k & 3);
       dst[o] = __uint_as_float(hi);
-      if (mixed) {
-        const int ob = ((k >> 3) * Npad + n) * 8 + (k & 7);
+      const int ob = ((k >> 3) * Npad + n) * 8 + (k & 7);
+      if (mixed == 1) {
         hib[ob] = (uint16_t)(pack_bf16x2(__uint_as_float(hi), 0.f) & 0xFFFFu);
         lob[ob] = (uint16_t)(pack_bf16x2(wv - __uint_as_float(hi), 0.f) & 0xFFFFu);
       } else {
         dst[part + o] = __uint_as_float(lo);
+        if (mixed == 2) hib[ob] = (uint16_t)(pack_bf16x2(__uint_as_float(hi), 0.f) & 0xFFFFu);
       }
     }
     if (l > 0) {
@@ -88,7 +101,7 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
       }
     }
     w += n_out * n_in + n_out;
-    dst += 2 * part;
+    dst += (mixed == 2) ? 2 * part + part / 2 : 2 * part;
     bias_dst += (l == L) ? 128 : 512;
     n_in = n_out;
   }
@@ -96,7 +109,8 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
 
 cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, int mlp_mode, cudaStream_t stream) {
   count_launch();
-  prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats(L), mlp_mode == HODE_MLP_TF32BF16 ? 1 : 0);
+  prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats_mode(L, mlp_mode),
+                                              mlp_mode == HODE_MLP_TF32BF16 ? 1 : (mlp_mode == HODE_MLP_TF32X2BF16 ? 2 : 0));
   return cudaGetLastError();
 }
 
@@ -293,28 +307,36 @@ __device__ __forceinline__ unsigned long long build_kink_mask(const TrajInputs& 
 // which keeps the kernel small enough for the instruction cache.
 // ---------------------------------------------------------------------------------------------------
 template <int X3, int SOLVER>
-__global__ void __launch_bounds__(2 * TILE* TILES_PER_CTA, 1)
+__global__ void __launch_bounds__(cta_threads<X3>(), 1)
 rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_floats, int* queue) {
+  constexpr int NT = tiles_per_cta<X3>();
+  constexpr int NMAIN = NT * TILE;
+  constexpr bool HELP = has_helpers<X3>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* img = reinterpret_cast<float*>(smem_raw);
-  float* t_sh_buf = img + ((img_floats + 3) & ~3);
-  __shared__ __align__(8) uint64_t mma_bar[TILES_PER_CTA];
+  // stage derivatives k1..k7 of every trajectory of the CTA: component (j, i) of main thread m at
+  // k_sm[(6 j + i) * NMAIN + m] (conflict-free); they are touched a few times per evaluation, so they
+  // live here instead of 42 registers per thread
+  float* k_sm = img + ((img_floats + 3) & ~3);
+  float* t_sh_buf = k_sm + N_KSTAGE * NMAIN;
+  __shared__ __align__(8) uint64_t mma_bar[NT];
   __shared__ __align__(8) uint64_t load_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ int tile_active[TILES_PER_CTA][4];
+  __shared__ int tile_active[NT][4];
   __shared__ int cta_queue;   // fused posterior-predictive mode: next trajectory of this CTA's range
 
   const int tid = threadIdx.x, lane_id = tid & 31;
   // warp-uniform by construction; the shuffle lets ptxas keep everything derived from it
   // (tile, TMEM base, barrier ids) in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  // warpgroups: 0/1 = main warps of tile 0/1 (one trajectory per thread), 2/3 = their helpers
-  const int tile = (warp >> 2) & 1, wq = warp & 3;
-  const bool helper = (warp >> 3) != 0;
+  // warpgroups: 0..NT-1 = main warps of the tiles (one trajectory per thread), NT.. = their helpers
+  const int wg = warp >> 2, wq = warp & 3;
+  const bool helper = HELP && wg >= NT;
+  const int tile = helper ? wg - NT : wg;
 
   if (tid == 0) {
-    tc::mbar_init(&mma_bar[0], 1);
-    tc::mbar_init(&mma_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) tc::mbar_init(&mma_bar[i], 1);
     tc::mbar_init(&load_bar, 1);
     tc::fence_mbar_init();
   }
@@ -331,18 +353,24 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   TileCtx c;
   c.img = img;
   c.mma_bar = &mma_bar[tile];
-  c.tmem = tmem_base_s + (uint32_t)tile * TM_TILE_STRIDE;
+  c.tmem = tmem_base_s + (uint32_t)tile * (X3 == MLP_MIX3 ? TM3_TILE_STRIDE : TM_TILE_STRIDE);
+  c.t_ones = (X3 == MLP_MIX3) ? tmem_base_s + TM3_ONES_ABS : c.tmem + TM_ONES;
   c.lane_base = (uint32_t)(wq * 32) << 16;
   c.parity = 0;
   c.bar_id = 1 + tile;
-  c.bar_all = 3 + tile;
+  c.bar_all = 1 + NT + tile;
   c.wq = wq;
   c.L = A.L;
   {  // constant A block of the bias k-step: this thread's TMEM lane gets [1, 1, 0, 0, 0, 0, 0, 0]
+     // (MLP_MIX3: one block for the CTA; every tile's thread of a lane writes the same values)
     uint32_t ones[8] = {0x3F800000u, 0x3F800000u, 0u, 0u, 0u, 0u, 0u, 0u};
-    HODE_TMEM_ST_X8(c.tmem + c.lane_base + TM_ONES, ones);
+    HODE_TMEM_ST_X8(c.t_ones + c.lane_base, ones);
     tc::wait_st();
   }
+  // all barriers of a MLP_MIX3 tile are over its 128 main threads
+  auto tile_sync = [&] { if (HELP) tile_sync_all(c); else tile_sync_main(c); };
+  float* const kp = k_sm + (tid < NMAIN ? tid : 0);
+#define KS(j, i) kp[((j) * NS + (i)) * NMAIN]
 
   constexpr int NSLOT = (SOLVER == HODE_SOLVER_RK4) ? 4 : 6;
   const int T = A.T;
@@ -363,7 +391,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   // to the main warpgroups, which carry the per-trajectory integrator state.  Each role's code is
   // entirely inside its branch so that ptxas allocates registers against the role's own budget.
   if (helper) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+    if (HELP) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     for (int si = 0; si < A.S; ++si) {
       const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
       __syncthreads();
@@ -384,7 +412,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+    if (HELP) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
     for (int si = 0; si < A.S; ++si) {
       const int s = (int)((blockIdx.x + (unsigned)si) % (unsigned)A.S);
       const int vi_n = vi ? si + 1 : 0;
@@ -419,12 +447,11 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       for (int i = 0; i < NS; ++i) { ln.y[i] = 0.f; ln.cmp[i] = 0.f; }
       bool queue_dry = false;
       int q_next = 0, q_end = 0;   // this warp's current chunk of the trajectory queue (warp-uniform)
-      // stage vectors: k[0] = k1 (FSAL) ... k[6] = k7;  RK4 uses k[0..3]
-      float k[7][NS];
+      // stage vectors: KS(0, .) = k1 (FSAL) ... KS(6, .) = k7;  RK4 uses k1..k4
   #pragma unroll
       for (int j = 0; j < 7; ++j)
   #pragma unroll
-        for (int i = 0; i < NS; ++i) k[j][i] = 0.f;
+        for (int i = 0; i < NS; ++i) KS(j, i) = 0.f;
       double h_abs = 0.0, t_stop = 0.0, t_bound = 0.0;
       unsigned long long kink_mask = 0ull;
       int attempts = 0, kink_cur = 1;
@@ -488,10 +515,10 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           // a lane without a trajectory that has not yet seen the end of the queue may still be served
         const bool any = __any_sync(0xffffffffu, ln.has || !queue_dry);
           if (lane_id == 0) tile_active[tile][wq] = any ? 1 : 0;
-          tile_sync_all(c);
+          tile_sync();
           const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
                           tile_active[tile][3];
-          tile_sync_all(c);
+          tile_sync();
           if (!go) break;
         }
 
@@ -570,40 +597,40 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             const float a = (slot == 0) ? 0.f : (slot == 3 ? hf : 0.5f * hf);
   #pragma unroll
             for (int i = 0; i < NS; ++i) {
-              const float kv = (slot == 1) ? k[0][i] : (slot == 2 ? k[1][i] : k[2][i]);
+              const float kv = (slot == 0) ? 0.f : KS(slot - 1, i);
               ys[i] = (slot == 0) ? ln.y[i] : fmaf(a, kv, ln.y[i]);
             }
             te = (slot == 0) ? t : (slot == 3 ? t + h : t + 0.5 * h);
           } else {
             if (slot == 0) {
   #pragma unroll
-              for (int i = 0; i < NS; ++i) ys[i] = init ? ln.y[i] : fmaf(hf, dp::a21 * k[0][i], ln.y[i]);
+              for (int i = 0; i < NS; ++i) ys[i] = init ? ln.y[i] : fmaf(hf, dp::a21 * KS(0, i), ln.y[i]);
               te = init ? t : t + (double)dp::c2 * h;
             } else if (slot == 1) {
   #pragma unroll
               for (int i = 0; i < NS; ++i)
-                ys[i] = init ? fmaf(h0f, k[0][i], ln.y[i])
-                             : fmaf(hf, fmaf(dp::a32, k[1][i], dp::a31 * k[0][i]), ln.y[i]);
+                ys[i] = init ? fmaf(h0f, KS(0, i), ln.y[i])
+                             : fmaf(hf, fmaf(dp::a32, KS(1, i), dp::a31 * KS(0, i)), ln.y[i]);
               te = init ? t + h0 : t + (double)dp::c3 * h;
             } else if (slot == 2) {
   #pragma unroll
               for (int i = 0; i < NS; ++i)
-                ys[i] = fmaf(hf, fmaf(dp::a43, k[2][i], fmaf(dp::a42, k[1][i], dp::a41 * k[0][i])), ln.y[i]);
+                ys[i] = fmaf(hf, fmaf(dp::a43, KS(2, i), fmaf(dp::a42, KS(1, i), dp::a41 * KS(0, i))), ln.y[i]);
               te = t + (double)dp::c4 * h;
             } else if (slot == 3) {
   #pragma unroll
               for (int i = 0; i < NS; ++i)
-                ys[i] = fmaf(hf, fmaf(dp::a54, k[3][i], fmaf(dp::a53, k[2][i], fmaf(dp::a52, k[1][i], dp::a51 * k[0][i]))), ln.y[i]);
+                ys[i] = fmaf(hf, fmaf(dp::a54, KS(3, i), fmaf(dp::a53, KS(2, i), fmaf(dp::a52, KS(1, i), dp::a51 * KS(0, i)))), ln.y[i]);
               te = t + (double)dp::c5 * h;
             } else if (slot == 4) {
   #pragma unroll
               for (int i = 0; i < NS; ++i)
-                ys[i] = fmaf(hf, fmaf(dp::a65, k[4][i], fmaf(dp::a64, k[3][i], fmaf(dp::a63, k[2][i], fmaf(dp::a62, k[1][i], dp::a61 * k[0][i])))), ln.y[i]);
+                ys[i] = fmaf(hf, fmaf(dp::a65, KS(4, i), fmaf(dp::a64, KS(3, i), fmaf(dp::a63, KS(2, i), fmaf(dp::a62, KS(1, i), dp::a61 * KS(0, i))))), ln.y[i]);
               te = t_new;
             } else {
   #pragma unroll
               for (int i = 0; i < NS; ++i) {
-                incr[i] = hf * fmaf(dp::b6, k[5][i], fmaf(dp::b5, k[4][i], fmaf(dp::b4, k[3][i], fmaf(dp::b3, k[2][i], dp::b1 * k[0][i]))));
+                incr[i] = hf * fmaf(dp::b6, KS(5, i), fmaf(dp::b5, KS(4, i), fmaf(dp::b4, KS(3, i), fmaf(dp::b3, KS(2, i), dp::b1 * KS(0, i)))));
                 ynew[i] = ln.y[i] + (incr[i] - ln.cmp[i]);
                 ys[i] = ynew[i];
               }
@@ -613,26 +640,14 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
           lane_eval<X3>(c, th, ln, te, ys, d);
           if (SOLVER == HODE_SOLVER_RK4) {
   #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              if (slot == 0) k[0][i] = d[i];
-              else if (slot == 1) k[1][i] = d[i];
-              else if (slot == 2) k[2][i] = d[i];
-              else k[3][i] = d[i];
-            }
+            for (int i = 0; i < NS; ++i) KS(slot, i) = d[i];
           } else {
   #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              if (slot == 0) k[1][i] = d[i];
-              else if (slot == 1) k[2][i] = d[i];
-              else if (slot == 2) k[3][i] = d[i];
-              else if (slot == 3) k[4][i] = d[i];
-              else if (slot == 4) k[5][i] = d[i];
-              else k[6][i] = d[i];
-            }
+            for (int i = 0; i < NS; ++i) KS(slot + 1, i) = d[i];
             if (init && slot == 0) {
               // f(t0, y0) -> k1; outputs at t_eval <= t0; first part of select_initial_step
   #pragma unroll
-              for (int i = 0; i < NS; ++i) k[0][i] = d[i];
+              for (int i = 0; i < NS; ++i) KS(0, i) = d[i];
               while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t) {
                 emit_row(A, ln.out, ln.b, ln.ei, ln.y, vi_n);
                 ++ln.ei;
@@ -655,7 +670,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               if (interval > 0) {
                 float v0[NS];
   #pragma unroll
-                for (int i = 0; i < NS; ++i) v0[i] = (d[i] - k[0][i]) / sc[i];
+                for (int i = 0; i < NS; ++i) v0[i] = (d[i] - KS(0, i)) / sc[i];
                 const float d2 = rms6v(v0) / h0f;
                 double h1;
                 if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmax(1e-6, h0 * 1e-3);
@@ -671,10 +686,17 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         // ---- close the round ----------------------------------------------------------------------------
         if (SOLVER == HODE_SOLVER_RK4) {
           if (run) {
-            if (A.save_n && ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf, k, 2);
+            if (A.save_n && ln.n_saved < A.max_saved) {
+              float kl[3][NS];
+  #pragma unroll
+              for (int j = 0; j < 3; ++j)
+  #pragma unroll
+                for (int i = 0; i < NS; ++i) kl[j][i] = KS(j, i);
+              lane_save_step(ln, A, t, hf, kl, 2);
+            }
   #pragma unroll
             for (int i = 0; i < NS; ++i) {
-              const float inc = (hf * (1.0f / 6.0f)) * (k[0][i] + 2.0f * k[1][i] + 2.0f * k[2][i] + k[3][i]);
+              const float inc = (hf * (1.0f / 6.0f)) * (KS(0, i) + 2.0f * KS(1, i) + 2.0f * KS(2, i) + KS(3, i));
               const float yk = inc - ln.cmp[i];
               const float tn = ln.y[i] + yk;
               ln.cmp[i] = (tn - ln.y[i]) - yk;
@@ -701,7 +723,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   #pragma unroll
           for (int i = 0; i < NS; ++i) {
             const float scale = fmaf(fmaxf(fabsf(ln.y[i]), fabsf(ynew[i])), rtol, atol);
-            const float ee = hf * fmaf(dp::e7, k[6][i], fmaf(dp::e6, k[5][i], fmaf(dp::e5, k[4][i], fmaf(dp::e4, k[3][i], fmaf(dp::e3, k[2][i], dp::e1 * k[0][i])))));
+            const float ee = hf * fmaf(dp::e7, KS(6, i), fmaf(dp::e6, KS(5, i), fmaf(dp::e5, KS(4, i), fmaf(dp::e4, KS(3, i), fmaf(dp::e3, KS(2, i), dp::e1 * KS(0, i))))));
             const float q = __fdividef(ee, scale);
             e2 = fmaf(q, q, e2);
             finite = finite && isfinite(ynew[i]);
@@ -714,14 +736,20 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             ++ln.n_acc;
             bool ok = true;
             if (A.save_n) {
-              if (ln.n_saved < A.max_saved) lane_save_step(ln, A, t, hf, k, 5);
-              else { ln.status = HODE_ST_REC_OVERFLOW; ok = false; }
+              if (ln.n_saved < A.max_saved) {
+                float kl[6][NS];
+  #pragma unroll
+                for (int j = 0; j < 6; ++j)
+  #pragma unroll
+                  for (int i = 0; i < NS; ++i) kl[j][i] = KS(j, i);
+                lane_save_step(ln, A, t, hf, kl, 5);
+              } else { ln.status = HODE_ST_REC_OVERFLOW; ok = false; }
             }
             if (ok) {
               if (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
                 float Q[NS][4];
   #pragma unroll
-                for (int i = 0; i < NS; ++i) dp::dense_q(k[0][i], k[2][i], k[3][i], k[4][i], k[5][i], k[6][i], Q[i]);
+                for (int i = 0; i < NS; ++i) dp::dense_q(KS(0, i), KS(2, i), KS(3, i), KS(4, i), KS(5, i), KS(6, i), Q[i]);
                 while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
                   const double te = (double)ln.in.t_obs[ln.ei];
                   float yo[NS];
@@ -745,7 +773,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
                 const float yk = incr[i] - ln.cmp[i];
                 ln.cmp[i] = (ynew[i] - ln.y[i]) - yk;
                 ln.y[i] = ynew[i];
-                k[0][i] = k[6][i];
+                KS(0, i) = KS(6, i);
               }
               ln.t = t_new;
               h_abs *= (double)factor;
@@ -771,6 +799,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
 
   }
 
+#undef KS
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
@@ -802,16 +831,17 @@ __global__ void kink_mask_kernel(const RolloutArgs A, unsigned long long* __rest
 }
 
 size_t tc_workspace_bytes(int S, int L, int B) {
-  return (size_t)S * tc_image_floats(L) * sizeof(float) + 256 + (((size_t)S * sizeof(int) + 255) & ~(size_t)255) +
+  return (size_t)S * tc_image_floats_mode(L, HODE_MLP_TF32X2BF16) * sizeof(float) + 256 + (((size_t)S * sizeof(int) + 255) & ~(size_t)255) +
          (size_t)B * sizeof(unsigned long long);
 }
 
 cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* workspace, cudaStream_t stream) {
   RolloutArgs A = A_in;
-  const int img_floats = tc_image_floats(A.L);
+  const int img_floats = tc_image_floats_mode(A.L, mlp_mode);
+  const int max_img_floats = tc_image_floats_mode(A.L, HODE_MLP_TF32X2BF16);   // the workspace layout is mode-independent
   float* img = reinterpret_cast<float*>(workspace);
   int* queue = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
-                                      (((size_t)A.S * img_floats * sizeof(float) + 255) / 256) * 256);
+                                      (((size_t)A.S * max_img_floats * sizeof(float) + 255) / 256) * 256);
   cudaError_t e = cudaMemsetAsync(queue, 0, (size_t)A.S * sizeof(int), stream);
   if (e != cudaSuccess) return e;
   if (A.solver == HODE_SOLVER_DOPRI5 && A.kink_mode == HODE_KINK_CLIP && A.T <= 64 &&
@@ -829,24 +859,29 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  size_t smem = (size_t)((img_floats + 3) & ~3) * sizeof(float);
+  const bool mix3 = mlp_mode == HODE_MLP_TF32X2BF16;
+  const int n_main = (mix3 ? tiles_per_cta<MLP_MIX3>() : tiles_per_cta<MLP_X3>()) * TILE;
+  const int n_thr = mix3 ? cta_threads<MLP_MIX3>() : cta_threads<MLP_X3>();
+  size_t smem = (size_t)(((img_floats + 3) & ~3) + N_KSTAGE * n_main) * sizeof(float);
   if (!A.t_per_traj && A.T <= HODE_SIMT_MAX_SHARED_T) smem += (size_t)A.T * sizeof(float);
   smem = (smem + 1023) & ~(size_t)1023;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   const long units = (long)A.B;
   int grid = sms;
-  const long need = (units + TILE * TILES_PER_CTA - 1) / (TILE * TILES_PER_CTA);
+  const long need = (units + n_main - 1) / n_main;
   if (need < grid) grid = (int)(need > 0 ? need : 1);
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     count_launch();
-    kern<<<grid, 2 * TILE * TILES_PER_CTA, smem, stream>>>(A, img, img_floats, queue);
+    kern<<<grid, n_thr, smem, stream>>>(A, img, img_floats, queue);
     return cudaSuccess;
   };
   const bool rk4 = A.solver == HODE_SOLVER_RK4;
   if (mlp_mode == HODE_MLP_TF32X3)
     e = rk4 ? launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_DOPRI5>);
+  else if (mix3)
+    e = rk4 ? launch(rollout_tc_kernel<MLP_MIX3, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_MIX3, HODE_SOLVER_DOPRI5>);
   else if (mlp_mode == HODE_MLP_TF32BF16)
     e = rk4 ? launch(rollout_tc_kernel<MLP_MIXED, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_MIXED, HODE_SOLVER_DOPRI5>);
   else

@@ -36,12 +36,18 @@ constexpr int H = 64;
 //   MLP_MIXED  D = bf16(A_lo) bf16(B_hi) + bf16(A_hi) bf16(B_lo) + A_hi B_hi: one kind::tf32 pass + two
 //              kind::f16 BF16 passes at twice its rate = 2 pass-equivalents (opt-in: max error 4.5e-7 of
 //              sum|a b|, 2x an FP32 FMA chain — csrc/probe/mix_probe.cu)
-constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2;
+//   MLP_MIX3   D = bf16(A_lo) bf16(B_hi) + A_hi B_lo + A_hi B_hi: two kind::tf32 passes + one BF16 pass = 2.5
+//              pass-equivalents; its A operand needs only 96 TMEM columns (no second copy of A_hi), so THREE
+//              tiles fit the 512 columns of an SM — the rollout's default (hode_rollout_tc.cu); at least as
+//              accurate as MLP_MIXED (the A_hi B_lo term is exact to TF32 instead of BF16)
+constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2, MLP_MIX3 = 3;
 // TMEM columns of one tile:
 //   [0,64) accumulator D | [64,128) A_hi (TF32) | [192,200) constant [1,1,0..] (bias step) |
 //   MLP_X3:    [128,192) A_lo = A - A_hi (TF32)
 //   MLP_MIXED: [128,160) bf16(A_hi), two features per column | [160,192) bf16(A - A_hi)
+//   MLP_MIX3:  [128,160) bf16(A - A_hi); tile stride 160, ONE constant block for the whole CTA at column 480
 constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_AHB = 128, TM_ALB = 160, TM_ONES = 192, TM_TILE_STRIDE = 256;
+constexpr uint32_t TM3_ALB = 128, TM3_TILE_STRIDE = 160, TM3_ONES_ABS = 480;
 // float offsets inside the shared-memory weight image (prep_tc_image_kernel, hode_rollout_tc.cu):
 //   layer 0 (K = 16: 9 features, feature 9 = constant 1 whose weight column is the bias, zero padding):
 //     [B_hi tf32 1024][second half 1024]
@@ -49,7 +55,11 @@ constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_AHB = 128, TM_ALB = 
 //   output layer (K = 64, N = 16):            [B_hi 1024][second half 1024]
 //   second half = B_lo (TF32 of B - B_hi; MLP_X3) or [bf16(B_hi)][bf16(B - B_hi)] (half as many floats each; MLP_MIXED)
 //   bias blocks (one K = 8 TF32 step, columns 0/1 = hi/lo): L x 512 (block 0 unused) + 128
+//   MLP_MIX3: [B_hi tf32][B_lo tf32][bf16(B_hi)] = 2.5 x the floats of B_hi per layer
 constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
+template <int MODE> __host__ __device__ constexpr uint32_t img_l0() { return MODE == MLP_MIX3 ? 2560u : IMG_L0; }
+template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MODE == MLP_MIX3 ? 10240u : IMG_HID; }
+template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : IMG_OUT; }
 
 // Activation stash of the adjoint (one block per hidden layer, per CTA): the tile's
 // a_l = relu(z_l) as the BF16 operand image the weight-gradient MMAs read (csrc/probe/bf16_probe.cu),
@@ -101,6 +111,7 @@ struct TileCtx {
   const float* img;     // shared-memory weight image
   uint64_t* mma_bar;    // this tile's MMA-complete mbarrier
   uint32_t tmem;        // this tile's TMEM column base (lane field 0)
+  uint32_t t_ones;      // TMEM address (lane field 0) of the constant [1,1,0..] block of the bias step
   uint32_t lane_base;   // (warp%4)*32 << 16
   uint32_t parity;      // mbarrier phase to wait for next
   int bar_id;           // named barrier of the tile's 4 main warps (128 threads)
@@ -111,6 +122,9 @@ struct TileCtx {
 
 __device__ __forceinline__ void tile_sync_all(const TileCtx& c) {
   asm volatile("bar.sync %0, 256;" ::"r"(c.bar_all) : "memory");
+}
+__device__ __forceinline__ void tile_sync_main(const TileCtx& c) {
+  asm volatile("bar.sync %0, 128;" ::"r"(c.bar_id) : "memory");
 }
 // kind::f16 instruction descriptor, BF16 operands, FP32 accumulation, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -132,7 +146,7 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // layers) or, in layer 0, the weight column of the constant-1 input feature.
 // b_hi: TF32 image of the weights; b_2: the second half of the layer's image (IMG_* above).
 template <int MODE, int N, int K, bool BIAS>
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32_t b_2, uint32_t b_bias) {
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32_t b_2, uint32_t b_bias, uint32_t t_ones) {
   constexpr uint32_t idesc = tc::make_idesc_tf32(TILE, N), idesc_b = make_idesc_bf16(TILE, N);
   constexpr uint32_t lbo16 = (uint32_t)N;                 // (N*16 bytes) >> 4: stride between 16-byte K chunks
   constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
@@ -142,7 +156,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32
   const uint32_t lo_bias = ((b_bias >> 4) & 0x3FFFu) | (lbo16 << 16);
   uint32_t acc = 0u;
   if (BIAS) {   // D = bias (hi + lo through the constant [1,1,0..] block): initialises the accumulator
-    tc::mma_tf32_ts(d, tmem + TM_ONES, ((uint64_t)desc_hi << 32) | (uint64_t)lo_bias, idesc, 0u);
+    tc::mma_tf32_ts(d, t_ones, ((uint64_t)desc_hi << 32) | (uint64_t)lo_bias, idesc, 0u);
     acc = 1u;
   }
   if (MODE == MLP_X3) {
@@ -168,6 +182,18 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32
     for (int ks = 0; ks < K / 16; ++ks)    // bf16(A_hi) bf16(B_lo)
       mma_bf16_ts(d, tmem + TM_AHB + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_lob + (uint32_t)ks * 2u * lbo16), idesc_b, 1u);
   }
+  if (MODE == MLP_MIX3) {
+    // b_2 = B_lo (TF32), then bf16(B_hi) after K * N * 4 bytes
+    const uint32_t lo_hib = lo_2 + ((uint32_t)(K * N * 4) >> 4);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {  // bf16(A_lo) bf16(B_hi)
+      mma_bf16_ts(d, tmem + TM3_ALB + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hib + (uint32_t)ks * 2u * lbo16), idesc_b, acc);
+      acc = 1u;
+    }
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ++ks)     // A_hi B_lo
+      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_2 + (uint32_t)ks * 2u * lbo16), idesc, 1u);
+  }
 #pragma unroll
   for (int ks = 0; ks < K / 8; ++ks) {     // A_hi B_hi
     tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, acc);
@@ -177,16 +203,16 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32
 
 // the MMAs of layer `next` (0 = input layer .. L = output layer) of a tile, from its shared-memory weight image
 template <int MODE>
-__device__ __forceinline__ void issue_mlp_layer(uint32_t tmem, uint32_t img_s, int L, int next) {
-  const uint32_t bias_s = img_s + (IMG_L0 + (uint32_t)(L - 1) * IMG_HID + IMG_OUT) * 4u;
+__device__ __forceinline__ void issue_mlp_layer(uint32_t tmem, uint32_t t_ones, uint32_t img_s, int L, int next) {
+  const uint32_t bias_s = img_s + (img_l0<MODE>() + (uint32_t)(L - 1) * img_hid<MODE>() + img_out<MODE>()) * 4u;
   if (next == 0) {
-    issue_layer<MODE, H, 16, false>(tmem, img_s, img_s + 1024u * 4u, 0u);
+    issue_layer<MODE, H, 16, false>(tmem, img_s, img_s + 1024u * 4u, 0u, t_ones);
   } else if (next < L) {
-    const uint32_t b = img_s + (IMG_L0 + (uint32_t)(next - 1) * IMG_HID) * 4u;
-    issue_layer<MODE, H, 64, true>(tmem, b, b + 4096u * 4u, bias_s + (uint32_t)next * 512u * 4u);
+    const uint32_t b = img_s + (img_l0<MODE>() + (uint32_t)(next - 1) * img_hid<MODE>()) * 4u;
+    issue_layer<MODE, H, 64, true>(tmem, b, b + 4096u * 4u, bias_s + (uint32_t)next * 512u * 4u, t_ones);
   } else {
-    const uint32_t b = img_s + (IMG_L0 + (uint32_t)(L - 1) * IMG_HID) * 4u;
-    issue_layer<MODE, 16, 64, true>(tmem, b, b + 1024u * 4u, bias_s + (uint32_t)L * 512u * 4u);
+    const uint32_t b = img_s + (img_l0<MODE>() + (uint32_t)(L - 1) * img_hid<MODE>()) * 4u;
+    issue_layer<MODE, 16, 64, true>(tmem, b, b + 1024u * 4u, bias_s + (uint32_t)L * 512u * 4u, t_ones);
   }
 }
 
@@ -217,6 +243,47 @@ __device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo, uint32_t* 
       }
     }
   }
+}
+// MLP_MIX3: v -> TF32 hi bits in place, lb = bf16 pairs of the remainder (8 columns); no other copies
+__device__ __forceinline__ void epilogue16_mix3(uint32_t* v, uint32_t* lb) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float a0 = fmaxf(__uint_as_float(v[j]), 0.f), a1 = fmaxf(__uint_as_float(v[j + 1]), 0.f);
+    const uint32_t h0 = (__float_as_uint(a0) + 0x1000u) & 0xFFFFE000u, h1 = (__float_as_uint(a1) + 0x1000u) & 0xFFFFE000u;
+    v[j] = h0;
+    v[j + 1] = h1;
+    lb[j >> 1] = pack_bf16x2(a0 - __uint_as_float(h0), a1 - __uint_as_float(h1));
+  }
+}
+// The hidden-layer epilogue of one MLP_MIX3 thread (no helper warps): all 64 accumulator columns of its lane.
+__device__ __forceinline__ void epilogue64_mix3(uint32_t t_lane) {
+#ifdef HODE_EPI64_WIDE
+  uint32_t v[32], w[32], lb[16];
+  HODE_TMEM_LD_X32(t_lane + TM_D0, v);
+  HODE_TMEM_LD_X32(t_lane + TM_D0 + 32, w);
+  tc::wait_ld();
+  epilogue16_mix3(v, lb);
+  epilogue16_mix3(v + 16, lb + 8);
+  HODE_TMEM_ST_X32(t_lane + TM_AHI, v);
+  HODE_TMEM_ST_X16(t_lane + TM3_ALB, lb);
+  epilogue16_mix3(w, lb);
+  epilogue16_mix3(w + 16, lb + 8);
+  HODE_TMEM_ST_X32(t_lane + TM_AHI + 32, w);
+  HODE_TMEM_ST_X16(t_lane + TM3_ALB + 16, lb);
+#else
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[32], lb[16];
+    HODE_TMEM_LD_X32(t_lane + TM_D0 + 32 * half, v);
+    tc::wait_ld();
+    epilogue16_mix3(v, lb);
+    epilogue16_mix3(v + 16, lb + 8);
+    HODE_TMEM_ST_X32(t_lane + TM_AHI + 32 * half, v);
+    HODE_TMEM_ST_X16(t_lane + TM3_ALB + 16 * half, lb);
+  }
+#endif
+  tc::wait_st();
+  tc::fence_before_sync();
 }
 
 // The hidden-layer epilogue of one thread: 32 accumulator columns [col0, col0 + 32) of its TMEM lane -> the next
@@ -269,6 +336,12 @@ __device__ __forceinline__ void store_input_operand(uint32_t t_lane, const float
     HODE_TMEM_ST_X8(t_lane + TM_AHB, hb);
     HODE_TMEM_ST_X8(t_lane + TM_ALB, lb);
   }
+  if (MODE == MLP_MIX3) {
+    uint32_t lb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) lb[c] = pack_bf16x2(__uint_as_float(lo[2 * c]), __uint_as_float(lo[2 * c + 1]));
+    HODE_TMEM_ST_X8(t_lane + TM3_ALB, lb);
+  }
   tc::wait_st();
   tc::fence_before_sync();
 }
@@ -289,12 +362,13 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, F
   // main AND helper warps: the helpers arrive here only after they have observed the previous
   // call's last mbarrier phase, so the layer-0 commit below cannot flip the barrier a second time
   // under a helper that is still busy (it would then wait for a phase that has already passed)
-  tile_sync_all(c);
+  // (MLP_MIX3 has no helper warps: every barrier of the tile is over its 128 main threads)
+  if (X3 == MLP_MIX3) tile_sync_main(c); else tile_sync_all(c);
   HODE_TL(2);
   if (c.wq == 0) {
     if (tc::elect_one()) {
       tc::fence_after_sync();
-      issue_mlp_layer<X3>(c.tmem, img_s, c.L, 0);
+      issue_mlp_layer<X3>(c.tmem, c.t_ones, img_s, c.L, 0);
       tc::mma_commit(c.mma_bar);
     }
     __syncwarp();
@@ -312,15 +386,21 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, F
     HODE_TL(10 + 10 * l);
     // the main warp owns accumulator columns [0,32) of its 32 lanes, the helper warp of the same
     // lane quarter columns [32,64) (mlp_tile_helper): the epilogue latency per layer is halved
-    uint32_t v0[32], lo[32];
-    epilogue32_to_tmem<X3>(t_lane, 0u, v0, lo);
-    HODE_TL(12 + 10 * l);
-    tile_sync_all(c);
+    if (X3 == MLP_MIX3) {
+      epilogue64_mix3(t_lane);
+      HODE_TL(12 + 10 * l);
+      tile_sync_main(c);
+    } else {
+      uint32_t v0[32], lo[32];
+      epilogue32_to_tmem<X3>(t_lane, 0u, v0, lo);
+      HODE_TL(12 + 10 * l);
+      tile_sync_all(c);
+    }
     HODE_TL(13 + 10 * l);
     if (c.wq == 0) {
       if (tc::elect_one()) {
         tc::fence_after_sync();
-        issue_mlp_layer<X3>(c.tmem, img_s, c.L, l + 1);
+        issue_mlp_layer<X3>(c.tmem, c.t_ones, img_s, c.L, l + 1);
         tc::mma_commit(c.mma_bar);
       }
       __syncwarp();

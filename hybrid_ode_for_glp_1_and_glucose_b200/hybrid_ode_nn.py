@@ -8,7 +8,8 @@ DESIGN.md:
   * the per-trajectory SciPy loop (:184-256) is one kernel launch for the whole batch;
   * solver='dopri5' is Dormand-Prince 5(4) (what BASELINE.json's north_star specifies);
     the reference silently maps it to DOP853 (:174-181).  'rk45' is the same kernel,
-    'rk4' is new (fixed step);
+    'rk4' is new (fixed step); 'dop853' is the reference's actual default integrator (SciPy DOP853) on the
+    FP32 kernels, forward only;
   * extra keyword arguments (kinks, n_substeps, precision, check_status) select kernel
     behaviour the reference has no switch for;
   * there is no CPU path: constructing with a CPU device works (host logic, state_dict),

@@ -19,8 +19,12 @@ SOLVERS = {
     # the reference maps 'dopri5' -> SciPy DOP853 (models/hybrid_ode_nn.py:174-181); here, as
     # BASELINE.json's north_star specifies, 'dopri5' is Dormand-Prince 5(4) (= SciPy 'RK45').
     "dopri5": _lib.SOLVER_DOPRI5, "rk45": _lib.SOLVER_DOPRI5, "rk4": _lib.SOLVER_RK4,
+    # ... and 'dop853' is that DOP853 (scipy rk.py:568-720): float32 RHS / float64 stepping like the reference,
+    # FP32 CUDA-core kernels, forward only — for callers who want the reference's actual default integrator
+    "dop853": _lib.SOLVER_DOP853,
 }
-PRECISIONS = {"fp32": _lib.MLP_FP32, "tf32x3": _lib.MLP_TF32X3, "tf32": _lib.MLP_TF32, "tf32bf16": _lib.MLP_TF32BF16}
+PRECISIONS = {"fp32": _lib.MLP_FP32, "tf32x3": _lib.MLP_TF32X3, "tf32": _lib.MLP_TF32, "tf32bf16": _lib.MLP_TF32BF16,
+              "tf32x2bf16": _lib.MLP_TF32X2BF16}
 
 
 def default_precision(hidden: int, layers: int) -> str:
@@ -184,6 +188,8 @@ def rollout(y0: torch.Tensor, t_obs: torch.Tensor, inputs: Optional[Dict[str, to
     cfg.save_steps = 1 if save_steps else 0
     cfg.max_saved_steps = int(max_saved_steps)
     if cfg.mlp != _lib.MLP_NONE:
+        if cfg.solver == _lib.SOLVER_DOP853 and precision == "auto":
+            precision = "fp32"   # the DOP853 kernels are the FP32 ones
         cfg.mlp = _mlp_mode(precision, hidden, layers)
     B, T, S = cfg.n_traj, cfg.n_obs, cfg.n_samples
     nc = bin(out_state_mask & 0x3F).count("1") if (out_state_mask & 0x3F) not in (0, 0x3F) else 6

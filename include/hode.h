@@ -45,7 +45,10 @@ extern "C" {
 /* solver keyword (reference models/hybrid_ode_nn.py:137,174-181) */
 enum {
   HODE_SOLVER_RK4 = 0,    /* classical fixed-step RK4, n_substeps per observation interval */
-  HODE_SOLVER_DOPRI5 = 1  /* Dormand-Prince 5(4), SciPy RK45 controller + dense output     */
+  HODE_SOLVER_DOPRI5 = 1, /* Dormand-Prince 5(4), SciPy RK45 controller + dense output     */
+  HODE_SOLVER_DOP853 = 2  /* Hairer's DOP853 as SciPy runs it (rk.py:568-720): what the reference's solver='dopri5'
+                             and 'dop853' reach (models/hybrid_ode_nn.py:174-181).  float32 RHS, float64 stepping
+                             (the reference's arithmetic); FP32 CUDA-core kernels only, forward only */
 };
 
 /* how one external input channel is supplied (reference models/hybrid_ode_nn.py:217-231) */
@@ -64,8 +67,12 @@ enum {
   HODE_MLP_FP32 = 1,   /* FP32 FMA on CUDA cores: parity mode                                */
   HODE_MLP_TF32X3 = 2, /* tcgen05 tensor cores, 3xTF32 split (fp32-equivalent accuracy)      */
   HODE_MLP_TF32 = 3,   /* tcgen05 tensor cores, single TF32 pass (fast, ~1e-3 on residual)   */
-  HODE_MLP_TF32BF16 = 4 /* tcgen05: one TF32 pass + two BF16 cross-term passes (2 pass-equivalents; max
-                           error 4.5e-7 of sum|ab| per product against 1.7e-7 for TF32X3: opt-in)   */
+  HODE_MLP_TF32BF16 = 4, /* tcgen05: one TF32 pass + two BF16 cross-term passes (2 pass-equivalents; max
+                            error 4.5e-7 of sum|ab| per product against 1.7e-7 for TF32X3: opt-in)   */
+  HODE_MLP_TF32X2BF16 = 5 /* tcgen05: A_hi*B_hi and A_hi*B_lo in TF32, A_lo*B_hi in BF16 (2.5 pass-equivalents,
+                             error <= TF32BF16's).  Its TMEM footprint lets the rollout run THREE 128-trajectory
+                             tiles per SM instead of two: the fastest float32-equivalent mode (nn_layers <= 4).
+                             Gradients of a rollout made in this mode are computed with the TF32X3 adjoint. */
 };
 
 /*

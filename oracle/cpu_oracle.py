@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libhode_oracle.so")
 
-SOLVER_RK4, SOLVER_DOPRI5 = 0, 1
+SOLVER_RK4, SOLVER_DOPRI5, SOLVER_DOP853 = 0, 1, 2
 IN_ABSENT, IN_CONST, IN_SERIES = 0, 1, 2
 MLP_NONE, MLP_FP32 = 0, 1
 RHS_F32, RHS_F64 = 0, 1
@@ -45,8 +45,10 @@ def build(force: bool = False) -> str:
     """Compile oracle/hode_oracle.c with gcc (idempotent)."""
     src = os.path.join(_HERE, "hode_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "hode.h")
+    coef = os.path.join(_HERE, "dop853_coef.h")
     stale = (not os.path.exists(_LIB_PATH)
              or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+             or os.path.getmtime(_LIB_PATH) < os.path.getmtime(coef)
              or (os.path.exists(hdr) and os.path.getmtime(_LIB_PATH) < os.path.getmtime(hdr)))
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
@@ -91,7 +93,7 @@ def make_cfg(B: int, T: int, t_obs: np.ndarray, inputs: Dict[str, Optional[np.nd
     cfg.nn_hidden, cfg.nn_layers = hidden, layers
     cfg.mlp = MLP_FP32 if has_nn else MLP_NONE
     cfg.n_samples = n_samples
-    cfg.solver = {"rk4": SOLVER_RK4, "dopri5": SOLVER_DOPRI5, "rk45": SOLVER_DOPRI5}[solver]
+    cfg.solver = {"rk4": SOLVER_RK4, "dopri5": SOLVER_DOPRI5, "rk45": SOLVER_DOPRI5, "dop853": SOLVER_DOP853}[solver]
     cfg.n_substeps, cfg.max_steps = n_substeps, max_steps
     cfg.rtol, cfg.atol = rtol, atol
     cfg.kink_mode = {"scipy": 0, "clip": 1}[kinks]
@@ -138,14 +140,15 @@ def rollout(y0, t_obs, inputs=None, theta=None, W=None, hidden=64, layers=4, sol
 
 
 def rollout_with_steps(b, y0, t_obs, inputs=None, theta=None, W=None, hidden=64, layers=4,
-                       rtol=1e-6, atol=1e-8, rhs="f32", cap=100000, kinks="scipy"):
-    """DP5(4) solve of trajectory b that also returns the accepted-step log (t_n, h_n)."""
+                       rtol=1e-6, atol=1e-8, rhs="f32", cap=100000, kinks="scipy", solver="dopri5"):
+    """Adaptive solve (DP5(4), or DOP853 with solver='dop853') of trajectory b that also returns the accepted-step
+    log (t_n, h_n)."""
     y0 = _f32(np.atleast_2d(y0))
     t_obs = _f32(t_obs)
     B, T = y0.shape[0], t_obs.shape[-1]
     inputs = {k: _f32(v) for k, v in (inputs or {}).items() if v is not None}
     theta = THETA_DEFAULT if theta is None else _f32(theta)
-    cfg = make_cfg(B, T, t_obs, inputs, hidden, layers, W is not None, 1, "dopri5", rtol, atol,
+    cfg = make_cfg(B, T, t_obs, inputs, hidden, layers, W is not None, 1, solver, rtol, atol,
                    1, 0, kinks)
     Wc = None if W is None else _f32(W)
     row = np.zeros((T, 6), dtype=np.float32)

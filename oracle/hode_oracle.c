@@ -18,6 +18,9 @@
  *   - RK45 = Dormand-Prince 5(4) . scipy/integrate/_ivp/rk.py:14-71,111-176,538-565
  *   - initial step ............... scipy/integrate/_ivp/common.py:68-134
  *   - t_eval dense-output loop ... scipy/integrate/_ivp/ivp.py:701-728, rk.py:178-180
+ *   - DOP853 (what the reference's solver='dopri5' / 'dop853' really runs,
+ *     models/hybrid_ode_nn.py:174-181) ... rk.py:568-720, tableau dop853_coefficients.py
+ *     (dop853_coef.h, generated from SciPy by gen_dop853_coef.py), dense output rk.py:739-765
  * 'rk4' (fixed step) has no counterpart in the reference; it is the classical tableau.
  *
  * Parity pin: tests/golden/ holds inputs/outputs produced by importing the reference
@@ -33,6 +36,7 @@
 #include <string.h>
 
 #include "../include/hode.h"
+#include "dop853_coef.h"
 
 #define NS HODE_N_STATE
 #define ORACLE_RHS_F32 0
@@ -238,7 +242,7 @@ static double rms_norm(const double* x, int n) {
 
 /* scipy common.py:68-134 (direction = +1, max_step = inf, order = 4) */
 static double select_initial_step(traj_ctx* c, double t0, const double* y0, double t_bound,
-                                  const double* f0, double rtol, double atol) {
+                                  const double* f0, double rtol, double atol, int order) {
   double interval = fabs(t_bound - t0);
   if (interval == 0.0) return 0.0;
   double scale[NS], a[NS], b[NS];
@@ -259,7 +263,7 @@ static double select_initial_step(traj_ctx* c, double t0, const double* y0, doub
   if (d1 <= 1e-15 && d2 <= 1e-15) {
     h1 = fmax(1e-6, h0 * 1e-3);
   } else {
-    h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+    h1 = pow(0.01 / fmax(d1, d2), 1.0 / (order + 1));
   }
   double h = 100 * h0;
   if (h1 < h) h = h1;
@@ -310,7 +314,7 @@ static int solve_dopri5(traj_ctx* c, const float* y0f, float* traj_out, int32_t*
   int ei = 0; /* t_eval_i */
   memset(traj_out, 0, sizeof(float) * (size_t)T * NS);
   rhs(c, t, y, f);
-  double h_abs = select_initial_step(c, t0, y, t_bound, f, rtol, atol);
+  double h_abs = select_initial_step(c, t0, y, t_bound, f, rtol, atol, 4);
   if (t == t_bound) { /* OdeSolver.step(): already finished; solve_ivp still emits t_eval==t */
     for (; ei < T && (double)c->t_obs[ei] <= t; ++ei)
       for (int i = 0; i < NS; ++i) traj_out[ei * NS + i] = (float)y[i];
@@ -414,6 +418,142 @@ done:
   return status;
 }
 
+/* One trajectory, DOP853 exactly as scipy.solve_ivp(method='DOP853', t_eval=...) does it: 12 stages with an
+   8(5,3) error norm (rk.py:683-691), the RK45 controller with exponent -1/8 (rk.py:111-176), and the 7th-order
+   dense output from three extra stages (rk.py:693-712, 739-765), evaluated only for steps that contain t_eval
+   points (ivp.py:701-718). */
+static int solve_dop853(traj_ctx* c, const float* y0f, float* traj_out, int32_t* n_acc,
+                        int32_t* n_rej, step_log* log) {
+  const hode_cfg* cfg = c->cfg;
+  const int T = cfg->n_obs;
+  const double rtol = (double)cfg->rtol, atol = (double)cfg->atol;
+  const int max_steps = cfg->max_steps > 0 ? cfg->max_steps : 100000;
+  const double t0 = (double)c->t_obs[0], t_bound = (double)c->t_obs[T - 1];
+  double t = t0, y[NS], f[NS], K[DOP853_N_STAGES_EXT][NS];
+  for (int i = 0; i < NS; ++i) y[i] = (double)y0f[i];
+  int accepted = 0, rejected = 0, status = HODE_ST_OK;
+  int ei = 0;
+  memset(traj_out, 0, sizeof(float) * (size_t)T * NS);
+  rhs(c, t, y, f);
+  double h_abs = select_initial_step(c, t0, y, t_bound, f, rtol, atol, 7);
+  if (t == t_bound) {
+    for (; ei < T && (double)c->t_obs[ei] <= t; ++ei)
+      for (int i = 0; i < NS; ++i) traj_out[ei * NS + i] = (float)y[i];
+    *n_acc = 0; *n_rej = 0;
+    return status;
+  }
+  int attempts = 0, kink_cursor = 1;
+  while (1) {
+    const double t_stop = next_stop(c, t, t_bound, &kink_cursor);
+    double min_step = 10.0 * fabs(nextafter(t, INFINITY) - t);
+    if (h_abs < min_step) h_abs = min_step;
+    int step_rejected = 0;
+    double h, t_new, y_new[NS], f_new[NS];
+    while (1) {
+      if (h_abs < min_step) { status = HODE_ST_STEP_TOO_SMALL; goto done; }
+      if (attempts >= max_steps) { status = HODE_ST_MAX_STEPS; goto done; }
+      ++attempts;
+      h = h_abs;
+      t_new = t + h;
+      if (t_new - t_stop > 0) t_new = t_stop;
+      h = t_new - t;
+      h_abs = fabs(h);
+      memcpy(K[0], f, sizeof f);
+      for (int s = 1; s < DOP853_N_STAGES; ++s) {
+        double ys[NS];
+        for (int i = 0; i < NS; ++i) {
+          double dy = 0;
+          for (int j = 0; j < s; ++j) dy += K[j][i] * DOP853_A[s][j];
+          ys[i] = y[i] + dy * h;
+        }
+        rhs(c, t + DOP853_C[s] * h, ys, K[s]);
+      }
+      for (int i = 0; i < NS; ++i) {
+        double acc = 0;
+        for (int j = 0; j < DOP853_N_STAGES; ++j) acc += K[j][i] * DOP853_B[j];
+        y_new[i] = y[i] + h * acc;
+      }
+      rhs(c, t + h, y_new, f_new);
+      memcpy(K[DOP853_N_STAGES], f_new, sizeof f_new);
+      /* _estimate_error_norm, rk.py:683-691 */
+      double e5n = 0, e3n = 0;
+      int finite = 1;
+      for (int i = 0; i < NS; ++i) {
+        const double scale = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+        double a5 = 0, a3 = 0;
+        for (int j = 0; j <= DOP853_N_STAGES; ++j) { a5 += K[j][i] * DOP853_E5[j]; a3 += K[j][i] * DOP853_E3[j]; }
+        a5 /= scale; a3 /= scale;
+        e5n += a5 * a5; e3n += a3 * a3;
+        if (!isfinite(y_new[i])) finite = 0;
+      }
+      double err;
+      if (e5n == 0 && e3n == 0) err = 0.0;
+      else err = fabs(h) * e5n / sqrt((e5n + 0.01 * e3n) * NS);
+      if (err < 1.0) {
+        double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -1.0 / 8.0));
+        if (step_rejected && factor > 1.0) factor = 1.0;
+        h_abs *= factor;
+        break;
+      }
+      if (!finite || !(err == err)) { status = HODE_ST_STEP_TOO_SMALL; ++rejected; goto done; }
+      h_abs *= fmax(0.2, 0.9 * pow(err, -1.0 / 8.0));
+      step_rejected = 1;
+      ++rejected;
+    }
+    ++accepted;
+    if (log && log->n < log->cap) { log->t[log->n] = t; log->h[log->n] = h; log->n++; }
+    {
+      int ei_new = ei;
+      while (ei_new < T && (double)c->t_obs[ei_new] <= t_new) ++ei_new;
+      if (ei_new > ei) {
+        /* _dense_output_impl, rk.py:693-712 */
+        for (int s = DOP853_N_STAGES + 1; s < DOP853_N_STAGES_EXT; ++s) {
+          double ys[NS];
+          for (int i = 0; i < NS; ++i) {
+            double dy = 0;
+            for (int j = 0; j < s; ++j) dy += K[j][i] * DOP853_A[s][j];
+            ys[i] = y[i] + dy * h;
+          }
+          rhs(c, t + DOP853_C[s] * h, ys, K[s]);
+        }
+        double F[7][NS];
+        for (int i = 0; i < NS; ++i) {
+          const double dy = y_new[i] - y[i];
+          F[0][i] = dy;
+          F[1][i] = h * K[0][i] - dy;
+          F[2][i] = 2 * dy - h * (f_new[i] + K[0][i]);
+          for (int q = 0; q < 4; ++q) {
+            double acc = 0;
+            for (int j = 0; j < DOP853_N_STAGES_EXT; ++j) acc += DOP853_D[q][j] * K[j][i];
+            F[3 + q][i] = h * acc;
+          }
+        }
+        for (int k = ei; k < ei_new; ++k) {
+          /* Dop853DenseOutput._call_impl, rk.py:746-765 */
+          const double x = ((double)c->t_obs[k] - t) / h;
+          for (int i = 0; i < NS; ++i) {
+            double v = 0;
+            for (int q = 0; q < 7; ++q) {
+              v += F[6 - q][i];
+              v *= (q % 2 == 0) ? x : 1 - x;
+            }
+            traj_out[k * NS + i] = (float)(v + y[i]);
+          }
+        }
+        ei = ei_new;
+      }
+    }
+    t = t_new;
+    memcpy(y, y_new, sizeof y);
+    memcpy(f, f_new, sizeof f);
+    if (t - t_bound >= 0) break;
+  }
+done:
+  *n_acc = accepted;
+  *n_rej = rejected;
+  return status;
+}
+
 /* One trajectory, classical RK4 with n_substeps equal steps per observation interval. */
 static int solve_rk4(traj_ctx* c, const float* y0f, float* traj_out, int32_t* n_acc) {
   const hode_cfg* cfg = c->cfg;
@@ -495,6 +635,7 @@ static void* worker(void* arg) {
       int st;
       float* out = j->traj + (size_t)unit * T * NS;
       if (cfg->solver == HODE_SOLVER_RK4) st = solve_rk4(&c, j->y0 + b * NS, out, &na);
+      else if (cfg->solver == HODE_SOLVER_DOP853) st = solve_dop853(&c, j->y0 + b * NS, out, &na, &nr, NULL);
       else st = solve_dopri5(&c, j->y0 + b * NS, out, &na, &nr, NULL);
       if (j->status) j->status[unit] = st;
       if (j->counters) { j->counters[unit] = na; j->counters[j->total + unit] = nr; }
@@ -554,7 +695,8 @@ int hode_oracle_rollout_log(const hode_cfg* cfg, int rhs_mode, long b, const flo
   bind_traj(&c, cfg, rhs_mode, b, 0, t_obs, u, theta, W);
   step_log log = {step_t, step_h, cap, 0};
   int32_t na = 0, nr = 0;
-  int st = solve_dopri5(&c, y0 + b * NS, traj_row, &na, &nr, &log);
+  int st = cfg->solver == HODE_SOLVER_DOP853 ? solve_dop853(&c, y0 + b * NS, traj_row, &na, &nr, &log)
+                                             : solve_dopri5(&c, y0 + b * NS, traj_row, &na, &nr, &log);
   *n_steps = log.n;
   return st;
 }

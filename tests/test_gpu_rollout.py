@@ -324,16 +324,20 @@ def test_module_forward_contract(dev, caplog):
 
 
 # ---------------------------------------------------------------------------- tensor-core MLP path
+TC_MODES = ["tf32x3", "tf32x2bf16"]   # 2 tiles / SM + helper warps, 3 tiles / SM (the default)
+
+
+@pytest.mark.parametrize("tc_mode", TC_MODES)
 @pytest.mark.parametrize("layers", [4, 2, 1])
-def test_tc_rk4_parity(dev, oracle, layers):
-    """tcgen05 3xTF32 path: same <= 1e-5 relative bar as the FP32 CUDA-core path."""
+def test_tc_rk4_parity(dev, oracle, layers, tc_mode):
+    """tcgen05 split-precision paths: same <= 1e-5 relative bar as the FP32 CUDA-core path."""
     y0, t, ins = cohort(700, seed=21)                      # not a multiple of the 128-row tile
     W = random_mlp(64, layers, seed=22)
     theta = oracle.THETA_DEFAULT
     ref, _, _, _ = oracle.rollout(y0, t, ins, theta, W, 64, layers, solver="rk4", n_substeps=2,
                                   n_threads=8)
     tr, st, na, _ = gpu_rollout(dev, y0, t, ins, theta, W, 64, layers, solver="rk4", n_substeps=2,
-                                precision="tf32x3")
+                                precision=tc_mode)
     assert (st == 0).all() and (na == 120).all()
     assert rel_err(tr, ref) < 1e-5, rel_err_report(tr, ref)
     # and it agrees with the FP32 CUDA-core kernel to the same level
@@ -347,7 +351,8 @@ def test_tc_rk4_parity(dev, oracle, layers):
     assert 1e-7 < e < 2e-2, e
 
 
-def test_tc_dopri5_accuracy_and_refill(dev, oracle):
+@pytest.mark.parametrize("tc_mode", TC_MODES)
+def test_tc_dopri5_accuracy_and_refill(dev, oracle, tc_mode):
     y0, t, ins = cohort(1500, seed=23)
     W = random_mlp(seed=24, out_std=0.02)
     theta = oracle.THETA_DEFAULT
@@ -356,7 +361,7 @@ def test_tc_dopri5_accuracy_and_refill(dev, oracle):
     truth = truth.astype(np.float64)
     orc, _, cn, _ = oracle.rollout(y0, t, ins, theta, W, kinks="clip", n_threads=8)
     tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip",
-                                 precision="tf32x3")
+                                 precision=tc_mode)
     assert (st == 0).all()
     sc = 1e-8 + 1e-6 * np.abs(truth)
     e_gpu = (np.abs(tr - truth) / sc).max(axis=(1, 2))
@@ -370,11 +375,12 @@ def test_tc_dopri5_accuracy_and_refill(dev, oracle):
     assert np.array_equal(tr[:, 0], y0)
     # lanes are refilled in arbitrary order, yet every trajectory is deterministic
     tr2, _, na2, nr2 = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip",
-                                   precision="tf32x3")
+                                   precision=tc_mode)
     assert np.array_equal(tr, tr2) and np.array_equal(na, na2) and np.array_equal(nr, nr2)
 
 
-def test_tc_layouts_failure_and_sweep(dev, oracle):
+@pytest.mark.parametrize("tc_mode", TC_MODES)
+def test_tc_layouts_failure_and_sweep(dev, oracle, tc_mode):
     rng = np.random.default_rng(25)
     B, T = 333, 25
     y0, _, _ = cohort(B, T, seed=25)
@@ -385,7 +391,7 @@ def test_tc_layouts_failure_and_sweep(dev, oracle):
     thetas = np.stack([oracle.THETA_DEFAULT * (1 + 0.05 * s) for s in range(S)]).astype(np.float32)
     Ws = np.stack([random_mlp(seed=30 + s) for s in range(S)])
     tr, st, _, _ = gpu_rollout(dev, y0, t, ins, thetas, Ws, solver="rk4", n_substeps=3,
-                               precision="tf32x3")
+                               precision=tc_mode)
     assert tr.shape == (S, B, T, 6) and (st == 0).all()
     for s in range(S):
         ref, _, _, _ = oracle.rollout(y0, t, ins, thetas[s], Ws[s], solver="rk4", n_substeps=3,
@@ -395,15 +401,16 @@ def test_tc_layouts_failure_and_sweep(dev, oracle):
     theta = oracle.THETA_DEFAULT.copy()
     theta[16] = 1e6
     trf, stf, _, _ = gpu_rollout(dev, y0[:50], t[0], None, theta, Ws[0], solver="dopri5",
-                                 max_steps=3000, precision="tf32x3")
+                                 max_steps=3000, precision=tc_mode)
     assert (stf != 0).all() and (trf[:, -1] == 0).all() and np.array_equal(trf[:, 0], y0[:50])
     tr1, st1, _, _ = gpu_rollout(dev, y0[:5], t[0, :1], None, oracle.THETA_DEFAULT, Ws[0],
-                                 solver="dopri5", precision="tf32x3")
+                                 solver="dopri5", precision=tc_mode)
     assert tr1.shape == (5, 1, 6) and np.array_equal(tr1[:, 0], y0[:5]) and (st1 == 0).all()
 
 
 # ---------------------------------------------------------------------------- BASELINE configs 3-5
-def test_config5_clinical_shape_long_horizon_per_row_grids(dev, oracle):
+@pytest.mark.parametrize("tc_mode", TC_MODES)
+def test_config5_clinical_shape_long_horizon_per_row_grids(dev, oracle, tc_mode):
     """mimic_clinical-shaped cohort: T = 577 over 48 h, per-row jittered time
     grids, irregular meal / tVNS events.  FP32 and tensor-core paths against the all-float64 truth on
     a subsample, and against each other on the whole batch."""
@@ -419,7 +426,7 @@ def test_config5_clinical_shape_long_horizon_per_row_grids(dev, oracle):
     W = random_mlp(seed=17, out_std=0.001)
     theta = oracle.THETA_DEFAULT
     a, st_a, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip")
-    b, st_b, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip", precision="tf32x3")
+    b, st_b, _, _ = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", kinks="clip", precision=tc_mode)
     assert (st_a == 0).all() and (st_b == 0).all()
     assert na.min() > 40 and (na + nr).max() < 20000
     sub = slice(0, 24)
@@ -432,20 +439,21 @@ def test_config5_clinical_shape_long_horizon_per_row_grids(dev, oracle):
     assert rel_err(b, a.astype(np.float64)) < 4e-4
     # fixed step on the same grids: 1e-5 against the float32-RHS oracle
     c, st_c, _, _ = gpu_rollout(dev, y0[:64], t[:64], {k: v[:64] for k, v in ins.items()}, theta, W,
-                                solver="rk4", n_substeps=2, precision="tf32x3")
+                                solver="rk4", n_substeps=2, precision=tc_mode)
     ref, _, _, _ = oracle.rollout(y0[:64], t[:64], {k: v[:64] for k, v in ins.items()}, theta, W,
                                   solver="rk4", n_substeps=2, n_threads=8)
     assert (st_c == 0).all() and rel_err(c, ref) < 1e-5, rel_err_report(c, ref)
 
 
-def test_config3_full_size_properties_hybrid(dev, oracle):
+@pytest.mark.parametrize("tc_mode", TC_MODES)
+def test_config3_full_size_properties_hybrid(dev, oracle, tc_mode):
     """BASELINE config 3 at bench size (262 144 trajectories, hybrid 64x4, dopri5 1e-6/1e-8, tensor
     cores): size-independent properties + an oracle check on a strided subsample."""
     B = 262144
     y0, t, ins = cohort(B, seed=1000)
     W = random_mlp(64, 4, seed=1234, out_std=0.05)
     theta = oracle.THETA_DEFAULT
-    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", precision="tf32x3")
+    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", precision=tc_mode)
     assert (st == 0).all()
     assert np.array_equal(tr[:, 0], y0)                      # first observation is the initial state
     assert np.isfinite(tr).all()
@@ -455,7 +463,7 @@ def test_config3_full_size_properties_hybrid(dev, oracle):
     # permuted result bit for bit
     perm = np.random.default_rng(0).permutation(B)
     tr2, st2, na2, _ = gpu_rollout(dev, y0[perm], t, {k: v[perm] for k, v in ins.items()}, theta, W,
-                                   solver="dopri5", precision="tf32x3")
+                                   solver="dopri5", precision=tc_mode)
     assert np.array_equal(tr2, tr[perm]) and np.array_equal(na2, na[perm])
     sub = np.arange(0, B, B // 48)
     truth, s2, _, _ = oracle.rollout(y0[sub], t, {k: v[sub] for k, v in ins.items()}, theta, W, rhs="f64",
@@ -487,3 +495,57 @@ def test_module_default_reaches_the_tensor_core_kernel(dev):
     assert torch.equal(a, b)
     assert not torch.equal(a, c)
     assert float((a - c).abs().max() / c.abs().max()) < 1e-4
+
+
+# ---------------------------------------------------------------------------- DOP853
+@pytest.mark.parametrize("name,key", [("dop853_fig2", "out_dop853"), ("dop853_smooth", "out_dop853"),
+                                      ("rollout_const_T2", "out_dopri5"), ("rollout_4gi_nn", "out_dopri5")])
+def test_dop853_matches_the_reference_and_the_oracle(dev, oracle, name, key):
+    """solver='dop853' = SciPy DOP853, what the reference's default solver='dopri5' really runs
+    (models/hybrid_ode_nn.py:174-181): float32 RHS, float64 stepping, kinks='scipy' (no clipping, like SciPy).
+    Against the reference's own outputs and against the oracle (same algorithm, same arithmetic: only the float32
+    RHS rounding differs), in units of the local tolerance atol + rtol |y|."""
+    d = golden(name)
+    ins = golden_inputs(d)
+    tr, st, na, nr = gpu_rollout(dev, d["y0"], d["t"], ins, d["theta"], d["W"], solver="dop853", kinks="scipy")
+    orc, so, cn, _ = oracle.rollout(d["y0"], d["t"], ins, d["theta"], d["W"], solver="dop853")
+    assert (st == 0).all() and (so == 0).all()
+    assert np.array_equal(tr[:, 0], d["y0"])
+    if name == "rollout_4gi_nn":
+        # kinked inputs that SciPy steps over (test_oracle.py::test_reference_steps_over_meal_spikes...): chaotic
+        # step sequences, so only the attempt counts and the size of the deviation are comparable
+        att_g, att_o = (na + nr).mean(), (cn[0] + cn[1]).mean()
+        assert abs(att_g - att_o) / att_o < 0.25
+        assert rel_err(tr, d[key]) < 5e-3 and rel_err(tr, orc) < 5e-3
+        return
+    assert scaled_err(tr, d[key]) < 300, scaled_err(tr, d[key])
+    assert scaled_err(tr, orc) < 300, scaled_err(tr, orc)
+    assert abs(int(na.sum()) - int(cn[0].sum())) <= 0.1 * cn[0].sum() + 2
+
+
+def test_dop853_clip_mode_sweep_and_unsupported_combinations(dev, oracle):
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    from hybrid_ode_for_glp_1_and_glucose_b200._lib import HodeError
+    y0, t, ins = cohort(300, seed=41)
+    W = random_mlp(seed=42, out_std=0.02)
+    thetas = np.stack([oracle.THETA_DEFAULT, oracle.THETA_DEFAULT * 1.05]).astype(np.float32)
+    Ws = np.stack([W, random_mlp(seed=43, out_std=0.02)])
+    tr, st, na, nr = gpu_rollout(dev, y0, t, ins, thetas, Ws, solver="dop853", kinks="clip")
+    assert tr.shape == (2, 300, 61, 6) and (st == 0).all()
+    truth, _, _, _ = oracle.rollout(y0, t, ins, thetas, Ws, rhs="f64", rtol=1e-11, atol=1e-13, kinks="clip", n_threads=8)
+    orc, _, _, _ = oracle.rollout(y0, t, ins, thetas, Ws, solver="dop853", kinks="clip", n_threads=8)
+    sc = 1e-8 + 1e-6 * np.abs(truth.astype(np.float64))
+    e_gpu = (np.abs(tr - truth) / sc).max(axis=(2, 3))
+    e_cpu = (np.abs(orc - truth) / sc).max(axis=(2, 3))
+    assert np.median(e_gpu) <= 1.5 * np.median(e_cpu) and np.percentile(e_gpu, 90) <= 2.0 * np.percentile(e_cpu, 90)
+    # mechanistic only
+    trm, stm, _, _ = gpu_rollout(dev, y0, t, ins, oracle.THETA_DEFAULT, None, solver="dop853")
+    orm, _, _, _ = oracle.rollout(y0, t, ins, oracle.THETA_DEFAULT, None, solver="dop853", kinks="clip", n_threads=8)
+    assert (stm == 0).all() and rel_err(trm, orm) < 1e-4
+    # the tensor-core kernels and the adjoint do not implement it: loud errors, no silent fallback
+    with pytest.raises(HodeError):
+        gpu_rollout(dev, y0, t, ins, oracle.THETA_DEFAULT, W, solver="dop853", precision="tf32x3")
+    with pytest.raises(HodeError):
+        ops.rollout(torch.from_numpy(y0), torch.from_numpy(t), {k: torch.from_numpy(v) for k, v in ins.items()},
+                    torch.from_numpy(oracle.THETA_DEFAULT), torch.from_numpy(W), device=dev, solver="dop853",
+                    save_steps=True)

@@ -10,7 +10,9 @@ flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "--expt-relaxed-constexpr"]
 subprocess.run(["nvcc", *flags, "-DHODE_TIMELINE", "-c", os.path.join(CSRC, "hode_rollout_tc.cu"), "-o",
                 "/tmp/hode_rollout_tc_tl.o"], check=True)
-objs = [os.path.join(CSRC, f) for f in ("hode_api.o", "hode_rollout_simt.o", "hode_adjoint_simt.o", "hode_adjoint_tc.o", "hode_gen4gi.o")]
+objs = [os.path.join(CSRC, f) for f in ("hode_api.o", "hode_rollout_simt.o", "hode_adjoint_simt.o", "hode_adjoint_tc.o", "hode_gen4gi.o",
+                                        "hode_train.o", "hode_data.o")]
+PRECISION = os.environ.get("TL_PRECISION", "tf32x2bf16")
 lib = os.path.join(ROOT, "hybrid_ode_for_glp_1_and_glucose_b200", "libhode.so")
 os.rename(lib, lib + ".bak")
 try:
@@ -28,7 +30,7 @@ try:
     L.hode_debug_timeline.restype = ctypes.c_int
     buf = np.zeros(2 * 16384, dtype=np.int64)
     for it in range(2):
-        ops.rollout(*args, solver="dopri5", precision="tf32x3", device=dev)
+        ops.rollout(*args, solver="dopri5", precision=PRECISION, device=dev)
         torch.cuda.synchronize()
         n = L.hode_debug_timeline(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), 16384)
     ev = buf[: 2 * n].reshape(n, 2)
