@@ -178,9 +178,24 @@ __device__ __forceinline__ void rhs_mech_fast(const Theta& p, const float* y, fl
   d[4] = 0.0f;
 }
 
+// the 19 floats stage_theta() wrote: no powf here
+__device__ __forceinline__ Theta load_theta_staged(const float* __restrict__ th) {
+  Theta p;
+  p.a_GI = th[0]; p.k_I = th[1]; p.rho = th[2]; p.G_b = th[3]; p.I_b = th[4];
+  p.E_max = th[5]; p.EC_50 = th[6]; p.Glu_b = th[7]; p.V_max = th[8]; p.K_m = th[9];
+  p.k_L = th[10]; p.k_GE0 = th[11]; p.IGD_50 = th[12]; p.g = th[13];
+  p.p_7 = th[14]; p.p_8 = th[15]; p.p_9 = th[16];
+  p.igd_pow = th[17];
+  p.kge0 = th[18];
+  return p;
+}
+
 // One evaluation of f_physio + g_NN for this lane (tile-collective).
+// th_sm: the parameter set's 19 floats (17 parameters, IGD_50^g, k_GE at GD = 0) in shared memory; th_row: this
+// trajectory's own 17 parameters in global memory (theta_per_traj mode) or nullptr.  The parameters are fetched
+// where they are used, behind the layer-0 MMAs, instead of living in 19 registers across the whole evaluation.
 template <int X3>
-__device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln, double te,
+__device__ __forceinline__ void lane_eval(TileCtx& c, const float* th_sm, const float* th_row, Lane& ln, double te,
                                           const float* ys, float* d) {
   const float t32 = (float)te;
   float meal = 0.f, tvns = 0.f, gd = 0.f;
@@ -206,7 +221,10 @@ __device__ __forceinline__ void lane_eval(TileCtx& c, const Theta& th, Lane& ln,
   x[7] = ys[3];
   x[8] = tvns;
   __syncwarp();
-  mlp_tile<X3>(c, x, r, [&] { rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d); });
+  mlp_tile<X3>(c, x, r, [&] {
+    const Theta th = th_row ? load_theta(th_row) : load_theta_staged(th_sm);
+    rhs_mech_fast(th, ys, meal, gd, ln.in.mode[HODE_CH_GD] != HODE_IN_ABSENT, d);
+  });
 #pragma unroll
   for (int i = 0; i < NS; ++i) d[i] = __fadd_rn(d[i], r[i]);
 }
@@ -324,6 +342,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   __shared__ uint32_t tmem_base_s;
   __shared__ int tile_active[NT][4];
   __shared__ int cta_queue;   // fused posterior-predictive mode: next trajectory of this CTA's range
+  __shared__ float th_sm[20];  // the current parameter set's mechanistic parameters + derived values
 
   const int tid = threadIdx.x, lane_id = tid & 31;
   // warp-uniform by construction; the shuffle lets ptxas keep everything derived from it
@@ -427,7 +446,14 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       }
       tc::mbar_wait(&load_bar, load_parity);
       load_parity ^= 1u;
-      Theta th = load_theta(A.theta + (size_t)s * HODE_N_THETA);   // (reloaded per trajectory in theta_per_traj mode)
+      if (tid == 0 && !A.theta_per_traj) {   // (the previous set's readers are behind the barriers above)
+        const Theta th0 = load_theta(A.theta + (size_t)s * HODE_N_THETA);
+#pragma unroll
+        for (int i = 0; i < HODE_N_THETA; ++i) th_sm[i] = A.theta[(size_t)s * HODE_N_THETA + i];
+        th_sm[17] = th0.igd_pow;
+        th_sm[18] = th0.kge0;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(15), "r"(NMAIN) : "memory");   // main threads only: th_sm is staged
 
       Lane ln;
       ln.has = false;
@@ -485,7 +511,6 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             if (want) {
               if (b < b_hi) {
                 if (A.order) b = (long)A.order[b];   // launch order hint: queue position -> trajectory
-                if (A.theta_per_traj) th = load_theta(A.theta + (size_t)b * HODE_N_THETA);
                 lane_bind(ln, A, t_shared, s, b);
                 ln.t = (double)ln.in.t_obs[0];
                 t_bound = (double)ln.in.t_obs[T - 1];
@@ -528,9 +553,15 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         bool run = ln.has && !init;   // lane performs a real step / attempt this round
         double t = ln.t, h = 0.0, t_new = ln.t, h0 = 0.0;
         float hf = 0.f, h0f = 0.f, d1 = 0.f;
-        float sc[NS], ynew[NS], incr[NS];
+        // y_new = y + h sum b_j k_j of a DP5(4) attempt, from the stage store (evaluated twice with the same operands:
+        // as the input of the 7th stage and again when the round is closed, instead of 12 registers held across it)
+        auto dp_increment = [&](float* incr, float* ynew) {
   #pragma unroll
-        for (int i = 0; i < NS; ++i) { sc[i] = 1.f; ynew[i] = ln.y[i]; incr[i] = 0.f; }
+          for (int i = 0; i < NS; ++i) {
+            incr[i] = hf * fmaf(dp::b6, KS(5, i), fmaf(dp::b5, KS(4, i), fmaf(dp::b4, KS(3, i), fmaf(dp::b3, KS(2, i), dp::b1 * KS(0, i)))));
+            ynew[i] = ln.y[i] + (incr[i] - ln.cmp[i]);
+          }
+        };
         if (SOLVER == HODE_SOLVER_RK4) {
           if (run) {
             const double ta = (double)ln.in.t_obs[rk_n];
@@ -628,16 +659,12 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
                 ys[i] = fmaf(hf, fmaf(dp::a65, KS(4, i), fmaf(dp::a64, KS(3, i), fmaf(dp::a63, KS(2, i), fmaf(dp::a62, KS(1, i), dp::a61 * KS(0, i))))), ln.y[i]);
               te = t_new;
             } else {
-  #pragma unroll
-              for (int i = 0; i < NS; ++i) {
-                incr[i] = hf * fmaf(dp::b6, KS(5, i), fmaf(dp::b5, KS(4, i), fmaf(dp::b4, KS(3, i), fmaf(dp::b3, KS(2, i), dp::b1 * KS(0, i)))));
-                ynew[i] = ln.y[i] + (incr[i] - ln.cmp[i]);
-                ys[i] = ynew[i];
-              }
+              float incr[NS];
+              dp_increment(incr, ys);
               te = t_new;
             }
           }
-          lane_eval<X3>(c, th, ln, te, ys, d);
+          lane_eval<X3>(c, th_sm, A.theta_per_traj ? A.theta + (size_t)ln.b * HODE_N_THETA : nullptr, ln, te, ys, d);
           if (SOLVER == HODE_SOLVER_RK4) {
   #pragma unroll
             for (int i = 0; i < NS; ++i) KS(slot, i) = d[i];
@@ -655,9 +682,9 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               float v0[NS], v1[NS];
   #pragma unroll
               for (int i = 0; i < NS; ++i) {
-                sc[i] = atol + fabsf(ln.y[i]) * rtol;
-                v0[i] = ln.y[i] / sc[i];
-                v1[i] = d[i] / sc[i];
+                const float sc = atol + fabsf(ln.y[i]) * rtol;
+                v0[i] = ln.y[i] / sc;
+                v1[i] = d[i] / sc;
               }
               const float d0 = rms6v(v0);
               d1 = rms6v(v1);
@@ -670,7 +697,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               if (interval > 0) {
                 float v0[NS];
   #pragma unroll
-                for (int i = 0; i < NS; ++i) v0[i] = (d[i] - KS(0, i)) / sc[i];
+                for (int i = 0; i < NS; ++i) v0[i] = (d[i] - KS(0, i)) / (atol + fabsf(ln.y[i]) * rtol);
                 const float d2 = rms6v(v0) / h0f;
                 double h1;
                 if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmax(1e-6, h0 * 1e-3);
@@ -718,6 +745,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         } else if (ln.has && !run) {
           lane_finish(ln, A, vi_n);                         // step too small / budget exhausted
         } else if (run) {
+          float ynew[NS], incr[NS];
+          dp_increment(incr, ynew);
           float e2 = 0.f;
           bool finite = true;
   #pragma unroll

@@ -244,15 +244,31 @@ __device__ __forceinline__ void epilogue16(uint32_t* v, uint32_t* lo, uint32_t* 
     }
   }
 }
-// MLP_MIX3: v -> TF32 hi bits in place, lb = bf16 pairs of the remainder (8 columns); no other copies
+// MLP_MIX3: v -> a = relu(v) in place — the tensor core reads the upper 19 bits of a kind::tf32 operand, i.e. it
+// truncates a to A_hi by itself — and lb = bf16 pairs of the remainder a - trunc(a) (8 columns).  3 instructions per
+// column: FMNMX, LOP3, half a packed FADD2 (sm_100 f32x2), half a F2FP.  Truncation instead of rounding makes the
+// remainder at most 2^-10 |a| instead of 2^-11 |a|; its BF16 rounding error (2^-19 |a|) stays far below the 1e-5
+// parity bar (tools/tc_mode_errors.py: 1.0e-6 against the oracle, the same as 3xTF32).
 __device__ __forceinline__ void epilogue16_mix3(uint32_t* v, uint32_t* lb) {
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     const float a0 = fmaxf(__uint_as_float(v[j]), 0.f), a1 = fmaxf(__uint_as_float(v[j + 1]), 0.f);
+#ifdef HODE_MIX3_TRUNC
+    const uint32_t h0 = __float_as_uint(a0) & 0xFFFFE000u, h1 = __float_as_uint(a1) & 0xFFFFE000u;
+    v[j] = __float_as_uint(a0);
+    v[j + 1] = __float_as_uint(a1);
+#else
     const uint32_t h0 = (__float_as_uint(a0) + 0x1000u) & 0xFFFFE000u, h1 = (__float_as_uint(a1) + 0x1000u) & 0xFFFFE000u;
     v[j] = h0;
     v[j + 1] = h1;
-    lb[j >> 1] = pack_bf16x2(a0 - __uint_as_float(h0), a1 - __uint_as_float(h1));
+#endif
+    uint64_t ap, hp, lp;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ap) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(hp) : "r"(h0), "r"(h1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(lp) : "l"(ap), "l"(hp));
+    float l0, l1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(l0), "=f"(l1) : "l"(lp));
+    lb[j >> 1] = pack_bf16x2(l0, l1);
   }
 }
 // The hidden-layer epilogue of one MLP_MIX3 thread (no helper warps): all 64 accumulator columns of its lane.
