@@ -50,8 +50,13 @@ constexpr int N_KSTAGE = 7 * NS;   // floats of the stage-derivative store per t
 // bias, then zero padding.  The other layers get a bias block: one K = 8 TF32 step whose columns 0/1 hold the
 // TF32 hi/lo parts of the bias; it multiplies a constant A block [1, 1, 0, ...] kept in TMEM, so the bias rides
 // on the tensor pipe instead of costing one FADD per accumulator element in the epilogue.
+int tc_image_floats_mode(int L, int mlp_mode);
 int tc_image_floats(int L) { return 2 * 1024 + (L - 1) * 2 * 4096 + 2 * 1024 + L * 512 + 128; }
 // MLP_MIX3 image: [B_hi tf32][B_lo tf32][bf16(B_hi)] per layer
+static int tc_image_floats_max(int L) {   // the workspace layout does not depend on the mode
+  const int a = tc_image_floats(L), b = tc_image_floats_mode(L, HODE_MLP_TF32X2BF16);
+  return a > b ? a : b;
+}
 int tc_image_floats_mode(int L, int mlp_mode) {
   if (mlp_mode != HODE_MLP_TF32X2BF16) return tc_image_floats(L);
   return (int)(img_l0<MLP_MIX3>() + (uint32_t)(L - 1) * img_hid<MLP_MIX3>() + img_out<MLP_MIX3>()) + L * 512 + 128;
@@ -188,6 +193,13 @@ __device__ __forceinline__ Theta load_theta_staged(const float* __restrict__ th)
   p.igd_pow = th[17];
   p.kge0 = th[18];
   return p;
+}
+
+// nextafter(t, +inf) - t for a finite t (SciPy's min_step = 10 ulp, rk.py:121), by stepping the bit pattern
+__device__ __forceinline__ double ulp_above(double t) {
+  if (t == 0.0) return 4.9406564584124654e-324;
+  const long long b = __double_as_longlong(t);
+  return __longlong_as_double(t > 0.0 ? b + 1 : b - 1) - t;
 }
 
 // One evaluation of f_physio + g_NN for this lane (tile-collective).
@@ -604,7 +616,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             }
             need_stop = false;
           }
-          const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+          const double min_step = 10.0 * ulp_above(t);
           if (!prev_rejected && h_abs < min_step) h_abs = min_step;
           if (h_abs < min_step) { ln.status = HODE_ST_STEP_TOO_SMALL; run = false; }
           else if (attempts >= max_steps) { ln.status = HODE_ST_MAX_STEPS; run = false; }
@@ -860,14 +872,14 @@ __global__ void kink_mask_kernel(const RolloutArgs A, unsigned long long* __rest
 }
 
 size_t tc_workspace_bytes(int S, int L, int B) {
-  return (size_t)S * tc_image_floats_mode(L, HODE_MLP_TF32X2BF16) * sizeof(float) + 256 + (((size_t)S * sizeof(int) + 255) & ~(size_t)255) +
+  return (size_t)S * tc_image_floats_max(L) * sizeof(float) + 256 + (((size_t)S * sizeof(int) + 255) & ~(size_t)255) +
          (size_t)B * sizeof(unsigned long long);
 }
 
 cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* workspace, cudaStream_t stream) {
   RolloutArgs A = A_in;
   const int img_floats = tc_image_floats_mode(A.L, mlp_mode);
-  const int max_img_floats = tc_image_floats_mode(A.L, HODE_MLP_TF32X2BF16);   // the workspace layout is mode-independent
+  const int max_img_floats = tc_image_floats_max(A.L);   // the workspace layout is mode-independent
   float* img = reinterpret_cast<float*>(workspace);
   int* queue = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
                                       (((size_t)A.S * max_img_floats * sizeof(float) + 255) / 256) * 256);

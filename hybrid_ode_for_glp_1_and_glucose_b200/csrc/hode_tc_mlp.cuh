@@ -59,6 +59,9 @@ constexpr uint32_t TM3_ALB = 128, TM3_TILE_STRIDE = 160, TM3_ONES_ABS = 480;
 constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
 template <int MODE> __host__ __device__ constexpr uint32_t img_l0() { return MODE == MLP_MIX3 ? 2560u : IMG_L0; }
 template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MODE == MLP_MIX3 ? 10240u : IMG_HID; }
+// (Measured dead end: the 64 -> 6 output layer of MLP_MIX3 on the CUDA cores — 384 FFMA per thread straight from the last
+// hidden accumulator, no N = 16 MMAs and one issue -> commit -> wake-up phase less — was 6 % SLOWER, 968 M against
+// 1 034 M trajectory-steps/s: the tile's chain is bound by its threads' instruction latency, not by the tensor phases.)
 template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : IMG_OUT; }
 
 // Activation stash of the adjoint (one block per hidden layer, per CTA): the tile's
@@ -273,31 +276,27 @@ __device__ __forceinline__ void epilogue16_mix3(uint32_t* v, uint32_t* lb) {
 }
 // The hidden-layer epilogue of one MLP_MIX3 thread (no helper warps): all 64 accumulator columns of its lane.
 __device__ __forceinline__ void epilogue64_mix3(uint32_t t_lane) {
-#ifdef HODE_EPI64_WIDE
-  uint32_t v[32], w[32], lb[16];
-  HODE_TMEM_LD_X32(t_lane + TM_D0, v);
-  HODE_TMEM_LD_X32(t_lane + TM_D0 + 32, w);
+  // four 16-column chunks, software-pipelined: tcgen05.wait::ld drains every outstanding load, so the loads of the
+  // next two chunks are issued before the arithmetic of the current ones and their latency hides behind it
+  uint32_t c0[16], c1[16], c2[16], c3[16], lb[8];
+  HODE_TMEM_LD_X16(t_lane + TM_D0, c0);
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + 16, c1);
   tc::wait_ld();
-  epilogue16_mix3(v, lb);
-  epilogue16_mix3(v + 16, lb + 8);
-  HODE_TMEM_ST_X32(t_lane + TM_AHI, v);
-  HODE_TMEM_ST_X16(t_lane + TM3_ALB, lb);
-  epilogue16_mix3(w, lb);
-  epilogue16_mix3(w + 16, lb + 8);
-  HODE_TMEM_ST_X32(t_lane + TM_AHI + 32, w);
-  HODE_TMEM_ST_X16(t_lane + TM3_ALB + 16, lb);
-#else
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t v[32], lb[16];
-    HODE_TMEM_LD_X32(t_lane + TM_D0 + 32 * half, v);
-    tc::wait_ld();
-    epilogue16_mix3(v, lb);
-    epilogue16_mix3(v + 16, lb + 8);
-    HODE_TMEM_ST_X32(t_lane + TM_AHI + 32 * half, v);
-    HODE_TMEM_ST_X16(t_lane + TM3_ALB + 16 * half, lb);
-  }
-#endif
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + 32, c2);
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + 48, c3);
+  epilogue16_mix3(c0, lb);
+  HODE_TMEM_ST_X16(t_lane + TM_AHI, c0);
+  HODE_TMEM_ST_X8(t_lane + TM3_ALB, lb);
+  epilogue16_mix3(c1, lb);
+  HODE_TMEM_ST_X16(t_lane + TM_AHI + 16, c1);
+  HODE_TMEM_ST_X8(t_lane + TM3_ALB + 8, lb);
+  tc::wait_ld();
+  epilogue16_mix3(c2, lb);
+  HODE_TMEM_ST_X16(t_lane + TM_AHI + 32, c2);
+  HODE_TMEM_ST_X8(t_lane + TM3_ALB + 16, lb);
+  epilogue16_mix3(c3, lb);
+  HODE_TMEM_ST_X16(t_lane + TM_AHI + 48, c3);
+  HODE_TMEM_ST_X8(t_lane + TM3_ALB + 24, lb);
   tc::wait_st();
   tc::fence_before_sync();
 }
