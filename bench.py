@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="hybrid_fwd",
                     choices=["hybrid_fwd", "hybrid_fwdbwd", "vi_predictive", "mech_rk4"])
     ap.add_argument("--traj-per-gpu", type=int, default=0)
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "tf32bf16", "tf32x2bf16"])
+    ap.add_argument("--precision", default="tf32x2bf16", choices=["fp32", "tf32x3", "tf32", "tf32bf16", "tf32x2bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs of the default run")
     return ap.parse_args()

@@ -202,6 +202,16 @@ __device__ __forceinline__ double ulp_above(double t) {
   return __longlong_as_double(t > 0.0 ? b + 1 : b - 1) - t;
 }
 
+// barrier + OR-reduction of a predicate over the n threads of named barrier `bar` in one instruction
+__device__ __forceinline__ bool tile_or(int bar, int n, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
+      "bar.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "r"(bar), "r"(n), "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
+
 // One evaluation of f_physio + g_NN for this lane (tile-collective).
 // th_sm: the parameter set's 19 floats (17 parameters, IGD_50^g, k_GE at GD = 0) in shared memory; th_row: this
 // trajectory's own 17 parameters in global memory (theta_per_traj mode) or nullptr.  The parameters are fetched
@@ -352,7 +362,6 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   __shared__ __align__(8) uint64_t mma_bar[NT];
   __shared__ __align__(8) uint64_t load_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ int tile_active[NT][4];
   __shared__ int cta_queue;   // fused posterior-predictive mode: next trajectory of this CTA's range
   __shared__ float th_sm[20];  // the current parameter set's mechanistic parameters + derived values
 
@@ -399,7 +408,6 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
     tc::wait_st();
   }
   // all barriers of a MLP_MIX3 tile are over its 128 main threads
-  auto tile_sync = [&] { if (HELP) tile_sync_all(c); else tile_sync_main(c); };
   float* const kp = k_sm + (tid < NMAIN ? tid : 0);
 #define KS(j, i) kp[((j) * NS + (i)) * NMAIN]
 
@@ -433,11 +441,7 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
       load_parity ^= 1u;
       // mirror of the main warps' round structure: same tile-wide barriers, NSLOT MLP calls per round
       for (;;) {
-        tile_sync_all(c);
-        const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
-                        tile_active[tile][3];
-        tile_sync_all(c);
-        if (!go) break;
+        if (!tile_or(c.bar_all, 2 * TILE, false)) break;
 #pragma unroll 1
         for (int slot = 0; slot < NSLOT; ++slot) mlp_tile_helper<X3>(c);
       }
@@ -548,16 +552,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         }
         HODE_TL(101);
         // ---- does this tile still have work? ------------------------------------------------------
-        {
-          // a lane without a trajectory that has not yet seen the end of the queue may still be served
-        const bool any = __any_sync(0xffffffffu, ln.has || !queue_dry);
-          if (lane_id == 0) tile_active[tile][wq] = any ? 1 : 0;
-          tile_sync();
-          const bool go = tile_active[tile][0] | tile_active[tile][1] | tile_active[tile][2] |
-                          tile_active[tile][3];
-          tile_sync();
-          if (!go) break;
-        }
+        // (a lane without a trajectory that has not yet seen the end of the queue may still be served)
+        if (!tile_or(HELP ? c.bar_all : c.bar_id, HELP ? 2 * TILE : TILE, ln.has || !queue_dry)) break;
 
         HODE_TL(102);
         // ---- round set-up ---------------------------------------------------------------------------
@@ -587,17 +583,20 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
         } else if (run) {
           if (need_stop) {
             t_stop = t_bound;
+            // the grid is float32 and t is float64: f > t  <=>  f > rd(t), the largest float <= t, so the searches
+            // below compare in float32 (the FP64 pipe is narrow, and these loops run every accepted step)
+            const float t_rd = __double2float_rd(t);
             if (clip && any_series(ln.in)) {
               if (T <= 64) {
                 unsigned long long m = kink_mask & ~((1ull << kink_cur) - 1ull);
                 while (m) {
                   const int i = __ffsll((long long)m) - 1;
-                  if ((double)ln.in.t_obs[i] > t) { t_stop = (double)ln.in.t_obs[i]; kink_cur = i; break; }
+                  if (ln.in.t_obs[i] > t_rd) { t_stop = (double)ln.in.t_obs[i]; kink_cur = i; break; }
                   m &= m - 1ull;
                   kink_cur = i + 1;
                 }
               } else {
-                while (kink_cur < T - 1 && !((double)ln.in.t_obs[kink_cur] > t && is_kink(ln.in, kink_cur)))
+                while (kink_cur < T - 1 && !(ln.in.t_obs[kink_cur] > t_rd && is_kink(ln.in, kink_cur)))
                   ++kink_cur;
                 if (kink_cur < T - 1) t_stop = (double)ln.in.t_obs[kink_cur];
               }
@@ -787,14 +786,18 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
               } else { ln.status = HODE_ST_REC_OVERFLOW; ok = false; }
             }
             if (ok) {
-              if (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
+              // f <= t_new  <=>  f <= rd(t_new);  f == t_new  <=>  t_new is a float and f == rd(t_new)
+              const float tn_rd = __double2float_rd(t_new);
+              const bool tn_is_float = (double)tn_rd == t_new;
+              if (ln.ei < T && ln.in.t_obs[ln.ei] <= tn_rd) {
                 float Q[NS][4];
   #pragma unroll
                 for (int i = 0; i < NS; ++i) dp::dense_q(KS(0, i), KS(2, i), KS(3, i), KS(4, i), KS(5, i), KS(6, i), Q[i]);
-                while (ln.ei < T && (double)ln.in.t_obs[ln.ei] <= t_new) {
-                  const double te = (double)ln.in.t_obs[ln.ei];
+                while (ln.ei < T && ln.in.t_obs[ln.ei] <= tn_rd) {
+                  const float tef = ln.in.t_obs[ln.ei];
+                  const double te = (double)tef;
                   float yo[NS];
-                  if (te == t_new) {
+                  if (tn_is_float && tef == tn_rd) {
   #pragma unroll
                     for (int i = 0; i < NS; ++i) yo[i] = ynew[i];
                   } else {

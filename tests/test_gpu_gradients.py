@@ -261,11 +261,13 @@ def test_differentiable_forward_trains_the_data_term(dev):
 
 
 # ---------------------------------------------------------------------------- tensor-core adjoint
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32x2bf16"])
 @pytest.mark.parametrize("solver,layers", [("rk4", 4), ("dopri5", 4), ("rk4", 2), ("dopri5", 1)])
-def test_tensor_core_adjoint_matches_autograd(dev, solver, layers):
-    """precision='tf32x3' routes hode_rollout_bwd to the tcgen05 adjoint (hode_adjoint_tc.cu)."""
+def test_tensor_core_adjoint_matches_autograd(dev, solver, layers, precision):
+    """The tensor-core precisions route hode_rollout_bwd to the tcgen05 adjoint (hode_adjoint_tc.cu); a rollout made
+    in the three-tile mode ('tf32x2bf16', the default) hands its step records to the same 3xTF32 adjoint."""
     kw = dict(n_substeps=2) if solver == "rk4" else {}
-    errs = _adjoint_case(dev, 6, 11, 64, layers, solver, seed=21 + layers, precision="tf32x3", **kw)
+    errs = _adjoint_case(dev, 6, 11, 64, layers, solver, seed=21 + layers, precision=precision, **kw)
     assert max(errs) < TOL, errs
 
 

@@ -25,7 +25,8 @@ def _sets(S, seed=0, spread=0.02):
 
 
 @pytest.mark.parametrize("precision,solver,B", [("fp32", "dopri5", 300), ("tf32x3", "dopri5", 700),
-                                                ("fp32", "rk4", 130), ("tf32x3", "rk4", 300)])
+                                                ("fp32", "rk4", 130), ("tf32x3", "rk4", 300),
+                                                ("tf32x2bf16", "dopri5", 900), ("tf32x2bf16", "rk4", 300)])
 def test_fused_mean_std_equals_stack_statistics(dev, precision, solver, B):
     from hybrid_ode_for_glp_1_and_glucose_b200 import ops
     S, T = 7, 21
