@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--precision", default="tf32x2bf16", choices=["fp32", "tf32x3", "tf32", "tf32bf16", "tf32x2bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs of the default run")
+    ap.add_argument("--arrival-order", action="store_true",
+                    help="time every pass in arrival order (no launch-order hint from the previous pass)")
     return ap.parse_args()
 
 
@@ -329,9 +331,27 @@ def run_ours(args):
             return traj, info
         return step
 
+    def adaptive(make_step, c, *a):
+        """A pass over a cohort that was integrated before hands its trajectories to the kernel longest first, in the
+        order of the PREVIOUS pass's attempt counters (ops.launch_order: a device-side argsort, inside the timed step).
+        Training and posterior sweeps re-integrate the same cohort every epoch / sample (reference
+        train/train_hybrid.py:225-275); at 4.6 trajectories per lane the arrival-order schedule of the persistent
+        kernel ends 30 % above its ideal makespan, the longest-first one 6 %.  The first pass of a
+        cohort has no counters and runs in arrival order (leg fwd_first_pass)."""
+        state = {"order": None}
+
+        def step():
+            out = make_step(c, *a, order=state["order"])()
+            state["order"] = ops.launch_order(out[1])
+            return out
+        return step
+
     def vi_step(c, thS, WS):
         return lambda: ops.vi_predictive(c.y0, c.t, c.ins, thS, WS, **c.kw)
 
+    KMODE = {"tf32x3": "x3", "tf32x2bf16": "mix3", "tf32bf16": "mixed", "tf32": "tf32", "fp32": "fp32"}[args.precision]
+    LAUNCH_ORDER_TEXT = ("longest first by the PREVIOUS pass's attempt counters (ops.launch_order: device-side argsort inside the "
+                         "timed step); the first pass of a cohort runs in arrival order: roofline.legs.fwd_first_pass")
     peaks_box = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
     peaks_r2 = load_json(os.path.join(ROOT, "profiles", "r02_measured_peaks.json"))
     traffic_db = load_json(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))
@@ -341,7 +361,7 @@ def run_ours(args):
             "MEASURED cuBLAS TF32 dense, sustained (torch.matmul 8192^3 float32 with allow_tf32, back to back for 4 s; "
             f"burst {(peaks_r2['tf32']).get('burst_tflops', 0):.0f}): profiles/r02_measured_peaks.json, made by tools/measure_peaks.py "
             "on this pool's B200 the way MEASURED_PEAKS.json was made.  achieved counts ALGORITHMIC flops (158 976 + 700 per "
-            "attempt); the 3xTF32 split issues 3 tensor passes per algorithmic pass")
+            "attempt); the split-precision MLP issues tensor_passes_per_algorithmic_pass TF32-equivalent passes per algorithmic pass")
     else:
         tensor_peak = float(peaks_box.get("bf16_tflops_sustained", 1400.0)) / 2.0
         tensor_src = "fallback: MEASURED_PEAKS.json bf16_tflops_sustained / 2 (no measured TF32 figure found)"
@@ -356,6 +376,9 @@ def run_ours(args):
 
     c = Cohort(w, keep_host=True)
     bwd, vi = bool(w.get("bwd")), bool(w.get("vi"))
+    # adaptive launch order (see adaptive()): the tensor-core DP5(4) rollout only — fixed-step and FP32 launches are
+    # one-thread-per-trajectory grids without a queue
+    ADAPTIVE = bool(w["nn"]) and args.precision != "fp32" and w["solver"] != "rk4" and not vi and not args.arrival_order
     warm = max(args.warmup, 3)
     steps = args.steps
     if vi:
@@ -365,9 +388,9 @@ def run_ours(args):
         warm, steps = max(1, min(args.warmup, 1)), max(1, min(args.steps, 3))   # one step = 64 x 1 M rollouts (~seconds)
     elif bwd:
         d_g = torch.full((B, T, 6), 1.0 / (B * T * 6), dtype=torch.float32, device=dev)
-        step = fwdbwd_step(c, d_g)
+        step = adaptive(fwdbwd_step, c, d_g) if ADAPTIVE else fwdbwd_step(c, d_g)
     else:
-        step = fwd_step(c)
+        step = adaptive(fwd_step, c) if ADAPTIVE else fwd_step(c)
 
     # ---- headline: kernel-resident timing, inputs already in HBM, K steps, CUDA events ------------
     sampler = ClockSampler(local)
@@ -524,18 +547,42 @@ def run_ours(args):
     if not args.no_extra and args.workload == "hybrid_fwd" and not args.traj_per_gpu:
         # (1) forward + discrete adjoint on the same cohort, with the packed gradient all-reduce when N > 1
         d_g = torch.full((B, T, 6), 1.0 / (B * T * 6), dtype=torch.float32, device=dev)
-        ms, o2, n_l = timed(fwdbwd_step(c, d_g), min(args.steps, 5), 2)
+        ms, o2, n_l = timed(adaptive(fwdbwd_step, c, d_g) if ADAPTIVE else fwdbwd_step(c, d_g), min(args.steps, 5), 2)
         launches += n_l
         ms, att = reduce_max_sum(ms, attempts_of(o2[-1]))
         k2 = min(args.steps, 5)
-        leg = tensor_roof(att / world, ms / k2, 3.0, "rollout_tc_kernel<x3,dopri5> (steps recorded) + rollout_bwd_tc_kernel")
+        leg = tensor_roof(att / world, ms / k2, 3.0, "rollout_tc_kernel<" + KMODE + ",dopri5> (steps recorded) + rollout_bwd_tc_kernel")
         legs["fwd_bwd"] = {"value": att * k2 / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world, "scaling": "weak",
                            "trajectories_per_gpu": B, "ms_per_step": ms / k2, "steps": k2,
+                           "launch_order": LAUNCH_ORDER_TEXT if ADAPTIVE else "arrival",
                            "collective": "packed NCCL all-reduce of grad theta[17] + grad W[13510] + loss slot inside the timed region"
                                          if world > 1 else "none (single GPU)",
-                           "what": "hode_rollout_fwd (3xTF32, accepted steps + stage derivatives recorded) + hode_rollout_bwd "
+                           "what": "hode_rollout_fwd (" + args.precision + ", accepted steps + stage derivatives recorded) + hode_rollout_bwd "
                                    "(tcgen05 discrete adjoint: grad y0, theta[17], W[13510])",
                            "roofline": {k: leg[k] for k in ("achieved", "peak", "frac", "unit")}}
+        # (1b) the same passes WITHOUT the launch-order hint: what the first pass over a cohort costs, and (1c) with a
+        #      hint that is one optimiser step old: the counters come from a pass whose network weights differ by 1 %
+        if ADAPTIVE:
+            for name, fn, fac in (("fwd_first_pass", fwd_step(c), 1.0), ("fwd_bwd_first_pass", fwdbwd_step(c, d_g), 3.0)):
+                ms, o5, n_l = timed(fn, k2, 2)
+                launches += n_l
+                ms, att = reduce_max_sum(ms, attempts_of(o5[-1]))
+                legs[name] = {"value": att * k2 / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world, "scaling": "weak",
+                              "trajectories_per_gpu": B, "ms_per_step": ms / k2, "steps": k2, "launch_order": "arrival (no counters yet)",
+                              "frac": att / world * FLOP_ATTEMPT_HYBRID * fac / (ms / k2 * 1e-3) / 1e12 / tensor_peak}
+            g = torch.Generator(device=dev); g.manual_seed(7)
+            W_prev = c.W * (1.0 + 0.01 * torch.randn(c.W.shape, device=dev, generator=g))
+            stale = ops.launch_order(ops.rollout(c.y0, c.t, c.ins, c.theta, W_prev, **c.kw)[1])
+            ms, o6, n_l = timed(fwd_step(c, stale), k2, 2)
+            launches += n_l
+            ms, att = reduce_max_sum(ms, attempts_of(o6[-1]))
+            legs["fwd_order_one_update_old"] = {
+                "value": att * k2 / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world, "scaling": "weak",
+                "trajectories_per_gpu": B, "ms_per_step": ms / k2, "steps": k2,
+                "launch_order": "longest first by the counters of a pass with every network weight changed by 1 % (N(0, 0.01) relative): "
+                                "the hint a training epoch inherits from the previous one",
+                "frac": att / world * FLOP_ATTEMPT_HYBRID / (ms / k2 * 1e-3) / 1e12 / tensor_peak}
+            del W_prev, stale
         del d_g
         # (2) config 3 as BASELINE.json states it: 262 144 trajectories in total over the N GPUs (strong scaling);
         #     at N = 1 the real per-GPU shard of the 8-GPU job (32 768) is timed instead
@@ -570,7 +617,7 @@ def run_ours(args):
         n_fail = torch.tensor([float((info_v.status != 0).sum().item())], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(n_fail)
-        leg = tensor_roof(att / world, ms, 1.0, "rollout_tc_kernel<x3,dopri5> (fused Welford mean/std)")
+        leg = tensor_roof(att / world, ms, 1.0, "rollout_tc_kernel<" + KMODE + ",dopri5> (fused Welford mean/std)")
         legs["vi_predictive_64x1M"] = {
             "value": att / (ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": world, "scaling": "strong (1 048 576 trajectories per box)",
             "samples": VI_SAMPLES, "trajectories_per_gpu": wv["B"], "trajectories_total": wv["B"] * world, "ms_per_step": ms, "steps": 1,
@@ -635,8 +682,8 @@ def run_ours(args):
         n_in = len(w["ins"])
         alg_bytes = B * BYTES_PER_TRAJ(T, n_in, False)
         if w["nn"] and args.precision != "fp32":
-            kname = ("rollout_tc_kernel<x3,dopri5> (fused Welford mean/std)" if vi else
-                     "rollout_tc_kernel<x3,dopri5>" + (" + rollout_bwd_tc_kernel" if bwd else ""))
+            kname = ("rollout_tc_kernel<" + KMODE + ",dopri5> (fused Welford mean/std)" if vi else
+                     "rollout_tc_kernel<" + KMODE + ",dopri5>" + (" + rollout_bwd_tc_kernel" if bwd else ""))
             passes = {"tf32x3": 3, "tf32bf16": 2, "tf32x2bf16": 2.5, "tf32": 1}[args.precision]
             roof = tensor_roof(attempts_per_step, ms_step, 3.0 if bwd else 1.0, kname, passes)
             roof["peak_source"] = tensor_src
@@ -677,6 +724,7 @@ def run_ours(args):
             "config": {"workload": w["name"], "mlp_arithmetic": args.precision if w["nn"] else "none",
                        "trajectories_per_gpu": B, "trajectories_total": B * world,
                        "attempts_per_trajectory": attempts_per_step / B / (VI_SAMPLES if vi else 1),
+                       "launch_order": LAUNCH_ORDER_TEXT if ADAPTIVE else "arrival (one launch per pass, no queue hint)",
                        "l2_policy": "inputs+outputs per step exceed L2 (no flush needed): "
                                     f"{alg_bytes / 2**20:.0f} MiB"},
             "clocks": clocks,

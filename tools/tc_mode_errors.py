@@ -47,3 +47,13 @@ for m in modes:
     ms = e0.elapsed_time(e1) / 5
     att = int(info.n_attempts.sum())
     print(f"dopri5 262144 traj: {m:11s} {ms:8.3f} ms  {att / ms / 1e3:8.1f} M trajectory-steps/s")
+    order = ops.launch_order(info)
+    for _ in range(2):
+        ops.rollout(*args, solver="dopri5", precision=m, device=dev, order=order)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        ops.rollout(*args, solver="dopri5", precision=m, device=dev, order=order)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"   ... longest first (previous pass's attempt counts): {ms:8.3f} ms  {att / ms / 1e3:8.1f} M trajectory-steps/s")

@@ -29,10 +29,13 @@ try:
     L = _lib.lib()
     L.hode_debug_timeline.restype = ctypes.c_int
     buf = np.zeros(2 * 16384, dtype=np.int64)
+    order = None
     for it in range(2):
-        ops.rollout(*args, solver="dopri5", precision=PRECISION, device=dev)
+        _, info = ops.rollout(*args, solver="dopri5", precision=PRECISION, device=dev, order=order)
         torch.cuda.synchronize()
         n = L.hode_debug_timeline(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), 16384)
+        if os.environ.get("TL_ORDER"):
+            order = ops.launch_order(info)   # second pass: longest first
     ev = buf[: 2 * n].reshape(n, 2)
     ids, clk = ev[:, 0], ev[:, 1]
     # skip the first 20 % (start-up), analyse deltas between consecutive events
