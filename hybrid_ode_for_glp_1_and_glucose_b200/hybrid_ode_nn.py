@@ -66,6 +66,15 @@ class HybridODENN(nn.Module):
         # adjoint, hode_rollout_bwd) to initial_state, the ODE parameters and the network.
         self.differentiable = False
         self.last_info: Optional[ops.RolloutInfo] = None
+        # Adaptive launch order: a batch this module integrated in its previous forward() (same initial_state tensor,
+        # unchanged since) is handed to the persistent tensor-core kernel longest first, by that pass's attempt
+        # counters — repeated sweeps and epochs over one cohort lose the scheduling tail of the first pass (bench.py:
+        # 1.38 G against 1.02 G trajectory-steps/s at 262 144 trajectories).  The order is a permutation hint only:
+        # every trajectory's result is independent of it, bit for bit.
+        self.adaptive_order = True
+        self.adaptive_order_min_batch = 8192
+        self._order_key = None
+        self._order = None
         if use_variational:
             self._setup_variational_inference(prior_params)
         else:
@@ -152,6 +161,14 @@ class HybridODENN(nn.Module):
                     kinks=kernel_opts.get("kinks", self.kinks),
                     precision=kernel_opts.get("precision", self.precision),
                     max_steps=kernel_opts.get("max_steps", 0))
+        order_key = None
+        if (self.adaptive_order and "order" not in kernel_opts and y0.shape[0] >= self.adaptive_order_min_batch
+                and ops.SOLVERS.get(str(solver).lower()) == ops._lib.SOLVER_DOPRI5):
+            order_key = (y0.data_ptr(), tuple(y0.shape), y0._version, t_span.data_ptr(), tuple(t_span.shape))
+            if order_key == self._order_key:
+                opts["order"] = self._order
+        elif "order" in kernel_opts:
+            opts["order"] = kernel_opts["order"]
         if kernel_opts.get("differentiable", self.differentiable) and torch.is_grad_enabled():
             opts["max_saved_steps"] = kernel_opts.get("max_saved_steps", 0)
             traj, info = autograd_ops.rollout(y0.to(dev), t_span, external_inputs, theta.to(dev),
@@ -160,6 +177,8 @@ class HybridODENN(nn.Module):
             traj, info = ops.rollout(y0, t_span, external_inputs, theta.to(dev),
                                      None if W is None else W.to(dev), device=dev, **opts)
         self.last_info = info
+        if order_key is not None:
+            self._order_key, self._order = order_key, ops.launch_order(info)
         if kernel_opts.get("check_status", self.check_status):
             self._warn_failures(info)
         return traj.squeeze(0) if squeeze else traj

@@ -554,3 +554,35 @@ def test_dop853_clip_mode_sweep_and_unsupported_combinations(dev, oracle):
         ops.rollout(torch.from_numpy(y0), torch.from_numpy(t), {k: torch.from_numpy(v) for k, v in ins.items()},
                     torch.from_numpy(oracle.THETA_DEFAULT), torch.from_numpy(W), device=dev, solver="dop853",
                     save_steps=True)
+
+
+def test_adaptive_launch_order_is_a_pure_scheduling_hint(dev):
+    """HybridODENN.forward() re-integrating the batch of its previous call hands the trajectories out longest first
+    (the previous pass's attempt counters); results and counters are bit-identical to the first pass, a changed
+    initial_state tensor drops the hint, and a stale or arbitrary permutation changes nothing either."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN, ops
+    B = 9000
+    y0, t, ins = cohort(B, seed=77)
+    m = HybridODENN(device=dev)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        for p in m.nn_residual.parameters():
+            p.copy_(0.05 * torch.randn_like(p))
+    d_y0, d_t = torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev)
+    tin = {k: torch.from_numpy(v).to(dev) for k, v in ins.items()}
+    a = m(d_y0, d_t, tin)
+    info_a = m.last_info
+    assert m._order is not None and m._order.shape == (B,)
+    att = (info_a.n_accept + info_a.n_reject)
+    assert bool((att[m._order.long()][:-1] >= att[m._order.long()][1:]).all())       # longest first
+    assert torch.equal(torch.sort(m._order.long()).values, torch.arange(B, device=dev))
+    b = m(d_y0, d_t, tin)                                                             # second pass: ordered launch
+    assert torch.equal(a, b) and torch.equal(info_a.n_accept, m.last_info.n_accept)
+    c = m(d_y0, d_t, tin, order=torch.randperm(B, device=dev).to(torch.int32))         # any permutation: same results
+    assert torch.equal(a, c)
+    d_y0.mul_(1.0)                                                                    # in-place write: version bump
+    key_before = m._order_key
+    m(d_y0, d_t, tin)
+    assert m._order_key != key_before
+    m.adaptive_order = False
+    assert torch.equal(a, m(d_y0, d_t, tin))
