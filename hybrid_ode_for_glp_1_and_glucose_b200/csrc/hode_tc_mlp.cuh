@@ -63,6 +63,18 @@ template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MO
 // hidden accumulator, no N = 16 MMAs and one issue -> commit -> wake-up phase less — was 6 % SLOWER, 968 M against
 // 1 034 M trajectory-steps/s: the tile's chain is bound by its threads' instruction latency, not by the tensor phases.)
 template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : IMG_OUT; }
+// What bounds MLP_MIX3 (round 2 measurements, tools/probe_sched.py + tools/timeline.py on 1 / 2 / 3 resident tiles):
+// the DP5(4) round of a tile takes 34.3 us whether the tile is alone on its SM or not, and the issue of a hidden
+// layer's 21 N = 64 MMAs takes 861 cycles alone (41 per MMA: tcgen05.mma issue is paced by execution, 32.5 cycles,
+// plus ~8) and 1 040 with three tiles.  Per evaluation a tile holds the tensor pipe for 3 x 21 x 41 + 5 x 41 + 21 x 17
+// ~ 3.1 k cycles, three tiles for 9.3 k of the 11.2 k cycles an evaluation lasts: the pipe is 83 % occupied in issue
+// terms (ncu counts 62 % "active": the gaps between MMAs and the N = 16 output layer are not active cycles).
+// Two measured dead ends follow from that.  (1) A split pipeline — every layer's accumulator produced as two N = 32
+// halves and consumed as two K = 32 halves, the next layer's K-half-0 MMAs running under the second half of the
+// epilogue — doubles the MMA count at 24.5 cycles each, i.e. trades chain latency for tensor time one to one:
+// correct (rk4 parity 1.6e-6) and 5 % SLOWER (969 M against 1 020 M trajectory-steps/s), both with warp 0 issuing
+// between the halves of its own epilogue and (2) with a dedicated issuer warp per tile (a fourth warpgroup,
+// setmaxnreg 160 / 24, 314 bytes of spills).  What is left is the 17 % between the chain and the pipe.
 
 // Activation stash of the adjoint (one block per hidden layer, per CTA): the tile's
 // a_l = relu(z_l) as the BF16 operand image the weight-gradient MMAs read (csrc/probe/bf16_probe.cu),

@@ -127,6 +127,47 @@ def test_config4_sixty_four_identical_sets(dev):
     assert int(info2.n_accept.sum()) == S * int(info.n_accept.sum())
 
 
+def test_config4_at_size_against_a_strided_oracle_subsample(dev, oracle):
+    """BASELINE.json config 4 at its full size: 64 parameter sets x 1 048 576 trajectories (T = 61, dopri5 1e-6) through
+    the fused sweep in one call, checked on a strided subsample of 16 trajectories against (a) the explicit [S,16,T,6]
+    stack of plain rollouts on the device (mean / std the reference's way, inference/vi.py:306-310) and (b) the CPU
+    oracle's stack of the same 16 x 64 units."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+    B, T, S = 1 << 20, 61, 64
+    y0, t, ins = cohort(B, T, seed=21)
+    theta, W = _sets(S, seed=5)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_y0, d_t, d_ins, d_th, d_W = tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W)
+    mean, std, info = ops.vi_predictive(d_y0, d_t, d_ins, d_th, d_W, device=dev)
+    assert mean.shape == (B, T, 6) and std.shape == (B, T, 6)
+    # solver failures are per-unit status codes (their rows enter the statistics zero-padded, as the reference stacks
+    # them: test_fused_edge_cases); at this size a handful of the 67 M units may fail — they must stay a handful
+    n_fail = int((info.status != 0).sum())
+    assert n_fail <= 1e-5 * S * B, torch.bincount(info.status.reshape(-1), minlength=5).tolist()
+    attempts = int(info.n_accept.sum()) + int(info.n_reject.sum())
+    assert 30 * S * B < attempts < 60 * S * B   # the cohort's 43.5 attempts per trajectory, per set
+    assert bool(torch.isfinite(mean).all()) and bool(torch.isfinite(std).all())
+    ok_traj = torch.nonzero((info.status == 0).all(dim=0)).reshape(-1).cpu().numpy()
+    sub = ok_traj[np.searchsorted(ok_traj, np.arange(16) * (B // 16) + 4099)]   # strided, every set solved
+    s_ins = {k: v[sub] for k, v in ins.items()}
+    d_sub = torch.from_numpy(sub).to(dev)
+    # (a) the same units as plain rollouts: [S,16,T,6]
+    stack, sinfo = ops.rollout(tt(y0[sub]), d_t, {k: tt(v) for k, v in s_ins.items()}, d_th, d_W, device=dev)
+    assert torch.equal(sinfo.n_accept, info.n_accept[:, d_sub])
+    ref_mean, ref_std = stack.double().mean(dim=0), stack.double().std(dim=0)
+    scale = stack.abs().amax(dim=(0, 2), keepdim=True)[0].double() + 1e-30
+    assert float(((mean[d_sub].double() - ref_mean).abs() / scale).max()) < 1e-6
+    assert float(((std[d_sub].double() - ref_std).abs() / scale).max()) < 2e-6
+    # (b) the oracle's stack (float64 stepping around the float32 RHS, same kink clipping)
+    orc, ost, _, _ = oracle.rollout(y0[sub], t, s_ins, theta, W, kinks="clip", n_threads=8)
+    assert (ost == 0).all()
+    o_mean, o_std = orc.astype(np.float64).mean(axis=0), orc.astype(np.float64).std(axis=0, ddof=1)
+    o_scale = np.abs(orc).max(axis=(0, 2), keepdims=True)[0] + 1e-30
+    # adaptive solves of the same tolerance class: the two step sequences differ, the results agree far inside 1e-4
+    assert float((np.abs(mean[d_sub].cpu().numpy() - o_mean) / o_scale).max()) < 1e-4
+    assert float((np.abs(std[d_sub].cpu().numpy() - o_std) / o_scale).max()) < 1e-4
+
+
 def test_reparameterised_elbo_gradient_matches_float64_autograd(dev):
     """with reparam_gradient=True the likelihood term of the ELBO back-propagates
     through hode_rollout_bwd into the variational means and log-stds (psi = mu + eps sigma).  Checked
