@@ -12,7 +12,7 @@ from typing import Optional
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libhode.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 N_STATE, N_THETA, NN_IN = 6, 17, 9
 SOLVER_RK4, SOLVER_DOPRI5, SOLVER_DOP853 = 0, 1, 2
 IN_ABSENT, IN_CONST, IN_SERIES = 0, 1, 2
@@ -54,15 +54,17 @@ class HodeCfg(ctypes.Structure):
 class HodeFwdOpts(ctypes.Structure):
     """Mirror of `struct hode_fwd_opts` (include/hode.h)."""
     _fields_ = [("struct_bytes", ctypes.c_int32), ("theta_per_traj", ctypes.c_int32), ("order", ctypes.c_void_p),
-                ("out_state_mask", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("out_state_mask", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("prev_counters", ctypes.c_void_p)]
 
 
-def new_fwd_opts(theta_per_traj: bool = False, order_ptr: Optional[int] = None, out_state_mask: int = 0) -> HodeFwdOpts:
+def new_fwd_opts(theta_per_traj: bool = False, order_ptr: Optional[int] = None, out_state_mask: int = 0,
+                 prev_counters_ptr: Optional[int] = None) -> HodeFwdOpts:
     o = HodeFwdOpts()
     o.struct_bytes = ctypes.sizeof(HodeFwdOpts)
     o.theta_per_traj = 1 if theta_per_traj else 0
     o.order = order_ptr
     o.out_state_mask = int(out_state_mask)
+    o.prev_counters = prev_counters_ptr   # host entries only: HOST pointer to a previous call's [2,B] counters
     return o
 
 

@@ -9,6 +9,8 @@
 
 #include <atomic>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "hode_kernels.h"
 
 namespace hode {
@@ -529,6 +531,29 @@ void tune_default_pool() {
 // complete; this thread polls the flags and queues that block's copy on a second stream.
 constexpr int STREAM_BLOCK = 8192;
 constexpr int STREAM_MAX_BLOCKS = 1024;
+// ... and the host->device copy of the inputs overlapped the other way round: the kernel starts as soon as the first
+// IN_FIRST trajectories (more than one wave of lanes: 148 SMs x 384) are resident; the rest follows in blocks of
+// IN_BLOCK on a second copy stream, each block followed by a 4-byte copy that raises its ready flag in device memory;
+// a lane that draws a trajectory of a block still in flight waits for the flag (hode_rollout_tc.cu).  Every block's
+// copies run 8 rows into the next block: a 128-byte line that straddles a block boundary is then already complete
+// when an SM first caches it.
+constexpr int IN_FIRST = 65536;
+constexpr int IN_BLOCK = 32768;
+constexpr int IN_OVERLAP_ROWS = 8;
+
+// Launch-order hint of the host entry (opts.prev_counters): sort key of trajectory b = (its input block, descending
+// attempt count of the previous pass); a stable radix sort of (key, b) gives the order — longest first within blocks
+// of IN_BLOCK trajectories, blocks in index order, so that inputs can still arrive, and result blocks complete, block
+// by block.
+__global__ void order_keys_kernel(const int32_t* __restrict__ counters, int B, int block, uint32_t* __restrict__ keys,
+                                  int32_t* __restrict__ vals) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long att = (long)counters[b] + (long)counters[B + b];
+  att = att < 0 ? 0 : (att > 0xFFFFF ? 0xFFFFF : att);
+  keys[b] = ((uint32_t)(b / block) << 20) | (uint32_t)(0xFFFFF - att);
+  vals[b] = b;
+}
 
 int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0_h, const float* t_obs_h,
                               const float* const uh[3], const float* theta_h, const float* W_h,
@@ -548,19 +573,35 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, co
   const size_t o_y0 = carve(B * 24), o_t = carve((cfg->t_per_traj ? B * T : T) * 4);
   size_t o_u[3];
   for (int ch = 0; ch < 3; ++ch) o_u[ch] = carve(ub[ch]);
+  const bool gated = B >= (size_t)IN_FIRST + IN_BLOCK;   // inputs of trajectories >= IN_FIRST follow the kernel launch
+  const size_t n_first = gated ? (size_t)IN_FIRST : B;
+  const int n_in_blk = gated ? (int)((B - n_first + IN_BLOCK - 1) / IN_BLOCK) : 0;
   const size_t o_th = carve(n_theta * 17 * 4), o_W = carve(P * 4), o_traj = carve(B * T * nc * 4), o_st = carve(B * 4),
-               o_cn = carve(2 * B * 4), o_done = carve((size_t)n_blk * 4), o_ws = carve(wsp.total);
+               o_cn = carve(2 * B * 4), o_done = carve((size_t)n_blk * 4), o_ready = carve((size_t)(n_in_blk + 1) * 4),
+               o_ws = carve(wsp.total);
+  // launch-order hint: previous counters, sort keys / values (double-buffered) and cub's scratch
+  const int32_t* prev_h = opts ? opts->prev_counters : nullptr;
+  size_t sort_tmp = 0;
+  if (prev_h) cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                              (const int32_t*)nullptr, (int32_t*)nullptr, (int)B, 0, 32, st);
+  const size_t o_pc = carve(prev_h ? 2 * B * 4 : 0), o_k0 = carve(prev_h ? B * 4 : 0), o_k1 = carve(prev_h ? B * 4 : 0),
+               o_v0 = carve(prev_h ? B * 4 : 0), o_ord = carve(prev_h ? B * 4 : 0), o_tmp = carve(sort_tmp);
 
-  static thread_local int* flags_h = nullptr;     // host-mapped completion flags (allocated once)
-  static thread_local cudaStream_t copy_stream = nullptr;
+  static thread_local int* flags_h = nullptr;     // host-mapped completion flags (allocated once); [STREAM_MAX_BLOCKS] = 1
+  static thread_local cudaStream_t copy_stream = nullptr, in_stream = nullptr;
   cudaError_t e = cudaSuccess;
   if (!flags_h) {
-    e = cudaHostAlloc((void**)&flags_h, STREAM_MAX_BLOCKS * sizeof(int), cudaHostAllocMapped);
+    e = cudaHostAlloc((void**)&flags_h, (STREAM_MAX_BLOCKS + 1) * sizeof(int), cudaHostAllocMapped);
     if (e != cudaSuccess) { flags_h = nullptr; return cuda_fail(e, "cudaHostAlloc(flags)"); }
+    flags_h[STREAM_MAX_BLOCKS] = 1;   // source of the ready-flag copies
   }
   if (!copy_stream) {
     e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { copy_stream = nullptr; return cuda_fail(e, "cudaStreamCreate"); }
+  }
+  if (!in_stream) {
+    e = cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { in_stream = nullptr; return cuda_fail(e, "cudaStreamCreate"); }
   }
   int* flags_d = nullptr;
   e = cudaHostGetDevicePointer((void**)&flags_d, flags_h, 0);
@@ -572,14 +613,42 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, co
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
   int lib_rc = 0;
   int copied = 0;
+  cudaEvent_t ev_alloc = nullptr;
+  // per-trajectory inputs of rows [lo, hi) (+ the overlap) on stream `cs`
+  auto copy_rows = [&](size_t lo, size_t hi, cudaStream_t cs) -> cudaError_t {
+    const size_t hi2 = hi + IN_OVERLAP_ROWS < B ? hi + IN_OVERLAP_ROWS : B;
+    cudaError_t ce = cudaMemcpyAsync(d + o_y0 + lo * 24, y0_h + lo * 6, (hi2 - lo) * 24, cudaMemcpyHostToDevice, cs);
+    if (ce == cudaSuccess && cfg->t_per_traj)
+      ce = cudaMemcpyAsync(d + o_t + lo * T * 4, t_obs_h + lo * T, (hi2 - lo) * T * 4, cudaMemcpyHostToDevice, cs);
+    for (int ch = 0; ch < 3 && ce == cudaSuccess; ++ch) {
+      const size_t row = ub[ch] / B;   // bytes per trajectory of this channel (0: absent)
+      if (row) ce = cudaMemcpyAsync(d + o_u[ch] + lo * row, (const char*)uh[ch] + lo * row, (hi2 - lo) * row, cudaMemcpyHostToDevice, cs);
+    }
+    return ce;
+  };
 #define CK(call) if ((e = (call)) != cudaSuccess) goto done
-  CK(cudaMemcpyAsync(d + o_y0, y0_h, B * 24, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + o_t, t_obs_h, (cfg->t_per_traj ? B * T : T) * 4, cudaMemcpyHostToDevice, st));
-  for (int ch = 0; ch < 3; ++ch)
-    if (ub[ch]) CK(cudaMemcpyAsync(d + o_u[ch], uh[ch], ub[ch], cudaMemcpyHostToDevice, st));
+  if (prev_h) {   // first, so that the sort runs under the input copies that follow
+    CK(cudaMemcpyAsync(d + o_pc, prev_h, 2 * B * 4, cudaMemcpyHostToDevice, st));
+    hode::count_launch();
+    order_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>((const int32_t*)(d + o_pc), (int)B, IN_BLOCK,
+                                                                (uint32_t*)(d + o_k0), (int32_t*)(d + o_v0));
+    CK(cudaGetLastError());
+    CK(cub::DeviceRadixSort::SortPairs(d + o_tmp, sort_tmp, (const uint32_t*)(d + o_k0), (uint32_t*)(d + o_k1),
+                                       (const int32_t*)(d + o_v0), (int32_t*)(d + o_ord), (int)B, 0, 32, st));
+  }
+  CK(copy_rows(0, n_first, st));
+  if (!cfg->t_per_traj) CK(cudaMemcpyAsync(d + o_t, t_obs_h, T * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d + o_th, theta_h, n_theta * 17 * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d + o_W, W_h, P * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(d + o_done, 0, (size_t)n_blk * 4, st));
+  CK(cudaMemsetAsync(d + o_done, 0, (size_t)n_blk * 4 , st));
+  CK(cudaMemsetAsync(d + o_ready, 0, (size_t)(n_in_blk + 1) * 4, st));
+  if (gated) {
+    // the staging buffer is a stream-ordered allocation of `st`: the second copy stream may touch it (and the cleared
+    // flags) only behind this event
+    CK(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_alloc, st));
+    CK(cudaStreamWaitEvent(in_stream, ev_alloc, 0));
+  }
   {
     hode::RolloutArgs A = make_args(cfg, (float*)(d + o_y0), (float*)(d + o_t),
                                     ub[0] ? (float*)(d + o_u[0]) : nullptr, ub[1] ? (float*)(d + o_u[1]) : nullptr,
@@ -593,7 +662,19 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, co
     A.out_mask = mask;
     A.out_nc = mask ? (int)nc : 0;
     A.theta_per_traj = n_theta > 1 ? 1 : 0;
+    if (prev_h) A.order = (const int32_t*)(d + o_ord);
+    if (gated) {
+      A.in_ready = (const int*)(d + o_ready);
+      A.in_ready_first = (int)n_first;
+      A.in_ready_block = IN_BLOCK;
+    }
     CK(hode::launch_rollout_tc(A, cfg->mlp, d + o_ws + wsp.off_tc, st));
+  }
+  // the rest of the inputs, block by block, behind the running kernel
+  for (int k = 0; k < n_in_blk; ++k) {
+    const size_t lo = n_first + (size_t)k * IN_BLOCK, hi = lo + IN_BLOCK < B ? lo + IN_BLOCK : B;
+    CK(copy_rows(lo, hi, in_stream));
+    CK(cudaMemcpyAsync(d + o_ready + (size_t)k * 4, flags_h + STREAM_MAX_BLOCKS, 4, cudaMemcpyHostToDevice, in_stream));
   }
   // copy every block back as soon as the kernel reports it complete
   {
@@ -627,10 +708,12 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, co
 #undef CK
 done:
   {
+    cudaError_t e1 = cudaStreamSynchronize(in_stream);
     cudaError_t e2 = cudaStreamSynchronize(copy_stream);
     cudaError_t e3 = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
+    if (e == cudaSuccess) e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   }
+  if (ev_alloc) cudaEventDestroy(ev_alloc);
   cudaFreeAsync(d, st);
   cudaStreamSynchronize(st);
   if (lib_rc) return lib_rc;

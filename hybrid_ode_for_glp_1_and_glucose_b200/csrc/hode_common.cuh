@@ -66,6 +66,12 @@ struct RolloutArgs {
   int* done_count;
   volatile int* done_flag;
   int done_block;
+  // optional input gating for the streaming host entry (S == 1): the inputs of trajectories b >= in_ready_first are
+  // still on their way from the host when the kernel starts; block k = (b - in_ready_first) / in_ready_block may be
+  // bound to a lane once in_ready[k] != 0 (device memory, written by the copy stream right after that block's inputs)
+  const int* in_ready;
+  int in_ready_first;
+  int in_ready_block;
 };
 
 // ---- step records ---------------------------------------------------------------------------------------

@@ -550,6 +550,14 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
             if (want) {
               if (b < b_hi) {
                 if (A.order) b = (long)A.order[b];   // launch order hint: queue position -> trajectory
+                if (A.in_ready && b >= (long)A.in_ready_first) {
+                  // streaming host entry: this trajectory's inputs may still be in flight (the copies were queued before
+                  // the kernel; the bound below only keeps a failed copy from hanging the device)
+                  const volatile int* f = A.in_ready + (b - (long)A.in_ready_first) / A.in_ready_block;
+                  const long long t0 = clock64();
+                  while (*f == 0 && clock64() - t0 < 4000000000LL) { }
+                  __threadfence();
+                }
                 lane_bind(ln, A, t_shared, s, b);
                 ln.t = (double)ln.in.t_obs[0];
                 t_bound = (double)ln.in.t_obs[T - 1];
@@ -562,7 +570,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
                   if (T < 2) lane_finish(ln, A, vi_n);
                 } else {
                   if (clip && T <= 64 && any_series(ln.in))
-                    kink_mask = A.kink_masks ? A.kink_masks[ln.b] : build_kink_mask(ln.in);
+                    kink_mask = (A.kink_masks && !(A.in_ready && ln.b >= (long)A.in_ready_first)) ? A.kink_masks[ln.b]
+                                                                                                   : build_kink_mask(ln.in);
                   // the two evaluations of select_initial_step (at t0 and t0 + h0) read the inputs through the
                   // cached piece: load the first grid interval now (the first real attempt reloads it)
                   if (ln.cached && any_series(ln.in) && T >= 2) lane_cache_inputs(ln, 0);
@@ -916,7 +925,12 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
     unsigned long long* masks = reinterpret_cast<unsigned long long*>(
         reinterpret_cast<char*>(queue) + (((size_t)A.S * sizeof(int) + 255) & ~(size_t)255));
     count_launch();
-    kink_mask_kernel<<<(unsigned)((A.B + 7) / 8), 256, 0, stream>>>(A, masks);
+    // (streaming host entry: only the first in_ready_first trajectories are resident yet; the others build their mask
+    // when they are bound)
+    const long n_masks = A.in_ready ? (long)A.in_ready_first : (long)A.B;
+    RolloutArgs Am = A;
+    Am.B = (int32_t)n_masks;
+    kink_mask_kernel<<<(unsigned)((n_masks + 7) / 8), 256, 0, stream>>>(Am, masks);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     A.kink_masks = masks;

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HODE_ABI_VERSION 3
+#define HODE_ABI_VERSION 4
 #define HODE_N_STATE 6
 #define HODE_N_THETA 17
 #define HODE_NN_IN 9
@@ -186,6 +186,11 @@ int hode_rollout_fwd(const hode_cfg* cfg, const float* y0, const float* t_obs,
  *   out_state_mask  hode_rollout_fwd_host only: bit i set = state column i is copied back to the host; traj_host is
  *                   then [B,T,popcount(mask)] (0 = all six columns).  The loss of the reference consumes all columns,
  *                   but its figures and metrics read glucose-centric ones (plots/plot_all.py:183-187).
+ *   prev_counters   hode_rollout_fwd_host(_ex) only: HOST pointer to the [2,B] attempt counters a previous call returned
+ *                   for this cohort (counters_host of that call; it may be the very buffer this call writes), or NULL.
+ *                   The library derives the launch order from them on the device: longest first within blocks of
+ *                   32 768 trajectories, blocks in index order — the tail of the launch disappears as with `order`, and
+ *                   result blocks still complete (and travel back) progressively.  A scheduling hint only.
  */
 typedef struct hode_fwd_opts {
   int32_t struct_bytes;    /* = sizeof(hode_fwd_opts); checked */
@@ -193,6 +198,7 @@ typedef struct hode_fwd_opts {
   const int32_t* order;
   uint32_t out_state_mask;
   uint32_t reserved;
+  const int32_t* prev_counters;
 } hode_fwd_opts;
 
 /* hode_rollout_fwd with options (opts == NULL: identical to hode_rollout_fwd). */
@@ -383,7 +389,8 @@ int hode_rollout_fwd_host(const hode_cfg* cfg, const float* y0_host, const float
                           void* stream);
 
 /* hode_rollout_fwd_host with options: opts->out_state_mask selects the state columns copied back (traj_host is
- * [B,T,popcount(mask)]); theta_per_traj as in hode_rollout_fwd_ex (theta_host is then [B,17]); order is ignored. */
+ * [B,T,popcount(mask)]); theta_per_traj as in hode_rollout_fwd_ex (theta_host is then [B,17]); prev_counters gives the
+ * launch-order hint of a cohort integrated before; order is ignored. */
 int hode_rollout_fwd_host_ex(const hode_cfg* cfg, const hode_fwd_opts* opts, const float* y0_host,
                              const float* t_obs_host, const float* u_meal_host, const float* u_tvns_host,
                              const float* u_gd_host, const float* theta_host, const float* W_host,

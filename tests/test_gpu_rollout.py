@@ -263,6 +263,37 @@ def test_host_entry_chunked_pipeline(dev, oracle, per_row_t, precision):
     assert np.array_equal(counters[0], na) and np.array_equal(counters[1], nr)
 
 
+def test_host_entry_streams_inputs_behind_the_kernel(dev, oracle):
+    """Host entry at a size where the inputs of trajectories >= 65 536 are copied in blocks BEHIND the running kernel
+    (ready flags in device memory, hode_api.cu IN_FIRST / IN_BLOCK): adaptive solver with kink clipping (the kink
+    masks of the late blocks are built at bind time), series inputs, default tensor-core mode, ragged last block —
+    bit-identical to the device-pointer path."""
+    from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, ops
+    B, T = 65536 + 3 * 32768 + 777, 21
+    y0, t, ins = cohort(B, T, seed=17, horizon=2.0)
+    W = random_mlp(seed=18, out_std=0.05)
+    theta = oracle.THETA_DEFAULT
+    ref, st_ref, na, nr = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", precision="auto")
+    cfg, _ = ops.prepare(torch.from_numpy(y0), torch.from_numpy(t),
+                         {k: torch.from_numpy(v) for k, v in ins.items()},
+                         torch.from_numpy(theta), torch.from_numpy(W), 64, 4, torch.device("cpu"))
+    cfg.solver, cfg.kink_mode, cfg.mlp = _lib.SOLVER_DOPRI5, _lib.KINK_CLIP, ops.PRECISIONS[ops.default_precision(64, 4)]
+    traj = np.empty((B, T, 6), np.float32)
+    status = np.full(B, -1, np.int32)
+    counters = np.full((2, B), -1, np.int32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    for it in range(3):   # (later calls reuse the pooled staging buffer: stale flags / lines would show here)
+        traj.fill(np.nan)
+        # from the second call on: the previous call's counters as the launch-order hint (the very buffer the call
+        # writes) — a scheduling hint, the results must not move
+        opts = _lib.new_fwd_opts(prev_counters_ptr=counters.ctypes.data if it else None)
+        rc = _lib.lib().hode_rollout_fwd_host_ex(ctypes.byref(cfg), ctypes.byref(opts), p(y0), p(t), p(ins["meal"]),
+                                                 p(ins["tVNS"]), None, p(theta), p(W), p(traj), p(status), p(counters), None)
+        _lib.check(rc, "hode_rollout_fwd_host_ex")
+        assert np.array_equal(traj, ref) and np.array_equal(status, st_ref)
+        assert np.array_equal(counters[0], na) and np.array_equal(counters[1], nr)
+
+
 def test_full_size_properties_config2(dev, oracle):
     """BASELINE config 2 at full size (1 048 576 trajectories, RK4): size-independent
     properties + an oracle check on a strided subsample."""

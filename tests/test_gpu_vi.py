@@ -140,10 +140,18 @@ def test_config4_at_size_against_a_strided_oracle_subsample(dev, oracle):
     d_y0, d_t, d_ins, d_th, d_W = tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(theta), tt(W)
     mean, std, info = ops.vi_predictive(d_y0, d_t, d_ins, d_th, d_W, device=dev)
     assert mean.shape == (B, T, 6) and std.shape == (B, T, 6)
-    # solver failures are per-unit status codes (their rows enter the statistics zero-padded, as the reference stacks
-    # them: test_fused_edge_cases); at this size a handful of the 67 M units may fail — they must stay a handful
-    n_fail = int((info.status != 0).sum())
-    assert n_fail <= 1e-5 * S * B, torch.bincount(info.status.reshape(-1), minlength=5).tolist()
+    # Solver failures are per-unit status codes (their rows enter the statistics zero-padded, as the reference stacks
+    # them: test_fused_edge_cases).  With these perturbed random networks 0.3 % of the 67 M units run into a
+    # singularity of the model ("required step size is less than spacing between numbers", SciPy's message): the
+    # oracle must fail on the same units.
+    hist = torch.bincount(info.status.reshape(-1), minlength=5).tolist()
+    assert hist[2] == 0 and hist[3] == 0 and hist[4] == 0, hist          # only OK / STEP_TOO_SMALL
+    assert hist[1] <= 0.01 * S * B, hist
+    fs, fb = [v.cpu().numpy() for v in torch.nonzero(info.status[:, : 1 << 14])[:5].unbind(dim=1)]
+    for s_, b_ in zip(fs, fb):
+        one = np.array([b_])
+        _, ost, _, _ = oracle.rollout(y0[one], t, {k: v[one] for k, v in ins.items()}, theta[s_], W[s_], kinks="clip")
+        assert int(ost[0]) == 1, (int(s_), int(b_), ost)
     attempts = int(info.n_accept.sum()) + int(info.n_reject.sum())
     assert 30 * S * B < attempts < 60 * S * B   # the cohort's 43.5 attempts per trajectory, per set
     assert bool(torch.isfinite(mean).all()) and bool(torch.isfinite(std).all())
