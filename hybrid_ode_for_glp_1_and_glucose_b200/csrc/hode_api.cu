@@ -5,6 +5,7 @@
 // allocator for its staging buffers), no CPU fallback: a configuration the CUDA kernels do
 // not cover returns HODE_E_UNSUPPORTED.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -529,8 +530,18 @@ void tune_default_pool() {
 // with the device->host copy of the results overlapped block by block: the kernel counts finished
 // trajectories per block of STREAM_BLOCK and raises a flag in host-mapped memory when a block is
 // complete; this thread polls the flags and queues that block's copy on a second stream.
-constexpr int STREAM_BLOCK = 8192;
 constexpr int STREAM_MAX_BLOCKS = 1024;
+// trajectories per result block (HODE_STREAM_BLOCK overrides it: measurement knob)
+static int stream_block() {
+  static int v = 0;
+  if (!v) {
+    const char* s = getenv("HODE_STREAM_BLOCK");
+    int x = s ? atoi(s) : 0;
+    v = (x >= 256 && x <= (1 << 20)) ? x : 8192;
+  }
+  return v;
+}
+#define STREAM_BLOCK (stream_block())
 // ... and the host->device copy of the inputs overlapped the other way round: the kernel starts as soon as the first
 // IN_FIRST trajectories (more than one wave of lanes: 148 SMs x 384) are resident; the rest follows in blocks of
 // IN_BLOCK on a second copy stream, each block followed by a 4-byte copy that raises its ready flag in device memory;
@@ -682,24 +693,29 @@ int rollout_fwd_host_streamed(const hode_cfg* cfg, const hode_fwd_opts* opts, co
     cudaEvent_t ev_kernel;
     CK(cudaEventCreateWithFlags(&ev_kernel, cudaEventDisableTiming));
     e = cudaEventRecord(ev_kernel, st);
-    while (e == cudaSuccess && copied < n_blk) {
-      if (vf[copied]) {
-        const size_t lo = (size_t)copied * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
+    // blocks complete out of order (a block is as late as its longest trajectory): every sweep over the flags queues the
+    // copies of all blocks that have completed since the last one; flags_h[i] = 2 marks "copy queued"
+    const size_t blk = (size_t)STREAM_BLOCK;
+    bool kernel_over = false;
+    while (e == cudaSuccess && copied < n_blk && !kernel_over) {
+      kernel_over = cudaEventQuery(ev_kernel) != cudaErrorNotReady;   // (checked BEFORE the sweep: flags raised by then are seen)
+      for (int i = 0; i < n_blk && e == cudaSuccess; ++i) {
+        if (vf[i] != 1) continue;
+        const size_t lo = (size_t)i * blk, hi = lo + blk < B ? lo + blk : B;
         e = cudaMemcpyAsync(traj_h + lo * T * nc, d + o_traj + lo * T * nc * 4, (hi - lo) * T * nc * 4, cudaMemcpyDeviceToHost,
                             copy_stream);
+        vf[i] = 2;
         ++copied;
-      } else if (cudaEventQuery(ev_kernel) != cudaErrorNotReady) {
-        // the kernel is over (normally every flag is up by now; on a launch failure none is):
-        // fall through to the plain copies below
-        break;
       }
     }
     cudaEventDestroy(ev_kernel);
     if (e != cudaSuccess) goto done;
   }
   CK(cudaStreamSynchronize(st));
-  for (; copied < n_blk; ++copied) {
-    const size_t lo = (size_t)copied * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
+  // whatever is left (normally nothing; everything after a launch failure)
+  for (int i = 0; i < n_blk; ++i) {
+    if (flags_h[i] == 2) continue;
+    const size_t lo = (size_t)i * STREAM_BLOCK, hi = lo + STREAM_BLOCK < B ? lo + STREAM_BLOCK : B;
     CK(cudaMemcpyAsync(traj_h + lo * T * nc, d + o_traj + lo * T * nc * 4, (hi - lo) * T * nc * 4, cudaMemcpyDeviceToHost,
                        copy_stream));
   }
