@@ -26,7 +26,8 @@ def _sets(S, seed=0, spread=0.02):
 
 @pytest.mark.parametrize("precision,solver,B", [("fp32", "dopri5", 300), ("tf32x3", "dopri5", 700),
                                                 ("fp32", "rk4", 130), ("tf32x3", "rk4", 300),
-                                                ("tf32x2bf16", "dopri5", 900), ("tf32x2bf16", "rk4", 300)])
+                                                ("tf32x2bf16", "dopri5", 900), ("tf32x2bf16", "rk4", 300),
+                                                ("f16bf16x2", "dopri5", 900), ("f16bf16x2", "rk4", 300)])
 def test_fused_mean_std_equals_stack_statistics(dev, precision, solver, B):
     from hybrid_ode_for_glp_1_and_glucose_b200 import ops
     S, T = 7, 21
@@ -153,7 +154,9 @@ def test_config4_at_size_against_a_strided_oracle_subsample(dev, oracle):
         _, ost, _, _ = oracle.rollout(y0[one], t, {k: v[one] for k, v in ins.items()}, theta[s_], W[s_], kinks="clip")
         assert int(ost[0]) == 1, (int(s_), int(b_), ost)
     attempts = int(info.n_accept.sum()) + int(info.n_reject.sum())
-    assert 30 * S * B < attempts < 60 * S * B   # the cohort's 43.5 attempts per trajectory, per set
+    # (28.6 attempts per unit on this cohort with these 64 perturbed networks — the bench cohort's network needs 43.5;
+    # the exact per-unit counts are compared against plain rollouts below)
+    assert 20 * S * B < attempts < 60 * S * B
     assert bool(torch.isfinite(mean).all()) and bool(torch.isfinite(std).all())
     ok_traj = torch.nonzero((info.status == 0).all(dim=0)).reshape(-1).cpu().numpy()
     sub = ok_traj[np.searchsorted(ok_traj, np.arange(16) * (B // 16) + 4099)]   # strided, every set solved

@@ -13,7 +13,7 @@ W = random_mlp(64, 4, seed=1234, out_std=0.05)
 tt = lambda a: torch.from_numpy(a).to(dev)
 a = (tt(y0), tt(t), {k: tt(v) for k, v in ins.items()}, tt(THETA_DEFAULT), tt(W))
 g = torch.full((B, 61, 6), 1.0 / (B * 366), device=dev)
-kw = dict(solver="dopri5", precision="tf32x3", device=dev)
+kw = dict(solver="dopri5", precision=(sys.argv[2] if len(sys.argv) > 2 else "auto"), device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 tf = tb = tp = 0.0
 n = 20
