@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="hybrid_fwd",
                     choices=["hybrid_fwd", "hybrid_fwdbwd", "vi_predictive", "mech_rk4"])
     ap.add_argument("--traj-per-gpu", type=int, default=0)
-    ap.add_argument("--precision", default="tf32x2bf16", choices=["fp32", "tf32x3", "tf32", "tf32bf16", "tf32x2bf16"])
+    ap.add_argument("--precision", default="f16bf16x2", choices=["fp32", "tf32x3", "tf32", "tf32bf16", "tf32x2bf16", "f16bf16x2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs of the default run")
     ap.add_argument("--arrival-order", action="store_true",
@@ -349,7 +349,7 @@ def run_ours(args):
     def vi_step(c, thS, WS):
         return lambda: ops.vi_predictive(c.y0, c.t, c.ins, thS, WS, **c.kw)
 
-    KMODE = {"tf32x3": "x3", "tf32x2bf16": "mix3", "tf32bf16": "mixed", "tf32": "tf32", "fp32": "fp32"}[args.precision]
+    KMODE = {"tf32x3": "x3", "tf32x2bf16": "mix3", "f16bf16x2": "h16", "tf32bf16": "mixed", "tf32": "tf32", "fp32": "fp32"}[args.precision]
     LAUNCH_ORDER_TEXT = ("longest first by the PREVIOUS pass's attempt counters (ops.launch_order: device-side argsort inside the "
                          "timed step); the first pass of a cohort runs in arrival order: roofline.legs.fwd_first_pass")
     peaks_box = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
@@ -696,9 +696,16 @@ def run_ours(args):
         if w["nn"] and args.precision != "fp32":
             kname = ("rollout_tc_kernel<" + KMODE + ",dopri5> (fused Welford mean/std)" if vi else
                      "rollout_tc_kernel<" + KMODE + ",dopri5>" + (" + rollout_bwd_tc_kernel" if bwd else ""))
-            passes = {"tf32x3": 3, "tf32bf16": 2, "tf32x2bf16": 2.5, "tf32": 1}[args.precision]
+            passes = {"tf32x3": 3, "tf32bf16": 2, "tf32x2bf16": 2.5, "f16bf16x2": 1.5, "tf32": 1}[args.precision]
             roof = tensor_roof(attempts_per_step, ms_step, 3.0 if bwd else 1.0, kname, passes)
             roof["peak_source"] = tensor_src
+            bf16_peak = peaks_box.get("bf16_tflops_sustained") or (peaks_r2.get("bf16") or {}).get("sustained_tflops")
+            if bf16_peak:
+                # the same algorithmic rate against the box's dense BF16 figure (MEASURED_PEAKS.json): the f16bf16x2 mode
+                # issues kind::f16 MMAs (3 FP16/BF16 passes per float32 product), so both denominators are shown
+                roof["frac_of_bf16_peak"] = roof["achieved"] / float(bf16_peak)
+                roof["bf16_peak"] = float(bf16_peak)
+                roof["issued_frac_of_bf16_peak"] = roof["achieved"] * passes * 2.0 / float(bf16_peak) if args.precision == "f16bf16x2" else None
             key = f"{args.workload}:{B}:{args.precision}"
             roof["traffic"] = traffic_db.get(key, {}).get("dram_bytes")
             roof["traffic_source"] = traffic_db.get(key, {}).get("source")

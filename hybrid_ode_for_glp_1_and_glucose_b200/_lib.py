@@ -16,7 +16,7 @@ ABI_VERSION = 4
 N_STATE, N_THETA, NN_IN = 6, 17, 9
 SOLVER_RK4, SOLVER_DOPRI5, SOLVER_DOP853 = 0, 1, 2
 IN_ABSENT, IN_CONST, IN_SERIES = 0, 1, 2
-MLP_NONE, MLP_FP32, MLP_TF32X3, MLP_TF32, MLP_TF32BF16, MLP_TF32X2BF16 = 0, 1, 2, 3, 4, 5
+MLP_NONE, MLP_FP32, MLP_TF32X3, MLP_TF32, MLP_TF32BF16, MLP_TF32X2BF16, MLP_F16BF16X2 = 0, 1, 2, 3, 4, 5, 6
 KINK_SCIPY, KINK_CLIP = 0, 1
 ST_OK, ST_STEP_TOO_SMALL, ST_MAX_STEPS, ST_NONFINITE, ST_REC_OVERFLOW = 0, 1, 2, 3, 4
 

@@ -43,7 +43,7 @@ struct Workspace {
 
 bool uses_tensor_cores(const hode_cfg* c) {
   return c->mlp == HODE_MLP_TF32X3 || c->mlp == HODE_MLP_TF32 || c->mlp == HODE_MLP_TF32BF16 ||
-         c->mlp == HODE_MLP_TF32X2BF16;
+         c->mlp == HODE_MLP_TF32X2BF16 || c->mlp == HODE_MLP_F16BF16X2;
 }
 
 int max_saved_steps(const hode_cfg* c) {
@@ -102,7 +102,7 @@ int validate(const hode_cfg* c) {
     if (c->save_steps)
       return fail(HODE_E_UNSUPPORTED, "HODE_SOLVER_DOP853 is forward only (no step records / adjoint)");
   }
-  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_TF32X2BF16)
+  if (c->mlp < HODE_MLP_NONE || c->mlp > HODE_MLP_F16BF16X2)
     return fail(HODE_E_UNSUPPORTED, "unknown mlp arithmetic");
   if (c->mlp != HODE_MLP_NONE) {
     if (c->nn_hidden < 1 || c->nn_hidden > HODE_MAX_HIDDEN || c->nn_layers < 1 ||
@@ -116,8 +116,8 @@ int validate(const hode_cfg* c) {
     if (uses_tensor_cores(c) && (c->nn_hidden != 64 || c->nn_layers > 5))
       return fail(HODE_E_UNSUPPORTED, "tensor-core MLP requires nn_hidden == 64 and nn_layers <= 5 (the weight image of "
                                       "deeper networks and the stage store do not fit the 227 KB of shared memory)");
-    if (c->mlp == HODE_MLP_TF32X2BF16 && c->nn_layers > 4)
-      return fail(HODE_E_UNSUPPORTED, "HODE_MLP_TF32X2BF16 (three tiles per SM) requires nn_layers <= 4");
+    if ((c->mlp == HODE_MLP_TF32X2BF16 || c->mlp == HODE_MLP_F16BF16X2) && c->nn_layers > 4)
+      return fail(HODE_E_UNSUPPORTED, "HODE_MLP_TF32X2BF16 / HODE_MLP_F16BF16X2 (three tiles per SM) require nn_layers <= 4");
   }
   if (c->solver != HODE_SOLVER_RK4 && (!(c->rtol > 0) || !(c->atol >= 0)))
     return fail(HODE_E_SIZE, "rtol must be > 0 and atol >= 0");

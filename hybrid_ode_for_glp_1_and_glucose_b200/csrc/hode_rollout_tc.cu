@@ -34,8 +34,9 @@ namespace hode {
 namespace {
 // MLP_MIX3: three tiles of 128 trajectories per CTA and no helper warps (384 threads x 168 registers; 3 x 160 + 8 TMEM
 // columns); the other modes: two tiles, each with a helper warpgroup (512 threads, setmaxnreg 200 / 56).
-template <int MODE> constexpr int tiles_per_cta() { return MODE == MLP_MIX3 ? 3 : 2; }
-template <int MODE> constexpr bool has_helpers() { return MODE != MLP_MIX3; }
+// MLP_H16: the same shape and TMEM footprint.
+template <int MODE> constexpr int tiles_per_cta() { return three_tiles<MODE>() ? 3 : 2; }
+template <int MODE> constexpr bool has_helpers() { return !three_tiles<MODE>(); }
 template <int MODE> constexpr int cta_threads() { return tiles_per_cta<MODE>() * TILE * (has_helpers<MODE>() ? 2 : 1); }
 constexpr int N_KSTAGE = 7 * NS;   // floats of the stage-derivative store per trajectory (k1..k7)
 }  // namespace
@@ -58,12 +59,15 @@ static int tc_image_floats_max(int L) {   // the workspace layout does not depen
   return a > b ? a : b;
 }
 int tc_image_floats_mode(int L, int mlp_mode) {
+  if (mlp_mode == HODE_MLP_F16BF16X2)
+    return (int)(img_l0<MLP_H16>() + (uint32_t)(L - 1) * img_hid<MLP_H16>() + img_out<MLP_H16>()) + L * 512 + 128;
   if (mlp_mode != HODE_MLP_TF32X2BF16) return tc_image_floats(L);
   return (int)(img_l0<MLP_MIX3>() + (uint32_t)(L - 1) * img_hid<MLP_MIX3>() + img_out<MLP_MIX3>()) + L * 512 + 128;
 }
 
 // mixed: 0 = 3xTF32 (second half B_lo), 1 = MLP_MIXED (second half bf16(B_hi), bf16(B_lo)),
-//        2 = MLP_MIX3 (B_lo, then bf16(B_hi): 2.5 parts per layer)
+//        2 = MLP_MIX3 (B_lo, then bf16(B_hi): 2.5 parts per layer),
+//        3 = MLP_H16 ([f16(W)][f16(64 (W - f16(W)))][bf16(f16(W))], 2-byte elements: 1.5 float-sized parts per layer)
 __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restrict__ img, int L, int P,
                                      int img_floats, int mixed) {
   const float* w = W + (size_t)blockIdx.x * P;
@@ -84,6 +88,12 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
     for (int i = threadIdx.x; i < n_out * n_cols; i += blockDim.x) {
       const int n = i / n_cols, k = i - n * n_cols;
       const float wv = (k < n_in) ? w[n * n_in + k] : w[n_out * n_in + n];
+      if (mixed == 3) {
+        uint16_t* h16 = reinterpret_cast<uint16_t*>(dst);
+        const int ob16 = ((k >> 3) * Npad + n) * 8 + (k & 7);
+        split_h16_weight(wv, h16[ob16], h16[part + ob16], h16[2 * part + ob16]);
+        continue;
+      }
       uint32_t hi, lo;
       tc::split_tf32(wv, hi, lo);
       const int o = ((k >> 2) * Npad + n) * 4 + (k & 3);
@@ -106,7 +116,7 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
       }
     }
     w += n_out * n_in + n_out;
-    dst += (mixed == 2) ? 2 * part + part / 2 : 2 * part;
+    dst += (mixed == 3) ? part + part / 2 : ((mixed == 2) ? 2 * part + part / 2 : 2 * part);
     bias_dst += (l == L) ? 128 : 512;
     n_in = n_out;
   }
@@ -115,7 +125,8 @@ __global__ void prep_tc_image_kernel(const float* __restrict__ W, float* __restr
 cudaError_t tc_prepare_fwd_images(const float* W, float* img, int S, int L, int P, int mlp_mode, cudaStream_t stream) {
   count_launch();
   prep_tc_image_kernel<<<S, 256, 0, stream>>>(W, img, L, P, tc_image_floats_mode(L, mlp_mode),
-                                              mlp_mode == HODE_MLP_TF32BF16 ? 1 : (mlp_mode == HODE_MLP_TF32X2BF16 ? 2 : 0));
+                                              mlp_mode == HODE_MLP_TF32BF16 ? 1 : (mlp_mode == HODE_MLP_TF32X2BF16 ? 2 :
+                                              (mlp_mode == HODE_MLP_F16BF16X2 ? 3 : 0)));
   return cudaGetLastError();
 }
 
@@ -393,8 +404,8 @@ rollout_tc_kernel(const RolloutArgs A, const float* __restrict__ img_g, int img_
   TileCtx c;
   c.img = img;
   c.mma_bar = &mma_bar[tile];
-  c.tmem = tmem_base_s + (uint32_t)tile * (X3 == MLP_MIX3 ? TM3_TILE_STRIDE : TM_TILE_STRIDE);
-  c.t_ones = (X3 == MLP_MIX3) ? tmem_base_s + TM3_ONES_ABS : c.tmem + TM_ONES;
+  c.tmem = tmem_base_s + (uint32_t)tile * tm_tile_stride<X3>();
+  c.t_ones = three_tiles<X3>() ? tmem_base_s + TM3_ONES_ABS : c.tmem + TM_ONES;
   c.lane_base = (uint32_t)(wq * 32) << 16;
   c.parity = 0;
   c.bar_id = 1 + tile;
@@ -940,7 +951,8 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const bool mix3 = mlp_mode == HODE_MLP_TF32X2BF16;
+  const bool h16 = mlp_mode == HODE_MLP_F16BF16X2;
+  const bool mix3 = mlp_mode == HODE_MLP_TF32X2BF16 || h16;   // the three-tile launch shape
   const int n_main = (mix3 ? tiles_per_cta<MLP_MIX3>() : tiles_per_cta<MLP_X3>()) * TILE;
   const int n_thr = mix3 ? cta_threads<MLP_MIX3>() : cta_threads<MLP_X3>();
   size_t smem = (size_t)(((img_floats + 3) & ~3) + N_KSTAGE * n_main) * sizeof(float);
@@ -961,6 +973,8 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
   const bool rk4 = A.solver == HODE_SOLVER_RK4;
   if (mlp_mode == HODE_MLP_TF32X3)
     e = rk4 ? launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_DOPRI5>);
+  else if (h16)
+    e = rk4 ? launch(rollout_tc_kernel<MLP_H16, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_H16, HODE_SOLVER_DOPRI5>);
   else if (mix3)
     e = rk4 ? launch(rollout_tc_kernel<MLP_MIX3, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_MIX3, HODE_SOLVER_DOPRI5>);
   else if (mlp_mode == HODE_MLP_TF32BF16)

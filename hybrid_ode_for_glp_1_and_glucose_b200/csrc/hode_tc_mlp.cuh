@@ -40,7 +40,23 @@ constexpr int H = 64;
 //              pass-equivalents; its A operand needs only 96 TMEM columns (no second copy of A_hi), so THREE
 //              tiles fit the 512 columns of an SM — the rollout's default (hode_rollout_tc.cu); at least as
 //              accurate as MLP_MIXED (the A_hi B_lo term is exact to TF32 instead of BF16)
-constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2, MLP_MIX3 = 3;
+//   MLP_H16    D = bf16(A_lo) bf16(B_hi) + f16(A_hi / 64) f16(64 B_lo) + f16(A_hi) f16(B_hi) with A_hi = fp16(a) (round to
+//              nearest, saturating at +-65504) and A_lo = a - A_hi, B likewise: THREE kind::f16 passes = 1.5
+//              pass-equivalents.  FP16 carries the same 11 significant bits as TF32, so the main term is as exact as a
+//              TF32 one at twice the rate.  The A_hi B_lo term runs in FP16 too, with the power-of-two scale moved from
+//              one operand to the other so that the remainder B_lo (<= 2^-11 |B|) sits in FP16's normal range: weights are
+//              then represented to 22 bits, as in MLP_MIX3.  (With bf16(A_hi) bf16(B_lo) instead, the 2^-20 rounding of
+//              B_lo acts like a fixed perturbation of the weights, because post-ReLU A_hi never changes sign: measured
+//              1.7e-5 instead of < 1e-5 on the parameter-sweep parity case; csrc/probe/f16_probe.cu mode 2.)
+//              A operand = 96 TMEM columns (f16(A_hi), f16(A_hi / 64), bf16(A_lo), two features per column), so three
+//              tiles fit like MLP_MIX3's; weights = 1.5 float-sized parts per layer.  (Mixed-format instructions —
+//              a_format != b_format in one kind::f16 descriptor — raise an illegal-instruction fault on B200.)
+//              Contract: float32-equivalent products while |activations|, |weights| <= 65504 (beyond that the hi part
+//              saturates and the remainder is carried with BF16's 8 bits); activations below 2^-8 and weight remainders
+//              below 2^-20 keep absolute precisions of 2^-19 / 2^-31 in the A_hi B_lo term (FP16 subnormals).
+constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2, MLP_MIX3 = 3, MLP_H16 = 4;
+// modes that run three tiles per CTA without helper warps
+template <int MODE> __host__ __device__ constexpr bool three_tiles() { return MODE == MLP_MIX3 || MODE == MLP_H16; }
 // TMEM columns of one tile:
 //   [0,64) accumulator D | [64,128) A_hi (TF32) | [192,200) constant [1,1,0..] (bias step) |
 //   MLP_X3:    [128,192) A_lo = A - A_hi (TF32)
@@ -48,6 +64,12 @@ constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2, MLP_MIX3 = 3;
 //   MLP_MIX3:  [128,160) bf16(A - A_hi); tile stride 160, ONE constant block for the whole CTA at column 480
 constexpr uint32_t TM_D0 = 0, TM_AHI = 64, TM_ALO = 128, TM_AHB = 128, TM_ALB = 160, TM_ONES = 192, TM_TILE_STRIDE = 256;
 constexpr uint32_t TM3_ALB = 128, TM3_TILE_STRIDE = 160, TM3_ONES_ABS = 480;
+//   MLP_H16:   [64,96) f16(A_hi), two features per column | [96,128) f16(A_hi / 64) | [128,160) bf16(A - A_hi); tile stride 160,
+//              constant block at 480 (the MLP_MIX3 map with a different A block)
+constexpr uint32_t TMH_A16 = 64, TMH_AHS = 96, TMH_ALB = 128, TMH_TILE_STRIDE = 160;
+template <int MODE> __host__ __device__ constexpr uint32_t tm_tile_stride() {
+  return MODE == MLP_MIX3 ? TM3_TILE_STRIDE : (MODE == MLP_H16 ? TMH_TILE_STRIDE : TM_TILE_STRIDE);
+}
 // float offsets inside the shared-memory weight image (prep_tc_image_kernel, hode_rollout_tc.cu):
 //   layer 0 (K = 16: 9 features, feature 9 = constant 1 whose weight column is the bias, zero padding):
 //     [B_hi tf32 1024][second half 1024]
@@ -57,12 +79,13 @@ constexpr uint32_t TM3_ALB = 128, TM3_TILE_STRIDE = 160, TM3_ONES_ABS = 480;
 //   bias blocks (one K = 8 TF32 step, columns 0/1 = hi/lo): L x 512 (block 0 unused) + 128
 //   MLP_MIX3: [B_hi tf32][B_lo tf32][bf16(B_hi)] = 2.5 x the floats of B_hi per layer
 constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
-template <int MODE> __host__ __device__ constexpr uint32_t img_l0() { return MODE == MLP_MIX3 ? 2560u : IMG_L0; }
-template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MODE == MLP_MIX3 ? 10240u : IMG_HID; }
+//   MLP_H16:  [f16(B)][f16(64 (B - f16(B)))][bf16(f16(B))], 2-byte elements = 1.5 x the floats of B_hi per layer
+template <int MODE> __host__ __device__ constexpr uint32_t img_l0() { return MODE == MLP_MIX3 ? 2560u : (MODE == MLP_H16 ? 1536u : IMG_L0); }
+template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MODE == MLP_MIX3 ? 10240u : (MODE == MLP_H16 ? 6144u : IMG_HID); }
 // (Measured dead end: the 64 -> 6 output layer of MLP_MIX3 on the CUDA cores — 384 FFMA per thread straight from the last
 // hidden accumulator, no N = 16 MMAs and one issue -> commit -> wake-up phase less — was 6 % SLOWER, 968 M against
 // 1 034 M trajectory-steps/s: the tile's chain is bound by its threads' instruction latency, not by the tensor phases.)
-template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : IMG_OUT; }
+template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : (MODE == MLP_H16 ? 1536u : IMG_OUT); }
 // What bounds MLP_MIX3 (round 2 measurements, tools/probe_sched.py + tools/timeline.py on 1 / 2 / 3 resident tiles):
 // the DP5(4) round of a tile takes 34.3 us whether the tile is alone on its SM or not, and the issue of a hidden
 // layer's 21 N = 64 MMAs takes 861 cycles alone (41 per MMA: tcgen05.mma issue is paced by execution, 32.5 cycles,
@@ -145,6 +168,10 @@ __device__ __forceinline__ void tile_sync_main(const TileCtx& c) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 instruction descriptor with separate operand formats (0 = F16, 1 = BF16), FP32 accumulation, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int fmt_a, int fmt_b, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt_a << 7) | ((uint32_t)fmt_b << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -209,10 +236,28 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32
     for (int ks = 0; ks < K / 8; ++ks)     // A_hi B_lo
       tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_2 + (uint32_t)ks * 2u * lbo16), idesc, 1u);
   }
+  if constexpr (MODE == MLP_H16) {
+    // b_hi = f16(B) (2-byte elements, K chunks of 8), then f16(64 (B - f16(B))) and bf16(f16(B)), K * N * 2 bytes each;
+    // one MMA contracts K = 16 = 8 TMEM columns of A and two 16-byte K chunks of B
+    constexpr uint32_t id_hh = make_idesc_f16(0, 0, TILE, N);
+    const uint32_t lo_los = lo_hi + ((uint32_t)(K * N * 2) >> 4), lo_hib = lo_los + ((uint32_t)(K * N * 2) >> 4);
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) {     // A_hi B_hi
-    tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, acc);
-    acc = 1u;
+    for (int ks = 0; ks < K / 16; ++ks) {  // bf16(A_lo) bf16(B_hi)
+      mma_bf16_ts(d, tmem + TMH_ALB + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hib + (uint32_t)ks * 2u * lbo16), idesc_b, acc);
+      acc = 1u;
+    }
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks)    // f16(A_hi / 64) f16(64 B_lo)
+      mma_bf16_ts(d, tmem + TMH_AHS + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_los + (uint32_t)ks * 2u * lbo16), id_hh, 1u);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks)    // f16(A_hi) f16(B_hi)
+      mma_bf16_ts(d, tmem + TMH_A16 + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), id_hh, 1u);
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ++ks) {     // A_hi B_hi
+      tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_hi + (uint32_t)ks * 2u * lbo16), idesc, acc);
+      acc = 1u;
+    }
   }
 }
 
@@ -286,6 +331,64 @@ __device__ __forceinline__ void epilogue16_mix3(uint32_t* v, uint32_t* lb) {
     lb[j >> 1] = pack_bf16x2(l0, l1);
   }
 }
+// MLP_H16: 16 accumulator columns -> 8 packed f16 pairs of a = relu(v) (round to nearest, saturating), the same scaled by
+// 2^-6, and 8 packed BF16 pairs of the remainder a - f16(a).  Per pair: 2 FMNMX, F2FP.F16, HMUL2, 2 HADD2.F32 (unpack), one
+// packed FADD2, F2FP.BF16.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // feature 2c in the low half
+  return r;
+}
+constexpr float H16_LO_SCALE = 64.f;   // 2^6: B_lo is stored as f16(64 B_lo), A_hi a second time as f16(A_hi / 64)
+__device__ __forceinline__ void split_h16_pair(float a0, float a1, uint32_t& h16, uint32_t& hs, uint32_t& lb) {
+  h16 = pack_f16x2_sat(a0, a1);
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hs) : "r"(h16), "r"(0x24002400u));   // x 2^-6 (exact unless subnormal)
+  float f0, f1;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f0), "=f"(f1) : "r"(h16));
+  uint64_t ap, hp, lp;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ap) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(hp) : "f"(f0), "f"(f1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(lp) : "l"(ap), "l"(hp));
+  float l0, l1;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(l0), "=f"(l1) : "l"(lp));
+  lb = pack_bf16x2(l0, l1);
+}
+// weight-side split of one element: f16(w), f16(64 (w - f16(w))), bf16(f16(w))
+__device__ __forceinline__ void split_h16_weight(float w, uint16_t& h16, uint16_t& los, uint16_t& hib) {
+  const uint32_t p = pack_f16x2_sat(w, 0.f);
+  float f0;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f0) : "r"(p));
+  h16 = (uint16_t)(p & 0xFFFFu);
+  los = (uint16_t)(pack_f16x2_sat((w - f0) * H16_LO_SCALE, 0.f) & 0xFFFFu);
+  hib = (uint16_t)(pack_bf16x2(f0, 0.f) & 0xFFFFu);
+}
+__device__ __forceinline__ void epilogue16_h16(const uint32_t* v, uint32_t* h16, uint32_t* hs, uint32_t* lb) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2)
+    split_h16_pair(fmaxf(__uint_as_float(v[j]), 0.f), fmaxf(__uint_as_float(v[j + 1]), 0.f), h16[j >> 1], hs[j >> 1], lb[j >> 1]);
+}
+// The hidden-layer epilogue of one MLP_H16 thread: all 64 accumulator columns of its lane, pipelined like MLP_MIX3's.
+__device__ __forceinline__ void epilogue64_h16(uint32_t t_lane) {
+  uint32_t c0[16], c1[16], c2[16], c3[16], h16[8], hs[8], lb[8];
+  HODE_TMEM_LD_X16(t_lane + TM_D0, c0);
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + 16, c1);
+  tc::wait_ld();
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + 32, c2);
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + 48, c3);
+#define HODE_H16_CHUNK(c, q)                          \
+  epilogue16_h16(c, h16, hs, lb);                     \
+  HODE_TMEM_ST_X8(t_lane + TMH_A16 + 8 * (q), h16);   \
+  HODE_TMEM_ST_X8(t_lane + TMH_AHS + 8 * (q), hs);    \
+  HODE_TMEM_ST_X8(t_lane + TMH_ALB + 8 * (q), lb)
+  HODE_H16_CHUNK(c0, 0);
+  HODE_H16_CHUNK(c1, 1);
+  tc::wait_ld();
+  HODE_H16_CHUNK(c2, 2);
+  HODE_H16_CHUNK(c3, 3);
+#undef HODE_H16_CHUNK
+  tc::wait_st();
+  tc::fence_before_sync();
+}
 // The hidden-layer epilogue of one MLP_MIX3 thread (no helper warps): all 64 accumulator columns of its lane.
 __device__ __forceinline__ void epilogue64_mix3(uint32_t t_lane) {
   // four 16-column chunks, software-pipelined: tcgen05.wait::ld drains every outstanding load, so the loads of the
@@ -344,6 +447,20 @@ __device__ __forceinline__ void epilogue32_to_tmem(uint32_t t_lane, uint32_t col
 // zero padding to K = 16
 template <int MODE>
 __device__ __forceinline__ void store_input_operand(uint32_t t_lane, const float* x) {
+  if constexpr (MODE == MLP_H16) {
+    uint32_t h16[8], hs[8], lb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float x0 = (2 * c < HODE_NN_IN) ? x[2 * c] : (2 * c == HODE_NN_IN ? 1.0f : 0.0f);
+      const float x1 = (2 * c + 1 < HODE_NN_IN) ? x[2 * c + 1] : (2 * c + 1 == HODE_NN_IN ? 1.0f : 0.0f);
+      split_h16_pair(x0, x1, h16[c], hs[c], lb[c]);
+    }
+    HODE_TMEM_ST_X8(t_lane + TMH_A16, h16);
+    HODE_TMEM_ST_X8(t_lane + TMH_AHS, hs);
+    HODE_TMEM_ST_X8(t_lane + TMH_ALB, lb);
+    tc::wait_st();
+    tc::fence_before_sync();
+  } else {
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -371,6 +488,7 @@ __device__ __forceinline__ void store_input_operand(uint32_t t_lane, const float
   }
   tc::wait_st();
   tc::fence_before_sync();
+  }
 }
 
 // The residual MLP for the 128 trajectories of a tile (reference models/nn_residual.py:136-146).
@@ -390,7 +508,7 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, F
   // call's last mbarrier phase, so the layer-0 commit below cannot flip the barrier a second time
   // under a helper that is still busy (it would then wait for a phase that has already passed)
   // (MLP_MIX3 has no helper warps: every barrier of the tile is over its 128 main threads)
-  if (X3 == MLP_MIX3) tile_sync_main(c); else tile_sync_all(c);
+  if (three_tiles<X3>()) tile_sync_main(c); else tile_sync_all(c);
   HODE_TL(2);
   if (c.wq == 0) {
     if (tc::elect_one()) {
@@ -413,8 +531,8 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, F
     HODE_TL(10 + 10 * l);
     // the main warp owns accumulator columns [0,32) of its 32 lanes, the helper warp of the same
     // lane quarter columns [32,64) (mlp_tile_helper): the epilogue latency per layer is halved
-    if (X3 == MLP_MIX3) {
-      epilogue64_mix3(t_lane);
+    if (three_tiles<X3>()) {
+      if (X3 == MLP_H16) epilogue64_h16(t_lane); else epilogue64_mix3(t_lane);
       HODE_TL(12 + 10 * l);
       tile_sync_main(c);
     } else {

@@ -24,17 +24,20 @@ SOLVERS = {
     "dop853": _lib.SOLVER_DOP853,
 }
 PRECISIONS = {"fp32": _lib.MLP_FP32, "tf32x3": _lib.MLP_TF32X3, "tf32": _lib.MLP_TF32, "tf32bf16": _lib.MLP_TF32BF16,
-              "tf32x2bf16": _lib.MLP_TF32X2BF16}
+              "tf32x2bf16": _lib.MLP_TF32X2BF16, "f16bf16x2": _lib.MLP_F16BF16X2}
 
 
 def default_precision(hidden: int, layers: int) -> str:
     """'auto' resolves to the tcgen05 kernels (split-precision passes, float32-equivalent accuracy) whenever
     the network has the shape both tensor-core kernels are compiled for (64 wide, <= 4 hidden layers: the
     reference's default, models/nn_residual.py:28-36), and to the FP32 CUDA-core kernels for any other shape.
-    The tensor-core default is 'tf32x2bf16' (three 128-trajectory tiles per SM; 1.0e-6 against the oracle on the
-    fixed-step parity cases, the same as 'tf32x3', which stays selectable — two tiles per SM, 15 % slower);
-    gradients of either are computed by the 3xTF32 adjoint.  precision='fp32' is the bit-conservative parity mode."""
-    return "tf32x2bf16" if hidden == 64 and 1 <= layers <= 4 else "fp32"
+    The tensor-core default is 'f16bf16x2' (three 128-trajectory tiles per SM; hi parts in FP16, remainders in BF16 /
+    scaled FP16: three kind::f16 passes = 1.5 TF32-pass equivalents; 0.8e-6 against the oracle on the fixed-step parity
+    cases — 'tf32x2bf16' 1.0-1.2e-6, 'tf32x3' 1.0e-6, both selectable: 14 % / 27 % slower).  Its products are
+    float32-equivalent while |activations| and |weights| stay below FP16's 65504 (include/hode.h HODE_MLP_F16BF16X2);
+    a network that leaves that range should ask for 'tf32x2bf16'.  Gradients of every tensor-core mode are computed by
+    the 3xTF32 adjoint.  precision='fp32' is the bit-conservative parity mode."""
+    return "f16bf16x2" if hidden == 64 and 1 <= layers <= 4 else "fp32"
 
 
 def _mlp_mode(precision: str, hidden: int, layers: int) -> int:

@@ -69,10 +69,15 @@ enum {
   HODE_MLP_TF32 = 3,   /* tcgen05 tensor cores, single TF32 pass (fast, ~1e-3 on residual)   */
   HODE_MLP_TF32BF16 = 4, /* tcgen05: one TF32 pass + two BF16 cross-term passes (2 pass-equivalents; max
                             error 4.5e-7 of sum|ab| per product against 1.7e-7 for TF32X3: opt-in)   */
-  HODE_MLP_TF32X2BF16 = 5 /* tcgen05: A_hi*B_hi and A_hi*B_lo in TF32, A_lo*B_hi in BF16 (2.5 pass-equivalents,
+  HODE_MLP_TF32X2BF16 = 5, /* tcgen05: A_hi*B_hi and A_hi*B_lo in TF32, A_lo*B_hi in BF16 (2.5 pass-equivalents,
                              error <= TF32BF16's).  Its TMEM footprint lets the rollout run THREE 128-trajectory
                              tiles per SM instead of two: the fastest float32-equivalent mode (nn_layers <= 4).
                              Gradients of a rollout made in this mode are computed with the TF32X3 adjoint. */
+  HODE_MLP_F16BF16X2 = 6  /* tcgen05: hi parts in FP16 (11 significant bits, like TF32), remainders in BF16; three
+                             kind::f16 passes f16(A_hi)*f16(B_hi) + f16(A_hi/64)*f16(64 B_lo) + bf16(A_lo)*bf16(B_hi) = 1.5
+                             pass-equivalents, three tiles per SM (nn_layers <= 4).  Float32-equivalent products while
+                             |activations| and |weights| stay below 65504 (FP16's range; the hi part saturates beyond
+                             it and precision falls to BF16's).  Gradients: TF32X3 adjoint, as above. */
 };
 
 /*

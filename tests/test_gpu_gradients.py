@@ -261,7 +261,7 @@ def test_differentiable_forward_trains_the_data_term(dev):
 
 
 # ---------------------------------------------------------------------------- tensor-core adjoint
-@pytest.mark.parametrize("precision", ["tf32x3", "tf32x2bf16"])
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32x2bf16", "f16bf16x2"])
 @pytest.mark.parametrize("solver,layers", [("rk4", 4), ("dopri5", 4), ("rk4", 2), ("dopri5", 1)])
 def test_tensor_core_adjoint_matches_autograd(dev, solver, layers, precision):
     """The tensor-core precisions route hode_rollout_bwd to the tcgen05 adjoint (hode_adjoint_tc.cu); a rollout made

@@ -355,7 +355,7 @@ def test_module_forward_contract(dev, caplog):
 
 
 # ---------------------------------------------------------------------------- tensor-core MLP path
-TC_MODES = ["tf32x3", "tf32x2bf16"]   # 2 tiles / SM + helper warps, 3 tiles / SM (the default)
+TC_MODES = ["tf32x3", "tf32x2bf16", "f16bf16x2"]   # 2 tiles / SM + helper warps; 3 tiles / SM: TF32+BF16 split, FP16+BF16 split
 
 
 @pytest.mark.parametrize("tc_mode", TC_MODES)
@@ -512,10 +512,10 @@ def test_config3_full_size_properties_hybrid(dev, oracle, tc_mode):
 
 def test_module_default_reaches_the_tensor_core_kernel(dev):
     """The drop-in class, constructed the way the reference's call sites construct it (64 x 4 network), must run the
-    tcgen05 rollout by default: its output is bit-identical to precision='tf32x2bf16' (the three-tile kernel) and not
+    tcgen05 rollout by default: its output is bit-identical to precision='f16bf16x2' (the three-tile FP16/BF16 kernel) and not
     to the FP32 kernels'.  Other network shapes default to the FP32 kernels."""
     from hybrid_ode_for_glp_1_and_glucose_b200 import HybridODENN, ops
-    assert ops.default_precision(64, 4) == "tf32x2bf16" and ops.default_precision(64, 1) == "tf32x2bf16"
+    assert ops.default_precision(64, 4) == "f16bf16x2" and ops.default_precision(64, 1) == "f16bf16x2"
     assert ops.default_precision(32, 3) == "fp32" and ops.default_precision(64, 5) == "fp32"
     y0, t, ins = cohort(300, seed=41)
     m = HybridODENN(device=dev)
@@ -526,7 +526,7 @@ def test_module_default_reaches_the_tensor_core_kernel(dev):
             p.copy_(0.05 * torch.randn_like(p))
     tin = {k: torch.from_numpy(v).to(dev) for k, v in ins.items()}
     a = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin)
-    b = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin, precision="tf32x2bf16")
+    b = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin, precision="f16bf16x2")
     c = m(torch.from_numpy(y0).to(dev), torch.from_numpy(t).to(dev), tin, precision="fp32")
     assert torch.equal(a, b)
     assert not torch.equal(a, c)

@@ -26,7 +26,8 @@ def _saltelli_like(P, seed=0):
 
 
 @pytest.mark.parametrize("precision,solver", [("tf32x3", "dopri5"), ("fp32", "dopri5"), ("tf32x3", "rk4"),
-                                              ("tf32x2bf16", "dopri5"), ("tf32x2bf16", "rk4")])
+                                              ("tf32x2bf16", "dopri5"), ("tf32x2bf16", "rk4"),
+                                              ("f16bf16x2", "dopri5"), ("f16bf16x2", "rk4")])
 def test_theta_per_trajectory_equals_the_parameter_set_sweep(dev, oracle, precision, solver):
     """theta [P,17] in per-trajectory mode == theta [P,17] as P parameter sets over ONE trajectory (the round-1 path,
     one 128-row tile per set on the tensor cores), bit for bit; and == the oracle on a few rows."""
