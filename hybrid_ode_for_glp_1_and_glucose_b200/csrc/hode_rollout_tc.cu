@@ -23,6 +23,7 @@
 // Trajectories are pulled lane by lane from a global queue, so a lane that finishes early
 // (adaptive steps diverge 5x between trajectories) is refilled instead of idling.
 #include <math.h>
+#include <stdlib.h>
 
 #include "hode_common.cuh"
 #include "hode_kernels.h"
@@ -952,7 +953,16 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool h16 = mlp_mode == HODE_MLP_F16BF16X2;
-  const bool mix3 = mlp_mode == HODE_MLP_TF32X2BF16 || h16;   // the three-tile launch shape
+  // HODE_MLP_F16BF16X2 has two launch shapes with bit-identical results: three tiles per SM (throughput) and two tiles
+  // with helper warps (a shorter round).  A cohort that fits two tiles per SM anyway runs the second one: small
+  // batches, config 3's 32 768-trajectory per-GPU shard.  HODE_H16_TILES=2|3 forces a shape (tests, measurements).
+  bool h16_2t = h16 && (long)A.B <= (long)sms * tiles_per_cta<MLP_H16_2T>() * TILE;
+  if (h16) {
+    const char* force = getenv("HODE_H16_TILES");
+    if (force && force[0] == '2') h16_2t = true;
+    if (force && force[0] == '3') h16_2t = false;
+  }
+  const bool mix3 = mlp_mode == HODE_MLP_TF32X2BF16 || (h16 && !h16_2t);   // the three-tile launch shape
   const int n_main = (mix3 ? tiles_per_cta<MLP_MIX3>() : tiles_per_cta<MLP_X3>()) * TILE;
   const int n_thr = mix3 ? cta_threads<MLP_MIX3>() : cta_threads<MLP_X3>();
   size_t smem = (size_t)(((img_floats + 3) & ~3) + N_KSTAGE * n_main) * sizeof(float);
@@ -973,6 +983,8 @@ cudaError_t launch_rollout_tc(const RolloutArgs& A_in, int mlp_mode, void* works
   const bool rk4 = A.solver == HODE_SOLVER_RK4;
   if (mlp_mode == HODE_MLP_TF32X3)
     e = rk4 ? launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_X3, HODE_SOLVER_DOPRI5>);
+  else if (h16_2t)
+    e = rk4 ? launch(rollout_tc_kernel<MLP_H16_2T, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_H16_2T, HODE_SOLVER_DOPRI5>);
   else if (h16)
     e = rk4 ? launch(rollout_tc_kernel<MLP_H16, HODE_SOLVER_RK4>) : launch(rollout_tc_kernel<MLP_H16, HODE_SOLVER_DOPRI5>);
   else if (mix3)

@@ -54,9 +54,13 @@ constexpr int H = 64;
 //              Contract: float32-equivalent products while |activations|, |weights| <= 65504 (beyond that the hi part
 //              saturates and the remainder is carried with BF16's 8 bits); activations below 2^-8 and weight remainders
 //              below 2^-20 keep absolute precisions of 2^-19 / 2^-31 in the A_hi B_lo term (FP16 subnormals).
-constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2, MLP_MIX3 = 3, MLP_H16 = 4;
+//   MLP_H16_2T the arithmetic of MLP_H16 (bit-identical results) in the two-tile shape with helper warps: every hidden-layer
+//              epilogue is split over two warps per lane quarter, which shortens the chain of a tile by ~18 %.  Used when the
+//              cohort fits two tiles per SM anyway (small batches / config 3's per-GPU shard): latency instead of occupancy.
+constexpr int MLP_TF32 = 0, MLP_X3 = 1, MLP_MIXED = 2, MLP_MIX3 = 3, MLP_H16 = 4, MLP_H16_2T = 5;
 // modes that run three tiles per CTA without helper warps
 template <int MODE> __host__ __device__ constexpr bool three_tiles() { return MODE == MLP_MIX3 || MODE == MLP_H16; }
+template <int MODE> __host__ __device__ constexpr bool is_h16() { return MODE == MLP_H16 || MODE == MLP_H16_2T; }
 // TMEM columns of one tile:
 //   [0,64) accumulator D | [64,128) A_hi (TF32) | [192,200) constant [1,1,0..] (bias step) |
 //   MLP_X3:    [128,192) A_lo = A - A_hi (TF32)
@@ -80,12 +84,12 @@ template <int MODE> __host__ __device__ constexpr uint32_t tm_tile_stride() {
 //   MLP_MIX3: [B_hi tf32][B_lo tf32][bf16(B_hi)] = 2.5 x the floats of B_hi per layer
 constexpr uint32_t IMG_L0 = 2048, IMG_HID = 8192, IMG_OUT = 2048;
 //   MLP_H16:  [f16(B)][f16(64 (B - f16(B)))][bf16(f16(B))], 2-byte elements = 1.5 x the floats of B_hi per layer
-template <int MODE> __host__ __device__ constexpr uint32_t img_l0() { return MODE == MLP_MIX3 ? 2560u : (MODE == MLP_H16 ? 1536u : IMG_L0); }
-template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MODE == MLP_MIX3 ? 10240u : (MODE == MLP_H16 ? 6144u : IMG_HID); }
+template <int MODE> __host__ __device__ constexpr uint32_t img_l0() { return MODE == MLP_MIX3 ? 2560u : (is_h16<MODE>() ? 1536u : IMG_L0); }
+template <int MODE> __host__ __device__ constexpr uint32_t img_hid() { return MODE == MLP_MIX3 ? 10240u : (is_h16<MODE>() ? 6144u : IMG_HID); }
 // (Measured dead end: the 64 -> 6 output layer of MLP_MIX3 on the CUDA cores — 384 FFMA per thread straight from the last
 // hidden accumulator, no N = 16 MMAs and one issue -> commit -> wake-up phase less — was 6 % SLOWER, 968 M against
 // 1 034 M trajectory-steps/s: the tile's chain is bound by its threads' instruction latency, not by the tensor phases.)
-template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : (MODE == MLP_H16 ? 1536u : IMG_OUT); }
+template <int MODE> __host__ __device__ constexpr uint32_t img_out() { return MODE == MLP_MIX3 ? 2560u : (is_h16<MODE>() ? 1536u : IMG_OUT); }
 // What bounds MLP_MIX3 (round 2 measurements, tools/probe_sched.py + tools/timeline.py on 1 / 2 / 3 resident tiles):
 // the DP5(4) round of a tile takes 34.3 us whether the tile is alone on its SM or not, and the issue of a hidden
 // layer's 21 N = 64 MMAs takes 861 cycles alone (41 per MMA: tcgen05.mma issue is paced by execution, 32.5 cycles,
@@ -236,7 +240,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_hi, uint32
     for (int ks = 0; ks < K / 8; ++ks)     // A_hi B_lo
       tc::mma_tf32_ts(d, ahi + ks * 8, ((uint64_t)desc_hi << 32) | (uint64_t)(lo_2 + (uint32_t)ks * 2u * lbo16), idesc, 1u);
   }
-  if constexpr (MODE == MLP_H16) {
+  if constexpr (is_h16<MODE>()) {
     // b_hi = f16(B) (2-byte elements, K chunks of 8), then f16(64 (B - f16(B))) and bf16(f16(B)), K * N * 2 bytes each;
     // one MMA contracts K = 16 = 8 TMEM columns of A and two 16-byte K chunks of B
     constexpr uint32_t id_hh = make_idesc_f16(0, 0, TILE, N);
@@ -416,6 +420,24 @@ __device__ __forceinline__ void epilogue64_mix3(uint32_t t_lane) {
   tc::fence_before_sync();
 }
 
+// MLP_H16_2T: 32 accumulator columns [col0, col0 + 32) of this thread's lane (main warp: col0 = 0, helper warp: 32)
+__device__ __forceinline__ void epilogue32_h16(uint32_t t_lane, uint32_t col0) {
+  uint32_t c0[16], c1[16], h16[8], hs[8], lb[8];
+  const uint32_t p0 = col0 >> 1;   // two features per operand column
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + col0, c0);
+  HODE_TMEM_LD_X16(t_lane + TM_D0 + col0 + 16, c1);
+  tc::wait_ld();
+  epilogue16_h16(c0, h16, hs, lb);
+  HODE_TMEM_ST_X8(t_lane + TMH_A16 + p0, h16);
+  HODE_TMEM_ST_X8(t_lane + TMH_AHS + p0, hs);
+  HODE_TMEM_ST_X8(t_lane + TMH_ALB + p0, lb);
+  epilogue16_h16(c1, h16, hs, lb);
+  HODE_TMEM_ST_X8(t_lane + TMH_A16 + p0 + 8, h16);
+  HODE_TMEM_ST_X8(t_lane + TMH_AHS + p0 + 8, hs);
+  HODE_TMEM_ST_X8(t_lane + TMH_ALB + p0 + 8, lb);
+  tc::wait_st();
+  tc::fence_before_sync();
+}
 // The hidden-layer epilogue of one thread: 32 accumulator columns [col0, col0 + 32) of its TMEM lane -> the next
 // layer's A operand.  v / lo keep a = v + lo for the adjoint's stash.  Ends with wait::st + fence: the caller
 // signals the MMA issuer next.  store = false: only v / lo are produced (the last hidden layer of the adjoint's
@@ -447,7 +469,7 @@ __device__ __forceinline__ void epilogue32_to_tmem(uint32_t t_lane, uint32_t col
 // zero padding to K = 16
 template <int MODE>
 __device__ __forceinline__ void store_input_operand(uint32_t t_lane, const float* x) {
-  if constexpr (MODE == MLP_H16) {
+  if constexpr (is_h16<MODE>()) {
     uint32_t h16[8], hs[8], lb[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -535,6 +557,10 @@ __device__ __forceinline__ void mlp_tile(TileCtx& c, const float* x, float* r, F
       if (X3 == MLP_H16) epilogue64_h16(t_lane); else epilogue64_mix3(t_lane);
       HODE_TL(12 + 10 * l);
       tile_sync_main(c);
+    } else if constexpr (X3 == MLP_H16_2T) {
+      epilogue32_h16(t_lane, 0u);
+      HODE_TL(12 + 10 * l);
+      tile_sync_all(c);
     } else {
       uint32_t v0[32], lo[32];
       epilogue32_to_tmem<X3>(t_lane, 0u, v0, lo);
@@ -580,8 +606,12 @@ __device__ __forceinline__ void mlp_tile_helper(TileCtx& c) {
     tc::mbar_wait(c.mma_bar, c.parity);
     c.parity ^= 1u;
     tc::fence_after_sync();
-    uint32_t v[32], lo[32];
-    epilogue32_to_tmem<X3>(t_lane, 32u, v, lo);
+    if constexpr (X3 == MLP_H16_2T) {
+      epilogue32_h16(t_lane, 32u);
+    } else {
+      uint32_t v[32], lo[32];
+      epilogue32_to_tmem<X3>(t_lane, 32u, v, lo);
+    }
     tile_sync_all(c);
   }
   // the output layer's phase: nothing to read, but the phase must be observed so that the next

@@ -510,6 +510,28 @@ def test_config3_full_size_properties_hybrid(dev, oracle, tc_mode):
     assert e_gpu < max(2.0 * e_ref, 2e-5), (e_gpu, e_ref)
 
 
+def test_default_mode_launch_shapes_are_bit_identical(dev, oracle, monkeypatch):
+    """'f16bf16x2' has two launch shapes: three 128-trajectory tiles per SM (cohorts larger than two tiles per SM) and two
+    tiles with helper warps (shorter round; picked for small cohorts).  Same arithmetic per trajectory -> identical bits,
+    attempt counts and statuses, whichever shape runs and whatever the tile composition."""
+    y0, t, ins = cohort(3000, seed=43)
+    W = random_mlp(seed=44, out_std=0.05)
+    theta = oracle.THETA_DEFAULT
+    out = {}
+    for shape in ("2", "3"):
+        monkeypatch.setenv("HODE_H16_TILES", shape)
+        for solver, kw in (("dopri5", {}), ("rk4", dict(n_substeps=2))):
+            out[shape, solver] = gpu_rollout(dev, y0, t, ins, theta, W, solver=solver, precision="f16bf16x2", **kw)
+    monkeypatch.delenv("HODE_H16_TILES")
+    auto = gpu_rollout(dev, y0, t, ins, theta, W, solver="dopri5", precision="f16bf16x2")
+    for solver in ("dopri5", "rk4"):
+        for a, b in zip(out["2", solver], out["3", solver]):
+            assert np.array_equal(a, b), solver
+    for a, b in zip(auto, out["2", "dopri5"]):
+        assert np.array_equal(a, b)
+    assert (out["3", "dopri5"][1] == 0).all()
+
+
 def test_module_default_reaches_the_tensor_core_kernel(dev):
     """The drop-in class, constructed the way the reference's call sites construct it (64 x 4 network), must run the
     tcgen05 rollout by default: its output is bit-identical to precision='f16bf16x2' (the three-tile FP16/BF16 kernel) and not
