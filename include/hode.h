@@ -77,7 +77,10 @@ enum {
                              kind::f16 passes f16(A_hi)*f16(B_hi) + f16(A_hi/64)*f16(64 B_lo) + bf16(A_lo)*bf16(B_hi) = 1.5
                              pass-equivalents, three tiles per SM (nn_layers <= 4).  Float32-equivalent products while
                              |activations| and |weights| stay below 65504 (FP16's range; the hi part saturates beyond
-                             it and precision falls to BF16's).  Gradients: TF32X3 adjoint, as above. */
+                             it and precision falls to BF16's).  Gradients: TF32X3 adjoint, as above.
+                             Two launch shapes with bit-identical results: three tiles per SM, or — when the cohort fits
+                             two tiles per SM anyway (n_traj <= 256 x SMs) — two tiles with helper warps (shorter round).
+                             The environment variable HODE_H16_TILES=2|3 forces one (tests and measurements). */
 };
 
 /*
