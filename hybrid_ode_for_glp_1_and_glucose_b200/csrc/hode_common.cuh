@@ -288,7 +288,11 @@ __device__ __forceinline__ void emit_row(const RolloutArgs& A, float* out, long 
   float* pm = A.vi_mean + ((size_t)b * A.T + ei) * NS;
   float* ps = A.vi_m2 + ((size_t)b * A.T + ei) * NS;
   float m[NS], q[NS];
+#ifdef HODE_DBG_VI_NO_RMW   // measurement build only (tools/build_variants.py): the update without its loads — wrong statistics
+  if (true) {
+#else
   if (vi_n == 1) {
+#endif
 #pragma unroll
     for (int i = 0; i < NS; ++i) { m[i] = y[i]; q[i] = 0.f; }
   } else {

@@ -9,7 +9,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from hybrid_ode_for_glp_1_and_glucose_b200 import ops
+from hybrid_ode_for_glp_1_and_glucose_b200 import _lib, ops
+if os.environ.get("HODE_LIB_PATH"):   # an experiment build from tools/build_variants.py
+    _lib.LIB_PATH = os.environ["HODE_LIB_PATH"]
+    print("library:", _lib.LIB_PATH)
 from hybrid_ode_for_glp_1_and_glucose_b200.synthetic import THETA_DEFAULT, cohort, random_mlp
 
 dev = torch.device("cuda:0")
