@@ -120,6 +120,17 @@ __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, in
   }
 }
 #define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+#elif defined(HODE_SPIN_WAIT)
+// measurement build (tools/build_variants.py): poll with test_wait instead of suspending in try_wait
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "HODE_SPIN_LOOP:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra HODE_SPIN_DONE;\n\t"
+      "bra HODE_SPIN_LOOP;\n\t"
+      "HODE_SPIN_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 #else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
