@@ -532,6 +532,32 @@ def test_default_mode_launch_shapes_are_bit_identical(dev, oracle, monkeypatch):
     assert (out["3", "dopri5"][1] == 0).all()
 
 
+def test_default_mode_outside_the_fp16_range_degrades_gracefully(dev, oracle):
+    """include/hode.h, HODE_MLP_F16BF16X2: products are float32-equivalent while |activations| <= 65504; beyond that the
+    FP16 hi part saturates and the remainder is carried with BF16's 8 bits — finite results of BF16-level accuracy, no
+    inf / NaN.  ReLU networks are positively homogeneous: layer 0 scaled by c and the output layer by 1 / c is (up to
+    the unscaled hidden biases) the same residual with hidden activations c times larger.  'tf32x2bf16' has TF32's
+    exponent range and must not notice."""
+    y0, t, ins = cohort(500, 13, seed=45, horizon=1.0)
+    W = random_mlp(seed=46, out_std=0.05).copy()
+    theta = oracle.THETA_DEFAULT
+    out0 = W.size - (6 * 64 + 6)
+    ref = {}
+    for c in (1.0, 3.0e4):
+        Wc = W.copy()
+        Wc[:640] *= c            # layer 0: weight [64,9] + bias [64]
+        Wc[out0:out0 + 6 * 64] /= c   # output weight [6,64] (its bias stays)
+        r32, st, _, _ = gpu_rollout(dev, y0, t, ins, theta, Wc, solver="rk4", n_substeps=2)            # FP32 CUDA cores
+        assert (st == 0).all() and np.isfinite(r32).all()
+        for prec in ("f16bf16x2", "tf32x2bf16"):
+            tr, st, _, _ = gpu_rollout(dev, y0, t, ins, theta, Wc, solver="rk4", n_substeps=2, precision=prec)
+            assert (st == 0).all() and np.isfinite(tr).all(), (c, prec)
+            ref[c, prec] = rel_err(tr, r32)
+    assert ref[1.0, "f16bf16x2"] < 1e-5 and ref[1.0, "tf32x2bf16"] < 1e-5, ref
+    assert ref[3.0e4, "tf32x2bf16"] < 1e-5, ref          # full exponent range
+    assert ref[3.0e4, "f16bf16x2"] < 2e-2, ref           # saturated hi part: BF16-level, finite
+
+
 def test_module_default_reaches_the_tensor_core_kernel(dev):
     """The drop-in class, constructed the way the reference's call sites construct it (64 x 4 network), must run the
     tcgen05 rollout by default: its output is bit-identical to precision='f16bf16x2' (the three-tile FP16/BF16 kernel) and not
