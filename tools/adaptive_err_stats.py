@@ -25,7 +25,7 @@ def run(name, B, seed, W, kinks, prec):
     eo = (np.abs(tr - orc.astype(np.float64)) / sc).max(axis=(1, 2))
     q = lambda v: f"p50 {np.percentile(v, 50):8.1f} p90 {np.percentile(v, 90):8.1f} p99 {np.percentile(v, 99):8.1f} max {v.max():8.1f}"
     print(f"{name:34s} gpu: {q(eg)} | oracle: {q(ec)} | gpu-vs-oracle: {q(eo)} | ratio p50 {np.median(eg)/np.median(ec):.2f} p90 {np.percentile(eg,90)/np.percentile(ec,90):.2f} max {eg.max()/ec.max():.2f}")
-for prec in ("fp32", "tf32x3"):
+for prec in (sys.argv[1:] or ("fp32", "tf32x3", "tf32x2bf16", "f16bf16x2")):
     for kinks in ("clip", "scipy"):
         run(f"hybrid {prec} {kinks} (seed 8)", 256, 8, random_mlp(seed=9, out_std=0.02), kinks, prec)
     run(f"hybrid {prec} clip out_std .05 (s0)", 256, 0, random_mlp(seed=1, out_std=0.05), "clip", prec)
